@@ -1,0 +1,1076 @@
+// acx mini-MPI implementation (see include/mpi.h for the rationale).
+//
+// Single node, N processes, one POSIX shm segment per job:
+//   [Header | per-rank blobs | shared scratch | N*N SPSC cell rings]
+// P2P: every ordered pair (src,dst) has a single-producer/single-consumer ring of
+// fixed-size cells. A message is a HDR cell followed by DATA cells streamed through
+// the ring (pipelined copy-in/copy-out, like the shm BTL/CH4 shm eager path). Device
+// buffers: small -> staged through the cells with cudaMemcpy; large -> CUDA-IPC
+// rendezvous (RTS cell carries the cudaIpcMemHandle, receiver issues cudaMemcpyAsync
+// from the mapped peer buffer on a private non-blocking stream, then FINs).
+// Matching: MPI (source, tag, comm) with wildcards, posted-receive and unexpected
+// queues, non-overtaking per pair. Progress is made only inside MPI calls (no helper
+// thread), under one global mutex (MPI_THREAD_MULTIPLE is honoured that way).
+//
+// All CUDA use is optional and resolved at run time (dlopen of libcudart) so the same
+// library serves GPU-less CI.
+#include <mpi.h>
+
+#include <atomic>
+#include <cerrno>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <list>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <signal.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <time.h>
+#include <unistd.h>
+
+namespace {
+
+// ---------------------------------------------------------------------------------
+// Optional CUDA runtime (dlopen) — only what a CUDA-aware intra-node MPI needs.
+// ---------------------------------------------------------------------------------
+struct CudaRt {
+    bool tried = false, ok = false;
+    void *h = nullptr;
+    int (*PointerGetAttributes)(void *attr, const void *ptr) = nullptr;
+    int (*Memcpy)(void *, const void *, size_t, int) = nullptr;
+    int (*MemcpyAsync)(void *, const void *, size_t, int, void *) = nullptr;
+    int (*StreamCreateWithFlags)(void **, unsigned) = nullptr;
+    int (*StreamSynchronize)(void *) = nullptr;
+    int (*StreamQuery)(void *) = nullptr;
+    int (*EventCreateWithFlags)(void **, unsigned) = nullptr;
+    int (*EventRecord)(void *, void *) = nullptr;
+    int (*EventQuery)(void *) = nullptr;
+    int (*EventDestroy)(void *) = nullptr;
+    int (*IpcGetMemHandle)(void *, void *) = nullptr;
+    int (*GetDeviceCount)(int *) = nullptr;
+    int (*GetLastError)() = nullptr;
+    int (*GetDevice)(int *) = nullptr;
+    void *stream = nullptr;
+};
+CudaRt g_cuda;
+
+struct IpcHandle { char b[64]; };
+typedef int (*IpcOpenFn)(void **, IpcHandle, unsigned);
+IpcOpenFn g_ipc_open = nullptr;
+typedef int (*MemGetAddressRangeFn)(unsigned long long *, size_t *, unsigned long long);
+
+// cudaPointerAttributes layout (CUDA 11+/12): {int type; int device; void* devicePointer; void* hostPointer;}
+struct PtrAttr { int type; int device; void *dptr; void *hptr; long pad[4]; };
+
+bool cuda_load() {
+    if (g_cuda.tried) return g_cuda.ok;
+    g_cuda.tried = true;
+    if (getenv("ACX_MPI_NO_CUDA")) return false;
+    const char *names[] = {"libcudart.so.12", "libcudart.so", "libcudart.so.13", nullptr};
+    for (int i = 0; names[i] && !g_cuda.h; i++) g_cuda.h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!g_cuda.h) return false;
+#define L(field, sym) *(void **)(&g_cuda.field) = dlsym(g_cuda.h, sym); if (!g_cuda.field) return false;
+    L(PointerGetAttributes, "cudaPointerGetAttributes")
+    L(Memcpy, "cudaMemcpy")
+    L(MemcpyAsync, "cudaMemcpyAsync")
+    L(StreamCreateWithFlags, "cudaStreamCreateWithFlags")
+    L(StreamSynchronize, "cudaStreamSynchronize")
+    L(StreamQuery, "cudaStreamQuery")
+    L(EventCreateWithFlags, "cudaEventCreateWithFlags")
+    L(EventRecord, "cudaEventRecord")
+    L(EventQuery, "cudaEventQuery")
+    L(EventDestroy, "cudaEventDestroy")
+    L(IpcGetMemHandle, "cudaIpcGetMemHandle")
+    L(GetDeviceCount, "cudaGetDeviceCount")
+    L(GetLastError, "cudaGetLastError")
+    L(GetDevice, "cudaGetDevice")
+#undef L
+    g_ipc_open = (IpcOpenFn)dlsym(g_cuda.h, "cudaIpcOpenMemHandle");
+    if (!g_ipc_open) return false;
+    int n = 0;
+    if (g_cuda.GetDeviceCount(&n) != 0 || n <= 0) { g_cuda.GetLastError(); return false; }
+    g_cuda.ok = true;
+    return true;
+}
+
+enum { kMemcpyDefault = 4 };
+
+// Returns true if p is device (or managed) memory the CPU must not touch directly.
+bool is_device_ptr(const void *p) {
+    if (!p || !cuda_load()) return false;
+    PtrAttr a;
+    memset(&a, 0, sizeof(a));
+    if (g_cuda.PointerGetAttributes(&a, p) != 0) { g_cuda.GetLastError(); return false; }
+    return a.type == 2 /*cudaMemoryTypeDevice*/;
+}
+
+void *cuda_stream() {
+    if (!g_cuda.stream) g_cuda.StreamCreateWithFlags(&g_cuda.stream, 1 /*NonBlocking*/);
+    return g_cuda.stream;
+}
+
+void die(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    fprintf(stderr, "[acx-mpi] fatal: ");
+    vfprintf(stderr, fmt, ap);
+    fprintf(stderr, "\n");
+    va_end(ap);
+    _exit(86);
+}
+
+// ---------------------------------------------------------------------------------
+// Shared segment layout
+// ---------------------------------------------------------------------------------
+constexpr uint32_t kMagic = 0xAC0B2001u;
+constexpr size_t kBlobBytes = 8192;         // per-rank exchange blob
+constexpr size_t kScratchBytes = 4u << 20;  // libacx control area (directories, registries)
+
+enum CellKind : uint32_t { CELL_HDR = 1, CELL_DATA = 2, CELL_RTS_IPC = 3, CELL_FIN = 4 };
+
+struct CellHdr {
+    uint32_t kind;
+    uint32_t len;       // payload bytes in this cell
+    int32_t tag;
+    int32_t comm;
+    int32_t part;       // partition index for partitioned traffic, -1 otherwise
+    uint32_t pad;
+    uint64_t total;     // message bytes (HDR / RTS)
+    uint64_t cookie;    // sender request cookie (RTS/FIN)
+};
+
+struct Ring {
+    alignas(64) std::atomic<uint64_t> head;  // producer cursor (cells written)
+    alignas(64) std::atomic<uint64_t> tail;  // consumer cursor (cells consumed)
+};
+
+struct Header {
+    std::atomic<uint32_t> magic;
+    uint32_t nranks;
+    uint32_t ncell;
+    uint32_t cell_bytes;  // payload bytes per cell
+    int32_t creator_pid;
+    std::atomic<int32_t> abort_code;
+    alignas(64) std::atomic<uint32_t> checkin;
+    alignas(64) std::atomic<uint32_t> bar_count;
+    alignas(64) std::atomic<uint32_t> bar_sense;
+    alignas(64) std::atomic<int32_t> pids[1024];
+};
+
+struct Seg {
+    Header *hdr = nullptr;
+    char *blobs = nullptr;
+    char *scratch = nullptr;
+    Ring *rings = nullptr;
+    char *cells = nullptr;
+    size_t bytes = 0;
+    size_t cell_stride = 0;
+    std::string name;
+};
+
+struct State {
+    bool initialized = false, finalized = false;
+    int rank = 0, size = 1;
+    int thread_level = MPI_THREAD_MULTIPLE;
+    std::string jobid;
+    Seg seg;
+    uint32_t my_sense = 0;
+    int next_comm = 16;
+    std::unordered_map<int, int> comm_ctx;  // dup'ed communicators -> context id
+};
+State g;
+std::recursive_mutex g_mu;
+
+inline Ring *ring_of(int src, int dst) { return &g.seg.rings[(size_t)src * g.size + dst]; }
+inline char *cell_of(int src, int dst, uint64_t idx) {
+    size_t r = (size_t)src * g.size + dst;
+    return g.seg.cells + (r * g.seg.hdr->ncell + (idx % g.seg.hdr->ncell)) * g.seg.cell_stride;
+}
+
+int env_int(const char *a, const char *b = nullptr, const char *c = nullptr, int dflt = -1) {
+    const char *names[] = {a, b, c};
+    for (const char *n : names) {
+        if (!n) continue;
+        const char *v = getenv(n);
+        if (v && *v) return atoi(v);
+    }
+    return dflt;
+}
+
+size_t seg_size(int n, uint32_t ncell, uint32_t cell_bytes, size_t *off_blobs, size_t *off_scratch,
+                size_t *off_rings, size_t *off_cells, size_t *stride) {
+    auto up = [](size_t x) { return (x + 4095) & ~(size_t)4095; };
+    size_t o = up(sizeof(Header));
+    *off_blobs = o;   o = up(o + kBlobBytes * n);
+    *off_scratch = o; o = up(o + kScratchBytes);
+    *off_rings = o;   o = up(o + sizeof(Ring) * n * n);
+    *off_cells = o;
+    *stride = (sizeof(CellHdr) + cell_bytes + 63) & ~(size_t)63;
+    o = up(o + (size_t)n * n * ncell * *stride);
+    return o;
+}
+
+void seg_attach() {
+    int n = g.size;
+    uint32_t ncell = (uint32_t)env_int("ACX_MPI_NCELL", nullptr, nullptr, n > 16 ? 8 : 32);
+    uint32_t cell_bytes = (uint32_t)env_int("ACX_MPI_CELL_BYTES", nullptr, nullptr, 16384);
+    size_t ob, os, orr, oc, stride;
+    size_t bytes = seg_size(n, ncell, cell_bytes, &ob, &os, &orr, &oc, &stride);
+    g.seg.name = "/acx_" + g.jobid;
+    int fd = -1;
+    if (n == 1 && !getenv("ACX_JOBID")) {
+        // Singleton: private anonymous mapping, no file.
+        void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+        if (p == MAP_FAILED) die("mmap singleton failed");
+        g.seg.hdr = (Header *)p;
+        g.seg.name.clear();
+    } else if (g.rank == 0) {
+        shm_unlink(g.seg.name.c_str());
+        fd = shm_open(g.seg.name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0) die("shm_open(create %s): %s", g.seg.name.c_str(), strerror(errno));
+        if (ftruncate(fd, (off_t)bytes) != 0) die("ftruncate(%zu): %s", bytes, strerror(errno));
+        void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (p == MAP_FAILED) die("mmap: %s", strerror(errno));
+        close(fd);
+        g.seg.hdr = (Header *)p;
+    } else {
+        // Wait for rank 0 to create + publish a segment for THIS job (creator alive, size matches).
+        double t0 = MPI_Wtime();
+        for (;;) {
+            fd = shm_open(g.seg.name.c_str(), O_RDWR, 0600);
+            if (fd >= 0) {
+                struct stat st;
+                if (fstat(fd, &st) == 0 && (size_t)st.st_size == bytes) {
+                    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+                    if (p != MAP_FAILED) {
+                        Header *h = (Header *)p;
+                        bool good = false;
+                        for (int spin = 0; spin < 2000; spin++) {
+                            if (h->magic.load(std::memory_order_acquire) == kMagic && h->nranks == (uint32_t)n &&
+                                h->creator_pid > 0 && kill(h->creator_pid, 0) == 0) { good = true; break; }
+                            usleep(100);
+                        }
+                        if (good) { close(fd); g.seg.hdr = h; break; }
+                        munmap(p, bytes);
+                    }
+                }
+                close(fd);
+            }
+            if (MPI_Wtime() - t0 > 120.0) die("rank %d: timed out waiting for shm segment %s", g.rank, g.seg.name.c_str());
+            usleep(1000);
+        }
+    }
+    char *base = (char *)g.seg.hdr;
+    g.seg.bytes = bytes;
+    g.seg.blobs = base + ob;
+    g.seg.scratch = base + os;
+    g.seg.rings = (Ring *)(base + orr);
+    g.seg.cells = base + oc;
+    g.seg.cell_stride = stride;
+    if (g.rank == 0) {
+        Header *h = g.seg.hdr;
+        h->nranks = n; h->ncell = ncell; h->cell_bytes = cell_bytes; h->creator_pid = getpid();
+        h->abort_code.store(0); h->checkin.store(0); h->bar_count.store(0); h->bar_sense.store(0);
+        h->magic.store(kMagic, std::memory_order_release);
+    }
+    g.seg.hdr->pids[g.rank].store(getpid());
+    g.seg.hdr->checkin.fetch_add(1);
+    double t0 = MPI_Wtime();
+    while (g.seg.hdr->checkin.load() < (uint32_t)n) {
+        if (MPI_Wtime() - t0 > 120.0) die("rank %d: only %u/%d ranks checked in", g.rank, g.seg.hdr->checkin.load(), n);
+        usleep(200);
+    }
+}
+
+void check_abort() {
+    int c = g.seg.hdr ? g.seg.hdr->abort_code.load(std::memory_order_relaxed) : 0;
+    if (c) { fprintf(stderr, "[acx-mpi] rank %d exiting: job aborted with code %d\n", g.rank, c); _exit(c & 0xff ? c & 0xff : 1); }
+}
+
+// ---------------------------------------------------------------------------------
+// Requests and matching
+// ---------------------------------------------------------------------------------
+enum ReqKind { RQ_SEND, RQ_RECV, RQ_PSEND, RQ_PRECV };
+
+}  // namespace
+
+struct acx_mpi_request_s {
+    ReqKind kind;
+    void *buf;
+    size_t bytes;       // send: message bytes; recv: capacity
+    int peer, tag, comm, part;
+    bool done = false, active = true, persistent = false, freed = false;
+    MPI_Status st{};
+    // send progress
+    size_t sent = 0;
+    bool hdr_sent = false, is_dev = false, wait_fin = false;
+    // recv progress
+    size_t got = 0, total = 0;
+    // ipc rendezvous on the receive side
+    void *ipc_event = nullptr;
+    uint64_t ipc_cookie = 0;
+    int ipc_src = -1;
+    // partitioned
+    int partitions = 0;
+    size_t part_bytes = 0;
+    std::vector<acx_mpi_request_s *> parts;  // child requests (one per partition)
+    std::vector<char> part_ready;
+};
+typedef acx_mpi_request_s Req;
+
+namespace {
+
+struct Unexpected {
+    int src, tag, comm, part;
+    size_t total, got;
+    std::vector<char> data;  // host staging
+    bool complete;
+    bool is_ipc = false;
+    IpcHandle ipc{};
+    size_t ipc_off = 0;
+    uint64_t cookie = 0;
+    Req *attached = nullptr;  // posted recv that adopted this message while streaming
+};
+
+std::list<Req *> g_posted;            // posted receives, in post order
+std::list<Unexpected *> g_unexp;      // unexpected messages, in arrival order
+std::vector<std::deque<Req *>> g_sendq;  // per-destination FIFO of sends being streamed
+std::vector<Unexpected *> g_cur_in;   // per-source: message currently being streamed in (unexpected)
+std::vector<Req *> g_cur_req;         // per-source: ... or directly into a matched posted recv
+std::unordered_map<uint64_t, Req *> g_await_fin;
+std::list<Req *> g_ipc_inflight;
+uint64_t g_cookie = 1;
+std::unordered_map<std::string, void *> g_ipc_cache;
+
+bool match(int rsrc, int rtag, int rcomm, int rpart, int src, int tag, int comm, int part) {
+    if (rcomm != comm || rpart != part) return false;
+    if (rsrc != MPI_ANY_SOURCE && rsrc != src) return false;
+    if (rtag != MPI_ANY_TAG && rtag != tag) return false;
+    return true;
+}
+
+void copy_in(void *dst, bool dst_dev, const void *src, size_t n) {
+    if (!n) return;
+    if (dst_dev) {
+        g_cuda.MemcpyAsync(dst, src, n, kMemcpyDefault, cuda_stream());
+        g_cuda.StreamSynchronize(cuda_stream());
+    } else {
+        memcpy(dst, src, n);
+    }
+}
+
+void *ipc_map(const IpcHandle &h) {
+    std::string key(h.b, 64);
+    auto it = g_ipc_cache.find(key);
+    if (it != g_ipc_cache.end()) return it->second;
+    void *p = nullptr;
+    int e = g_ipc_open(&p, h, 1 /*cudaIpcMemLazyEnablePeerAccess*/);
+    if (e != 0) die("cudaIpcOpenMemHandle failed (%d)", e);
+    g_ipc_cache[key] = p;
+    return p;
+}
+
+void complete_recv(Req *r, int src, int tag, size_t total) {
+    r->st.MPI_SOURCE = src;
+    r->st.MPI_TAG = tag;
+    r->st.MPI_ERROR = total > r->bytes ? MPI_ERR_TRUNCATE : MPI_SUCCESS;
+    r->st._bytes = (long long)(total > r->bytes ? r->bytes : total);
+    r->done = true;
+}
+
+bool ring_push(int dst, const CellHdr &h, const void *payload) {
+    Ring *rg = ring_of(g.rank, dst);
+    uint64_t head = rg->head.load(std::memory_order_relaxed);
+    uint64_t tail = rg->tail.load(std::memory_order_acquire);
+    if (head - tail >= g.seg.hdr->ncell) return false;
+    char *c = cell_of(g.rank, dst, head);
+    memcpy(c, &h, sizeof(h));
+    if (h.len && payload) memcpy(c + sizeof(CellHdr), payload, h.len);
+    rg->head.store(head + 1, std::memory_order_release);
+    return true;
+}
+
+void start_ipc_pull(Req *r, int src, const IpcHandle &h, size_t off, size_t total, uint64_t cookie, int tag) {
+    char *peer = src == g.rank ? (char *)off : (char *)ipc_map(h) + off;
+    size_t n = total < r->bytes ? total : r->bytes;
+    g_cuda.MemcpyAsync(r->buf, peer, n, kMemcpyDefault, cuda_stream());
+    g_cuda.EventCreateWithFlags(&r->ipc_event, 2 /*DisableTiming*/);
+    g_cuda.EventRecord(r->ipc_event, cuda_stream());
+    r->ipc_cookie = cookie;
+    r->ipc_src = src;
+    r->total = total;
+    r->st.MPI_TAG = tag;
+    g_ipc_inflight.push_back(r);
+}
+
+// Pull cells from one incoming ring.
+void drain_from(int src) {
+    Ring *rg = ring_of(src, g.rank);
+    for (;;) {
+        uint64_t tail = rg->tail.load(std::memory_order_relaxed);
+        uint64_t head = rg->head.load(std::memory_order_acquire);
+        if (tail == head) return;
+        char *c = cell_of(src, g.rank, tail);
+        CellHdr h;
+        memcpy(&h, c, sizeof(h));
+        const char *payload = c + sizeof(CellHdr);
+        if (h.kind == CELL_FIN) {
+            auto it = g_await_fin.find(h.cookie);
+            if (it != g_await_fin.end()) { it->second->done = true; g_await_fin.erase(it); }
+        } else if (h.kind == CELL_HDR || h.kind == CELL_RTS_IPC) {
+            Req *m = nullptr;
+            for (auto it = g_posted.begin(); it != g_posted.end(); ++it) {
+                if (match((*it)->peer, (*it)->tag, (*it)->comm, (*it)->part, src, h.tag, h.comm, h.part)) {
+                    m = *it; g_posted.erase(it); break;
+                }
+            }
+            if (h.kind == CELL_RTS_IPC) {
+                IpcHandle ih; size_t off;
+                memcpy(&ih, payload, 64); memcpy(&off, payload + 64, sizeof(size_t));
+                if (m) {
+                    start_ipc_pull(m, src, ih, off, h.total, h.cookie, h.tag);
+                } else {
+                    Unexpected *u = new Unexpected{src, h.tag, h.comm, h.part, (size_t)h.total, 0, {}, true};
+                    u->is_ipc = true; u->ipc = ih; u->ipc_off = off; u->cookie = h.cookie;
+                    g_unexp.push_back(u);
+                }
+            } else if (m) {
+                m->total = h.total; m->got = 0; m->st.MPI_TAG = h.tag;
+                if (h.total == 0) complete_recv(m, src, h.tag, 0);
+                else g_cur_req[src] = m;
+            } else {
+                Unexpected *u = new Unexpected{src, h.tag, h.comm, h.part, (size_t)h.total, 0, {}, h.total == 0};
+                u->data.resize(h.total);
+                g_unexp.push_back(u);
+                if (h.total) g_cur_in[src] = u;
+            }
+        } else if (h.kind == CELL_DATA) {
+            if (Req *m = g_cur_req[src]) {
+                size_t room = m->got < m->bytes ? m->bytes - m->got : 0;
+                size_t n = h.len < room ? h.len : room;
+                copy_in((char *)m->buf + m->got, m->is_dev, payload, n);
+                m->got += h.len;
+                if (m->got >= m->total) { complete_recv(m, src, m->st.MPI_TAG, m->total); g_cur_req[src] = nullptr; }
+            } else if (Unexpected *u = g_cur_in[src]) {
+                memcpy(u->data.data() + u->got, payload, h.len);
+                u->got += h.len;
+                if (u->got >= u->total) {
+                    u->complete = true; g_cur_in[src] = nullptr;
+                    if (u->attached) {
+                        Req *m = u->attached;
+                        size_t n = u->total < m->bytes ? u->total : m->bytes;
+                        copy_in(m->buf, m->is_dev, u->data.data(), n);
+                        complete_recv(m, u->src, u->tag, u->total);
+                        g_unexp.remove(u); delete u;
+                    }
+                }
+            } else {
+                die("DATA cell with no message in flight from %d", src);
+            }
+        }
+        rg->tail.store(tail + 1, std::memory_order_release);
+    }
+}
+
+// Push as much of the head-of-line send to `dst` as the ring accepts.
+void pump_sends(int dst) {
+    auto &q = g_sendq[dst];
+    while (!q.empty()) {
+        Req *s = q.front();
+        if (!s->hdr_sent) {
+            CellHdr h{};
+            h.tag = s->tag; h.comm = s->comm; h.part = s->part; h.total = s->bytes;
+            size_t ipc_min = (size_t)env_int("ACX_MPI_IPC_THRESHOLD", nullptr, nullptr, 32768);
+            if (s->is_dev && s->bytes >= ipc_min) {
+                // CUDA-IPC rendezvous: ship handle+offset; receiver copies and FINs.
+                static MemGetAddressRangeFn get_range = nullptr;
+                static bool tried = false;
+                if (!tried) { tried = true; void *cu = dlopen("libcuda.so.1", RTLD_NOW); if (cu) get_range = (MemGetAddressRangeFn)dlsym(cu, "cuMemGetAddressRange_v2"); }
+                unsigned long long base = 0; size_t sz = 0;
+                if (!get_range || get_range(&base, &sz, (unsigned long long)s->buf) != 0) die("cuMemGetAddressRange failed");
+                IpcHandle ih;
+                memset(&ih, 0, sizeof ih);
+                size_t off = (size_t)((unsigned long long)s->buf - base);
+                if (dst == g.rank) off = (size_t)s->buf;  // self-send: same address space, no IPC
+                else if (g_cuda.IpcGetMemHandle(&ih, (void *)base) != 0) die("cudaIpcGetMemHandle failed");
+                char pl[64 + sizeof(size_t)];
+                memcpy(pl, &ih, 64); memcpy(pl + 64, &off, sizeof(size_t));
+                h.kind = CELL_RTS_IPC; h.len = sizeof(pl); h.cookie = g_cookie++;
+                if (!ring_push(dst, h, pl)) return;
+                g_await_fin[h.cookie] = s;
+                s->hdr_sent = true; s->wait_fin = true; s->sent = s->bytes;
+                q.pop_front();
+                continue;
+            }
+            h.kind = CELL_HDR; h.len = 0;
+            if (!ring_push(dst, h, nullptr)) return;
+            s->hdr_sent = true;
+        }
+        while (s->sent < s->bytes) {
+            size_t n = s->bytes - s->sent;
+            if (n > g.seg.hdr->cell_bytes) n = g.seg.hdr->cell_bytes;
+            CellHdr h{};
+            h.kind = CELL_DATA; h.len = (uint32_t)n;
+            if (s->is_dev) {
+                Ring *rg = ring_of(g.rank, dst);
+                uint64_t head = rg->head.load(std::memory_order_relaxed);
+                if (head - rg->tail.load(std::memory_order_acquire) >= g.seg.hdr->ncell) return;
+                char *c = cell_of(g.rank, dst, head);
+                memcpy(c, &h, sizeof(h));
+                g_cuda.MemcpyAsync(c + sizeof(CellHdr), (char *)s->buf + s->sent, n, kMemcpyDefault, cuda_stream());
+                g_cuda.StreamSynchronize(cuda_stream());
+                rg->head.store(head + 1, std::memory_order_release);
+            } else if (!ring_push(dst, h, (char *)s->buf + s->sent)) {
+                return;
+            }
+            s->sent += n;
+        }
+        s->done = true;  // buffered-send semantics: data fully handed to the ring
+        q.pop_front();
+    }
+}
+
+void progress() {
+    check_abort();
+    for (int p = 0; p < g.size; p++) drain_from(p);
+    for (int p = 0; p < g.size; p++) if (!g_sendq[p].empty()) pump_sends(p);
+    for (auto it = g_ipc_inflight.begin(); it != g_ipc_inflight.end();) {
+        Req *r = *it;
+        if (g_cuda.EventQuery(r->ipc_event) == 0) {
+            g_cuda.EventDestroy(r->ipc_event); r->ipc_event = nullptr;
+            CellHdr h{}; h.kind = CELL_FIN; h.cookie = r->ipc_cookie;
+            if (!ring_push(r->ipc_src, h, nullptr)) { ++it; continue; }  // retry FIN next round
+            complete_recv(r, r->ipc_src, r->st.MPI_TAG, r->total);
+            it = g_ipc_inflight.erase(it);
+        } else {
+            g_cuda.GetLastError();
+            ++it;
+        }
+    }
+}
+
+size_t dt_size(MPI_Datatype dt) { return (size_t)(dt & 0xff); }
+
+int ctx_of(MPI_Comm c) {
+    if (c == MPI_COMM_WORLD) return 1;
+    if (c == MPI_COMM_SELF) return 2;
+    auto it = g.comm_ctx.find(c);
+    return it == g.comm_ctx.end() ? -1 : it->second;
+}
+
+Req *post_send(const void *buf, size_t bytes, int dest, int tag, int comm, int part) {
+    Req *s = new Req();
+    s->kind = RQ_SEND; s->buf = (void *)buf; s->bytes = bytes; s->peer = dest; s->tag = tag; s->comm = comm; s->part = part;
+    s->is_dev = is_device_ptr(buf);
+    if (dest == MPI_PROC_NULL) { s->done = true; return s; }
+    g_sendq[dest].push_back(s);
+    pump_sends(dest);
+    return s;
+}
+
+Req *post_recv(void *buf, size_t bytes, int src, int tag, int comm, int part) {
+    Req *r = new Req();
+    r->kind = RQ_RECV; r->buf = buf; r->bytes = bytes; r->peer = src; r->tag = tag; r->comm = comm; r->part = part;
+    r->is_dev = is_device_ptr(buf);
+    if (src == MPI_PROC_NULL) { r->done = true; r->st.MPI_SOURCE = MPI_PROC_NULL; r->st.MPI_TAG = MPI_ANY_TAG; return r; }
+    for (auto it = g_unexp.begin(); it != g_unexp.end(); ++it) {
+        Unexpected *u = *it;
+        if (u->attached || !match(src, tag, comm, part, u->src, u->tag, u->comm, u->part)) continue;
+        if (u->is_ipc) {
+            start_ipc_pull(r, u->src, u->ipc, u->ipc_off, u->total, u->cookie, u->tag);
+            g_unexp.erase(it); delete u;
+        } else if (u->complete) {
+            size_t n = u->total < bytes ? u->total : bytes;
+            copy_in(buf, r->is_dev, u->data.data(), n);
+            complete_recv(r, u->src, u->tag, u->total);
+            g_unexp.erase(it); delete u;
+        } else {
+            u->attached = r;  // finishes when the remaining cells arrive
+        }
+        return r;
+    }
+    g_posted.push_back(r);
+    return r;
+}
+
+void wait_req(Req *r) {
+    while (!r->done) {
+        progress();
+        if (!r->done) { g_mu.unlock(); sched_yield(); g_mu.lock(); }
+    }
+}
+
+void shm_barrier() {
+    Header *h = g.seg.hdr;
+    g.my_sense ^= 1;
+    if (h->bar_count.fetch_add(1) + 1 == (uint32_t)g.size) {
+        h->bar_count.store(0);
+        h->bar_sense.store(g.my_sense, std::memory_order_release);
+    } else {
+        while (h->bar_sense.load(std::memory_order_acquire) != g.my_sense) {
+            progress();
+            g_mu.unlock(); sched_yield(); g_mu.lock();
+        }
+    }
+}
+
+template <typename T> void reduce_typed(T *acc, const T *in, int n, MPI_Op op) {
+    for (int i = 0; i < n; i++) {
+        switch (op) {
+            case MPI_SUM: acc[i] = acc[i] + in[i]; break;
+            case MPI_PROD: acc[i] = acc[i] * in[i]; break;
+            case MPI_MAX: acc[i] = acc[i] > in[i] ? acc[i] : in[i]; break;
+            case MPI_MIN: acc[i] = acc[i] < in[i] ? acc[i] : in[i]; break;
+            case MPI_LAND: acc[i] = (T)(acc[i] && in[i]); break;
+            case MPI_LOR: acc[i] = (T)(acc[i] || in[i]); break;
+            default: break;
+        }
+    }
+}
+template <typename T> void reduce_bits(T *acc, const T *in, int n, MPI_Op op) {
+    for (int i = 0; i < n; i++) {
+        if (op == MPI_BAND) acc[i] &= in[i];
+        else if (op == MPI_BOR) acc[i] |= in[i];
+    }
+}
+
+void reduce_into(void *acc, const void *in, int n, MPI_Datatype dt, MPI_Op op) {
+    if (op == MPI_BAND || op == MPI_BOR) {
+        switch (dt_size(dt)) {
+            case 1: reduce_bits((uint8_t *)acc, (const uint8_t *)in, n, op); return;
+            case 2: reduce_bits((uint16_t *)acc, (const uint16_t *)in, n, op); return;
+            case 4: reduce_bits((uint32_t *)acc, (const uint32_t *)in, n, op); return;
+            default: reduce_bits((uint64_t *)acc, (const uint64_t *)in, n, op); return;
+        }
+    }
+    switch (dt) {
+        case MPI_FLOAT: reduce_typed((float *)acc, (const float *)in, n, op); break;
+        case MPI_DOUBLE: reduce_typed((double *)acc, (const double *)in, n, op); break;
+        case MPI_INT: case MPI_INT32_T: reduce_typed((int32_t *)acc, (const int32_t *)in, n, op); break;
+        case MPI_UNSIGNED: case MPI_UINT32_T: reduce_typed((uint32_t *)acc, (const uint32_t *)in, n, op); break;
+        case MPI_LONG: case MPI_LONG_LONG: case MPI_INT64_T: case MPI_COUNT: case MPI_AINT:
+            reduce_typed((int64_t *)acc, (const int64_t *)in, n, op); break;
+        case MPI_UNSIGNED_LONG: case MPI_UNSIGNED_LONG_LONG: case MPI_UINT64_T:
+            reduce_typed((uint64_t *)acc, (const uint64_t *)in, n, op); break;
+        case MPI_SHORT: case MPI_INT16_T: reduce_typed((int16_t *)acc, (const int16_t *)in, n, op); break;
+        case MPI_UNSIGNED_SHORT: case MPI_UINT16_T: reduce_typed((uint16_t *)acc, (const uint16_t *)in, n, op); break;
+        case MPI_CHAR: case MPI_SIGNED_CHAR: case MPI_INT8_T: reduce_typed((int8_t *)acc, (const int8_t *)in, n, op); break;
+        case MPI_UNSIGNED_CHAR: case MPI_BYTE: case MPI_UINT8_T: case MPI_C_BOOL:
+            reduce_typed((uint8_t *)acc, (const uint8_t *)in, n, op); break;
+        default: die("MPI reduction on unsupported datatype 0x%x", dt);
+    }
+}
+
+void atexit_cleanup() {
+    if (g.initialized && g.rank == 0 && !g.seg.name.empty()) shm_unlink(g.seg.name.c_str());
+}
+
+#define LOCK std::lock_guard<std::recursive_mutex> _lk(g_mu)
+
+}  // namespace
+
+// =====================================================================================
+// Public API
+// =====================================================================================
+extern "C" {
+
+int MPI_Init_thread(int *, char ***, int required, int *provided) {
+    LOCK;
+    if (g.initialized) { if (provided) *provided = g.thread_level; return MPI_SUCCESS; }
+    g.rank = env_int("ACX_RANK", "RANK", "PMI_RANK", 0);
+    g.size = env_int("ACX_SIZE", "WORLD_SIZE", "PMI_SIZE", 1);
+    if (g.size > 1024 || g.rank < 0 || g.rank >= g.size) die("bad rank/size %d/%d", g.rank, g.size);
+    const char *jid = getenv("ACX_JOBID");
+    if (jid && *jid) g.jobid = jid;
+    else {
+        const char *port = getenv("MASTER_PORT");
+        const char *run = getenv("TORCHELASTIC_RUN_ID");
+        char tmp[256];
+        if (g.size == 1 && !port) snprintf(tmp, sizeof tmp, "solo_%d", (int)getpid());
+        else snprintf(tmp, sizeof tmp, "u%d_p%s_%s", (int)getuid(), port ? port : "0", run ? run : "x");
+        for (char *p = tmp; *p; p++) if (*p == '/' || *p == ' ') *p = '_';
+        g.jobid = tmp;
+    }
+    seg_attach();
+    g_sendq.assign(g.size, {});
+    g_cur_in.assign(g.size, nullptr);
+    g_cur_req.assign(g.size, nullptr);
+    g.thread_level = MPI_THREAD_MULTIPLE;
+    (void)required;
+    if (provided) *provided = MPI_THREAD_MULTIPLE;
+    g.initialized = true;
+    atexit(atexit_cleanup);
+    return MPI_SUCCESS;
+}
+
+int MPI_Init(int *argc, char ***argv) { int p; return MPI_Init_thread(argc, argv, MPI_THREAD_SINGLE, &p); }
+
+int MPI_Finalize(void) {
+    LOCK;
+    if (!g.initialized || g.finalized) return MPI_ERR_OTHER;
+    // Drain our outgoing traffic, then rendezvous so nobody unmaps a live ring.
+    for (;;) {
+        bool busy = false;
+        for (int p = 0; p < g.size; p++) if (!g_sendq[p].empty()) busy = true;
+        if (!busy) break;
+        progress();
+        g_mu.unlock(); sched_yield(); g_mu.lock();
+    }
+    shm_barrier();
+    g.finalized = true;
+    if (g.rank == 0 && !g.seg.name.empty()) shm_unlink(g.seg.name.c_str());
+    return MPI_SUCCESS;
+}
+
+int MPI_Initialized(int *flag) { *flag = g.initialized; return MPI_SUCCESS; }
+int MPI_Finalized(int *flag) { *flag = g.finalized; return MPI_SUCCESS; }
+int MPI_Query_thread(int *provided) { *provided = g.thread_level; return MPI_SUCCESS; }
+
+int MPI_Abort(MPI_Comm, int code) {
+    fprintf(stderr, "[acx-mpi] MPI_Abort(%d) on rank %d\n", code, g.rank);
+    if (g.seg.hdr) {
+        g.seg.hdr->abort_code.store(code ? code : 1);
+        for (int r = 0; r < g.size; r++) {
+            int pid = g.seg.hdr->pids[r].load();
+            if (r != g.rank && pid > 0) kill(pid, SIGTERM);
+        }
+        if (g.rank == 0 && !g.seg.name.empty()) shm_unlink(g.seg.name.c_str());
+    }
+    _exit(code ? (code & 0xff ? code & 0xff : 1) : 1);
+}
+
+int MPI_Error_string(int code, char *s, int *len) {
+    const char *m = "unknown error";
+    switch (code) {
+        case MPI_SUCCESS: m = "no error"; break;
+        case MPI_ERR_BUFFER: m = "invalid buffer"; break;
+        case MPI_ERR_COUNT: m = "invalid count"; break;
+        case MPI_ERR_TYPE: m = "invalid datatype"; break;
+        case MPI_ERR_TAG: m = "invalid tag"; break;
+        case MPI_ERR_COMM: m = "invalid communicator"; break;
+        case MPI_ERR_RANK: m = "invalid rank"; break;
+        case MPI_ERR_REQUEST: m = "invalid request"; break;
+        case MPI_ERR_TRUNCATE: m = "message truncated"; break;
+        case MPI_ERR_ARG: m = "invalid argument"; break;
+        case MPI_ERR_OTHER: m = "other error"; break;
+        case MPI_ERR_INTERN: m = "internal error"; break;
+    }
+    snprintf(s, MPI_MAX_ERROR_STRING, "%s", m);
+    if (len) *len = (int)strlen(s);
+    return MPI_SUCCESS;
+}
+
+int MPI_Comm_set_errhandler(MPI_Comm, MPI_Errhandler) { return MPI_SUCCESS; }
+
+double MPI_Wtime(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+int MPI_Get_processor_name(char *name, int *len) {
+    if (gethostname(name, MPI_MAX_PROCESSOR_NAME) != 0) snprintf(name, MPI_MAX_PROCESSOR_NAME, "localhost");
+    if (len) *len = (int)strlen(name);
+    return MPI_SUCCESS;
+}
+
+int MPI_Comm_rank(MPI_Comm c, int *rank) {
+    if (ctx_of(c) < 0) return MPI_ERR_COMM;
+    *rank = c == MPI_COMM_SELF ? 0 : g.rank;
+    return MPI_SUCCESS;
+}
+int MPI_Comm_size(MPI_Comm c, int *size) {
+    if (ctx_of(c) < 0) return MPI_ERR_COMM;
+    *size = c == MPI_COMM_SELF ? 1 : g.size;
+    return MPI_SUCCESS;
+}
+int MPI_Comm_dup(MPI_Comm c, MPI_Comm *out) {
+    LOCK;
+    if (ctx_of(c) < 0) return MPI_ERR_COMM;
+    // Collective by convention: every rank dups in the same order, so ids agree.
+    int id = g.next_comm++;
+    g.comm_ctx[id] = c == MPI_COMM_SELF ? -id : id;
+    *out = id;
+    return MPI_SUCCESS;
+}
+int MPI_Comm_free(MPI_Comm *c) { LOCK; g.comm_ctx.erase(*c); *c = MPI_COMM_NULL; return MPI_SUCCESS; }
+
+int MPI_Type_size(MPI_Datatype dt, int *size) { *size = (int)dt_size(dt); return *size ? MPI_SUCCESS : MPI_ERR_TYPE; }
+int MPI_Get_count(const MPI_Status *st, MPI_Datatype dt, int *count) {
+    size_t s = dt_size(dt);
+    if (!s) return MPI_ERR_TYPE;
+    *count = (st->_bytes % (long long)s) ? MPI_UNDEFINED : (int)(st->_bytes / (long long)s);
+    return MPI_SUCCESS;
+}
+
+int MPI_Barrier(MPI_Comm c) {
+    LOCK;
+    if (c == MPI_COMM_SELF || g.size == 1) return MPI_SUCCESS;
+    shm_barrier();
+    return MPI_SUCCESS;
+}
+
+int ACX_Mpi_exchange(const void *mine, void *all, size_t bytes) {
+    LOCK;
+    if (bytes > kBlobBytes) return MPI_ERR_ARG;
+    shm_barrier();  // previous readers are done with the blobs
+    memcpy(g.seg.blobs + (size_t)g.rank * kBlobBytes, mine, bytes);
+    shm_barrier();
+    for (int r = 0; r < g.size; r++) memcpy((char *)all + (size_t)r * bytes, g.seg.blobs + (size_t)r * kBlobBytes, bytes);
+    return MPI_SUCCESS;
+}
+
+void *ACX_Mpi_shared_scratch(size_t *bytes) { if (bytes) *bytes = kScratchBytes; return g.seg.scratch; }
+int ACX_Mpi_local_rank(void) { return env_int("ACX_LOCAL_RANK", "LOCAL_RANK", nullptr, g.rank); }
+const char *ACX_Mpi_jobid(void) { return g.jobid.c_str(); }
+
+int MPI_Allgather(const void *sb, int sc, MPI_Datatype sdt, void *rb, int rc, MPI_Datatype rdt, MPI_Comm c) {
+    LOCK;
+    size_t sbytes = (size_t)sc * dt_size(sdt), rbytes = (size_t)rc * dt_size(rdt);
+    if (c == MPI_COMM_SELF || g.size == 1) { if (sb != MPI_IN_PLACE) memcpy(rb, sb, sbytes); return MPI_SUCCESS; }
+    const char *src = sb == MPI_IN_PLACE ? (char *)rb + rbytes * g.rank : (const char *)sb;
+    std::vector<char> mine(src, src + rbytes);
+    for (size_t off = 0; off < rbytes; off += kBlobBytes) {
+        size_t n = rbytes - off < kBlobBytes ? rbytes - off : kBlobBytes;
+        std::vector<char> tmp(n * g.size);
+        ACX_Mpi_exchange(mine.data() + off, tmp.data(), n);
+        for (int r = 0; r < g.size; r++) memcpy((char *)rb + rbytes * r + off, tmp.data() + n * r, n);
+    }
+    return MPI_SUCCESS;
+}
+
+int MPI_Allreduce(const void *sb, void *rb, int count, MPI_Datatype dt, MPI_Op op, MPI_Comm c) {
+    LOCK;
+    size_t es = dt_size(dt), bytes = es * (size_t)count;
+    if (sb != MPI_IN_PLACE) memcpy(rb, sb, bytes);
+    if (c == MPI_COMM_SELF || g.size == 1) return MPI_SUCCESS;
+    int per = (int)(kBlobBytes / es);
+    std::vector<char> tmp(kBlobBytes * g.size);
+    for (int off = 0; off < count; off += per) {
+        int n = count - off < per ? count - off : per;
+        ACX_Mpi_exchange((char *)rb + es * off, tmp.data(), es * n);
+        memcpy((char *)rb + es * off, tmp.data(), es * n);
+        for (int r = 1; r < g.size; r++) reduce_into((char *)rb + es * off, tmp.data() + es * n * r, n, dt, op);
+    }
+    return MPI_SUCCESS;
+}
+
+int MPI_Reduce(const void *sb, void *rb, int count, MPI_Datatype dt, MPI_Op op, int root, MPI_Comm c) {
+    std::vector<char> tmp(dt_size(dt) * (size_t)count);
+    const void *in = sb == MPI_IN_PLACE ? rb : sb;
+    memcpy(tmp.data(), in, tmp.size());
+    int e = MPI_Allreduce(MPI_IN_PLACE, tmp.data(), count, dt, op, c);
+    int rank; MPI_Comm_rank(c, &rank);
+    if (rank == root) memcpy(rb, tmp.data(), tmp.size());
+    return e;
+}
+
+int MPI_Bcast(void *buf, int count, MPI_Datatype dt, int root, MPI_Comm c) {
+    LOCK;
+    if (c == MPI_COMM_SELF || g.size == 1) return MPI_SUCCESS;
+    size_t bytes = dt_size(dt) * (size_t)count;
+    std::vector<char> tmp(kBlobBytes * g.size);
+    for (size_t off = 0; off < bytes; off += kBlobBytes) {
+        size_t n = bytes - off < kBlobBytes ? bytes - off : kBlobBytes;
+        ACX_Mpi_exchange((char *)buf + off, tmp.data(), n);
+        memcpy((char *)buf + off, tmp.data() + n * root, n);
+    }
+    return MPI_SUCCESS;
+}
+
+int MPI_Isend(const void *buf, int count, MPI_Datatype dt, int dest, int tag, MPI_Comm c, MPI_Request *req) {
+    LOCK;
+    int ctx = ctx_of(c);
+    if (ctx < 0) return MPI_ERR_COMM;
+    if (c == MPI_COMM_SELF && dest == 0) dest = g.rank;
+    if (dest != MPI_PROC_NULL && (dest < 0 || dest >= g.size)) return MPI_ERR_RANK;
+    *req = post_send(buf, dt_size(dt) * (size_t)count, dest, tag, ctx, -1);
+    return MPI_SUCCESS;
+}
+
+int MPI_Irecv(void *buf, int count, MPI_Datatype dt, int src, int tag, MPI_Comm c, MPI_Request *req) {
+    LOCK;
+    int ctx = ctx_of(c);
+    if (ctx < 0) return MPI_ERR_COMM;
+    if (c == MPI_COMM_SELF && src == 0) src = g.rank;
+    if (src != MPI_PROC_NULL && src != MPI_ANY_SOURCE && (src < 0 || src >= g.size)) return MPI_ERR_RANK;
+    *req = post_recv(buf, dt_size(dt) * (size_t)count, src, tag, ctx, -1);
+    progress();
+    return MPI_SUCCESS;
+}
+
+static void finish_req(MPI_Request *req, MPI_Status *st) {
+    Req *r = *req;
+    if (st) *st = r->st;
+    if (r->persistent) { r->active = false; return; }
+    delete r;
+    *req = MPI_REQUEST_NULL;
+}
+
+static bool test_partitioned(Req *r) {
+    bool all = true;
+    for (Req *p : r->parts) if (p && !p->done) all = false;
+    if (r->kind == RQ_PSEND) for (int i = 0; i < r->partitions; i++) if (!r->part_ready[i]) all = false;
+    return all;
+}
+
+int MPI_Test(MPI_Request *req, int *flag, MPI_Status *st) {
+    LOCK;
+    if (!*req) { *flag = 1; return MPI_SUCCESS; }
+    progress();
+    Req *r = *req;
+    if (r->persistent) {
+        if (!r->active) { *flag = 1; return MPI_SUCCESS; }
+        *flag = test_partitioned(r);
+        if (*flag) {
+            for (Req *&p : r->parts) { delete p; p = nullptr; }
+            r->st.MPI_SOURCE = r->peer; r->st.MPI_TAG = r->tag; r->st.MPI_ERROR = MPI_SUCCESS;
+            finish_req(req, st);
+        }
+        return MPI_SUCCESS;
+    }
+    *flag = r->done;
+    if (r->done) finish_req(req, st);
+    return MPI_SUCCESS;
+}
+
+int MPI_Wait(MPI_Request *req, MPI_Status *st) {
+    LOCK;
+    if (!*req) return MPI_SUCCESS;
+    for (;;) {
+        int flag = 0;
+        MPI_Test(req, &flag, st);
+        if (flag) return MPI_SUCCESS;
+        g_mu.unlock(); sched_yield(); g_mu.lock();
+    }
+}
+
+int MPI_Waitall(int n, MPI_Request *reqs, MPI_Status *sts) {
+    for (int i = 0; i < n; i++) MPI_Wait(&reqs[i], sts ? &sts[i] : MPI_STATUS_IGNORE);
+    return MPI_SUCCESS;
+}
+
+int MPI_Testall(int n, MPI_Request *reqs, int *flag, MPI_Status *sts) {
+    LOCK;
+    progress();
+    for (int i = 0; i < n; i++) {
+        Req *r = reqs[i];
+        if (!r) continue;
+        bool d = r->persistent ? (!r->active || test_partitioned(r)) : r->done;
+        if (!d) { *flag = 0; return MPI_SUCCESS; }
+    }
+    *flag = 1;
+    for (int i = 0; i < n; i++) { int f; MPI_Test(&reqs[i], &f, sts ? &sts[i] : MPI_STATUS_IGNORE); }
+    return MPI_SUCCESS;
+}
+
+int MPI_Send(const void *buf, int count, MPI_Datatype dt, int dest, int tag, MPI_Comm c) {
+    MPI_Request r;
+    int e = MPI_Isend(buf, count, dt, dest, tag, c, &r);
+    return e ? e : MPI_Wait(&r, MPI_STATUS_IGNORE);
+}
+int MPI_Recv(void *buf, int count, MPI_Datatype dt, int src, int tag, MPI_Comm c, MPI_Status *st) {
+    MPI_Request r;
+    int e = MPI_Irecv(buf, count, dt, src, tag, c, &r);
+    return e ? e : MPI_Wait(&r, st);
+}
+int MPI_Sendrecv(const void *sb, int sc, MPI_Datatype sdt, int dest, int stag, void *rb, int rc, MPI_Datatype rdt,
+                 int src, int rtag, MPI_Comm c, MPI_Status *st) {
+    MPI_Request r[2];
+    int e = MPI_Irecv(rb, rc, rdt, src, rtag, c, &r[0]);
+    if (e) return e;
+    e = MPI_Isend(sb, sc, sdt, dest, stag, c, &r[1]);
+    if (e) return e;
+    MPI_Wait(&r[1], MPI_STATUS_IGNORE);
+    return MPI_Wait(&r[0], st);
+}
+
+int MPI_Request_free(MPI_Request *req) {
+    LOCK;
+    Req *r = *req;
+    if (!r) return MPI_SUCCESS;
+    if (r->persistent) {
+        for (Req *p : r->parts) if (p) wait_req(p), delete p;
+        delete r;
+    } else {
+        // Non-persistent: let it finish in the background (sends only); simple approach: wait.
+        wait_req(r);
+        delete r;
+    }
+    *req = MPI_REQUEST_NULL;
+    return MPI_SUCCESS;
+}
+
+// ---- partitioned -------------------------------------------------------------------
+static int pinit(ReqKind k, void *buf, int partitions, MPI_Count count, MPI_Datatype dt, int peer, int tag, MPI_Comm c,
+                 MPI_Request *req) {
+    LOCK;
+    int ctx = ctx_of(c);
+    if (ctx < 0) return MPI_ERR_COMM;
+    if (partitions <= 0 || count < 0) return MPI_ERR_COUNT;
+    Req *r = new Req();
+    r->kind = k; r->buf = buf; r->partitions = partitions; r->part_bytes = dt_size(dt) * (size_t)count;
+    r->bytes = r->part_bytes * partitions; r->peer = peer; r->tag = tag; r->comm = ctx | 0x40000000; r->part = -1;
+    r->persistent = true; r->active = false; r->done = false;
+    r->parts.assign(partitions, nullptr);
+    r->part_ready.assign(partitions, 0);
+    *req = r;
+    return MPI_SUCCESS;
+}
+
+int MPI_Psend_init(const void *buf, int partitions, MPI_Count count, MPI_Datatype dt, int dest, int tag, MPI_Comm c,
+                   MPI_Info, MPI_Request *req) {
+    return pinit(RQ_PSEND, (void *)buf, partitions, count, dt, dest, tag, c, req);
+}
+int MPI_Precv_init(void *buf, int partitions, MPI_Count count, MPI_Datatype dt, int src, int tag, MPI_Comm c, MPI_Info,
+                   MPI_Request *req) {
+    return pinit(RQ_PRECV, buf, partitions, count, dt, src, tag, c, req);
+}
+
+int MPI_Start(MPI_Request *req) {
+    LOCK;
+    Req *r = *req;
+    if (!r || !r->persistent || r->active) return MPI_ERR_REQUEST;
+    r->active = true;
+    std::fill(r->part_ready.begin(), r->part_ready.end(), 0);
+    if (r->kind == RQ_PRECV)
+        for (int p = 0; p < r->partitions; p++)
+            r->parts[p] = post_recv((char *)r->buf + r->part_bytes * p, r->part_bytes, r->peer, r->tag, r->comm, p);
+    return MPI_SUCCESS;
+}
+int MPI_Startall(int n, MPI_Request *reqs) {
+    for (int i = 0; i < n; i++) { int e = MPI_Start(&reqs[i]); if (e) return e; }
+    return MPI_SUCCESS;
+}
+
+int MPI_Pready(int partition, MPI_Request r) {
+    LOCK;
+    if (!r || r->kind != RQ_PSEND || !r->active || partition < 0 || partition >= r->partitions) return MPI_ERR_REQUEST;
+    if (r->part_ready[partition]) return MPI_ERR_ARG;
+    r->part_ready[partition] = 1;
+    r->parts[partition] = post_send((char *)r->buf + r->part_bytes * partition, r->part_bytes, r->peer, r->tag, r->comm, partition);
+    return MPI_SUCCESS;
+}
+
+int MPI_Parrived(MPI_Request r, int partition, int *flag) {
+    LOCK;
+    if (!r || r->kind != RQ_PRECV || partition < 0 || partition >= r->partitions) return MPI_ERR_REQUEST;
+    if (!r->active) { *flag = 1; return MPI_SUCCESS; }  // inactive request: completed round
+    progress();
+    *flag = r->parts[partition] && r->parts[partition]->done;
+    return MPI_SUCCESS;
+}
+
+}  // extern "C"
