@@ -1,0 +1,54 @@
+# acx-b200 build: libacx.so (runtime + bundled mini-MPI), acxrun launcher, C/CUDA tests.
+# The reference builds a static lib with nvcc -dc for sm_80 (reference Makefile:3,8,36);
+# we target sm_100a only and need no relocatable device code (device API is header-inline).
+NVCC      ?= nvcc
+CXX       ?= g++
+GENCODE   ?= -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS ?= $(GENCODE) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter -Iinclude
+CXXFLAGS  ?= -O2 -std=c++17 -fPIC -Wall -Wextra -Iinclude
+B := build
+
+LIB   := lib/libacx.so
+MPILIB := lib/libacxmpi.a
+BINS  := bin/acxrun
+BENCH := $(patsubst bench/%.cu,bin/%,$(wildcard bench/*.cu))
+CTESTS := $(patsubst tests/c/%.c,$(B)/tests/%,$(wildcard tests/c/*.c)) $(patsubst tests/c/%.cu,$(B)/tests/%,$(wildcard tests/c/*.cu))
+
+.PHONY: all clean lib tests bench
+all: lib $(BINS) tests bench
+bench: $(BENCH)
+bin/%: bench/%.cu $(LIB)
+	@mkdir -p bin
+	$(NVCC) $(GENCODE) -O3 -std=c++17 -lineinfo -Iinclude -Ibench $< -o $@ -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../lib' -cudart static
+lib: $(LIB) $(MPILIB)
+
+$(B)/minimpi.o: src/minimpi/minimpi.cpp include/mpi.h
+	@mkdir -p $(B)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(MPILIB): $(B)/minimpi.o
+	@mkdir -p lib
+	ar rcs $@ $^
+
+$(B)/acx.o: src/core/acx.cu src/core/internal.h src/core/kernels.cuh include/mpi-acx.h include/acx_device.cuh include/mpi.h
+	@mkdir -p $(B)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(LIB): $(B)/acx.o $(B)/minimpi.o
+	@mkdir -p lib
+	$(NVCC) $(GENCODE) -shared -o $@ $^ -cudart static -ldl -lpthread -lrt
+
+bin/acxrun: launcher/acxrun.cpp
+	@mkdir -p bin
+	$(CXX) -O2 -std=c++17 -Wall $< -o $@
+
+tests: $(CTESTS)
+$(B)/tests/%: tests/c/%.c $(LIB)
+	@mkdir -p $(B)/tests
+	$(NVCC) $(GENCODE) -O2 -Iinclude $< -o $@ -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
+$(B)/tests/%: tests/c/%.cu $(LIB)
+	@mkdir -p $(B)/tests
+	$(NVCC) $(GENCODE) -O2 -lineinfo -Iinclude $< -o $@ -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
+
+clean:
+	rm -rf $(B) lib bin

@@ -1,0 +1,206 @@
+#!/usr/bin/env python
+"""Headline benchmark (driver contract): ring send/recv bandwidth through the stream-triggered
+MPIX_Isend_enqueue / MPIX_Irecv_enqueue / MPIX_Waitall_enqueue API on N GPUs of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # acx-b200 (this repo)
+    python bench.py --impl reference --gpus N ...            # unmodified NVIDIA/mpi-acx from baseline/_ref
+
+Metric (BASELINE.json): "send/recv GB/s" — every rank sends MSG bytes to its right neighbour and
+receives MSG bytes from its left one per step (N=1: to itself); value = total bytes delivered per
+second over all N GPUs, device-timed with CUDA events, max over ranks. MSG = 256 MiB by default so
+the 512 MiB working set per GPU is larger than the 126 MB L2 (no flush needed between steps).
+`e2e` repeats the measurement with a host->device copy of the step's send buffer from pinned memory
+and a device->host read-back of 4 KiB of the received data inside every timed step.
+Extra keys carry the latency / small-message / partitioned numbers gathered in the same run.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="acx", choices=["acx", "reference"])
+    ap.add_argument("--bytes", type=int, default=256 << 20)
+    ap.add_argument("--no-extras", action="store_true")
+    return ap.parse_args()
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(a) -> int:
+    rank, world, local = env_rank()
+    exe = REPO / "baseline" / "_ref" / "bin" / "p2p_bench"
+    if not exe.exists():
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/bin/p2p_bench missing (run baseline/build_ref.sh; the reference is a C/CUDA library, not pip-installable)"}))
+        return 0
+    env = dict(os.environ)
+    env["MPIACX_NFLAGS"] = str(max(4096, 4 * (a.steps + a.warmup) + 64))
+    port = os.environ.get("MASTER_PORT", "0")
+    outs = {}
+    for phase, extra in (("dev", []), ("e2e", ["--e2e"])):
+        env["ACX_JOBID"] = f"ref_{port}_{phase}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}"
+        cmd = [str(exe), "ring", "--bytes", str(a.bytes), "--steps", str(a.steps), "--warmup", str(max(3, a.warmup)), "--no-heap"] + extra
+        from mpi_acx_b200.utils.clocks import ClockSampler
+        with ClockSampler(local) as cs:
+            p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1800)
+        if p.returncode != 0:
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": f"reference run failed rc={p.returncode}: {(p.stderr or p.stdout)[-300:]!r}"}))
+            return 0
+        if rank == 0:
+            line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+            outs[phase] = json.loads(line)
+            outs[phase + "_clocks"] = cs.summary
+    if rank == 0:
+        d, e = outs["dev"], outs["e2e"]
+        print(json.dumps({
+            "impl": "reference", "metric": "ring_sendrecv_bandwidth", "value": d["gbs_total"], "unit": "GB/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(3, a.warmup), "ms_per_step": d["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bytes",
+            "data": "synthetic", "clocks": outs["dev_clocks"],
+            "e2e": {"value": e["gbs_total"], "unit": "GB/s", "h2d_bytes_per_step": e["h2d_bytes_per_step"], "d2h_bytes_per_step": e["d2h_bytes_per_step"], "ms_per_step": e["ms_per_step"]},
+            "gpu_launches": None,
+            "config": {"model": "ring Isend/Irecv_enqueue + Waitall_enqueue", "msg_bytes": a.bytes, "global_batch": a.bytes * world, "seq_len": None,
+                       "parallelism": f"p2p-ring{world}", "l2": "working set 2x msg_bytes > L2, no flush",
+                       "note": "unmodified NVIDIA/mpi-acx (CPU proxy) over the bundled mini-MPI shim (shm + CUDA-IPC cudaMemcpyAsync); cudaMalloc buffers"},
+        }))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+def run_acx(a) -> int:
+    import torch
+    rank, world, local = env_rank()
+    os.environ.setdefault("ACX_HEAP_BYTES", str(max(2 * a.bytes + (192 << 20), 512 << 20)))
+    os.environ.setdefault("ACX_WATCHDOG_MS", "60000")
+    import mpi_acx_b200 as acx
+    from mpi_acx_b200.utils.clocks import ClockSampler
+    if not torch.cuda.is_available():
+        print(json.dumps({"metric": "ring_sendrecv_bandwidth", "value": None, "error": "no CUDA device"}))
+        return 1
+    torch.cuda.set_device(local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    acx.init(local)
+    assert acx.size() == world and acx.rank() == rank, (acx.size(), world)
+    right, left = (rank + 1) % world, (rank - 1) % world
+    n = a.bytes
+    sbuf = acx.empty(n, torch.uint8)
+    rbuf = acx.empty(n, torch.uint8)
+    sbuf.copy_(torch.arange(n, device="cuda", dtype=torch.int32).to(torch.uint8) + rank)
+    rbuf.zero_()
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_in.fill_(rank + 1)
+    h_out = torch.empty(4096, dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not use_dist:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step(e2e: bool):
+        if e2e:
+            sbuf.copy_(h_in, non_blocking=True)
+        rr = acx.irecv(rbuf, left, 0)
+        rs = acx.isend(sbuf, right, 0)
+        acx.waitall_enqueue([rr, rs])
+        if e2e:
+            h_out.copy_(rbuf[:4096], non_blocking=True)
+
+    def timed(e2e: bool, steps: int, warmup: int):
+        for _ in range(warmup):
+            step(e2e)
+        barrier()
+        k0 = acx.stats()["kernels_launched"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as cs:
+            e0.record(stream)
+            for _ in range(steps):
+                step(e2e)
+            e1.record(stream)
+            torch.cuda.synchronize()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        return ms, acx.stats()["kernels_launched"] - k0, cs.summary
+
+    W = max(3, a.warmup)
+    ms, launches, clocks = timed(False, a.steps, W)
+    # correctness of what was timed: the received buffer must be the left neighbour's pattern
+    exp = (torch.arange(4096, device="cuda", dtype=torch.int32).to(torch.uint8) + left)
+    ok = bool(torch.equal(rbuf[:4096], exp)) and bool(torch.equal(rbuf[-4096:], (torch.arange(n - 4096, n, device="cuda", dtype=torch.int64).to(torch.uint8) + left)))
+    ms_e2e, _, _ = timed(True, a.steps, W)
+    ok_e2e = bool((h_out == (left + 1)).all())
+    gbs = world * n / ms / 1e6
+    gbs_e2e = world * n / ms_e2e / 1e6
+
+    extras = {}
+    if not a.no_extras:
+        # small-message latency through the same API (ring of 8 B and 4 KiB messages, host buffers avoided)
+        for nb in (8, 4096, 1 << 20):
+            s2, r2 = acx.empty(nb, torch.uint8), acx.empty(nb, torch.uint8)
+            def small():
+                q = [acx.irecv(r2, left, 9), acx.isend(s2, right, 9)]
+                acx.waitall_enqueue(q)
+            for _ in range(10):
+                small()
+            barrier()
+            iters = 200
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(iters):
+                small()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            extras[f"ring_step_us_{nb}B"] = round(max_over_ranks(e0.elapsed_time(e1)) / iters * 1e3, 3)
+            del s2, r2
+    out = {
+        "metric": "ring_sendrecv_bandwidth", "value": round(gbs, 3), "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": W,
+        "ms_per_step": round(ms, 6), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bytes", "data": "synthetic",
+        "impl": "acx-b200", "verified": ok and ok_e2e, "clocks": clocks,
+        "e2e": {"value": round(gbs_e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 4096, "ms_per_step": round(ms_e2e, 6)},
+        "gpu_launches": int(launches),
+        "config": {"model": "ring Isend/Irecv_enqueue + Waitall_enqueue", "msg_bytes": n, "global_batch": n * world, "seq_len": None,
+                   "parallelism": f"p2p-ring{world}", "l2": "working set 2x msg_bytes > L2, no flush", "buffers": "symmetric heap (zero-copy NVLink push/pull)",
+                   "nvlink_fraction_of_770GBs_per_gpu": round(gbs / world / 770.0, 3) if world > 1 else None},
+        "extra": extras,
+    }
+    if rank == 0:
+        print(json.dumps(out))
+        sys.stdout.flush()
+    del sbuf, rbuf
+    barrier()
+    acx.finalize()
+    if use_dist:
+        dist.destroy_process_group()
+    return 0 if (ok and ok_e2e) else 1
+
+
+if __name__ == "__main__":
+    args = parse()
+    sys.exit(run_reference(args) if args.impl == "reference" else run_acx(args))

@@ -1,0 +1,210 @@
+// acx-b200 device API: flag primitives (release/acquire at system scope across NVLink),
+// the partitioned-channel device handle, and Pready / Parrived in single-thread,
+// warp- and CTA-cooperative flavours.
+//
+// Reference behaviour being replaced (src/partitioned.cu:200-231): Pready = one
+// volatile int store to a host-pinned flag (no fence, defect D5), a CPU proxy then
+// calls MPI_Pready; Parrived = one volatile load of a host flag over PCIe.
+// Here: Pready moves the partition's bytes into the peer GPU's HBM (or the producer
+// already stored them there) and publishes a release flag in the peer's HBM; Parrived
+// is an acquire load from local HBM. No host involvement.
+#ifndef ACX_DEVICE_CUH
+#define ACX_DEVICE_CUH
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define ACX_HD __host__ __device__
+#define ACX_D __device__ __forceinline__
+#else
+#define ACX_HD
+#endif
+
+enum { ACX_PKIND_SEND = 1, ACX_PKIND_RECV = 2 };
+
+// Device-resident descriptor of one partitioned request (persistent channel endpoint).
+// MPIX_Prequest is a device pointer to this struct; kernels receive it by value.
+struct acx_pchan {
+    int32_t kind;            // ACX_PKIND_*
+    int32_t partitions;
+    uint64_t part_bytes;
+    char *user_buf;          // local user buffer (device-accessible: heap / device / mapped host)
+    char *land;              // SEND: peer-mapped landing buffer in the receiver's heap
+                             // RECV: local landing buffer (== user_buf when the user buffer is in the heap)
+    uint64_t *arrived;       // SEND: peer-mapped arrived[partitions] in the receiver's HBM; RECV: same array, local
+    uint64_t *local_flags;   // SEND: sent[partitions] (local);  RECV: copied[partitions] (copy-out claim/complete)
+    uint64_t *cts;           // SEND: local clear-to-send epoch, written remotely by the receiver at Start
+    uint64_t *epoch;         // local current epoch (Start bumps it)
+    int32_t zero_copy;       // SEND: user_buf needs no copy because producer wrote `land` directly (set by acx::remote_ptr users)
+    int32_t peer;
+    int32_t tag;
+    int32_t pad;
+};
+
+#ifdef __CUDACC__
+namespace acx {
+
+// ---- system-scope flag primitives ---------------------------------------------------
+ACX_D uint64_t ld_acquire_sys(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+ACX_D uint64_t ld_relaxed_sys(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+ACX_D void st_release_sys(uint64_t *p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+ACX_D void st_relaxed_sys(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+ACX_D void red_release_add_sys(uint64_t *p, uint64_t v) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+ACX_D uint64_t atom_add_acqrel_sys(uint64_t *p, uint64_t v) {
+    uint64_t old;
+    asm volatile("atom.acq_rel.sys.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
+ACX_D uint64_t atom_cas_acqrel_sys(uint64_t *p, uint64_t cmp, uint64_t val) {
+    uint64_t old;
+    asm volatile("atom.acq_rel.sys.global.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(cmp), "l"(val) : "memory");
+    return old;
+}
+// Spin until *p >= v (acquire). Exponential nanosleep backoff keeps the LSU quiet.
+ACX_D void wait_geq_sys(const uint64_t *p, uint64_t v) {
+    unsigned ns = 0;
+    while (ld_acquire_sys(p) < v) {
+        if (ns) __nanosleep(ns);
+        ns = ns < 256 ? ns * 2 + 20 : 256;
+    }
+}
+
+// ---- byte movers used by the single-thread / warp / CTA flavours ---------------------
+// Copy n bytes with the widest access both pointers allow; `tid`/`nthr` describe the
+// cooperating group (1 thread, a warp, or a CTA).
+ACX_D void copy_bytes(char *dst, const char *src, uint64_t n, unsigned tid, unsigned nthr) {
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+        uint64_t nv = n >> 4;
+        const int4 *s = (const int4 *)src;
+        int4 *d = (int4 *)dst;
+        uint64_t i = tid;
+        // 4 independent 16-B loads in flight per thread before the stores (MLP over NVLink)
+        for (; i + 3ull * nthr < nv; i += 4ull * nthr) {
+            int4 a = s[i], b = s[i + nthr], c = s[i + 2ull * nthr], e = s[i + 3ull * nthr];
+            d[i] = a; d[i + nthr] = b; d[i + 2ull * nthr] = c; d[i + 3ull * nthr] = e;
+        }
+        for (; i < nv; i += nthr) d[i] = s[i];
+        for (uint64_t b = (nv << 4) + tid; b < n; b += nthr) dst[b] = src[b];
+    } else if ((((uintptr_t)dst | (uintptr_t)src) & 3) == 0) {
+        uint64_t nv = n >> 2;
+        for (uint64_t i = tid; i < nv; i += nthr) ((int *)dst)[i] = ((const int *)src)[i];
+        for (uint64_t b = (nv << 2) + tid; b < n; b += nthr) dst[b] = src[b];
+    } else {
+        for (uint64_t b = tid; b < n; b += nthr) dst[b] = src[b];
+    }
+}
+
+// ---- partitioned device API ------------------------------------------------------------
+ACX_D const acx_pchan *pchan(const void *preq) { return (const acx_pchan *)preq; }
+
+// Pointer into the RECEIVER's memory where partition `p` of this send request lands.
+// A producer kernel may store its output tile there directly (zero-copy over NVLink)
+// and then call pready_signal(). Blocks until the receiver has started the round.
+ACX_D char *remote_partition_ptr(const void *preq, int p) {
+    const acx_pchan *ch = pchan(preq);
+    wait_geq_sys(ch->cts, ld_relaxed_sys(ch->epoch));
+    return ch->land + (uint64_t)p * ch->part_bytes;
+}
+
+// Flag-only Pready: the partition's bytes were already stored to remote_partition_ptr().
+// Call from ONE thread after the writers' stores are ordered before it (e.g. after
+// __syncthreads() in the producing CTA); the release makes them visible to the peer.
+ACX_D int pready_signal(int p, const void *preq) {
+    const acx_pchan *ch = pchan(preq);
+    uint64_t e = ld_relaxed_sys(ch->epoch);
+    __threadfence_system();
+    st_release_sys(ch->arrived + p, e);
+    st_release_sys(ch->local_flags + p, e);
+    return 0;
+}
+
+// Cooperative Pready: `nthr` threads (tid in [0,nthr)) of one warp or CTA copy the
+// partition from the local send buffer into the peer's landing buffer, then thread 0
+// publishes the flag. `sync` must be a barrier over exactly those threads.
+template <typename Sync>
+ACX_D int pready_group(int p, const void *preq, unsigned tid, unsigned nthr, Sync sync) {
+    const acx_pchan *ch = pchan(preq);
+    uint64_t e = ld_relaxed_sys(ch->epoch);
+    if (tid == 0) wait_geq_sys(ch->cts, e);
+    sync();
+    uint64_t off = (uint64_t)p * ch->part_bytes;
+    copy_bytes(ch->land + off, ch->user_buf + off, ch->part_bytes, tid, nthr);
+    __threadfence_system();
+    sync();
+    if (tid == 0) {
+        st_release_sys(ch->arrived + p, e);
+        st_release_sys(ch->local_flags + p, e);
+    }
+    return 0;
+}
+ACX_D int pready_warp(int p, const void *preq) {
+    return pready_group(p, preq, threadIdx.x & 31, 32, [] { __syncwarp(); });
+}
+ACX_D int pready_cta(int p, const void *preq) {
+    unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    return pready_group(p, preq, tid, blockDim.x * blockDim.y * blockDim.z, [] { __syncthreads(); });
+}
+
+// MPI-conformant single-thread Pready (what MPIX_Pready maps to on the device):
+// the calling thread moves the partition itself, then releases the flag.
+ACX_D int pready(int p, const void *preq) {
+    return pready_group(p, preq, 0, 1, [] {});
+}
+
+// Non-blocking arrival test (MPIX_Parrived on the device). When the user's receive
+// buffer is not in the symmetric heap the first poller to see the arrival copies the
+// partition out of the landing buffer (claimed with a CAS); others see flag=0 until
+// the copy is published.
+ACX_D int parrived(const void *preq, int p, int *flag) {
+    const acx_pchan *ch = pchan(preq);
+    uint64_t e = ld_relaxed_sys(ch->epoch);
+    if (ld_acquire_sys(ch->arrived + p) < e) { *flag = 0; return 0; }
+    if (ch->land == ch->user_buf) { *flag = 1; return 0; }
+    uint64_t done = 2 * e, claimed = 2 * e - 1;
+    uint64_t c = ld_acquire_sys(ch->local_flags + p);
+    if (c == done) { *flag = 1; return 0; }
+    if (c == claimed) { *flag = 0; return 0; }
+    if (atom_cas_acqrel_sys(ch->local_flags + p, c, claimed) != c) { *flag = 0; return 0; }
+    uint64_t off = (uint64_t)p * ch->part_bytes;
+    copy_bytes(ch->user_buf + off, ch->land + off, ch->part_bytes, 0, 1);
+    __threadfence_system();
+    st_release_sys(ch->local_flags + p, done);
+    *flag = 1;
+    return 0;
+}
+
+// Blocking convenience: spin (with backoff) until partition p has arrived. One thread.
+ACX_D void wait_arrived(const void *preq, int p) {
+    int f = 0;
+    unsigned ns = 0;
+    for (;;) {
+        parrived(preq, p, &f);
+        if (f) return;
+        if (ns) __nanosleep(ns);
+        ns = ns < 256 ? ns * 2 + 20 : 256;
+    }
+}
+
+// Local pointer to where partition p's data is readable after arrival (RECV side).
+ACX_D const char *local_partition_ptr(const void *preq, int p) {
+    const acx_pchan *ch = pchan(preq);
+    return ch->land + (uint64_t)p * ch->part_bytes;
+}
+
+}  // namespace acx
+#endif  // __CUDACC__
+#endif

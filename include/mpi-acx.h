@@ -1,0 +1,138 @@
+/* acx-b200 public API.
+ *
+ * Same entry points and signatures as NVIDIA/mpi-acx (reference include/mpi-acx.h:42-104):
+ * stream/graph-triggered MPIX_Isend/Irecv/Wait/Waitall_enqueue and kernel-triggered
+ * partitioned MPIX_Psend_init/Precv_init/Start/Pready/Parrived — but implemented
+ * GPU-natively: payload and completion flags move GPU->GPU over NVLink from inside
+ * CUDA kernels; there is no CPU proxy thread and no MPI call on any data path.
+ *
+ * Build: include <mpi.h> (a real MPI, or the bundled mini-MPI in include/mpi.h) first.
+ * Device functions are header-inline (no relocatable-device-code link step needed,
+ * unlike the reference, Makefile:8).
+ */
+#ifndef MPI_ACX_H
+#define MPI_ACX_H
+
+#include <mpi.h>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPIX_ACX_B200 1
+#define MPIX_ACX_VERSION_MAJOR 0
+#define MPIX_ACX_VERSION_MINOR 1
+
+typedef void *MPIX_Request;
+typedef void *MPIX_Prequest;
+
+#define MPIX_REQUEST_NULL  NULL
+#define MPIX_PREQUEST_NULL NULL
+
+int MPIX_Init(void);
+int MPIX_Finalize(void);
+
+/* ENQUEUED OPERATIONS ********************************************************/
+
+enum {
+    MPIX_QUEUE_CUDA_STREAM,  /* queue is cudaStream_t*  (the stream may be capturing)   */
+    MPIX_QUEUE_CUDA_GRAPH    /* queue is cudaGraph_t*   (OUT: a new graph with the op)  */
+};
+
+int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datatype, int dest,
+                       int tag, MPI_Comm comm, MPIX_Request *request, int qtype, void *queue);
+
+int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, int source,
+                       int tag, MPI_Comm comm, MPIX_Request *request, int qtype, void *queue);
+
+int MPIX_Wait_enqueue(MPIX_Request *req, MPI_Status *status, int qtype, void *queue);
+int MPIX_Waitall_enqueue(int count, MPIX_Request *reqs, MPI_Status *statuses, int qtype, void *queue);
+
+/* PARTITIONED OPERATIONS *****************************************************/
+
+int MPIX_Psend_init(const void *buf, int partitions, MPI_Count count,
+                    MPI_Datatype datatype, int dest, int tag, MPI_Comm comm,
+                    MPI_Info info, MPIX_Request *request);
+
+int MPIX_Precv_init(void *buf, int partitions, MPI_Count count,
+                    MPI_Datatype datatype, int source, int tag, MPI_Comm comm,
+                    MPI_Info info, MPIX_Request *request);
+
+int MPIX_Prequest_create(MPIX_Request request, MPIX_Prequest *prequest);
+int MPIX_Prequest_free(MPIX_Prequest *request);
+
+/* HELPERS ********************************************************************/
+
+int MPIX_Start(MPIX_Request *request);
+int MPIX_Startall(int count, MPIX_Request *request);
+
+int MPIX_Wait(MPIX_Request *req, MPI_Status *status);
+int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses);
+
+int MPIX_Request_free(MPIX_Request *request);
+
+/* EXTENSIONS (not in the reference) ******************************************/
+
+/* Symmetric communication heap: device memory that every peer GPU has mapped at init.
+ * Buffers allocated here are sent/received zero-copy (the sending kernel stores
+ * straight into the peer's HBM). Any other buffer (cudaMalloc, host) still works
+ * but is staged through a bounce buffer in this heap. */
+int MPIX_Alloc_mem(size_t bytes, MPI_Info info, void *baseptr /* void** */);
+int MPIX_Free_mem(void *base);
+
+/* Host-side versions of the __host__ __device__ pair below (usable from C). */
+int MPIX_Pready_host(int partition, MPIX_Request *request);
+int MPIX_Parrived_host(MPIX_Request *request, int partition, int *flag);
+
+/* Stream-ordered partitioned round control (the reference only has host Start/Wait):
+ * enqueue the Start / the completion wait of a partitioned request on a stream. */
+int MPIX_Start_enqueue(MPIX_Request *request, int qtype, void *queue);
+int MPIX_Pwait_enqueue(MPIX_Request *request, int qtype, void *queue);
+
+/* Runtime introspection / observability. */
+typedef struct MPIX_Acx_stats {
+    unsigned long long sends_enqueued, recvs_enqueued, waits_enqueued;
+    unsigned long long bytes_sent, bytes_received;
+    unsigned long long eager_msgs, rendezvous_msgs, bounce_copies;
+    unsigned long long kernels_launched, graph_nodes_added;
+    unsigned long long slots_in_use, slots_high_water;
+    unsigned long long heap_bytes_in_use, heap_bytes_high_water;
+} MPIX_Acx_stats;
+int MPIX_Get_stats(MPIX_Acx_stats *stats);
+/* 1 when the GPU transport is active, 0 when running on the host (no-GPU) transport. */
+int MPIX_Is_device_transport(void);
+/* Dump the device-side trace ring (ACX_TRACE=1) as JSON lines to `path`. */
+int MPIX_Trace_dump(const char *path);
+
+#ifdef __cplusplus
+}
+#endif
+
+/* DEVICE FUNCTIONS FOR PARTITIONED OPERATIONS ********************************/
+
+#ifdef __CUDACC__
+#include "acx_device.cuh"
+/* Request argument is void* so host and device share one signature (as in the
+ * reference, include/mpi-acx.h:96-103):
+ *   __host__   -- MPIX_Request *request
+ *   __device__ -- MPIX_Prequest  request (the handle value itself)
+ */
+static __host__ __device__ __forceinline__ int MPIX_Pready(int partition, void *request) {
+#ifdef __CUDA_ARCH__
+    return acx::pready(partition, request);
+#else
+    return MPIX_Pready_host(partition, (MPIX_Request *)request);
+#endif
+}
+static __host__ __device__ __forceinline__ int MPIX_Parrived(void *request, int partition, int *flag) {
+#ifdef __CUDA_ARCH__
+    return acx::parrived(request, partition, flag);
+#else
+    return MPIX_Parrived_host((MPIX_Request *)request, partition, flag);
+#endif
+}
+#endif /* __CUDACC__ */
+
+#endif

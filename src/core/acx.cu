@@ -1,0 +1,1229 @@
+// acx-b200 runtime: init/finalize, windows + CUDA-IPC bootstrap, allocators, and the
+// host front-ends of the whole MPIX_* API (enqueue / wait / graph / partitioned).
+//
+// Behavioural contract mirrors NVIDIA/mpi-acx (reference src/init.cpp, src/sendrecv.cu,
+// src/partitioned.cu, src/triggered.cpp); the mechanism does not: see internal.h.
+#include <mpi.h>
+#include "../../include/mpi-acx.h"
+#include "internal.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <thread>
+#include <unistd.h>
+
+AcxState *g_acx = nullptr;
+
+using namespace acxk;
+
+// =======================================================================================
+// small utilities
+// =======================================================================================
+int acx_env_int(const char *name, const char *alt, long dflt, long *out) {
+    const char *v = getenv(name);
+    if ((!v || !*v) && alt) v = getenv(alt);
+    if (!v || !*v) { *out = dflt; return 0; }
+    char *end = nullptr;
+    long x = strtol(v, &end, 0);
+    if (end && (*end == 'k' || *end == 'K')) x <<= 10;
+    else if (end && (*end == 'm' || *end == 'M')) x <<= 20;
+    else if (end && (*end == 'g' || *end == 'G')) x <<= 30;
+    *out = x;
+    return 1;
+}
+
+static uint64_t *g_diag = nullptr, *g_diag_d = nullptr;      // watchdog diagnostics (pinned)
+static uint64_t *g_trace_cursor = nullptr;                   // device
+static std::vector<int> g_deferred_slots;                    // freed by graph user-object destructors
+static std::mutex g_deferred_mu;
+
+static Watchdog make_wd() {
+    Watchdog w;
+    w.budget_ns = g_acx->watchdog_ms > 0 ? (uint64_t)g_acx->watchdog_ms * 1000000ull : 0;
+    w.diag = g_diag_d;
+    return w;
+}
+static TraceCtx make_tr() {
+    TraceCtx t{nullptr, 0, nullptr};
+    if (g_acx->trace) {
+        t.ring = (acx_trace_rec *)(g_acx->ctrl + g_acx->geom.off_trace);
+        t.mask = g_acx->geom.ntrace - 1;
+        t.cursor = g_trace_cursor;
+    }
+    return t;
+}
+
+static void report_watchdog() {
+    if (g_diag && g_diag[0]) {
+        const char *what = "unknown";
+        switch (g_diag[0]) {
+            case 0x5e01: what = "send trigger: ring slot never freed (receiver not consuming; > ACX_DEPTH unconsumed sends on one channel?)"; break;
+            case 0x5e02: what = "recv trigger: own ring slot still in use (> ACX_DEPTH outstanding receives on one channel)"; break;
+            case 0x5e03: what = "wait(send): rendezvous never completed (no matching receive)"; break;
+            case 0x5e04: what = "wait(recv): message never arrived (no matching send)"; break;
+            case 0x5e05: what = "host wait: operation was never triggered on its stream/graph"; break;
+            case 0x5e06: what = "partitioned wait(send): a partition was never marked ready"; break;
+            case 0x5e07: what = "partitioned wait(recv): a partition never arrived"; break;
+            case 0x5e08: what = "partitioned wait(recv): a device poller never finished its copy-out"; break;
+        }
+        ACX_ERR("WATCHDOG (code 0x%llx, a=0x%llx b=0x%llx): %s", (unsigned long long)g_diag[0], (unsigned long long)g_diag[1],
+                (unsigned long long)g_diag[2], what);
+    }
+}
+
+#define ACX_CUDA_WD(stmt)                                                  \
+    do {                                                                   \
+        cudaError_t _e = (stmt);                                           \
+        if (_e != cudaSuccess) {                                           \
+            report_watchdog();                                             \
+            ACX_ERR("%s failed: %s", #stmt, cudaGetErrorString(_e));       \
+            return MPI_ERR_OTHER;                                          \
+        }                                                                  \
+    } while (0)
+
+// =======================================================================================
+// allocators
+// =======================================================================================
+static void release_request_resources(AcxRequest *r) {
+    if (r->bounce_off >= 0) { acx_heap_free(r->bounce_off); r->bounce_off = -1; }
+}
+
+void acx_slot_free(int slot) {
+    // caller holds g_acx->mu
+    AcxRequest *r = g_acx->slot_req[slot];
+    if (r) {
+        release_request_resources(r);
+        r->magic = 0;
+        delete r;
+    }
+    g_acx->slot_req[slot] = nullptr;
+    g_acx->slot_busy[slot] = 0;
+    g_acx->hstat[slot].retired = 0;
+    g_acx->free_slots.push_back(slot);
+    g_acx->slots_in_use--;
+}
+
+void acx_reclaim_retired() {
+    // caller holds g_acx->mu. Stream-mode slots whose wait kernel has run mark themselves retired
+    // in pinned host memory; graph-owned slots come back through the deferred list.
+    {
+        std::lock_guard<std::mutex> lk(g_deferred_mu);
+        for (int s : g_deferred_slots) if (g_acx->slot_busy[s]) acx_slot_free(s);
+        g_deferred_slots.clear();
+    }
+    for (int s = 0; s < g_acx->geom.nops; s++)
+        if (g_acx->slot_busy[s] == 3 && g_acx->hstat[s].retired) acx_slot_free(s);
+}
+
+int acx_slot_alloc(AcxRequest *r, bool graph) {
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    if (g_acx->free_slots.empty()) acx_reclaim_retired();
+    if (g_acx->free_slots.empty()) {
+        // Waited-on stream ops retire asynchronously; give in-flight waits a moment.
+        for (int i = 0; i < 2000 && g_acx->free_slots.empty(); i++) { usleep(100); acx_reclaim_retired(); }
+        if (g_acx->free_slots.empty()) {
+            ACX_ERR("out of request slots (%d); raise ACX_NFLAGS / MPIACX_NFLAGS", g_acx->geom.nops);
+            return -1;
+        }
+    }
+    int s = g_acx->free_slots.back();
+    g_acx->free_slots.pop_back();
+    g_acx->slot_busy[s] = graph ? 2 : 1;
+    g_acx->slot_req[s] = r;
+    g_acx->hstat[s].retired = 0;
+    g_acx->slots_in_use++;
+    unsigned long long hw = g_acx->st.slots_hw.load();
+    if ((unsigned long long)g_acx->slots_in_use > hw) g_acx->st.slots_hw.store(g_acx->slots_in_use);
+    return s;
+}
+
+int64_t acx_heap_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    bytes = (bytes + 255) & ~(size_t)255;
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        for (auto it = g_acx->heap_free.begin(); it != g_acx->heap_free.end(); ++it) {
+            if (it->second >= bytes) {
+                size_t off = it->first, sz = it->second;
+                g_acx->heap_free.erase(it);
+                if (sz > bytes) g_acx->heap_free[off + bytes] = sz - bytes;
+                g_acx->heap_used[off] = bytes;
+                g_acx->heap_in_use += bytes;
+                if (g_acx->heap_in_use > g_acx->st.heap_hw.load()) g_acx->st.heap_hw.store(g_acx->heap_in_use);
+                return (int64_t)off;
+            }
+        }
+        acx_reclaim_retired();  // bounce buffers of retired requests come back here
+    }
+    ACX_ERR("symmetric heap exhausted (%zu bytes requested, %zu in use of %zu); raise ACX_HEAP_BYTES", bytes, g_acx->heap_in_use,
+            g_acx->heap_bytes);
+    return -1;
+}
+
+void acx_heap_free(int64_t off) {
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    auto it = g_acx->heap_used.find((size_t)off);
+    if (it != g_acx->heap_used.end()) {
+        size_t o = it->first, sz = it->second;
+        g_acx->heap_used.erase(it);
+        g_acx->heap_in_use -= sz;
+        auto nx = g_acx->heap_free.lower_bound(o);
+        if (nx != g_acx->heap_free.end() && o + sz == nx->first) { sz += nx->second; nx = g_acx->heap_free.erase(nx); }
+        if (nx != g_acx->heap_free.begin()) {
+            auto pv = std::prev(nx);
+            if (pv->first + pv->second == o) { pv->second += sz; sz = 0; }
+        }
+        if (sz) g_acx->heap_free[o] = sz;
+    }
+}
+
+int64_t acx_heap_offset_of(const void *p) {
+    const char *c = (const char *)p;
+    if (g_acx->heap && c >= g_acx->heap && c < g_acx->heap + g_acx->heap_bytes) return c - g_acx->heap;
+    return -1;
+}
+
+uint32_t acx_pflags_alloc(uint32_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    if (g_acx->pflags_next + n > g_acx->geom.npflags) { ACX_ERR("out of partition flags (%u); raise ACX_NPFLAGS", g_acx->geom.npflags); return UINT32_MAX; }
+    uint32_t r = g_acx->pflags_next;
+    g_acx->pflags_next += n;
+    return r;
+}
+
+int acx_device_alias(const void *p, size_t bytes, char **out) {
+    if (!p || bytes == 0) { *out = (char *)p; return 0; }
+    if (acx_heap_offset_of(p) >= 0) { *out = (char *)p; return 0; }
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); a.type = cudaMemoryTypeUnregistered; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) { *out = (char *)p; return 0; }
+    if (a.type == cudaMemoryTypeHost) { *out = (char *)a.devicePointer; return 0; }
+    // pageable host memory: pin + map the covering pages (cached)
+    const uintptr_t page = 4096;
+    uintptr_t lo = (uintptr_t)p & ~(page - 1), hi = ((uintptr_t)p + bytes + page - 1) & ~(page - 1);
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    for (auto &r : g_acx->host_regs)
+        if (lo >= r.lo && hi <= r.hi) { *out = r.dptr + ((uintptr_t)p - r.lo); return 0; }
+    // merge with overlapping/adjacent registrations
+    for (size_t i = 0; i < g_acx->host_regs.size();) {
+        AcxHostReg &r = g_acx->host_regs[i];
+        if (r.lo <= hi && lo <= r.hi) {
+            cudaHostUnregister((void *)r.lo);
+            lo = std::min(lo, r.lo); hi = std::max(hi, r.hi);
+            g_acx->host_regs.erase(g_acx->host_regs.begin() + i);
+        } else i++;
+    }
+    e = cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (g_acx->pageable_access) { *out = (char *)p; return 0; }  // HMM/ATS: the GPU can touch it as is
+        ACX_ERR("cannot make host buffer %p (+%zu) device-accessible: %s", p, bytes, cudaGetErrorString(e));
+        return MPI_ERR_BUFFER;
+    }
+    char *d = nullptr;
+    e = cudaHostGetDevicePointer((void **)&d, (void *)lo, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); cudaHostUnregister((void *)lo); ACX_ERR("cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); return MPI_ERR_BUFFER; }
+    g_acx->host_regs.push_back({lo, hi, d});
+    *out = d + ((uintptr_t)p - lo);
+    return 0;
+}
+
+int acx_comm_ctx(MPI_Comm comm, int *ctx) {
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    for (size_t i = 0; i < g_acx->comms.size(); i++) if (g_acx->comms[i] == comm) { *ctx = (int)i; return 0; }
+    int sz = 0;
+    if (MPI_Comm_size(comm, &sz) != MPI_SUCCESS || sz != g_acx->size) {
+        ACX_ERR("only communicators spanning all of MPI_COMM_WORLD (in world rank order) are supported");
+        return MPI_ERR_COMM;
+    }
+    g_acx->comms.push_back(comm);
+    *ctx = (int)g_acx->comms.size() - 1;
+    return 0;
+}
+
+// =======================================================================================
+// init / finalize
+// =======================================================================================
+struct Bootstrap {
+    cudaIpcMemHandle_t ctrl, heap;
+    int dev, pid;
+    unsigned long long heap_bytes, ctrl_bytes;
+    char host[64];
+};
+
+static void make_geom(acx_geom &g, int n) {
+    long v;
+    g.nranks = n;
+    acx_env_int("ACX_NCHAN", nullptr, 16, &v); g.nchan = (int)std::max(1L, v);
+    acx_env_int("ACX_DEPTH", nullptr, 32, &v); g.depth = (int)std::max(2L, v);
+    acx_env_int("ACX_NFLAGS", "MPIACX_NFLAGS", 4096, &v); g.nops = (int)std::max(8L, v);
+    acx_env_int("ACX_EAGER_MAX", nullptr, 8192, &v); g.eager_max = (uint32_t)((std::max(16L, v) + 15) & ~15L);
+    acx_env_int("ACX_NPFLAGS", nullptr, 1 << 16, &v); g.npflags = (uint32_t)v;
+    acx_env_int("ACX_TRACE_RECORDS", nullptr, 1 << 14, &v);
+    uint32_t nt = 1; while (nt < (uint32_t)v) nt <<= 1; g.ntrace = nt;
+    auto up = [](uint64_t x) { return (x + 255) & ~255ull; };
+    uint64_t o = 0;
+    uint64_t nslots = (uint64_t)n * g.nchan * g.depth;
+    g.off_entries = o;  o = up(o + nslots * sizeof(acx_entry));
+    g.off_sack = o;     o = up(o + nslots * sizeof(acx_sack));
+    g.off_send_seq = o; o = up(o + (uint64_t)n * g.nchan * 8);
+    g.off_recv_seq = o; o = up(o + (uint64_t)n * g.nchan * 8);
+    g.off_ops = o;      o = up(o + (uint64_t)g.nops * sizeof(acx_op));
+    g.off_pflags = o;   o = up(o + (uint64_t)g.npflags * 8);
+    g.off_trace = o;    o = up(o + (uint64_t)g.ntrace * sizeof(acx_trace_rec));
+    g.off_eager = o;    o = up(o + nslots * g.eager_max);
+    g.bytes = o;
+}
+
+extern "C" int MPIX_Init(void) {
+    int initialized = 0, finalized = 0, thread_level = 0;
+    MPI_Initialized(&initialized);
+    MPI_Finalized(&finalized);
+    if (!initialized || finalized) {
+        fprintf(stderr, "[acx] MPIX_Init: MPI is not initialized (%d) or already finalized (%d)\n", initialized, finalized);
+        return 1;
+    }
+    MPI_Query_thread(&thread_level);
+    if (g_acx && g_acx->initialized) return 0;
+    g_acx = new AcxState();
+    MPI_Comm_rank(MPI_COMM_WORLD, &g_acx->rank);
+    MPI_Comm_size(MPI_COMM_WORLD, &g_acx->size);
+    long v;
+    acx_env_int("ACX_VERBOSE", nullptr, 0, &v); g_acx->verbose = (int)v;
+    acx_env_int("ACX_TRACE", nullptr, 0, &v); g_acx->trace = v != 0;
+    acx_env_int("ACX_WATCHDOG_MS", nullptr, 0, &v); g_acx->watchdog_ms = v;
+    acx_env_int("ACX_MOVER_MAX_CTAS", nullptr, 0, &v); g_acx->mover_max_ctas = (int)v;
+    acx_env_int("ACX_MOVER_CTA_BYTES", nullptr, 64 << 10, &v); g_acx->mover_min_cta_bytes = (size_t)std::max(4096L, v);
+    g_acx->comms.push_back(MPI_COMM_WORLD);
+    if (MPI_Comm_dup(MPI_COMM_WORLD, &g_acx->icomm) != MPI_SUCCESS) { ACX_ERR("MPI_Comm_dup failed"); return 1; }
+
+    int ndev = 0;
+    long force_host = 0;
+    acx_env_int("ACX_FORCE_HOST", nullptr, 0, &force_host);
+    if (force_host || cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        // All ranks must agree on the transport.
+        int have = 0, all = 0;
+        MPI_Allreduce(&have, &all, 1, MPI_INT, MPI_MIN, MPI_COMM_WORLD);
+        g_acx->device = false;
+        g_acx->initialized = true;
+        ACX_LOG(1, "no CUDA device: host transport (MPI p2p, ops trigger at enqueue time)");
+        return 0;
+    }
+    {
+        int have = 1, all = 0;
+        MPI_Allreduce(&have, &all, 1, MPI_INT, MPI_MIN, MPI_COMM_WORLD);
+        if (!all) { g_acx->device = false; g_acx->initialized = true; return 0; }
+    }
+    long want_dev;
+    if (acx_env_int("ACX_DEVICE", nullptr, -1, &want_dev) && want_dev >= 0) {
+        if (cudaSetDevice((int)(want_dev % ndev)) != cudaSuccess) { ACX_ERR("cudaSetDevice(%ld) failed", want_dev); return 1; }
+    }
+    if (cudaGetDevice(&g_acx->dev) != cudaSuccess) { ACX_ERR("cudaGetDevice failed"); return 1; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, g_acx->dev) != cudaSuccess) { ACX_ERR("cudaGetDeviceProperties failed"); return 1; }
+    g_acx->sm_count = prop.multiProcessorCount;
+    cudaDeviceGetAttribute(&g_acx->pageable_access, cudaDevAttrPageableMemoryAccess, g_acx->dev);
+
+    make_geom(g_acx->geom, g_acx->size);
+    acx_env_int("ACX_HEAP_BYTES", nullptr, 512L << 20, &v);
+    g_acx->heap_bytes = ((size_t)v + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&g_acx->ctrl, g_acx->geom.bytes)) != cudaSuccess || (e = cudaMalloc((void **)&g_acx->heap, g_acx->heap_bytes)) != cudaSuccess) {
+        ACX_ERR("cudaMalloc of windows (%llu + %zu bytes) failed: %s", (unsigned long long)g_acx->geom.bytes, g_acx->heap_bytes, cudaGetErrorString(e));
+        return 1;
+    }
+    cudaMemset(g_acx->ctrl, 0, g_acx->geom.bytes);
+    cudaMalloc((void **)&g_trace_cursor, 8);
+    cudaMemset(g_trace_cursor, 0, 8);
+    cudaDeviceSynchronize();
+    g_acx->heap_free[0] = g_acx->heap_bytes;
+
+    // ---- exchange IPC handles, map every peer's windows ----
+    Bootstrap mine;
+    memset(&mine, 0, sizeof mine);
+    if (g_acx->size > 1) {
+        if ((e = cudaIpcGetMemHandle(&mine.ctrl, g_acx->ctrl)) != cudaSuccess || (e = cudaIpcGetMemHandle(&mine.heap, g_acx->heap)) != cudaSuccess) {
+            ACX_ERR("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+            return 1;
+        }
+    }
+    mine.dev = g_acx->dev; mine.pid = (int)getpid(); mine.heap_bytes = g_acx->heap_bytes; mine.ctrl_bytes = g_acx->geom.bytes;
+    gethostname(mine.host, sizeof mine.host - 1);
+    std::vector<Bootstrap> all(g_acx->size);
+    MPI_Allgather(&mine, (int)sizeof(Bootstrap), MPI_BYTE, all.data(), (int)sizeof(Bootstrap), MPI_BYTE, MPI_COMM_WORLD);
+    g_acx->peer_ctrl.assign(g_acx->size, nullptr);
+    g_acx->peer_heap.assign(g_acx->size, nullptr);
+    for (int p = 0; p < g_acx->size; p++) {
+        if (p == g_acx->rank) { g_acx->peer_ctrl[p] = g_acx->ctrl; g_acx->peer_heap[p] = g_acx->heap; continue; }
+        if (all[p].heap_bytes != g_acx->heap_bytes || all[p].ctrl_bytes != g_acx->geom.bytes) { ACX_ERR("rank %d has a different window geometry (env mismatch)", p); return 1; }
+        if (strncmp(all[p].host, mine.host, sizeof mine.host) != 0) { ACX_ERR("rank %d is on another node (%s); multi-node is not supported", p, all[p].host); return 1; }
+        if (all[p].dev != g_acx->dev) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, g_acx->dev, all[p].dev);
+            if (!can) { ACX_ERR("device %d cannot access peer device %d", g_acx->dev, all[p].dev); return 1; }
+        }
+        if ((e = cudaIpcOpenMemHandle((void **)&g_acx->peer_ctrl[p], all[p].ctrl, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess ||
+            (e = cudaIpcOpenMemHandle((void **)&g_acx->peer_heap[p], all[p].heap, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) {
+            ACX_ERR("cudaIpcOpenMemHandle(rank %d) failed: %s", p, cudaGetErrorString(e));
+            return 1;
+        }
+    }
+    // ---- host-side tables ----
+    if ((e = cudaHostAlloc((void **)&g_acx->hstat, sizeof(acx_host_status) * g_acx->geom.nops, cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostAlloc((void **)&g_diag, 64, cudaHostAllocMapped)) != cudaSuccess) {
+        ACX_ERR("cudaHostAlloc failed: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    memset(g_acx->hstat, 0, sizeof(acx_host_status) * g_acx->geom.nops);
+    memset(g_diag, 0, 64);
+    cudaHostGetDevicePointer((void **)&g_acx->hstat_d, g_acx->hstat, 0);
+    cudaHostGetDevicePointer((void **)&g_diag_d, g_diag, 0);
+    cudaStreamCreateWithFlags(&g_acx->istream, cudaStreamNonBlocking);
+    g_acx->slot_busy.assign(g_acx->geom.nops, 0);
+    g_acx->slot_req.assign(g_acx->geom.nops, nullptr);
+    for (int s = g_acx->geom.nops - 1; s >= 0; s--) g_acx->free_slots.push_back(s);
+    g_acx->recv_outstanding.assign(g_acx->size, std::vector<int>(g_acx->geom.nchan, 0));
+    g_acx->device = true;
+    g_acx->initialized = true;
+    MPI_Barrier(MPI_COMM_WORLD);
+    ACX_LOG(1, "device transport up: dev %d (%s, %d SMs), %d ranks, ctrl %.1f MiB, heap %.0f MiB, eager<=%u, depth %d, chans %d", g_acx->dev, prop.name,
+            g_acx->sm_count, g_acx->size, g_acx->geom.bytes / 1048576.0, g_acx->heap_bytes / 1048576.0, g_acx->geom.eager_max, g_acx->geom.depth, g_acx->geom.nchan);
+    return 0;
+}
+
+extern "C" int MPIX_Finalize(void) {
+    if (!g_acx || !g_acx->initialized) return 1;
+    int err = 0;
+    if (g_acx->device) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { report_watchdog(); ACX_ERR("device error at finalize: %s", cudaGetErrorString(e)); err = 1; }
+        MPI_Barrier(MPI_COMM_WORLD);  // nobody unmaps while a peer may still store into us
+        {
+            std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+            acx_reclaim_retired();
+            int leaked = 0;
+            for (int s = 0; s < g_acx->geom.nops; s++) if (g_acx->slot_busy[s] == 1 || g_acx->slot_busy[s] == 2) leaked++;
+            if (leaked) printf("Warning: %d request slot(s) still in use at MPIX_Finalize (un-waited operations or live graphs)\n", leaked);
+        }
+        if (g_acx->trace) {
+            char path[256];
+            snprintf(path, sizeof path, "%s/acx_trace_rank%d.jsonl", getenv("ACX_TRACE_DIR") ? getenv("ACX_TRACE_DIR") : ".", g_acx->rank);
+            MPIX_Trace_dump(path);
+        }
+        if (g_acx->verbose >= 1) {
+            MPIX_Acx_stats s;
+            MPIX_Get_stats(&s);
+            fprintf(stderr, "[acx %d] stats: sends %llu recvs %llu waits %llu | bytes tx %llu rx(cap) %llu | eager %llu rndv %llu bounce %llu | kernels %llu graph-nodes %llu | slots hw %llu heap hw %llu\n",
+                    g_acx->rank, s.sends_enqueued, s.recvs_enqueued, s.waits_enqueued, s.bytes_sent, s.bytes_received, s.eager_msgs, s.rendezvous_msgs, s.bounce_copies,
+                    s.kernels_launched, s.graph_nodes_added, s.slots_high_water, s.heap_bytes_high_water);
+        }
+        for (int p = 0; p < g_acx->size; p++) {
+            if (p == g_acx->rank) continue;
+            if (g_acx->peer_ctrl[p]) cudaIpcCloseMemHandle(g_acx->peer_ctrl[p]);
+            if (g_acx->peer_heap[p]) cudaIpcCloseMemHandle(g_acx->peer_heap[p]);
+        }
+        MPI_Barrier(MPI_COMM_WORLD);
+        for (auto &r : g_acx->host_regs) cudaHostUnregister((void *)r.lo);
+        cudaStreamDestroy(g_acx->istream);
+        cudaFreeHost(g_acx->hstat);
+        cudaFreeHost(g_diag);
+        cudaFree(g_trace_cursor);
+        cudaFree(g_acx->ctrl);
+        cudaFree(g_acx->heap);
+        g_diag = g_diag_d = nullptr;
+    }
+    MPI_Comm_free(&g_acx->icomm);
+    delete g_acx;
+    g_acx = nullptr;
+    return err;
+}
+
+extern "C" int MPIX_Is_device_transport(void) { return g_acx && g_acx->device ? 1 : 0; }
+
+extern "C" int MPIX_Get_stats(MPIX_Acx_stats *s) {
+    if (!g_acx || !s) return MPI_ERR_ARG;
+    s->sends_enqueued = g_acx->st.sends; s->recvs_enqueued = g_acx->st.recvs; s->waits_enqueued = g_acx->st.waits;
+    s->bytes_sent = g_acx->st.bytes_sent; s->bytes_received = g_acx->st.bytes_recv;
+    s->eager_msgs = g_acx->st.eager; s->rendezvous_msgs = g_acx->st.rndv; s->bounce_copies = g_acx->st.bounce;
+    s->kernels_launched = g_acx->st.kernels; s->graph_nodes_added = g_acx->st.graph_nodes;
+    s->slots_in_use = g_acx->slots_in_use; s->slots_high_water = g_acx->st.slots_hw;
+    s->heap_bytes_in_use = g_acx->heap_in_use; s->heap_bytes_high_water = g_acx->st.heap_hw;
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Trace_dump(const char *path) {
+    if (!g_acx || !g_acx->device || !g_acx->trace) return MPI_ERR_OTHER;
+    uint64_t cur = 0;
+    cudaMemcpy(&cur, g_trace_cursor, 8, cudaMemcpyDeviceToHost);
+    uint32_t n = g_acx->geom.ntrace;
+    std::vector<acx_trace_rec> recs(n);
+    cudaMemcpy(recs.data(), g_acx->ctrl + g_acx->geom.off_trace, sizeof(acx_trace_rec) * n, cudaMemcpyDeviceToHost);
+    FILE *f = fopen(path, "w");
+    if (!f) return MPI_ERR_OTHER;
+    static const char *names[] = {"?", "send_trigger", "recv_trigger", "move_begin", "move_end", "wait_begin", "wait_end"};
+    uint64_t first = cur > n ? cur - n : 0;
+    for (uint64_t i = first; i < cur; i++) {
+        const acx_trace_rec &r = recs[i & (n - 1)];
+        fprintf(f, "{\"rank\": %d, \"t_ns\": %llu, \"ev\": \"%s\", \"peer\": %u, \"a\": %llu, \"b\": %llu}\n", g_acx->rank, (unsigned long long)r.t_ns,
+                r.ev < 7 ? names[r.ev] : "?", r.peer, (unsigned long long)r.a, (unsigned long long)r.b);
+    }
+    fclose(f);
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Alloc_mem(size_t bytes, MPI_Info, void *baseptr) {
+    if (!g_acx || !g_acx->initialized) return MPI_ERR_OTHER;
+    if (!g_acx->device) {
+        void *p = malloc(bytes ? bytes : 1);
+        *(void **)baseptr = p;
+        return p ? MPI_SUCCESS : MPI_ERR_OTHER;
+    }
+    int64_t off = acx_heap_alloc(bytes);
+    if (off < 0) return MPI_ERR_OTHER;
+    *(void **)baseptr = g_acx->heap + off;
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Free_mem(void *base) {
+    if (!g_acx || !g_acx->initialized) return MPI_ERR_OTHER;
+    if (!g_acx->device) { free(base); return MPI_SUCCESS; }
+    int64_t off = acx_heap_offset_of(base);
+    if (off < 0) return MPI_ERR_ARG;
+    acx_heap_free(off);
+    return MPI_SUCCESS;
+}
+
+// =======================================================================================
+// emitter: the same op sequence goes to a stream, a capturing stream, or a fresh graph
+// =======================================================================================
+struct Emitter {
+    int qtype = MPIX_QUEUE_CUDA_STREAM;
+    cudaStream_t stream = nullptr;
+    bool capturing = false;
+    cudaGraph_t graph = nullptr;          // GRAPH mode: graph under construction; capture: the capture graph
+    cudaGraphNode_t last = nullptr;
+    bool parallel = false;                // GRAPH mode: do not chain nodes (independent waits)
+
+    int begin(int qt, void *queue) {
+        qtype = qt;
+        if (qt == MPIX_QUEUE_CUDA_STREAM) {
+            stream = *(cudaStream_t *)queue;
+            cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+            cudaGraph_t cg = nullptr;
+            cudaError_t e = cudaStreamGetCaptureInfo_v2(stream, &st, nullptr, &cg, nullptr, nullptr);
+            if (e != cudaSuccess) { ACX_ERR("cudaStreamGetCaptureInfo: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+            capturing = st == cudaStreamCaptureStatusActive;
+            graph = capturing ? cg : nullptr;
+            return 0;
+        }
+        if (qt == MPIX_QUEUE_CUDA_GRAPH) {
+            cudaError_t e = cudaGraphCreate(&graph, 0);
+            if (e != cudaSuccess) { ACX_ERR("cudaGraphCreate: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+            return 0;
+        }
+        ACX_ERR("invalid queue type %d", qt);
+        return MPI_ERR_ARG;
+    }
+    bool in_graph() const { return qtype == MPIX_QUEUE_CUDA_GRAPH || capturing; }
+
+    template <typename P>
+    int launch(void (*kern)(P), dim3 grid, dim3 block, P &params) {
+        void *args[] = {&params};
+        if (qtype == MPIX_QUEUE_CUDA_STREAM) {
+            cudaError_t e = cudaLaunchKernel((const void *)kern, grid, block, args, 0, stream);
+            if (e != cudaSuccess) { report_watchdog(); ACX_ERR("kernel launch failed: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+            g_acx->st.kernels++;
+            if (capturing) g_acx->st.graph_nodes++;
+            return 0;
+        }
+        cudaKernelNodeParams np = {};
+        np.func = (void *)kern; np.gridDim = grid; np.blockDim = block; np.sharedMemBytes = 0; np.kernelParams = args; np.extra = nullptr;
+        cudaGraphNode_t node;
+        cudaError_t e = cudaGraphAddKernelNode(&node, graph, (last && !parallel) ? &last : nullptr, (last && !parallel) ? 1 : 0, &np);
+        if (e != cudaSuccess) { ACX_ERR("cudaGraphAddKernelNode: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+        last = node;
+        g_acx->st.graph_nodes++;
+        return 0;
+    }
+    int launch3(void (*kern)(char *, const char *, uint64_t), dim3 grid, dim3 block, char *a, const char *b, uint64_t c) {
+        void *args[] = {&a, &b, &c};
+        if (qtype == MPIX_QUEUE_CUDA_STREAM) {
+            cudaError_t e = cudaLaunchKernel((const void *)kern, grid, block, args, 0, stream);
+            if (e != cudaSuccess) { ACX_ERR("kernel launch failed: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+            g_acx->st.kernels++;
+            return 0;
+        }
+        cudaKernelNodeParams np = {};
+        np.func = (void *)kern; np.gridDim = grid; np.blockDim = block; np.kernelParams = args;
+        cudaGraphNode_t node;
+        cudaError_t e = cudaGraphAddKernelNode(&node, graph, last ? &last : nullptr, last ? 1 : 0, &np);
+        if (e != cudaSuccess) { ACX_ERR("cudaGraphAddKernelNode: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+        last = node;
+        g_acx->st.graph_nodes++;
+        return 0;
+    }
+};
+
+// Resources that must live as long as a CUDA graph does (the reference attaches a
+// cudaUserObject whose destructor host-spins and frees, src/sendrecv.cu:106-127,174-184;
+// ours only queues the slots for reuse — destructors may not call CUDA).
+struct AcxGraphRes { std::vector<int> slots; };
+static void CUDART_CB graph_res_destroy(void *p) {
+    AcxGraphRes *g = (AcxGraphRes *)p;
+    {
+        std::lock_guard<std::mutex> lk(g_deferred_mu);
+        for (int s : g->slots) g_deferred_slots.push_back(s);
+    }
+    delete g;
+}
+static int attach_to_graph(cudaGraph_t graph, int slot) {
+    AcxGraphRes *res = new AcxGraphRes();
+    res->slots.push_back(slot);
+    cudaUserObject_t obj;
+    cudaError_t e = cudaUserObjectCreate(&obj, res, graph_res_destroy, 1, cudaUserObjectNoDestructorSync);
+    if (e != cudaSuccess) { delete res; ACX_ERR("cudaUserObjectCreate: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+    e = cudaGraphRetainUserObject(graph, obj, 1, cudaGraphUserObjectMove);
+    if (e != cudaSuccess) { ACX_ERR("cudaGraphRetainUserObject: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+    return 0;
+}
+
+static int mover_grid(size_t bytes) {
+    size_t g = (bytes + g_acx->mover_min_cta_bytes - 1) / g_acx->mover_min_cta_bytes;
+    int cap = g_acx->mover_max_ctas > 0 ? g_acx->mover_max_ctas : 4 * g_acx->sm_count;
+    if (g < 1) g = 1;
+    if (g > (size_t)cap) g = cap;
+    return (int)g;
+}
+
+static inline int chan_of(int tag, int ctx) { return (int)(((unsigned)tag + 7u * (unsigned)ctx) % (unsigned)g_acx->geom.nchan); }
+
+static AcxRequest *new_request(AcxReqKind kind, int peer, int tag, int ctx, size_t bytes, const void *buf) {
+    AcxRequest *r = new AcxRequest();
+    memset((void *)r, 0, sizeof *r);
+    r->magic = ACX_REQ_MAGIC; r->kind = kind; r->peer = peer; r->tag = tag; r->comm_ctx = ctx; r->bytes = bytes;
+    r->user_buf = (void *)buf; r->bounce_off = -1; r->heap_off = -1; r->slot = -1; r->land_off = -1;
+    r->serial = g_acx->serial++;
+    r->mpi_req = MPI_REQUEST_NULL;
+    return r;
+}
+
+static int check_common(const char *fn, int count, MPI_Datatype dt, int peer, int tag, MPI_Comm comm, MPIX_Request *request, void *queue, size_t *bytes, int *ctx) {
+    if (!g_acx || !g_acx->initialized) { fprintf(stderr, "[acx] %s: MPIX_Init has not been called\n", fn); return MPI_ERR_OTHER; }
+    if (!request || !queue) { ACX_ERR("%s: null request/queue", fn); return MPI_ERR_ARG; }
+    if (count < 0) { ACX_ERR("%s: negative count", fn); return MPI_ERR_COUNT; }
+    int sz = 0;
+    if (MPI_Type_size(dt, &sz) != MPI_SUCCESS || sz <= 0) { ACX_ERR("%s: invalid datatype", fn); return MPI_ERR_TYPE; }
+    if (peer < 0 || peer >= g_acx->size) { ACX_ERR("%s: peer %d out of range (wildcards / MPI_PROC_NULL are not supported)", fn, peer); return MPI_ERR_RANK; }
+    if (tag < 0) { ACX_ERR("%s: tag %d invalid (MPI_ANY_TAG is not supported)", fn, tag); return MPI_ERR_TAG; }
+    *bytes = (size_t)count * (size_t)sz;
+    return acx_comm_ctx(comm, ctx);
+}
+
+// =======================================================================================
+// MPIX_Isend_enqueue / MPIX_Irecv_enqueue
+// =======================================================================================
+extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm, MPIX_Request *request,
+                                  int qtype, void *queue) {
+    size_t bytes; int ctx;
+    int rc = check_common("MPIX_Isend_enqueue", count, datatype, dest, tag, comm, request, queue, &bytes, &ctx);
+    if (rc) return rc;
+    AcxRequest *r = new_request(ACX_REQ_SEND, dest, tag, ctx, bytes, buf);
+    if (!g_acx->device) {
+        if (qtype != MPIX_QUEUE_CUDA_STREAM) { ACX_ERR("graph queues need a GPU"); delete r; return MPI_ERR_OTHER; }
+        r->host_transport = true;
+        rc = MPI_Isend(buf, count, datatype, dest, tag, comm, &r->mpi_req);
+        if (rc) { delete r; return rc; }
+        g_acx->st.sends++; g_acx->st.bytes_sent += bytes;
+        *request = r;
+        return MPI_SUCCESS;
+    }
+    Emitter em;
+    if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
+    r->in_graph = em.in_graph();
+    r->chan = chan_of(tag, ctx);
+    if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
+    if ((rc = acx_device_alias(buf, bytes, &r->dev_buf))) goto fail;
+    {
+        const acx_geom &G = g_acx->geom;
+        const bool eager = bytes <= G.eager_max;
+        uint64_t src_off = ~0ull;
+        const char *src_local = r->dev_buf;
+        if (!eager) {
+            r->heap_off = acx_heap_offset_of(buf);
+            if (r->heap_off >= 0) src_off = (uint64_t)r->heap_off;
+            else {
+                // private source: bounce into the symmetric heap first (local HBM copy)
+                if ((r->bounce_off = acx_heap_alloc(bytes)) < 0) { rc = MPI_ERR_OTHER; goto fail; }
+                src_off = (uint64_t)r->bounce_off;
+                src_local = g_acx->heap + r->bounce_off;
+                if ((rc = em.launch3(copy_kernel, dim3(mover_grid(bytes)), dim3(kMoverThreads), g_acx->heap + r->bounce_off, r->dev_buf, (uint64_t)bytes))) goto fail;
+                g_acx->st.bounce++;
+            }
+        }
+        const uint64_t ring_idx = acx_entry_index(G, g_acx->rank, r->chan, 0);  // at the receiver: [src = me][chan]
+        const uint64_t sack_idx = acx_entry_index(G, dest, r->chan, 0);       // at me: [dst][chan]
+        SendParams sp;
+        memset(&sp, 0, sizeof sp);
+        sp.ring = acx_entries_of(g_acx->peer_ctrl[dest]) + ring_idx;
+        sp.eager = g_acx->peer_ctrl[dest] + G.off_eager + ring_idx * G.eager_max;
+        sp.sack = acx_sacks_of(g_acx->ctrl) + sack_idx;
+        sp.seq = (uint64_t *)(g_acx->ctrl + G.off_send_seq) + ((uint64_t)dest * G.nchan + r->chan);
+        sp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
+        sp.src = r->dev_buf;
+        sp.peer_heap = g_acx->peer_heap[dest];
+        sp.src_off = src_off; sp.bytes = bytes; sp.serial = r->serial;
+        sp.tag = (uint32_t)tag; sp.depth = G.depth; sp.eager_max = G.eager_max; sp.peer = dest;
+        sp.wd = make_wd(); sp.tr = make_tr();
+        if ((rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
+        if (!eager) {
+            MoverParams mp;
+            memset(&mp, 0, sizeof mp);
+            mp.op = sp.op; mp.local = (char *)src_local; mp.ring = sp.ring; mp.sack = sp.sack; mp.depth = G.depth; mp.push = 1; mp.peer = dest; mp.tr = sp.tr;
+            if ((rc = em.launch(mover, dim3(mover_grid(bytes)), dim3(kMoverThreads), mp))) goto fail;
+            g_acx->st.rndv++;
+        } else {
+            g_acx->st.eager++;
+        }
+    }
+    if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;
+    if (qtype == MPIX_QUEUE_CUDA_GRAPH) {
+        if ((rc = attach_to_graph(em.graph, r->slot))) goto fail;
+        *(cudaGraph_t *)queue = em.graph;
+    }
+    g_acx->st.sends++; g_acx->st.bytes_sent += bytes;
+    *request = r;
+    return MPI_SUCCESS;
+fail:
+    if (qtype == MPIX_QUEUE_CUDA_GRAPH && em.graph) cudaGraphDestroy(em.graph);
+    { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); acx_slot_free(r->slot); }
+    return rc;
+}
+
+extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPIX_Request *request, int qtype,
+                                  void *queue) {
+    size_t bytes; int ctx;
+    int rc = check_common("MPIX_Irecv_enqueue", count, datatype, source, tag, comm, request, queue, &bytes, &ctx);
+    if (rc) return rc;
+    AcxRequest *r = new_request(ACX_REQ_RECV, source, tag, ctx, bytes, buf);
+    if (!g_acx->device) {
+        if (qtype != MPIX_QUEUE_CUDA_STREAM) { ACX_ERR("graph queues need a GPU"); delete r; return MPI_ERR_OTHER; }
+        r->host_transport = true;
+        rc = MPI_Irecv(buf, count, datatype, source, tag, comm, &r->mpi_req);
+        if (rc) { delete r; return rc; }
+        g_acx->st.recvs++; g_acx->st.bytes_recv += bytes;
+        *request = r;
+        return MPI_SUCCESS;
+    }
+    Emitter em;
+    if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
+    r->in_graph = em.in_graph();
+    r->chan = chan_of(tag, ctx);
+    if (!r->in_graph) {
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        if (g_acx->recv_outstanding[source][r->chan] >= g_acx->geom.depth) {
+            ACX_ERR("more than ACX_DEPTH=%d receives outstanding (posted, not yet waited) from rank %d on the channel of tag %d; wait on earlier ones or raise ACX_DEPTH",
+                    g_acx->geom.depth, source, tag);
+            delete r;
+            return MPI_ERR_OTHER;
+        }
+        g_acx->recv_outstanding[source][r->chan]++;
+    }
+    if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
+    if ((rc = acx_device_alias(buf, bytes, &r->dev_buf))) goto fail;
+    {
+        const acx_geom &G = g_acx->geom;
+        const bool rndv_capable = bytes > G.eager_max;
+        uint64_t dst_off = ~0ull;
+        char *dst_local = r->dev_buf;
+        r->heap_off = acx_heap_offset_of(buf);
+        if (r->heap_off >= 0) dst_off = (uint64_t)r->heap_off;
+        else if (rndv_capable) {
+            if ((r->bounce_off = acx_heap_alloc(bytes)) < 0) { rc = MPI_ERR_OTHER; goto fail; }
+            dst_off = (uint64_t)r->bounce_off;
+            dst_local = g_acx->heap + r->bounce_off;
+            g_acx->st.bounce++;
+        }
+        const uint64_t ring_idx = acx_entry_index(G, source, r->chan, 0);        // at me: [src][chan]
+        const uint64_t sack_idx = acx_entry_index(G, g_acx->rank, r->chan, 0);     // at the sender: [dst = me][chan]
+        RecvParams rp;
+        memset(&rp, 0, sizeof rp);
+        rp.ring = acx_entries_of(g_acx->ctrl) + ring_idx;
+        rp.seq = (uint64_t *)(g_acx->ctrl + G.off_recv_seq) + ((uint64_t)source * G.nchan + r->chan);
+        rp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
+        rp.peer_heap = g_acx->peer_heap[source];
+        rp.dst_off = dst_off; rp.cap = bytes; rp.serial = r->serial; rp.depth = G.depth; rp.peer = source;
+        rp.wd = make_wd(); rp.tr = make_tr();
+        if ((rc = em.launch(recv_trigger, dim3(1), dim3(32), rp))) goto fail;
+        if (rndv_capable) {
+            MoverParams mp;
+            memset(&mp, 0, sizeof mp);
+            mp.op = rp.op; mp.local = dst_local; mp.ring = rp.ring; mp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;
+            mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr;
+            if ((rc = em.launch(mover, dim3(mover_grid(bytes)), dim3(kMoverThreads), mp))) goto fail;
+        }
+    }
+    if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;
+    if (qtype == MPIX_QUEUE_CUDA_GRAPH) {
+        if ((rc = attach_to_graph(em.graph, r->slot))) goto fail;
+        *(cudaGraph_t *)queue = em.graph;
+    }
+    g_acx->st.recvs++; g_acx->st.bytes_recv += bytes;
+    *request = r;
+    return MPI_SUCCESS;
+fail:
+    if (qtype == MPIX_QUEUE_CUDA_GRAPH && em.graph) cudaGraphDestroy(em.graph);
+    { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); acx_slot_free(r->slot); }
+    return rc;
+}
+
+// =======================================================================================
+// waits
+// =======================================================================================
+static AcxRequest *as_request(MPIX_Request h) {
+    AcxRequest *r = (AcxRequest *)h;
+    if (!r || r->magic != ACX_REQ_MAGIC) return nullptr;
+    return r;
+}
+
+static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_wait, WaitOne *w) {
+    const acx_geom &G = g_acx->geom;
+    memset(w, 0, sizeof *w);
+    w->op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
+    w->hstat = g_acx->hstat_d + r->slot;
+    w->depth = G.depth; w->eager_max = G.eager_max;
+    w->serial = host_wait ? r->serial : 0;
+    w->retire = retire ? 1 : 0;
+    w->src = r->peer; w->tag = r->tag;
+    w->off_source = w->off_tag = w->off_error = w->off_bytes = 0xffff;
+    if (r->kind == ACX_REQ_SEND) {
+        w->is_recv = 0;
+        w->sack = acx_sacks_of(g_acx->ctrl) + acx_entry_index(G, r->peer, r->chan, 0);
+    } else {
+        w->is_recv = 1;
+        const uint64_t ring_idx = acx_entry_index(G, r->peer, r->chan, 0);
+        w->ring = acx_entries_of(g_acx->ctrl) + ring_idx;
+        w->eager = g_acx->ctrl + G.off_eager + ring_idx * G.eager_max;
+        w->sack = acx_sacks_of(g_acx->peer_ctrl[r->peer]) + acx_entry_index(G, g_acx->rank, r->chan, 0);
+        w->dst = r->dev_buf;
+        w->bounce = r->bounce_off >= 0 ? g_acx->heap + r->bounce_off : nullptr;
+        w->cap = r->bytes;
+        if (status != MPI_STATUS_IGNORE && !host_wait) {
+            char *ds = nullptr;
+            int rc = acx_device_alias(status, sizeof(MPI_Status), &ds);
+            if (rc) return rc;
+            w->ustatus = ds;
+            w->off_source = (uint16_t)offsetof(MPI_Status, MPI_SOURCE);
+            w->off_tag = (uint16_t)offsetof(MPI_Status, MPI_TAG);
+            w->off_error = (uint16_t)offsetof(MPI_Status, MPI_ERROR);
+#ifdef ACX_MINI_MPI
+            w->off_bytes = (uint16_t)offsetof(MPI_Status, _bytes);
+#endif
+        }
+    }
+    return 0;
+}
+
+static void host_status_send(MPI_Status *st, AcxRequest *r) {
+    if (st == MPI_STATUS_IGNORE) return;
+    st->MPI_SOURCE = r->peer; st->MPI_TAG = r->tag; st->MPI_ERROR = MPI_SUCCESS;
+#ifdef ACX_MINI_MPI
+    st->_bytes = 0;
+#endif
+}
+
+static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses, int qtype, void *queue) {
+    if (!g_acx || !g_acx->initialized) return MPI_ERR_OTHER;
+    if (count < 0 || (count > 0 && !reqs) || !queue) return MPI_ERR_ARG;
+    std::vector<AcxRequest *> rs;
+    for (int i = 0; i < count; i++) {
+        if (reqs[i] == MPIX_REQUEST_NULL) continue;
+        AcxRequest *r = as_request(reqs[i]);
+        if (!r) { ACX_ERR("invalid request handle at index %d", i); return MPI_ERR_REQUEST; }
+        if (r->kind == ACX_REQ_PSEND || r->kind == ACX_REQ_PRECV) {
+            ACX_ERR("partitioned requests cannot be completed with MPIX_Wait(all)_enqueue; use MPIX_Wait / MPIX_Pwait_enqueue");
+            return MPI_ERR_REQUEST;
+        }
+        rs.push_back(r);
+    }
+    if (!g_acx->device) {
+        // host transport: "the stream" is the calling thread; complete in order.
+        if (qtype != MPIX_QUEUE_CUDA_STREAM) return MPI_ERR_OTHER;
+        for (int i = 0; i < count; i++) {
+            AcxRequest *r = as_request(reqs[i]);
+            if (!r) continue;
+            MPI_Status *st = statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[i];
+            int rc = MPI_Wait(&r->mpi_req, st);
+            if (rc) return rc;
+            r->magic = 0; delete r;
+            reqs[i] = MPIX_REQUEST_NULL;
+            g_acx->st.waits++;
+        }
+        return MPI_SUCCESS;
+    }
+    Emitter em;
+    int rc = em.begin(qtype, queue);
+    if (rc) return rc;
+    em.parallel = true;  // explicit graphs: independent wait nodes (reference: src/sendrecv.cu:544-566)
+    for (AcxRequest *r : rs) {
+        if (r->in_graph != em.in_graph()) {
+            ACX_ERR("%s", r->in_graph ? "in-graph operations must be waited on in a graph" : "on-stream operations cannot be waited on from a graph");
+            if (qtype == MPIX_QUEUE_CUDA_GRAPH) cudaGraphDestroy(em.graph);
+            return MPI_ERR_REQUEST;
+        }
+    }
+    const bool retire = !em.in_graph();
+    int idx = 0;
+    for (size_t base = 0; base < rs.size(); base += kWaitBatch) {
+        WaitBatch wb;
+        memset(&wb, 0, sizeof wb);
+        int n = (int)std::min((size_t)kWaitBatch, rs.size() - base);
+        for (int j = 0; j < n; j++) {
+            // map back to the user's status slot
+            while (reqs[idx] == MPIX_REQUEST_NULL) idx++;
+            MPI_Status *st = statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[idx];
+            AcxRequest *r = rs[base + j];
+            if (r->kind == ACX_REQ_SEND && st != MPI_STATUS_IGNORE && !em.in_graph()) host_status_send(st, r);
+            if ((rc = fill_wait(r, st, retire, false, &wb.w[j]))) return rc;
+            idx++;
+        }
+        wb.wd = make_wd(); wb.tr = make_tr();
+        if ((rc = em.launch(wait_kernel, dim3(n), dim3(kWaitThreads), wb))) return rc;
+    }
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        for (AcxRequest *r : rs) {
+            if (retire) g_acx->slot_busy[r->slot] = 3;  // reclaimed once the wait kernel marks it retired
+            if (retire && r->kind == ACX_REQ_RECV && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
+        }
+    }
+    for (int i = 0; i < count; i++) reqs[i] = MPIX_REQUEST_NULL;  // handle is consumed at enqueue time (reference: src/sendrecv.cu:430-432)
+    g_acx->st.waits += rs.size();
+    if (qtype == MPIX_QUEUE_CUDA_GRAPH) *(cudaGraph_t *)queue = em.graph;
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Wait_enqueue(MPIX_Request *req, MPI_Status *status, int qtype, void *queue) {
+    if (!req) return MPI_ERR_ARG;
+    return wait_enqueue_impl(1, req, status == MPI_STATUS_IGNORE ? MPI_STATUSES_IGNORE : status, qtype, queue);
+}
+
+extern "C" int MPIX_Waitall_enqueue(int count, MPIX_Request *reqs, MPI_Status *statuses, int qtype, void *queue) {
+    return wait_enqueue_impl(count, reqs, statuses, qtype, queue);
+}
+
+// ---- partitioned: forward declarations ----
+static int pwait_host(AcxRequest *r, MPI_Status *status);
+
+extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
+    if (!g_acx || !g_acx->initialized || !req) return MPI_ERR_OTHER;
+    if (*req == MPIX_REQUEST_NULL) return MPI_SUCCESS;
+    AcxRequest *r = as_request(*req);
+    if (!r) { ACX_ERR("invalid request handle"); return MPI_ERR_REQUEST; }
+    if (r->kind == ACX_REQ_PSEND || r->kind == ACX_REQ_PRECV) return pwait_host(r, status);
+    if (r->host_transport) {
+        int rc = MPI_Wait(&r->mpi_req, status);
+        r->magic = 0; delete r;
+        *req = MPIX_REQUEST_NULL;
+        return rc;
+    }
+    if (r->in_graph) { ACX_ERR("in-graph operations must be completed by a wait inside a graph"); return MPI_ERR_REQUEST; }
+    WaitBatch wb;
+    memset(&wb, 0, sizeof wb);
+    int rc = fill_wait(r, MPI_STATUS_IGNORE, false, true, &wb.w[0]);
+    if (rc) return rc;
+    wb.wd = make_wd(); wb.tr = make_tr();
+    void *args[] = {&wb};
+    ACX_CUDA_WD(cudaLaunchKernel((const void *)wait_kernel, dim3(1), dim3(kWaitThreads), args, 0, g_acx->istream));
+    g_acx->st.kernels++;
+    ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    if (status != MPI_STATUS_IGNORE) {
+        if (r->kind == ACX_REQ_SEND) host_status_send(status, r);
+        else {
+            const acx_host_status &h = g_acx->hstat[r->slot];
+            status->MPI_SOURCE = h.source; status->MPI_TAG = h.tag; status->MPI_ERROR = h.error;
+#ifdef ACX_MINI_MPI
+            status->_bytes = h.bytes;
+#endif
+        }
+    }
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        if (r->kind == ACX_REQ_RECV && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
+        acx_slot_free(r->slot);
+    }
+    *req = MPIX_REQUEST_NULL;
+    g_acx->st.waits++;
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses) {
+    for (int i = 0; i < count; i++) {
+        int rc = MPIX_Wait(&reqs[i], statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[i]);
+        if (rc) return rc;
+    }
+    return MPI_SUCCESS;
+}
+
+// =======================================================================================
+// partitioned
+// =======================================================================================
+struct PInfo {  // handshake record exchanged over the private communicator
+    int32_t partitions;
+    int32_t pad;
+    uint64_t part_bytes;
+    int64_t land_off;       // receiver: landing buffer offset in its heap
+    uint32_t pf_arrived;    // receiver: arrived[] index in its pflags
+    uint32_t pf_cts;        // sender: cts word index in its pflags
+};
+
+struct PHandshake { PInfo mine, theirs; MPI_Request sreq, rreq; };
+static std::unordered_map<AcxRequest *, PHandshake *> g_hs;
+
+static int pinit_common(AcxReqKind kind, const void *buf, int partitions, MPI_Count count, MPI_Datatype dt, int peer, int tag, MPI_Comm comm,
+                        MPIX_Request *request) {
+    if (!g_acx || !g_acx->initialized) return MPI_ERR_OTHER;
+    if (!request) return MPI_ERR_ARG;
+    if (partitions <= 0) { ACX_ERR("partitions must be > 0"); return MPI_ERR_COUNT; }
+    int sz = 0, ctx = 0;
+    if (MPI_Type_size(dt, &sz) != MPI_SUCCESS || sz <= 0) return MPI_ERR_TYPE;
+    if (peer < 0 || peer >= g_acx->size) return MPI_ERR_RANK;
+    if (tag < 0) return MPI_ERR_TAG;
+    int rc = acx_comm_ctx(comm, &ctx);
+    if (rc) return rc;
+    size_t part_bytes = (size_t)count * (size_t)sz;
+    AcxRequest *r = new_request(kind, peer, tag, ctx, part_bytes * partitions, buf);
+    r->partitions = partitions; r->part_bytes = part_bytes;
+    if (!g_acx->device) {
+        r->host_transport = true;
+        rc = kind == ACX_REQ_PSEND ? MPI_Psend_init(buf, partitions, count, dt, peer, tag, comm, MPI_INFO_NULL, &r->mpi_req)
+                                   : MPI_Precv_init((void *)buf, partitions, count, dt, peer, tag, comm, MPI_INFO_NULL, &r->mpi_req);
+        if (rc) { delete r; return rc; }
+        *request = r;
+        return MPI_SUCCESS;
+    }
+    if ((rc = acx_device_alias(buf, r->bytes, &r->dev_buf))) { delete r; return rc; }
+    PHandshake *hs = new PHandshake();
+    memset(hs, 0, sizeof *hs);
+    hs->mine.partitions = partitions; hs->mine.part_bytes = part_bytes; hs->mine.land_off = -1;
+    if (kind == ACX_REQ_PSEND) {
+        uint32_t base = acx_pflags_alloc(partitions + 2);
+        if (base == UINT32_MAX) { delete r; delete hs; return MPI_ERR_OTHER; }
+        r->pf_local = base; r->pf_cts = base + partitions; r->pf_epoch = base + partitions + 1;
+        hs->mine.pf_cts = r->pf_cts;
+    } else {
+        uint32_t base = acx_pflags_alloc(2 * partitions + 1);
+        if (base == UINT32_MAX) { delete r; delete hs; return MPI_ERR_OTHER; }
+        r->pf_arrived = base; r->pf_local = base + partitions; r->pf_epoch = base + 2 * partitions;
+        r->heap_off = acx_heap_offset_of(buf);
+        if (r->heap_off >= 0) { r->land_off = r->heap_off; r->land_is_user = true; }
+        else {
+            if ((r->land_off = acx_heap_alloc(r->bytes)) < 0) { delete r; delete hs; return MPI_ERR_OTHER; }
+            g_acx->st.bounce++;
+        }
+        hs->mine.land_off = r->land_off; hs->mine.pf_arrived = r->pf_arrived;
+    }
+    // Exchange descriptors on the private communicator; matching order per (peer, tag)
+    // follows MPI's own non-overtaking rule, which is exactly the init-order pairing we need.
+    const int t_out = tag * 2 + (kind == ACX_REQ_PSEND ? 0 : 1), t_in = tag * 2 + (kind == ACX_REQ_PSEND ? 1 : 0);
+    MPI_Irecv(&hs->theirs, (int)sizeof(PInfo), MPI_BYTE, peer, t_in, g_acx->icomm, &hs->rreq);
+    MPI_Isend(&hs->mine, (int)sizeof(PInfo), MPI_BYTE, peer, t_out, g_acx->icomm, &hs->sreq);
+    { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); g_hs[r] = hs; }
+    *request = r;
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Psend_init(const void *buf, int partitions, MPI_Count count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm, MPI_Info,
+                               MPIX_Request *request) {
+    return pinit_common(ACX_REQ_PSEND, buf, partitions, count, datatype, dest, tag, comm, request);
+}
+extern "C" int MPIX_Precv_init(void *buf, int partitions, MPI_Count count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPI_Info,
+                               MPIX_Request *request) {
+    return pinit_common(ACX_REQ_PRECV, buf, partitions, count, datatype, source, tag, comm, request);
+}
+
+// Complete the handshake (blocks until the peer has called its matching *_init) and build
+// the device descriptor.
+static int presolve(AcxRequest *r) {
+    if (r->resolved) return 0;
+    PHandshake *hs;
+    { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); hs = g_hs[r]; }
+    MPI_Wait(&hs->sreq, MPI_STATUS_IGNORE);
+    MPI_Wait(&hs->rreq, MPI_STATUS_IGNORE);
+    if (hs->theirs.partitions != r->partitions || hs->theirs.part_bytes != r->part_bytes) {
+        ACX_ERR("partitioned send/recv geometry mismatch with rank %d: mine %d x %zu B, theirs %d x %llu B (equal partitioning is required)", r->peer,
+                r->partitions, r->part_bytes, hs->theirs.partitions, (unsigned long long)hs->theirs.part_bytes);
+        return MPI_ERR_OTHER;
+    }
+    acx_pchan &c = r->pchan_h;
+    memset(&c, 0, sizeof c);
+    c.partitions = r->partitions; c.part_bytes = r->part_bytes; c.user_buf = r->dev_buf; c.peer = r->peer; c.tag = r->tag;
+    uint64_t *mypf = acx_pflags_of(g_acx->ctrl), *peerpf = acx_pflags_of(g_acx->peer_ctrl[r->peer]);
+    c.epoch = mypf + r->pf_epoch;
+    if (r->kind == ACX_REQ_PSEND) {
+        c.kind = ACX_PKIND_SEND;
+        c.land = g_acx->peer_heap[r->peer] + hs->theirs.land_off;
+        c.arrived = peerpf + hs->theirs.pf_arrived;
+        c.local_flags = mypf + r->pf_local;
+        c.cts = mypf + r->pf_cts;
+    } else {
+        c.kind = ACX_PKIND_RECV;
+        c.land = r->land_is_user ? r->dev_buf : g_acx->heap + r->land_off;
+        c.arrived = mypf + r->pf_arrived;
+        c.local_flags = mypf + r->pf_local;
+        c.cts = peerpf + hs->theirs.pf_cts;  // remote: written at Start
+    }
+    ACX_CUDA(cudaMalloc((void **)&r->pchan_d, sizeof(acx_pchan)));
+    ACX_CUDA(cudaMemcpy(r->pchan_d, &c, sizeof c, cudaMemcpyHostToDevice));
+    { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); g_hs.erase(r); }
+    delete hs;
+    r->resolved = true;
+    return 0;
+}
+
+extern "C" int MPIX_Prequest_create(MPIX_Request request, MPIX_Prequest *prequest) {
+    AcxRequest *r = as_request(request);
+    if (!r || (r->kind != ACX_REQ_PSEND && r->kind != ACX_REQ_PRECV) || !prequest) return MPI_ERR_REQUEST;
+    if (!g_acx->device) { ACX_ERR("device partitioned handles need a GPU"); return MPI_ERR_OTHER; }
+    int rc = presolve(r);
+    if (rc) return rc;
+    *prequest = (MPIX_Prequest)r->pchan_d;
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Prequest_free(MPIX_Prequest *preq) {
+    if (!preq) return MPI_ERR_ARG;
+    *preq = MPIX_PREQUEST_NULL;  // the descriptor is owned by the request (freed in MPIX_Request_free)
+    return MPI_SUCCESS;
+}
+
+static int pstart_emit(AcxRequest *r, cudaStream_t stream) {
+    int rc = presolve(r);
+    if (rc) return rc;
+    if (r->active) { ACX_ERR("MPIX_Start on an active partitioned request"); return MPI_ERR_REQUEST; }
+    r->epoch++;
+    r->active = true;
+    uint64_t *epoch_local = r->pchan_h.epoch;
+    uint64_t *cts_remote = r->kind == ACX_REQ_PRECV ? r->pchan_h.cts : nullptr;
+    uint64_t e = r->epoch;
+    void *args[] = {&epoch_local, &cts_remote, &e};
+    ACX_CUDA_WD(cudaLaunchKernel((const void *)pstart_kernel, dim3(1), dim3(1), args, 0, stream));
+    g_acx->st.kernels++;
+    return 0;
+}
+
+extern "C" int MPIX_Startall(int count, MPIX_Request *reqs) {
+    if (!g_acx || !g_acx->initialized) return MPI_ERR_OTHER;
+    bool any_dev = false;
+    for (int i = 0; i < count; i++) {
+        AcxRequest *r = as_request(reqs[i]);
+        if (!r || (r->kind != ACX_REQ_PSEND && r->kind != ACX_REQ_PRECV)) { ACX_ERR("MPIX_Start needs a partitioned request"); return MPI_ERR_REQUEST; }
+        if (r->host_transport) { int rc = MPI_Start(&r->mpi_req); if (rc) return rc; r->active = true; continue; }
+        int rc = pstart_emit(r, g_acx->istream);
+        if (rc) return rc;
+        any_dev = true;
+    }
+    // Kernels launched by the user right after Start (on any stream) must observe the new epoch.
+    if (any_dev) ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    return MPI_SUCCESS;
+}
+extern "C" int MPIX_Start(MPIX_Request *request) { return MPIX_Startall(1, request); }
+
+extern "C" int MPIX_Start_enqueue(MPIX_Request *request, int qtype, void *queue) {
+    AcxRequest *r = request ? as_request(*request) : nullptr;
+    if (!r || r->host_transport || qtype != MPIX_QUEUE_CUDA_STREAM) return MPI_ERR_REQUEST;
+    return pstart_emit(r, *(cudaStream_t *)queue);
+}
+
+static int pwait_emit(AcxRequest *r, cudaStream_t stream) {
+    if (!r->active) return 0;
+    const acx_pchan *ch = r->pchan_d;
+    uint64_t e = r->epoch;
+    Watchdog wd = make_wd();
+    void *args[] = {&ch, &e, &wd};
+    ACX_CUDA_WD(cudaLaunchKernel((const void *)pwait_kernel, dim3(1), dim3(kWaitThreads), args, 0, stream));
+    g_acx->st.kernels++;
+    r->active = false;
+    return 0;
+}
+
+extern "C" int MPIX_Pwait_enqueue(MPIX_Request *request, int qtype, void *queue) {
+    AcxRequest *r = request ? as_request(*request) : nullptr;
+    if (!r || r->host_transport || qtype != MPIX_QUEUE_CUDA_STREAM) return MPI_ERR_REQUEST;
+    return pwait_emit(r, *(cudaStream_t *)queue);
+}
+
+static int pwait_host(AcxRequest *r, MPI_Status *status) {
+    if (r->host_transport) {
+        int rc = MPI_Wait(&r->mpi_req, status);
+        r->active = false;
+        return rc;
+    }
+    int rc = pwait_emit(r, g_acx->istream);
+    if (rc) return rc;
+    ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    if (status != MPI_STATUS_IGNORE) {
+        status->MPI_SOURCE = r->peer; status->MPI_TAG = r->tag; status->MPI_ERROR = MPI_SUCCESS;
+#ifdef ACX_MINI_MPI
+        status->_bytes = r->kind == ACX_REQ_PRECV ? (long long)r->bytes : 0;
+#endif
+    }
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Request_free(MPIX_Request *request) {
+    if (!request || *request == MPIX_REQUEST_NULL) return MPI_SUCCESS;
+    AcxRequest *r = as_request(*request);
+    if (!r) return MPI_ERR_REQUEST;
+    if (r->kind == ACX_REQ_SEND || r->kind == ACX_REQ_RECV) {
+        // The reference silently ignores basic requests here (src/sendrecv.cu:667); we do the
+        // sensible thing: an un-waited basic request is completed and released.
+        return MPIX_Wait(request, MPI_STATUS_IGNORE);
+    }
+    if (r->active) { ACX_ERR("MPIX_Request_free on an active partitioned request"); return MPI_ERR_REQUEST; }
+    if (r->host_transport) {
+        MPI_Request_free(&r->mpi_req);
+    } else {
+        if (!r->resolved) presolve(r);  // drain the handshake so the peer's messages are matched
+        if (r->pchan_d) cudaFree(r->pchan_d);
+        if (r->kind == ACX_REQ_PRECV && !r->land_is_user && r->land_off >= 0) acx_heap_free(r->land_off);
+    }
+    r->magic = 0;
+    delete r;
+    *request = MPIX_REQUEST_NULL;
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Pready_host(int partition, MPIX_Request *request) {
+    AcxRequest *r = request ? as_request(*request) : nullptr;
+    if (!r || r->kind != ACX_REQ_PSEND) return MPI_ERR_REQUEST;
+    if (partition < 0 || partition >= r->partitions) return MPI_ERR_ARG;
+    if (r->host_transport) return MPI_Pready(partition, r->mpi_req);
+    const acx_pchan *ch = r->pchan_d;
+    void *args[] = {&ch, &partition};
+    ACX_CUDA_WD(cudaLaunchKernel((const void *)pready_host_kernel, dim3(1), dim3(256), args, 0, g_acx->istream));
+    ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Parrived_host(MPIX_Request *request, int partition, int *flag) {
+    AcxRequest *r = request ? as_request(*request) : nullptr;
+    if (!r || r->kind != ACX_REQ_PRECV || !flag) return MPI_ERR_REQUEST;
+    if (partition < 0 || partition >= r->partitions) return MPI_ERR_ARG;
+    if (r->host_transport) return MPI_Parrived(r->mpi_req, partition, flag);
+    if (!r->active) { *flag = 1; return MPI_SUCCESS; }
+    static int *dflag = nullptr;
+    if (!dflag) ACX_CUDA(cudaHostAlloc((void **)&dflag, sizeof(int), cudaHostAllocMapped));
+    *dflag = 0;
+    const acx_pchan *ch = r->pchan_d;
+    int *dp = nullptr;
+    cudaHostGetDevicePointer((void **)&dp, dflag, 0);
+    void *args[] = {&ch, &partition, &dp};
+    ACX_CUDA_WD(cudaLaunchKernel((const void *)parrived_host_kernel, dim3(1), dim3(1), args, 0, g_acx->istream));
+    ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    *flag = *dflag;
+    return MPI_SUCCESS;
+}

@@ -1,0 +1,229 @@
+// acx-b200 internal definitions: control-window layout shared by host and device,
+// global state, request objects, logging/error macros.
+//
+// Design (vs the reference's flags-in-host-memory + CPU proxy):
+//  * every rank owns two device allocations, both CUDA-IPC mapped into every peer at
+//    MPIX_Init: a CONTROL window (rendezvous rings, acks, op records, eager slots,
+//    partitioned flags) and a symmetric HEAP (user-visible via MPIX_Alloc_mem, also
+//    used for bounce buffers);
+//  * a message S->R on channel c (= hash(tag,comm)) takes ticket k from a device-side
+//    counter when its trigger kernel EXECUTES (stream/graph order == matching order,
+//    relaunch-safe); slot e = k % depth, generation g = k / depth of the ring that
+//    lives in R's control window;
+//  * eager (<= eager_max): the send kernel stores payload+header into R's slot and
+//    bumps the slot's arrival count (red.release.sys); the receiver's wait kernel copies
+//    out locally;
+//  * rendezvous: both triggers add to the slot's 64-bit state word (hi32 = sends arrived,
+//    lo32 = recvs posted). Whoever arrives SECOND moves the data: a sender pushes
+//    (st over NVLink), a receiver pulls (ld over NVLink), then publishes done (to R)
+//    and sdone (to S). Nobody spins on remote memory, nothing waits for the peer's
+//    *stream* to make progress (MPI progress semantics without a progress thread).
+#ifndef ACX_INTERNAL_H
+#define ACX_INTERNAL_H
+
+#include <mpi.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/acx_device.cuh"
+
+// ---- shared host/device layout -----------------------------------------------------
+enum { ACX_KIND_EAGER = 1, ACX_KIND_RNDV = 2 };
+
+struct alignas(64) acx_entry {  // one slot of a (src -> me, channel) ring; lives at the receiver
+    uint64_t state;      // hi32: #sends arrived on this slot, lo32: #recvs posted (atomic add, never reset)
+    uint64_t done;       // #generations whose data has fully landed (mover: release store)
+    uint64_t consumed;   // #generations the receiver has finished with (receiver-local bookkeeping)
+    uint64_t s_src_off;  // sender: heap offset of the source (rendezvous)
+    uint64_t s_bytes;    // sender: message bytes
+    uint64_t r_dst_off;  // receiver: heap offset of the destination (rendezvous)
+    uint64_t r_cap;      // receiver: capacity in bytes
+    uint32_t s_tag;
+    uint32_t s_kind;     // ACX_KIND_*
+};
+
+struct alignas(16) acx_sack {  // per slot, lives at the SENDER, written by the receiver / mover
+    uint64_t sdone;   // #generations whose send completed (source buffer reusable)
+    uint64_t efree;   // #generations the receiver has consumed (slot reusable by generation efree)
+};
+
+struct alignas(64) acx_op {  // per request slot, local
+    uint64_t ticket;     // k assigned by the trigger kernel
+    uint64_t armed;      // request serial written by the trigger after `ticket` (host waits key on it)
+    uint64_t peer_ptr;   // mover: translated remote address
+    uint64_t n;          // mover: bytes to move
+    uint32_t mover;      // 1 if this side arrived second and must move the data
+    uint32_t eager;      // send side: message went eager (nothing to wait for)
+    uint32_t cta_count;  // last-CTA detection
+    uint32_t pad;
+    uint64_t recv_bytes; // receive side: actual message size
+};
+
+struct acx_host_status {  // pinned host memory, one per request slot; written by wait kernels
+    int32_t source, tag, error, retired;
+    int64_t bytes;
+    int64_t pad;
+};
+
+struct acx_trace_rec {  // device-side trace ring (ACX_TRACE=1)
+    uint64_t t_ns;      // %globaltimer
+    uint32_t ev, peer;
+    uint64_t a, b;
+};
+enum { ACX_EV_SEND_TRIGGER = 1, ACX_EV_RECV_TRIGGER, ACX_EV_MOVE_BEGIN, ACX_EV_MOVE_END, ACX_EV_WAIT_BEGIN, ACX_EV_WAIT_END };
+
+// Geometry of a control window; identical on every rank (derived from env + nranks).
+struct acx_geom {
+    int nranks, nchan, depth, nops;
+    uint32_t eager_max;
+    uint64_t off_entries, off_sack, off_send_seq, off_recv_seq, off_ops, off_pflags, off_trace, off_eager, bytes;
+    uint32_t npflags, ntrace;
+};
+
+#ifdef __CUDACC__
+#define ACX_HDI __host__ __device__ __forceinline__
+#else
+#define ACX_HDI inline
+#endif
+ACX_HDI uint64_t acx_entry_index(const acx_geom &g, int src, int chan, int e) { return ((uint64_t)src * g.nchan + chan) * g.depth + e; }
+
+// ---- host-side state -------------------------------------------------------------------
+#ifdef __cplusplus
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+enum AcxReqKind { ACX_REQ_SEND = 1, ACX_REQ_RECV = 2, ACX_REQ_PSEND = 3, ACX_REQ_PRECV = 4 };
+
+struct AcxGraphRes;  // resources owned by a CUDA graph (released by its user object)
+
+struct AcxRequest {
+    uint32_t magic;
+    AcxReqKind kind;
+    int peer, tag, comm_ctx, chan;
+    int slot;                 // op slot (basic) / -1
+    uint64_t serial;
+    size_t bytes;             // message bytes (send) / capacity (recv)
+    void *user_buf;           // as passed by the user
+    char *dev_buf;            // device-accessible alias of user_buf
+    int64_t bounce_off;       // heap offset of bounce buffer, -1 if none
+    int64_t heap_off;         // heap offset of user_buf if it lives in the heap, else -1
+    bool in_graph;
+    bool host_transport;      // no-GPU mode: backed by an MPI_Request
+    MPI_Request mpi_req;
+    MPI_Status *user_status;
+    AcxGraphRes *gres;
+    // partitioned
+    int partitions;
+    size_t part_bytes;
+    uint64_t epoch;
+    bool active;
+    bool resolved;
+    int pair_rec;             // index of the handshake record
+    int64_t land_off;         // RECV: landing buffer heap offset (may alias user buffer)
+    bool land_is_user;
+    uint32_t pf_arrived;      // RECV: index of arrived[] in my pflags; SEND: in the peer's
+    uint32_t pf_local;        // SEND: sent[] ; RECV: copied[]
+    uint32_t pf_cts;          // SEND: cts word index (mine); RECV: the sender's cts index
+    uint32_t pf_epoch;        // my epoch word
+    acx_pchan *pchan_d;       // device descriptor (lives in my pflags-adjacent area via cudaMalloc)
+    acx_pchan pchan_h;
+};
+
+struct AcxHostReg { uintptr_t lo, hi; char *dptr; };
+
+struct AcxState {
+    bool initialized = false;
+    bool device = false;      // GPU transport active
+    int rank = 0, size = 1, dev = -1;
+    int sm_count = 148;
+    acx_geom geom{};
+    // my windows
+    char *ctrl = nullptr, *heap = nullptr;
+    size_t heap_bytes = 0;
+    // peer mappings (index = rank; self = own pointers)
+    std::vector<char *> peer_ctrl, peer_heap;
+    // pinned host mirrors
+    acx_host_status *hstat = nullptr, *hstat_d = nullptr;
+    cudaStream_t istream = nullptr;  // internal non-blocking stream (host waits, start/finish)
+    // allocators
+    std::recursive_mutex mu;
+    std::vector<int> free_slots;
+    std::vector<char> slot_busy;     // 0 free, 1 in use (stream), 2 in use (graph)
+    std::vector<AcxRequest *> slot_req;
+    std::map<size_t, size_t> heap_free;      // offset -> size (free blocks)
+    std::unordered_map<size_t, size_t> heap_used;  // offset -> size
+    uint32_t pflags_next = 0;
+    std::vector<AcxHostReg> host_regs;
+    std::vector<MPI_Comm> comms;             // known communicators; index = context id
+    MPI_Comm icomm;                          // private dup of COMM_WORLD for handshakes
+    uint64_t serial = 1;
+    std::vector<std::vector<int>> recv_outstanding;  // [src][chan] posted-not-yet-waited recvs
+    // config
+    bool trace = false;
+    int verbose = 0;
+    long watchdog_ms = 0;
+    size_t mover_min_cta_bytes = 64 << 10;
+    int mover_max_ctas = 0;
+    // stats
+    struct {
+        std::atomic<unsigned long long> sends{0}, recvs{0}, waits{0}, bytes_sent{0}, bytes_recv{0}, eager{0}, rndv{0}, bounce{0},
+            kernels{0}, graph_nodes{0}, slots_hw{0}, heap_hw{0};
+    } st;
+    size_t heap_in_use = 0;
+    int slots_in_use = 0;
+    int pageable_access = 0;
+};
+
+extern AcxState *g_acx;
+
+#define ACX_REQ_MAGIC 0xACB200A1u
+
+#define ACX_ERR(...)                                                                         \
+    do {                                                                                     \
+        fprintf(stderr, "[acx %d] %s:%d %s: ", g_acx ? g_acx->rank : -1, __FILE__, __LINE__, __func__); \
+        fprintf(stderr, __VA_ARGS__);                                                        \
+        fprintf(stderr, "\n");                                                               \
+    } while (0)
+#define ACX_LOG(lvl, ...)                                                  \
+    do {                                                                   \
+        if (g_acx && g_acx->verbose >= (lvl)) {                                \
+            fprintf(stderr, "[acx %d] ", g_acx->rank);                       \
+            fprintf(stderr, __VA_ARGS__);                                  \
+            fprintf(stderr, "\n");                                         \
+        }                                                                  \
+    } while (0)
+#define ACX_CUDA(stmt)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (stmt);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ACX_ERR("%s failed: %s", #stmt, cudaGetErrorString(_e));                         \
+            return MPI_ERR_OTHER;                                                            \
+        }                                                                                    \
+    } while (0)
+
+// allocators (init.cu)
+int acx_slot_alloc(AcxRequest *r, bool graph);
+void acx_slot_free(int slot);
+void acx_reclaim_retired();
+int64_t acx_heap_alloc(size_t bytes);
+void acx_heap_free(int64_t off);
+int64_t acx_heap_offset_of(const void *p);  // -1 if not inside my heap
+uint32_t acx_pflags_alloc(uint32_t n);
+// Device-accessible alias of an arbitrary user pointer (host memory gets pinned+mapped).
+int acx_device_alias(const void *p, size_t bytes, char **out);
+int acx_comm_ctx(MPI_Comm comm, int *ctx);
+int acx_env_int(const char *name, const char *alt, long dflt, long *out);
+
+// layout helpers
+inline acx_entry *acx_entries_of(char *ctrl) { return (acx_entry *)(ctrl + g_acx->geom.off_entries); }
+inline acx_sack *acx_sacks_of(char *ctrl) { return (acx_sack *)(ctrl + g_acx->geom.off_sack); }
+inline uint64_t *acx_pflags_of(char *ctrl) { return (uint64_t *)(ctrl + g_acx->geom.off_pflags); }
+
+#endif  // __cplusplus
+#endif

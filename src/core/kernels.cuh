@@ -1,0 +1,355 @@
+// acx-b200 point-to-point kernels: triggers, data movers, waits.
+//
+// These replace the reference's four <<<1,1>>> flag kernels (set / wait / wait_and_set /
+// waitall, src/sendrecv.cu:44-72), which only poke a host-memory flag for a CPU proxy.
+// Here the kernels ARE the transport: they match, move payload over NVLink and signal.
+#ifndef ACX_KERNELS_CUH
+#define ACX_KERNELS_CUH
+
+#include "internal.h"
+
+namespace acxk {
+
+using namespace acx;
+
+constexpr int kTriggerThreads = 256;
+constexpr int kMoverThreads = 512;
+constexpr int kWaitThreads = 256;
+constexpr int kWaitBatch = 12;
+
+struct TraceCtx {
+    acx_trace_rec *ring;  // null when tracing is off
+    uint32_t mask;        // ring size - 1
+    uint64_t *cursor;
+};
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace(const TraceCtx &t, uint32_t ev, uint32_t peer, uint64_t a, uint64_t b) {
+    if (!t.ring) return;
+    uint64_t i = atomicAdd((unsigned long long *)t.cursor, 1ull);
+    acx_trace_rec *r = t.ring + (i & t.mask);
+    r->t_ns = globaltimer_ns(); r->ev = ev; r->peer = peer; r->a = a; r->b = b;
+}
+
+// Watchdog: a spin that exceeds the budget records a diagnostic and traps, instead of
+// hanging the GPU forever (the reference's spins have no timeout, src/sendrecv.cu:51).
+struct Watchdog {
+    uint64_t budget_ns;   // 0 = disabled
+    uint64_t *diag;       // [0]=code [1]=a [2]=b (pinned host memory)
+};
+__device__ __forceinline__ void spin_geq(const uint64_t *p, uint64_t v, const Watchdog &wd, uint64_t code) {
+    unsigned ns = 0;
+    uint64_t t0 = wd.budget_ns ? globaltimer_ns() : 0;
+    while (ld_acquire_sys(p) < v) {
+        if (ns) __nanosleep(ns);
+        ns = ns < 256 ? ns * 2 + 20 : 256;
+        if (wd.budget_ns && globaltimer_ns() - t0 > wd.budget_ns) {
+            wd.diag[1] = (uint64_t)p; wd.diag[2] = v; wd.diag[0] = code;
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Plain copy (bounce-in for private send buffers). Grid-stride, 16-B vectors.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMoverThreads) copy_kernel(char *dst, const char *src, uint64_t n) {
+    copy_bytes(dst, src, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// ---------------------------------------------------------------------------------------
+// SEND trigger: take a ticket, wait for slot credit, then either deposit eagerly or do
+// the rendezvous handshake (remote atomic on the slot's state word).
+// ---------------------------------------------------------------------------------------
+struct SendParams {
+    acx_entry *ring;        // peer-mapped: receiver's ring for (me -> dst, chan)
+    char *eager;            // peer-mapped: receiver's eager slots for that ring
+    acx_sack *sack;         // local: acks for (me -> dst, chan)
+    uint64_t *seq;          // local: send ticket counter
+    acx_op *op;             // local op record
+    const char *src;        // device-accessible source
+    char *peer_heap;        // peer-mapped heap base of dst
+    uint64_t src_off;       // heap offset of the (possibly bounced) source; rendezvous only
+    uint64_t bytes;
+    uint64_t serial;
+    uint32_t tag, depth, eager_max, peer;
+    Watchdog wd;
+    TraceCtx tr;
+};
+
+__global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
+    __shared__ uint64_t s_k;
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) {
+        uint64_t k = atomicAdd((unsigned long long *)p.seq, 1ull);
+        uint32_t e = (uint32_t)(k % p.depth);
+        uint64_t g = k / p.depth;
+        spin_geq(&p.sack[e].efree, g, p.wd, 0x5e01);  // slot's previous generation consumed
+        s_k = k;
+    }
+    __syncthreads();
+    const uint64_t k = s_k;
+    const uint32_t e = (uint32_t)(k % p.depth);
+    const uint64_t g = k / p.depth;
+    acx_entry *ent = p.ring + e;
+    if (p.bytes <= p.eager_max) {
+        copy_bytes(p.eager + (uint64_t)e * p.eager_max, p.src, p.bytes, tid, blockDim.x);
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            ent->s_bytes = p.bytes; ent->s_tag = p.tag; ent->s_kind = ACX_KIND_EAGER;
+            red_release_add_sys(&ent->state, 1ull << 32);
+            p.op->ticket = k; p.op->mover = 0; p.op->eager = 1;
+            st_release_sys(&p.op->armed, p.serial);
+            trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes);
+        }
+    } else if (tid == 0) {
+        ent->s_src_off = p.src_off; ent->s_bytes = p.bytes; ent->s_tag = p.tag; ent->s_kind = ACX_KIND_RNDV;
+        uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull << 32);
+        p.op->ticket = k; p.op->eager = 0; p.op->cta_count = 0;
+        if ((uint32_t)old == (uint32_t)(g + 1)) {  // receive already posted: I move the data (push)
+            uint64_t cap = ld_relaxed_sys(&ent->r_cap), off = ld_relaxed_sys(&ent->r_dst_off);
+            p.op->peer_ptr = (uint64_t)(p.peer_heap + off);
+            p.op->n = p.bytes < cap ? p.bytes : cap;
+            p.op->mover = 1;
+        } else {
+            p.op->mover = 0;
+        }
+        st_release_sys(&p.op->armed, p.serial);
+        trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes | (1ull << 63));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// RECV trigger: take a ticket, publish destination, add to the state word.
+// ---------------------------------------------------------------------------------------
+struct RecvParams {
+    acx_entry *ring;        // local ring for (src -> me, chan)
+    uint64_t *seq;          // local recv ticket counter
+    acx_op *op;
+    char *peer_heap;        // peer-mapped heap base of src
+    uint64_t dst_off;       // heap offset of destination (or bounce); ~0 when not rendezvous-capable
+    uint64_t cap;
+    uint64_t serial;
+    uint32_t depth, peer;
+    Watchdog wd;
+    TraceCtx tr;
+};
+
+__global__ void recv_trigger(RecvParams p) {
+    if (threadIdx.x != 0) return;
+    uint64_t k = atomicAdd((unsigned long long *)p.seq, 1ull);
+    uint32_t e = (uint32_t)(k % p.depth);
+    uint64_t g = k / p.depth;
+    acx_entry *ent = p.ring + e;
+    spin_geq(&ent->consumed, g, p.wd, 0x5e02);  // my own previous use of this slot is finished
+    ent->r_dst_off = p.dst_off; ent->r_cap = p.cap;
+    uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull);
+    p.op->ticket = k; p.op->cta_count = 0; p.op->mover = 0;
+    if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && ent->s_kind == ACX_KIND_RNDV) {
+        // the send is already here and waiting: I move the data (pull)
+        uint64_t sb = ent->s_bytes;
+        p.op->peer_ptr = (uint64_t)(p.peer_heap + ent->s_src_off);
+        p.op->n = sb < p.cap ? sb : p.cap;
+        p.op->mover = 1;
+    }
+    st_release_sys(&p.op->armed, p.serial);
+    trace(p.tr, ACX_EV_RECV_TRIGGER, p.peer, k, p.cap);
+}
+
+// ---------------------------------------------------------------------------------------
+// Mover: launched right after a rendezvous-capable trigger with a bandwidth-sized grid.
+// Exits immediately unless the trigger found this side to be the second arriver.
+//   push (sender second):  local src  -> peer dst   (STG over NVLink)
+//   pull (receiver second): peer src  -> local dst  (LDG over NVLink)
+// The last CTA to finish publishes completion to both sides.
+// ---------------------------------------------------------------------------------------
+struct MoverParams {
+    acx_op *op;
+    char *local;            // push: local source; pull: local destination
+    acx_entry *ring;        // push: peer-mapped ring; pull: local ring
+    acx_sack *sack;         // push: local sack; pull: peer-mapped sack at the sender
+    uint32_t depth, push, peer, pad;
+    TraceCtx tr;
+};
+
+__global__ void __launch_bounds__(kMoverThreads) mover(MoverParams p) {
+    acx_op *op = p.op;
+    if (!op->mover) return;
+    const uint64_t n = op->n;
+    char *peer = (char *)op->peer_ptr;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace(p.tr, ACX_EV_MOVE_BEGIN, p.peer, op->ticket, n);
+    // Contiguous chunk per CTA: keeps each CTA's NVLink stream sequential.
+    const uint64_t per = ((n + gridDim.x - 1) / gridDim.x + 127) & ~127ull;
+    const uint64_t lo = per * blockIdx.x;
+    if (lo < n) {
+        const uint64_t len = n - lo < per ? n - lo : per;
+        if (p.push) copy_bytes(peer + lo, p.local + lo, len, threadIdx.x, blockDim.x);
+        else copy_bytes(p.local + lo, peer + lo, len, threadIdx.x, blockDim.x);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(&op->cta_count, 1u);
+        if (t == gridDim.x - 1) {
+            __threadfence_system();
+            const uint64_t k = op->ticket;
+            const uint32_t e = (uint32_t)(k % p.depth);
+            const uint64_t g = k / p.depth;
+            op->cta_count = 0;
+            st_release_sys(&p.ring[e].done, g + 1);   // receiver may consume
+            st_release_sys(&p.sack[e].sdone, g + 1);  // sender's buffer is reusable
+            trace(p.tr, ACX_EV_MOVE_END, p.peer, k, n);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Waits. One CTA per request, up to kWaitBatch requests per launch (Waitall = 1 launch).
+// ---------------------------------------------------------------------------------------
+struct WaitOne {
+    acx_op *op;
+    acx_entry *ring;        // recv: local ring;  send: unused
+    acx_sack *sack;         // recv: peer-mapped sack at the sender; send: local sack
+    char *eager;            // recv: local eager slots of the ring
+    char *dst;              // recv: final destination (device-accessible)
+    char *bounce;           // recv: bounce buffer the mover filled (null if dst is in the heap)
+    acx_host_status *hstat; // pinned host record of this slot (device alias)
+    char *ustatus;          // device alias of the user's MPI_Status (null = ignore)
+    uint64_t cap;
+    uint64_t serial;        // != 0: first wait until op->armed == serial (host-side waits)
+    int32_t src, tag;
+    uint32_t depth, eager_max;
+    uint16_t is_recv, retire;
+    uint16_t off_source, off_tag, off_error, off_bytes;  // field offsets inside MPI_Status (0xffff = absent)
+};
+struct WaitBatch {
+    WaitOne w[kWaitBatch];
+    Watchdog wd;
+    TraceCtx tr;
+};
+
+__global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
+    const WaitOne &w = b.w[blockIdx.x];
+    __shared__ uint64_t s_n;
+    __shared__ int s_eager;
+    const unsigned tid = threadIdx.x;
+    acx_op *op = w.op;
+    if (tid == 0) {
+        if (w.serial) {
+            unsigned ns = 0;
+            uint64_t t0 = b.wd.budget_ns ? globaltimer_ns() : 0;
+            while (ld_acquire_sys(&op->armed) != w.serial) {
+                __nanosleep(ns); ns = ns < 256 ? ns * 2 + 20 : 256;
+                if (b.wd.budget_ns && globaltimer_ns() - t0 > b.wd.budget_ns) { b.wd.diag[1] = w.serial; b.wd.diag[0] = 0x5e05; __threadfence_system(); __trap(); }
+            }
+        }
+        const uint64_t k = op->ticket;
+        const uint32_t e = (uint32_t)(k % w.depth);
+        const uint64_t g = k / w.depth;
+        trace(b.tr, ACX_EV_WAIT_BEGIN, w.src, k, w.is_recv);
+        if (!w.is_recv) {
+            if (!op->eager) spin_geq(&w.sack[e].sdone, g + 1, b.wd, 0x5e03);
+            s_n = 0; s_eager = 0;
+        } else {
+            acx_entry *ent = w.ring + e;
+            // arrival: either an eager deposit (state.hi reached g+1 with kind EAGER) or mover done
+            unsigned ns = 0;
+            uint64_t t0 = b.wd.budget_ns ? globaltimer_ns() : 0;
+            int eager = 0;
+            for (;;) {
+                if (ld_acquire_sys(&ent->done) >= g + 1) break;
+                if ((uint32_t)(ld_acquire_sys(&ent->state) >> 32) >= (uint32_t)(g + 1) && ent->s_kind == ACX_KIND_EAGER) { eager = 1; break; }
+                if (ns) __nanosleep(ns);
+                ns = ns < 256 ? ns * 2 + 20 : 256;
+                if (b.wd.budget_ns && globaltimer_ns() - t0 > b.wd.budget_ns) { b.wd.diag[1] = k; b.wd.diag[2] = ent->state; b.wd.diag[0] = 0x5e04; __threadfence_system(); __trap(); }
+            }
+            uint64_t sb = ent->s_bytes;
+            s_n = sb < w.cap ? sb : w.cap;
+            s_eager = eager;
+        }
+    }
+    __syncthreads();
+    if (w.is_recv) {
+        const uint64_t k = op->ticket;
+        const uint32_t e = (uint32_t)(k % w.depth);
+        const uint64_t g = k / w.depth;
+        const uint64_t n = s_n;
+        if (s_eager) copy_bytes(w.dst, w.eager + (uint64_t)e * w.eager_max, n, tid, blockDim.x);
+        else if (w.bounce) copy_bytes(w.dst, w.bounce, n, tid, blockDim.x);
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            acx_entry *ent = w.ring + e;
+            const uint64_t sb = ent->s_bytes;
+            const int32_t err = (sb > w.cap) ? MPI_ERR_TRUNCATE : ((int32_t)ent->s_tag != w.tag ? MPI_ERR_TAG : MPI_SUCCESS);
+            op->recv_bytes = n;
+            if (w.ustatus) {
+                if (w.off_source != 0xffff) *(int32_t *)(w.ustatus + w.off_source) = w.src;
+                if (w.off_tag != 0xffff) *(int32_t *)(w.ustatus + w.off_tag) = (int32_t)ent->s_tag;
+                if (w.off_error != 0xffff) *(int32_t *)(w.ustatus + w.off_error) = err;
+                if (w.off_bytes != 0xffff) *(int64_t *)(w.ustatus + w.off_bytes) = (int64_t)n;
+            }
+            w.hstat->source = w.src; w.hstat->tag = (int32_t)ent->s_tag; w.hstat->error = err; w.hstat->bytes = (int64_t)n;
+            if (s_eager) st_release_sys(&ent->done, g + 1);
+            st_release_sys(&ent->consumed, g + 1);
+            st_release_sys(&w.sack[e].efree, g + 1);  // remote: slot may be reused by generation g+1
+        }
+    }
+    if (tid == 0) {
+        if (w.retire) { __threadfence_system(); w.hstat->retired = 1; }
+        trace(b.tr, ACX_EV_WAIT_END, w.src, op->ticket, s_n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Partitioned helpers (host Start / Wait paths; the device-side API is in acx_device.cuh)
+// ---------------------------------------------------------------------------------------
+__global__ void pstart_kernel(uint64_t *epoch_local, uint64_t *cts_remote, uint64_t e) {
+    st_release_sys(epoch_local, e);
+    if (cts_remote) { __threadfence_system(); st_release_sys(cts_remote, e); }
+}
+
+// Completes one round: SEND waits until every partition was marked ready (sent[p]==e);
+// RECV waits for every arrival and copies out what device pollers have not claimed.
+__global__ void __launch_bounds__(kWaitThreads) pwait_kernel(const acx_pchan *ch, uint64_t e, Watchdog wd) {
+    __shared__ int s_copy;
+    for (int p = 0; p < ch->partitions; p++) {
+        if (ch->kind == ACX_PKIND_SEND) {
+            if (threadIdx.x == 0) spin_geq(ch->local_flags + p, e, wd, 0x5e06);
+            continue;
+        }
+        if (threadIdx.x == 0) {
+            spin_geq(ch->arrived + p, e, wd, 0x5e07);
+            int do_copy = 0;
+            if (ch->land != ch->user_buf) {
+                const uint64_t done = 2 * e, claimed = 2 * e - 1;
+                uint64_t c = ld_acquire_sys(ch->local_flags + p);
+                if (c != done && c != claimed && atom_cas_acqrel_sys(ch->local_flags + p, c, claimed) == c) do_copy = 1;
+                else spin_geq(ch->local_flags + p, done, wd, 0x5e08);  // a device poller owns the copy
+            }
+            s_copy = do_copy;
+        }
+        __syncthreads();
+        if (s_copy) {
+            uint64_t off = (uint64_t)p * ch->part_bytes;
+            copy_bytes(ch->user_buf + off, ch->land + off, ch->part_bytes, threadIdx.x, blockDim.x);
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_sys(ch->local_flags + p, 2 * e);
+        }
+        __syncthreads();
+    }
+}
+
+// Host-callable single-partition operations (MPIX_Pready_host / MPIX_Parrived_host).
+__global__ void pready_host_kernel(const acx_pchan *ch, int p) { pready_cta(p, ch); }
+__global__ void parrived_host_kernel(const acx_pchan *ch, int p, int *flag) { parrived(ch, p, flag); }
+
+}  // namespace acxk
+#endif
