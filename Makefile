@@ -34,7 +34,12 @@ $(B)/acx.o: src/core/acx.cu src/core/internal.h src/core/kernels.cuh include/mpi
 	@mkdir -p $(B)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
-$(LIB): $(B)/acx.o $(B)/minimpi.o
+KOBJS := $(patsubst src/kernels/%.cu,$(B)/k_%.o,$(wildcard src/kernels/*.cu))
+$(B)/k_%.o: src/kernels/%.cu include/mpi-acx.h include/acx_device.cuh include/acx_kernels.h
+	@mkdir -p $(B)
+	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c $< -o $@ 2> $(B)/k_$*.ptxas.log || (cat $(B)/k_$*.ptxas.log; false)
+
+$(LIB): $(B)/acx.o $(B)/minimpi.o $(KOBJS)
 	@mkdir -p lib
 	$(NVCC) $(GENCODE) -shared -o $@ $^ -cudart static -ldl -lpthread -lrt
 

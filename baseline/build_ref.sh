@@ -3,7 +3,8 @@
 # the bundled mini-MPI (the image has no MPI). Nothing under /root/reference is edited: the
 # tree is copied to a scratch dir because its Makefile writes objects next to the sources.
 #   - MPI_ACX_MEMOPS_V2=1: the v1 memOps attribute no longer exists in CUDA 12
-#   - gencode sm_100 (the reference defaults to sm_80)
+#   - gencode sm_100a via the reference Makefile's own NVCC_GENCODE knob (it defaults to sm_80); the "a" target is
+#     needed because the shared pipeline-GEMM benchmark links a tcgen05 kernel against the library (RDC)
 # Then build the shared benchmark/test programs (bench/*.c,*.cu — written against the common
 # MPIX_* API) against the reference library, so both arms run the same harness.
 set -e
@@ -11,7 +12,7 @@ REPO=$(cd "$(dirname "$0")/.." && pwd)
 REF_SRC=${REF_SRC:-/root/reference}
 OUT=$REPO/baseline/_ref
 SCRATCH=$(mktemp -d /tmp/acx_ref_build.XXXXXX)
-GEN="-gencode=arch=compute_100,code=sm_100"
+GEN="-gencode=arch=compute_100a,code=sm_100a"
 make -C "$REPO" lib >/dev/null
 rm -rf "$OUT"; mkdir -p "$OUT"/{include,lib,bin,mpi/include,mpi/lib}
 cp "$REPO/include/mpi.h" "$OUT/mpi/include/mpi.h"

@@ -132,6 +132,21 @@ ACX_D int pready_signal(int p, const void *preq) {
     return 0;
 }
 
+// Explicit-epoch variants for persistent multi-step kernels that advance rounds on the
+// device (no host MPIX_Start between rounds; the caller guarantees buffer reuse safety, e.g.
+// by double buffering with a data dependence as the halo-stencil kernel does).
+ACX_D char *remote_partition_ptr_nowait(const void *preq, int p) {
+    const acx_pchan *ch = pchan(preq);
+    return ch->land + (uint64_t)p * ch->part_bytes;
+}
+ACX_D void pready_signal_epoch(int p, const void *preq, uint64_t e) {
+    const acx_pchan *ch = pchan(preq);
+    __threadfence_system();
+    st_release_sys(ch->arrived + p, e);
+}
+ACX_D bool parrived_epoch(const void *preq, int p, uint64_t e) { return ld_acquire_sys(pchan(preq)->arrived + p) >= e; }
+ACX_D void wait_arrived_epoch(const void *preq, int p, uint64_t e) { wait_geq_sys(pchan(preq)->arrived + p, e); }
+
 // Cooperative Pready: `nthr` threads (tid in [0,nthr)) of one warp or CTA copy the
 // partition from the local send buffer into the peer's landing buffer, then thread 0
 // publishes the flag. `sync` must be a barrier over exactly those threads.

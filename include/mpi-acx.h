@@ -82,6 +82,14 @@ int MPIX_Request_free(MPIX_Request *request);
 int MPIX_Alloc_mem(size_t bytes, MPI_Info info, void *baseptr /* void** */);
 int MPIX_Free_mem(void *base);
 
+/* Address of a symmetric-heap object as mapped from `peer`'s copy of the heap, i.e. the pointer
+ * this GPU dereferences to load/store the peer's instance directly over NVLink (cf. nvshmem_ptr).
+ * `local` must come from MPIX_Alloc_mem at the same allocation sequence point on both ranks. */
+int MPIX_Peer_ptr(const void *local, int peer, void **peer_ptr);
+/* Asymmetric allocations: exchange MPIX_Heap_offset() values, then map the peer's offset. */
+int MPIX_Heap_offset(const void *local, size_t *offset);
+int MPIX_Peer_ptr_at(size_t offset, int peer, void **peer_ptr);
+
 /* Host-side versions of the __host__ __device__ pair below (usable from C). */
 int MPIX_Pready_host(int partition, MPIX_Request *request);
 int MPIX_Parrived_host(MPIX_Request *request, int partition, int *flag);

@@ -99,7 +99,7 @@ int main(int argc, char **argv) {
             int code = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + WTERMSIG(st);
             if (code != 0) {
                 if (!killed) fprintf(stderr, "acxrun: rank %d exited with status %d%s\n", r, code, live ? "; terminating job" : "");
-                if (code > worst) worst = code;
+                if (!killed && (worst == 0 || code > worst)) worst = code;  // ranks we terminate ourselves do not count
                 if (!killed && live) { kill_all(SIGTERM); killed = true; t0 = now(); timeout = 5; }
             }
             continue;

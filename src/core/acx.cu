@@ -157,6 +157,14 @@ int64_t acx_heap_alloc(size_t bytes) {
         }
         acx_reclaim_retired();  // bounce buffers of retired requests come back here
     }
+    // Bounce buffers of in-flight stream operations return when their wait kernels retire: poll briefly.
+    for (int i = 0; i < 20000; i++) {
+        usleep(100);
+        acx_reclaim_retired();
+        for (auto it = g_acx->heap_free.begin(); it != g_acx->heap_free.end(); ++it)
+            if (it->second >= bytes) { i = 1 << 30; break; }
+        if (i >= (1 << 30)) return acx_heap_alloc(bytes);
+    }
     ACX_ERR("symmetric heap exhausted (%zu bytes requested, %zu in use of %zu); raise ACX_HEAP_BYTES", bytes, g_acx->heap_in_use,
             g_acx->heap_bytes);
     return -1;
@@ -497,6 +505,27 @@ extern "C" int MPIX_Free_mem(void *base) {
     return MPI_SUCCESS;
 }
 
+extern "C" int MPIX_Peer_ptr(const void *local, int peer, void **peer_ptr) {
+    if (!g_acx || !g_acx->device || !peer_ptr || peer < 0 || peer >= g_acx->size) return MPI_ERR_ARG;
+    int64_t off = acx_heap_offset_of(local);
+    if (off < 0) return MPI_ERR_BUFFER;
+    *peer_ptr = g_acx->peer_heap[peer] + off;
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Heap_offset(const void *local, size_t *offset) {
+    if (!g_acx || !g_acx->device || !offset) return MPI_ERR_ARG;
+    int64_t off = acx_heap_offset_of(local);
+    if (off < 0) return MPI_ERR_BUFFER;
+    *offset = (size_t)off;
+    return MPI_SUCCESS;
+}
+extern "C" int MPIX_Peer_ptr_at(size_t offset, int peer, void **peer_ptr) {
+    if (!g_acx || !g_acx->device || !peer_ptr || peer < 0 || peer >= g_acx->size || offset >= g_acx->heap_bytes) return MPI_ERR_ARG;
+    *peer_ptr = g_acx->peer_heap[peer] + offset;
+    return MPI_SUCCESS;
+}
+
 // =======================================================================================
 // emitter: the same op sequence goes to a stream, a capturing stream, or a fresh graph
 // =======================================================================================
@@ -673,6 +702,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         sp.sack = acx_sacks_of(g_acx->ctrl) + sack_idx;
         sp.seq = (uint64_t *)(g_acx->ctrl + G.off_send_seq) + ((uint64_t)dest * G.nchan + r->chan);
         sp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
+        sp.hstat = (eager && !r->in_graph) ? g_acx->hstat_d + r->slot : nullptr;
         sp.src = r->dev_buf;
         sp.peer_heap = g_acx->peer_heap[dest];
         sp.src_off = src_off; sp.bytes = bytes; sp.serial = r->serial;
@@ -754,6 +784,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         rp.ring = acx_entries_of(g_acx->ctrl) + ring_idx;
         rp.seq = (uint64_t *)(g_acx->ctrl + G.off_recv_seq) + ((uint64_t)source * G.nchan + r->chan);
         rp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
+        rp.sack = rndv_capable ? acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx : nullptr;
         rp.peer_heap = g_acx->peer_heap[source];
         rp.dst_off = dst_off; rp.cap = bytes; rp.serial = r->serial; rp.depth = G.depth; rp.peer = source;
         rp.wd = make_wd(); rp.tr = make_tr();
@@ -876,27 +907,56 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
         }
     }
     const bool retire = !em.in_graph();
-    int idx = 0;
-    for (size_t base = 0; base < rs.size(); base += kWaitBatch) {
-        WaitBatch wb;
-        memset(&wb, 0, sizeof wb);
-        int n = (int)std::min((size_t)kWaitBatch, rs.size() - base);
-        for (int j = 0; j < n; j++) {
-            // map back to the user's status slot
+    // Eager sends complete when their trigger kernel retires: stream/graph order already gives the
+    // guarantee a wait would, so no node is emitted for them (the trigger marks the slot retired).
+    struct Item { AcxRequest *r; MPI_Status *st; };
+    std::vector<Item> need;
+    {
+        int idx = 0;
+        for (AcxRequest *r : rs) {
             while (reqs[idx] == MPIX_REQUEST_NULL) idx++;
             MPI_Status *st = statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[idx];
-            AcxRequest *r = rs[base + j];
-            if (r->kind == ACX_REQ_SEND && st != MPI_STATUS_IGNORE && !em.in_graph()) host_status_send(st, r);
-            if ((rc = fill_wait(r, st, retire, false, &wb.w[j]))) return rc;
             idx++;
+            if (r->kind == ACX_REQ_SEND && st != MPI_STATUS_IGNORE && !em.in_graph()) host_status_send(st, r);
+            if (r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max) continue;
+            need.push_back({r, st});
+        }
+    }
+    for (size_t base = 0; base < need.size(); base += kWaitBatch) {
+        WaitBatch wb;
+        memset(&wb, 0, sizeof wb);
+        int n = (int)std::min((size_t)kWaitBatch, need.size() - base);
+        std::vector<AcxRequest *> bounced;
+        for (int j = 0; j < n; j++) {
+            AcxRequest *r = need[base + j].r;
+            // Large private destinations: copy-out at full width by a follow-up kernel, which then retires.
+            const bool big_bounce = r->kind == ACX_REQ_RECV && r->bounce_off >= 0 && r->bytes > (256u << 10);
+            if ((rc = fill_wait(r, need[base + j].st, retire && !big_bounce, false, &wb.w[j]))) return rc;
+            wb.w[j].bounce_kernel = big_bounce ? 1 : 0;
+            if (big_bounce) bounced.push_back(r);
         }
         wb.wd = make_wd(); wb.tr = make_tr();
         if ((rc = em.launch(wait_kernel, dim3(n), dim3(kWaitThreads), wb))) return rc;
+        for (AcxRequest *r : bounced) {
+            BounceOutParams bp;
+            memset(&bp, 0, sizeof bp);
+            bp.op = (acx_op *)(g_acx->ctrl + g_acx->geom.off_ops) + r->slot;
+            bp.dst = r->dev_buf; bp.bounce = g_acx->heap + r->bounce_off; bp.hstat = g_acx->hstat_d + r->slot; bp.retire = retire ? 1 : 0;
+            const bool par = em.parallel;
+            em.parallel = false;  // must follow the wait node
+            rc = em.launch(bounce_out_kernel, dim3(mover_grid(r->bytes)), dim3(kMoverThreads), bp);
+            em.parallel = par;
+            if (rc) return rc;
+        }
+    }
+    if (qtype == MPIX_QUEUE_CUDA_GRAPH && !em.last) {
+        cudaGraphNode_t node;
+        cudaGraphAddEmptyNode(&node, em.graph, nullptr, 0);
     }
     {
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
         for (AcxRequest *r : rs) {
-            if (retire) g_acx->slot_busy[r->slot] = 3;  // reclaimed once the wait kernel marks it retired
+            if (retire) g_acx->slot_busy[r->slot] = 3;  // reclaimed once the device marks it retired
             if (retire && r->kind == ACX_REQ_RECV && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
         }
     }
@@ -931,15 +991,28 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
         return rc;
     }
     if (r->in_graph) { ACX_ERR("in-graph operations must be completed by a wait inside a graph"); return MPI_ERR_REQUEST; }
-    WaitBatch wb;
-    memset(&wb, 0, sizeof wb);
-    int rc = fill_wait(r, MPI_STATUS_IGNORE, false, true, &wb.w[0]);
-    if (rc) return rc;
-    wb.wd = make_wd(); wb.tr = make_tr();
-    void *args[] = {&wb};
-    ACX_CUDA_WD(cudaLaunchKernel((const void *)wait_kernel, dim3(1), dim3(kWaitThreads), args, 0, g_acx->istream));
-    g_acx->st.kernels++;
-    ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    if (r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max) {
+        // eager send: complete once its trigger kernel has run; it says so in pinned host memory
+        volatile int32_t *flag = &g_acx->hstat[r->slot].retired;
+        auto t0 = std::chrono::steady_clock::now();
+        while (!*flag) {
+            if (g_acx->watchdog_ms > 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(g_acx->watchdog_ms)) {
+                ACX_ERR("MPIX_Wait: send was never triggered on its stream (waited %ld ms)", g_acx->watchdog_ms);
+                return MPI_ERR_OTHER;
+            }
+            std::this_thread::yield();
+        }
+    } else {
+        WaitBatch wb;
+        memset(&wb, 0, sizeof wb);
+        int rc = fill_wait(r, MPI_STATUS_IGNORE, false, true, &wb.w[0]);
+        if (rc) return rc;
+        wb.wd = make_wd(); wb.tr = make_tr();
+        void *args[] = {&wb};
+        ACX_CUDA_WD(cudaLaunchKernel((const void *)wait_kernel, dim3(1), dim3(kWaitThreads), args, 0, g_acx->istream));
+        g_acx->st.kernels++;
+        ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    }
     if (status != MPI_STATUS_IGNORE) {
         if (r->kind == ACX_REQ_SEND) host_status_send(status, r);
         else {

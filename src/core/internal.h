@@ -44,9 +44,11 @@ struct alignas(64) acx_entry {  // one slot of a (src -> me, channel) ring; live
     uint32_t s_kind;     // ACX_KIND_*
 };
 
-struct alignas(16) acx_sack {  // per slot, lives at the SENDER, written by the receiver / mover
-    uint64_t sdone;   // #generations whose send completed (source buffer reusable)
-    uint64_t efree;   // #generations the receiver has consumed (slot reusable by generation efree)
+struct alignas(32) acx_sack {  // per slot, lives at the SENDER, written by the receiver / mover
+    uint64_t sdone;      // #generations whose send completed (source buffer reusable)
+    uint64_t efree;      // #generations the receiver has consumed (slot reusable by generation efree)
+    uint64_t r_dst_off;  // mirror of the receiver's posted destination (so a late sender reads it locally)
+    uint64_t r_cap;
 };
 
 struct alignas(64) acx_op {  // per request slot, local
@@ -59,6 +61,7 @@ struct alignas(64) acx_op {  // per request slot, local
     uint32_t cta_count;  // last-CTA detection
     uint32_t pad;
     uint64_t recv_bytes; // receive side: actual message size
+    uint64_t bounce_n;   // receive side: bytes the bounce-out kernel still has to copy (0 if eager/zero-copy)
 };
 
 struct acx_host_status {  // pinned host memory, one per request slot; written by wait kernels

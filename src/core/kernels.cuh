@@ -72,6 +72,7 @@ struct SendParams {
     acx_sack *sack;         // local: acks for (me -> dst, chan)
     uint64_t *seq;          // local: send ticket counter
     acx_op *op;             // local op record
+    acx_host_status *hstat; // pinned host record (null: do not signal the host)
     const char *src;        // device-accessible source
     char *peer_heap;        // peer-mapped heap base of dst
     uint64_t src_off;       // heap offset of the (possibly bounced) source; rendezvous only
@@ -98,22 +99,26 @@ __global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
     const uint64_t g = k / p.depth;
     acx_entry *ent = p.ring + e;
     if (p.bytes <= p.eager_max) {
+        // Eager: payload + header into the receiver's slot, then ONE release (the barrier makes the
+        // other threads' stores cumulative under thread 0's release).
         copy_bytes(p.eager + (uint64_t)e * p.eager_max, p.src, p.bytes, tid, blockDim.x);
-        __threadfence_system();
         __syncthreads();
         if (tid == 0) {
-            ent->s_bytes = p.bytes; ent->s_tag = p.tag; ent->s_kind = ACX_KIND_EAGER;
+            ent->s_bytes = p.bytes;
+            *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)ACX_KIND_EAGER << 32);
             red_release_add_sys(&ent->state, 1ull << 32);
-            p.op->ticket = k; p.op->mover = 0; p.op->eager = 1;
-            st_release_sys(&p.op->armed, p.serial);
+            // The source buffer is reusable as soon as this kernel retires: nothing to wait for later.
+            if (p.hstat) p.hstat->retired = 1;
             trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes);
         }
     } else if (tid == 0) {
-        ent->s_src_off = p.src_off; ent->s_bytes = p.bytes; ent->s_tag = p.tag; ent->s_kind = ACX_KIND_RNDV;
+        ent->s_src_off = p.src_off; ent->s_bytes = p.bytes;
+        *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)ACX_KIND_RNDV << 32);
         uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull << 32);
         p.op->ticket = k; p.op->eager = 0; p.op->cta_count = 0;
         if ((uint32_t)old == (uint32_t)(g + 1)) {  // receive already posted: I move the data (push)
-            uint64_t cap = ld_relaxed_sys(&ent->r_cap), off = ld_relaxed_sys(&ent->r_dst_off);
+            // the receiver mirrored its destination into MY sack before it bumped the state word
+            uint64_t cap = ld_relaxed_sys(&p.sack[e].r_cap), off = ld_relaxed_sys(&p.sack[e].r_dst_off);
             p.op->peer_ptr = (uint64_t)(p.peer_heap + off);
             p.op->n = p.bytes < cap ? p.bytes : cap;
             p.op->mover = 1;
@@ -130,6 +135,7 @@ __global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
 // ---------------------------------------------------------------------------------------
 struct RecvParams {
     acx_entry *ring;        // local ring for (src -> me, chan)
+    acx_sack *sack;         // peer-mapped: the sender's sack for (src -> me, chan); null if not rendezvous-capable
     uint64_t *seq;          // local recv ticket counter
     acx_op *op;
     char *peer_heap;        // peer-mapped heap base of src
@@ -148,9 +154,12 @@ __global__ void recv_trigger(RecvParams p) {
     uint64_t g = k / p.depth;
     acx_entry *ent = p.ring + e;
     spin_geq(&ent->consumed, g, p.wd, 0x5e02);  // my own previous use of this slot is finished
-    ent->r_dst_off = p.dst_off; ent->r_cap = p.cap;
-    uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull);
-    p.op->ticket = k; p.op->cta_count = 0; p.op->mover = 0;
+    if (p.sack) {  // mirror the destination into the sender's memory: a late sender then needs no remote load
+        st_relaxed_sys(&p.sack[e].r_dst_off, p.dst_off);
+        st_relaxed_sys(&p.sack[e].r_cap, p.cap);
+    }
+    uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull);   // release orders the mirror stores before it
+    p.op->ticket = k; p.op->cta_count = 0; p.op->mover = 0; p.op->bounce_n = 0;
     if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && ent->s_kind == ACX_KIND_RNDV) {
         // the send is already here and waiting: I move the data (pull)
         uint64_t sb = ent->s_bytes;
@@ -192,18 +201,18 @@ __global__ void __launch_bounds__(kMoverThreads) mover(MoverParams p) {
         if (p.push) copy_bytes(peer + lo, p.local + lo, len, threadIdx.x, blockDim.x);
         else copy_bytes(p.local + lo, peer + lo, len, threadIdx.x, blockDim.x);
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();   // one fence per CTA, cumulative over the CTA's stores (ordered by the barrier)
         unsigned t = atomicAdd(&op->cta_count, 1u);
         if (t == gridDim.x - 1) {
-            __threadfence_system();
+            __threadfence();
             const uint64_t k = op->ticket;
             const uint32_t e = (uint32_t)(k % p.depth);
             const uint64_t g = k / p.depth;
             op->cta_count = 0;
-            st_release_sys(&p.ring[e].done, g + 1);   // receiver may consume
-            st_release_sys(&p.sack[e].sdone, g + 1);  // sender's buffer is reusable
+            st_relaxed_sys(&p.ring[e].done, g + 1);   // receiver may consume
+            st_relaxed_sys(&p.sack[e].sdone, g + 1);  // sender's buffer is reusable
             trace(p.tr, ACX_EV_MOVE_END, p.peer, k, n);
         }
     }
@@ -226,6 +235,7 @@ struct WaitOne {
     int32_t src, tag;
     uint32_t depth, eager_max;
     uint16_t is_recv, retire;
+    uint16_t bounce_kernel, pad16;  // bounce_kernel: a bounce_out_kernel follows (large private destination)
     uint16_t off_source, off_tag, off_error, off_bytes;  // field offsets inside MPI_Status (0xffff = absent)
 };
 struct WaitBatch {
@@ -254,7 +264,7 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
         const uint64_t g = k / w.depth;
         trace(b.tr, ACX_EV_WAIT_BEGIN, w.src, k, w.is_recv);
         if (!w.is_recv) {
-            if (!op->eager) spin_geq(&w.sack[e].sdone, g + 1, b.wd, 0x5e03);
+            spin_geq(&w.sack[e].sdone, g + 1, b.wd, 0x5e03);
             s_n = 0; s_eager = 0;
         } else {
             acx_entry *ent = w.ring + e;
@@ -281,29 +291,51 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
         const uint64_t g = k / w.depth;
         const uint64_t n = s_n;
         if (s_eager) copy_bytes(w.dst, w.eager + (uint64_t)e * w.eager_max, n, tid, blockDim.x);
-        else if (w.bounce) copy_bytes(w.dst, w.bounce, n, tid, blockDim.x);
-        __threadfence_system();
+        else if (w.bounce && !w.bounce_kernel) copy_bytes(w.dst, w.bounce, n, tid, blockDim.x);
         __syncthreads();
         if (tid == 0) {
             acx_entry *ent = w.ring + e;
             const uint64_t sb = ent->s_bytes;
-            const int32_t err = (sb > w.cap) ? MPI_ERR_TRUNCATE : ((int32_t)ent->s_tag != w.tag ? MPI_ERR_TAG : MPI_SUCCESS);
+            const int32_t stag = (int32_t)ent->s_tag;
+            const int32_t err = (sb > w.cap) ? MPI_ERR_TRUNCATE : (stag != w.tag ? MPI_ERR_TAG : MPI_SUCCESS);
             op->recv_bytes = n;
+            op->bounce_n = (w.bounce && w.bounce_kernel && !s_eager) ? n : 0;
             if (w.ustatus) {
                 if (w.off_source != 0xffff) *(int32_t *)(w.ustatus + w.off_source) = w.src;
-                if (w.off_tag != 0xffff) *(int32_t *)(w.ustatus + w.off_tag) = (int32_t)ent->s_tag;
+                if (w.off_tag != 0xffff) *(int32_t *)(w.ustatus + w.off_tag) = stag;
                 if (w.off_error != 0xffff) *(int32_t *)(w.ustatus + w.off_error) = err;
                 if (w.off_bytes != 0xffff) *(int64_t *)(w.ustatus + w.off_bytes) = (int64_t)n;
             }
-            w.hstat->source = w.src; w.hstat->tag = (int32_t)ent->s_tag; w.hstat->error = err; w.hstat->bytes = (int64_t)n;
-            if (s_eager) st_release_sys(&ent->done, g + 1);
-            st_release_sys(&ent->consumed, g + 1);
-            st_release_sys(&w.sack[e].efree, g + 1);  // remote: slot may be reused by generation g+1
+            if (w.serial) { w.hstat->source = w.src; w.hstat->tag = stag; w.hstat->error = err; w.hstat->bytes = (int64_t)n; }
+            // All reads of the slot are complete (data dependence + barrier): plain stores suffice.
+            st_relaxed_sys(&ent->consumed, g + 1);
+            st_relaxed_sys(&w.sack[e].efree, g + 1);  // remote: slot may be reused by generation g+1
         }
     }
     if (tid == 0) {
-        if (w.retire) { __threadfence_system(); w.hstat->retired = 1; }
+        if (w.retire) w.hstat->retired = 1;
         trace(b.tr, ACX_EV_WAIT_END, w.src, op->ticket, s_n);
+    }
+}
+
+// Copy-out of a bounced (private-destination) rendezvous receive at full width; the last CTA
+// retires the slot. Launched right after the wait kernel when the destination is not in the heap.
+struct BounceOutParams {
+    acx_op *op;
+    char *dst;
+    const char *bounce;
+    acx_host_status *hstat;
+    uint32_t retire, pad;
+};
+__global__ void __launch_bounds__(kMoverThreads) bounce_out_kernel(BounceOutParams p) {
+    const uint64_t n = p.op->bounce_n;
+    if (n) copy_bytes(p.dst, p.bounce, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    if (!p.retire) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicAdd(&p.op->cta_count, 1u);
+        if (t == gridDim.x - 1) { p.op->cta_count = 0; p.hstat->retired = 1; }
     }
 }
 

@@ -1,0 +1,311 @@
+// Fused halo-exchange + 3-D 7-point stencil for sm_100a (BASELINE.json config #3).
+//
+// There is nothing like this in the reference (it never touches payload).
+// Each rank owns an nx*ny*nz bf16 block of a periodic px*py*pz decomposition. One kernel
+// per time step does everything:
+//   * tiles on a block face first wait (ld.acquire on LOCAL HBM flags) for the neighbour's
+//     face partition of the previous step, which the neighbour's kernel stored straight
+//     into this GPU's landing buffers over NVLink;
+//   * every tile z-marches through its 256x16x32 cells (16-B vector loads, fp32 math,
+//     y-neighbours through shared memory, x-neighbours through warp shuffles);
+//   * face cells are stored twice: into the local output array and — packed, 16-B vectors —
+//     into the neighbour's landing buffer (peer-mapped partitioned channel), followed by
+//     a release flag per partition (acx::pready_signal_epoch);
+//   * boundary tiles are scheduled first so the NVLink traffic overlaps the interior.
+// The 12+12 partitioned channels are ordinary MPIX_Psend_init/Precv_init requests on
+// symmetric-heap buffers; rounds advance on the device (explicit epochs), double-buffered.
+// Host involvement per step: one kernel launch (capturable in a CUDA graph).
+#include <mpi.h>
+#include "../../include/mpi-acx.h"
+#include "../../include/acx_kernels.h"
+#include <cuda_bf16.h>
+#include <stdio.h>
+#include <vector>
+#include <algorithm>
+
+namespace {
+
+constexpr int TX = 256, TY = 16, TZ = 32;   // tile; 32 lanes x 8 cells along x, 16 rows, z-march of 32
+constexpr int LX = 32;
+
+struct HaloDev {
+    const __nv_bfloat16 *u;
+    __nv_bfloat16 *un;
+    int nx, ny, nz, ntx, nty, ntz;
+    const acx_pchan *send[6];   // my face f -> neighbour in direction f (buffers of parity (s+1)&1)
+    const acx_pchan *recv[6];   // halo from direction f (parity s&1)
+    unsigned long long wait_val, signal_val;
+    float c0, c1;
+    const int *order;
+    int ntiles;
+};
+
+__device__ __forceinline__ void unpack8(const uint4 &v, float f[8]) {
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float f[8]) {
+    uint4 v;
+    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+}
+__device__ __forceinline__ float bf(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
+// Face ids: 0 X-, 1 X+, 2 Y-, 3 Y+, 4 Z-, 5 Z+.
+__global__ void __launch_bounds__(LX * TY, 2) halo_stencil_step(HaloDev P) {
+    __shared__ uint4 rows[2][TY][LX];                 // current plane, double-buffered (16 KiB)
+    __shared__ __align__(16) __nv_bfloat16 xface[2][TZ * TY];  // packed X-/X+ face of this tile (2 KiB)
+    const int lx = threadIdx.x, ly = threadIdx.y;
+    const int tid = ly * LX + lx;
+    const size_t plane = (size_t)P.nx * P.ny;
+    for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x) {
+        const int t = P.order[it];
+        const int tx = t % P.ntx, ty = (t / P.ntx) % P.nty, tz = t / (P.ntx * P.nty);
+        const bool fxm = tx == 0, fxp = tx == P.ntx - 1, fym = ty == 0, fyp = ty == P.nty - 1, fzm = tz == 0, fzp = tz == P.ntz - 1;
+        const int px_ = tz * P.nty + ty, py_ = tz * P.ntx + tx, pz_ = ty * P.ntx + tx;   // partition index per face family
+        if (tid == 0) {
+            if (fxm) acx::wait_arrived_epoch(P.recv[0], px_, P.wait_val);
+            if (fxp) acx::wait_arrived_epoch(P.recv[1], px_, P.wait_val);
+            if (fym) acx::wait_arrived_epoch(P.recv[2], py_, P.wait_val);
+            if (fyp) acx::wait_arrived_epoch(P.recv[3], py_, P.wait_val);
+            if (fzm) acx::wait_arrived_epoch(P.recv[4], pz_, P.wait_val);
+            if (fzp) acx::wait_arrived_epoch(P.recv[5], pz_, P.wait_val);
+        }
+        __syncthreads();
+        const int x0 = tx * TX + lx * 8, y = ty * TY + ly, z0 = tz * TZ;
+        // landing buffers (local) and remote partitions for this tile
+        const __nv_bfloat16 *hxm = fxm ? (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[0], px_) : nullptr;
+        const __nv_bfloat16 *hxp = fxp ? (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[1], px_) : nullptr;
+        const uint4 *hym = fym ? (const uint4 *)acx::local_partition_ptr(P.recv[2], py_) : nullptr;
+        const uint4 *hyp = fyp ? (const uint4 *)acx::local_partition_ptr(P.recv[3], py_) : nullptr;
+        const uint4 *hzm = fzm ? (const uint4 *)acx::local_partition_ptr(P.recv[4], pz_) : nullptr;
+        const uint4 *hzp = fzp ? (const uint4 *)acx::local_partition_ptr(P.recv[5], pz_) : nullptr;
+        uint4 *rym = fym ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[2], py_) : nullptr;
+        uint4 *ryp = fyp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[3], py_) : nullptr;
+        uint4 *rzm = fzm ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[4], pz_) : nullptr;
+        uint4 *rzp = fzp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[5], pz_) : nullptr;
+
+        const __nv_bfloat16 *col = P.u + (size_t)y * P.nx + x0;   // + z*plane
+        auto load_plane = [&](int z) -> uint4 {
+            if (z < 0) return hzm[ly * LX + lx];
+            if (z >= P.nz) return hzp[ly * LX + lx];
+            return *reinterpret_cast<const uint4 *>(col + (size_t)z * plane);
+        };
+        float prev[8], cur[8], nxt[8];
+        uint4 vcur = load_plane(z0), vnext;
+        unpack8(load_plane(z0 - 1), prev);
+        unpack8(vcur, cur);
+        for (int zl = 0; zl < TZ; zl++) {
+            const int z = z0 + zl;
+            vnext = load_plane(z + 1);
+            rows[zl & 1][ly][lx] = vcur;
+            // x neighbours of the 8-cell vector's ends
+            float left = __shfl_up_sync(0xffffffffu, cur[7], 1), right = __shfl_down_sync(0xffffffffu, cur[0], 1);
+            if (lx == 0) left = fxm ? __bfloat162float(hxm[zl * TY + ly]) : bf(col + (size_t)z * plane - 1);
+            if (lx == LX - 1) right = fxp ? __bfloat162float(hxp[zl * TY + ly]) : bf(col + (size_t)z * plane + 8);
+            __syncthreads();
+            float ym[8], yp[8];
+            if (ly > 0) unpack8(rows[zl & 1][ly - 1][lx], ym);
+            else unpack8(fym ? hym[zl * LX + lx] : *reinterpret_cast<const uint4 *>(col + (size_t)z * plane - P.nx), ym);
+            if (ly < TY - 1) unpack8(rows[zl & 1][ly + 1][lx], yp);
+            else unpack8(fyp ? hyp[zl * LX + lx] : *reinterpret_cast<const uint4 *>(col + (size_t)z * plane + P.nx), yp);
+            unpack8(vnext, nxt);
+            float out[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float xm = i == 0 ? left : cur[i - 1], xp = i == 7 ? right : cur[i + 1];
+                out[i] = P.c0 * cur[i] + P.c1 * (((xm + xp) + (ym[i] + yp[i])) + (prev[i] + nxt[i]));
+            }
+            const uint4 vo = pack8(out);
+            *reinterpret_cast<uint4 *>(P.un + (size_t)z * plane + (size_t)y * P.nx + x0) = vo;
+            // face cells also go straight into the neighbours' landing buffers (NVLink stores)
+            if (fzm && zl == 0) rzm[ly * LX + lx] = vo;
+            if (fzp && zl == TZ - 1) rzp[ly * LX + lx] = vo;
+            if (fym && ly == 0) rym[zl * LX + lx] = vo;
+            if (fyp && ly == TY - 1) ryp[zl * LX + lx] = vo;
+            if (fxm && lx == 0) xface[0][zl * TY + ly] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[0];
+            if (fxp && lx == LX - 1) xface[1][zl * TY + ly] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[7];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { prev[i] = cur[i]; cur[i] = nxt[i]; }
+            vcur = vnext;
+        }
+        __syncthreads();
+        if (fxm && tid < TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[0], px_))[tid] = ((const uint4 *)xface[0])[tid];
+        if (fxp && tid >= 64 && tid < 64 + TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[1], px_))[tid - 64] = ((const uint4 *)xface[1])[tid - 64];
+        if (fxm | fxp | fym | fyp | fzm | fzp) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                if (fxm) acx::pready_signal_epoch(px_, P.send[0], P.signal_val);
+                if (fxp) acx::pready_signal_epoch(px_, P.send[1], P.signal_val);
+                if (fym) acx::pready_signal_epoch(py_, P.send[2], P.signal_val);
+                if (fyp) acx::pready_signal_epoch(py_, P.send[3], P.signal_val);
+                if (fzm) acx::pready_signal_epoch(pz_, P.send[4], P.signal_val);
+                if (fzp) acx::pready_signal_epoch(pz_, P.send[5], P.signal_val);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Initial exchange: faces of u^0 -> neighbours' parity-0 landing buffers, flag value 1.
+// One CTA per (face, partition).
+struct PackDev {
+    const __nv_bfloat16 *u;
+    int nx, ny, nz, ntx, nty, ntz;
+    const acx_pchan *send[6];
+    unsigned long long signal_val;
+};
+__global__ void halo_pack_faces(PackDev P) {
+    const int f = blockIdx.y, p = blockIdx.x;
+    const int nparts = f < 2 ? P.nty * P.ntz : f < 4 ? P.ntx * P.ntz : P.ntx * P.nty;
+    if (p >= nparts) return;
+    __nv_bfloat16 *dst = (__nv_bfloat16 *)acx::remote_partition_ptr_nowait(P.send[f], p);
+    const size_t plane = (size_t)P.nx * P.ny;
+    if (f < 2) {
+        const int tz = p / P.nty, ty = p % P.nty, x = f == 0 ? 0 : P.nx - 1;
+        for (int i = threadIdx.x; i < TZ * TY; i += blockDim.x) {
+            const int zl = i / TY, yl = i % TY;
+            dst[i] = P.u[(size_t)(tz * TZ + zl) * plane + (size_t)(ty * TY + yl) * P.nx + x];
+        }
+    } else if (f < 4) {
+        const int tz = p / P.ntx, tx = p % P.ntx, y = f == 2 ? 0 : P.ny - 1;
+        for (int i = threadIdx.x; i < TZ * TX; i += blockDim.x) {
+            const int zl = i / TX, xl = i % TX;
+            dst[i] = P.u[(size_t)(tz * TZ + zl) * plane + (size_t)y * P.nx + tx * TX + xl];
+        }
+    } else {
+        const int ty = p / P.ntx, tx = p % P.ntx, z = f == 4 ? 0 : P.nz - 1;
+        for (int i = threadIdx.x; i < TY * TX; i += blockDim.x) {
+            const int yl = i / TX, xl = i % TX;
+            dst[i] = P.u[(size_t)z * plane + (size_t)(ty * TY + yl) * P.nx + tx * TX + xl];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) acx::pready_signal_epoch(p, P.send[f], P.signal_val);
+}
+
+}  // namespace
+
+struct acx_halo {
+    int nx, ny, nz, px, py, pz, rank, size;
+    int ntx, nty, ntz, ntiles;
+    float c0, c1;
+    __nv_bfloat16 *u[2];
+    int cur;                       // u[cur] holds u^step
+    unsigned long long step;       // number of completed steps
+    bool exchanged;
+    void *land[2][6];              // recv landing buffers per parity/face (symmetric heap)
+    MPIX_Request sreq[2][6], rreq[2][6];
+    MPIX_Prequest spre[2][6], rpre[2][6];
+    int *order_d;
+    int grid;
+};
+
+#define HCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[acx halo] %s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return 1; } } while (0)
+#define HOK(x) do { int r_ = (x); if (r_) { fprintf(stderr, "[acx halo] %s:%d %s -> %d\n", __FILE__, __LINE__, #x, r_); return 1; } } while (0)
+
+extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, float c0, float c1, acx_halo **out) {
+    int rank, size;
+    MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+    MPI_Comm_size(MPI_COMM_WORLD, &size);
+    if (px * py * pz != size) { fprintf(stderr, "[acx halo] decomposition %dx%dx%d != %d ranks\n", px, py, pz, size); return 1; }
+    if (nx % TX || ny % TY || nz % TZ) { fprintf(stderr, "[acx halo] block %dx%dx%d must be a multiple of the %dx%dx%d tile\n", nx, ny, nz, TX, TY, TZ); return 1; }
+    acx_halo *h = new acx_halo();
+    h->nx = nx; h->ny = ny; h->nz = nz; h->px = px; h->py = py; h->pz = pz; h->rank = rank; h->size = size; h->c0 = c0; h->c1 = c1;
+    h->ntx = nx / TX; h->nty = ny / TY; h->ntz = nz / TZ; h->ntiles = h->ntx * h->nty * h->ntz;
+    h->cur = 0; h->step = 0; h->exchanged = false;
+    const size_t cells = (size_t)nx * ny * nz;
+    HCK(cudaMalloc((void **)&h->u[0], cells * 2));
+    HCK(cudaMalloc((void **)&h->u[1], cells * 2));
+    const int cx = rank % px, cy = (rank / px) % py, cz = rank / (px * py);
+    auto rk = [&](int x, int y, int z) { return (((z + pz) % pz) * py + ((y + py) % py)) * px + ((x + px) % px); };
+    const int nbr[6] = {rk(cx - 1, cy, cz), rk(cx + 1, cy, cz), rk(cx, cy - 1, cz), rk(cx, cy + 1, cz), rk(cx, cy, cz - 1), rk(cx, cy, cz + 1)};
+    const int nparts[6] = {h->nty * h->ntz, h->nty * h->ntz, h->ntx * h->ntz, h->ntx * h->ntz, h->ntx * h->nty, h->ntx * h->nty};
+    const size_t pbytes[6] = {(size_t)TY * TZ * 2, (size_t)TY * TZ * 2, (size_t)TX * TZ * 2, (size_t)TX * TZ * 2, (size_t)TX * TY * 2, (size_t)TX * TY * 2};
+    for (int par = 0; par < 2; par++)
+        for (int f = 0; f < 6; f++) {
+            HOK(MPIX_Alloc_mem(nparts[f] * pbytes[f], MPI_INFO_NULL, &h->land[par][f]));
+            HCK(cudaMemset(h->land[par][f], 0, nparts[f] * pbytes[f]));
+            // My face f travels to nbr[f] and lands in ITS "halo from direction f^1" buffer: tag by the sender's face id.
+            const int tag_send = 100 + par * 8 + f, tag_recv = 100 + par * 8 + (f ^ 1);
+            HOK(MPIX_Psend_init(nullptr, nparts[f], (MPI_Count)pbytes[f], MPI_BYTE, nbr[f], tag_send, MPI_COMM_WORLD, MPI_INFO_NULL, &h->sreq[par][f]));
+            HOK(MPIX_Precv_init(h->land[par][f], nparts[f], (MPI_Count)pbytes[f], MPI_BYTE, nbr[f], tag_recv, MPI_COMM_WORLD, MPI_INFO_NULL, &h->rreq[par][f]));
+        }
+    for (int par = 0; par < 2; par++)
+        for (int f = 0; f < 6; f++) {
+            HOK(MPIX_Prequest_create(h->sreq[par][f], &h->spre[par][f]));
+            HOK(MPIX_Prequest_create(h->rreq[par][f], &h->rpre[par][f]));
+        }
+    // boundary tiles first: their NVLink stores overlap the interior sweep
+    std::vector<int> order(h->ntiles);
+    for (int i = 0; i < h->ntiles; i++) order[i] = i;
+    auto nfaces = [&](int t) {
+        int tx = t % h->ntx, ty = (t / h->ntx) % h->nty, tz = t / (h->ntx * h->nty);
+        return (tx == 0) + (tx == h->ntx - 1) + (ty == 0) + (ty == h->nty - 1) + (tz == 0) + (tz == h->ntz - 1);
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nfaces(a) > nfaces(b); });
+    HCK(cudaMalloc((void **)&h->order_d, sizeof(int) * h->ntiles));
+    HCK(cudaMemcpy(h->order_d, order.data(), sizeof(int) * h->ntiles, cudaMemcpyHostToDevice));
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step, LX * TY, 0);
+    if (occ < 1) occ = 1;
+    h->grid = std::min(h->ntiles, sms * occ);
+    MPI_Barrier(MPI_COMM_WORLD);
+    *out = h;
+    return 0;
+}
+
+extern "C" void *acx_halo_field(acx_halo *h) { return h->u[h->cur]; }
+extern "C" unsigned long long acx_halo_steps_done(acx_halo *h) { return h->step; }
+
+extern "C" int acx_halo_exchange_initial(acx_halo *h, cudaStream_t stream) {
+    PackDev P;
+    P.u = h->u[h->cur]; P.nx = h->nx; P.ny = h->ny; P.nz = h->nz; P.ntx = h->ntx; P.nty = h->nty; P.ntz = h->ntz;
+    const int par = (int)(h->step & 1);
+    for (int f = 0; f < 6; f++) P.send[f] = (const acx_pchan *)h->spre[par][f];
+    P.signal_val = h->step + 1;
+    int maxp = std::max(h->nty * h->ntz, std::max(h->ntx * h->ntz, h->ntx * h->nty));
+    halo_pack_faces<<<dim3(maxp, 6), 256, 0, stream>>>(P);
+    HCK(cudaGetLastError());
+    h->exchanged = true;
+    return 0;
+}
+
+extern "C" int acx_halo_step(acx_halo *h, int nsteps, cudaStream_t stream) {
+    if (!h->exchanged) HOK(acx_halo_exchange_initial(h, stream));
+    for (int s = 0; s < nsteps; s++) {
+        HaloDev P;
+        P.u = h->u[h->cur]; P.un = h->u[h->cur ^ 1];
+        P.nx = h->nx; P.ny = h->ny; P.nz = h->nz; P.ntx = h->ntx; P.nty = h->nty; P.ntz = h->ntz;
+        const int rp = (int)(h->step & 1), sp = rp ^ 1;
+        for (int f = 0; f < 6; f++) { P.recv[f] = (const acx_pchan *)h->rpre[rp][f]; P.send[f] = (const acx_pchan *)h->spre[sp][f]; }
+        P.wait_val = h->step + 1; P.signal_val = h->step + 2;
+        P.c0 = h->c0; P.c1 = h->c1; P.order = h->order_d; P.ntiles = h->ntiles;
+        halo_stencil_step<<<h->grid, dim3(LX, TY), 0, stream>>>(P);
+        HCK(cudaGetLastError());
+        h->cur ^= 1;
+        h->step++;
+    }
+    return 0;
+}
+
+extern "C" int acx_halo_destroy(acx_halo *h) {
+    cudaDeviceSynchronize();
+    MPI_Barrier(MPI_COMM_WORLD);
+    for (int par = 0; par < 2; par++)
+        for (int f = 0; f < 6; f++) {
+            MPIX_Prequest_free(&h->spre[par][f]); MPIX_Prequest_free(&h->rpre[par][f]);
+            MPIX_Request_free(&h->sreq[par][f]); MPIX_Request_free(&h->rreq[par][f]);
+            MPIX_Free_mem(h->land[par][f]);
+        }
+    cudaFree(h->u[0]); cudaFree(h->u[1]); cudaFree(h->order_d);
+    delete h;
+    return 0;
+}

@@ -62,6 +62,8 @@ struct CudaRt {
     int (*GetDeviceCount)(int *) = nullptr;
     int (*GetLastError)() = nullptr;
     int (*GetDevice)(int *) = nullptr;
+    int (*SetDevice)(int) = nullptr;
+    int (*Free)(void *) = nullptr;
     void *stream = nullptr;
 };
 CudaRt g_cuda;
@@ -96,6 +98,8 @@ bool cuda_load() {
     L(GetDeviceCount, "cudaGetDeviceCount")
     L(GetLastError, "cudaGetLastError")
     L(GetDevice, "cudaGetDevice")
+    L(SetDevice, "cudaSetDevice")
+    L(Free, "cudaFree")
 #undef L
     g_ipc_open = (IpcOpenFn)dlsym(g_cuda.h, "cudaIpcOpenMemHandle");
     if (!g_ipc_open) return false;
@@ -107,18 +111,32 @@ bool cuda_load() {
 
 enum { kMemcpyDefault = 4 };
 
+// MPI calls may come from threads that never touched CUDA (e.g. the reference's proxy
+// thread): bind the calling thread to the device that owns the buffer, as CUDA-aware MPIs do.
+thread_local int t_bound_dev = -1;
+void bind_thread_to(int dev) {
+    if (dev < 0 || dev == t_bound_dev) return;
+    g_cuda.SetDevice(dev);
+    g_cuda.Free(nullptr);  // force the primary context current on this thread (driver calls follow)
+    t_bound_dev = dev;
+}
+
 // Returns true if p is device (or managed) memory the CPU must not touch directly.
 bool is_device_ptr(const void *p) {
     if (!p || !cuda_load()) return false;
     PtrAttr a;
     memset(&a, 0, sizeof(a));
     if (g_cuda.PointerGetAttributes(&a, p) != 0) { g_cuda.GetLastError(); return false; }
-    return a.type == 2 /*cudaMemoryTypeDevice*/;
+    if (a.type == 2 /*cudaMemoryTypeDevice*/) { bind_thread_to(a.device); return true; }
+    return false;
 }
 
 void *cuda_stream() {
-    if (!g_cuda.stream) g_cuda.StreamCreateWithFlags(&g_cuda.stream, 1 /*NonBlocking*/);
-    return g_cuda.stream;
+    static void *streams[64] = {nullptr};
+    int d = t_bound_dev < 0 ? 0 : t_bound_dev & 63;
+    if (t_bound_dev < 0) { int cur = 0; if (g_cuda.GetDevice(&cur) == 0) { d = cur & 63; } }
+    if (!streams[d]) g_cuda.StreamCreateWithFlags(&streams[d], 1 /*NonBlocking*/);
+    return streams[d];
 }
 
 void die(const char *fmt, ...) {
@@ -364,6 +382,7 @@ bool match(int rsrc, int rtag, int rcomm, int rpart, int src, int tag, int comm,
 void copy_in(void *dst, bool dst_dev, const void *src, size_t n) {
     if (!n) return;
     if (dst_dev) {
+        is_device_ptr(dst);
         g_cuda.MemcpyAsync(dst, src, n, kMemcpyDefault, cuda_stream());
         g_cuda.StreamSynchronize(cuda_stream());
     } else {
@@ -403,6 +422,7 @@ bool ring_push(int dst, const CellHdr &h, const void *payload) {
 }
 
 void start_ipc_pull(Req *r, int src, const IpcHandle &h, size_t off, size_t total, uint64_t cookie, int tag) {
+    is_device_ptr(r->buf);  // binds this thread to the destination's device (progress may run on any thread)
     char *peer = src == g.rank ? (char *)off : (char *)ipc_map(h) + off;
     size_t n = total < r->bytes ? total : r->bytes;
     g_cuda.MemcpyAsync(r->buf, peer, n, kMemcpyDefault, cuda_stream());
@@ -489,6 +509,7 @@ void pump_sends(int dst) {
     auto &q = g_sendq[dst];
     while (!q.empty()) {
         Req *s = q.front();
+        if (s->is_dev) is_device_ptr(s->buf);  // bind the progressing thread to the source's device
         if (!s->hdr_sent) {
             CellHdr h{};
             h.tag = s->tag; h.comm = s->comm; h.part = s->part; h.total = s->bytes;
