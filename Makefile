@@ -35,13 +35,13 @@ $(B)/acx.o: src/core/acx.cu src/core/internal.h src/core/kernels.cuh include/mpi
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 KOBJS := $(patsubst src/kernels/%.cu,$(B)/k_%.o,$(wildcard src/kernels/*.cu))
-$(B)/k_%.o: src/kernels/%.cu include/mpi-acx.h include/acx_device.cuh include/acx_kernels.h
+$(B)/k_%.o: src/kernels/%.cu include/mpi-acx.h include/acx_device.cuh include/acx_kernels.h src/kernels/gemm_fp8_sm100.cuh
 	@mkdir -p $(B)
 	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c $< -o $@ 2> $(B)/k_$*.ptxas.log || (cat $(B)/k_$*.ptxas.log; false)
 
-$(LIB): $(B)/acx.o $(B)/minimpi.o $(KOBJS)
+$(LIB): $(B)/acx.o $(B)/minimpi.o $(KOBJS) src/core/acx.map
 	@mkdir -p lib
-	$(NVCC) $(GENCODE) -shared -o $@ $^ -cudart static -ldl -lpthread -lrt
+	$(NVCC) $(GENCODE) -shared -o $@ $(filter %.o,$^) -cudart static -ldl -lpthread -lrt -Xlinker --version-script=src/core/acx.map
 
 bin/acxrun: launcher/acxrun.cpp
 	@mkdir -p bin

@@ -19,6 +19,9 @@ int acx_halo_exchange_initial(acx_halo *h, cudaStream_t stream);
 int acx_halo_step(acx_halo *h, int nsteps, cudaStream_t stream);
 int acx_halo_destroy(acx_halo *h);
 
+/* ---- fp8 (e4m3) GEMM, tcgen05/TMEM: Y[M][N] = scale * X[M][K] * W[N][K]^T (M%128, N%256, K%128 == 0) ---- */
+int acx_gemm_fp8(const void *X, const void *W, void *Y, int M, int N, int K, float scale, cudaStream_t stream);
+
 /* ---- pipeline-parallel fp8 GEMM chain (tcgen05/TMEM), one stage per rank ------------------- */
 typedef struct acx_ppgemm acx_ppgemm;
 /* Collective. Stage r computes Y = scale * X * W_r^T with X [M][D], W_r [D][D] (e4m3), and its

@@ -1,0 +1,4 @@
+from .pipeline import PartitionedLink
+from .ring import allpairs_exchange, ring_exchange, ring_neighbours
+
+__all__ = ["ring_exchange", "ring_neighbours", "allpairs_exchange", "PartitionedLink"]

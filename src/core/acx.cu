@@ -13,6 +13,7 @@
 #include <cstring>
 #include <thread>
 #include <unistd.h>
+#include <nvtx3/nvToolsExt.h>
 
 AcxState *g_acx = nullptr;
 
@@ -38,6 +39,20 @@ static uint64_t *g_diag = nullptr, *g_diag_d = nullptr;      // watchdog diagnos
 static uint64_t *g_trace_cursor = nullptr;                   // device
 static std::vector<int> g_deferred_slots;                    // freed by graph user-object destructors
 static std::mutex g_deferred_mu;
+
+// NVTX ranges around the API calls (ACX_NVTX=1); header-only NVTX, a no-op without a tool attached.
+static int g_mover_tma = 0, g_mover_256 = 0;
+static int g_pdl = 1;   // programmatic dependent launch between consecutive acx kernels on a stream (ACX_PDL)
+static bool g_nvtx = false;
+struct AcxRange {
+    bool on;
+    explicit AcxRange(const char *name) : on(g_nvtx) { if (on) nvtxRangePushA(name); }
+    ~AcxRange() { if (on) nvtxRangePop(); }
+};
+// Fault injection for tests (ACX_FAULT_DROP_SEND=n): the n-th send is never triggered, so the
+// matching receive can only end in the watchdog (failure-detection path).
+static long g_fault_drop_send = 0;
+static std::atomic<long> g_send_counter{0};
 
 static Watchdog make_wd() {
     Watchdog w;
@@ -209,33 +224,49 @@ int acx_device_alias(const void *p, size_t bytes, char **out) {
     if (e != cudaSuccess) { cudaGetLastError(); a.type = cudaMemoryTypeUnregistered; }
     if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) { *out = (char *)p; return 0; }
     if (a.type == cudaMemoryTypeHost) { *out = (char *)a.devicePointer; return 0; }
-    // pageable host memory: pin + map the covering pages (cached)
+    // pageable host memory: pin + map the covering pages. Registrations are never undone while the
+    // library is up (device aliases are baked into persistent requests and graphs), so a new range that
+    // partially overlaps earlier ones only registers the pages that are still uncovered.
     const uintptr_t page = 4096;
     uintptr_t lo = (uintptr_t)p & ~(page - 1), hi = ((uintptr_t)p + bytes + page - 1) & ~(page - 1);
     std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
-    for (auto &r : g_acx->host_regs)
-        if (lo >= r.lo && hi <= r.hi) { *out = r.dptr + ((uintptr_t)p - r.lo); return 0; }
-    // merge with overlapping/adjacent registrations
-    for (size_t i = 0; i < g_acx->host_regs.size();) {
-        AcxHostReg &r = g_acx->host_regs[i];
-        if (r.lo <= hi && lo <= r.hi) {
-            cudaHostUnregister((void *)r.lo);
-            lo = std::min(lo, r.lo); hi = std::max(hi, r.hi);
-            g_acx->host_regs.erase(g_acx->host_regs.begin() + i);
-        } else i++;
+    if (!g_acx->host_ptr_is_dev_ptr) {
+        // no unified addressing for registered memory: one registration must cover the buffer
+        for (auto &r : g_acx->host_regs)
+            if (lo >= r.lo && hi <= r.hi) { *out = r.dptr + ((uintptr_t)p - r.lo); return 0; }
+        e = cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterMapped | cudaHostRegisterPortable);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (g_acx->pageable_access) { *out = (char *)p; return 0; }
+            ACX_ERR("cannot make host buffer %p (+%zu) device-accessible: %s", p, bytes, cudaGetErrorString(e));
+            return MPI_ERR_BUFFER;
+        }
+        char *d = nullptr;
+        cudaHostGetDevicePointer((void **)&d, (void *)lo, 0);
+        g_acx->host_regs.push_back({lo, hi, d});
+        *out = d + ((uintptr_t)p - lo);
+        return 0;
     }
-    e = cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterMapped | cudaHostRegisterPortable);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        if (g_acx->pageable_access) { *out = (char *)p; return 0; }  // HMM/ATS: the GPU can touch it as is
-        ACX_ERR("cannot make host buffer %p (+%zu) device-accessible: %s", p, bytes, cudaGetErrorString(e));
-        return MPI_ERR_BUFFER;
+    // unified addressing: device alias == host pointer once every page is registered
+    uintptr_t cur = lo;
+    while (cur < hi) {
+        // skip pages already covered
+        bool covered = false;
+        for (auto &r : g_acx->host_regs) if (cur >= r.lo && cur < r.hi) { cur = r.hi; covered = true; break; }
+        if (covered) continue;
+        uintptr_t end = hi;
+        for (auto &r : g_acx->host_regs) if (r.lo > cur && r.lo < end) end = r.lo;
+        e = cudaHostRegister((void *)cur, end - cur, cudaHostRegisterMapped | cudaHostRegisterPortable);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (g_acx->pageable_access) { *out = (char *)p; return 0; }  // HMM/ATS: the GPU can touch it as is
+            ACX_ERR("cannot make host buffer %p (+%zu) device-accessible: %s", p, bytes, cudaGetErrorString(e));
+            return MPI_ERR_BUFFER;
+        }
+        g_acx->host_regs.push_back({cur, end, (char *)cur});
+        cur = end;
     }
-    char *d = nullptr;
-    e = cudaHostGetDevicePointer((void **)&d, (void *)lo, 0);
-    if (e != cudaSuccess) { cudaGetLastError(); cudaHostUnregister((void *)lo); ACX_ERR("cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); return MPI_ERR_BUFFER; }
-    g_acx->host_regs.push_back({lo, hi, d});
-    *out = d + ((uintptr_t)p - lo);
+    *out = (char *)p;
     return 0;
 }
 
@@ -251,6 +282,122 @@ int acx_comm_ctx(MPI_Comm comm, int *ctx) {
     *ctx = (int)g_acx->comms.size() - 1;
     return 0;
 }
+
+// =======================================================================================
+// registration cache: zero-copy for plain cudaMalloc buffers (incl. torch tensors)
+// =======================================================================================
+// The owner publishes {buffer id, base, size, CUDA-IPC handle} in the job's shared scratch; every
+// rank maps new entries of its peers during its own MPIX calls, writes the mapped base into its
+// device-side xlat table and acks. The owner switches a buffer from the bounce path to the
+// registered (zero-copy) path for a given peer once that peer has acked — nobody ever waits for a
+// mapping, so there is no progress thread and no deadlock behind a spinning kernel.
+#ifdef ACX_MINI_MPI
+struct AcxRegEntry { uint64_t buffer_id, base, size; cudaIpcMemHandle_t handle; uint64_t pad; };
+struct AcxRegTable {
+    std::atomic<uint32_t> count;
+    uint32_t pad[15];
+    AcxRegEntry e[64];
+    std::atomic<uint8_t> ack[64][64];   // [reader rank][entry]
+};
+static bool g_reg_on = false;
+static AcxRegTable *g_reg_tables = nullptr;
+static std::unordered_map<uint64_t, int> g_reg_mine;     // buffer id -> entry index (-1: not registrable)
+static std::vector<uint32_t> g_reg_seen;
+static std::vector<void *> g_reg_opened;
+typedef int (*cuMemGetAddressRangeFn)(unsigned long long *, size_t *, unsigned long long);
+typedef int (*cuPointerGetAttributeFn)(void *, int, unsigned long long);
+static cuMemGetAddressRangeFn g_cuMemGetAddressRange = nullptr;
+static cuPointerGetAttributeFn g_cuPointerGetAttribute = nullptr;
+
+static void reg_init() {
+    long on = 1;
+    acx_env_int("ACX_REGCACHE", nullptr, 1, &on);
+    size_t sb = 0;
+    void *scratch = ACX_Mpi_shared_scratch(&sb);
+    if (!on || !scratch || g_acx->size > 64 || sb < sizeof(AcxRegTable) * (size_t)g_acx->size) return;
+    void *f1 = nullptr, *f2 = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f1, cudaEnableDefault, &q) != cudaSuccess || !f1) return;
+    if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &f2, cudaEnableDefault, &q) != cudaSuccess || !f2) return;
+    g_cuMemGetAddressRange = (cuMemGetAddressRangeFn)f1;
+    g_cuPointerGetAttribute = (cuPointerGetAttributeFn)f2;
+    g_reg_tables = (AcxRegTable *)scratch;   // zero-initialised by the job's rank 0 before anyone runs
+    g_reg_seen.assign(g_acx->size, 0);
+    g_reg_on = true;
+}
+
+// Map registrations our peers have published since the last call; ack them. Cheap when idle.
+static void reg_progress() {
+    if (!g_reg_on) return;
+    bool wrote = false;
+    std::vector<std::pair<int, uint32_t>> to_ack;
+    for (int p = 0; p < g_acx->size; p++) {
+        AcxRegTable *t = g_reg_tables + p;
+        const uint32_t c = t->count.load(std::memory_order_acquire);
+        for (uint32_t i = g_reg_seen[p]; i < c && i < g_acx->geom.maxreg; i++) {
+            uint64_t mapped = 0;
+            if (p == g_acx->rank) mapped = t->e[i].base;
+            else {
+                void *m = nullptr;
+                if (cudaIpcOpenMemHandle(&m, t->e[i].handle, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) { mapped = (uint64_t)m; g_reg_opened.push_back(m); }
+                else cudaGetLastError();
+            }
+            if (mapped) {
+                cudaMemcpyAsync(g_acx->ctrl + g_acx->geom.off_xlat + ((uint64_t)p * g_acx->geom.maxreg + i) * 8, &mapped, 8, cudaMemcpyHostToDevice, g_acx->istream);
+                cudaStreamSynchronize(g_acx->istream);   // `mapped` is a stack variable; entries are rare
+                to_ack.push_back({p, i});
+                wrote = true;
+            }
+        }
+        g_reg_seen[p] = c;
+    }
+    if (wrote) for (auto &a : to_ack) g_reg_tables[a.first].ack[g_acx->rank][a.second].store(1, std::memory_order_release);
+}
+
+// Location code (ACX_OFF_REG_BIT set) of [p, p+bytes) if it lies in a registered allocation that `peer`
+// has mapped; ~0 otherwise (caller bounces). Publishes the allocation on first sight.
+static uint64_t reg_encode(const void *p, size_t bytes, int peer) {
+    if (!g_reg_on) return ~0ull;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return ~0ull; }
+    if (a.type != cudaMemoryTypeDevice || a.device != g_acx->dev) return ~0ull;
+    unsigned long long id = 0;
+    if (g_cuPointerGetAttribute(&id, 9 /*CU_POINTER_ATTRIBUTE_BUFFER_ID*/, (unsigned long long)p) != 0) return ~0ull;
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    AcxRegTable *mine = g_reg_tables + g_acx->rank;
+    auto it = g_reg_mine.find(id);
+    int idx;
+    if (it != g_reg_mine.end()) idx = it->second;
+    else {
+        idx = -1;
+        unsigned long long base = 0; size_t size = 0;
+        const uint32_t c = mine->count.load(std::memory_order_relaxed);
+        cudaIpcMemHandle_t h;
+        if (c < g_acx->geom.maxreg && g_cuMemGetAddressRange(&base, &size, (unsigned long long)p) == 0 &&
+            cudaIpcGetMemHandle(&h, (void *)base) == cudaSuccess) {
+            mine->e[c].buffer_id = id; mine->e[c].base = base; mine->e[c].size = size; mine->e[c].handle = h;
+            mine->count.store(c + 1, std::memory_order_release);
+            idx = (int)c;
+            ACX_LOG(2, "registered allocation %p (+%zu) as #%d", (void *)base, size, idx);
+        } else cudaGetLastError();
+        g_reg_mine[id] = idx;
+    }
+    if (idx < 0) return ~0ull;
+    const AcxRegEntry &e = mine->e[idx];
+    if ((uint64_t)p < e.base || (uint64_t)p + bytes > e.base + e.size) return ~0ull;
+    if (!mine->ack[peer][idx].load(std::memory_order_acquire)) return ~0ull;   // peer has not mapped it yet
+    return ACX_OFF_REG_BIT | ((uint64_t)idx << 48) | ((uint64_t)p - e.base);
+}
+static void reg_finalize() {
+    for (void *m : g_reg_opened) cudaIpcCloseMemHandle(m);
+    g_reg_opened.clear(); g_reg_mine.clear(); g_reg_on = false;
+}
+#else
+static void reg_init() {}
+static void reg_progress() {}
+static uint64_t reg_encode(const void *, size_t, int) { return ~0ull; }
+static void reg_finalize() {}
+#endif
 
 // =======================================================================================
 // init / finalize
@@ -282,6 +429,8 @@ static void make_geom(acx_geom &g, int n) {
     g.off_ops = o;      o = up(o + (uint64_t)g.nops * sizeof(acx_op));
     g.off_pflags = o;   o = up(o + (uint64_t)g.npflags * 8);
     g.off_trace = o;    o = up(o + (uint64_t)g.ntrace * sizeof(acx_trace_rec));
+    acx_env_int("ACX_MAXREG", nullptr, 64, &v); g.maxreg = (uint32_t)std::min(std::max(1L, v), 64L);
+    g.off_xlat = o;     o = up(o + (uint64_t)n * g.maxreg * 8);
     g.off_eager = o;    o = up(o + nslots * g.eager_max);
     g.bytes = o;
 }
@@ -303,6 +452,10 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_VERBOSE", nullptr, 0, &v); g_acx->verbose = (int)v;
     acx_env_int("ACX_TRACE", nullptr, 0, &v); g_acx->trace = v != 0;
     acx_env_int("ACX_WATCHDOG_MS", nullptr, 0, &v); g_acx->watchdog_ms = v;
+    acx_env_int("ACX_NVTX", nullptr, 0, &v); g_nvtx = v != 0;
+    { const char *m = getenv("ACX_MOVER"); g_mover_tma = m && !strcmp(m, "tma"); g_mover_256 = m && !strcmp(m, "ldst256"); }
+    acx_env_int("ACX_PDL", nullptr, 1, &v); g_pdl = v != 0;
+    acx_env_int("ACX_FAULT_DROP_SEND", nullptr, 0, &v); g_fault_drop_send = v;
     acx_env_int("ACX_MOVER_MAX_CTAS", nullptr, 0, &v); g_acx->mover_max_ctas = (int)v;
     acx_env_int("ACX_MOVER_CTA_BYTES", nullptr, 64 << 10, &v); g_acx->mover_min_cta_bytes = (size_t)std::max(4096L, v);
     g_acx->comms.push_back(MPI_COMM_WORLD);
@@ -335,6 +488,7 @@ extern "C" int MPIX_Init(void) {
     if (cudaGetDeviceProperties(&prop, g_acx->dev) != cudaSuccess) { ACX_ERR("cudaGetDeviceProperties failed"); return 1; }
     g_acx->sm_count = prop.multiProcessorCount;
     cudaDeviceGetAttribute(&g_acx->pageable_access, cudaDevAttrPageableMemoryAccess, g_acx->dev);
+    cudaDeviceGetAttribute(&g_acx->host_ptr_is_dev_ptr, cudaDevAttrCanUseHostPointerForRegisteredMem, g_acx->dev);
 
     make_geom(g_acx->geom, g_acx->size);
     acx_env_int("ACX_HEAP_BYTES", nullptr, 512L << 20, &v);
@@ -397,6 +551,7 @@ extern "C" int MPIX_Init(void) {
     g_acx->recv_outstanding.assign(g_acx->size, std::vector<int>(g_acx->geom.nchan, 0));
     g_acx->device = true;
     g_acx->initialized = true;
+    reg_init();
     MPI_Barrier(MPI_COMM_WORLD);
     ACX_LOG(1, "device transport up: dev %d (%s, %d SMs), %d ranks, ctrl %.1f MiB, heap %.0f MiB, eager<=%u, depth %d, chans %d", g_acx->dev, prop.name,
             g_acx->sm_count, g_acx->size, g_acx->geom.bytes / 1048576.0, g_acx->heap_bytes / 1048576.0, g_acx->geom.eager_max, g_acx->geom.depth, g_acx->geom.nchan);
@@ -429,6 +584,7 @@ extern "C" int MPIX_Finalize(void) {
                     g_acx->rank, s.sends_enqueued, s.recvs_enqueued, s.waits_enqueued, s.bytes_sent, s.bytes_received, s.eager_msgs, s.rendezvous_msgs, s.bounce_copies,
                     s.kernels_launched, s.graph_nodes_added, s.slots_high_water, s.heap_bytes_high_water);
         }
+        reg_finalize();
         for (int p = 0; p < g_acx->size; p++) {
             if (p == g_acx->rank) continue;
             if (g_acx->peer_ctrl[p]) cudaIpcCloseMemHandle(g_acx->peer_ctrl[p]);
@@ -560,17 +716,28 @@ struct Emitter {
     bool in_graph() const { return qtype == MPIX_QUEUE_CUDA_GRAPH || capturing; }
 
     template <typename P>
-    int launch(void (*kern)(P), dim3 grid, dim3 block, P &params) {
+    int launch(void (*kern)(P), dim3 grid, dim3 block, P &params, size_t smem = 0) {
         void *args[] = {&params};
         if (qtype == MPIX_QUEUE_CUDA_STREAM) {
-            cudaError_t e = cudaLaunchKernel((const void *)kern, grid, block, args, 0, stream);
+            cudaError_t e;
+            if (g_pdl && !capturing) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                e = cudaLaunchKernelExC(&cfg, (const void *)kern, args);
+            } else {
+                e = cudaLaunchKernel((const void *)kern, grid, block, args, smem, stream);
+            }
             if (e != cudaSuccess) { report_watchdog(); ACX_ERR("kernel launch failed: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
             g_acx->st.kernels++;
             if (capturing) g_acx->st.graph_nodes++;
             return 0;
         }
         cudaKernelNodeParams np = {};
-        np.func = (void *)kern; np.gridDim = grid; np.blockDim = block; np.sharedMemBytes = 0; np.kernelParams = args; np.extra = nullptr;
+        np.func = (void *)kern; np.gridDim = grid; np.blockDim = block; np.sharedMemBytes = (unsigned)smem; np.kernelParams = args; np.extra = nullptr;
         cudaGraphNode_t node;
         cudaError_t e = cudaGraphAddKernelNode(&node, graph, (last && !parallel) ? &last : nullptr, (last && !parallel) ? 1 : 0, &np);
         if (e != cudaSuccess) { ACX_ERR("cudaGraphAddKernelNode: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
@@ -621,11 +788,34 @@ static int attach_to_graph(cudaGraph_t graph, int slot) {
 }
 
 static int mover_grid(size_t bytes) {
+    if (g_mover_tma) {
+        size_t g = (bytes + (256u << 10) - 1) / (256u << 10);   // >= 8 chunks per CTA keeps the ring busy
+        int cap = g_acx->mover_max_ctas > 0 ? g_acx->mover_max_ctas : g_acx->sm_count;
+        return (int)std::max<size_t>(1, std::min<size_t>(g, cap));
+    }
+    return 0;
+}
+static int mover_grid_ldst(size_t bytes);
+static int mover_grid_any(size_t bytes) { int g = mover_grid(bytes); return g ? g : mover_grid_ldst(bytes); }
+static int mover_grid_ldst(size_t bytes) {
     size_t g = (bytes + g_acx->mover_min_cta_bytes - 1) / g_acx->mover_min_cta_bytes;
     int cap = g_acx->mover_max_ctas > 0 ? g_acx->mover_max_ctas : 4 * g_acx->sm_count;
     if (g < 1) g = 1;
     if (g > (size_t)cap) g = cap;
     return (int)g;
+}
+
+static int launch_mover(Emitter &em, MoverParams &mp, size_t bytes) {
+    if (g_mover_tma) {
+        static bool attr = false;
+        if (!attr) {
+            if (cudaFuncSetAttribute(mover_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem) != cudaSuccess) { ACX_ERR("cannot raise dynamic smem for mover_tma"); return MPI_ERR_OTHER; }
+            attr = true;
+        }
+        return em.launch(mover_tma, dim3(mover_grid(bytes)), dim3(kTmaThreads), mp, kTmaSmem);
+    }
+    mp.vec256 = g_mover_256;
+    return em.launch(mover, dim3(mover_grid_ldst(bytes)), dim3(kMoverThreads), mp);
 }
 
 static inline int chan_of(int tag, int ctx) { return (int)(((unsigned)tag + 7u * (unsigned)ctx) % (unsigned)g_acx->geom.nchan); }
@@ -657,6 +847,7 @@ static int check_common(const char *fn, int count, MPI_Datatype dt, int peer, in
 // =======================================================================================
 extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm, MPIX_Request *request,
                                   int qtype, void *queue) {
+    AcxRange _r("MPIX_Isend_enqueue");
     size_t bytes; int ctx;
     int rc = check_common("MPIX_Isend_enqueue", count, datatype, dest, tag, comm, request, queue, &bytes, &ctx);
     if (rc) return rc;
@@ -682,14 +873,17 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         uint64_t src_off = ~0ull;
         const char *src_local = r->dev_buf;
         if (!eager) {
+            reg_progress();
             r->heap_off = acx_heap_offset_of(buf);
+            uint64_t enc = ~0ull;
             if (r->heap_off >= 0) src_off = (uint64_t)r->heap_off;
+            else if ((enc = reg_encode(buf, bytes, dest)) != ~0ull) src_off = enc;   // registered allocation: zero-copy
             else {
                 // private source: bounce into the symmetric heap first (local HBM copy)
                 if ((r->bounce_off = acx_heap_alloc(bytes)) < 0) { rc = MPI_ERR_OTHER; goto fail; }
                 src_off = (uint64_t)r->bounce_off;
                 src_local = g_acx->heap + r->bounce_off;
-                if ((rc = em.launch3(copy_kernel, dim3(mover_grid(bytes)), dim3(kMoverThreads), g_acx->heap + r->bounce_off, r->dev_buf, (uint64_t)bytes))) goto fail;
+                if ((rc = em.launch3(copy_kernel, dim3(mover_grid_ldst(bytes)), dim3(kMoverThreads), g_acx->heap + r->bounce_off, r->dev_buf, (uint64_t)bytes))) goto fail;
                 g_acx->st.bounce++;
             }
         }
@@ -705,15 +899,18 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         sp.hstat = (eager && !r->in_graph) ? g_acx->hstat_d + r->slot : nullptr;
         sp.src = r->dev_buf;
         sp.peer_heap = g_acx->peer_heap[dest];
+        sp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)dest * G.maxreg;
         sp.src_off = src_off; sp.bytes = bytes; sp.serial = r->serial;
         sp.tag = (uint32_t)tag; sp.depth = G.depth; sp.eager_max = G.eager_max; sp.peer = dest;
         sp.wd = make_wd(); sp.tr = make_tr();
-        if ((rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
+        const bool dropped = g_fault_drop_send > 0 && ++g_send_counter == g_fault_drop_send;
+        if (dropped) ACX_ERR("FAULT INJECTION: dropping send #%ld (tag %d -> rank %d)", g_fault_drop_send, tag, dest);
+        if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
         if (!eager) {
             MoverParams mp;
             memset(&mp, 0, sizeof mp);
             mp.op = sp.op; mp.local = (char *)src_local; mp.ring = sp.ring; mp.sack = sp.sack; mp.depth = G.depth; mp.push = 1; mp.peer = dest; mp.tr = sp.tr;
-            if ((rc = em.launch(mover, dim3(mover_grid(bytes)), dim3(kMoverThreads), mp))) goto fail;
+            if ((rc = launch_mover(em, mp, bytes))) goto fail;
             g_acx->st.rndv++;
         } else {
             g_acx->st.eager++;
@@ -735,6 +932,7 @@ fail:
 
 extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPIX_Request *request, int qtype,
                                   void *queue) {
+    AcxRange _r("MPIX_Irecv_enqueue");
     size_t bytes; int ctx;
     int rc = check_common("MPIX_Irecv_enqueue", count, datatype, source, tag, comm, request, queue, &bytes, &ctx);
     if (rc) return rc;
@@ -770,7 +968,10 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         uint64_t dst_off = ~0ull;
         char *dst_local = r->dev_buf;
         r->heap_off = acx_heap_offset_of(buf);
+        uint64_t enc = ~0ull;
+        if (rndv_capable) reg_progress();
         if (r->heap_off >= 0) dst_off = (uint64_t)r->heap_off;
+        else if (rndv_capable && (enc = reg_encode(buf, bytes, source)) != ~0ull) dst_off = enc;   // registered: zero-copy
         else if (rndv_capable) {
             if ((r->bounce_off = acx_heap_alloc(bytes)) < 0) { rc = MPI_ERR_OTHER; goto fail; }
             dst_off = (uint64_t)r->bounce_off;
@@ -786,6 +987,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         rp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
         rp.sack = rndv_capable ? acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx : nullptr;
         rp.peer_heap = g_acx->peer_heap[source];
+        rp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)source * G.maxreg;
         rp.dst_off = dst_off; rp.cap = bytes; rp.serial = r->serial; rp.depth = G.depth; rp.peer = source;
         rp.wd = make_wd(); rp.tr = make_tr();
         if ((rc = em.launch(recv_trigger, dim3(1), dim3(32), rp))) goto fail;
@@ -794,7 +996,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
             memset(&mp, 0, sizeof mp);
             mp.op = rp.op; mp.local = dst_local; mp.ring = rp.ring; mp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;
             mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr;
-            if ((rc = em.launch(mover, dim3(mover_grid(bytes)), dim3(kMoverThreads), mp))) goto fail;
+            if ((rc = launch_mover(em, mp, bytes))) goto fail;
         }
     }
     if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;
@@ -867,6 +1069,7 @@ static void host_status_send(MPI_Status *st, AcxRequest *r) {
 }
 
 static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses, int qtype, void *queue) {
+    AcxRange _r("MPIX_Wait(all)_enqueue");
     if (!g_acx || !g_acx->initialized) return MPI_ERR_OTHER;
     if (count < 0 || (count > 0 && !reqs) || !queue) return MPI_ERR_ARG;
     std::vector<AcxRequest *> rs;
@@ -944,7 +1147,7 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             bp.dst = r->dev_buf; bp.bounce = g_acx->heap + r->bounce_off; bp.hstat = g_acx->hstat_d + r->slot; bp.retire = retire ? 1 : 0;
             const bool par = em.parallel;
             em.parallel = false;  // must follow the wait node
-            rc = em.launch(bounce_out_kernel, dim3(mover_grid(r->bytes)), dim3(kMoverThreads), bp);
+            rc = em.launch(bounce_out_kernel, dim3(mover_grid_ldst(r->bytes)), dim3(kMoverThreads), bp);
             em.parallel = par;
             if (rc) return rc;
         }
@@ -977,6 +1180,7 @@ extern "C" int MPIX_Waitall_enqueue(int count, MPIX_Request *reqs, MPI_Status *s
 
 // ---- partitioned: forward declarations ----
 static int pwait_host(AcxRequest *r, MPI_Status *status);
+static int pwait_emit(AcxRequest *r, cudaStream_t stream);
 
 extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
     if (!g_acx || !g_acx->initialized || !req) return MPI_ERR_OTHER;
@@ -1034,6 +1238,19 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
 }
 
 extern "C" int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses) {
+    // partitioned requests on the device transport: emit every completion kernel first, synchronize once
+    if (g_acx && g_acx->device) {
+        bool any = false;
+        for (int i = 0; i < count; i++) {
+            AcxRequest *r = reqs[i] ? as_request(reqs[i]) : nullptr;
+            if (r && (r->kind == ACX_REQ_PSEND || r->kind == ACX_REQ_PRECV) && !r->host_transport && r->active) {
+                int rc = pwait_emit(r, g_acx->istream);
+                if (rc) return rc;
+                any = true;
+            }
+        }
+        if (any) ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    }
     for (int i = 0; i < count; i++) {
         int rc = MPIX_Wait(&reqs[i], statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[i]);
         if (rc) return rc;

@@ -32,6 +32,13 @@
 // ---- shared host/device layout -----------------------------------------------------
 enum { ACX_KIND_EAGER = 1, ACX_KIND_RNDV = 2 };
 
+// Buffer locations travel as 64-bit "offsets": bit 63 clear = offset into the owner's symmetric heap;
+// bit 63 set = registered user allocation: bits [62:48] registration index, bits [47:0] offset inside it
+// (translated through the reader's xlat table, filled when it opened the owner's CUDA-IPC handle).
+#define ACX_OFF_REG_BIT (1ull << 63)
+#define ACX_OFF_REG_IDX(o) ((uint32_t)(((o) >> 48) & 0x7fff))
+#define ACX_OFF_REG_OFF(o) ((o) & 0xffffffffffffull)
+
 struct alignas(64) acx_entry {  // one slot of a (src -> me, channel) ring; lives at the receiver
     uint64_t state;      // hi32: #sends arrived on this slot, lo32: #recvs posted (atomic add, never reset)
     uint64_t done;       // #generations whose data has fully landed (mover: release store)
@@ -81,8 +88,8 @@ enum { ACX_EV_SEND_TRIGGER = 1, ACX_EV_RECV_TRIGGER, ACX_EV_MOVE_BEGIN, ACX_EV_M
 struct acx_geom {
     int nranks, nchan, depth, nops;
     uint32_t eager_max;
-    uint64_t off_entries, off_sack, off_send_seq, off_recv_seq, off_ops, off_pflags, off_trace, off_eager, bytes;
-    uint32_t npflags, ntrace;
+    uint64_t off_entries, off_sack, off_send_seq, off_recv_seq, off_ops, off_pflags, off_trace, off_xlat, off_eager, bytes;
+    uint32_t npflags, ntrace, maxreg;
 };
 
 #ifdef __CUDACC__
@@ -181,6 +188,7 @@ struct AcxState {
     size_t heap_in_use = 0;
     int slots_in_use = 0;
     int pageable_access = 0;
+    int host_ptr_is_dev_ptr = 0;
 };
 
 extern AcxState *g_acx;

@@ -23,6 +23,14 @@ struct TraceCtx {
     uint64_t *cursor;
 };
 
+// Programmatic dependent launch: let the NEXT kernel in the stream get scheduled while this one still runs,
+// then wait for the PREVIOUS kernel's completion + memory flush before touching anything. Both instructions
+// are no-ops when the launch did not opt in (ACX_PDL=0, graph nodes, user kernels in between).
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -55,11 +63,44 @@ __device__ __forceinline__ void spin_geq(const uint64_t *p, uint64_t v, const Wa
     }
 }
 
+// 256-bit (LDG.256 / STG.256, new on sm_100) copy loop: half the LSU instructions per byte and
+// 1-KiB contiguous runs per warp instruction. Needs 32-B aligned pointers; tail via copy_bytes.
+struct alignas(32) v8u32 { uint32_t r[8]; };
+__device__ __forceinline__ v8u32 ld256(const char *p) {
+    v8u32 v;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7]) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st256(char *p, const v8u32 &v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(v.r[0]), "r"(v.r[1]), "r"(v.r[2]), "r"(v.r[3]), "r"(v.r[4]), "r"(v.r[5]), "r"(v.r[6]), "r"(v.r[7]) : "memory");
+}
+__device__ __forceinline__ void copy_bytes_256(char *dst, const char *src, uint64_t n, unsigned tid, unsigned nthr) {
+    if ((((uintptr_t)dst | (uintptr_t)src) & 31) != 0) { copy_bytes(dst, src, n, tid, nthr); return; }
+    const uint64_t nv = n >> 5;
+    uint64_t i = tid;
+    for (; i + 3ull * nthr < nv; i += 4ull * nthr) {
+        v8u32 a = ld256(src + (i << 5)), b = ld256(src + ((i + nthr) << 5)), c = ld256(src + ((i + 2ull * nthr) << 5)), d = ld256(src + ((i + 3ull * nthr) << 5));
+        st256(dst + (i << 5), a); st256(dst + ((i + nthr) << 5), b); st256(dst + ((i + 2ull * nthr) << 5), c); st256(dst + ((i + 3ull * nthr) << 5), d);
+    }
+    for (; i < nv; i += nthr) st256(dst + (i << 5), ld256(src + (i << 5)));
+    const uint64_t done = nv << 5;
+    if (done < n) copy_bytes(dst + done, src + done, n - done, tid, nthr);
+}
+
 // ---------------------------------------------------------------------------------------
 // Plain copy (bounce-in for private send buffers). Grid-stride, 16-B vectors.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMoverThreads) copy_kernel(char *dst, const char *src, uint64_t n) {
+    pdl_prologue();
     copy_bytes(dst, src, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// Resolve a peer buffer location (see ACX_OFF_REG_BIT) to an address this GPU can dereference.
+__device__ __forceinline__ char *translate_peer(char *peer_heap, const uint64_t *xlat_row, uint64_t off) {
+    if (off & ACX_OFF_REG_BIT) return (char *)(xlat_row[ACX_OFF_REG_IDX(off)] + ACX_OFF_REG_OFF(off));
+    return peer_heap + off;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -75,6 +116,7 @@ struct SendParams {
     acx_host_status *hstat; // pinned host record (null: do not signal the host)
     const char *src;        // device-accessible source
     char *peer_heap;        // peer-mapped heap base of dst
+    const uint64_t *xlat;   // local: translation row for registrations owned by dst
     uint64_t src_off;       // heap offset of the (possibly bounced) source; rendezvous only
     uint64_t bytes;
     uint64_t serial;
@@ -84,6 +126,7 @@ struct SendParams {
 };
 
 __global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
+    pdl_prologue();
     __shared__ uint64_t s_k;
     const unsigned tid = threadIdx.x;
     if (tid == 0) {
@@ -119,7 +162,7 @@ __global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
         if ((uint32_t)old == (uint32_t)(g + 1)) {  // receive already posted: I move the data (push)
             // the receiver mirrored its destination into MY sack before it bumped the state word
             uint64_t cap = ld_relaxed_sys(&p.sack[e].r_cap), off = ld_relaxed_sys(&p.sack[e].r_dst_off);
-            p.op->peer_ptr = (uint64_t)(p.peer_heap + off);
+            p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, off);
             p.op->n = p.bytes < cap ? p.bytes : cap;
             p.op->mover = 1;
         } else {
@@ -139,6 +182,7 @@ struct RecvParams {
     uint64_t *seq;          // local recv ticket counter
     acx_op *op;
     char *peer_heap;        // peer-mapped heap base of src
+    const uint64_t *xlat;   // local: translation row for registrations owned by src
     uint64_t dst_off;       // heap offset of destination (or bounce); ~0 when not rendezvous-capable
     uint64_t cap;
     uint64_t serial;
@@ -148,6 +192,7 @@ struct RecvParams {
 };
 
 __global__ void recv_trigger(RecvParams p) {
+    pdl_prologue();
     if (threadIdx.x != 0) return;
     uint64_t k = atomicAdd((unsigned long long *)p.seq, 1ull);
     uint32_t e = (uint32_t)(k % p.depth);
@@ -163,7 +208,7 @@ __global__ void recv_trigger(RecvParams p) {
     if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && ent->s_kind == ACX_KIND_RNDV) {
         // the send is already here and waiting: I move the data (pull)
         uint64_t sb = ent->s_bytes;
-        p.op->peer_ptr = (uint64_t)(p.peer_heap + ent->s_src_off);
+        p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, ent->s_src_off);
         p.op->n = sb < p.cap ? sb : p.cap;
         p.op->mover = 1;
     }
@@ -183,11 +228,12 @@ struct MoverParams {
     char *local;            // push: local source; pull: local destination
     acx_entry *ring;        // push: peer-mapped ring; pull: local ring
     acx_sack *sack;         // push: local sack; pull: peer-mapped sack at the sender
-    uint32_t depth, push, peer, pad;
+    uint32_t depth, push, peer, vec256;
     TraceCtx tr;
 };
 
 __global__ void __launch_bounds__(kMoverThreads) mover(MoverParams p) {
+    pdl_prologue();
     acx_op *op = p.op;
     if (!op->mover) return;
     const uint64_t n = op->n;
@@ -198,8 +244,10 @@ __global__ void __launch_bounds__(kMoverThreads) mover(MoverParams p) {
     const uint64_t lo = per * blockIdx.x;
     if (lo < n) {
         const uint64_t len = n - lo < per ? n - lo : per;
-        if (p.push) copy_bytes(peer + lo, p.local + lo, len, threadIdx.x, blockDim.x);
-        else copy_bytes(p.local + lo, peer + lo, len, threadIdx.x, blockDim.x);
+        char *d = p.push ? peer + lo : p.local + lo;
+        const char *s = p.push ? p.local + lo : peer + lo;
+        if (p.vec256) copy_bytes_256(d, s, len, threadIdx.x, blockDim.x);
+        else copy_bytes(d, s, len, threadIdx.x, blockDim.x);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -213,6 +261,89 @@ __global__ void __launch_bounds__(kMoverThreads) mover(MoverParams p) {
             op->cta_count = 0;
             st_relaxed_sys(&p.ring[e].done, g + 1);   // receiver may consume
             st_relaxed_sys(&p.sack[e].sdone, g + 1);  // sender's buffer is reusable
+            trace(p.tr, ACX_EV_MOVE_END, p.peer, k, n);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA flavour of the mover (ACX_MOVER=tma): one elected thread per CTA drives a 4-stage ring of
+// 32-KiB bulk copies through shared memory — cp.async.bulk global->smem (mbarrier complete_tx),
+// then cp.async.bulk smem->global (bulk_group). The SM issues two instructions per 32 KiB instead
+// of 4096 LDG/STG pairs; peer addresses are served over NVLink by the TMA unit directly.
+// Falls back to the LDG/STG loop for pointers/sizes that are not 16-B aligned.
+// ---------------------------------------------------------------------------------------
+constexpr int kTmaStages = 4;
+constexpr uint32_t kTmaChunk = 32768;
+constexpr int kTmaThreads = 128;
+constexpr int kTmaSmem = kTmaStages * (int)kTmaChunk + 64;
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kTmaThreads) mover_tma(MoverParams p) {
+    extern __shared__ __align__(128) unsigned char tsm[];
+    pdl_prologue();
+    acx_op *op = p.op;
+    if (!op->mover) return;
+    const uint64_t n = op->n;
+    char *peer = (char *)op->peer_ptr;
+    const char *src = p.push ? p.local : peer;
+    char *dst = p.push ? peer : p.local;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace(p.tr, ACX_EV_MOVE_BEGIN, p.peer, op->ticket, n);
+    const uint64_t per = ((n + gridDim.x - 1) / gridDim.x + kTmaChunk - 1) / kTmaChunk * kTmaChunk;
+    const uint64_t lo = per * blockIdx.x;
+    if (lo < n) {
+        const uint64_t len = n - lo < per ? n - lo : per;
+        const bool aligned = ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) && (len % 16 == 0);
+        if (!aligned) {
+            copy_bytes(dst + lo, src + lo, len, threadIdx.x, blockDim.x);
+        } else if (threadIdx.x == 0) {
+            uint64_t *bars = reinterpret_cast<uint64_t *>(tsm + kTmaStages * kTmaChunk);
+            for (int i = 0; i < kTmaStages; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&bars[i])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint64_t nchunks = (len + kTmaChunk - 1) / kTmaChunk;
+            uint32_t phase_bits = 0;
+            auto load = [&](uint64_t c) {
+                const int st = (int)(c % kTmaStages);
+                const uint32_t bytes = (uint32_t)(len - c * kTmaChunk < kTmaChunk ? len - c * kTmaChunk : kTmaChunk);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&bars[st])), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_addr_u32(tsm + st * kTmaChunk)), "l"(src + lo + c * kTmaChunk), "r"(bytes), "r"(smem_addr_u32(&bars[st])) : "memory");
+            };
+            const uint64_t pre = nchunks < (uint64_t)kTmaStages ? nchunks : (uint64_t)kTmaStages;
+            for (uint64_t c = 0; c < pre; c++) load(c);
+            for (uint64_t c = 0; c < nchunks; c++) {
+                const int st = (int)(c % kTmaStages);
+                const uint32_t parity = (phase_bits >> st) & 1;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tTW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra.uni TD;\n\tbra.uni TW;\n\tTD:\n\t}"
+                    ::"r"(smem_addr_u32(&bars[st])), "r"(parity) : "memory");
+                phase_bits ^= 1u << st;
+                const uint32_t bytes = (uint32_t)(len - c * kTmaChunk < kTmaChunk ? len - c * kTmaChunk : kTmaChunk);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + lo + c * kTmaChunk), "r"(smem_addr_u32(tsm + st * kTmaChunk)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (c >= 1 && c - 1 + kTmaStages < nchunks) {
+                    // store(c-1) has finished READING its stage once at most one group (store c) is pending
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    load(c - 1 + kTmaStages);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete (writes performed)
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        unsigned t = atomicAdd(&op->cta_count, 1u);
+        if (t == gridDim.x - 1) {
+            __threadfence();
+            const uint64_t k = op->ticket;
+            const uint32_t e = (uint32_t)(k % p.depth);
+            const uint64_t g = k / p.depth;
+            op->cta_count = 0;
+            st_relaxed_sys(&p.ring[e].done, g + 1);
+            st_relaxed_sys(&p.sack[e].sdone, g + 1);
             trace(p.tr, ACX_EV_MOVE_END, p.peer, k, n);
         }
     }
@@ -245,6 +376,7 @@ struct WaitBatch {
 };
 
 __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
+    pdl_prologue();
     const WaitOne &w = b.w[blockIdx.x];
     __shared__ uint64_t s_n;
     __shared__ int s_eager;
@@ -328,6 +460,7 @@ struct BounceOutParams {
     uint32_t retire, pad;
 };
 __global__ void __launch_bounds__(kMoverThreads) bounce_out_kernel(BounceOutParams p) {
+    pdl_prologue();
     const uint64_t n = p.op->bounce_n;
     if (n) copy_bytes(p.dst, p.bounce, n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     if (!p.retire) return;

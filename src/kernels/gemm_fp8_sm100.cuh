@@ -24,6 +24,9 @@
 #include <stdint.h>
 
 namespace acxg {
+namespace {   // internal linkage: every module that includes this header owns a private copy of the kernel and its
+              // host stub (a shared copy would be interposed across libacx.so / executables, each of which
+              // carries its own static CUDA runtime)
 
 constexpr int BM = 128, BN = 256, BK = 128;      // tile; BK in bytes == elements (fp8)
 constexpr int UMMA_K = 32;                       // bytes of K per tcgen05.mma (8-bit types)
@@ -338,5 +341,6 @@ inline int launch_gemm_fp8(const uint8_t *X, const uint8_t *W, uint8_t *out, int
     return cudaGetLastError() == cudaSuccess ? 0 : 6;
 }
 
+}  // namespace
 }  // namespace acxg
 #endif

@@ -20,6 +20,7 @@
 #include "../../include/acx_kernels.h"
 #include <cuda_bf16.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 
@@ -55,7 +56,11 @@ __device__ __forceinline__ uint4 pack8(const float f[8]) {
 __device__ __forceinline__ float bf(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
 
 // Face ids: 0 X-, 1 X+, 2 Y-, 3 Y+, 4 Z-, 5 Z+.
-__global__ void __launch_bounds__(LX * TY, 2) halo_stencil_step(HaloDev P) {
+// PD = software-pipeline depth of the z-march (planes in flight per thread); MINB = CTAs per SM the
+// register allocation is tuned for. Variants are selected at run time (ACX_HALO_VARIANT).
+template <int PD, int MINB>
+__global__ void __launch_bounds__(LX * TY, MINB) halo_stencil_step(HaloDev P) {
+    static_assert(TZ % PD == 0, "TZ must be a multiple of the prefetch depth");
     __shared__ uint4 rows[2][TY][LX];                 // current plane, double-buffered (16 KiB)
     __shared__ __align__(16) __nv_bfloat16 xface[2][TZ * TY];  // packed X-/X+ face of this tile (2 KiB)
     const int lx = threadIdx.x, ly = threadIdx.y;
@@ -94,51 +99,220 @@ __global__ void __launch_bounds__(LX * TY, 2) halo_stencil_step(HaloDev P) {
             if (z >= P.nz) return hzp[ly * LX + lx];
             return *reinterpret_cast<const uint4 *>(col + (size_t)z * plane);
         };
-        float prev[8], cur[8], nxt[8];
-        uint4 vcur = load_plane(z0), vnext;
+        // Edge operands come from global memory / landing buffers instead of shared memory; they are
+        // software-pipelined PD planes ahead exactly like the centre column, so no thread ever issues a
+        // load in the same iteration that consumes it.
+        const bool yedge = ly == 0 || ly == TY - 1, xedge = lx == 0 || lx == LX - 1;
+        const bool ylow = ly == 0, xlow = lx == 0;
+        auto load_yrow = [&](int zl) -> uint4 {   // row y-1 (ly==0) or y+1 (ly==TY-1) of plane z0+zl
+            const size_t zoff = (size_t)(z0 + zl) * plane;
+            if (ylow) return fym ? hym[zl * LX + lx] : *reinterpret_cast<const uint4 *>(col + zoff - P.nx);
+            return fyp ? hyp[zl * LX + lx] : *reinterpret_cast<const uint4 *>(col + zoff + P.nx);
+        };
+        auto load_xedge = [&](int zl) -> __nv_bfloat16 {   // cell x0-1 (lane 0) or x0+8 (lane 31) of plane z0+zl
+            const size_t zoff = (size_t)(z0 + zl) * plane;
+            if (xlow) return fxm ? hxm[zl * TY + ly] : col[zoff - 1];
+            return fxp ? hxp[zl * TY + ly] : col[zoff + 8];
+        };
+        uint4 q[PD], qy[PD];
+        __nv_bfloat16 qx[PD];
+#pragma unroll
+        for (int j = 0; j < PD; j++) {
+            q[j] = load_plane(z0 + 1 + j);
+            if (yedge) qy[j] = load_yrow(j);
+            if (xedge) qx[j] = load_xedge(j);
+        }
+        float prev[8], cur[8];
+        uint4 vcur = load_plane(z0);
         unpack8(load_plane(z0 - 1), prev);
         unpack8(vcur, cur);
-        for (int zl = 0; zl < TZ; zl++) {
-            const int z = z0 + zl;
-            vnext = load_plane(z + 1);
-            rows[zl & 1][ly][lx] = vcur;
-            // x neighbours of the 8-cell vector's ends
-            float left = __shfl_up_sync(0xffffffffu, cur[7], 1), right = __shfl_down_sync(0xffffffffu, cur[0], 1);
-            if (lx == 0) left = fxm ? __bfloat162float(hxm[zl * TY + ly]) : bf(col + (size_t)z * plane - 1);
-            if (lx == LX - 1) right = fxp ? __bfloat162float(hxp[zl * TY + ly]) : bf(col + (size_t)z * plane + 8);
-            __syncthreads();
-            float ym[8], yp[8];
-            if (ly > 0) unpack8(rows[zl & 1][ly - 1][lx], ym);
-            else unpack8(fym ? hym[zl * LX + lx] : *reinterpret_cast<const uint4 *>(col + (size_t)z * plane - P.nx), ym);
-            if (ly < TY - 1) unpack8(rows[zl & 1][ly + 1][lx], yp);
-            else unpack8(fyp ? hyp[zl * LX + lx] : *reinterpret_cast<const uint4 *>(col + (size_t)z * plane + P.nx), yp);
-            unpack8(vnext, nxt);
-            float out[8];
+#pragma unroll 1
+        for (int zb = 0; zb < TZ; zb += PD) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float xm = i == 0 ? left : cur[i - 1], xp = i == 7 ? right : cur[i + 1];
-                out[i] = P.c0 * cur[i] + P.c1 * (((xm + xp) + (ym[i] + yp[i])) + (prev[i] + nxt[i]));
+            for (int j = 0; j < PD; j++) {
+                const int zl = zb + j, z = z0 + zl;
+                const uint4 vnext = q[j];
+                const uint4 vy = qy[j];
+                const __nv_bfloat16 vx = qx[j];
+                if (zl + 1 + PD <= TZ) q[j] = load_plane(z + 1 + PD);
+                if (zl + PD < TZ) {
+                    if (yedge) qy[j] = load_yrow(zl + PD);
+                    if (xedge) qx[j] = load_xedge(zl + PD);
+                }
+                rows[zl & 1][ly][lx] = vcur;
+                float left = __shfl_up_sync(0xffffffffu, cur[7], 1), right = __shfl_down_sync(0xffffffffu, cur[0], 1);
+                if (lx == 0) left = __bfloat162float(vx);
+                if (lx == LX - 1) right = __bfloat162float(vx);
+                __syncthreads();
+                float ym[8], yp[8], nxt[8];
+                unpack8(ly > 0 ? rows[zl & 1][ly - 1][lx] : vy, ym);
+                unpack8(ly < TY - 1 ? rows[zl & 1][ly + 1][lx] : vy, yp);
+                unpack8(vnext, nxt);
+                float out[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float xm = i == 0 ? left : cur[i - 1], xp = i == 7 ? right : cur[i + 1];
+                    out[i] = P.c0 * cur[i] + P.c1 * (((xm + xp) + (ym[i] + yp[i])) + (prev[i] + nxt[i]));
+                }
+                const uint4 vo = pack8(out);
+                *reinterpret_cast<uint4 *>(P.un + (size_t)z * plane + (size_t)y * P.nx + x0) = vo;
+                // face cells also go straight into the neighbours' landing buffers (NVLink stores)
+                if (fzm && zl == 0) rzm[ly * LX + lx] = vo;
+                if (fzp && zl == TZ - 1) rzp[ly * LX + lx] = vo;
+                if (fym && ly == 0) rym[zl * LX + lx] = vo;
+                if (fyp && ly == TY - 1) ryp[zl * LX + lx] = vo;
+                if (fxm && lx == 0) xface[0][zl * TY + ly] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[0];
+                if (fxp && lx == LX - 1) xface[1][zl * TY + ly] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[7];
+#pragma unroll
+                for (int i = 0; i < 8; i++) { prev[i] = cur[i]; cur[i] = nxt[i]; }
+                vcur = vnext;
             }
-            const uint4 vo = pack8(out);
-            *reinterpret_cast<uint4 *>(P.un + (size_t)z * plane + (size_t)y * P.nx + x0) = vo;
-            // face cells also go straight into the neighbours' landing buffers (NVLink stores)
-            if (fzm && zl == 0) rzm[ly * LX + lx] = vo;
-            if (fzp && zl == TZ - 1) rzp[ly * LX + lx] = vo;
-            if (fym && ly == 0) rym[zl * LX + lx] = vo;
-            if (fyp && ly == TY - 1) ryp[zl * LX + lx] = vo;
-            if (fxm && lx == 0) xface[0][zl * TY + ly] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[0];
-            if (fxp && lx == LX - 1) xface[1][zl * TY + ly] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[7];
-#pragma unroll
-            for (int i = 0; i < 8; i++) { prev[i] = cur[i]; cur[i] = nxt[i]; }
-            vcur = vnext;
         }
         __syncthreads();
         if (fxm && tid < TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[0], px_))[tid] = ((const uint4 *)xface[0])[tid];
         if (fxp && tid >= 64 && tid < 64 + TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[1], px_))[tid - 64] = ((const uint4 *)xface[1])[tid - 64];
         if (fxm | fxp | fym | fyp | fzm | fzp) {
-            __threadfence_system();
             __syncthreads();
             if (tid == 0) {
+                __threadfence_system();   // one cumulative fence (the barrier ordered the other threads' stores before it)
+                if (fxm) acx::pready_signal_epoch(px_, P.send[0], P.signal_val);
+                if (fxp) acx::pready_signal_epoch(px_, P.send[1], P.signal_val);
+                if (fym) acx::pready_signal_epoch(py_, P.send[2], P.signal_val);
+                if (fyp) acx::pready_signal_epoch(py_, P.send[3], P.signal_val);
+                if (fzm) acx::pready_signal_epoch(pz_, P.send[4], P.signal_val);
+                if (fzp) acx::pready_signal_epoch(pz_, P.send[5], P.signal_val);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Barrier-free variant (default): 4 warps per CTA, each warp owns 4 rows x 256 columns of the tile
+// and z-marches on its own — y-neighbours of the strip's inner rows are already in registers, the two
+// rows above/below come from global memory (the adjacent warp loaded them a moment ago: L1/L2 hits)
+// or from the Y landing buffers, software-pipelined one plane ahead. No shared-memory exchange and no
+// __syncthreads inside the march; ~3x fewer instructions per cell than the shared-memory variants.
+// Same tile geometry (256x16x32), same partitions, same flags.
+// ---------------------------------------------------------------------------------------------
+constexpr int RW = 4;              // rows per warp
+constexpr int NW = TY / RW;        // warps per CTA
+
+template <int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) halo_stencil_step_rows(HaloDev P) {
+    __shared__ __align__(16) __nv_bfloat16 xface[2][TZ * TY];
+    const int lx = threadIdx.x & 31, w = threadIdx.x >> 5, tid = threadIdx.x;
+    const size_t plane = (size_t)P.nx * P.ny;
+    for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x) {
+        const int t = P.order[it];
+        const int tx = t % P.ntx, ty = (t / P.ntx) % P.nty, tz = t / (P.ntx * P.nty);
+        const bool fxm = tx == 0, fxp = tx == P.ntx - 1, fym = ty == 0, fyp = ty == P.nty - 1, fzm = tz == 0, fzp = tz == P.ntz - 1;
+        const int px_ = tz * P.nty + ty, py_ = tz * P.ntx + tx, pz_ = ty * P.ntx + tx;
+        if (tid == 0) {
+            if (fxm) acx::wait_arrived_epoch(P.recv[0], px_, P.wait_val);
+            if (fxp) acx::wait_arrived_epoch(P.recv[1], px_, P.wait_val);
+            if (fym) acx::wait_arrived_epoch(P.recv[2], py_, P.wait_val);
+            if (fyp) acx::wait_arrived_epoch(P.recv[3], py_, P.wait_val);
+            if (fzm) acx::wait_arrived_epoch(P.recv[4], pz_, P.wait_val);
+            if (fzp) acx::wait_arrived_epoch(P.recv[5], pz_, P.wait_val);
+        }
+        __syncthreads();
+        const int x0 = tx * TX + lx * 8, yl0 = w * RW, y0 = ty * TY + yl0, z0 = tz * TZ;
+        const __nv_bfloat16 *hxm = fxm ? (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[0], px_) : nullptr;
+        const __nv_bfloat16 *hxp = fxp ? (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[1], px_) : nullptr;
+        const uint4 *hym = fym ? (const uint4 *)acx::local_partition_ptr(P.recv[2], py_) : nullptr;
+        const uint4 *hyp = fyp ? (const uint4 *)acx::local_partition_ptr(P.recv[3], py_) : nullptr;
+        const uint4 *hzm = fzm ? (const uint4 *)acx::local_partition_ptr(P.recv[4], pz_) : nullptr;
+        const uint4 *hzp = fzp ? (const uint4 *)acx::local_partition_ptr(P.recv[5], pz_) : nullptr;
+        uint4 *rym = fym ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[2], py_) : nullptr;
+        uint4 *ryp = fyp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[3], py_) : nullptr;
+        uint4 *rzm = fzm ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[4], pz_) : nullptr;
+        uint4 *rzp = fzp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[5], pz_) : nullptr;
+        const __nv_bfloat16 *col = P.u + (size_t)y0 * P.nx + x0;            // row r, plane z: col + z*plane + r*nx
+        __nv_bfloat16 *ocol = P.un + (size_t)y0 * P.nx + x0;
+        const bool top = w == 0, bot = w == NW - 1;
+        auto load_own = [&](int z, int r) -> uint4 {                          // own row r of plane z (z may be the z-halo)
+            if (z < 0) return hzm[(yl0 + r) * LX + lx];
+            if (z >= P.nz) return hzp[(yl0 + r) * LX + lx];
+            return *reinterpret_cast<const uint4 *>(col + (size_t)z * plane + (size_t)r * P.nx);
+        };
+        auto load_halo_lo = [&](int zl) -> uint4 {                            // row y0-1 of plane z0+zl
+            if (top && fym) return hym[zl * LX + lx];
+            return *reinterpret_cast<const uint4 *>(col + (size_t)(z0 + zl) * plane - P.nx);
+        };
+        auto load_halo_hi = [&](int zl) -> uint4 {                            // row y0+RW of plane z0+zl
+            if (bot && fyp) return hyp[zl * LX + lx];
+            return *reinterpret_cast<const uint4 *>(col + (size_t)(z0 + zl) * plane + (size_t)RW * P.nx);
+        };
+        auto load_xe = [&](int zl, int r) -> __nv_bfloat16 {                  // lane 0: cell x0-1; lane 31: cell x0+8
+            const size_t o = (size_t)(z0 + zl) * plane + (size_t)r * P.nx;
+            if (lx == 0) return fxm ? hxm[zl * TY + yl0 + r] : col[o - 1];
+            return fxp ? hxp[zl * TY + yl0 + r] : col[o + 8];
+        };
+        const bool xedge = lx == 0 || lx == LX - 1;
+        float prev[RW][8], cur[RW][8];
+        uint4 nxt[RW], hlo, hhi;
+        __nv_bfloat16 xe[RW];
+#pragma unroll
+        for (int r = 0; r < RW; r++) {
+            unpack8(load_own(z0 - 1, r), prev[r]);
+            unpack8(load_own(z0, r), cur[r]);
+            nxt[r] = load_own(z0 + 1, r);
+            xe[r] = xedge ? load_xe(0, r) : __float2bfloat16(0.f);
+        }
+        hlo = load_halo_lo(0); hhi = load_halo_hi(0);
+#pragma unroll 1
+        for (int zl = 0; zl < TZ; zl++) {
+            const int z = z0 + zl;
+            // consume this plane's prefetched operands ...
+            uint4 vn[RW];
+            float edge[RW];
+#pragma unroll
+            for (int r = 0; r < RW; r++) { vn[r] = nxt[r]; edge[r] = __bfloat162float(xe[r]); }
+            const uint4 vlo = hlo, vhi = hhi;
+            // ... and put the next plane's in flight before the math
+            if (zl + 1 < TZ) {
+#pragma unroll
+                for (int r = 0; r < RW; r++) { nxt[r] = load_own(z + 2, r); if (xedge) xe[r] = load_xe(zl + 1, r); }
+                hlo = load_halo_lo(zl + 1); hhi = load_halo_hi(zl + 1);
+            }
+            float below[8];                       // old value of the row beneath the one being updated (y-1)
+            unpack8(vlo, below);
+#pragma unroll
+            for (int r = 0; r < RW; r++) {
+                float above[8], nf[8], out[8];
+                if (r < RW - 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) above[i] = cur[r + 1][i];
+                } else unpack8(vhi, above);
+                unpack8(vn[r], nf);
+                float left = __shfl_up_sync(0xffffffffu, cur[r][7], 1), right = __shfl_down_sync(0xffffffffu, cur[r][0], 1);
+                if (lx == 0) left = edge[r];
+                if (lx == LX - 1) right = edge[r];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float xm = i == 0 ? left : cur[r][i - 1], xp = i == 7 ? right : cur[r][i + 1];
+                    out[i] = P.c0 * cur[r][i] + P.c1 * (((xm + xp) + (below[i] + above[i])) + (prev[r][i] + nf[i]));
+                }
+                const uint4 vo = pack8(out);
+                *reinterpret_cast<uint4 *>(ocol + (size_t)z * plane + (size_t)r * P.nx) = vo;
+                if (fzm && zl == 0) rzm[(yl0 + r) * LX + lx] = vo;
+                if (fzp && zl == TZ - 1) rzp[(yl0 + r) * LX + lx] = vo;
+                if (fym && top && r == 0) rym[zl * LX + lx] = vo;
+                if (fyp && bot && r == RW - 1) ryp[zl * LX + lx] = vo;
+                if (fxm && lx == 0) xface[0][zl * TY + yl0 + r] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[0];
+                if (fxp && lx == LX - 1) xface[1][zl * TY + yl0 + r] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[7];
+#pragma unroll
+                for (int i = 0; i < 8; i++) { below[i] = cur[r][i]; prev[r][i] = cur[r][i]; cur[r][i] = nf[i]; }
+            }
+        }
+        __syncthreads();
+        if (fxm && tid < TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[0], px_))[tid] = ((const uint4 *)xface[0])[tid];
+        if (fxp && tid >= 64 && tid < 64 + TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[1], px_))[tid - 64] = ((const uint4 *)xface[1])[tid - 64];
+        if (fxm | fxp | fym | fyp | fzm | fzp) {
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence_system();
                 if (fxm) acx::pready_signal_epoch(px_, P.send[0], P.signal_val);
                 if (fxp) acx::pready_signal_epoch(px_, P.send[1], P.signal_val);
                 if (fym) acx::pready_signal_epoch(py_, P.send[2], P.signal_val);
@@ -203,7 +377,7 @@ struct acx_halo {
     MPIX_Request sreq[2][6], rreq[2][6];
     MPIX_Prequest spre[2][6], rpre[2][6];
     int *order_d;
-    int grid;
+    int grid, variant;
 };
 
 #define HCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[acx halo] %s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return 1; } } while (0)
@@ -254,7 +428,13 @@ extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, f
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step, LX * TY, 0);
+    const char *var = getenv("ACX_HALO_VARIANT");
+    h->variant = var ? atoi(var) : 3;
+    if (h->variant == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step<1, 2>, LX * TY, 0);
+    else if (h->variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step<2, 1>, LX * TY, 0);
+    else if (h->variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step<4, 1>, LX * TY, 0);
+    else if (h->variant == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_rows<3>, NW * 32, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_rows<2>, NW * 32, 0);
     if (occ < 1) occ = 1;
     h->grid = std::min(h->ntiles, sms * occ);
     MPI_Barrier(MPI_COMM_WORLD);
@@ -288,7 +468,11 @@ extern "C" int acx_halo_step(acx_halo *h, int nsteps, cudaStream_t stream) {
         for (int f = 0; f < 6; f++) { P.recv[f] = (const acx_pchan *)h->rpre[rp][f]; P.send[f] = (const acx_pchan *)h->spre[sp][f]; }
         P.wait_val = h->step + 1; P.signal_val = h->step + 2;
         P.c0 = h->c0; P.c1 = h->c1; P.order = h->order_d; P.ntiles = h->ntiles;
-        halo_stencil_step<<<h->grid, dim3(LX, TY), 0, stream>>>(P);
+        if (h->variant == 0) halo_stencil_step<1, 2><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
+        else if (h->variant == 1) halo_stencil_step<2, 1><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
+        else if (h->variant == 2) halo_stencil_step<4, 1><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
+        else if (h->variant == 3) halo_stencil_step_rows<3><<<h->grid, NW * 32, 0, stream>>>(P);
+        else halo_stencil_step_rows<2><<<h->grid, NW * 32, 0, stream>>>(P);
         HCK(cudaGetLastError());
         h->cur ^= 1;
         h->step++;

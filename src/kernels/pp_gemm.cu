@@ -27,6 +27,15 @@ struct acx_ppgemm {
 #define PCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[acx ppgemm] %s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return 1; } } while (0)
 #define POK(x) do { int r_ = (x); if (r_) { fprintf(stderr, "[acx ppgemm] %s:%d %s -> %d\n", __FILE__, __LINE__, #x, r_); return 1; } } while (0)
 
+// Plain (non-communicating) use of the same kernel: Y = scale * X * W^T, all local.
+extern "C" int acx_gemm_fp8(const void *X, const void *W, void *Y, int M, int N, int K, float scale, cudaStream_t stream) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    acxg::Gating g = {};
+    return acxg::launch_gemm_fp8((const uint8_t *)X, (const uint8_t *)W, (uint8_t *)Y, M, N, K, scale, g, sms, stream);
+}
+
 extern "C" int acx_ppgemm_create(int M, int D, int partitions, float scale, acx_ppgemm **out) {
     acx_ppgemm *h = new acx_ppgemm();
     memset(h, 0, sizeof *h);

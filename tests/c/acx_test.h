@@ -40,6 +40,7 @@ static int t_rank, t_size, t_errs, t_gpu;
 /* Init MPI + device selection (rank % ndevices, like the reference tests) + ACX. */
 static void t_init(int *argc, char ***argv, int need_gpu) {
     int provided, ndev = 0;
+    setvbuf(stdout, NULL, _IONBF, 0);
     MPI_Init_thread(argc, argv, MPI_THREAD_MULTIPLE, &provided);
     if (provided < MPI_THREAD_MULTIPLE) MPI_Abort(MPI_COMM_WORLD, 1);
     MPI_Comm_rank(MPI_COMM_WORLD, &t_rank);

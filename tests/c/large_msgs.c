@@ -22,8 +22,8 @@ int main(int argc, char **argv) {
             size_t n = sizes[si] > maxb ? maxb : sizes[si];
             int salt = t_rank * 17 + (int)si;
             for (size_t i = 0; i < n; i++) h[i] = pat(i, salt);
-            T_CUDA(cudaMemcpy(d_out, h, n, cudaMemcpyHostToDevice));
-            T_CUDA(cudaMemset(d_in, 0xee, n + 16));
+            T_CUDA(cudaMemcpyAsync(d_out, h, n, cudaMemcpyHostToDevice, stream));   /* same stream as the ops: ordered before them */
+            T_CUDA(cudaMemsetAsync(d_in, 0xee, n + 16, stream));
             MPIX_Request rq[2];
             MPI_Status st;
             if (si & 1) {
@@ -50,8 +50,8 @@ int main(int argc, char **argv) {
             enum { K = 6, LEN = 3000, CAP = 5000 };
             MPIX_Request sq[2 * K], rq[2 * K];
             for (int i = 0; i < 2 * K * LEN; i++) h[i] = pat(i, t_rank + 99);
-            T_CUDA(cudaMemcpy(d_out, h, 2 * K * LEN, cudaMemcpyHostToDevice));
-            T_CUDA(cudaMemset(d_in, 0, 2 * K * CAP));
+            T_CUDA(cudaMemcpyAsync(d_out, h, 2 * K * LEN, cudaMemcpyHostToDevice, stream));
+            T_CUDA(cudaMemsetAsync(d_in, 0, 2 * K * CAP, stream));
             for (int k = 0; k < K; k++) for (int tg = 0; tg < 2; tg++)
                 T_OK(MPIX_Isend_enqueue(d_out + (size_t)(2 * k + tg) * LEN, LEN, MPI_BYTE, T_RIGHT, 20 + tg, MPI_COMM_WORLD, &sq[2 * k + tg], MPIX_QUEUE_CUDA_STREAM, &stream));
             for (int tg = 1; tg >= 0; tg--) for (int k = 0; k < K; k++)

@@ -79,3 +79,104 @@ def test_bench_smoke_one_gpu():
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     j = json.loads(line)
     assert j["verified"] and j["value"] > 0 and j["gpu_launches"] > 0
+
+
+def test_watchdog_reports_dropped_send(built):
+    """Failure detection: with fault injection dropping the first send, the matching receive must end in
+    the device watchdog (trap + diagnostic), not in a hang."""
+    r = acxrun(built, 1, built / "build/tests/ring", env={"ACX_FAULT_DROP_SEND": "1", "ACX_WATCHDOG_MS": "1500"}, timeout=120)
+    assert r.returncode != 0
+    assert "FAULT INJECTION" in r.stderr and "WATCHDOG" in (r.stderr + r.stdout)
+
+
+def test_trace_ring_dump(built, tmp_path):
+    r = acxrun(built, 2, built / "build/tests/ring_all_device", env={"ACX_TRACE": "1", "ACX_TRACE_DIR": str(tmp_path)})
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    import json
+    recs = [json.loads(l) for l in (tmp_path / "acx_trace_rank0.jsonl").read_text().splitlines()]
+    evs = {x["ev"] for x in recs}
+    assert {"send_trigger", "recv_trigger", "wait_begin", "wait_end"} <= evs and ("move_begin" in evs)
+    assert all(a["t_ns"] <= b["t_ns"] + 10_000_000 for a, b in zip(recs, recs[1:]))
+
+
+def test_recv_depth_limit_is_an_error_not_a_deadlock(tmp_path):
+    src = tmp_path / "depth.c"
+    src.write_text(r'''
+#include <mpi.h>
+#include <mpi-acx.h>
+#include <stdio.h>
+int main(int argc, char **argv) {
+    int prov; MPI_Init_thread(&argc, &argv, MPI_THREAD_MULTIPLE, &prov);
+    cudaSetDevice(0);
+    if (MPIX_Init()) return 2;
+    cudaStream_t s = 0; static int buf[64]; MPIX_Request q[64]; int rc = 0, i;
+    for (i = 0; i < 40 && rc == 0; i++) rc = MPIX_Irecv_enqueue(&buf[i], 1, MPI_INT, 0, 3, MPI_COMM_WORLD, &q[i], MPIX_QUEUE_CUDA_STREAM, &s);
+    printf("posted %d rc %d\n", i, rc);
+    /* satisfy the posted ones so finalize is clean */
+    int n = rc ? i - 1 : i, v = 7; MPIX_Request sq;
+    for (int k = 0; k < n; k++) { MPIX_Isend_enqueue(&v, 1, MPI_INT, 0, 3, MPI_COMM_WORLD, &sq, MPIX_QUEUE_CUDA_STREAM, &s); MPIX_Wait_enqueue(&sq, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &s); }
+    MPIX_Waitall_enqueue(n, q, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &s);
+    cudaStreamSynchronize(s);
+    MPIX_Finalize(); MPI_Finalize();
+    return rc != 0 && i == 33 ? 0 : 1;
+}
+''')
+    exe = tmp_path / "depth"
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-I", str(REPO / "include"), str(src), "-o", str(exe), "-L", str(REPO / "lib"), "-lacx",
+                    "-Xlinker", f"-rpath,{REPO / 'lib'}"], check=True, capture_output=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120, env=dict(os.environ, ACX_WATCHDOG_MS="20000"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ACX_DEPTH" in r.stderr
+
+
+def test_halo_stencil_matches_torch_reference():
+    """Fused halo+stencil kernel on one GPU (periodic self-exchange) vs the plain PyTorch fp32 reference."""
+    script = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import mpi_acx_b200 as acx
+from mpi_acx_b200.ops import HaloStencil, stencil_reference
+acx.init(0)
+op = HaloStencil(256, 32, 64, (1, 1, 1))
+torch.manual_seed(3)
+u0 = torch.randn(64, 32, 256, device="cuda").to(torch.bfloat16)
+op.field().copy_(u0)
+op.step(5)
+torch.cuda.synchronize()
+got = op.field().float()
+ref = stencil_reference(u0, steps=5).float()
+err = (got - ref).abs().max().item()
+print("max abs err", err)
+assert err <= 0.02, err
+op.close(); acx.finalize(); print("HALO OK")
+""" % str(REPO)
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300, env=dict(os.environ, ACX_WATCHDOG_MS="30000"))
+    assert r.returncode == 0 and "HALO OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_gemm_fp8_matches_torch_reference():
+    """tcgen05 fp8 GEMM vs a plain PyTorch fp32 matmul of the dequantized operands."""
+    script = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import mpi_acx_b200 as acx
+from mpi_acx_b200.ops import gemm_fp8
+acx.init(0)
+torch.manual_seed(5)
+for (M, N, K) in [(128, 256, 128), (256, 512, 1024), (1024, 1024, 4096)]:
+    x = torch.randn(M, K, device="cuda").clamp_(-3, 3).to(torch.float8_e4m3fn)
+    w = torch.randn(N, K, device="cuda").clamp_(-3, 3).to(torch.float8_e4m3fn)
+    scale = 1.0 / K ** 0.5
+    y = gemm_fp8(x, w, scale).float()
+    torch.cuda.synchronize()
+    ref = (x.float() @ w.float().t()) * scale
+    # the kernel rounds fp32 -> e4m3 (3 mantissa bits): compare against the fp32 reference with e4m3 resolution
+    err = (y - ref).abs()
+    tol = ref.abs() * 0.07 + 0.02
+    bad = (err > tol).sum().item()
+    print(M, N, K, "max err", err.max().item(), "bad", bad)
+    assert bad == 0, (M, N, K, bad)
+acx.finalize(); print("GEMM OK")
+""" % str(REPO)
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "GEMM OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]

@@ -37,3 +37,10 @@ for f in ["pingpong_acx_heap.json","pingpong_acx_private.json","pingpong_ref.jso
         print(f, [(r["bytes"], round(r["oneway_us"],1), round(r["gbs"],1)) for r in j["rows"] if r["bytes"] in (8,1024,8192,16384,65536,1<<20,16<<20,256<<20,1<<30)])
     except Exception as e: print(f, "ERR", e)
 PY
+echo "### gemm fp8 single GPU"
+timeout 120 build/tests/gemm_fp8_test 1024 1024 1024 5 2>&1 | tail -n 12
+timeout 120 build/tests/gemm_fp8_test 8192 8192 8192 10 2>&1 | tail -n 6
+echo "### ppgemm fused np=2"
+ACX_HEAP_BYTES=1g timeout 120 ./bin/acxrun -np 2 --timeout 100 bin/ppgemm_bench fused --steps 10 2>&1 | tail -n 6 | tee $O/ppgemm_fused_n2.json
+ACX_HEAP_BYTES=1g timeout 120 ./bin/acxrun -np 1 --timeout 100 bin/ppgemm_bench fused --steps 10 2>&1 | tail -n 4
+timeout 300 ./bin/acxrun -np 2 --timeout 280 $R/ppgemm_bench api --steps 5 2>&1 | tail -n 4 | tee $O/ppgemm_api_ref_n2.json
