@@ -45,6 +45,14 @@ def env_rank():
 def run_reference(a) -> int:
     rank, world, local = env_rank()
     exe = REPO / "baseline" / "_ref" / "bin" / "p2p_bench"
+    if not exe.exists() and Path("/root/reference/Makefile").exists() and rank == 0:
+        subprocess.run([str(REPO / "baseline" / "build_ref.sh")], capture_output=True, timeout=900)   # one-off build of the unmodified reference
+    if world > 1 and Path("/root/reference/Makefile").exists():
+        import time
+        for _ in range(600):   # other ranks wait for rank 0's build
+            if exe.exists():
+                break
+            time.sleep(1)
     if not exe.exists():
         if rank == 0:
             print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/bin/p2p_bench missing (run baseline/build_ref.sh; the reference is a C/CUDA library, not pip-installable)"}))

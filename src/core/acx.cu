@@ -42,6 +42,7 @@ static std::mutex g_deferred_mu;
 
 // NVTX ranges around the API calls (ACX_NVTX=1); header-only NVTX, a no-op without a tool attached.
 static int g_mover_tma = 0, g_mover_256 = 0;
+static int g_fuse_rndv = 1, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
 static int g_pdl = 1;   // programmatic dependent launch between consecutive acx kernels on a stream (ACX_PDL)
 static bool g_nvtx = false;
 struct AcxRange {
@@ -82,6 +83,7 @@ static void report_watchdog() {
             case 0x5e06: what = "partitioned wait(send): a partition was never marked ready"; break;
             case 0x5e07: what = "partitioned wait(recv): a partition never arrived"; break;
             case 0x5e08: what = "partitioned wait(recv): a device poller never finished its copy-out"; break;
+            case 0x5e09: what = "fused rendezvous: CTA 0 never published the match decision"; break;
         }
         ACX_ERR("WATCHDOG (code 0x%llx, a=0x%llx b=0x%llx): %s", (unsigned long long)g_diag[0], (unsigned long long)g_diag[1],
                 (unsigned long long)g_diag[2], what);
@@ -455,6 +457,8 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_NVTX", nullptr, 0, &v); g_nvtx = v != 0;
     { const char *m = getenv("ACX_MOVER"); g_mover_tma = m && !strcmp(m, "tma"); g_mover_256 = m && !strcmp(m, "ldst256"); }
     acx_env_int("ACX_PDL", nullptr, 1, &v); g_pdl = v != 0;
+    acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
+    acx_env_int("ACX_FUSE_MAX_CTAS", nullptr, 32, &v); g_fuse_max_ctas = (int)v;
     acx_env_int("ACX_FAULT_DROP_SEND", nullptr, 0, &v); g_fault_drop_send = v;
     acx_env_int("ACX_MOVER_MAX_CTAS", nullptr, 0, &v); g_acx->mover_max_ctas = (int)v;
     acx_env_int("ACX_MOVER_CTA_BYTES", nullptr, 64 << 10, &v); g_acx->mover_min_cta_bytes = (size_t)std::max(4096L, v);
@@ -745,6 +749,34 @@ struct Emitter {
         g_acx->st.graph_nodes++;
         return 0;
     }
+    template <typename P, typename Q>
+    int launch2(void (*kern)(P, Q), dim3 grid, dim3 block, P &p1, Q &p2) {
+        void *args[] = {&p1, &p2};
+        if (qtype == MPIX_QUEUE_CUDA_STREAM) {
+            cudaError_t e;
+            if (g_pdl && !capturing) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = grid; cfg.blockDim = block; cfg.stream = stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                e = cudaLaunchKernelExC(&cfg, (const void *)kern, args);
+            } else e = cudaLaunchKernel((const void *)kern, grid, block, args, 0, stream);
+            if (e != cudaSuccess) { report_watchdog(); ACX_ERR("kernel launch failed: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+            g_acx->st.kernels++;
+            if (capturing) g_acx->st.graph_nodes++;
+            return 0;
+        }
+        cudaKernelNodeParams np = {};
+        np.func = (void *)kern; np.gridDim = grid; np.blockDim = block; np.kernelParams = args;
+        cudaGraphNode_t node;
+        cudaError_t e = cudaGraphAddKernelNode(&node, graph, (last && !parallel) ? &last : nullptr, (last && !parallel) ? 1 : 0, &np);
+        if (e != cudaSuccess) { ACX_ERR("cudaGraphAddKernelNode: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+        last = node;
+        g_acx->st.graph_nodes++;
+        return 0;
+    }
     int launch3(void (*kern)(char *, const char *, uint64_t), dim3 grid, dim3 block, char *a, const char *b, uint64_t c) {
         void *args[] = {&a, &b, &c};
         if (qtype == MPIX_QUEUE_CUDA_STREAM) {
@@ -905,12 +937,16 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         sp.wd = make_wd(); sp.tr = make_tr();
         const bool dropped = g_fault_drop_send > 0 && ++g_send_counter == g_fault_drop_send;
         if (dropped) ACX_ERR("FAULT INJECTION: dropping send #%ld (tag %d -> rank %d)", g_fault_drop_send, tag, dest);
-        if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
+        MoverParams mp;
+        memset(&mp, 0, sizeof mp);
+        mp.op = sp.op; mp.local = (char *)src_local; mp.ring = sp.ring; mp.sack = sp.sack; mp.depth = G.depth; mp.push = 1; mp.peer = dest; mp.tr = sp.tr;
+        mp.vec256 = g_mover_256;
+        const int fgrid = (!eager && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
+        const bool fused = fgrid > 0 && fgrid <= g_fuse_max_ctas;
+        if (!dropped && fused) { if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail; }
+        else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
         if (!eager) {
-            MoverParams mp;
-            memset(&mp, 0, sizeof mp);
-            mp.op = sp.op; mp.local = (char *)src_local; mp.ring = sp.ring; mp.sack = sp.sack; mp.depth = G.depth; mp.push = 1; mp.peer = dest; mp.tr = sp.tr;
-            if ((rc = launch_mover(em, mp, bytes))) goto fail;
+            if (!fused && (rc = launch_mover(em, mp, bytes))) goto fail;
             g_acx->st.rndv++;
         } else {
             g_acx->st.eager++;
@@ -990,13 +1026,16 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         rp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)source * G.maxreg;
         rp.dst_off = dst_off; rp.cap = bytes; rp.serial = r->serial; rp.depth = G.depth; rp.peer = source;
         rp.wd = make_wd(); rp.tr = make_tr();
-        if ((rc = em.launch(recv_trigger, dim3(1), dim3(32), rp))) goto fail;
-        if (rndv_capable) {
-            MoverParams mp;
-            memset(&mp, 0, sizeof mp);
-            mp.op = rp.op; mp.local = dst_local; mp.ring = rp.ring; mp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;
-            mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr;
-            if ((rc = launch_mover(em, mp, bytes))) goto fail;
+        MoverParams mp;
+        memset(&mp, 0, sizeof mp);
+        mp.op = rp.op; mp.local = dst_local; mp.ring = rp.ring; mp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;
+        mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr; mp.vec256 = g_mover_256;
+        const int fgrid = (rndv_capable && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
+        if (fgrid > 0 && fgrid <= g_fuse_max_ctas) {
+            if ((rc = em.launch2(recv_rndv_fused, dim3(fgrid), dim3(kMoverThreads), rp, mp))) goto fail;
+        } else {
+            if ((rc = em.launch(recv_trigger, dim3(1), dim3(32), rp))) goto fail;
+            if (rndv_capable && (rc = launch_mover(em, mp, bytes))) goto fail;
         }
     }
     if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;

@@ -66,9 +66,11 @@ struct alignas(64) acx_op {  // per request slot, local
     uint32_t mover;      // 1 if this side arrived second and must move the data
     uint32_t eager;      // send side: message went eager (nothing to wait for)
     uint32_t cta_count;  // last-CTA detection
-    uint32_t pad;
+    uint32_t pad;        // fused rendezvous: CTAs that have left the kernel (last one re-arms the gate)
     uint64_t recv_bytes; // receive side: actual message size
     uint64_t bounce_n;   // receive side: bytes the bounce-out kernel still has to copy (0 if eager/zero-copy)
+    uint64_t fused_decided;  // single-launch rendezvous gate: 1 once CTA 0 has published the match of this launch
+    uint64_t pad2;
 };
 
 struct acx_host_status {  // pinned host memory, one per request slot; written by wait kernels

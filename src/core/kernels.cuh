@@ -125,6 +125,30 @@ struct SendParams {
     TraceCtx tr;
 };
 
+// Rendezvous half of the send trigger (one thread): publish the source, add to the slot's state word,
+// and if the receive is already posted resolve the destination (this side will push).
+__device__ __forceinline__ void send_rndv_match(const SendParams &p, uint64_t k) {
+    const uint32_t e = (uint32_t)(k % p.depth);
+    const uint64_t g = k / p.depth;
+    acx_entry *ent = p.ring + e;
+
+    ent->s_src_off = p.src_off; ent->s_bytes = p.bytes;
+    *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)ACX_KIND_RNDV << 32);
+    uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull << 32);
+    p.op->ticket = k; p.op->eager = 0; p.op->cta_count = 0;
+    if ((uint32_t)old == (uint32_t)(g + 1)) {  // receive already posted: I move the data (push)
+        // the receiver mirrored its destination into MY sack before it bumped the state word
+        uint64_t cap = ld_relaxed_sys(&p.sack[e].r_cap), off = ld_relaxed_sys(&p.sack[e].r_dst_off);
+        p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, off);
+        p.op->n = p.bytes < cap ? p.bytes : cap;
+        p.op->mover = 1;
+    } else {
+        p.op->mover = 0;
+    }
+    st_release_sys(&p.op->armed, p.serial);
+    trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes | (1ull << 63));
+}
+
 __global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
     pdl_prologue();
     __shared__ uint64_t s_k;
@@ -155,24 +179,9 @@ __global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
             trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes);
         }
     } else if (tid == 0) {
-        ent->s_src_off = p.src_off; ent->s_bytes = p.bytes;
-        *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)ACX_KIND_RNDV << 32);
-        uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull << 32);
-        p.op->ticket = k; p.op->eager = 0; p.op->cta_count = 0;
-        if ((uint32_t)old == (uint32_t)(g + 1)) {  // receive already posted: I move the data (push)
-            // the receiver mirrored its destination into MY sack before it bumped the state word
-            uint64_t cap = ld_relaxed_sys(&p.sack[e].r_cap), off = ld_relaxed_sys(&p.sack[e].r_dst_off);
-            p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, off);
-            p.op->n = p.bytes < cap ? p.bytes : cap;
-            p.op->mover = 1;
-        } else {
-            p.op->mover = 0;
-        }
-        st_release_sys(&p.op->armed, p.serial);
-        trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes | (1ull << 63));
+        send_rndv_match(p, k);
     }
 }
-
 // ---------------------------------------------------------------------------------------
 // RECV trigger: take a ticket, publish destination, add to the state word.
 // ---------------------------------------------------------------------------------------
@@ -191,9 +200,7 @@ struct RecvParams {
     TraceCtx tr;
 };
 
-__global__ void recv_trigger(RecvParams p) {
-    pdl_prologue();
-    if (threadIdx.x != 0) return;
+__device__ __forceinline__ void recv_match(const RecvParams &p) {   // one thread
     uint64_t k = atomicAdd((unsigned long long *)p.seq, 1ull);
     uint32_t e = (uint32_t)(k % p.depth);
     uint64_t g = k / p.depth;
@@ -216,6 +223,11 @@ __global__ void recv_trigger(RecvParams p) {
     trace(p.tr, ACX_EV_RECV_TRIGGER, p.peer, k, p.cap);
 }
 
+__global__ void recv_trigger(RecvParams p) {
+    pdl_prologue();
+    if (threadIdx.x == 0) recv_match(p);
+}
+
 // ---------------------------------------------------------------------------------------
 // Mover: launched right after a rendezvous-capable trigger with a bandwidth-sized grid.
 // Exits immediately unless the trigger found this side to be the second arriver.
@@ -232,8 +244,7 @@ struct MoverParams {
     TraceCtx tr;
 };
 
-__global__ void __launch_bounds__(kMoverThreads) mover(MoverParams p) {
-    pdl_prologue();
+__device__ __forceinline__ void mover_body(const MoverParams &p) {
     acx_op *op = p.op;
     if (!op->mover) return;
     const uint64_t n = op->n;
@@ -264,6 +275,58 @@ __global__ void __launch_bounds__(kMoverThreads) mover(MoverParams p) {
             trace(p.tr, ACX_EV_MOVE_END, p.peer, k, n);
         }
     }
+}
+
+__global__ void __launch_bounds__(kMoverThreads) mover(MoverParams p) {
+    pdl_prologue();
+    mover_body(p);
+}
+
+// Single-launch rendezvous for small grids (all CTAs co-resident): CTA 0 runs the match and publishes the
+// decision; the others wait for it on a launch-indexed word (relaunch-safe in graphs), then everyone moves.
+// Saves one kernel launch + inter-kernel gap per message on each side.
+__device__ __forceinline__ void fused_exit(acx_op *op) {
+    // Every CTA is past the gate once it gets here: the last one out re-arms the gate for the next launch
+    // (graph relaunch) or the next owner of this request slot.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(&op->pad, 1u);
+        if (old == gridDim.x - 1) { op->pad = 0; st_relaxed_sys(&op->fused_decided, 0); }
+    }
+}
+__global__ void __launch_bounds__(kMoverThreads) send_rndv_fused(SendParams sp, MoverParams mp) {
+    pdl_prologue();
+    acx_op *op = sp.op;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            const uint64_t k = atomicAdd((unsigned long long *)sp.seq, 1ull);
+            spin_geq(&sp.sack[k % sp.depth].efree, k / sp.depth, sp.wd, 0x5e01);
+            send_rndv_match(sp, k);
+            __threadfence();
+            st_release_sys(&op->fused_decided, 1);
+        } else {
+            spin_geq(&op->fused_decided, 1, sp.wd, 0x5e09);
+        }
+    }
+    __syncthreads();
+    mover_body(mp);
+    fused_exit(op);
+}
+__global__ void __launch_bounds__(kMoverThreads) recv_rndv_fused(RecvParams rp, MoverParams mp) {
+    pdl_prologue();
+    acx_op *op = rp.op;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            recv_match(rp);
+            __threadfence();
+            st_release_sys(&op->fused_decided, 1);
+        } else {
+            spin_geq(&op->fused_decided, 1, rp.wd, 0x5e09);
+        }
+    }
+    __syncthreads();
+    mover_body(mp);
+    fused_exit(op);
 }
 
 // ---------------------------------------------------------------------------------------
