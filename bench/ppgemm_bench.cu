@@ -118,7 +118,12 @@ static int run_api(int M, int D, int P, int steps, int warmup, bool check) {
     const size_t act = (size_t)M * D;
     const bool first = g_rank == 0, last = g_rank == g_size - 1;
     uint8_t *W, *xin, *ysend;
-    CK(cudaMalloc(&W, (size_t)D * D)); CK(cudaMalloc(&xin, act)); CK(cudaMalloc(&ysend, act));
+    CK(cudaMalloc(&W, (size_t)D * D));
+#ifndef ACX_BENCH_REFERENCE
+    OK(MPIX_Alloc_mem(act, MPI_INFO_NULL, &xin)); OK(MPIX_Alloc_mem(act, MPI_INFO_NULL, &ysend));   // symmetric heap: partitions land in place
+#else
+    CK(cudaMalloc(&xin, act)); CK(cudaMalloc(&ysend, act));
+#endif
     fill_e4m3<<<1024, 256>>>(W, (size_t)D * D, 1000u + g_rank);
     if (first) fill_e4m3<<<1024, 256>>>(xin, act, 7u);
     CK(cudaDeviceSynchronize());
@@ -171,7 +176,12 @@ static int run_api(int M, int D, int P, int steps, int warmup, bool check) {
     if (rq) MPIX_Prequest_free(&rq);
     if (sq) MPIX_Prequest_free(&sq);
     for (int i = 0; i < nreq; i++) OK(MPIX_Request_free(&reqs[i]));
-    cudaFree(W); cudaFree(xin); cudaFree(ysend);
+    cudaFree(W);
+#ifndef ACX_BENCH_REFERENCE
+    MPIX_Free_mem(xin); MPIX_Free_mem(ysend);
+#else
+    cudaFree(xin); cudaFree(ysend);
+#endif
     return badmax != 0;
 }
 

@@ -7,7 +7,7 @@ import subprocess
 from typing import Optional
 
 _Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-      "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+      "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
 
 class ClockSampler:
@@ -34,7 +34,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
             out, _ = self.p.communicate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, busy = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
@@ -44,7 +44,13 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                if len(f) > 8 and float(f[8]) >= 10.0:
+                    busy.append(float(f[1]))
+            except ValueError:
+                pass
             for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        load = busy or sm   # median over samples taken while the GPU was busy; all samples if none qualified
+        return {"sm_mhz": statistics.median(load) if load else None, "samples_under_load": len(busy), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}

@@ -37,12 +37,15 @@ int acx_env_int(const char *name, const char *alt, long dflt, long *out) {
 
 static uint64_t *g_diag = nullptr, *g_diag_d = nullptr;      // watchdog diagnostics (pinned)
 static uint64_t *g_trace_cursor = nullptr;                   // device
+static std::vector<int> g_pending_retire;                    // slots whose wait has been enqueued; freed once the device marks them retired
 static std::vector<int> g_deferred_slots;                    // freed by graph user-object destructors
 static std::mutex g_deferred_mu;
 
 // NVTX ranges around the API calls (ACX_NVTX=1); header-only NVTX, a no-op without a tool attached.
 static int g_mover_tma = 0, g_mover_256 = 0;
-static int g_fuse_rndv = 1, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
+static int g_side_on = 1;                 // run large movers on per-peer side streams so transfers to different peers overlap (ACX_SIDE_STREAMS)
+static std::vector<cudaStream_t> g_side;  // side streams, indexed by peer % size
+static int g_fuse_rndv = 1, g_fuse_min_ctas = 8, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
 static int g_pdl = 1;   // programmatic dependent launch between consecutive acx kernels on a stream (ACX_PDL)
 static bool g_nvtx = false;
 struct AcxRange {
@@ -103,8 +106,18 @@ static void report_watchdog() {
 // =======================================================================================
 // allocators
 // =======================================================================================
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t event_get() {
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return e;
+}
 static void release_request_resources(AcxRequest *r) {
     if (r->bounce_off >= 0) { acx_heap_free(r->bounce_off); r->bounce_off = -1; }
+    if (r->ev_trig) { g_event_pool.push_back(r->ev_trig); r->ev_trig = nullptr; }
+    if (r->ev_done) { g_event_pool.push_back(r->ev_done); r->ev_done = nullptr; }
 }
 
 void acx_slot_free(int slot) {
@@ -130,13 +143,18 @@ void acx_reclaim_retired() {
         for (int s : g_deferred_slots) if (g_acx->slot_busy[s]) acx_slot_free(s);
         g_deferred_slots.clear();
     }
-    for (int s = 0; s < g_acx->geom.nops; s++)
+    size_t keep = 0;
+    for (size_t i = 0; i < g_pending_retire.size(); i++) {
+        const int s = g_pending_retire[i];
         if (g_acx->slot_busy[s] == 3 && g_acx->hstat[s].retired) acx_slot_free(s);
+        else if (g_acx->slot_busy[s] == 3) g_pending_retire[keep++] = s;
+    }
+    g_pending_retire.resize(keep);
 }
 
 int acx_slot_alloc(AcxRequest *r, bool graph) {
     std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
-    if (g_acx->free_slots.empty()) acx_reclaim_retired();
+    if (g_acx->free_slots.empty() || g_pending_retire.size() >= 64) acx_reclaim_retired();
     if (g_acx->free_slots.empty()) {
         // Waited-on stream ops retire asynchronously; give in-flight waits a moment.
         for (int i = 0; i < 2000 && g_acx->free_slots.empty(); i++) { usleep(100); acx_reclaim_retired(); }
@@ -364,7 +382,7 @@ static uint64_t reg_encode(const void *p, size_t bytes, int peer) {
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return ~0ull; }
     if (a.type != cudaMemoryTypeDevice || a.device != g_acx->dev) return ~0ull;
     unsigned long long id = 0;
-    if (g_cuPointerGetAttribute(&id, 9 /*CU_POINTER_ATTRIBUTE_BUFFER_ID*/, (unsigned long long)p) != 0) return ~0ull;
+    if (g_cuPointerGetAttribute(&id, 7 /*CU_POINTER_ATTRIBUTE_BUFFER_ID*/, (unsigned long long)p) != 0) return ~0ull;
     std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
     AcxRegTable *mine = g_reg_tables + g_acx->rank;
     auto it = g_reg_mine.find(id);
@@ -458,7 +476,9 @@ extern "C" int MPIX_Init(void) {
     { const char *m = getenv("ACX_MOVER"); g_mover_tma = m && !strcmp(m, "tma"); g_mover_256 = m && !strcmp(m, "ldst256"); }
     acx_env_int("ACX_PDL", nullptr, 1, &v); g_pdl = v != 0;
     acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
+    acx_env_int("ACX_SIDE_STREAMS", nullptr, 1, &v); g_side_on = v != 0;
     acx_env_int("ACX_FUSE_MAX_CTAS", nullptr, 32, &v); g_fuse_max_ctas = (int)v;
+    acx_env_int("ACX_FUSE_MIN_CTAS", nullptr, 8, &v); g_fuse_min_ctas = (int)v;
     acx_env_int("ACX_FAULT_DROP_SEND", nullptr, 0, &v); g_fault_drop_send = v;
     acx_env_int("ACX_MOVER_MAX_CTAS", nullptr, 0, &v); g_acx->mover_max_ctas = (int)v;
     acx_env_int("ACX_MOVER_CTA_BYTES", nullptr, 64 << 10, &v); g_acx->mover_min_cta_bytes = (size_t)std::max(4096L, v);
@@ -549,6 +569,8 @@ extern "C" int MPIX_Init(void) {
     cudaHostGetDevicePointer((void **)&g_acx->hstat_d, g_acx->hstat, 0);
     cudaHostGetDevicePointer((void **)&g_diag_d, g_diag, 0);
     cudaStreamCreateWithFlags(&g_acx->istream, cudaStreamNonBlocking);
+    g_side.assign(8, nullptr);
+    for (auto &ss : g_side) cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking);
     g_acx->slot_busy.assign(g_acx->geom.nops, 0);
     g_acx->slot_req.assign(g_acx->geom.nops, nullptr);
     for (int s = g_acx->geom.nops - 1; s >= 0; s--) g_acx->free_slots.push_back(s);
@@ -589,6 +611,7 @@ extern "C" int MPIX_Finalize(void) {
                     s.kernels_launched, s.graph_nodes_added, s.slots_high_water, s.heap_bytes_high_water);
         }
         reg_finalize();
+        g_pending_retire.clear();
         for (int p = 0; p < g_acx->size; p++) {
             if (p == g_acx->rank) continue;
             if (g_acx->peer_ctrl[p]) cudaIpcCloseMemHandle(g_acx->peer_ctrl[p]);
@@ -597,6 +620,10 @@ extern "C" int MPIX_Finalize(void) {
         MPI_Barrier(MPI_COMM_WORLD);
         for (auto &r : g_acx->host_regs) cudaHostUnregister((void *)r.lo);
         cudaStreamDestroy(g_acx->istream);
+        for (auto ss : g_side) if (ss) cudaStreamDestroy(ss);
+        g_side.clear();
+        for (auto e : g_event_pool) cudaEventDestroy(e);
+        g_event_pool.clear();
         cudaFreeHost(g_acx->hstat);
         cudaFreeHost(g_diag);
         cudaFree(g_trace_cursor);
@@ -821,8 +848,8 @@ static int attach_to_graph(cudaGraph_t graph, int slot) {
 
 static int mover_grid(size_t bytes) {
     if (g_mover_tma) {
-        size_t g = (bytes + (256u << 10) - 1) / (256u << 10);   // >= 8 chunks per CTA keeps the ring busy
-        int cap = g_acx->mover_max_ctas > 0 ? g_acx->mover_max_ctas : g_acx->sm_count;
+        size_t g = (bytes + (128u << 10) - 1) / (128u << 10);   // >= 8 chunks per CTA keeps the ring busy
+        int cap = g_acx->mover_max_ctas > 0 ? g_acx->mover_max_ctas : 2 * g_acx->sm_count;
         return (int)std::max<size_t>(1, std::min<size_t>(g, cap));
     }
     return 0;
@@ -848,6 +875,24 @@ static int launch_mover(Emitter &em, MoverParams &mp, size_t bytes) {
     }
     mp.vec256 = g_mover_256;
     return em.launch(mover, dim3(mover_grid_ldst(bytes)), dim3(kMoverThreads), mp);
+}
+
+// Unfused movers of stream-mode operations run on a per-peer side stream, forked after the trigger kernel: the
+// user's stream is not held up by the transfer, and transfers to/from different peers overlap (all-pairs,
+// halo-style neighbour exchanges). The wait joins the side stream (required when capturing).
+static int launch_mover_maybe_side(Emitter &em, AcxRequest *r, MoverParams &mp, size_t bytes) {
+    if (!g_side_on || em.qtype != MPIX_QUEUE_CUDA_STREAM || g_side.empty()) return launch_mover(em, mp, bytes);
+    r->ev_trig = event_get(); r->ev_done = event_get();
+    if (!r->ev_trig || !r->ev_done) return launch_mover(em, mp, bytes);
+    cudaStream_t side = g_side[(size_t)r->peer % g_side.size()];
+    ACX_CUDA(cudaEventRecord(r->ev_trig, em.stream));
+    ACX_CUDA(cudaStreamWaitEvent(side, r->ev_trig, 0));
+    Emitter es = em;
+    es.stream = side;
+    int rc = launch_mover(es, mp, bytes);
+    if (rc) return rc;
+    ACX_CUDA(cudaEventRecord(r->ev_done, side));
+    return 0;
 }
 
 static inline int chan_of(int tag, int ctx) { return (int)(((unsigned)tag + 7u * (unsigned)ctx) % (unsigned)g_acx->geom.nchan); }
@@ -942,11 +987,11 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         mp.op = sp.op; mp.local = (char *)src_local; mp.ring = sp.ring; mp.sack = sp.sack; mp.depth = G.depth; mp.push = 1; mp.peer = dest; mp.tr = sp.tr;
         mp.vec256 = g_mover_256;
         const int fgrid = (!eager && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
-        const bool fused = fgrid > 0 && fgrid <= g_fuse_max_ctas;
+        const bool fused = fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas;   // measured: pays off from ~512 KiB, costs ~1.5 us below
         if (!dropped && fused) { if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail; }
         else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
         if (!eager) {
-            if (!fused && (rc = launch_mover(em, mp, bytes))) goto fail;
+            if (!fused && (rc = launch_mover_maybe_side(em, r, mp, bytes))) goto fail;
             g_acx->st.rndv++;
         } else {
             g_acx->st.eager++;
@@ -1031,11 +1076,11 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         mp.op = rp.op; mp.local = dst_local; mp.ring = rp.ring; mp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;
         mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr; mp.vec256 = g_mover_256;
         const int fgrid = (rndv_capable && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
-        if (fgrid > 0 && fgrid <= g_fuse_max_ctas) {
+        if (fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas) {
             if ((rc = em.launch2(recv_rndv_fused, dim3(fgrid), dim3(kMoverThreads), rp, mp))) goto fail;
         } else {
             if ((rc = em.launch(recv_trigger, dim3(1), dim3(32), rp))) goto fail;
-            if (rndv_capable && (rc = launch_mover(em, mp, bytes))) goto fail;
+            if (rndv_capable && (rc = launch_mover_maybe_side(em, r, mp, bytes))) goto fail;
         }
     }
     if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;
@@ -1160,6 +1205,10 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             MPI_Status *st = statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[idx];
             idx++;
             if (r->kind == ACX_REQ_SEND && st != MPI_STATUS_IGNORE && !em.in_graph()) host_status_send(st, r);
+            if (r->ev_done && em.capturing) {   // join the forked mover branch back into the capturing stream
+                cudaError_t je = cudaStreamWaitEvent(em.stream, r->ev_done, 0);
+                if (je != cudaSuccess) { ACX_ERR("cudaStreamWaitEvent(join): %s", cudaGetErrorString(je)); return MPI_ERR_OTHER; }
+            }
             if (r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max) continue;
             need.push_back({r, st});
         }
@@ -1198,7 +1247,7 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
     {
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
         for (AcxRequest *r : rs) {
-            if (retire) g_acx->slot_busy[r->slot] = 3;  // reclaimed once the device marks it retired
+            if (retire) { g_acx->slot_busy[r->slot] = 3; g_pending_retire.push_back(r->slot); }  // reclaimed once the device marks it retired
             if (retire && r->kind == ACX_REQ_RECV && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
         }
     }

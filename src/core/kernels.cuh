@@ -331,13 +331,13 @@ __global__ void __launch_bounds__(kMoverThreads) recv_rndv_fused(RecvParams rp, 
 
 // ---------------------------------------------------------------------------------------
 // TMA flavour of the mover (ACX_MOVER=tma): one elected thread per CTA drives a 4-stage ring of
-// 32-KiB bulk copies through shared memory — cp.async.bulk global->smem (mbarrier complete_tx),
-// then cp.async.bulk smem->global (bulk_group). The SM issues two instructions per 32 KiB instead
-// of 4096 LDG/STG pairs; peer addresses are served over NVLink by the TMA unit directly.
+// 16-KiB bulk copies through shared memory — cp.async.bulk global->smem (mbarrier complete_tx),
+// then cp.async.bulk smem->global (bulk_group). The SM issues two instructions per 16 KiB instead
+// of 2048 LDG/STG pairs; peer addresses are served over NVLink by the TMA unit directly.
 // Falls back to the LDG/STG loop for pointers/sizes that are not 16-B aligned.
 // ---------------------------------------------------------------------------------------
 constexpr int kTmaStages = 4;
-constexpr uint32_t kTmaChunk = 32768;
+constexpr uint32_t kTmaChunk = 16384;   // 4 x 16 KiB per CTA: three CTAs fit per SM, so a pushing and a pulling mover can co-reside
 constexpr int kTmaThreads = 128;
 constexpr int kTmaSmem = kTmaStages * (int)kTmaChunk + 64;
 

@@ -21,7 +21,9 @@ static void run(int use_heap, int host_calls) {
     int stack_send[NPART * PER], stack_recv[NPART * PER];
     int *send = stack_send, *recv = stack_recv;
     if (use_heap) { T_OK(MPIX_Alloc_mem(sizeof stack_send, MPI_INFO_NULL, &send)); T_OK(MPIX_Alloc_mem(sizeof stack_recv, MPI_INFO_NULL, &recv)); }
-    int h_send[NPART * PER], h_recv[NPART * PER];
+    /* staging copies live off the stack: the library pins the pages of host communication buffers in place, and CUDA
+     * rejects a cudaMemcpy whose host range is only partially pinned (a neighbour on the same stack page could be) */
+    static int h_send[NPART * PER], h_recv[NPART * PER];
     MPIX_Request rq[2];
     MPIX_Prequest pq[2];
     MPI_Status sts[2];

@@ -10,7 +10,7 @@ from conftest import REPO, acxrun
 
 pytestmark = pytest.mark.gpu
 
-CPROGS = ["ring", "ring_all", "ring_all_device", "ring_all_graph", "ring_graph_construction", "ring_partitioned", "large_msgs", "regcache"]
+CPROGS = ["ring", "ring_all", "ring_all_device", "ring_all_graph", "ring_graph_construction", "ring_partitioned", "large_msgs", "regcache", "ordering", "stress"]
 
 
 @pytest.mark.parametrize("prog", CPROGS)
