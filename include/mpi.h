@@ -185,6 +185,8 @@ int  ACX_Mpi_exchange(const void *mine, void *all, size_t bytes_per_rank);
 /* Raw pointer + size of a per-job shared scratch area libacx may carve up
  * (channel directories, registration tables). Zero-initialised at job start. */
 void *ACX_Mpi_shared_scratch(size_t *bytes);
+/* Called once at the start of MPI_Abort (diagnostics of layered libraries). */
+void ACX_Mpi_set_abort_hook(void (*fn)(void));
 
 #ifdef __cplusplus
 }

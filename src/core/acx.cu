@@ -578,6 +578,9 @@ extern "C" int MPIX_Init(void) {
     g_acx->device = true;
     g_acx->initialized = true;
     reg_init();
+#ifdef ACX_MINI_MPI
+    ACX_Mpi_set_abort_hook(report_watchdog);
+#endif
     MPI_Barrier(MPI_COMM_WORLD);
     ACX_LOG(1, "device transport up: dev %d (%s, %d SMs), %d ranks, ctrl %.1f MiB, heap %.0f MiB, eager<=%u, depth %d, chans %d", g_acx->dev, prop.name,
             g_acx->sm_count, g_acx->size, g_acx->geom.bytes / 1048576.0, g_acx->heap_bytes / 1048576.0, g_acx->geom.eager_max, g_acx->geom.depth, g_acx->geom.nchan);

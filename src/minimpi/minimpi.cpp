@@ -759,7 +759,11 @@ int MPI_Initialized(int *flag) { *flag = g.initialized; return MPI_SUCCESS; }
 int MPI_Finalized(int *flag) { *flag = g.finalized; return MPI_SUCCESS; }
 int MPI_Query_thread(int *provided) { *provided = g.thread_level; return MPI_SUCCESS; }
 
+static void (*g_abort_hook)(void) = nullptr;
+void ACX_Mpi_set_abort_hook(void (*fn)(void)) { g_abort_hook = fn; }
+
 int MPI_Abort(MPI_Comm, int code) {
+    if (g_abort_hook) { void (*h)(void) = g_abort_hook; g_abort_hook = nullptr; h(); }   // e.g. libacx's watchdog diagnostics
     fprintf(stderr, "[acx-mpi] MPI_Abort(%d) on rank %d\n", code, g.rank);
     if (g.seg.hdr) {
         g.seg.hdr->abort_code.store(code ? code : 1);

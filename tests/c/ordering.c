@@ -10,6 +10,8 @@ int main(int argc, char **argv) {
     int *s0, *s1, *s2, *r0, *r1, *r2;
     T_OK(MPIX_Alloc_mem(64, MPI_INFO_NULL, &s0)); T_OK(MPIX_Alloc_mem(big * 4, MPI_INFO_NULL, &s1)); T_OK(MPIX_Alloc_mem(64, MPI_INFO_NULL, &s2));
     T_OK(MPIX_Alloc_mem(big * 4, MPI_INFO_NULL, &r0)); T_OK(MPIX_Alloc_mem(big * 4, MPI_INFO_NULL, &r1)); T_OK(MPIX_Alloc_mem(big * 4, MPI_INFO_NULL, &r2));
+    int *t_s, *t_r;   /* the second stream's buffers: separate allocations (stream a memsets all of r0) */
+    T_OK(MPIX_Alloc_mem(64, MPI_INFO_NULL, &t_s)); T_OK(MPIX_Alloc_mem(64, MPI_INFO_NULL, &t_r));
     int *h = (int *)malloc(big * 4);
     cudaStream_t a, b;
     T_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
@@ -34,7 +36,6 @@ int main(int argc, char **argv) {
         T_OK(MPIX_Waitall_enqueue(3, sq, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &a));
         /* a second stream talks on another tag at the same time */
         MPIX_Request q2[2];
-        int *t_s = s0 + 8, *t_r = r0 + big - 8;   /* spare words */
         int v9 = 900 + round + t_rank;
         T_CUDA(cudaMemcpyAsync(t_s, &v9, 4, cudaMemcpyHostToDevice, b));
         T_OK(MPIX_Isend_enqueue(t_s, 1, MPI_INT, T_RIGHT, 10, MPI_COMM_WORLD, &q2[0], MPIX_QUEUE_CUDA_STREAM, &b));
@@ -55,6 +56,7 @@ int main(int argc, char **argv) {
         T_CHECK(g9 == 900 + round + T_LEFT, "second stream got %d", g9);
     }
     free(h);
+    MPIX_Free_mem(t_s); MPIX_Free_mem(t_r);
     MPIX_Free_mem(s0); MPIX_Free_mem(s1); MPIX_Free_mem(s2); MPIX_Free_mem(r0); MPIX_Free_mem(r1); MPIX_Free_mem(r2);
     cudaStreamDestroy(a); cudaStreamDestroy(b);
     return t_finish("ordering");
