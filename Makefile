@@ -57,3 +57,11 @@ $(B)/tests/%: tests/c/%.cu $(LIB)
 
 clean:
 	rm -rf $(B) lib bin
+
+# ThreadSanitizer build of the mini-MPI + its threaded test (host-side race detection; the reference has none)
+tsan:
+	@mkdir -p $(B)
+	$(CXX) -O1 -g -fsanitize=thread -std=c++17 -Iinclude -c src/minimpi/minimpi.cpp -o $(B)/minimpi_tsan.o
+	gcc -O1 -g -fsanitize=thread -Iinclude -c tests/c/minimpi_threads.c -o $(B)/mt_tsan.o
+	$(CXX) -fsanitize=thread $(B)/mt_tsan.o $(B)/minimpi_tsan.o -o $(B)/tests/minimpi_threads_tsan -ldl -lpthread -lrt
+	bin/acxrun -np 2 --timeout 100 $(B)/tests/minimpi_threads_tsan

@@ -112,6 +112,60 @@ static int run_ring(size_t bytes, int steps, int warmup, bool heap, bool e2e, bo
 }
 
 // ------------------------------------------------------------------------------------------
+// Same ping-pong, but `unroll` iterations are captured once into a CUDA graph and the graph is relaunched: the host's
+// per-call launch cost (the limiter of the plain on-stream loop) is paid once, what remains is the device-side path.
+static int run_pingpong_graph(size_t min_b, size_t max_b, bool heap, int launches) {
+    if (g_size < 2) { if (g_rank == 0) printf("{\"bench\": \"pingpong_graph\", \"skipped\": \"needs >= 2 ranks\"}\n"); return 0; }
+    const int unroll = 16;
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    char *sbuf = (char *)comm_alloc(max_b, heap), *rbuf = (char *)comm_alloc(max_b, heap);
+    CK(cudaMemset(sbuf, 1, max_b)); CK(cudaMemset(rbuf, 0, max_b));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    if (g_rank == 0) printf("{\"bench\": \"pingpong_graph\", \"impl\": \"%s\", \"heap\": %d, \"unroll\": %d, \"rows\": [", kImpl, (int)heap, unroll);
+    bool first = true;
+    for (size_t b = min_b; b <= max_b; b *= 4) {
+        cudaGraph_t g; cudaGraphExec_t ge;
+        if (g_rank < 2) {
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal));
+            for (int i = 0; i < unroll; i++) {
+                MPIX_Request q;
+                if (g_rank == 0) {
+                    OK(MPIX_Isend_enqueue(sbuf, (int)b, MPI_BYTE, 1, 1, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
+                    OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
+                    OK(MPIX_Irecv_enqueue(rbuf, (int)b, MPI_BYTE, 1, 2, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
+                    OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
+                } else {
+                    OK(MPIX_Irecv_enqueue(rbuf, (int)b, MPI_BYTE, 0, 1, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
+                    OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
+                    OK(MPIX_Isend_enqueue(sbuf, (int)b, MPI_BYTE, 0, 2, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
+                    OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
+                }
+            }
+            CK(cudaStreamEndCapture(st, &g));
+            CK(cudaGraphInstantiate(&ge, g, 0));
+        }
+        float ms = 0;
+        for (int phase = 0; phase < 2; phase++) {
+            int n = phase == 0 ? 2 : launches;
+            MPI_Barrier(MPI_COMM_WORLD);
+            if (phase == 1) CK(cudaEventRecord(e0, st));
+            if (g_rank < 2) for (int i = 0; i < n; i++) CK(cudaGraphLaunch(ge, st));
+            if (phase == 1) CK(cudaEventRecord(e1, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double rtt_us = max_over_ranks(g_rank < 2 ? ms : 0) * 1e3 / (launches * unroll);
+        if (g_rank == 0) { printf("%s{\"bytes\": %zu, \"oneway_us\": %.3f, \"gbs\": %.3f}", first ? "" : ", ", b, rtt_us / 2, b / (rtt_us / 2) / 1e3); first = false; fflush(stdout); }
+        if (g_rank < 2) { CK(cudaGraphExecDestroy(ge)); CK(cudaGraphDestroy(g)); }
+    }
+    if (g_rank == 0) printf("]}\n");
+    comm_free(sbuf, heap); comm_free(rbuf, heap);
+    cudaStreamDestroy(st);
+    return 0;
+}
+
 static int run_pingpong(size_t min_b, size_t max_b, bool heap, int max_iters) {
     if (g_size < 2) { if (g_rank == 0) printf("{\"bench\": \"pingpong\", \"skipped\": \"needs >= 2 ranks\"}\n"); return 0; }
     cudaStream_t st;
@@ -236,6 +290,7 @@ int main(int argc, char **argv) {
     }
     if (mode == "ring") rc = run_ring(bytes, steps, warmup, heap, e2e, verify);
     else if (mode == "pingpong") rc = run_pingpong(minb, maxb, heap, iters);
+    else if (mode == "pingpong_graph") rc = run_pingpong_graph(minb, maxb, heap, iters > 40 ? 20 : iters);
     else if (mode == "allpairs") rc = run_allpairs(bytes, steps, warmup, heap);
     else { fprintf(stderr, "unknown mode %s\n", mode.c_str()); rc = 2; }
     fflush(stdout);

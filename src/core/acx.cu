@@ -43,6 +43,8 @@ static std::mutex g_deferred_mu;
 
 // NVTX ranges around the API calls (ACX_NVTX=1); header-only NVTX, a no-op without a tool attached.
 static int g_mover_tma = 0, g_mover_256 = 0;
+static int g_apush = 1;                   // deterministic large-message mode: the sender always pushes, gated on its per-channel stream (ACX_SENDER_PUSH)
+static std::map<std::pair<int, int>, cudaStream_t> g_chan_streams;   // (peer, channel) -> stream for sender-push movers
 static int g_side_on = 1;                 // run large movers on per-peer side streams so transfers to different peers overlap (ACX_SIDE_STREAMS)
 static std::vector<cudaStream_t> g_side;  // side streams, indexed by peer % size
 static int g_fuse_rndv = 1, g_fuse_min_ctas = 8, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
@@ -87,6 +89,7 @@ static void report_watchdog() {
             case 0x5e07: what = "partitioned wait(recv): a partition never arrived"; break;
             case 0x5e08: what = "partitioned wait(recv): a device poller never finished its copy-out"; break;
             case 0x5e09: what = "fused rendezvous: CTA 0 never published the match decision"; break;
+            case 0x5e0a: what = "sender-push gate: the matching receive was never posted"; break;
         }
         ACX_ERR("WATCHDOG (code 0x%llx, a=0x%llx b=0x%llx): %s", (unsigned long long)g_diag[0], (unsigned long long)g_diag[1],
                 (unsigned long long)g_diag[2], what);
@@ -473,10 +476,12 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_TRACE", nullptr, 0, &v); g_acx->trace = v != 0;
     acx_env_int("ACX_WATCHDOG_MS", nullptr, 0, &v); g_acx->watchdog_ms = v;
     acx_env_int("ACX_NVTX", nullptr, 0, &v); g_nvtx = v != 0;
+    if (getenv("MPIACX_DISABLE_MEMOPS")) ACX_LOG(1, "MPIACX_DISABLE_MEMOPS is accepted for compatibility; this library never uses stream memOps (kernels only)");
     { const char *m = getenv("ACX_MOVER"); g_mover_tma = m && !strcmp(m, "tma"); g_mover_256 = m && !strcmp(m, "ldst256"); }
     acx_env_int("ACX_PDL", nullptr, 1, &v); g_pdl = v != 0;
     acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
     acx_env_int("ACX_SIDE_STREAMS", nullptr, 1, &v); g_side_on = v != 0;
+    acx_env_int("ACX_SENDER_PUSH", nullptr, 1, &v); g_apush = v != 0;
     acx_env_int("ACX_FUSE_MAX_CTAS", nullptr, 32, &v); g_fuse_max_ctas = (int)v;
     acx_env_int("ACX_FUSE_MIN_CTAS", nullptr, 8, &v); g_fuse_min_ctas = (int)v;
     acx_env_int("ACX_FAULT_DROP_SEND", nullptr, 0, &v); g_fault_drop_send = v;
@@ -625,6 +630,8 @@ extern "C" int MPIX_Finalize(void) {
         cudaStreamDestroy(g_acx->istream);
         for (auto ss : g_side) if (ss) cudaStreamDestroy(ss);
         g_side.clear();
+        for (auto &kv : g_chan_streams) cudaStreamDestroy(kv.second);
+        g_chan_streams.clear();
         for (auto e : g_event_pool) cudaEventDestroy(e);
         g_event_pool.clear();
         cudaFreeHost(g_acx->hstat);
@@ -898,6 +905,38 @@ static int launch_mover_maybe_side(Emitter &em, AcxRequest *r, MoverParams &mp, 
     return 0;
 }
 
+// Deterministic large-message path: gate + push mover on the sender's (peer, channel) stream. FIFO order inside one
+// channel is the matching order anyway, so a gate waiting for a late receive only ever delays messages that could not
+// complete before it; every GPU moves exactly its own sends (no arrival-order lottery about who does the work).
+static int launch_sender_push(Emitter &em, AcxRequest *r, SendParams &sp, MoverParams &mp, size_t bytes) {
+    cudaStream_t cs;
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        auto key = std::make_pair(r->peer, r->chan);
+        auto it = g_chan_streams.find(key);
+        if (it == g_chan_streams.end()) {
+            cudaStream_t ns = nullptr;
+            ACX_CUDA(cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking));
+            it = g_chan_streams.emplace(key, ns).first;
+        }
+        cs = it->second;
+    }
+    r->ev_trig = event_get(); r->ev_done = event_get();
+    if (!r->ev_trig || !r->ev_done) return MPI_ERR_OTHER;
+    ACX_CUDA(cudaEventRecord(r->ev_trig, em.stream));
+    ACX_CUDA(cudaStreamWaitEvent(cs, r->ev_trig, 0));
+    Emitter es = em;
+    es.stream = cs;
+    GateParams gp;
+    memset(&gp, 0, sizeof gp);
+    gp.op = sp.op; gp.sack = sp.sack; gp.peer_heap = sp.peer_heap; gp.xlat = sp.xlat; gp.bytes = bytes; gp.depth = sp.depth; gp.peer = sp.peer; gp.wd = sp.wd;
+    int rc = es.launch(push_gate, dim3(1), dim3(32), gp);
+    if (rc) return rc;
+    if ((rc = launch_mover(es, mp, bytes))) return rc;
+    ACX_CUDA(cudaEventRecord(r->ev_done, cs));
+    return 0;
+}
+
 static inline int chan_of(int tag, int ctx) { return (int)(((unsigned)tag + 7u * (unsigned)ctx) % (unsigned)g_acx->geom.nchan); }
 
 static AcxRequest *new_request(AcxReqKind kind, int peer, int tag, int ctx, size_t bytes, const void *buf) {
@@ -991,10 +1030,13 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         mp.vec256 = g_mover_256;
         const int fgrid = (!eager && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
         const bool fused = fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas;   // measured: pays off from ~512 KiB, costs ~1.5 us below
+        const bool apush = !eager && !fused && g_apush && g_side_on && qtype == MPIX_QUEUE_CUDA_STREAM;
+        sp.apush = apush ? 1 : 0;
         if (!dropped && fused) { if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail; }
         else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
         if (!eager) {
-            if (!fused && (rc = launch_mover_maybe_side(em, r, mp, bytes))) goto fail;
+            if (apush) { if (!dropped && (rc = launch_sender_push(em, r, sp, mp, bytes))) goto fail; }
+            else if (!fused && (rc = launch_mover_maybe_side(em, r, mp, bytes))) goto fail;
             g_acx->st.rndv++;
         } else {
             g_acx->st.eager++;

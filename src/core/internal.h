@@ -30,7 +30,7 @@
 #include "../../include/acx_device.cuh"
 
 // ---- shared host/device layout -----------------------------------------------------
-enum { ACX_KIND_EAGER = 1, ACX_KIND_RNDV = 2 };
+enum { ACX_KIND_EAGER = 1, ACX_KIND_RNDV = 2, ACX_KIND_RNDV_PUSH = 3 };   // RNDV: second arriver moves; RNDV_PUSH: the sender always pushes
 
 // Buffer locations travel as 64-bit "offsets": bit 63 clear = offset into the owner's symmetric heap;
 // bit 63 set = registered user allocation: bits [62:48] registration index, bits [47:0] offset inside it
@@ -56,6 +56,8 @@ struct alignas(32) acx_sack {  // per slot, lives at the SENDER, written by the 
     uint64_t efree;      // #generations the receiver has consumed (slot reusable by generation efree)
     uint64_t r_dst_off;  // mirror of the receiver's posted destination (so a late sender reads it locally)
     uint64_t r_cap;
+    uint64_t r_gen;      // #generations for which the mirror above has been published (release-stored last)
+    uint64_t pad;
 };
 
 struct alignas(64) acx_op {  // per request slot, local

@@ -121,6 +121,7 @@ struct SendParams {
     uint64_t bytes;
     uint64_t serial;
     uint32_t tag, depth, eager_max, peer;
+    uint32_t apush, pad0;   // apush: deterministic mode — this sender pushes the payload itself (gate + mover on its channel stream)
     Watchdog wd;
     TraceCtx tr;
 };
@@ -133,10 +134,12 @@ __device__ __forceinline__ void send_rndv_match(const SendParams &p, uint64_t k)
     acx_entry *ent = p.ring + e;
 
     ent->s_src_off = p.src_off; ent->s_bytes = p.bytes;
-    *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)ACX_KIND_RNDV << 32);
+    *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)(p.apush ? ACX_KIND_RNDV_PUSH : ACX_KIND_RNDV) << 32);
     uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull << 32);
     p.op->ticket = k; p.op->eager = 0; p.op->cta_count = 0;
-    if ((uint32_t)old == (uint32_t)(g + 1)) {  // receive already posted: I move the data (push)
+    if (p.apush) {
+        p.op->mover = 0;   // decided by push_gate on the channel stream once the receive is posted
+    } else if ((uint32_t)old == (uint32_t)(g + 1)) {  // receive already posted: I move the data (push)
         // the receiver mirrored its destination into MY sack before it bumped the state word
         uint64_t cap = ld_relaxed_sys(&p.sack[e].r_cap), off = ld_relaxed_sys(&p.sack[e].r_dst_off);
         p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, off);
@@ -209,6 +212,7 @@ __device__ __forceinline__ void recv_match(const RecvParams &p) {   // one threa
     if (p.sack) {  // mirror the destination into the sender's memory: a late sender then needs no remote load
         st_relaxed_sys(&p.sack[e].r_dst_off, p.dst_off);
         st_relaxed_sys(&p.sack[e].r_cap, p.cap);
+        st_release_sys(&p.sack[e].r_gen, g + 1);   // a pushing sender's gate keys on this
     }
     uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull);   // release orders the mirror stores before it
     p.op->ticket = k; p.op->cta_count = 0; p.op->mover = 0; p.op->bounce_n = 0;
@@ -243,6 +247,31 @@ struct MoverParams {
     uint32_t depth, push, peer, vec256;
     TraceCtx tr;
 };
+
+// Gate of the deterministic "sender always pushes" mode: runs on the sender's per-channel stream right before the
+// mover; waits (on LOCAL memory) until the receiver has published its destination for this generation, then
+// resolves it. Keeping the big mover grid out of the wait leaves the SMs free while the receive is late.
+struct GateParams {
+    acx_op *op;
+    acx_sack *sack;          // local
+    char *peer_heap;
+    const uint64_t *xlat;
+    uint64_t bytes;
+    uint32_t depth, peer;
+    Watchdog wd;
+};
+__global__ void push_gate(GateParams p) {
+    pdl_prologue();
+    if (threadIdx.x != 0) return;
+    const uint64_t k = p.op->ticket;
+    const uint32_t e = (uint32_t)(k % p.depth);
+    const uint64_t g = k / p.depth;
+    spin_geq(&p.sack[e].r_gen, g + 1, p.wd, 0x5e0a);
+    const uint64_t cap = ld_relaxed_sys(&p.sack[e].r_cap), off = ld_relaxed_sys(&p.sack[e].r_dst_off);
+    p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, off);
+    p.op->n = p.bytes < cap ? p.bytes : cap;
+    p.op->mover = 1;
+}
 
 __device__ __forceinline__ void mover_body(const MoverParams &p) {
     acx_op *op = p.op;

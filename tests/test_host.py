@@ -18,6 +18,12 @@ def test_minimpi_smoke(built, np_):
     assert "PASS" in r.stdout
 
 
+@pytest.mark.parametrize("np_", [1, 2, 3])
+def test_minimpi_thread_multiple(built, np_):
+    r = acxrun(built, np_, built / "build/tests/minimpi_threads")
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("prog", ["ring", "ring_all"])
 @pytest.mark.parametrize("np_", [1, 2, 3])
 def test_ring_host_transport(built, prog, np_):
