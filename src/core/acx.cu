@@ -43,7 +43,7 @@ static std::mutex g_deferred_mu;
 
 // NVTX ranges around the API calls (ACX_NVTX=1); header-only NVTX, a no-op without a tool attached.
 static int g_mover_tma = 0, g_mover_256 = 0;
-static int g_apush = 1;                   // deterministic large-message mode: the sender always pushes, gated on its per-channel stream (ACX_SENDER_PUSH)
+static int g_apush = 0;                   // deterministic large-message mode: the sender always pushes, gated on its per-channel stream (ACX_SENDER_PUSH)
 static std::map<std::pair<int, int>, cudaStream_t> g_chan_streams;   // (peer, channel) -> stream for sender-push movers
 static int g_side_on = 1;                 // run large movers on per-peer side streams so transfers to different peers overlap (ACX_SIDE_STREAMS)
 static std::vector<cudaStream_t> g_side;  // side streams, indexed by peer % size
@@ -481,7 +481,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_PDL", nullptr, 1, &v); g_pdl = v != 0;
     acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
     acx_env_int("ACX_SIDE_STREAMS", nullptr, 1, &v); g_side_on = v != 0;
-    acx_env_int("ACX_SENDER_PUSH", nullptr, 1, &v); g_apush = v != 0;
+    acx_env_int("ACX_SENDER_PUSH", nullptr, 0, &v); g_apush = v != 0;   // opt-in: a spinning gate can deadlock against device-synchronizing host calls
     acx_env_int("ACX_FUSE_MAX_CTAS", nullptr, 32, &v); g_fuse_max_ctas = (int)v;
     acx_env_int("ACX_FUSE_MIN_CTAS", nullptr, 8, &v); g_fuse_min_ctas = (int)v;
     acx_env_int("ACX_FAULT_DROP_SEND", nullptr, 0, &v); g_fault_drop_send = v;
@@ -868,7 +868,9 @@ static int mover_grid_ldst(size_t bytes);
 static int mover_grid_any(size_t bytes) { int g = mover_grid(bytes); return g ? g : mover_grid_ldst(bytes); }
 static int mover_grid_ldst(size_t bytes) {
     size_t g = (bytes + g_acx->mover_min_cta_bytes - 1) / g_acx->mover_min_cta_bytes;
-    int cap = g_acx->mover_max_ctas > 0 ? g_acx->mover_max_ctas : 4 * g_acx->sm_count;
+    // Half an SM-count of 512-thread CTAs already saturates one NVLink direction (measured 647 vs 652 GB/s at 148) and
+    // leaves room for a pull and a push mover to co-reside when one GPU ends up doing both.
+    int cap = g_acx->mover_max_ctas > 0 ? g_acx->mover_max_ctas : std::max(1, g_acx->sm_count / 2);
     if (g < 1) g = 1;
     if (g > (size_t)cap) g = cap;
     return (int)g;
