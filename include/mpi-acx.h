@@ -25,53 +25,48 @@ extern "C" {
 #define MPIX_ACX_VERSION_MAJOR 0
 #define MPIX_ACX_VERSION_MINOR 1
 
+/* Opaque handles. MPIX_Prequest is a device pointer; kernels receive it by value. */
 typedef void *MPIX_Request;
 typedef void *MPIX_Prequest;
-
 #define MPIX_REQUEST_NULL  NULL
 #define MPIX_PREQUEST_NULL NULL
 
+/* Kind of `queue_handle` in the *_enqueue calls. */
+enum {
+    MPIX_QUEUE_CUDA_STREAM,  /* cudaStream_t*  (in; the stream may be capturing)        */
+    MPIX_QUEUE_CUDA_GRAPH    /* cudaGraph_t*   (out: a new graph that contains the op)  */
+};
+
+/* ---- lifecycle (after MPI_Init_thread and cudaSetDevice; collective over MPI_COMM_WORLD) ---- */
 int MPIX_Init(void);
 int MPIX_Finalize(void);
 
-/* ENQUEUED OPERATIONS ********************************************************/
+/* ---- stream / graph triggered two-sided operations -------------------------------------------
+ * The transfer starts no earlier than the point where the call sits in the stream or graph; the
+ * buffer must stay valid until a wait on the returned request has completed. */
+int MPIX_Isend_enqueue(const void *sendbuf, int nelems, MPI_Datatype dtype, int dst_rank, int tag, MPI_Comm comm, MPIX_Request *req_out, int queue_kind, void *queue_handle);
+int MPIX_Irecv_enqueue(void *recvbuf, int nelems, MPI_Datatype dtype, int src_rank, int tag, MPI_Comm comm, MPIX_Request *req_out, int queue_kind, void *queue_handle);
 
-enum {
-    MPIX_QUEUE_CUDA_STREAM,  /* queue is cudaStream_t*  (the stream may be capturing)   */
-    MPIX_QUEUE_CUDA_GRAPH    /* queue is cudaGraph_t*   (OUT: a new graph with the op)  */
-};
+/* Work queued behind these runs only after the operation(s) completed; the handles are consumed
+ * (set to MPIX_REQUEST_NULL) at enqueue time. Not for partitioned requests. */
+int MPIX_Wait_enqueue(MPIX_Request *req, MPI_Status *status, int queue_kind, void *queue_handle);
+int MPIX_Waitall_enqueue(int nreq, MPIX_Request *reqs, MPI_Status *statuses, int queue_kind, void *queue_handle);
 
-int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datatype, int dest,
-                       int tag, MPI_Comm comm, MPIX_Request *request, int qtype, void *queue);
-
-int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, int source,
-                       int tag, MPI_Comm comm, MPIX_Request *request, int qtype, void *queue);
-
-int MPIX_Wait_enqueue(MPIX_Request *req, MPI_Status *status, int qtype, void *queue);
-int MPIX_Waitall_enqueue(int count, MPIX_Request *reqs, MPI_Status *statuses, int qtype, void *queue);
-
-/* PARTITIONED OPERATIONS *****************************************************/
-
-int MPIX_Psend_init(const void *buf, int partitions, MPI_Count count,
-                    MPI_Datatype datatype, int dest, int tag, MPI_Comm comm,
-                    MPI_Info info, MPIX_Request *request);
-
-int MPIX_Precv_init(void *buf, int partitions, MPI_Count count,
-                    MPI_Datatype datatype, int source, int tag, MPI_Comm comm,
-                    MPI_Info info, MPIX_Request *request);
-
-int MPIX_Prequest_create(MPIX_Request request, MPIX_Prequest *prequest);
-int MPIX_Prequest_free(MPIX_Prequest *request);
-
-/* HELPERS ********************************************************************/
-
-int MPIX_Start(MPIX_Request *request);
-int MPIX_Startall(int count, MPIX_Request *request);
-
+/* Host-blocking completion: basic requests that were enqueued on a stream (frees them), or one round
+ * of a partitioned request (which stays allocated, inactive, for the next MPIX_Start). */
 int MPIX_Wait(MPIX_Request *req, MPI_Status *status);
-int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses);
+int MPIX_Waitall(int nreq, MPIX_Request *reqs, MPI_Status *statuses);
 
-int MPIX_Request_free(MPIX_Request *request);
+/* ---- persistent partitioned operations (MPI-4 semantics: `nelems` is PER PARTITION) ----------- */
+int MPIX_Psend_init(const void *sendbuf, int partitions, MPI_Count nelems, MPI_Datatype dtype, int dst_rank, int tag, MPI_Comm comm, MPI_Info info, MPIX_Request *req_out);
+int MPIX_Precv_init(void *recvbuf, int partitions, MPI_Count nelems, MPI_Datatype dtype, int src_rank, int tag, MPI_Comm comm, MPI_Info info, MPIX_Request *req_out);
+int MPIX_Start(MPIX_Request *req);
+int MPIX_Startall(int nreq, MPIX_Request *reqs);
+int MPIX_Request_free(MPIX_Request *req);
+
+/* Device-side handle of a partitioned request (several may exist per request). */
+int MPIX_Prequest_create(MPIX_Request req, MPIX_Prequest *preq_out);
+int MPIX_Prequest_free(MPIX_Prequest *preq);
 
 /* EXTENSIONS (not in the reference) ******************************************/
 
