@@ -42,7 +42,7 @@ static std::vector<int> g_deferred_slots;                    // freed by graph u
 static std::mutex g_deferred_mu;
 
 // NVTX ranges around the API calls (ACX_NVTX=1); header-only NVTX, a no-op without a tool attached.
-static int g_mover_tma = 0, g_mover_256 = 0;
+static int g_mover_tma = 0, g_mover_256 = 0, g_mover_block = 0;   // g_mover_block: interleaved block size in bytes (ACX_MOVER_BLOCK; 0 = one chunk per CTA)
 static int g_apush = 0;                   // deterministic large-message mode: the sender always pushes, gated on its per-channel stream (ACX_SENDER_PUSH)
 static std::map<std::pair<int, int>, cudaStream_t> g_chan_streams;   // (peer, channel) -> stream for sender-push movers
 static int g_side_on = 1;                 // run large movers on per-peer side streams so transfers to different peers overlap (ACX_SIDE_STREAMS)
@@ -479,6 +479,7 @@ extern "C" int MPIX_Init(void) {
     if (getenv("MPIACX_DISABLE_MEMOPS")) ACX_LOG(1, "MPIACX_DISABLE_MEMOPS is accepted for compatibility; this library never uses stream memOps (kernels only)");
     { const char *m = getenv("ACX_MOVER"); g_mover_tma = m && !strcmp(m, "tma"); g_mover_256 = m && !strcmp(m, "ldst256"); }
     acx_env_int("ACX_PDL", nullptr, 1, &v); g_pdl = v != 0;
+    acx_env_int("ACX_MOVER_BLOCK", nullptr, 0, &v); g_mover_block = (int)std::max(0L, v) & ~511;
     acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
     acx_env_int("ACX_SIDE_STREAMS", nullptr, 1, &v); g_side_on = v != 0;
     acx_env_int("ACX_SENDER_PUSH", nullptr, 0, &v); g_apush = v != 0;   // opt-in: a spinning gate can deadlock against device-synchronizing host calls
@@ -886,7 +887,16 @@ static int launch_mover(Emitter &em, MoverParams &mp, size_t bytes) {
         return em.launch(mover_tma, dim3(mover_grid(bytes)), dim3(kTmaThreads), mp, kTmaSmem);
     }
     mp.vec256 = g_mover_256;
-    return em.launch(mover, dim3(mover_grid_ldst(bytes)), dim3(kMoverThreads), mp);
+    mp.block_bytes = (uint32_t)g_mover_block;
+    int grid = mover_grid_ldst(bytes);
+    if ((int)mp.peer == g_acx->rank && g_acx->mover_max_ctas <= 0) {
+        // Self-transfer (local HBM copy, no link to share): a full-width grid sweeping interleaved 128-KiB blocks
+        // measured 0.129 ms per 256 MiB vs 0.144 ms for the NVLink-sized grid (profiles/raw/self_copy_layouts.txt).
+        size_t g = (bytes + g_acx->mover_min_cta_bytes - 1) / g_acx->mover_min_cta_bytes;
+        grid = (int)std::max<size_t>(1, std::min<size_t>(g, (size_t)4 * g_acx->sm_count));
+        if (!mp.block_bytes) mp.block_bytes = 128u << 10;
+    }
+    return em.launch(mover, dim3(grid), dim3(kMoverThreads), mp);
 }
 
 // Unfused movers of stream-mode operations run on a per-peer side stream, forked after the trigger kernel: the
@@ -1029,7 +1039,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         MoverParams mp;
         memset(&mp, 0, sizeof mp);
         mp.op = sp.op; mp.local = (char *)src_local; mp.ring = sp.ring; mp.sack = sp.sack; mp.depth = G.depth; mp.push = 1; mp.peer = dest; mp.tr = sp.tr;
-        mp.vec256 = g_mover_256;
+        mp.vec256 = g_mover_256; mp.block_bytes = (uint32_t)g_mover_block;
         const int fgrid = (!eager && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
         const bool fused = fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas;   // measured: pays off from ~512 KiB, costs ~1.5 us below
         const bool apush = !eager && !fused && g_apush && g_side_on && qtype == MPIX_QUEUE_CUDA_STREAM;
@@ -1121,7 +1131,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         MoverParams mp;
         memset(&mp, 0, sizeof mp);
         mp.op = rp.op; mp.local = dst_local; mp.ring = rp.ring; mp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;
-        mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr; mp.vec256 = g_mover_256;
+        mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr; mp.vec256 = g_mover_256; mp.block_bytes = (uint32_t)g_mover_block;
         const int fgrid = (rndv_capable && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
         if (fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas) {
             if ((rc = em.launch2(recv_rndv_fused, dim3(fgrid), dim3(kMoverThreads), rp, mp))) goto fail;

@@ -245,6 +245,7 @@ struct MoverParams {
     acx_entry *ring;        // push: peer-mapped ring; pull: local ring
     acx_sack *sack;         // push: local sack; pull: peer-mapped sack at the sender
     uint32_t depth, push, peer, vec256;
+    uint32_t block_bytes, pad1;   // 0: one contiguous chunk per CTA; else CTAs sweep interleaved blocks of this size (DRAM-page friendly)
     TraceCtx tr;
 };
 
@@ -279,10 +280,22 @@ __device__ __forceinline__ void mover_body(const MoverParams &p) {
     const uint64_t n = op->n;
     char *peer = (char *)op->peer_ptr;
     if (blockIdx.x == 0 && threadIdx.x == 0) trace(p.tr, ACX_EV_MOVE_BEGIN, p.peer, op->ticket, n);
+    if (p.block_bytes) {
+        // Interleaved blocks: at any instant the resident CTAs cover one contiguous window of the buffers, so the
+        // DRAM pages they touch (source and destination) stay few — the access pattern of a plain elementwise copy.
+        const uint64_t bs = p.block_bytes;
+        for (uint64_t lo = (uint64_t)blockIdx.x * bs; lo < n; lo += (uint64_t)gridDim.x * bs) {
+            const uint64_t len = n - lo < bs ? n - lo : bs;
+            char *d = p.push ? peer + lo : p.local + lo;
+            const char *s = p.push ? p.local + lo : peer + lo;
+            if (p.vec256) copy_bytes_256(d, s, len, threadIdx.x, blockDim.x);
+            else copy_bytes(d, s, len, threadIdx.x, blockDim.x);
+        }
+    }
     // Contiguous chunk per CTA: keeps each CTA's NVLink stream sequential.
     const uint64_t per = ((n + gridDim.x - 1) / gridDim.x + 127) & ~127ull;
     const uint64_t lo = per * blockIdx.x;
-    if (lo < n) {
+    if (!p.block_bytes && lo < n) {
         const uint64_t len = n - lo < per ? n - lo : per;
         char *d = p.push ? peer + lo : p.local + lo;
         const char *s = p.push ? p.local + lo : peer + lo;
