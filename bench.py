@@ -34,6 +34,9 @@ def parse():
     ap.add_argument("--impl", default="acx", choices=["acx", "reference"])
     ap.add_argument("--bytes", type=int, default=256 << 20)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--order", default="auto", choices=["auto", "prepost", "simple"],
+                    help="prepost: the receive of step i+1 is posted before step i is waited on (double-buffered); simple: irecv, isend, waitall per step; "
+                         "auto: prepost from 3 GPUs up (where the arrival-order lottery of the simple order costs up to 2x, BASELINE.md 4.6), simple below")
     return ap.parse_args()
 
 
@@ -94,29 +97,55 @@ def run_reference(a) -> int:
 def run_acx(a) -> int:
     import torch
     rank, world, local = env_rank()
-    os.environ.setdefault("ACX_HEAP_BYTES", str(max(2 * a.bytes + (192 << 20), 512 << 20)))
+    os.environ.setdefault("ACX_HEAP_BYTES", str(max(3 * a.bytes + (192 << 20), 512 << 20)))
     os.environ.setdefault("ACX_WATCHDOG_MS", "60000")
     import mpi_acx_b200 as acx
     from mpi_acx_b200.utils.clocks import ClockSampler
-    if not torch.cuda.is_available():
+    # ACX_BENCH_DRYRUN_CPU=1: exercise this script's control flow on the host transport (no GPU, gloo, wall-clock
+    # "events") — used by the CPU test-suite; its numbers mean nothing.
+    dry = bool(os.environ.get("ACX_BENCH_DRYRUN_CPU"))
+    dev = "cpu" if dry else "cuda"
+    if dry:
+        import time as _time
+
+        class _Ev:
+            def __init__(self, enable_timing=True): self.t = 0.0
+            def record(self, stream=None): self.t = _time.perf_counter()
+            def elapsed_time(self, other): return (other.t - self.t) * 1e3
+        torch.cuda.Event = _Ev
+        torch.cuda.synchronize = lambda *a_, **k_: None
+        torch.cuda.current_stream = lambda *a_, **k_: None
+        os.environ["ACX_FORCE_HOST"] = "1"
+        a.no_extras = True
+    elif not torch.cuda.is_available():
         print(json.dumps({"metric": "ring_sendrecv_bandwidth", "value": None, "error": "no CUDA device"}))
         return 1
-    torch.cuda.set_device(local)
+    else:
+        torch.cuda.set_device(local)
     use_dist = world > 1
     if use_dist:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if dry:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     acx.init(local)
     assert acx.size() == world and acx.rank() == rank, (acx.size(), world)
     right, left = (rank + 1) % world, (rank - 1) % world
     n = a.bytes
+    if a.order == "auto":
+        a.order = "prepost" if world >= 3 else "simple"
     sbuf = acx.empty(n, torch.uint8)
-    rbuf = acx.empty(n, torch.uint8)
-    sbuf.copy_(torch.arange(n, device="cuda", dtype=torch.int32).to(torch.uint8) + rank)
-    rbuf.zero_()
-    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    rbufs = [acx.empty(n, torch.uint8), acx.empty(n, torch.uint8)]
+    rbuf = rbufs[0]
+    sbuf.copy_(torch.arange(n, device=dev, dtype=torch.int32).to(torch.uint8) + rank)
+    for b in rbufs:
+        b.zero_()
+    h_in = torch.empty(n, dtype=torch.uint8)
+    h_out = torch.empty(4096, dtype=torch.uint8)
+    if not dry:
+        h_in, h_out = h_in.pin_memory(), h_out.pin_memory()
     h_in.fill_(rank + 1)
-    h_out = torch.empty(4096, dtype=torch.uint8).pin_memory()
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -128,7 +157,7 @@ def run_acx(a) -> int:
     def max_over_ranks(x: float) -> float:
         if not use_dist:
             return x
-        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -141,15 +170,28 @@ def run_acx(a) -> int:
         if e2e:
             h_out.copy_(rbuf[:4096], non_blocking=True)
 
+    from mpi_acx_b200.parallel import ring_exchange_prepost
+
+    def run_steps(e2e: bool, k: int):
+        """k ring steps; returns the buffer that holds the last received message."""
+        if a.order == "simple":
+            for _ in range(k):
+                step(e2e)
+            return rbuf
+        before = (lambda i: sbuf.copy_(h_in, non_blocking=True)) if e2e else None
+        after = (lambda i, buf: h_out.copy_(buf[:4096], non_blocking=True)) if e2e else None
+        ring_exchange_prepost(sbuf, rbufs, k, 0, None, before, after)
+        return rbufs[(k - 1) % 2]
+
+    last_buf = {"t": rbuf}
+
     def timed(e2e: bool, steps: int, warmup: int):
-        for _ in range(warmup):
-            step(e2e)
+        run_steps(e2e, warmup)
         barrier()
         k0 = acx.stats()["kernels_launched"]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
-            step(e2e)
+        last_buf["t"] = run_steps(e2e, steps)
         e1.record(stream)
         torch.cuda.synchronize()
         barrier()
@@ -158,7 +200,7 @@ def run_acx(a) -> int:
 
     # One nvidia-smi sampler (rank 0's GPU), started well before the first timed region and kept running across
     # both: starting NVML clients on every rank at the instant the timed loop begins stalls kernel launches.
-    sampler = ClockSampler(local, period_ms=20) if rank == 0 else None
+    sampler = ClockSampler(local, period_ms=20) if rank == 0 and not dry else None
     if sampler:
         sampler.__enter__()
         import time
@@ -168,8 +210,9 @@ def run_acx(a) -> int:
     W = max(3, a.warmup)
     ms, launches = timed(False, a.steps, W)
     # correctness of what was timed: the received buffer must be the left neighbour's pattern
-    exp = (torch.arange(4096, device="cuda", dtype=torch.int32).to(torch.uint8) + left)
-    ok = bool(torch.equal(rbuf[:4096], exp)) and bool(torch.equal(rbuf[-4096:], (torch.arange(n - 4096, n, device="cuda", dtype=torch.int64).to(torch.uint8) + left)))
+    exp = (torch.arange(4096, device=dev, dtype=torch.int32).to(torch.uint8) + left)
+    got = last_buf["t"]
+    ok = bool(torch.equal(got[:4096], exp)) and bool(torch.equal(got[-4096:], (torch.arange(n - 4096, n, device=dev, dtype=torch.int64).to(torch.uint8) + left)))
     ms_e2e, _ = timed(True, a.steps, W)
     ok_e2e = bool((h_out == (left + 1)).all())
     clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -200,7 +243,9 @@ def run_acx(a) -> int:
             torch.cuda.synchronize()
             extras[f"ring_step_us_{nb}B"] = round(max_over_ranks(e0.elapsed_time(e1)) / iters * 1e3, 3)
             del s2, r2
-        del sbuf, rbuf
+        del sbuf, rbuf, got
+        rbufs.clear()
+        last_buf.clear()
         sbuf = rbuf = None
         # the two fused showcase kernels at this GPU count (BASELINE.json configs #3 and #4), best effort
         try:
@@ -249,14 +294,17 @@ def run_acx(a) -> int:
         "e2e": {"value": round(gbs_e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 4096, "ms_per_step": round(ms_e2e, 6)},
         "gpu_launches": int(launches),
         "config": {"model": "ring Isend/Irecv_enqueue + Waitall_enqueue", "msg_bytes": n, "global_batch": n * world, "seq_len": None,
-                   "parallelism": f"p2p-ring{world}", "l2": "working set 2x msg_bytes > L2, no flush", "buffers": "symmetric heap (zero-copy NVLink push/pull)",
+                   "parallelism": f"p2p-ring{world}", "l2": "working set >= 2x msg_bytes > L2, no flush", "buffers": "symmetric heap (zero-copy NVLink push/pull)",
+                   "order": "receive of step i+1 posted before step i is waited on (two receive buffers)" if a.order == "prepost" else "irecv, isend, waitall per step",
                    "nvlink_fraction_of_770GBs_per_gpu": round(gbs / world / 770.0, 3) if world > 1 else None},
         "extra": extras,
     }
     if rank == 0:
         print(json.dumps(out))
         sys.stdout.flush()
-    sbuf = rbuf = None
+    sbuf = rbuf = got = None
+    rbufs.clear()
+    last_buf.clear()
     barrier()
     acx.finalize()
     if use_dist:

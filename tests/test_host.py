@@ -108,3 +108,34 @@ def test_api_surface_matches_reference_header(built):
             assert mr and len(m.group(1).split(",")) == len(mr.group(1).split(",")), n
     for c in ["MPIX_REQUEST_NULL", "MPIX_PREQUEST_NULL", "MPIX_QUEUE_CUDA_STREAM", "MPIX_QUEUE_CUDA_GRAPH"]:
         assert c in ours
+
+
+@pytest.mark.parametrize("order", ["prepost", "simple"])
+@pytest.mark.parametrize("world", [1, 3])
+def test_bench_control_flow_dry_run(built, order, world):
+    """bench.py's step logic (pre-posted double-buffered ring, verification, JSON contract) on the host transport."""
+    import json
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, ACX_BENCH_DRYRUN_CPU="1", RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(29740 + world + (0 if order == "prepost" else 5)))
+        procs.append(subprocess.Popen([sys.executable, str(REPO / "bench.py"), "--gpus", str(world), "--steps", "4", "--warmup", "3", "--bytes", "32768", "--order", order],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = [l for l in outs[0].splitlines() if l.startswith("{")][-1]
+    j = json.loads(line)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks"):
+        assert key in j, key
+    assert j["verified"] and j["n_gpus"] == world and j["steps"] == 4 and j["e2e"]["h2d_bytes_per_step"] == 32768
+
+
+def test_bench_reference_arm_reports_unavailable_without_gpu(built):
+    import json
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0
+    j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert j["impl"] == "reference" and ("unavailable" in j or "value" in j)
