@@ -58,10 +58,11 @@ __global__ void check_kernel(const unsigned *p, size_t n, unsigned seed, unsigne
 }
 
 // ------------------------------------------------------------------------------------------
-static int run_ring(size_t bytes, int steps, int warmup, bool heap, bool e2e, bool verify) {
+static int run_ring(size_t bytes, int steps, int warmup, bool heap, bool e2e, bool verify, bool prepost) {
     cudaStream_t st;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     char *sbuf = (char *)comm_alloc(bytes, heap), *rbuf = (char *)comm_alloc(bytes, heap);
+    char *rbuf2 = prepost ? (char *)comm_alloc(bytes, heap) : nullptr;   // --prepost: receives are posted one step ahead into alternating buffers
     char *h_in = nullptr, *h_out = nullptr;
     const size_t d2h = 4096 < bytes ? 4096 : bytes;
     if (e2e) { CK(cudaMallocHost((void **)&h_in, bytes)); CK(cudaMallocHost((void **)&h_out, d2h)); memset(h_in, g_rank + 1, bytes); }
@@ -79,20 +80,35 @@ static int run_ring(size_t bytes, int steps, int warmup, bool heap, bool e2e, bo
         OK(MPIX_Waitall_enqueue(2, rq, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
         if (e2e) CK(cudaMemcpyAsync(h_out, rbuf, d2h, cudaMemcpyDeviceToHost, st));
     };
-    for (int i = 0; i < warmup; i++) step(0);
+    // Pre-posted variant: K steps = first receive, then per step {send i, receive i+1, wait(recv i, send i)}.
+    auto run_prepost = [&](int k) {
+        MPIX_Request pend, nxt = MPIX_REQUEST_NULL;
+        OK(MPIX_Irecv_enqueue(rbuf, (int)bytes, MPI_BYTE, left, 0, MPI_COMM_WORLD, &pend, MPIX_QUEUE_CUDA_STREAM, &st));
+        for (int i = 0; i < k; i++) {
+            MPIX_Request rq[2];
+            if (e2e) CK(cudaMemcpyAsync(sbuf, h_in, bytes, cudaMemcpyHostToDevice, st));
+            OK(MPIX_Isend_enqueue(sbuf, (int)bytes, MPI_BYTE, right, 0, MPI_COMM_WORLD, &rq[1], MPIX_QUEUE_CUDA_STREAM, &st));
+            if (i + 1 < k) OK(MPIX_Irecv_enqueue((i + 1) & 1 ? rbuf2 : rbuf, (int)bytes, MPI_BYTE, left, 0, MPI_COMM_WORLD, &nxt, MPIX_QUEUE_CUDA_STREAM, &st));
+            rq[0] = pend;
+            OK(MPIX_Waitall_enqueue(2, rq, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
+            if (e2e) CK(cudaMemcpyAsync(h_out, i & 1 ? rbuf2 : rbuf, d2h, cudaMemcpyDeviceToHost, st));
+            pend = nxt;
+        }
+    };
+    if (prepost) run_prepost(warmup); else for (int i = 0; i < warmup; i++) step(0);
     CK(cudaStreamSynchronize(st));
     unsigned long long bad = 0;
     if (verify && !e2e) {
         unsigned long long *dbad;
         CK(cudaMalloc(&dbad, 8)); CK(cudaMemset(dbad, 0, 8));
-        check_kernel<<<592, 256, 0, st>>>((const unsigned *)rbuf, bytes / 4, 77u * left, dbad);
+        check_kernel<<<592, 256, 0, st>>>((const unsigned *)((prepost && ((warmup - 1) & 1)) ? rbuf2 : rbuf), bytes / 4, 77u * left, dbad);
         CK(cudaMemcpyAsync(&bad, dbad, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         cudaFree(dbad);
     }
     MPI_Barrier(MPI_COMM_WORLD);
     CK(cudaEventRecord(e0, st));
-    for (int i = 0; i < steps; i++) step(0);
+    if (prepost) run_prepost(steps); else for (int i = 0; i < steps; i++) step(0);
     CK(cudaEventRecord(e1, st));
     CK(cudaStreamSynchronize(st));
     MPI_Barrier(MPI_COMM_WORLD);
@@ -100,10 +116,11 @@ static int run_ring(size_t bytes, int steps, int warmup, bool heap, bool e2e, bo
     CK(cudaEventElapsedTime(&ms, e0, e1));
     double tmax = max_over_ranks(ms) / steps;
     double badmax = max_over_ranks((double)bad);
+    if (rbuf2) comm_free(rbuf2, heap);
     if (g_rank == 0)
-        printf("{\"bench\": \"ring%s\", \"impl\": \"%s\", \"n_gpus\": %d, \"bytes\": %zu, \"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.6f, "
+        printf("{\"bench\": \"ring%s%s\", \"impl\": \"%s\", \"n_gpus\": %d, \"bytes\": %zu, \"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.6f, "
                "\"gbs_per_gpu\": %.3f, \"gbs_total\": %.3f, \"heap\": %d, \"bad_words\": %.0f, \"h2d_bytes_per_step\": %zu, \"d2h_bytes_per_step\": %zu}\n",
-               e2e ? "_e2e" : "", kImpl, g_size, bytes, steps, warmup, tmax, bytes / tmax / 1e6, g_size * (bytes / tmax / 1e6), (int)heap, badmax,
+               e2e ? "_e2e" : "", prepost ? "_prepost" : "", kImpl, g_size, bytes, steps, warmup, tmax, bytes / tmax / 1e6, g_size * (bytes / tmax / 1e6), (int)heap, badmax,
                e2e ? bytes : (size_t)0, e2e ? d2h : (size_t)0);
     comm_free(sbuf, heap); comm_free(rbuf, heap);
     if (e2e) { cudaFreeHost(h_in); cudaFreeHost(h_out); }
@@ -274,7 +291,7 @@ int main(int argc, char **argv) {
     std::string mode = argc > 1 ? argv[1] : "ring";
     size_t bytes = 256u << 20, minb = 8, maxb = 1u << 30;
     int steps = 20, warmup = 5, iters = 200, rc = 0;
-    bool heap = true, e2e = false, verify = true;
+    bool heap = true, e2e = false, verify = true, prepost = false;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         auto val = [&]() { return i + 1 < argc ? atoll(argv[++i]) : 0LL; };
@@ -287,8 +304,9 @@ int main(int argc, char **argv) {
         else if (a == "--no-heap") heap = false;
         else if (a == "--e2e") e2e = true;
         else if (a == "--no-verify") verify = false;
+        else if (a == "--prepost") prepost = true;
     }
-    if (mode == "ring") rc = run_ring(bytes, steps, warmup, heap, e2e, verify);
+    if (mode == "ring") rc = run_ring(bytes, steps, warmup, heap, e2e, verify, prepost);
     else if (mode == "pingpong") rc = run_pingpong(minb, maxb, heap, iters);
     else if (mode == "pingpong_graph") rc = run_pingpong_graph(minb, maxb, heap, iters > 40 ? 20 : iters);
     else if (mode == "allpairs") rc = run_allpairs(bytes, steps, warmup, heap);
