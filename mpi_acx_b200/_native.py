@@ -45,7 +45,10 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
         if not LIB_PATH.exists():
-            raise ImportError(f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()) first")
+            try:
+                build_native()   # nvcc is part of the image on both the CPU and the GPU box
+            except Exception as ex:  # noqa: BLE001
+                raise ImportError(f"{LIB_PATH} is missing and `make` failed ({ex}); run __graft_entry__.build() first") from ex
         _lib = ctypes.CDLL(str(LIB_PATH), mode=ctypes.RTLD_GLOBAL)
         vp, ci, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
         P = ctypes.POINTER
