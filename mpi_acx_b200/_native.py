@@ -35,7 +35,14 @@ class AcxStats(ctypes.Structure):
 def build_native(force: bool = False) -> None:
     """Build lib/libacx.so, bin/acxrun and the fused-kernel library with make (sm_100a)."""
     if force or not LIB_PATH.exists():
-        subprocess.run(["make", "-C", str(REPO), "-j8", "lib", "bin/acxrun"], check=True)
+        import fcntl
+        with open(REPO / ".build.lock", "w") as lk:   # several ranks may import at once: build exactly once
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            try:
+                if force or not LIB_PATH.exists():
+                    subprocess.run(["make", "-C", str(REPO), "-j8", "lib", "bin/acxrun"], check=True, capture_output=True)
+            finally:
+                fcntl.flock(lk, fcntl.LOCK_UN)
 
 
 _lib = None
