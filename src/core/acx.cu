@@ -458,6 +458,8 @@ static void make_geom(acx_geom &g, int n) {
     g.bytes = o;
 }
 
+// Reference: MPIX_Init, src/init.cpp:157-253 (flag table in mapped host memory + proxy thread). Here: device windows,
+// CUDA-IPC exchange, no thread.
 extern "C" int MPIX_Init(void) {
     int initialized = 0, finalized = 0, thread_level = 0;
     MPI_Initialized(&initialized);
@@ -593,6 +595,7 @@ extern "C" int MPIX_Init(void) {
     return 0;
 }
 
+// Reference: MPIX_Finalize, src/init.cpp:255-275 (join proxy, warn on leaked slots).
 extern "C" int MPIX_Finalize(void) {
     if (!g_acx || !g_acx->initialized) return 1;
     int err = 0;
@@ -976,6 +979,7 @@ static int check_common(const char *fn, int count, MPI_Datatype dt, int peer, in
 // =======================================================================================
 // MPIX_Isend_enqueue / MPIX_Irecv_enqueue
 // =======================================================================================
+// Reference: MPIX_Isend_enqueue, src/sendrecv.cu:129-228 (slot + WriteValue32(PENDING) / set<<<1,1>>>; proxy posts MPI_Isend).
 extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm, MPIX_Request *request,
                                   int qtype, void *queue) {
     AcxRange _r("MPIX_Isend_enqueue");
@@ -1068,6 +1072,7 @@ fail:
     return rc;
 }
 
+// Reference: MPIX_Irecv_enqueue, src/sendrecv.cu:231-327.
 extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPIX_Request *request, int qtype,
                                   void *queue) {
     AcxRange _r("MPIX_Irecv_enqueue");
@@ -1314,6 +1319,8 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
     return MPI_SUCCESS;
 }
 
+// Reference: MPIX_Wait_enqueue, src/sendrecv.cu:330-436 (WaitValue32(COMPLETED)+WriteValue32(CLEANUP) or wait kernels; GRAPH path waits
+// for the wrong constant, defect D2). MPIX_Waitall_enqueue: src/sendrecv.cu:439-579.
 extern "C" int MPIX_Wait_enqueue(MPIX_Request *req, MPI_Status *status, int qtype, void *queue) {
     if (!req) return MPI_ERR_ARG;
     return wait_enqueue_impl(1, req, status == MPI_STATUS_IGNORE ? MPI_STATUSES_IGNORE : status, qtype, queue);
@@ -1327,6 +1334,7 @@ extern "C" int MPIX_Waitall_enqueue(int count, MPIX_Request *reqs, MPI_Status *s
 static int pwait_host(AcxRequest *r, MPI_Status *status);
 static int pwait_emit(AcxRequest *r, cudaStream_t stream);
 
+// Reference: MPIX_Wait / MPIX_Waitall, src/sendrecv.cu:582-651 (host spin on the flag; partitioned: spin per partition + MPI_Wait).
 extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
     if (!g_acx || !g_acx->initialized || !req) return MPI_ERR_OTHER;
     if (*req == MPIX_REQUEST_NULL) return MPI_SUCCESS;
@@ -1471,6 +1479,7 @@ static int pinit_common(AcxReqKind kind, const void *buf, int partitions, MPI_Co
     return MPI_SUCCESS;
 }
 
+// Reference: MPIX_Psend_init / MPIX_Precv_init, src/partitioned.cu:36-123 (MPI_Psend_init/MPI_Precv_init + one flag slot per partition).
 extern "C" int MPIX_Psend_init(const void *buf, int partitions, MPI_Count count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm, MPI_Info,
                                MPIX_Request *request) {
     return pinit_common(ACX_REQ_PSEND, buf, partitions, count, datatype, dest, tag, comm, request);
@@ -1519,6 +1528,7 @@ static int presolve(AcxRequest *r) {
     return 0;
 }
 
+// Reference: MPIX_Prequest_create / _free, src/partitioned.cu:160-197 (device copy of {idx[], flags}).
 extern "C" int MPIX_Prequest_create(MPIX_Request request, MPIX_Prequest *prequest) {
     AcxRequest *r = as_request(request);
     if (!r || (r->kind != ACX_REQ_PSEND && r->kind != ACX_REQ_PRECV) || !prequest) return MPI_ERR_REQUEST;
@@ -1550,6 +1560,7 @@ static int pstart_emit(AcxRequest *r, cudaStream_t stream) {
     return 0;
 }
 
+// Reference: MPIX_Start / MPIX_Startall, src/partitioned.cu:125-157 (MPI_Start; recv flags -> ISSUED so the proxy polls MPI_Parrived).
 extern "C" int MPIX_Startall(int count, MPIX_Request *reqs) {
     if (!g_acx || !g_acx->initialized) return MPI_ERR_OTHER;
     bool any_dev = false;
@@ -1609,6 +1620,7 @@ static int pwait_host(AcxRequest *r, MPI_Status *status) {
     return MPI_SUCCESS;
 }
 
+// Reference: MPIX_Request_free, src/sendrecv.cu:654-682 (partitioned only; basic requests silently ignored, defect D11).
 extern "C" int MPIX_Request_free(MPIX_Request *request) {
     if (!request || *request == MPIX_REQUEST_NULL) return MPI_SUCCESS;
     AcxRequest *r = as_request(*request);
@@ -1632,6 +1644,7 @@ extern "C" int MPIX_Request_free(MPIX_Request *request) {
     return MPI_SUCCESS;
 }
 
+// Reference: host side of MPIX_Pready / MPIX_Parrived, src/partitioned.cu:206-231.
 extern "C" int MPIX_Pready_host(int partition, MPIX_Request *request) {
     AcxRequest *r = request ? as_request(*request) : nullptr;
     if (!r || r->kind != ACX_REQ_PSEND) return MPI_ERR_REQUEST;
