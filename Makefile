@@ -14,7 +14,7 @@ BINS  := bin/acxrun
 BENCH := $(patsubst bench/%.cu,bin/%,$(wildcard bench/*.cu))
 CTESTS := $(patsubst tests/c/%.c,$(B)/tests/%,$(wildcard tests/c/*.c)) $(patsubst tests/c/%.cu,$(B)/tests/%,$(wildcard tests/c/*.cu))
 
-.PHONY: all clean lib tests bench
+.PHONY: all clean lib tests bench examples tsan asan
 all: lib $(BINS) tests bench
 bench: $(BENCH)
 bin/%: bench/%.cu $(LIB)
@@ -54,6 +54,11 @@ $(B)/tests/%: tests/c/%.c $(LIB)
 $(B)/tests/%: tests/c/%.cu $(LIB)
 	@mkdir -p $(B)/tests
 	$(NVCC) $(GENCODE) -O2 -lineinfo -Iinclude $< -o $@ -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
+
+examples: $(LIB)
+	@mkdir -p $(B)/examples
+	$(NVCC) $(GENCODE) -O2 -Iinclude examples/stream_ring.c -o $(B)/examples/stream_ring -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
+	$(NVCC) $(GENCODE) -O2 -Iinclude examples/partitioned_producer.cu -o $(B)/examples/partitioned_producer -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
 
 clean:
 	rm -rf $(B) lib bin

@@ -139,3 +139,12 @@ def test_bench_reference_arm_reports_unavailable_without_gpu(built):
     assert r.returncode == 0
     j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert j["impl"] == "reference" and ("unavailable" in j or "value" in j)
+
+
+def test_examples_compile_and_python_example_runs(built):
+    """examples/ are the switch-over guide for users of the reference: they must build against include/ + libacx."""
+    r = subprocess.run(["make", "-C", str(built), "examples"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", ACX_FORCE_HOST="1")
+    r = subprocess.run([sys.executable, str(built / "examples/torch_ring.py")], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "received tensor filled with 1.0" in r.stdout, r.stdout + r.stderr
