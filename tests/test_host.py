@@ -148,3 +148,16 @@ def test_examples_compile_and_python_example_runs(built):
     env = dict(os.environ, RANK="0", WORLD_SIZE="1", ACX_FORCE_HOST="1")
     r = subprocess.run([sys.executable, str(built / "examples/torch_ring.py")], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "received tensor filled with 1.0" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("mode", ["ring", "allpairs"])
+def test_nccl_baseline_tool_control_flow(mode):
+    """bench/nccl_p2p.py (the independent NCCL yardstick) on gloo: same traffic pattern, payload verified."""
+    import json
+    env = dict(os.environ, NCCL_P2P_DRYRUN_CPU="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29617",
+           str(REPO / "bench/nccl_p2p.py"), mode, "--bytes", "8192", "--steps", "2", "--warmup", "1"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["impl"] == "nccl-p2p" and d["bad_words"] == 0 and d["n_gpus"] == 2
