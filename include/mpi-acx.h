@@ -43,7 +43,9 @@ int MPIX_Finalize(void);
 
 /* ---- stream / graph triggered two-sided operations -------------------------------------------
  * The transfer starts no earlier than the point where the call sits in the stream or graph; the
- * buffer must stay valid until a wait on the returned request has completed. */
+ * buffer must stay valid until a wait on the returned request has completed. MPI_PROC_NULL peers are
+ * accepted (the operation completes at its wait, moving nothing); MPI_ANY_SOURCE / MPI_ANY_TAG receives
+ * are honoured on the host transport and rejected (MPI_ERR_RANK / MPI_ERR_TAG) on the device transport. */
 int MPIX_Isend_enqueue(const void *sendbuf, int nelems, MPI_Datatype dtype, int dst_rank, int tag, MPI_Comm comm, MPIX_Request *req_out, int queue_kind, void *queue_handle);
 int MPIX_Irecv_enqueue(void *recvbuf, int nelems, MPI_Datatype dtype, int src_rank, int tag, MPI_Comm comm, MPIX_Request *req_out, int queue_kind, void *queue_handle);
 

@@ -295,14 +295,27 @@ int acx_device_alias(const void *p, size_t bytes, char **out) {
 
 int acx_comm_ctx(MPI_Comm comm, int *ctx) {
     std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
-    for (size_t i = 0; i < g_acx->comms.size(); i++) if (g_acx->comms[i] == comm) { *ctx = (int)i; return 0; }
+    // The context id feeds the channel hash and the partitioned handshake tag, so it must be the SAME number on
+    // both ends of a message. The bundled mini-MPI assigns communicator ids collectively (identical on every
+    // rank), so the id itself is used; with another MPI the order of first use is the only portable stand-in
+    // (ranks must then first-use their communicators in the same order).
+    auto id_of = [](MPI_Comm c, size_t index) {
+#ifdef ACX_MINI_MPI
+        (void)index;
+        return (int)c - (int)MPI_COMM_WORLD;
+#else
+        (void)c;
+        return (int)index;
+#endif
+    };
+    for (size_t i = 0; i < g_acx->comms.size(); i++) if (g_acx->comms[i] == comm) { *ctx = id_of(comm, i); return 0; }
     int sz = 0;
     if (MPI_Comm_size(comm, &sz) != MPI_SUCCESS || sz != g_acx->size) {
         ACX_ERR("only communicators spanning all of MPI_COMM_WORLD (in world rank order) are supported");
         return MPI_ERR_COMM;
     }
     g_acx->comms.push_back(comm);
-    *ctx = (int)g_acx->comms.size() - 1;
+    *ctx = id_of(comm, g_acx->comms.size() - 1);
     return 0;
 }
 
@@ -964,16 +977,64 @@ static AcxRequest *new_request(AcxReqKind kind, int peer, int tag, int ctx, size
     return r;
 }
 
-static int check_common(const char *fn, int count, MPI_Datatype dt, int peer, int tag, MPI_Comm comm, MPIX_Request *request, void *queue, size_t *bytes, int *ctx) {
+static int check_common(const char *fn, bool is_recv, int count, MPI_Datatype dt, int peer, int tag, MPI_Comm comm, MPIX_Request *request, void *queue, size_t *bytes, int *ctx) {
     if (!g_acx || !g_acx->initialized) { fprintf(stderr, "[acx] %s: MPIX_Init has not been called\n", fn); return MPI_ERR_OTHER; }
     if (!request || !queue) { ACX_ERR("%s: null request/queue", fn); return MPI_ERR_ARG; }
     if (count < 0) { ACX_ERR("%s: negative count", fn); return MPI_ERR_COUNT; }
     int sz = 0;
     if (MPI_Type_size(dt, &sz) != MPI_SUCCESS || sz <= 0) { ACX_ERR("%s: invalid datatype", fn); return MPI_ERR_TYPE; }
-    if (peer < 0 || peer >= g_acx->size) { ACX_ERR("%s: peer %d out of range (wildcards / MPI_PROC_NULL are not supported)", fn, peer); return MPI_ERR_RANK; }
-    if (tag < 0) { ACX_ERR("%s: tag %d invalid (MPI_ANY_TAG is not supported)", fn, tag); return MPI_ERR_TAG; }
+    // MPI_PROC_NULL is valid everywhere. Wildcards (receive side only) are matched by the MPI library on the host
+    // transport; the device transport pairs messages by (peer, channel) tickets and cannot honour them yet.
+    const bool wild_ok = is_recv && !g_acx->device;
+    if (peer != MPI_PROC_NULL && !(wild_ok && peer == MPI_ANY_SOURCE) && (peer < 0 || peer >= g_acx->size)) {
+        ACX_ERR("%s: peer %d out of range%s", fn, peer, peer == MPI_ANY_SOURCE ? " (MPI_ANY_SOURCE is only supported on the host transport)" : "");
+        return MPI_ERR_RANK;
+    }
+    if (tag < 0 && !(wild_ok && tag == MPI_ANY_TAG) && peer != MPI_PROC_NULL) {
+        ACX_ERR("%s: tag %d invalid%s", fn, tag, tag == MPI_ANY_TAG ? " (MPI_ANY_TAG is only supported on the host transport)" : "");
+        return MPI_ERR_TAG;
+    }
     *bytes = (size_t)count * (size_t)sz;
     return acx_comm_ctx(comm, ctx);
+}
+
+// A send to / receive from MPI_PROC_NULL: nothing is enqueued and no slot is taken; the request completes at the
+// first wait with an empty status (source MPI_PROC_NULL, tag MPI_ANY_TAG, 0 bytes), as MPI prescribes. In
+// explicit-graph mode the caller still gets a (one empty node) graph to embed.
+static int make_null_op(AcxRequest *r, int qtype, void *queue, MPIX_Request *request) {
+    r->null_op = true;
+    r->in_graph = false;
+    if (qtype == MPIX_QUEUE_CUDA_GRAPH) {
+        cudaGraph_t g = nullptr;
+        cudaGraphNode_t node;
+        if (cudaGraphCreate(&g, 0) != cudaSuccess || cudaGraphAddEmptyNode(&node, g, nullptr, 0) != cudaSuccess) {
+            ACX_ERR("cudaGraphCreate failed for a MPI_PROC_NULL operation");
+            if (g) cudaGraphDestroy(g);
+            r->magic = 0; delete r;
+            return MPI_ERR_OTHER;
+        }
+        *(cudaGraph_t *)queue = g;
+        r->in_graph = true;
+    } else if (qtype != MPIX_QUEUE_CUDA_STREAM) {
+        r->magic = 0; delete r;
+        return MPI_ERR_ARG;
+    } else {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(*(cudaStream_t *)queue, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) r->in_graph = true;
+        else cudaGetLastError();
+    }
+    *request = r;
+    return MPI_SUCCESS;
+}
+static void complete_null_op(AcxRequest *r, MPI_Status *st) {
+    if (st != MPI_STATUS_IGNORE) {
+        st->MPI_SOURCE = MPI_PROC_NULL; st->MPI_TAG = MPI_ANY_TAG; st->MPI_ERROR = MPI_SUCCESS;
+#ifdef ACX_MINI_MPI
+        st->_bytes = 0;
+#endif
+    }
+    r->magic = 0;
+    delete r;
 }
 
 // =======================================================================================
@@ -984,7 +1045,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
                                   int qtype, void *queue) {
     AcxRange _r("MPIX_Isend_enqueue");
     size_t bytes; int ctx;
-    int rc = check_common("MPIX_Isend_enqueue", count, datatype, dest, tag, comm, request, queue, &bytes, &ctx);
+    int rc = check_common("MPIX_Isend_enqueue", false, count, datatype, dest, tag, comm, request, queue, &bytes, &ctx);
     if (rc) return rc;
     AcxRequest *r = new_request(ACX_REQ_SEND, dest, tag, ctx, bytes, buf);
     if (!g_acx->device) {
@@ -996,6 +1057,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         *request = r;
         return MPI_SUCCESS;
     }
+    if (dest == MPI_PROC_NULL) return make_null_op(r, qtype, queue, request);
     Emitter em;
     if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
     r->in_graph = em.in_graph();
@@ -1077,7 +1139,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
                                   void *queue) {
     AcxRange _r("MPIX_Irecv_enqueue");
     size_t bytes; int ctx;
-    int rc = check_common("MPIX_Irecv_enqueue", count, datatype, source, tag, comm, request, queue, &bytes, &ctx);
+    int rc = check_common("MPIX_Irecv_enqueue", true, count, datatype, source, tag, comm, request, queue, &bytes, &ctx);
     if (rc) return rc;
     AcxRequest *r = new_request(ACX_REQ_RECV, source, tag, ctx, bytes, buf);
     if (!g_acx->device) {
@@ -1089,6 +1151,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         *request = r;
         return MPI_SUCCESS;
     }
+    if (source == MPI_PROC_NULL) return make_null_op(r, qtype, queue, request);
     Emitter em;
     if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
     r->in_graph = em.in_graph();
@@ -1227,6 +1290,11 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             ACX_ERR("partitioned requests cannot be completed with MPIX_Wait(all)_enqueue; use MPIX_Wait / MPIX_Pwait_enqueue");
             return MPI_ERR_REQUEST;
         }
+        if (r->null_op) {   // MPI_PROC_NULL: complete on the spot, nothing to enqueue
+            complete_null_op(r, statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[i]);
+            reqs[i] = MPIX_REQUEST_NULL;
+            continue;
+        }
         rs.push_back(r);
     }
     if (!g_acx->device) {
@@ -1347,6 +1415,7 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
         *req = MPIX_REQUEST_NULL;
         return rc;
     }
+    if (r->null_op) { complete_null_op(r, status); *req = MPIX_REQUEST_NULL; return MPI_SUCCESS; }
     if (r->in_graph) { ACX_ERR("in-graph operations must be completed by a wait inside a graph"); return MPI_ERR_REQUEST; }
     if (r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max) {
         // eager send: complete once its trigger kernel has run; it says so in pinned host memory
@@ -1471,7 +1540,9 @@ static int pinit_common(AcxReqKind kind, const void *buf, int partitions, MPI_Co
     }
     // Exchange descriptors on the private communicator; matching order per (peer, tag)
     // follows MPI's own non-overtaking rule, which is exactly the init-order pairing we need.
-    const int t_out = tag * 2 + (kind == ACX_REQ_PSEND ? 0 : 1), t_in = tag * 2 + (kind == ACX_REQ_PSEND ? 1 : 0);
+    // (per communicator: the context id occupies the tag bits above the user's tag range)
+    const int t_base = (int)(((unsigned)ctx & 0x3fu) << 24) | ((tag & 0x7fffff) << 1);
+    const int t_out = t_base + (kind == ACX_REQ_PSEND ? 0 : 1), t_in = t_base + (kind == ACX_REQ_PSEND ? 1 : 0);
     MPI_Irecv(&hs->theirs, (int)sizeof(PInfo), MPI_BYTE, peer, t_in, g_acx->icomm, &hs->rreq);
     MPI_Isend(&hs->mine, (int)sizeof(PInfo), MPI_BYTE, peer, t_out, g_acx->icomm, &hs->sreq);
     { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); g_hs[r] = hs; }

@@ -130,6 +130,7 @@ struct AcxRequest {
     cudaEvent_t ev_trig, ev_done;  // large transfers: mover runs on a per-peer side stream (fork after the trigger / join at the wait)
     bool in_graph;
     bool host_transport;      // no-GPU mode: backed by an MPI_Request
+    bool null_op;             // peer was MPI_PROC_NULL: completes immediately, moves nothing, owns no slot
     MPI_Request mpi_req;
     MPI_Status *user_status;
     AcxGraphRes *gres;

@@ -180,3 +180,12 @@ acx.finalize(); print("GEMM OK")
 """ % str(REPO)
     r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "GEMM OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_proc_null_and_communicator_contexts(built, np_):
+    """MPI_PROC_NULL on stream / host / explicit-graph paths, dup'ed communicators first used in different orders on
+    different ranks, clean rejection of wildcards on the device transport (tests/c/procnull_comms.c)."""
+    r = acxrun(built, np_, built / "build/tests/procnull_comms")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout
