@@ -47,6 +47,7 @@ static int g_apush = 0;                   // deterministic large-message mode: t
 static std::map<std::pair<int, int>, cudaStream_t> g_chan_streams;   // (peer, channel) -> stream for sender-push movers
 static int g_side_on = 1;                 // run large movers on per-peer side streams so transfers to different peers overlap (ACX_SIDE_STREAMS)
 static std::vector<cudaStream_t> g_side;  // side streams, indexed by peer % size
+static int g_branch = 0;                  // ACX_PEER_BRANCH: run EVERY operation with a peer on that peer's side stream (fork at enqueue, join at the wait)
 static int g_fuse_rndv = 1, g_fuse_min_ctas = 8, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
 static int g_pdl = 1;   // programmatic dependent launch between consecutive acx kernels on a stream (ACX_PDL)
 static bool g_nvtx = false;
@@ -497,6 +498,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_MOVER_BLOCK", nullptr, 0, &v); g_mover_block = (int)std::max(0L, v) & ~511;
     acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
     acx_env_int("ACX_SIDE_STREAMS", nullptr, 1, &v); g_side_on = v != 0;
+    acx_env_int("ACX_PEER_BRANCH", nullptr, 0, &v); g_branch = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_SENDER_PUSH", nullptr, 0, &v); g_apush = v != 0;   // opt-in: a spinning gate can deadlock against device-synchronizing host calls
     acx_env_int("ACX_FUSE_MAX_CTAS", nullptr, 32, &v); g_fuse_max_ctas = (int)v;
     acx_env_int("ACX_FUSE_MIN_CTAS", nullptr, 8, &v); g_fuse_min_ctas = (int)v;
@@ -882,7 +884,6 @@ static int mover_grid(size_t bytes) {
     return 0;
 }
 static int mover_grid_ldst(size_t bytes);
-static int mover_grid_any(size_t bytes) { int g = mover_grid(bytes); return g ? g : mover_grid_ldst(bytes); }
 static int mover_grid_ldst(size_t bytes) {
     size_t g = (bytes + g_acx->mover_min_cta_bytes - 1) / g_acx->mover_min_cta_bytes;
     // Half an SM-count of 512-thread CTAs already saturates one NVLink direction (measured 647 vs 652 GB/s at 148) and
@@ -915,11 +916,46 @@ static int launch_mover(Emitter &em, MoverParams &mp, size_t bytes) {
     return em.launch(mover, dim3(grid), dim3(kMoverThreads), mp);
 }
 
+// Whole-operation branching (ACX_PEER_BRANCH=1): every kernel of an operation with peer p — bounce-in copy, trigger,
+// mover or fused rendezvous — goes to p's side stream, forked from the caller's stream at the enqueue point and
+// joined at the wait. Operations with different peers then run concurrently (an all-pairs step is 2(N-1) kernels deep
+// otherwise), while everything addressed to ONE peer stays on one stream, so device-assigned tickets keep the
+// enqueue order per (peer, channel). Because eager sends also leave the caller's stream, their "complete when the
+// trigger retires" shortcut needs the join too: the wait makes the caller's stream depend on ev_done.
+struct BranchScope {
+    Emitter &em;
+    AcxRequest *r;
+    cudaStream_t user = nullptr;
+    bool on = false;
+    BranchScope(Emitter &e, AcxRequest *req) : em(e), r(req) {}
+    int begin() {
+        if (!g_branch || g_apush || em.qtype != MPIX_QUEUE_CUDA_STREAM || g_side.empty()) return 0;
+        r->ev_trig = event_get(); r->ev_done = event_get();
+        if (!r->ev_trig || !r->ev_done) return 0;   // out of events: stay on the caller's stream (still correct)
+        cudaStream_t side = g_side[(size_t)r->peer % g_side.size()];
+        ACX_CUDA(cudaEventRecord(r->ev_trig, em.stream));
+        ACX_CUDA(cudaStreamWaitEvent(side, r->ev_trig, 0));
+        user = em.stream;
+        em.stream = side;
+        on = true;
+        r->branched = true;
+        return 0;
+    }
+    int end() {
+        if (!on) return 0;
+        on = false;
+        cudaStream_t side = em.stream;
+        em.stream = user;
+        ACX_CUDA(cudaEventRecord(r->ev_done, side));
+        return 0;
+    }
+};
+
 // Unfused movers of stream-mode operations run on a per-peer side stream, forked after the trigger kernel: the
 // user's stream is not held up by the transfer, and transfers to/from different peers overlap (all-pairs,
 // halo-style neighbour exchanges). The wait joins the side stream (required when capturing).
 static int launch_mover_maybe_side(Emitter &em, AcxRequest *r, MoverParams &mp, size_t bytes) {
-    if (!g_side_on || em.qtype != MPIX_QUEUE_CUDA_STREAM || g_side.empty()) return launch_mover(em, mp, bytes);
+    if (!g_side_on || em.qtype != MPIX_QUEUE_CUDA_STREAM || g_side.empty() || r->branched) return launch_mover(em, mp, bytes);
     r->ev_trig = event_get(); r->ev_done = event_get();
     if (!r->ev_trig || !r->ev_done) return launch_mover(em, mp, bytes);
     cudaStream_t side = g_side[(size_t)r->peer % g_side.size()];
@@ -1059,11 +1095,13 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
     }
     if (dest == MPI_PROC_NULL) return make_null_op(r, qtype, queue, request);
     Emitter em;
+    BranchScope branch(em, r);
     if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
     r->in_graph = em.in_graph();
     r->chan = chan_of(tag, ctx);
     if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
     if ((rc = acx_device_alias(buf, bytes, &r->dev_buf))) goto fail;
+    if ((rc = branch.begin())) goto fail;
     {
         const acx_geom &G = g_acx->geom;
         const bool eager = bytes <= G.eager_max;
@@ -1120,6 +1158,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
             g_acx->st.eager++;
         }
     }
+    if ((rc = branch.end())) goto fail;
     if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;
     if (qtype == MPIX_QUEUE_CUDA_GRAPH) {
         if ((rc = attach_to_graph(em.graph, r->slot))) goto fail;
@@ -1153,6 +1192,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
     }
     if (source == MPI_PROC_NULL) return make_null_op(r, qtype, queue, request);
     Emitter em;
+    BranchScope branch(em, r);
     if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
     r->in_graph = em.in_graph();
     r->chan = chan_of(tag, ctx);
@@ -1168,6 +1208,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
     }
     if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
     if ((rc = acx_device_alias(buf, bytes, &r->dev_buf))) goto fail;
+    if ((rc = branch.begin())) goto fail;
     {
         const acx_geom &G = g_acx->geom;
         const bool rndv_capable = bytes > G.eager_max;
@@ -1208,6 +1249,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
             if (rndv_capable && (rc = launch_mover_maybe_side(em, r, mp, bytes))) goto fail;
         }
     }
+    if ((rc = branch.end())) goto fail;
     if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;
     if (qtype == MPIX_QUEUE_CUDA_GRAPH) {
         if ((rc = attach_to_graph(em.graph, r->slot))) goto fail;
@@ -1335,7 +1377,7 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             MPI_Status *st = statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[idx];
             idx++;
             if (r->kind == ACX_REQ_SEND && st != MPI_STATUS_IGNORE && !em.in_graph()) host_status_send(st, r);
-            if (r->ev_done && em.capturing) {   // join the forked mover branch back into the capturing stream
+            if (r->ev_done && (em.capturing || r->branched)) {   // join the forked branch: required when capturing, and for branched operations (eager sends rely on it)
                 cudaError_t je = cudaStreamWaitEvent(em.stream, r->ev_done, 0);
                 if (je != cudaSuccess) { ACX_ERR("cudaStreamWaitEvent(join): %s", cudaGetErrorString(je)); return MPI_ERR_OTHER; }
             }

@@ -131,6 +131,7 @@ struct AcxRequest {
     bool in_graph;
     bool host_transport;      // no-GPU mode: backed by an MPI_Request
     bool null_op;             // peer was MPI_PROC_NULL: completes immediately, moves nothing, owns no slot
+    bool branched;            // ACX_PEER_BRANCH: all of this operation's kernels ran on the peer's side stream (the wait joins ev_done)
     MPI_Request mpi_req;
     MPI_Status *user_status;
     AcxGraphRes *gres;

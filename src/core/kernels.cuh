@@ -166,7 +166,6 @@ __global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
     __syncthreads();
     const uint64_t k = s_k;
     const uint32_t e = (uint32_t)(k % p.depth);
-    const uint64_t g = k / p.depth;
     acx_entry *ent = p.ring + e;
     if (p.bytes <= p.eager_max) {
         // Eager: payload + header into the receiver's slot, then ONE release (the barrier makes the

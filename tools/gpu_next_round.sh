@@ -1,0 +1,50 @@
+#!/bin/bash
+# First GPU pass of the NEXT round: validates and measures everything that was written after round 1's GPU budget was
+# spent (none of it is on a default path except bench.py's pre-posted order for >= 3 GPUs and the self-transfer grid).
+#   gpurun --gpus 2 --timeout 900 -- tools/gpu_next_round.sh 2
+#   gpurun --gpus 8 --timeout 900 -- tools/gpu_next_round.sh 8
+NP=${1:-2}
+export ACX_WATCHDOG_MS=30000
+O=gpurun_out; mkdir -p $O
+R=baseline/_ref/bin
+run() { timeout 120 ./bin/acxrun -np $NP --timeout 100 "$@" 2>&1 | tail -n 2; }
+
+echo "### 1. new conformance program (PROC_NULL, communicator contexts, wildcard rejection)"
+for np in 1 $NP; do timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/procnull_comms 2>&1 | tail -n 3; done
+
+echo "### 2. examples"
+make examples > /dev/null 2>&1
+for e in stream_ring partitioned_producer; do timeout 60 ./bin/acxrun -np $NP --timeout 50 build/examples/$e 2>&1 | tail -n $NP; done
+timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29701 examples/torch_ring.py 2>&1 | grep "rank" | head -n $NP
+
+echo "### 3. ACX_PEER_BRANCH=1 (whole-operation per-peer branches): conformance, then all-pairs + ring against the default"
+for t in ring ring_all ring_all_device ring_all_graph ring_graph_construction large_msgs ordering stress regcache; do
+  ACX_PEER_BRANCH=1 run build/tests/$t | tail -n 1
+done
+for b in 1048576 16777216; do
+  for br in 0 1; do
+    echo "allpairs bytes=$b branch=$br: $(ACX_PEER_BRANCH=$br ACX_HEAP_BYTES=1g run bin/p2p_bench allpairs --bytes $b | tail -n 1)" | tee -a $O/allpairs_branch_n${NP}.txt
+  done
+  echo "allpairs bytes=$b reference: $(run $R/p2p_bench allpairs --bytes $b --no-heap | tail -n 1)" | tee -a $O/allpairs_branch_n${NP}.txt
+done
+for br in 0 1; do echo "ring branch=$br: $(ACX_PEER_BRANCH=$br ACX_HEAP_BYTES=1g run bin/p2p_bench ring --bytes 268435456 | tail -n 1)"; done
+for br in 0 1; do echo "pingpong branch=$br: $(ACX_PEER_BRANCH=$br timeout 120 ./bin/acxrun -np 2 --timeout 100 bin/p2p_bench pingpong 2>&1 | tail -n 1 | cut -c1-400)"; done
+
+echo "### 4. ring with pre-posted receives (C harness) and bench.py at N=$NP (auto order = prepost from 3 GPUs up)"
+ACX_HEAP_BYTES=1g run bin/p2p_bench ring --bytes 268435456 --prepost | tee $O/ring_acx_prepost_n${NP}.json
+run $R/p2p_bench ring --bytes 268435456 --no-heap --prepost | tee $O/ring_ref_prepost_n${NP}.json
+for order in auto simple; do
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29702 bench.py --gpus $NP --order $order > $O/bench_acx_n${NP}_$order.json 2> $O/bench_acx_n${NP}_$order.err
+  echo "bench.py order=$order rc=$?"; grep '^{' $O/bench_acx_n${NP}_$order.json | tail -n 1 | cut -c1-600
+done
+
+echo "### 5. NCCL p2p yardstick"
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29703 bench/nccl_p2p.py"
+timeout 300 $T ring --bytes 268435456 2>/dev/null | grep '^{' | tee $O/nccl_ring_n${NP}.json
+timeout 300 $T allpairs --bytes 16777216 --graph 2>/dev/null | grep '^{' | tee $O/nccl_allpairs_n${NP}.json
+timeout 300 $T allpairs --bytes 1048576 --graph 2>/dev/null | grep '^{'
+[ "$NP" = 2 ] && timeout 600 $T pingpong 2>/dev/null | grep '^{' | tee $O/nccl_pingpong.json | cut -c1-600
+
+echo "### 6. self-transfer (N=1): mover on the caller's stream vs the side stream"
+for ss in 1 0; do echo "side_streams=$ss: $(ACX_SIDE_STREAMS=$ss ACX_HEAP_BYTES=1g timeout 60 ./bin/acxrun -np 1 --timeout 50 bin/p2p_bench ring --bytes 268435456 --steps 20 --warmup 5 2>&1 | tail -n 1 | cut -c100-200)"; done
+echo "reference: $(timeout 60 ./bin/acxrun -np 1 --timeout 50 $R/p2p_bench ring --bytes 268435456 --steps 20 --warmup 5 --no-heap 2>&1 | tail -n 1 | cut -c60-160)"
