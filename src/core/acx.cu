@@ -47,6 +47,9 @@ static int g_apush = 0;                   // deterministic large-message mode: t
 static std::map<std::pair<int, int>, cudaStream_t> g_chan_streams;   // (peer, channel) -> stream for sender-push movers
 static int g_side_on = 1;                 // run large movers on per-peer side streams so transfers to different peers overlap (ACX_SIDE_STREAMS)
 static std::vector<cudaStream_t> g_side;  // side streams, indexed by peer % size
+static int g_wild = 0;                    // ACX_WILDCARDS: MPI_ANY_SOURCE / MPI_ANY_TAG receives on the device transport (experimental; matched at wait time)
+static AnyTable *g_any_tbl_d = nullptr;   // device copy of the peer window bases, built on first wildcard use
+static acx_anyres *g_anyres_d = nullptr;  // one resolution record per request slot
 static int g_branch = 0;                  // ACX_PEER_BRANCH: run EVERY operation with a peer on that peer's side stream (fork at enqueue, join at the wait)
 static int g_fuse_rndv = 1, g_fuse_min_ctas = 8, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
 static int g_pdl = 1;   // programmatic dependent launch between consecutive acx kernels on a stream (ACX_PDL)
@@ -498,6 +501,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_MOVER_BLOCK", nullptr, 0, &v); g_mover_block = (int)std::max(0L, v) & ~511;
     acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
     acx_env_int("ACX_SIDE_STREAMS", nullptr, 1, &v); g_side_on = v != 0;
+    acx_env_int("ACX_WILDCARDS", nullptr, 0, &v); g_wild = v != 0;   // experimental device-side wildcard matching (see recv_any_kernel)
     acx_env_int("ACX_PEER_BRANCH", nullptr, 0, &v); g_branch = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_SENDER_PUSH", nullptr, 0, &v); g_apush = v != 0;   // opt-in: a spinning gate can deadlock against device-synchronizing host calls
     acx_env_int("ACX_FUSE_MAX_CTAS", nullptr, 32, &v); g_fuse_max_ctas = (int)v;
@@ -656,6 +660,8 @@ extern "C" int MPIX_Finalize(void) {
         cudaFreeHost(g_acx->hstat);
         cudaFreeHost(g_diag);
         cudaFree(g_trace_cursor);
+        if (g_any_tbl_d) { cudaFree(g_any_tbl_d); g_any_tbl_d = nullptr; }
+        if (g_anyres_d) { cudaFree(g_anyres_d); g_anyres_d = nullptr; }
         cudaFree(g_acx->ctrl);
         cudaFree(g_acx->heap);
         g_diag = g_diag_d = nullptr;
@@ -1021,13 +1027,13 @@ static int check_common(const char *fn, bool is_recv, int count, MPI_Datatype dt
     if (MPI_Type_size(dt, &sz) != MPI_SUCCESS || sz <= 0) { ACX_ERR("%s: invalid datatype", fn); return MPI_ERR_TYPE; }
     // MPI_PROC_NULL is valid everywhere. Wildcards (receive side only) are matched by the MPI library on the host
     // transport; the device transport pairs messages by (peer, channel) tickets and cannot honour them yet.
-    const bool wild_ok = is_recv && !g_acx->device;
+    const bool wild_ok = is_recv && (!g_acx->device || g_wild);
     if (peer != MPI_PROC_NULL && !(wild_ok && peer == MPI_ANY_SOURCE) && (peer < 0 || peer >= g_acx->size)) {
-        ACX_ERR("%s: peer %d out of range%s", fn, peer, peer == MPI_ANY_SOURCE ? " (MPI_ANY_SOURCE is only supported on the host transport)" : "");
+        ACX_ERR("%s: peer %d out of range%s", fn, peer, peer == MPI_ANY_SOURCE ? " (MPI_ANY_SOURCE on the device transport needs ACX_WILDCARDS=1)" : "");
         return MPI_ERR_RANK;
     }
     if (tag < 0 && !(wild_ok && tag == MPI_ANY_TAG) && peer != MPI_PROC_NULL) {
-        ACX_ERR("%s: tag %d invalid%s", fn, tag, tag == MPI_ANY_TAG ? " (MPI_ANY_TAG is only supported on the host transport)" : "");
+        ACX_ERR("%s: tag %d invalid%s", fn, tag, tag == MPI_ANY_TAG ? " (MPI_ANY_TAG on the device transport needs ACX_WILDCARDS=1)" : "");
         return MPI_ERR_TAG;
     }
     *bytes = (size_t)count * (size_t)sz;
@@ -1071,6 +1077,40 @@ static void complete_null_op(AcxRequest *r, MPI_Status *st) {
     }
     r->magic = 0;
     delete r;
+}
+
+// Wildcard receives (experimental): device tables on first use, and the kernel that resolves + matches one at wait time.
+static int any_tables() {
+    if (g_any_tbl_d) return 0;
+    if (g_acx->size > kAnyMaxRanks) { ACX_ERR("wildcard receives support up to %d ranks", kAnyMaxRanks); return MPI_ERR_OTHER; }
+    AnyTable h;
+    memset(&h, 0, sizeof h);
+    for (int i = 0; i < g_acx->size; i++) { h.peer_ctrl[i] = g_acx->peer_ctrl[i]; h.peer_heap[i] = g_acx->peer_heap[i]; }
+    ACX_CUDA(cudaMalloc((void **)&g_any_tbl_d, sizeof h));
+    ACX_CUDA(cudaMemcpy(g_any_tbl_d, &h, sizeof h, cudaMemcpyHostToDevice));
+    ACX_CUDA(cudaMalloc((void **)&g_anyres_d, sizeof(acx_anyres) * (size_t)g_acx->geom.nops));
+    ACX_CUDA(cudaMemset(g_anyres_d, 0, sizeof(acx_anyres) * (size_t)g_acx->geom.nops));
+    return 0;
+}
+static void fill_any(AcxRequest *r, AnyParams *ap) {
+    const acx_geom &G = g_acx->geom;
+    memset(ap, 0, sizeof *ap);
+    ap->tbl = g_any_tbl_d; ap->ctrl = g_acx->ctrl; ap->res = g_anyres_d + r->slot;
+    ap->op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
+    const bool rndv_capable = r->bytes > G.eager_max;
+    ap->rndv_capable = rndv_capable ? 1 : 0;
+    ap->dst = r->bounce_off >= 0 ? g_acx->heap + r->bounce_off : r->dev_buf;
+    ap->dst_off = r->bounce_off >= 0 ? (uint64_t)r->bounce_off : (r->heap_off >= 0 ? (uint64_t)r->heap_off : ~0ull);
+    ap->cap = r->bytes; ap->serial = r->serial; ap->geom = G;
+    if (r->peer == MPI_ANY_SOURCE) { ap->src_lo = 0; ap->src_hi = g_acx->size - 1; } else { ap->src_lo = ap->src_hi = r->peer; }
+    if (r->tag == MPI_ANY_TAG) { ap->chan_lo = 0; ap->chan_hi = G.nchan - 1; } else { ap->chan_lo = ap->chan_hi = chan_of(r->tag, r->comm_ctx); }
+    ap->want_tag = r->tag; ap->me = (uint32_t)g_acx->rank; ap->vec256 = (uint32_t)g_mover_256;
+    ap->wd = make_wd(); ap->tr = make_tr();
+}
+static int any_grid(const AcxRequest *r) {
+    if (r->bytes <= g_acx->geom.eager_max) return 1;
+    size_t g = (r->bytes + g_acx->mover_min_cta_bytes - 1) / g_acx->mover_min_cta_bytes;
+    return (int)std::max<size_t>(1, std::min<size_t>(g, 32));   // all CTAs must be co-resident: they wait for CTA 0's match
 }
 
 // =======================================================================================
@@ -1195,6 +1235,20 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
     BranchScope branch(em, r);
     if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
     r->in_graph = em.in_graph();
+    if (source == MPI_ANY_SOURCE || tag == MPI_ANY_TAG) {
+        // Wildcard: nothing is launched now; the wait resolves, matches and (for a rendezvous message) pulls.
+        r->wild = true; r->chan = -1;
+        if ((rc = any_tables())) { if (qtype == MPIX_QUEUE_CUDA_GRAPH) cudaGraphDestroy(em.graph); delete r; return rc; }
+        if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { if (qtype == MPIX_QUEUE_CUDA_GRAPH) cudaGraphDestroy(em.graph); delete r; return MPI_ERR_OTHER; }
+        if ((rc = acx_device_alias(buf, bytes, &r->dev_buf))) goto fail;
+        r->heap_off = acx_heap_offset_of(buf);
+        if (bytes > g_acx->geom.eager_max && r->heap_off < 0) {   // a sender may push: the landing zone must be in the heap
+            if ((r->bounce_off = acx_heap_alloc(bytes)) < 0) { rc = MPI_ERR_OTHER; goto fail; }
+            g_acx->st.bounce++;
+        }
+        if (qtype == MPIX_QUEUE_CUDA_GRAPH) { cudaGraphNode_t node; cudaGraphAddEmptyNode(&node, em.graph, nullptr, 0); }
+        goto done;
+    }
     r->chan = chan_of(tag, ctx);
     if (!r->in_graph) {
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
@@ -1250,6 +1304,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         }
     }
     if ((rc = branch.end())) goto fail;
+done:
     if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;
     if (qtype == MPIX_QUEUE_CUDA_GRAPH) {
         if ((rc = attach_to_graph(em.graph, r->slot))) goto fail;
@@ -1288,10 +1343,14 @@ static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_w
         w->sack = acx_sacks_of(g_acx->ctrl) + acx_entry_index(G, r->peer, r->chan, 0);
     } else {
         w->is_recv = 1;
-        const uint64_t ring_idx = acx_entry_index(G, r->peer, r->chan, 0);
-        w->ring = acx_entries_of(g_acx->ctrl) + ring_idx;
-        w->eager = g_acx->ctrl + G.off_eager + ring_idx * G.eager_max;
-        w->sack = acx_sacks_of(g_acx->peer_ctrl[r->peer]) + acx_entry_index(G, g_acx->rank, r->chan, 0);
+        if (r->wild) {
+            w->any = g_anyres_d + r->slot;   // ring / sack / eager / source are resolved on the device
+        } else {
+            const uint64_t ring_idx = acx_entry_index(G, r->peer, r->chan, 0);
+            w->ring = acx_entries_of(g_acx->ctrl) + ring_idx;
+            w->eager = g_acx->ctrl + G.off_eager + ring_idx * G.eager_max;
+            w->sack = acx_sacks_of(g_acx->peer_ctrl[r->peer]) + acx_entry_index(G, g_acx->rank, r->chan, 0);
+        }
         w->dst = r->dev_buf;
         w->bounce = r->bounce_off >= 0 ? g_acx->heap + r->bounce_off : nullptr;
         w->cap = r->bytes;
@@ -1385,6 +1444,26 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             need.push_back({r, st});
         }
     }
+    // Wildcard receives: resolve + match (+ pull) kernel, then a single-entry wait that reads the resolution.
+    {
+        std::vector<Item> plain;
+        for (const Item &it : need) {
+            if (!it.r->wild) { plain.push_back(it); continue; }
+            const bool par = em.parallel;
+            em.parallel = false;   // the wait node must follow the resolver node
+            AnyParams ap;
+            fill_any(it.r, &ap);
+            rc = em.launch(recv_any_kernel, dim3(any_grid(it.r)), dim3(kMoverThreads), ap);
+            WaitBatch wb;
+            memset(&wb, 0, sizeof wb);
+            if (!rc) rc = fill_wait(it.r, it.st, retire, false, &wb.w[0]);
+            wb.wd = make_wd(); wb.tr = make_tr();
+            if (!rc) rc = em.launch(wait_kernel, dim3(1), dim3(kWaitThreads), wb);
+            em.parallel = par;
+            if (rc) return rc;
+        }
+        need.swap(plain);
+    }
     for (size_t base = 0; base < need.size(); base += kWaitBatch) {
         WaitBatch wb;
         memset(&wb, 0, sizeof wb);
@@ -1420,7 +1499,7 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
         for (AcxRequest *r : rs) {
             if (retire) { g_acx->slot_busy[r->slot] = 3; g_pending_retire.push_back(r->slot); }  // reclaimed once the device marks it retired
-            if (retire && r->kind == ACX_REQ_RECV && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
+            if (retire && r->kind == ACX_REQ_RECV && !r->wild && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
         }
     }
     for (int i = 0; i < count; i++) reqs[i] = MPIX_REQUEST_NULL;  // handle is consumed at enqueue time (reference: src/sendrecv.cu:430-432)
@@ -1471,6 +1550,13 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
             std::this_thread::yield();
         }
     } else {
+        if (r->wild) {   // resolve + match first (same internal stream, so the wait kernel below follows it)
+            AnyParams ap;
+            fill_any(r, &ap);
+            void *aargs[] = {&ap};
+            ACX_CUDA_WD(cudaLaunchKernel((const void *)recv_any_kernel, dim3(any_grid(r)), dim3(kMoverThreads), aargs, 0, g_acx->istream));
+            g_acx->st.kernels++;
+        }
         WaitBatch wb;
         memset(&wb, 0, sizeof wb);
         int rc = fill_wait(r, MPI_STATUS_IGNORE, false, true, &wb.w[0]);
@@ -1493,7 +1579,7 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
     }
     {
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
-        if (r->kind == ACX_REQ_RECV && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
+        if (r->kind == ACX_REQ_RECV && !r->wild && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
         acx_slot_free(r->slot);
     }
     *req = MPIX_REQUEST_NULL;

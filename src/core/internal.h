@@ -75,6 +75,13 @@ struct alignas(64) acx_op {  // per request slot, local
     uint64_t pad2;
 };
 
+struct acx_anyres {  // resolution of a wildcard receive (device memory, one per request slot): which ring the matched message sits in
+    acx_entry *ring;     // local ring of the matched (source, channel)
+    acx_sack *sack;      // peer-mapped acks at the matched sender
+    char *eager;         // local eager slots of that ring
+    int32_t src, pad;
+};
+
 struct acx_host_status {  // pinned host memory, one per request slot; written by wait kernels
     int32_t source, tag, error, retired;
     int64_t bytes;
@@ -131,6 +138,7 @@ struct AcxRequest {
     bool in_graph;
     bool host_transport;      // no-GPU mode: backed by an MPI_Request
     bool null_op;             // peer was MPI_PROC_NULL: completes immediately, moves nothing, owns no slot
+    bool wild;                // wildcard receive (MPI_ANY_SOURCE / MPI_ANY_TAG): matched by recv_any_kernel when the wait runs
     bool branched;            // ACX_PEER_BRANCH: all of this operation's kernels ran on the peer's side stream (the wait joins ev_done)
     MPI_Request mpi_req;
     MPI_Status *user_status;

@@ -202,8 +202,7 @@ struct RecvParams {
     TraceCtx tr;
 };
 
-__device__ __forceinline__ void recv_match(const RecvParams &p) {   // one thread
-    uint64_t k = atomicAdd((unsigned long long *)p.seq, 1ull);
+__device__ __forceinline__ void recv_match_at(const RecvParams &p, uint64_t k) {   // one thread; k = this receive's ticket
     uint32_t e = (uint32_t)(k % p.depth);
     uint64_t g = k / p.depth;
     acx_entry *ent = p.ring + e;
@@ -224,6 +223,10 @@ __device__ __forceinline__ void recv_match(const RecvParams &p) {   // one threa
     }
     st_release_sys(&p.op->armed, p.serial);
     trace(p.tr, ACX_EV_RECV_TRIGGER, p.peer, k, p.cap);
+}
+
+__device__ __forceinline__ void recv_match(const RecvParams &p) {   // one thread
+    recv_match_at(p, atomicAdd((unsigned long long *)p.seq, 1ull));
 }
 
 __global__ void recv_trigger(RecvParams p) {
@@ -371,6 +374,99 @@ __global__ void __launch_bounds__(kMoverThreads) recv_rndv_fused(RecvParams rp, 
 }
 
 // ---------------------------------------------------------------------------------------
+// Wildcard receive (MPI_ANY_SOURCE and/or MPI_ANY_TAG; experimental, ACX_WILDCARDS=1). Matching is deferred to the
+// WAIT: nothing runs when the receive is enqueued (so no kernel ever spins at Irecv time), and the wait emits this
+// kernel in front of the ordinary wait kernel. CTA 0 scans the candidate (source, channel) rings for the next
+// unclaimed ticket whose send has already arrived (and whose tag fits), claims that ticket with a CAS on the same
+// counter ordinary receives fetch-add, and from there behaves like an ordinary receive that arrived second: it
+// publishes its destination, and pulls if the message is a rendezvous. The resolved ring/ack/eager pointers and the
+// source are left in `res` for the wait kernel, whose own parameters cannot know them.
+// ---------------------------------------------------------------------------------------
+constexpr int kAnyMaxRanks = 64;
+struct AnyTable {   // device copy of the peer window bases (built on first wildcard use)
+    char *peer_ctrl[kAnyMaxRanks];
+    char *peer_heap[kAnyMaxRanks];
+};
+struct AnyParams {
+    const AnyTable *tbl;
+    char *ctrl;                 // my control window
+    acx_anyres *res;            // per-slot resolution record (device memory)
+    acx_op *op;
+    char *dst;                  // local landing address for a rendezvous pull (heap buffer or bounce)
+    uint64_t dst_off, cap, serial;
+    acx_geom geom;
+    int32_t src_lo, src_hi, chan_lo, chan_hi;   // inclusive candidate ranges
+    int32_t want_tag;           // MPI_ANY_TAG = any
+    uint32_t me, vec256, rndv_capable;
+    Watchdog wd;
+    TraceCtx tr;
+};
+
+__global__ void __launch_bounds__(kMoverThreads) recv_any_kernel(AnyParams p) {
+    pdl_prologue();
+    acx_op *op = p.op;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            const acx_geom &G = p.geom;
+            acx_entry *entries = (acx_entry *)(p.ctrl + G.off_entries);
+            uint64_t *seqs = (uint64_t *)(p.ctrl + G.off_recv_seq);
+            unsigned ns = 0;
+            const uint64_t t0 = p.wd.budget_ns ? globaltimer_ns() : 0;
+            int src = -1, chan = -1;
+            uint64_t k = 0;
+            for (;;) {
+                for (int s = p.src_lo; s <= p.src_hi && src < 0; s++) {
+                    for (int c = p.chan_lo; c <= p.chan_hi; c++) {
+                        uint64_t *seq = seqs + ((uint64_t)s * G.nchan + c);
+                        const uint64_t kk = ld_relaxed_sys(seq);
+                        const uint32_t e = (uint32_t)(kk % G.depth);
+                        const uint64_t g = kk / G.depth;
+                        acx_entry *ent = entries + acx_entry_index(G, s, c, e);
+                        if (ld_acquire_sys(&ent->consumed) < g) continue;                                   // my previous use of the slot is not finished
+                        if ((uint32_t)(ld_acquire_sys(&ent->state) >> 32) < (uint32_t)(g + 1)) continue;    // the send with ticket kk is not here yet
+                        if (p.want_tag != MPI_ANY_TAG && (int32_t)ent->s_tag != p.want_tag) continue;       // head of this channel carries another tag
+                        if (atomicCAS((unsigned long long *)seq, (unsigned long long)kk, (unsigned long long)(kk + 1)) != kk) continue;   // a concurrent receive took it
+                        src = s; chan = c; k = kk;
+                        break;
+                    }
+                }
+                if (src >= 0) break;
+                if (ns) __nanosleep(ns);
+                ns = ns < 1024 ? ns * 2 + 20 : 1024;
+                if (p.wd.budget_ns && globaltimer_ns() - t0 > p.wd.budget_ns) {
+                    p.wd.diag[1] = (uint64_t)(int64_t)p.src_lo; p.wd.diag[2] = (uint64_t)(int64_t)p.want_tag; p.wd.diag[0] = 0x5e0b;
+                    __threadfence_system();
+                    __trap();
+                }
+            }
+            const uint64_t ring_idx = acx_entry_index(G, src, chan, 0);
+            acx_sack *peer_sack = (acx_sack *)(p.tbl->peer_ctrl[src] + G.off_sack) + acx_entry_index(G, (int)p.me, chan, 0);
+            RecvParams rp;
+            rp.ring = entries + ring_idx;
+            rp.sack = p.rndv_capable ? peer_sack : nullptr;
+            rp.seq = nullptr;
+            rp.op = op;
+            rp.peer_heap = p.tbl->peer_heap[src];
+            rp.xlat = (const uint64_t *)(p.ctrl + G.off_xlat) + (uint64_t)src * G.maxreg;
+            rp.dst_off = p.dst_off; rp.cap = p.cap; rp.serial = p.serial; rp.depth = (uint32_t)G.depth; rp.peer = (uint32_t)src;
+            rp.wd = p.wd; rp.tr = p.tr;
+            p.res->ring = rp.ring; p.res->sack = peer_sack; p.res->eager = p.ctrl + G.off_eager + ring_idx * G.eager_max; p.res->src = src;
+            recv_match_at(rp, k);
+            __threadfence();
+            st_release_sys(&op->fused_decided, 1);
+        } else {
+            spin_geq(&op->fused_decided, 1, p.wd, 0x5e09);
+        }
+    }
+    __syncthreads();
+    MoverParams mp;
+    mp.op = op; mp.local = p.dst; mp.ring = p.res->ring; mp.sack = p.res->sack;
+    mp.depth = (uint32_t)p.geom.depth; mp.push = 0; mp.peer = (uint32_t)p.res->src; mp.vec256 = p.vec256; mp.block_bytes = 0; mp.pad1 = 0; mp.tr = p.tr;
+    mover_body(mp);
+    fused_exit(op);
+}
+
+// ---------------------------------------------------------------------------------------
 // TMA flavour of the mover (ACX_MOVER=tma): one elected thread per CTA drives a 4-stage ring of
 // 16-KiB bulk copies through shared memory — cp.async.bulk global->smem (mbarrier complete_tx),
 // then cp.async.bulk smem->global (bulk_group). The SM issues two instructions per 16 KiB instead
@@ -472,6 +568,7 @@ struct WaitOne {
     uint16_t is_recv, retire;
     uint16_t bounce_kernel, pad16;  // bounce_kernel: a bounce_out_kernel follows (large private destination)
     uint16_t off_source, off_tag, off_error, off_bytes;  // field offsets inside MPI_Status (0xffff = absent)
+    const acx_anyres *any;  // wildcard receive: ring / sack / eager / src come from here (written by recv_any_kernel)
 };
 struct WaitBatch {
     WaitOne w[kWaitBatch];
@@ -503,7 +600,7 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
             spin_geq(&w.sack[e].sdone, g + 1, b.wd, 0x5e03);
             s_n = 0; s_eager = 0;
         } else {
-            acx_entry *ent = w.ring + e;
+            acx_entry *ent = (w.any ? w.any->ring : w.ring) + e;
             // arrival: either an eager deposit (state.hi reached g+1 with kind EAGER) or mover done
             unsigned ns = 0;
             uint64_t t0 = b.wd.budget_ns ? globaltimer_ns() : 0;
@@ -526,26 +623,30 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
         const uint32_t e = (uint32_t)(k % w.depth);
         const uint64_t g = k / w.depth;
         const uint64_t n = s_n;
-        if (s_eager) copy_bytes(w.dst, w.eager + (uint64_t)e * w.eager_max, n, tid, blockDim.x);
+        acx_entry *const ring = w.any ? w.any->ring : w.ring;
+        acx_sack *const sack = w.any ? w.any->sack : w.sack;
+        const char *const eager = w.any ? w.any->eager : w.eager;
+        const int32_t src = w.any ? w.any->src : w.src;
+        if (s_eager) copy_bytes(w.dst, eager + (uint64_t)e * w.eager_max, n, tid, blockDim.x);
         else if (w.bounce && !w.bounce_kernel) copy_bytes(w.dst, w.bounce, n, tid, blockDim.x);
         __syncthreads();
         if (tid == 0) {
-            acx_entry *ent = w.ring + e;
+            acx_entry *ent = ring + e;
             const uint64_t sb = ent->s_bytes;
             const int32_t stag = (int32_t)ent->s_tag;
-            const int32_t err = (sb > w.cap) ? MPI_ERR_TRUNCATE : (stag != w.tag ? MPI_ERR_TAG : MPI_SUCCESS);
+            const int32_t err = (sb > w.cap) ? MPI_ERR_TRUNCATE : ((w.tag != MPI_ANY_TAG && stag != w.tag) ? MPI_ERR_TAG : MPI_SUCCESS);
             op->recv_bytes = n;
             op->bounce_n = (w.bounce && w.bounce_kernel && !s_eager) ? n : 0;
             if (w.ustatus) {
-                if (w.off_source != 0xffff) *(int32_t *)(w.ustatus + w.off_source) = w.src;
+                if (w.off_source != 0xffff) *(int32_t *)(w.ustatus + w.off_source) = src;
                 if (w.off_tag != 0xffff) *(int32_t *)(w.ustatus + w.off_tag) = stag;
                 if (w.off_error != 0xffff) *(int32_t *)(w.ustatus + w.off_error) = err;
                 if (w.off_bytes != 0xffff) *(int64_t *)(w.ustatus + w.off_bytes) = (int64_t)n;
             }
-            if (w.serial) { w.hstat->source = w.src; w.hstat->tag = stag; w.hstat->error = err; w.hstat->bytes = (int64_t)n; }
+            if (w.serial) { w.hstat->source = src; w.hstat->tag = stag; w.hstat->error = err; w.hstat->bytes = (int64_t)n; }
             // All reads of the slot are complete (data dependence + barrier): plain stores suffice.
             st_relaxed_sys(&ent->consumed, g + 1);
-            st_relaxed_sys(&w.sack[e].efree, g + 1);  // remote: slot may be reused by generation g+1
+            st_relaxed_sys(&sack[e].efree, g + 1);  // remote: slot may be reused by generation g+1
         }
     }
     if (tid == 0) {

@@ -12,6 +12,10 @@ run() { timeout 120 ./bin/acxrun -np $NP --timeout 100 "$@" 2>&1 | tail -n 2; }
 echo "### 1. new conformance program (PROC_NULL, communicator contexts, wildcard rejection)"
 for np in 1 $NP; do timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/procnull_comms 2>&1 | tail -n 3; done
 
+echo "### 1b. experimental device-side wildcards (ACX_WILDCARDS=1)"
+for np in 1 2 $NP; do ACX_WILDCARDS=1 timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/wildcards 2>&1 | tail -n 3; done
+timeout 60 ./bin/acxrun -np 2 --timeout 50 build/tests/wildcards 2>&1 | tail -n 1   # default: rejected cleanly
+
 echo "### 2. examples"
 make examples > /dev/null 2>&1
 for e in stream_ring partitioned_producer; do timeout 60 ./bin/acxrun -np $NP --timeout 50 build/examples/$e 2>&1 | tail -n $NP; done
