@@ -45,7 +45,9 @@ int MPIX_Finalize(void);
  * The transfer starts no earlier than the point where the call sits in the stream or graph; the
  * buffer must stay valid until a wait on the returned request has completed. MPI_PROC_NULL peers are
  * accepted (the operation completes at its wait, moving nothing); MPI_ANY_SOURCE / MPI_ANY_TAG receives
- * are honoured on the host transport and rejected (MPI_ERR_RANK / MPI_ERR_TAG) on the device transport. */
+ * are honoured on the host transport and rejected (MPI_ERR_RANK / MPI_ERR_TAG) on the device transport.
+ * `comm` may be any communicator made of MPI_COMM_WORLD members (dup, split, Cartesian); ranks and
+ * MPI_Status.MPI_SOURCE are in that communicator's rank space. */
 int MPIX_Isend_enqueue(const void *sendbuf, int nelems, MPI_Datatype dtype, int dst_rank, int tag, MPI_Comm comm, MPIX_Request *req_out, int queue_kind, void *queue_handle);
 int MPIX_Irecv_enqueue(void *recvbuf, int nelems, MPI_Datatype dtype, int src_rank, int tag, MPI_Comm comm, MPIX_Request *req_out, int queue_kind, void *queue_handle);
 

@@ -34,6 +34,7 @@ typedef int MPI_Datatype;
 typedef int MPI_Op;
 typedef int MPI_Info;
 typedef int MPI_Errhandler;
+typedef int MPI_Group;
 typedef long long MPI_Count;
 typedef long long MPI_Aint;
 typedef struct acx_mpi_request_s *MPI_Request;
@@ -48,6 +49,8 @@ typedef struct MPI_Status {
 #define MPI_COMM_NULL  ((MPI_Comm)0)
 #define MPI_COMM_WORLD ((MPI_Comm)1)
 #define MPI_COMM_SELF  ((MPI_Comm)2)
+#define MPI_GROUP_NULL  ((MPI_Group)0)
+#define MPI_GROUP_EMPTY ((MPI_Group)1)
 
 /* datatype handle = 0x100 | log-free encoding: low byte is the element size */
 #define ACX_DT(id, size) ((MPI_Datatype)(((id) << 8) | (size)))
@@ -144,6 +147,18 @@ int MPI_Comm_rank(MPI_Comm comm, int *rank);
 int MPI_Comm_size(MPI_Comm comm, int *size);
 int MPI_Comm_dup(MPI_Comm comm, MPI_Comm *newcomm);
 int MPI_Comm_free(MPI_Comm *comm);
+int MPI_Comm_split(MPI_Comm comm, int color, int key, MPI_Comm *newcomm);   /* color MPI_UNDEFINED -> MPI_COMM_NULL */
+int MPI_Comm_group(MPI_Comm comm, MPI_Group *group);
+int MPI_Group_size(MPI_Group group, int *size);
+int MPI_Group_rank(MPI_Group group, int *rank);
+int MPI_Group_translate_ranks(MPI_Group group1, int n, const int ranks1[], MPI_Group group2, int ranks2[]);
+int MPI_Group_free(MPI_Group *group);
+/* Cartesian topologies (reorder is accepted and ignored: ranks keep their order) */
+int MPI_Dims_create(int nnodes, int ndims, int dims[]);
+int MPI_Cart_create(MPI_Comm comm_old, int ndims, const int dims[], const int periods[], int reorder, MPI_Comm *comm_cart);
+int MPI_Cart_coords(MPI_Comm comm, int rank, int maxdims, int coords[]);
+int MPI_Cart_rank(MPI_Comm comm, const int coords[], int *rank);
+int MPI_Cart_shift(MPI_Comm comm, int direction, int disp, int *rank_source, int *rank_dest);
 int MPI_Type_size(MPI_Datatype datatype, int *size);
 int MPI_Get_count(const MPI_Status *status, MPI_Datatype datatype, int *count);
 

@@ -297,29 +297,43 @@ int acx_device_alias(const void *p, size_t bytes, char **out) {
     return 0;
 }
 
-int acx_comm_ctx(MPI_Comm comm, int *ctx) {
+int acx_comm_ctx(MPI_Comm comm, int *ctx, const AcxCommMap **map) {
     std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    for (size_t i = 0; i < g_acx->comms.size(); i++)
+        if (g_acx->comms[i].comm == comm) { *ctx = g_acx->comms[i].ctx; if (map) *map = &g_acx->comms[i]; return 0; }
+    AcxCommMap m;
+    m.comm = comm;
     // The context id feeds the channel hash and the partitioned handshake tag, so it must be the SAME number on
-    // both ends of a message. The bundled mini-MPI assigns communicator ids collectively (identical on every
-    // rank), so the id itself is used; with another MPI the order of first use is the only portable stand-in
-    // (ranks must then first-use their communicators in the same order).
-    auto id_of = [](MPI_Comm c, size_t index) {
+    // every member. The bundled mini-MPI agrees on communicator handles collectively (identical on all members),
+    // so the handle itself is used; with another MPI the order of first use is the only portable stand-in (ranks
+    // must then first-use their communicators in the same order).
 #ifdef ACX_MINI_MPI
-        (void)index;
-        return (int)c - (int)MPI_COMM_WORLD;
+    m.ctx = (int)comm - (int)MPI_COMM_WORLD;
 #else
-        (void)c;
-        return (int)index;
+    m.ctx = (int)g_acx->comms.size();
 #endif
-    };
-    for (size_t i = 0; i < g_acx->comms.size(); i++) if (g_acx->comms[i] == comm) { *ctx = id_of(comm, i); return 0; }
-    int sz = 0;
-    if (MPI_Comm_size(comm, &sz) != MPI_SUCCESS || sz != g_acx->size) {
-        ACX_ERR("only communicators spanning all of MPI_COMM_WORLD (in world rank order) are supported");
+    MPI_Group gc, gw;
+    if (MPI_Comm_size(comm, &m.size) != MPI_SUCCESS || MPI_Comm_rank(comm, &m.me) != MPI_SUCCESS || MPI_Comm_group(comm, &gc) != MPI_SUCCESS) {
+        ACX_ERR("invalid communicator");
         return MPI_ERR_COMM;
     }
-    g_acx->comms.push_back(comm);
-    *ctx = id_of(comm, g_acx->comms.size() - 1);
+    MPI_Comm_group(MPI_COMM_WORLD, &gw);
+    std::vector<int> mine((size_t)m.size);
+    for (int i = 0; i < m.size; i++) mine[i] = i;
+    m.to_world.assign((size_t)m.size, -1);
+    int rc = MPI_Group_translate_ranks(gc, m.size, mine.data(), gw, m.to_world.data());
+    MPI_Group_free(&gc); MPI_Group_free(&gw);
+    if (rc != MPI_SUCCESS) { ACX_ERR("cannot translate the communicator's ranks to MPI_COMM_WORLD"); return MPI_ERR_COMM; }
+    m.identity = m.size == g_acx->size;
+    for (int i = 0; i < m.size; i++) {
+        if (m.to_world[i] < 0 || m.to_world[i] >= g_acx->size) { ACX_ERR("communicator has a member outside MPI_COMM_WORLD"); return MPI_ERR_COMM; }
+        if (m.to_world[i] != i) m.identity = false;
+    }
+    g_acx->comms.reserve(64);   // callers keep pointers into this vector
+    if (g_acx->comms.size() >= 64 && g_acx->comms.size() == g_acx->comms.capacity()) { ACX_ERR("too many communicators"); return MPI_ERR_COMM; }
+    g_acx->comms.push_back(m);
+    *ctx = m.ctx;
+    if (map) *map = &g_acx->comms.back();
     return 0;
 }
 
@@ -509,7 +523,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_FAULT_DROP_SEND", nullptr, 0, &v); g_fault_drop_send = v;
     acx_env_int("ACX_MOVER_MAX_CTAS", nullptr, 0, &v); g_acx->mover_max_ctas = (int)v;
     acx_env_int("ACX_MOVER_CTA_BYTES", nullptr, 64 << 10, &v); g_acx->mover_min_cta_bytes = (size_t)std::max(4096L, v);
-    g_acx->comms.push_back(MPI_COMM_WORLD);
+    { int c0; if (acx_comm_ctx(MPI_COMM_WORLD, &c0)) return 1; }
     if (MPI_Comm_dup(MPI_COMM_WORLD, &g_acx->icomm) != MPI_SUCCESS) { ACX_ERR("MPI_Comm_dup failed"); return 1; }
 
     int ndev = 0;
@@ -1012,14 +1026,16 @@ static inline int chan_of(int tag, int ctx) { return (int)(((unsigned)tag + 7u *
 static AcxRequest *new_request(AcxReqKind kind, int peer, int tag, int ctx, size_t bytes, const void *buf) {
     AcxRequest *r = new AcxRequest();
     memset((void *)r, 0, sizeof *r);
-    r->magic = ACX_REQ_MAGIC; r->kind = kind; r->peer = peer; r->tag = tag; r->comm_ctx = ctx; r->bytes = bytes;
+    r->magic = ACX_REQ_MAGIC; r->kind = kind; r->peer = peer; r->comm_peer = peer; r->tag = tag; r->comm_ctx = ctx; r->bytes = bytes;
     r->user_buf = (void *)buf; r->bounce_off = -1; r->heap_off = -1; r->slot = -1; r->land_off = -1;
     r->serial = g_acx->serial++;
     r->mpi_req = MPI_REQUEST_NULL;
     return r;
 }
 
-static int check_common(const char *fn, bool is_recv, int count, MPI_Datatype dt, int peer, int tag, MPI_Comm comm, MPIX_Request *request, void *queue, size_t *bytes, int *ctx) {
+// Validates the arguments shared by the enqueue calls; *wpeer receives the peer's MPI_COMM_WORLD rank (wildcards and
+// MPI_PROC_NULL pass through unchanged).
+static int check_common(const char *fn, bool is_recv, int count, MPI_Datatype dt, int peer, int tag, MPI_Comm comm, MPIX_Request *request, void *queue, size_t *bytes, int *ctx, int *wpeer) {
     if (!g_acx || !g_acx->initialized) { fprintf(stderr, "[acx] %s: MPIX_Init has not been called\n", fn); return MPI_ERR_OTHER; }
     if (!request || !queue) { ACX_ERR("%s: null request/queue", fn); return MPI_ERR_ARG; }
     if (count < 0) { ACX_ERR("%s: negative count", fn); return MPI_ERR_COUNT; }
@@ -1027,8 +1043,17 @@ static int check_common(const char *fn, bool is_recv, int count, MPI_Datatype dt
     if (MPI_Type_size(dt, &sz) != MPI_SUCCESS || sz <= 0) { ACX_ERR("%s: invalid datatype", fn); return MPI_ERR_TYPE; }
     // MPI_PROC_NULL is valid everywhere. Wildcards (receive side only) are matched by the MPI library on the host
     // transport; the device transport pairs messages by (peer, channel) tickets and cannot honour them yet.
+    const AcxCommMap *cm = nullptr;
+    {
+        int rc = acx_comm_ctx(comm, ctx, &cm);
+        if (rc) return rc;
+    }
     const bool wild_ok = is_recv && (!g_acx->device || g_wild);
-    if (peer != MPI_PROC_NULL && !(wild_ok && peer == MPI_ANY_SOURCE) && (peer < 0 || peer >= g_acx->size)) {
+    if (peer == MPI_ANY_SOURCE && wild_ok && g_acx->device && !cm->identity) {
+        ACX_ERR("%s: MPI_ANY_SOURCE on the device transport is limited to communicators that span MPI_COMM_WORLD in order", fn);
+        return MPI_ERR_RANK;
+    }
+    if (peer != MPI_PROC_NULL && !(wild_ok && peer == MPI_ANY_SOURCE) && (peer < 0 || peer >= cm->size)) {
         ACX_ERR("%s: peer %d out of range%s", fn, peer, peer == MPI_ANY_SOURCE ? " (MPI_ANY_SOURCE on the device transport needs ACX_WILDCARDS=1)" : "");
         return MPI_ERR_RANK;
     }
@@ -1037,7 +1062,8 @@ static int check_common(const char *fn, bool is_recv, int count, MPI_Datatype dt
         return MPI_ERR_TAG;
     }
     *bytes = (size_t)count * (size_t)sz;
-    return acx_comm_ctx(comm, ctx);
+    *wpeer = peer >= 0 ? cm->to_world[(size_t)peer] : peer;
+    return 0;
 }
 
 // A send to / receive from MPI_PROC_NULL: nothing is enqueued and no slot is taken; the request completes at the
@@ -1120,10 +1146,11 @@ static int any_grid(const AcxRequest *r) {
 extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm, MPIX_Request *request,
                                   int qtype, void *queue) {
     AcxRange _r("MPIX_Isend_enqueue");
-    size_t bytes; int ctx;
-    int rc = check_common("MPIX_Isend_enqueue", false, count, datatype, dest, tag, comm, request, queue, &bytes, &ctx);
+    size_t bytes; int ctx, wdest;
+    int rc = check_common("MPIX_Isend_enqueue", false, count, datatype, dest, tag, comm, request, queue, &bytes, &ctx, &wdest);
     if (rc) return rc;
-    AcxRequest *r = new_request(ACX_REQ_SEND, dest, tag, ctx, bytes, buf);
+    AcxRequest *r = new_request(ACX_REQ_SEND, wdest, tag, ctx, bytes, buf);
+    r->comm_peer = dest;
     if (!g_acx->device) {
         if (qtype != MPIX_QUEUE_CUDA_STREAM) { ACX_ERR("graph queues need a GPU"); delete r; return MPI_ERR_OTHER; }
         r->host_transport = true;
@@ -1134,6 +1161,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         return MPI_SUCCESS;
     }
     if (dest == MPI_PROC_NULL) return make_null_op(r, qtype, queue, request);
+    dest = wdest;   // from here on: the world rank (windows, rings and side streams are indexed by it)
     Emitter em;
     BranchScope branch(em, r);
     if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
@@ -1217,10 +1245,11 @@ fail:
 extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPIX_Request *request, int qtype,
                                   void *queue) {
     AcxRange _r("MPIX_Irecv_enqueue");
-    size_t bytes; int ctx;
-    int rc = check_common("MPIX_Irecv_enqueue", true, count, datatype, source, tag, comm, request, queue, &bytes, &ctx);
+    size_t bytes; int ctx, wsource;
+    int rc = check_common("MPIX_Irecv_enqueue", true, count, datatype, source, tag, comm, request, queue, &bytes, &ctx, &wsource);
     if (rc) return rc;
-    AcxRequest *r = new_request(ACX_REQ_RECV, source, tag, ctx, bytes, buf);
+    AcxRequest *r = new_request(ACX_REQ_RECV, wsource, tag, ctx, bytes, buf);
+    r->comm_peer = source;
     if (!g_acx->device) {
         if (qtype != MPIX_QUEUE_CUDA_STREAM) { ACX_ERR("graph queues need a GPU"); delete r; return MPI_ERR_OTHER; }
         r->host_transport = true;
@@ -1231,6 +1260,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         return MPI_SUCCESS;
     }
     if (source == MPI_PROC_NULL) return make_null_op(r, qtype, queue, request);
+    source = wsource;   // world rank from here on
     Emitter em;
     BranchScope branch(em, r);
     if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
@@ -1336,7 +1366,7 @@ static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_w
     w->depth = G.depth; w->eager_max = G.eager_max;
     w->serial = host_wait ? r->serial : 0;
     w->retire = retire ? 1 : 0;
-    w->src = r->peer; w->tag = r->tag;
+    w->src = r->comm_peer; w->tag = r->tag;   // status reports the peer in the caller's communicator
     w->off_source = w->off_tag = w->off_error = w->off_bytes = 0xffff;
     if (r->kind == ACX_REQ_SEND) {
         w->is_recv = 0;
@@ -1372,7 +1402,7 @@ static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_w
 
 static void host_status_send(MPI_Status *st, AcxRequest *r) {
     if (st == MPI_STATUS_IGNORE) return;
-    st->MPI_SOURCE = r->peer; st->MPI_TAG = r->tag; st->MPI_ERROR = MPI_SUCCESS;
+    st->MPI_SOURCE = r->comm_peer; st->MPI_TAG = r->tag; st->MPI_ERROR = MPI_SUCCESS;
 #ifdef ACX_MINI_MPI
     st->_bytes = 0;
 #endif
@@ -1630,21 +1660,26 @@ static int pinit_common(AcxReqKind kind, const void *buf, int partitions, MPI_Co
     if (partitions <= 0) { ACX_ERR("partitions must be > 0"); return MPI_ERR_COUNT; }
     int sz = 0, ctx = 0;
     if (MPI_Type_size(dt, &sz) != MPI_SUCCESS || sz <= 0) return MPI_ERR_TYPE;
-    if (peer < 0 || peer >= g_acx->size) return MPI_ERR_RANK;
     if (tag < 0) return MPI_ERR_TAG;
-    int rc = acx_comm_ctx(comm, &ctx);
+    const AcxCommMap *cm = nullptr;
+    int rc = acx_comm_ctx(comm, &ctx, &cm);
     if (rc) return rc;
+    if (peer < 0 || peer >= cm->size) return MPI_ERR_RANK;
+    const int cpeer = peer;                 // as named by the caller (host transport, status)
+    const int wpeer = cm->to_world[(size_t)peer];
     size_t part_bytes = (size_t)count * (size_t)sz;
-    AcxRequest *r = new_request(kind, peer, tag, ctx, part_bytes * partitions, buf);
+    AcxRequest *r = new_request(kind, wpeer, tag, ctx, part_bytes * partitions, buf);
+    r->comm_peer = cpeer;
     r->partitions = partitions; r->part_bytes = part_bytes;
     if (!g_acx->device) {
         r->host_transport = true;
-        rc = kind == ACX_REQ_PSEND ? MPI_Psend_init(buf, partitions, count, dt, peer, tag, comm, MPI_INFO_NULL, &r->mpi_req)
-                                   : MPI_Precv_init((void *)buf, partitions, count, dt, peer, tag, comm, MPI_INFO_NULL, &r->mpi_req);
+        rc = kind == ACX_REQ_PSEND ? MPI_Psend_init(buf, partitions, count, dt, cpeer, tag, comm, MPI_INFO_NULL, &r->mpi_req)
+                                   : MPI_Precv_init((void *)buf, partitions, count, dt, cpeer, tag, comm, MPI_INFO_NULL, &r->mpi_req);
         if (rc) { delete r; return rc; }
         *request = r;
         return MPI_SUCCESS;
     }
+    peer = wpeer;   // device transport: world rank from here on (the handshake runs on a dup of MPI_COMM_WORLD)
     if ((rc = acx_device_alias(buf, r->bytes, &r->dev_buf))) { delete r; return rc; }
     PHandshake *hs = new PHandshake();
     memset(hs, 0, sizeof *hs);
@@ -1811,7 +1846,7 @@ static int pwait_host(AcxRequest *r, MPI_Status *status) {
     if (rc) return rc;
     ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
     if (status != MPI_STATUS_IGNORE) {
-        status->MPI_SOURCE = r->peer; status->MPI_TAG = r->tag; status->MPI_ERROR = MPI_SUCCESS;
+        status->MPI_SOURCE = r->comm_peer; status->MPI_TAG = r->tag; status->MPI_ERROR = MPI_SUCCESS;
 #ifdef ACX_MINI_MPI
         status->_bytes = r->kind == ACX_REQ_PRECV ? (long long)r->bytes : 0;
 #endif

@@ -126,7 +126,8 @@ struct AcxGraphRes;  // resources owned by a CUDA graph (released by its user ob
 struct AcxRequest {
     uint32_t magic;
     AcxReqKind kind;
-    int peer, tag, comm_ctx, chan;
+    int peer, tag, comm_ctx, chan;   // peer: WORLD rank (indexes windows/rings)
+    int comm_peer;            // the peer as the caller named it (rank in the operation's communicator): what MPI_Status reports
     int slot;                 // op slot (basic) / -1
     uint64_t serial;
     size_t bytes;             // message bytes (send) / capacity (recv)
@@ -162,6 +163,16 @@ struct AcxRequest {
 
 struct AcxHostReg { uintptr_t lo, hi; char *dptr; };
 
+// A communicator the library has seen: its matching context and the translation between its ranks and COMM_WORLD's
+// (all windows, rings and side streams are indexed by world rank; the API speaks communicator ranks).
+struct AcxCommMap {
+    MPI_Comm comm;
+    int ctx;                    // same number on every member (see acx_comm_ctx)
+    int size, me;
+    bool identity;              // every world rank, in world order
+    std::vector<int> to_world;  // comm rank -> world rank
+};
+
 struct AcxState {
     bool initialized = false;
     bool device = false;      // GPU transport active
@@ -185,7 +196,7 @@ struct AcxState {
     std::unordered_map<size_t, size_t> heap_used;  // offset -> size
     uint32_t pflags_next = 0;
     std::vector<AcxHostReg> host_regs;
-    std::vector<MPI_Comm> comms;             // known communicators; index = context id
+    std::vector<AcxCommMap> comms;           // known communicators (context id + rank translation)
     MPI_Comm icomm;                          // private dup of COMM_WORLD for handshakes
     uint64_t serial = 1;
     std::vector<std::vector<int>> recv_outstanding;  // [src][chan] posted-not-yet-waited recvs
@@ -243,7 +254,7 @@ int64_t acx_heap_offset_of(const void *p);  // -1 if not inside my heap
 uint32_t acx_pflags_alloc(uint32_t n);
 // Device-accessible alias of an arbitrary user pointer (host memory gets pinned+mapped).
 int acx_device_alias(const void *p, size_t bytes, char **out);
-int acx_comm_ctx(MPI_Comm comm, int *ctx);
+int acx_comm_ctx(MPI_Comm comm, int *ctx, const AcxCommMap **map = nullptr);
 int acx_env_int(const char *name, const char *alt, long dflt, long *out);
 
 // layout helpers

@@ -14,6 +14,7 @@
 //
 // All CUDA use is optional and resolved at run time (dlopen of libcudart) so the same
 // library serves GPU-less CI.
+#include <algorithm>
 #include <mpi.h>
 
 #include <atomic>
@@ -206,8 +207,20 @@ struct State {
     Seg seg;
     uint32_t my_sense = 0;
     int next_comm = 16;
-    std::unordered_map<int, int> comm_ctx;  // dup'ed communicators -> context id
+    int next_group = 16;
 };
+// A communicator: matching context + ordered member list (world ranks). Handles are small integers agreed on by all
+// members when the communicator is created (max over the members' private counters), so a handle doubles as a
+// job-wide context id: libacx hashes it into its channel index.
+struct CommInfo {
+    int ctx = 0;
+    std::vector<int> ranks;      // comm rank -> world rank
+    int me = 0;                  // my rank in this communicator
+    bool world_like = false;     // all of COMM_WORLD in world order: collectives take the shared-memory fast path
+    std::vector<int> dims, periods;   // Cartesian topology (empty: none)
+};
+std::unordered_map<int, CommInfo> g_comms;
+std::unordered_map<int, std::vector<int>> g_groups;   // group handle -> world ranks
 State g;
 std::recursive_mutex g_mu;
 
@@ -329,6 +342,7 @@ struct acx_mpi_request_s {
     void *buf;
     size_t bytes;       // send: message bytes; recv: capacity
     int peer, tag, comm, part;
+    int cid = 1;        // communicator handle (status.MPI_SOURCE is reported in its rank space)
     bool done = false, active = true, persistent = false, freed = false;
     MPI_Status st{};
     // send progress
@@ -584,11 +598,31 @@ void progress() {
 
 size_t dt_size(MPI_Datatype dt) { return (size_t)(dt & 0xff); }
 
-int ctx_of(MPI_Comm c) {
-    if (c == MPI_COMM_WORLD) return 1;
-    if (c == MPI_COMM_SELF) return 2;
-    auto it = g.comm_ctx.find(c);
-    return it == g.comm_ctx.end() ? -1 : it->second;
+CommInfo *comm_of(MPI_Comm c) {
+    auto it = g_comms.find(c);
+    return it == g_comms.end() ? nullptr : &it->second;
+}
+// comm rank -> world rank (wildcard / PROC_NULL pass through); -1000 = out of range
+int to_world(const CommInfo *ci, int r) {
+    if (r == MPI_PROC_NULL || r == MPI_ANY_SOURCE) return r;
+    if (r < 0 || r >= (int)ci->ranks.size()) return -1000;
+    return ci->ranks[r];
+}
+int from_world(const CommInfo *ci, int w) {
+    if (w < 0 || !ci) return w;
+    if (ci->world_like) return w;
+    for (size_t i = 0; i < ci->ranks.size(); i++) if (ci->ranks[i] == w) return (int)i;
+    return w;
+}
+void register_comm(int id, int ctx, const std::vector<int> &ranks) {
+    CommInfo ci;
+    ci.ctx = ctx; ci.ranks = ranks;
+    ci.world_like = (int)ranks.size() == g.size;
+    for (size_t i = 0; i < ranks.size(); i++) {
+        if (ranks[i] == g.rank) ci.me = (int)i;
+        if (ranks[i] != (int)i) ci.world_like = false;
+    }
+    g_comms[id] = ci;
 }
 
 Req *post_send(const void *buf, size_t bytes, int dest, int tag, int comm, int part) {
@@ -698,6 +732,43 @@ void atexit_cleanup() {
     if (g.initialized && g.rank == 0 && !g.seg.name.empty()) shm_unlink(g.seg.name.c_str());
 }
 
+// Collectives on communicators that are not "all of COMM_WORLD in order" cannot use the job-wide shared-memory barrier;
+// they run over point-to-point messages in a reserved context (linear fan-in/fan-out through comm rank 0: these
+// communicators are small, and nothing here is on a data path).
+constexpr int kCollCtx = 0x20000000;
+void coll_send(const CommInfo &ci, int dst, const void *buf, size_t n, int tag) {
+    Req *q = post_send(buf, n, ci.ranks[dst], tag, ci.ctx | kCollCtx, -1);
+    wait_req(q);
+    delete q;
+}
+void coll_recv(const CommInfo &ci, int src, void *buf, size_t n, int tag) {
+    Req *q = post_recv(buf, n, ci.ranks[src], tag, ci.ctx | kCollCtx, -1);
+    wait_req(q);
+    delete q;
+}
+void sub_bcast(const CommInfo &ci, void *buf, size_t bytes, int root, int tag) {
+    const int n = (int)ci.ranks.size();
+    if (ci.me == root) { for (int r = 0; r < n; r++) if (r != root) coll_send(ci, r, buf, bytes, tag); }
+    else coll_recv(ci, root, buf, bytes, tag);
+}
+void sub_barrier(const CommInfo &ci) {
+    const int n = (int)ci.ranks.size();
+    char b = 0;
+    if (ci.me == 0) { for (int r = 1; r < n; r++) coll_recv(ci, r, &b, 1, 1); }
+    else coll_send(ci, 0, &b, 1, 1);
+    sub_bcast(ci, &b, 1, 0, 2);
+}
+void sub_allgather(const CommInfo &ci, const void *mine, void *all, size_t bytes) {
+    const int n = (int)ci.ranks.size();
+    if (ci.me == 0) {
+        if (mine != all) memmove(all, mine, bytes);
+        for (int r = 1; r < n; r++) coll_recv(ci, r, (char *)all + bytes * r, bytes, 3);
+    } else {
+        coll_send(ci, 0, mine, bytes, 3);
+    }
+    sub_bcast(ci, all, bytes * n, 0, 4);
+}
+
 #define LOCK std::lock_guard<std::recursive_mutex> _lk(g_mu)
 
 }  // namespace
@@ -728,6 +799,12 @@ int MPI_Init_thread(int *, char ***, int required, int *provided) {
     g_sendq.assign(g.size, {});
     g_cur_in.assign(g.size, nullptr);
     g_cur_req.assign(g.size, nullptr);
+    {
+        std::vector<int> all(g.size);
+        for (int i = 0; i < g.size; i++) all[i] = i;
+        register_comm(MPI_COMM_WORLD, 1, all);
+        register_comm(MPI_COMM_SELF, 2, std::vector<int>(1, g.rank));
+    }
     g.thread_level = MPI_THREAD_MULTIPLE;
     (void)required;
     if (provided) *provided = MPI_THREAD_MULTIPLE;
@@ -812,25 +889,192 @@ int MPI_Get_processor_name(char *name, int *len) {
 }
 
 int MPI_Comm_rank(MPI_Comm c, int *rank) {
-    if (ctx_of(c) < 0) return MPI_ERR_COMM;
-    *rank = c == MPI_COMM_SELF ? 0 : g.rank;
+    LOCK;
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    *rank = ci->me;
     return MPI_SUCCESS;
 }
 int MPI_Comm_size(MPI_Comm c, int *size) {
-    if (ctx_of(c) < 0) return MPI_ERR_COMM;
-    *size = c == MPI_COMM_SELF ? 1 : g.size;
+    LOCK;
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    *size = (int)ci->ranks.size();
     return MPI_SUCCESS;
 }
+
+// Handle for a communicator being created collectively over `parent`: the maximum of the members' private counters,
+// so every member (and therefore both ends of any message on the new communicator) uses the same number.
+static int agree_comm_id(MPI_Comm parent) {
+    int id = g.next_comm;
+    MPI_Allreduce(MPI_IN_PLACE, &id, 1, MPI_INT, MPI_MAX, parent);
+    g.next_comm = id + 1;
+    return id;
+}
+
 int MPI_Comm_dup(MPI_Comm c, MPI_Comm *out) {
     LOCK;
-    if (ctx_of(c) < 0) return MPI_ERR_COMM;
-    // Collective by convention: every rank dups in the same order, so ids agree.
-    int id = g.next_comm++;
-    g.comm_ctx[id] = c == MPI_COMM_SELF ? -id : id;
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    const int id = agree_comm_id(c);
+    CommInfo copy = *comm_of(c);
+    copy.ctx = id;
+    g_comms[id] = copy;
     *out = id;
     return MPI_SUCCESS;
 }
-int MPI_Comm_free(MPI_Comm *c) { LOCK; g.comm_ctx.erase(*c); *c = MPI_COMM_NULL; return MPI_SUCCESS; }
+
+int MPI_Comm_split(MPI_Comm c, int color, int key, MPI_Comm *out) {
+    LOCK;
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    const int n = (int)ci->ranks.size();
+    int mine[2] = {color, key};
+    std::vector<int> all(2 * (size_t)n);
+    MPI_Allgather(mine, 2, MPI_INT, all.data(), 2, MPI_INT, c);
+    const int id = agree_comm_id(c);
+    if (color == MPI_UNDEFINED) { *out = MPI_COMM_NULL; return MPI_SUCCESS; }
+    ci = comm_of(c);
+    std::vector<std::pair<std::pair<int, int>, int>> members;   // ((key, parent rank), world rank)
+    for (int r = 0; r < n; r++) if (all[2 * r] == color) members.push_back({{all[2 * r + 1], r}, ci->ranks[r]});
+    std::sort(members.begin(), members.end());
+    std::vector<int> ranks;
+    for (auto &m : members) ranks.push_back(m.second);
+    register_comm(id, id, ranks);
+    *out = id;
+    return MPI_SUCCESS;
+}
+
+int MPI_Comm_free(MPI_Comm *c) {
+    LOCK;
+    if (*c != MPI_COMM_WORLD && *c != MPI_COMM_SELF) g_comms.erase(*c);
+    *c = MPI_COMM_NULL;
+    return MPI_SUCCESS;
+}
+
+int MPI_Comm_group(MPI_Comm c, MPI_Group *group) {
+    LOCK;
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    int id = g.next_group++;
+    g_groups[id] = ci->ranks;
+    *group = id;
+    return MPI_SUCCESS;
+}
+int MPI_Group_size(MPI_Group group, int *size) {
+    LOCK;
+    if (group == MPI_GROUP_EMPTY) { *size = 0; return MPI_SUCCESS; }
+    auto it = g_groups.find(group);
+    if (it == g_groups.end()) return MPI_ERR_ARG;
+    *size = (int)it->second.size();
+    return MPI_SUCCESS;
+}
+int MPI_Group_rank(MPI_Group group, int *rank) {
+    LOCK;
+    *rank = MPI_UNDEFINED;
+    auto it = g_groups.find(group);
+    if (it == g_groups.end()) return group == MPI_GROUP_EMPTY ? MPI_SUCCESS : MPI_ERR_ARG;
+    for (size_t i = 0; i < it->second.size(); i++) if (it->second[i] == g.rank) *rank = (int)i;
+    return MPI_SUCCESS;
+}
+int MPI_Group_translate_ranks(MPI_Group g1, int n, const int r1[], MPI_Group g2, int r2[]) {
+    LOCK;
+    auto a = g_groups.find(g1), b = g_groups.find(g2);
+    if (a == g_groups.end() || b == g_groups.end()) return MPI_ERR_ARG;
+    for (int i = 0; i < n; i++) {
+        r2[i] = MPI_UNDEFINED;
+        if (r1[i] == MPI_PROC_NULL) { r2[i] = MPI_PROC_NULL; continue; }
+        if (r1[i] < 0 || r1[i] >= (int)a->second.size()) return MPI_ERR_RANK;
+        const int w = a->second[r1[i]];
+        for (size_t j = 0; j < b->second.size(); j++) if (b->second[j] == w) { r2[i] = (int)j; break; }
+    }
+    return MPI_SUCCESS;
+}
+int MPI_Group_free(MPI_Group *group) {
+    LOCK;
+    g_groups.erase(*group);
+    *group = MPI_GROUP_NULL;
+    return MPI_SUCCESS;
+}
+
+// ---- Cartesian topologies ------------------------------------------------------------
+int MPI_Dims_create(int nnodes, int ndims, int dims[]) {
+    if (nnodes <= 0 || ndims <= 0) return MPI_ERR_ARG;
+    int fixed = 1, free_dims = 0;
+    for (int i = 0; i < ndims; i++) { if (dims[i] < 0) return MPI_ERR_ARG; if (dims[i] > 0) fixed *= dims[i]; else free_dims++; }
+    if (nnodes % fixed) return MPI_ERR_ARG;
+    int rest = nnodes / fixed;
+    std::vector<int> f(free_dims > 0 ? free_dims : 0, 1);
+    // distribute prime factors, largest first, always onto the currently smallest dimension: as square as possible
+    std::vector<int> primes;
+    for (int p = 2; p * p <= rest; p++) while (rest % p == 0) { primes.push_back(p); rest /= p; }
+    if (rest > 1) primes.push_back(rest);
+    if (free_dims == 0) return primes.empty() ? MPI_SUCCESS : MPI_ERR_ARG;
+    std::sort(primes.rbegin(), primes.rend());
+    for (int p : primes) *std::min_element(f.begin(), f.end()) *= p;
+    std::sort(f.rbegin(), f.rend());   // non-increasing order, as the standard asks
+    int k = 0;
+    for (int i = 0; i < ndims; i++) if (dims[i] == 0) dims[i] = f[k++];
+    return MPI_SUCCESS;
+}
+int MPI_Cart_create(MPI_Comm c, int ndims, const int dims[], const int periods[], int, MPI_Comm *out) {
+    LOCK;
+    CommInfo *ci = comm_of(c);
+    if (!ci || ndims <= 0) return MPI_ERR_COMM;
+    int total = 1;
+    for (int i = 0; i < ndims; i++) total *= dims[i];
+    if (total > (int)ci->ranks.size()) return MPI_ERR_ARG;
+    // ranks beyond the grid get MPI_COMM_NULL (split keeps parent order, i.e. row-major coordinates)
+    MPI_Comm nc;
+    int e = MPI_Comm_split(c, ci->me < total ? 0 : MPI_UNDEFINED, ci->me, &nc);
+    if (e) return e;
+    if (nc != MPI_COMM_NULL) {
+        CommInfo *ni = comm_of(nc);
+        ni->dims.assign(dims, dims + ndims);
+        ni->periods.assign(periods, periods + ndims);
+    }
+    *out = nc;
+    return MPI_SUCCESS;
+}
+int MPI_Cart_coords(MPI_Comm c, int rank, int maxdims, int coords[]) {
+    LOCK;
+    CommInfo *ci = comm_of(c);
+    if (!ci || ci->dims.empty()) return MPI_ERR_COMM;
+    if (rank < 0 || rank >= (int)ci->ranks.size()) return MPI_ERR_RANK;
+    const int nd = (int)ci->dims.size();
+    for (int i = nd - 1; i >= 0; i--) { if (i < maxdims) coords[i] = rank % ci->dims[i]; rank /= ci->dims[i]; }
+    return MPI_SUCCESS;
+}
+int MPI_Cart_rank(MPI_Comm c, const int coords[], int *rank) {
+    LOCK;
+    CommInfo *ci = comm_of(c);
+    if (!ci || ci->dims.empty()) return MPI_ERR_COMM;
+    int r = 0;
+    for (size_t i = 0; i < ci->dims.size(); i++) {
+        int x = coords[i];
+        if (ci->periods[i]) x = ((x % ci->dims[i]) + ci->dims[i]) % ci->dims[i];
+        else if (x < 0 || x >= ci->dims[i]) return MPI_ERR_RANK;
+        r = r * ci->dims[i] + x;
+    }
+    *rank = r;
+    return MPI_SUCCESS;
+}
+int MPI_Cart_shift(MPI_Comm c, int direction, int disp, int *src, int *dst) {
+    LOCK;
+    CommInfo *ci = comm_of(c);
+    if (!ci || ci->dims.empty() || direction < 0 || direction >= (int)ci->dims.size()) return MPI_ERR_COMM;
+    std::vector<int> me(ci->dims.size());
+    MPI_Cart_coords(c, ci->me, (int)me.size(), me.data());
+    auto at = [&](int delta) {
+        std::vector<int> x = me;
+        x[direction] += delta;
+        int r;
+        return MPI_Cart_rank(c, x.data(), &r) == MPI_SUCCESS ? r : MPI_PROC_NULL;
+    };
+    *src = at(-disp);
+    *dst = at(disp);
+    return MPI_SUCCESS;
+}
 
 int MPI_Type_size(MPI_Datatype dt, int *size) { *size = (int)dt_size(dt); return *size ? MPI_SUCCESS : MPI_ERR_TYPE; }
 int MPI_Get_count(const MPI_Status *st, MPI_Datatype dt, int *count) {
@@ -842,8 +1086,11 @@ int MPI_Get_count(const MPI_Status *st, MPI_Datatype dt, int *count) {
 
 int MPI_Barrier(MPI_Comm c) {
     LOCK;
-    if (c == MPI_COMM_SELF || g.size == 1) return MPI_SUCCESS;
-    shm_barrier();
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    if (ci->ranks.size() == 1) return MPI_SUCCESS;
+    if (ci->world_like) shm_barrier();
+    else { CommInfo snap = *ci; sub_barrier(snap); }
     return MPI_SUCCESS;
 }
 
@@ -864,9 +1111,17 @@ const char *ACX_Mpi_jobid(void) { return g.jobid.c_str(); }
 int MPI_Allgather(const void *sb, int sc, MPI_Datatype sdt, void *rb, int rc, MPI_Datatype rdt, MPI_Comm c) {
     LOCK;
     size_t sbytes = (size_t)sc * dt_size(sdt), rbytes = (size_t)rc * dt_size(rdt);
-    if (c == MPI_COMM_SELF || g.size == 1) { if (sb != MPI_IN_PLACE) memcpy(rb, sb, sbytes); return MPI_SUCCESS; }
-    const char *src = sb == MPI_IN_PLACE ? (char *)rb + rbytes * g.rank : (const char *)sb;
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    if (ci->ranks.size() == 1) { if (sb != MPI_IN_PLACE) memcpy(rb, sb, sbytes); return MPI_SUCCESS; }
+    const char *src = sb == MPI_IN_PLACE ? (char *)rb + rbytes * ci->me : (const char *)sb;
     std::vector<char> mine(src, src + rbytes);
+    if (!ci->world_like) {
+        CommInfo snap = *ci;
+        if (snap.me == 0) memcpy(rb, mine.data(), rbytes);
+        sub_allgather(snap, snap.me == 0 ? rb : (void *)mine.data(), rb, rbytes);
+        return MPI_SUCCESS;
+    }
     for (size_t off = 0; off < rbytes; off += kBlobBytes) {
         size_t n = rbytes - off < kBlobBytes ? rbytes - off : kBlobBytes;
         std::vector<char> tmp(n * g.size);
@@ -880,7 +1135,21 @@ int MPI_Allreduce(const void *sb, void *rb, int count, MPI_Datatype dt, MPI_Op o
     LOCK;
     size_t es = dt_size(dt), bytes = es * (size_t)count;
     if (sb != MPI_IN_PLACE) memcpy(rb, sb, bytes);
-    if (c == MPI_COMM_SELF || g.size == 1) return MPI_SUCCESS;
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    if (ci->ranks.size() == 1) return MPI_SUCCESS;
+    if (!ci->world_like) {
+        CommInfo snap = *ci;
+        const int n = (int)snap.ranks.size();
+        if (snap.me == 0) {
+            std::vector<char> in(bytes);
+            for (int r = 1; r < n; r++) { coll_recv(snap, r, in.data(), bytes, 5); reduce_into(rb, in.data(), count, dt, op); }
+        } else {
+            coll_send(snap, 0, rb, bytes, 5);
+        }
+        sub_bcast(snap, rb, bytes, 0, 6);
+        return MPI_SUCCESS;
+    }
     int per = (int)(kBlobBytes / es);
     std::vector<char> tmp(kBlobBytes * g.size);
     for (int off = 0; off < count; off += per) {
@@ -904,8 +1173,12 @@ int MPI_Reduce(const void *sb, void *rb, int count, MPI_Datatype dt, MPI_Op op, 
 
 int MPI_Bcast(void *buf, int count, MPI_Datatype dt, int root, MPI_Comm c) {
     LOCK;
-    if (c == MPI_COMM_SELF || g.size == 1) return MPI_SUCCESS;
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    if (ci->ranks.size() == 1) return MPI_SUCCESS;
     size_t bytes = dt_size(dt) * (size_t)count;
+    if (root < 0 || root >= (int)ci->ranks.size()) return MPI_ERR_RANK;
+    if (!ci->world_like) { CommInfo snap = *ci; sub_bcast(snap, buf, bytes, root, 7); return MPI_SUCCESS; }
     std::vector<char> tmp(kBlobBytes * g.size);
     for (size_t off = 0; off < bytes; off += kBlobBytes) {
         size_t n = bytes - off < kBlobBytes ? bytes - off : kBlobBytes;
@@ -917,28 +1190,31 @@ int MPI_Bcast(void *buf, int count, MPI_Datatype dt, int root, MPI_Comm c) {
 
 int MPI_Isend(const void *buf, int count, MPI_Datatype dt, int dest, int tag, MPI_Comm c, MPI_Request *req) {
     LOCK;
-    int ctx = ctx_of(c);
-    if (ctx < 0) return MPI_ERR_COMM;
-    if (c == MPI_COMM_SELF && dest == 0) dest = g.rank;
-    if (dest != MPI_PROC_NULL && (dest < 0 || dest >= g.size)) return MPI_ERR_RANK;
-    *req = post_send(buf, dt_size(dt) * (size_t)count, dest, tag, ctx, -1);
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    if (dest == MPI_ANY_SOURCE || (dest = to_world(ci, dest)) == -1000) return MPI_ERR_RANK;
+    *req = post_send(buf, dt_size(dt) * (size_t)count, dest, tag, ci->ctx, -1);
+    (*req)->cid = c;
     return MPI_SUCCESS;
 }
 
 int MPI_Irecv(void *buf, int count, MPI_Datatype dt, int src, int tag, MPI_Comm c, MPI_Request *req) {
     LOCK;
-    int ctx = ctx_of(c);
-    if (ctx < 0) return MPI_ERR_COMM;
-    if (c == MPI_COMM_SELF && src == 0) src = g.rank;
-    if (src != MPI_PROC_NULL && src != MPI_ANY_SOURCE && (src < 0 || src >= g.size)) return MPI_ERR_RANK;
-    *req = post_recv(buf, dt_size(dt) * (size_t)count, src, tag, ctx, -1);
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    if ((src = to_world(ci, src)) == -1000) return MPI_ERR_RANK;
+    *req = post_recv(buf, dt_size(dt) * (size_t)count, src, tag, ci->ctx, -1);
+    (*req)->cid = c;
     progress();
     return MPI_SUCCESS;
 }
 
 static void finish_req(MPI_Request *req, MPI_Status *st) {
     Req *r = *req;
-    if (st) *st = r->st;
+    if (st) {
+        *st = r->st;
+        if (st->MPI_SOURCE >= 0) st->MPI_SOURCE = from_world(comm_of(r->cid), st->MPI_SOURCE);   // report in the communicator's rank space
+    }
     if (r->persistent) { r->active = false; return; }
     delete r;
     *req = MPI_REQUEST_NULL;
@@ -1042,10 +1318,13 @@ int MPI_Request_free(MPI_Request *req) {
 static int pinit(ReqKind k, void *buf, int partitions, MPI_Count count, MPI_Datatype dt, int peer, int tag, MPI_Comm c,
                  MPI_Request *req) {
     LOCK;
-    int ctx = ctx_of(c);
-    if (ctx < 0) return MPI_ERR_COMM;
+    CommInfo *ci = comm_of(c);
+    if (!ci) return MPI_ERR_COMM;
+    const int ctx = ci->ctx;
     if (partitions <= 0 || count < 0) return MPI_ERR_COUNT;
+    if (peer == MPI_ANY_SOURCE || (peer = to_world(ci, peer)) == -1000) return MPI_ERR_RANK;
     Req *r = new Req();
+    r->cid = c;
     r->kind = k; r->buf = buf; r->partitions = partitions; r->part_bytes = dt_size(dt) * (size_t)count;
     r->bytes = r->part_bytes * partitions; r->peer = peer; r->tag = tag; r->comm = ctx | 0x40000000; r->part = -1;
     r->persistent = true; r->active = false; r->done = false;

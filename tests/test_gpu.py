@@ -189,3 +189,13 @@ def test_proc_null_and_communicator_contexts(built, np_):
     r = acxrun(built, np_, built / "build/tests/procnull_comms")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [2, 4])
+def test_sub_communicators(built, np_):
+    """Ring, rendezvous and partitioned exchanges inside MPI_Comm_split halves (reverse rank order) and on a Cartesian
+    communicator: peers are translated to world ranks, statuses report communicator ranks (tests/c/subcomm.c).
+    np=4 shares one GPU between ranks when fewer devices are present."""
+    r = acxrun(built, np_, built / "build/tests/subcomm")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout

@@ -18,13 +18,20 @@ def test_minimpi_smoke(built, np_):
     assert "PASS" in r.stdout
 
 
+@pytest.mark.parametrize("np_", [1, 2, 4, 7])
+def test_minimpi_subcommunicators(built, np_):
+    """MPI_Comm_split / groups / Cartesian topologies and collectives on sub-communicators (tests/c/minimpi_comms.c)."""
+    r = acxrun(built, np_, built / "build/tests/minimpi_comms")
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("np_", [1, 2, 3])
 def test_minimpi_thread_multiple(built, np_):
     r = acxrun(built, np_, built / "build/tests/minimpi_threads")
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("prog", ["ring", "ring_all", "procnull_comms", "wildcards"])
+@pytest.mark.parametrize("prog", ["ring", "ring_all", "procnull_comms", "wildcards", "subcomm"])
 @pytest.mark.parametrize("np_", [1, 2, 3])
 def test_ring_host_transport(built, prog, np_):
     r = acxrun(built, np_, built / f"build/tests/{prog}", env={"ACX_FORCE_HOST": "1"})
