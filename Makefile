@@ -63,18 +63,19 @@ examples: $(LIB)
 clean:
 	rm -rf $(B) lib bin
 
+SAN_CXX ?= $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 # ThreadSanitizer build of the mini-MPI + its threaded test (host-side race detection; the reference has none)
 tsan:
 	@mkdir -p $(B)
-	$(CXX) -O1 -g -fsanitize=thread -std=c++17 -Iinclude -c src/minimpi/minimpi.cpp -o $(B)/minimpi_tsan.o
+	$(SAN_CXX) -O1 -g -fsanitize=thread -std=c++17 -Iinclude -c src/minimpi/minimpi.cpp -o $(B)/minimpi_tsan.o
 	gcc -O1 -g -fsanitize=thread -Iinclude -c tests/c/minimpi_threads.c -o $(B)/mt_tsan.o
-	$(CXX) -fsanitize=thread $(B)/mt_tsan.o $(B)/minimpi_tsan.o -o $(B)/tests/minimpi_threads_tsan -ldl -lpthread -lrt
+	$(SAN_CXX) -fsanitize=thread $(B)/mt_tsan.o $(B)/minimpi_tsan.o -o $(B)/tests/minimpi_threads_tsan -ldl -lpthread -lrt
 	bin/acxrun -np 2 --timeout 100 $(B)/tests/minimpi_threads_tsan
 
 # AddressSanitizer + UBSan build of the host side (mini-MPI + runtime front-ends on the host transport)
 asan:
 	@mkdir -p $(B)/asan
-	$(CXX) -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -std=c++17 -fPIC -Iinclude -c src/minimpi/minimpi.cpp -o $(B)/asan/minimpi.o
+	$(SAN_CXX) -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -std=c++17 -fPIC -Iinclude -c src/minimpi/minimpi.cpp -o $(B)/asan/minimpi.o
 	$(NVCC) $(GENCODE) -O1 -std=c++17 -Xcompiler -fPIC,-fsanitize=address,-fno-omit-frame-pointer -Iinclude -c src/core/acx.cu -o $(B)/asan/acx.o
-	$(NVCC) $(GENCODE) -shared -o $(B)/asan/libacx_asan.so $(B)/asan/acx.o $(B)/asan/minimpi.o -cudart static -ldl -lpthread -lrt -Xcompiler -fsanitize=address,undefined
-	for t in ring ring_all minimpi_smoke; do gcc -O1 -g -fsanitize=address,undefined -Iinclude -I/usr/local/cuda/include tests/c/$$t.c -o $(B)/asan/$$t -L$(B)/asan -lacx_asan -Wl,-rpath,$(CURDIR)/$(B)/asan -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,/usr/local/cuda/lib64 && ASAN_OPTIONS=detect_leaks=0 ACX_FORCE_HOST=1 bin/acxrun -np 3 --timeout 100 $(B)/asan/$$t || exit 1; done
+	$(NVCC) $(GENCODE) -shared -o $(B)/asan/libacx_asan.so $(B)/asan/acx.o $(B)/asan/minimpi.o -cudart static -ldl -lpthread -lrt -Xcompiler -fsanitize=address -Xcompiler -fsanitize=undefined
+	for t in ring ring_all minimpi_smoke minimpi_comms procnull_comms wildcards subcomm; do gcc -O1 -g -fsanitize=address,undefined -Iinclude -I/usr/local/cuda/include tests/c/$$t.c -o $(B)/asan/$$t -L$(B)/asan -lacx_asan -Wl,-rpath,$(CURDIR)/$(B)/asan -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,/usr/local/cuda/lib64 && ASAN_OPTIONS=detect_leaks=0 ACX_FORCE_HOST=1 bin/acxrun -np 3 --timeout 100 $(B)/asan/$$t || exit 1; done
