@@ -78,4 +78,4 @@ asan:
 	$(SAN_CXX) -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -std=c++17 -fPIC -Iinclude -c src/minimpi/minimpi.cpp -o $(B)/asan/minimpi.o
 	$(NVCC) $(GENCODE) -O1 -std=c++17 -Xcompiler -fPIC,-fsanitize=address,-fno-omit-frame-pointer -Iinclude -c src/core/acx.cu -o $(B)/asan/acx.o
 	$(NVCC) $(GENCODE) -shared -o $(B)/asan/libacx_asan.so $(B)/asan/acx.o $(B)/asan/minimpi.o -cudart static -ldl -lpthread -lrt -Xcompiler -fsanitize=address -Xcompiler -fsanitize=undefined
-	for t in ring ring_all minimpi_smoke minimpi_comms procnull_comms wildcards subcomm; do gcc -O1 -g -fsanitize=address,undefined -Iinclude -I/usr/local/cuda/include tests/c/$$t.c -o $(B)/asan/$$t -L$(B)/asan -lacx_asan -Wl,-rpath,$(CURDIR)/$(B)/asan -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,/usr/local/cuda/lib64 && ASAN_OPTIONS=detect_leaks=0 ACX_FORCE_HOST=1 bin/acxrun -np 3 --timeout 100 $(B)/asan/$$t || exit 1; done
+	for t in ring ring_all minimpi_smoke minimpi_comms minimpi_types procnull_comms wildcards subcomm datatypes; do gcc -O1 -g -fsanitize=address,undefined -Iinclude -I/usr/local/cuda/include tests/c/$$t.c -o $(B)/asan/$$t -L$(B)/asan -lacx_asan -Wl,-rpath,$(CURDIR)/$(B)/asan -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,/usr/local/cuda/lib64 && ASAN_OPTIONS=detect_leaks=0 ACX_FORCE_HOST=1 bin/acxrun -np 3 --timeout 100 $(B)/asan/$$t || exit 1; done

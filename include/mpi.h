@@ -86,6 +86,11 @@ typedef struct MPI_Status {
 #define MPIX_FLOAT16      ACX_DT(27, 2)
 #define MPIX_FLOAT8_E4M3  ACX_DT(28, 1)
 
+/* derived datatypes: handles >= ACX_DT_DERIVED_BASE index a per-process table */
+#define ACX_DT_DERIVED_BASE 0x100000
+#define MPI_ORDER_C       56
+#define MPI_ORDER_FORTRAN 57
+
 #define MPI_OP_NULL ((MPI_Op)0)
 #define MPI_SUM  ((MPI_Op)1)
 #define MPI_MAX  ((MPI_Op)2)
@@ -161,6 +166,17 @@ int MPI_Cart_rank(MPI_Comm comm, const int coords[], int *rank);
 int MPI_Cart_shift(MPI_Comm comm, int direction, int disp, int *rank_source, int *rank_dest);
 int MPI_Type_size(MPI_Datatype datatype, int *size);
 int MPI_Get_count(const MPI_Status *status, MPI_Datatype datatype, int *count);
+/* Derived datatypes (the regular strided layouts halo exchanges use). Any of these may be nested as long as the result
+ * is expressible as <= 3 strided dimensions around one contiguous run. */
+int MPI_Type_contiguous(int count, MPI_Datatype oldtype, MPI_Datatype *newtype);
+int MPI_Type_vector(int count, int blocklength, int stride, MPI_Datatype oldtype, MPI_Datatype *newtype);
+int MPI_Type_create_hvector(int count, int blocklength, MPI_Aint stride_bytes, MPI_Datatype oldtype, MPI_Datatype *newtype);
+int MPI_Type_create_subarray(int ndims, const int sizes[], const int subsizes[], const int starts[], int order,
+                             MPI_Datatype oldtype, MPI_Datatype *newtype);
+int MPI_Type_commit(MPI_Datatype *datatype);
+int MPI_Type_free(MPI_Datatype *datatype);
+int MPI_Type_get_extent(MPI_Datatype datatype, MPI_Aint *lb, MPI_Aint *extent);
+int MPI_Pack_size(int incount, MPI_Datatype datatype, MPI_Comm comm, int *size);
 
 int MPI_Barrier(MPI_Comm comm);
 int MPI_Bcast(void *buf, int count, MPI_Datatype dt, int root, MPI_Comm comm);
@@ -200,6 +216,15 @@ int  ACX_Mpi_exchange(const void *mine, void *all, size_t bytes_per_rank);
 /* Raw pointer + size of a per-job shared scratch area libacx may carve up
  * (channel directories, registration tables). Zero-initialised at job start. */
 void *ACX_Mpi_shared_scratch(size_t *bytes);
+/* Memory layout of a datatype in canonical form, for layers that move the bytes themselves (libacx's pack/unpack
+ * kernels): element (i2,i1,i0) of one item starts at  disp + i2*stride[2] + i1*stride[1] + i0*stride[0]  and is `run`
+ * contiguous bytes; consecutive items of a count>1 transfer are `extent` bytes apart. Unused dimensions have n = 1. */
+typedef struct ACX_Mpi_layout {
+    long long n[3], stride[3];
+    long long run, disp, extent, size;   /* size: packed bytes of one item = n[0]*n[1]*n[2]*run */
+    int contiguous;                      /* 1: one item is a single run of `size` bytes starting at `disp` and extent == size */
+} ACX_Mpi_layout;
+int ACX_Mpi_type_layout(MPI_Datatype datatype, ACX_Mpi_layout *layout);
 /* Called once at the start of MPI_Abort (diagnostics of layered libraries). */
 void ACX_Mpi_set_abort_hook(void (*fn)(void));
 

@@ -1033,9 +1033,44 @@ static AcxRequest *new_request(AcxReqKind kind, int peer, int tag, int ctx, size
     return r;
 }
 
+// Layout of `count` items of `dt`. Contiguous types (the common case) come back with noncontig = false and are moved
+// as count x size bytes; strided ones (vector / subarray / nestings, as halo faces are) are packed / unpacked by kernels.
+static int describe_type(const char *fn, MPI_Datatype dt, int count, int sz, AcxLayout *out) {
+    memset(out, 0, sizeof *out);
+    out->n[0] = out->n[1] = out->n[2] = 1;
+    out->run = sz; out->extent = sz; out->count = count; out->span = (long long)count * sz;
+#ifdef ACX_MINI_MPI
+    ACX_Mpi_layout L;
+    if (ACX_Mpi_type_layout(dt, &L) != MPI_SUCCESS) { ACX_ERR("%s: invalid datatype", fn); return MPI_ERR_TYPE; }
+    if (L.contiguous && L.disp == 0) return 0;
+    long long reach = L.disp + L.run;
+    for (int d = 0; d < 3; d++) {
+        if (L.stride[d] < 0) { ACX_ERR("%s: datatypes with negative strides are not supported", fn); return MPI_ERR_TYPE; }
+        out->n[d] = L.n[d]; out->stride[d] = L.stride[d];
+        reach += (L.n[d] - 1) * L.stride[d];
+    }
+    if (L.disp < 0 || L.extent < 0) { ACX_ERR("%s: datatypes with negative displacement/extent are not supported", fn); return MPI_ERR_TYPE; }
+    out->run = L.run; out->disp = L.disp; out->extent = L.extent;
+    out->span = count > 0 ? (long long)(count - 1) * L.extent + reach : 0;
+    out->noncontig = true;
+    return 0;
+#else
+    MPI_Aint lb = 0, ext = 0;
+    if (MPI_Type_get_extent(dt, &lb, &ext) != MPI_SUCCESS || lb != 0 || ext != (MPI_Aint)sz) {
+        ACX_ERR("%s: non-contiguous datatypes need the bundled MPI (layout introspection); pack the buffer first", fn);
+        return MPI_ERR_TYPE;
+    }
+    return 0;
+#endif
+}
+static int pack_grid(size_t bytes, uint32_t vec) {
+    size_t units = bytes / vec, ctas = (units + 256 * 8 - 1) / (256 * 8);   // ~8 units per thread
+    return (int)std::max<size_t>(1, std::min<size_t>(ctas, (size_t)4 * g_acx->sm_count));
+}
+
 // Validates the arguments shared by the enqueue calls; *wpeer receives the peer's MPI_COMM_WORLD rank (wildcards and
 // MPI_PROC_NULL pass through unchanged).
-static int check_common(const char *fn, bool is_recv, int count, MPI_Datatype dt, int peer, int tag, MPI_Comm comm, MPIX_Request *request, void *queue, size_t *bytes, int *ctx, int *wpeer) {
+static int check_common(const char *fn, bool is_recv, int count, MPI_Datatype dt, int peer, int tag, MPI_Comm comm, MPIX_Request *request, void *queue, size_t *bytes, int *ctx, int *wpeer, AcxLayout *ty) {
     if (!g_acx || !g_acx->initialized) { fprintf(stderr, "[acx] %s: MPIX_Init has not been called\n", fn); return MPI_ERR_OTHER; }
     if (!request || !queue) { ACX_ERR("%s: null request/queue", fn); return MPI_ERR_ARG; }
     if (count < 0) { ACX_ERR("%s: negative count", fn); return MPI_ERR_COUNT; }
@@ -1063,7 +1098,7 @@ static int check_common(const char *fn, bool is_recv, int count, MPI_Datatype dt
     }
     *bytes = (size_t)count * (size_t)sz;
     *wpeer = peer >= 0 ? cm->to_world[(size_t)peer] : peer;
-    return 0;
+    return describe_type(fn, dt, count, sz, ty);
 }
 
 // A send to / receive from MPI_PROC_NULL: nothing is enqueued and no slot is taken; the request completes at the
@@ -1147,7 +1182,8 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
                                   int qtype, void *queue) {
     AcxRange _r("MPIX_Isend_enqueue");
     size_t bytes; int ctx, wdest;
-    int rc = check_common("MPIX_Isend_enqueue", false, count, datatype, dest, tag, comm, request, queue, &bytes, &ctx, &wdest);
+    AcxLayout ty;
+    int rc = check_common("MPIX_Isend_enqueue", false, count, datatype, dest, tag, comm, request, queue, &bytes, &ctx, &wdest, &ty);
     if (rc) return rc;
     AcxRequest *r = new_request(ACX_REQ_SEND, wdest, tag, ctx, bytes, buf);
     r->comm_peer = dest;
@@ -1168,14 +1204,25 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
     r->in_graph = em.in_graph();
     r->chan = chan_of(tag, ctx);
     if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
-    if ((rc = acx_device_alias(buf, bytes, &r->dev_buf))) goto fail;
+    if ((rc = acx_device_alias(buf, ty.noncontig ? (size_t)ty.span : bytes, &r->dev_buf))) goto fail;
     if ((rc = branch.begin())) goto fail;
     {
         const acx_geom &G = g_acx->geom;
         const bool eager = bytes <= G.eager_max;
         uint64_t src_off = ~0ull;
         const char *src_local = r->dev_buf;
-        if (!eager) {
+        if (ty.noncontig && bytes > 0) {
+            // strided layout: gather it into a heap staging buffer, which then travels like any contiguous heap buffer
+            r->typed = true; r->layout = ty;
+            if ((r->bounce_off = acx_heap_alloc(bytes)) < 0) { rc = MPI_ERR_OTHER; goto fail; }
+            PackParams pp;
+            memset(&pp, 0, sizeof pp);
+            pp.packed = g_acx->heap + r->bounce_off; pp.user = r->dev_buf; pp.L = acx_device_layout(ty, r->dev_buf, pp.packed);
+            if ((rc = em.launch(pack_kernel, dim3(pack_grid(bytes, pp.L.vec)), dim3(256), pp))) goto fail;
+            src_off = (uint64_t)r->bounce_off;
+            src_local = pp.packed;
+            r->heap_off = -1;
+        } else if (!eager) {
             reg_progress();
             r->heap_off = acx_heap_offset_of(buf);
             uint64_t enc = ~0ull;
@@ -1200,7 +1247,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         sp.seq = (uint64_t *)(g_acx->ctrl + G.off_send_seq) + ((uint64_t)dest * G.nchan + r->chan);
         sp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
         sp.hstat = (eager && !r->in_graph) ? g_acx->hstat_d + r->slot : nullptr;
-        sp.src = r->dev_buf;
+        sp.src = src_local;   // eager payload source: the user's buffer, or the packed image of a strided one
         sp.peer_heap = g_acx->peer_heap[dest];
         sp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)dest * G.maxreg;
         sp.src_off = src_off; sp.bytes = bytes; sp.serial = r->serial;
@@ -1246,7 +1293,8 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
                                   void *queue) {
     AcxRange _r("MPIX_Irecv_enqueue");
     size_t bytes; int ctx, wsource;
-    int rc = check_common("MPIX_Irecv_enqueue", true, count, datatype, source, tag, comm, request, queue, &bytes, &ctx, &wsource);
+    AcxLayout ty;
+    int rc = check_common("MPIX_Irecv_enqueue", true, count, datatype, source, tag, comm, request, queue, &bytes, &ctx, &wsource, &ty);
     if (rc) return rc;
     AcxRequest *r = new_request(ACX_REQ_RECV, wsource, tag, ctx, bytes, buf);
     r->comm_peer = source;
@@ -1267,6 +1315,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
     r->in_graph = em.in_graph();
     if (source == MPI_ANY_SOURCE || tag == MPI_ANY_TAG) {
         // Wildcard: nothing is launched now; the wait resolves, matches and (for a rendezvous message) pulls.
+        if (ty.noncontig) { ACX_ERR("wildcard receives with non-contiguous datatypes are not supported on the device transport"); if (qtype == MPIX_QUEUE_CUDA_GRAPH) cudaGraphDestroy(em.graph); delete r; return MPI_ERR_TYPE; }
         r->wild = true; r->chan = -1;
         if ((rc = any_tables())) { if (qtype == MPIX_QUEUE_CUDA_GRAPH) cudaGraphDestroy(em.graph); delete r; return rc; }
         if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { if (qtype == MPIX_QUEUE_CUDA_GRAPH) cudaGraphDestroy(em.graph); delete r; return MPI_ERR_OTHER; }
@@ -1291,7 +1340,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         g_acx->recv_outstanding[source][r->chan]++;
     }
     if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
-    if ((rc = acx_device_alias(buf, bytes, &r->dev_buf))) goto fail;
+    if ((rc = acx_device_alias(buf, ty.noncontig ? (size_t)ty.span : bytes, &r->dev_buf))) goto fail;
     if ((rc = branch.begin())) goto fail;
     {
         const acx_geom &G = g_acx->geom;
@@ -1301,7 +1350,14 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         r->heap_off = acx_heap_offset_of(buf);
         uint64_t enc = ~0ull;
         if (rndv_capable) reg_progress();
-        if (r->heap_off >= 0) dst_off = (uint64_t)r->heap_off;
+        if (ty.noncontig && bytes > 0) {
+            // strided destination: the packed image lands in a heap staging buffer; unpack_kernel scatters it after the wait
+            r->typed = true; r->layout = ty; r->heap_off = -1;
+            if ((r->bounce_off = acx_heap_alloc(bytes)) < 0) { rc = MPI_ERR_OTHER; goto fail; }
+            dst_off = (uint64_t)r->bounce_off;
+            dst_local = g_acx->heap + r->bounce_off;
+            g_acx->st.bounce++;
+        } else if (r->heap_off >= 0) dst_off = (uint64_t)r->heap_off;
         else if (rndv_capable && (enc = reg_encode(buf, bytes, source)) != ~0ull) dst_off = enc;   // registered: zero-copy
         else if (rndv_capable) {
             if ((r->bounce_off = acx_heap_alloc(bytes)) < 0) { rc = MPI_ERR_OTHER; goto fail; }
@@ -1383,6 +1439,7 @@ static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_w
         }
         w->dst = r->dev_buf;
         w->bounce = r->bounce_off >= 0 ? g_acx->heap + r->bounce_off : nullptr;
+        if (r->typed) { w->dst = w->bounce; w->bounce = nullptr; }   // eager payloads are copied into the staging buffer too; unpack_kernel does the rest
         w->cap = r->bytes;
         if (status != MPI_STATUS_IGNORE && !host_wait) {
             char *ds = nullptr;
@@ -1406,6 +1463,14 @@ static void host_status_send(MPI_Status *st, AcxRequest *r) {
 #ifdef ACX_MINI_MPI
     st->_bytes = 0;
 #endif
+}
+
+static void fill_unpack(AcxRequest *r, bool retire, UnpackParams *up) {
+    memset(up, 0, sizeof *up);
+    up->op = (acx_op *)(g_acx->ctrl + g_acx->geom.off_ops) + r->slot;
+    up->user = r->dev_buf; up->packed = g_acx->heap + r->bounce_off; up->hstat = g_acx->hstat_d + r->slot;
+    up->L = acx_device_layout(r->layout, r->dev_buf, up->packed);
+    up->retire = retire ? 1 : 0;
 }
 
 static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses, int qtype, void *queue) {
@@ -1498,17 +1563,29 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
         WaitBatch wb;
         memset(&wb, 0, sizeof wb);
         int n = (int)std::min((size_t)kWaitBatch, need.size() - base);
-        std::vector<AcxRequest *> bounced;
+        std::vector<AcxRequest *> bounced, typed;
         for (int j = 0; j < n; j++) {
             AcxRequest *r = need[base + j].r;
             // Large private destinations: copy-out at full width by a follow-up kernel, which then retires.
-            const bool big_bounce = r->kind == ACX_REQ_RECV && r->bounce_off >= 0 && r->bytes > (256u << 10);
-            if ((rc = fill_wait(r, need[base + j].st, retire && !big_bounce, false, &wb.w[j]))) return rc;
+            // Strided destinations: unpack_kernel scatters the staged image, then retires.
+            const bool is_typed = r->kind == ACX_REQ_RECV && r->typed;
+            const bool big_bounce = !is_typed && r->kind == ACX_REQ_RECV && r->bounce_off >= 0 && r->bytes > (256u << 10);
+            if ((rc = fill_wait(r, need[base + j].st, retire && !big_bounce && !is_typed, false, &wb.w[j]))) return rc;
             wb.w[j].bounce_kernel = big_bounce ? 1 : 0;
             if (big_bounce) bounced.push_back(r);
+            if (is_typed) typed.push_back(r);
         }
         wb.wd = make_wd(); wb.tr = make_tr();
         if ((rc = em.launch(wait_kernel, dim3(n), dim3(kWaitThreads), wb))) return rc;
+        for (AcxRequest *r : typed) {
+            UnpackParams up;
+            fill_unpack(r, retire, &up);
+            const bool par = em.parallel;
+            em.parallel = false;  // must follow the wait node
+            rc = em.launch(unpack_kernel, dim3(pack_grid(r->bytes, up.L.vec)), dim3(256), up);
+            em.parallel = par;
+            if (rc) return rc;
+        }
         for (AcxRequest *r : bounced) {
             BounceOutParams bp;
             memset(&bp, 0, sizeof bp);
@@ -1595,6 +1672,13 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
         void *args[] = {&wb};
         ACX_CUDA_WD(cudaLaunchKernel((const void *)wait_kernel, dim3(1), dim3(kWaitThreads), args, 0, g_acx->istream));
         g_acx->st.kernels++;
+        if (r->kind == ACX_REQ_RECV && r->typed) {   // strided destination: scatter the staged image
+            UnpackParams up;
+            fill_unpack(r, false, &up);
+            void *uargs[] = {&up};
+            ACX_CUDA_WD(cudaLaunchKernel((const void *)unpack_kernel, dim3(pack_grid(r->bytes, up.L.vec)), dim3(256), uargs, 0, g_acx->istream));
+            g_acx->st.kernels++;
+        }
         ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
     }
     if (status != MPI_STATUS_IGNORE) {
@@ -1664,6 +1748,11 @@ static int pinit_common(AcxReqKind kind, const void *buf, int partitions, MPI_Co
     const AcxCommMap *cm = nullptr;
     int rc = acx_comm_ctx(comm, &ctx, &cm);
     if (rc) return rc;
+    {
+        AcxLayout ty;
+        if ((rc = describe_type("MPIX_Psend/Precv_init", dt, (int)count, sz, &ty))) return rc;
+        if (ty.noncontig) { ACX_ERR("partitioned operations take contiguous datatypes (a partition is a byte range of the buffer)"); return MPI_ERR_TYPE; }
+    }
     if (peer < 0 || peer >= cm->size) return MPI_ERR_RANK;
     const int cpeer = peer;                 // as named by the caller (host transport, status)
     const int wpeer = cm->to_world[(size_t)peer];

@@ -110,6 +110,28 @@ struct acx_geom {
 #endif
 ACX_HDI uint64_t acx_entry_index(const acx_geom &g, int src, int chan, int e) { return ((uint64_t)src * g.nchan + chan) * g.depth + e; }
 
+// Strided datatype layout as the pack / unpack kernels consume it. Work is split in `vec`-byte units (the widest power of
+// two <= 16 dividing the run, every stride in use and both base addresses); unit j of the packed image belongs at
+// acx_layout_unit_offset(L, j) bytes from the user's buffer address.
+struct TypeLayout {
+    long long n[3], stride[3];
+    long long run, disp, extent, count;
+    uint32_t vec, pad;
+};
+ACX_HDI uint64_t acx_layout_units(const TypeLayout &L, uint64_t limit_bytes) {
+    const uint64_t units = (uint64_t)(L.count * L.n[2] * L.n[1] * L.n[0]) * ((uint64_t)L.run / L.vec);
+    return units * L.vec > limit_bytes ? limit_bytes / L.vec : units;
+}
+ACX_HDI long long acx_layout_unit_offset(const TypeLayout &L, uint64_t j) {
+    const uint64_t upr = (uint64_t)L.run / L.vec;   // units per contiguous run
+    uint64_t r = j / upr;
+    const uint64_t within = (j - r * upr) * L.vec;
+    const uint64_t i0 = r % (uint64_t)L.n[0]; r /= (uint64_t)L.n[0];
+    const uint64_t i1 = r % (uint64_t)L.n[1]; r /= (uint64_t)L.n[1];
+    const uint64_t i2 = r % (uint64_t)L.n[2]; r /= (uint64_t)L.n[2];
+    return (long long)r * L.extent + L.disp + (long long)i2 * L.stride[2] + (long long)i1 * L.stride[1] + (long long)i0 * L.stride[0] + (long long)within;
+}
+
 // ---- host-side state -------------------------------------------------------------------
 #ifdef __cplusplus
 #include <atomic>
@@ -120,6 +142,28 @@ ACX_HDI uint64_t acx_entry_index(const acx_geom &g, int src, int chan, int e) { 
 #include <vector>
 
 enum AcxReqKind { ACX_REQ_SEND = 1, ACX_REQ_RECV = 2, ACX_REQ_PSEND = 3, ACX_REQ_PRECV = 4 };
+
+// Datatype layout in canonical form (see ACX_Mpi_layout in the bundled mpi.h): element (c,i2,i1,i0) is `run` contiguous
+// bytes at c*extent + disp + i2*stride[2] + i1*stride[1] + i0*stride[0].
+struct AcxLayout {
+    long long n[3], stride[3];
+    long long run, disp, extent, count;
+    long long span;           // bytes of user memory touched, measured from the buffer address
+    bool noncontig;
+};
+
+inline TypeLayout acx_device_layout(const AcxLayout &a, const void *user, const void *packed) {
+    TypeLayout t{};
+    for (int d = 0; d < 3; d++) { t.n[d] = a.n[d]; t.stride[d] = a.stride[d]; }
+    t.run = a.run; t.disp = a.disp; t.extent = a.extent; t.count = a.count;
+    unsigned long long bits = (unsigned long long)a.run | (unsigned long long)a.disp | (uintptr_t)user | (uintptr_t)packed;
+    for (int d = 0; d < 3; d++) if (a.n[d] > 1) bits |= (unsigned long long)a.stride[d];
+    if (a.count > 1) bits |= (unsigned long long)a.extent;
+    uint32_t vec = 16;
+    while (vec > 1 && (bits & (vec - 1))) vec >>= 1;
+    t.vec = vec;
+    return t;
+}
 
 struct AcxGraphRes;  // resources owned by a CUDA graph (released by its user object)
 
@@ -139,6 +183,8 @@ struct AcxRequest {
     bool in_graph;
     bool host_transport;      // no-GPU mode: backed by an MPI_Request
     bool null_op;             // peer was MPI_PROC_NULL: completes immediately, moves nothing, owns no slot
+    bool typed;               // non-contiguous datatype: the wire image is staged in the heap (bounce_off), packed before the send / unpacked after the wait
+    AcxLayout layout;
     bool wild;                // wildcard receive (MPI_ANY_SOURCE / MPI_ANY_TAG): matched by recv_any_kernel when the wait runs
     bool branched;            // ACX_PEER_BRANCH: all of this operation's kernels ran on the peer's side stream (the wait joins ev_done)
     MPI_Request mpi_req;

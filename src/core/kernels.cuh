@@ -678,6 +678,60 @@ __global__ void __launch_bounds__(kMoverThreads) bounce_out_kernel(BounceOutPara
 }
 
 // ---------------------------------------------------------------------------------------
+// Non-contiguous datatypes (vector / subarray layouts, e.g. halo faces): the wire format is the packed image.
+// Send: pack_kernel gathers the user's strided layout into a heap staging buffer, which then travels like any
+// contiguous heap buffer. Receive: the message lands (eager copy-out or rendezvous mover) in a heap staging buffer and
+// unpack_kernel, launched behind the wait kernel, scatters it; its last CTA retires the slot.
+// Element (c, i2, i1, i0) of the layout is `run` contiguous bytes at  c*extent + disp + i2*s2 + i1*s1 + i0*s0.
+// Work is split in `vec`-byte units (the widest power of two <= 16 that divides run, strides and both base addresses).
+// ---------------------------------------------------------------------------------------
+template <bool kPack>
+__device__ __forceinline__ void pack_unpack_body(char *packed, char *user, const TypeLayout &L, uint64_t limit) {
+    const uint64_t units = acx_layout_units(L, limit);                  // short message: only what arrived
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < units; j += (uint64_t)gridDim.x * blockDim.x) {
+        char *u = user + acx_layout_unit_offset(L, j);
+        char *p = packed + j * L.vec;
+        char *d = kPack ? p : u;
+        const char *s = kPack ? u : p;
+        switch (L.vec) {
+            case 16: *(int4 *)d = *(const int4 *)s; break;
+            case 8: *(int2 *)d = *(const int2 *)s; break;
+            case 4: *(int *)d = *(const int *)s; break;
+            case 2: *(short *)d = *(const short *)s; break;
+            default: *d = *s; break;
+        }
+    }
+}
+struct PackParams {
+    char *packed;        // heap staging buffer
+    const char *user;    // device-accessible alias of the user's buffer
+    TypeLayout L;
+};
+__global__ void __launch_bounds__(256) pack_kernel(PackParams p) {
+    pdl_prologue();
+    pack_unpack_body<true>(p.packed, (char *)p.user, p.L, ~0ull);
+}
+struct UnpackParams {
+    acx_op *op;          // recv_bytes: how much actually arrived
+    char *user;
+    const char *packed;
+    acx_host_status *hstat;
+    TypeLayout L;
+    uint32_t retire, pad;
+};
+__global__ void __launch_bounds__(256) unpack_kernel(UnpackParams p) {
+    pdl_prologue();
+    pack_unpack_body<false>((char *)p.packed, p.user, p.L, p.op->recv_bytes);
+    if (!p.retire) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicAdd(&p.op->cta_count, 1u);
+        if (t == gridDim.x - 1) { p.op->cta_count = 0; p.hstat->retired = 1; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Partitioned helpers (host Start / Wait paths; the device-side API is in acx_device.cuh)
 // ---------------------------------------------------------------------------------------
 __global__ void pstart_kernel(uint64_t *epoch_local, uint64_t *cts_remote, uint64_t e) {

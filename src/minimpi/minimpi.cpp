@@ -343,6 +343,8 @@ struct acx_mpi_request_s {
     size_t bytes;       // send: message bytes; recv: capacity
     int peer, tag, comm, part;
     int cid = 1;        // communicator handle (status.MPI_SOURCE is reported in its rank space)
+    std::vector<char> packed;   // non-contiguous datatype: the wire image (send: packed at post time; recv: unpacked at completion)
+    void *user_buf = nullptr; long long user_count = 0; int user_dt = 0;   // recv: where and how to unpack
     bool done = false, active = true, persistent = false, freed = false;
     MPI_Status st{};
     // send progress
@@ -596,7 +598,90 @@ void progress() {
     }
 }
 
-size_t dt_size(MPI_Datatype dt) { return (size_t)(dt & 0xff); }
+// ---- datatypes -----------------------------------------------------------------------
+// Basic handles carry their size in the low byte. Derived handles index g_types; every derived type is kept in the
+// canonical form of ACX_Mpi_layout (<= 3 strided dimensions around one contiguous run), which covers contiguous,
+// (h)vector and 1-3-D subarray types and their nestings — the layouts of halo faces.
+std::vector<ACX_Mpi_layout> g_types;
+std::vector<char> g_type_live;
+bool is_derived(MPI_Datatype dt) { return dt >= ACX_DT_DERIVED_BASE; }
+const ACX_Mpi_layout *layout_of(MPI_Datatype dt) {
+    if (!is_derived(dt)) return nullptr;
+    size_t i = (size_t)(dt - ACX_DT_DERIVED_BASE);
+    return i < g_types.size() && g_type_live[i] ? &g_types[i] : nullptr;
+}
+bool get_layout(MPI_Datatype dt, ACX_Mpi_layout *L) {
+    if (is_derived(dt)) { const ACX_Mpi_layout *p = layout_of(dt); if (!p) return false; *L = *p; return true; }
+    const long long sz = dt & 0xff;
+    if (!sz) return false;
+    for (int i = 0; i < 3; i++) { L->n[i] = 1; L->stride[i] = 0; }
+    L->run = sz; L->disp = 0; L->extent = sz; L->size = sz; L->contiguous = 1;
+    return true;
+}
+size_t dt_size(MPI_Datatype dt) {
+    if (is_derived(dt)) { const ACX_Mpi_layout *p = layout_of(dt); return p ? (size_t)p->size : 0; }
+    return (size_t)(dt & 0xff);
+}
+bool dt_contig(MPI_Datatype dt) { const ACX_Mpi_layout *p = layout_of(dt); return !is_derived(dt) || (p && p->contiguous && p->disp == 0); }
+MPI_Datatype add_type(const ACX_Mpi_layout &L) {
+    g_types.push_back(L);
+    g_type_live.push_back(1);
+    return (MPI_Datatype)(ACX_DT_DERIVED_BASE + g_types.size() - 1);
+}
+void normalize(ACX_Mpi_layout &L) {
+    // drop unit dimensions, then fold the innermost dimension into the run while it continues it seamlessly
+    long long n[3], st[3];
+    int k = 0;
+    for (int d = 0; d < 3; d++) if (L.n[d] > 1) { n[k] = L.n[d]; st[k] = L.stride[d]; k++; }
+    int lo = 0;
+    while (lo < k && st[lo] == L.run) { L.run *= n[lo]; lo++; }
+    for (int d = 0; d < 3; d++) {
+        if (lo + d < k) { L.n[d] = n[lo + d]; L.stride[d] = st[lo + d]; }
+        else { L.n[d] = 1; L.stride[d] = 0; }
+    }
+    L.size = L.n[0] * L.n[1] * L.n[2] * L.run;
+    L.contiguous = (L.n[0] == 1 && L.n[1] == 1 && L.n[2] == 1 && L.extent == L.size) ? 1 : 0;
+}
+// `count` blocks of `blocklen` old items, `stride_bytes` apart: adds (up to) two dimensions around `old`.
+bool make_strided(const ACX_Mpi_layout &old, long long count, long long blocklen, long long stride_bytes, ACX_Mpi_layout *out) {
+    ACX_Mpi_layout L = old;
+    int used = 0;
+    for (int d = 0; d < 3; d++) if (L.n[d] > 1) used = d + 1;
+    auto push = [&](long long n, long long st) {
+        if (n == 1) return true;
+        if (used == 3) return false;
+        L.n[used] = n; L.stride[used] = st; used++;
+        return true;
+    };
+    if (old.contiguous && old.disp == 0) {   // a block of contiguous items is one longer run
+        L.run = old.size * blocklen;
+        if (!push(count, stride_bytes)) return false;
+    } else {
+        if (!push(blocklen, old.extent) || !push(count, stride_bytes)) return false;
+    }
+    L.extent = (count - 1) * stride_bytes + blocklen * old.extent;
+    if (count == 0 || blocklen == 0) { L.n[0] = L.n[1] = L.n[2] = 1; L.run = 0; L.extent = 0; }
+    normalize(L);
+    *out = L;
+    return true;
+}
+template <bool kPack>
+void pack_unpack(char *packed, char *user, long long count, const ACX_Mpi_layout &L, size_t limit) {
+    size_t done = 0;
+    for (long long c = 0; c < count; c++) {
+        char *base = user + c * L.extent + L.disp;
+        for (long long i2 = 0; i2 < L.n[2]; i2++)
+            for (long long i1 = 0; i1 < L.n[1]; i1++)
+                for (long long i0 = 0; i0 < L.n[0]; i0++) {
+                    if (done >= limit) return;
+                    size_t n = (size_t)L.run;
+                    if (done + n > limit) n = limit - done;
+                    char *u = base + i2 * L.stride[2] + i1 * L.stride[1] + i0 * L.stride[0];
+                    if (kPack) memcpy(packed + done, u, n); else memcpy(u, packed + done, n);
+                    done += n;
+                }
+    }
+}
 
 CommInfo *comm_of(MPI_Comm c) {
     auto it = g_comms.find(c);
@@ -1076,13 +1161,86 @@ int MPI_Cart_shift(MPI_Comm c, int direction, int disp, int *src, int *dst) {
     return MPI_SUCCESS;
 }
 
-int MPI_Type_size(MPI_Datatype dt, int *size) { *size = (int)dt_size(dt); return *size ? MPI_SUCCESS : MPI_ERR_TYPE; }
+int MPI_Type_size(MPI_Datatype dt, int *size) { LOCK; *size = (int)dt_size(dt); return (*size || layout_of(dt)) ? MPI_SUCCESS : MPI_ERR_TYPE; }
 int MPI_Get_count(const MPI_Status *st, MPI_Datatype dt, int *count) {
     size_t s = dt_size(dt);
     if (!s) return MPI_ERR_TYPE;
     *count = (st->_bytes % (long long)s) ? MPI_UNDEFINED : (int)(st->_bytes / (long long)s);
     return MPI_SUCCESS;
 }
+
+int MPI_Type_contiguous(int count, MPI_Datatype old, MPI_Datatype *nt) {
+    LOCK;
+    ACX_Mpi_layout o, L;
+    if (count < 0 || !get_layout(old, &o)) return MPI_ERR_TYPE;
+    if (!make_strided(o, 1, count, 0, &L)) return MPI_ERR_TYPE;
+    *nt = add_type(L);
+    return MPI_SUCCESS;
+}
+int MPI_Type_create_hvector(int count, int blocklen, MPI_Aint stride_bytes, MPI_Datatype old, MPI_Datatype *nt) {
+    LOCK;
+    ACX_Mpi_layout o, L;
+    if (count < 0 || blocklen < 0 || !get_layout(old, &o)) return MPI_ERR_TYPE;
+    if (!make_strided(o, count, blocklen, stride_bytes, &L)) return MPI_ERR_TYPE;   // more than 3 strided dimensions
+    *nt = add_type(L);
+    return MPI_SUCCESS;
+}
+int MPI_Type_vector(int count, int blocklen, int stride, MPI_Datatype old, MPI_Datatype *nt) {
+    ACX_Mpi_layout o;
+    { LOCK; if (!get_layout(old, &o)) return MPI_ERR_TYPE; }
+    return MPI_Type_create_hvector(count, blocklen, (MPI_Aint)stride * o.extent, old, nt);
+}
+int MPI_Type_create_subarray(int ndims, const int sizes[], const int subsizes[], const int starts[], int order, MPI_Datatype old,
+                             MPI_Datatype *nt) {
+    LOCK;
+    ACX_Mpi_layout o;
+    if (ndims < 1 || ndims > 4 || !get_layout(old, &o) || !(o.contiguous && o.disp == 0)) return MPI_ERR_TYPE;
+    // walk the dimensions from fastest to slowest varying
+    ACX_Mpi_layout L = o;
+    long long pitch = o.extent, disp = 0, total = 1;
+    int used = 0;
+    for (int k = 0; k < ndims; k++) {
+        const int d = order == MPI_ORDER_FORTRAN ? k : ndims - 1 - k;
+        if (subsizes[d] < 1 || starts[d] < 0 || starts[d] + subsizes[d] > sizes[d]) return MPI_ERR_ARG;
+        disp += (long long)starts[d] * pitch;
+        if (k == 0) L.run = o.size * subsizes[d];
+        else if (subsizes[d] > 1) {
+            if (used == 3) return MPI_ERR_TYPE;
+            L.n[used] = subsizes[d]; L.stride[used] = pitch; used++;
+        }
+        pitch *= sizes[d];
+        total *= sizes[d];
+    }
+    L.disp = disp;
+    L.extent = total * o.extent;
+    normalize(L);
+    if (L.disp != 0) L.contiguous = 0;
+    *nt = add_type(L);
+    return MPI_SUCCESS;
+}
+int MPI_Type_commit(MPI_Datatype *dt) { LOCK; return (!is_derived(*dt) || layout_of(*dt)) ? MPI_SUCCESS : MPI_ERR_TYPE; }
+int MPI_Type_free(MPI_Datatype *dt) {
+    LOCK;
+    if (is_derived(*dt) && layout_of(*dt)) g_type_live[(size_t)(*dt - ACX_DT_DERIVED_BASE)] = 0;
+    *dt = MPI_DATATYPE_NULL;
+    return MPI_SUCCESS;
+}
+int MPI_Type_get_extent(MPI_Datatype dt, MPI_Aint *lb, MPI_Aint *extent) {
+    LOCK;
+    ACX_Mpi_layout L;
+    if (!get_layout(dt, &L)) return MPI_ERR_TYPE;
+    if (lb) *lb = 0;
+    if (extent) *extent = L.extent;
+    return MPI_SUCCESS;
+}
+int MPI_Pack_size(int incount, MPI_Datatype dt, MPI_Comm, int *size) {
+    LOCK;
+    size_t s = dt_size(dt);
+    if (!s && !is_derived(dt)) return MPI_ERR_TYPE;
+    *size = (int)(s * (size_t)incount);
+    return MPI_SUCCESS;
+}
+int ACX_Mpi_type_layout(MPI_Datatype dt, ACX_Mpi_layout *L) { LOCK; return get_layout(dt, L) ? MPI_SUCCESS : MPI_ERR_TYPE; }
 
 int MPI_Barrier(MPI_Comm c) {
     LOCK;
@@ -1193,6 +1351,18 @@ int MPI_Isend(const void *buf, int count, MPI_Datatype dt, int dest, int tag, MP
     CommInfo *ci = comm_of(c);
     if (!ci) return MPI_ERR_COMM;
     if (dest == MPI_ANY_SOURCE || (dest = to_world(ci, dest)) == -1000) return MPI_ERR_RANK;
+    if (!dt_contig(dt)) {
+        // non-contiguous layout: pack now (sends have buffered semantics anyway), ship the packed image
+        ACX_Mpi_layout L;
+        if (!get_layout(dt, &L) || is_device_ptr(buf)) return MPI_ERR_TYPE;
+        std::vector<char> img((size_t)L.size * (size_t)count);
+        pack_unpack<true>(img.data(), (char *)buf, count, L, img.size());
+        const char *data = img.data();
+        *req = post_send(data, img.size(), dest, tag, ci->ctx, -1);
+        (*req)->packed = std::move(img);   // the buffer (and `data`) stays where it is
+        (*req)->cid = c;
+        return MPI_SUCCESS;
+    }
     *req = post_send(buf, dt_size(dt) * (size_t)count, dest, tag, ci->ctx, -1);
     (*req)->cid = c;
     return MPI_SUCCESS;
@@ -1203,6 +1373,19 @@ int MPI_Irecv(void *buf, int count, MPI_Datatype dt, int src, int tag, MPI_Comm 
     CommInfo *ci = comm_of(c);
     if (!ci) return MPI_ERR_COMM;
     if ((src = to_world(ci, src)) == -1000) return MPI_ERR_RANK;
+    if (!dt_contig(dt)) {
+        ACX_Mpi_layout L;
+        if (!get_layout(dt, &L) || is_device_ptr(buf)) return MPI_ERR_TYPE;
+        std::vector<char> img((size_t)L.size * (size_t)count);
+        char *data = img.data();
+        if (src == MPI_PROC_NULL) { *req = post_recv(buf, 0, src, tag, ci->ctx, -1); (*req)->cid = c; return MPI_SUCCESS; }
+        *req = post_recv(data, img.size(), src, tag, ci->ctx, -1);
+        (*req)->packed = std::move(img);
+        (*req)->user_buf = buf; (*req)->user_count = count; (*req)->user_dt = dt;
+        (*req)->cid = c;
+        progress();
+        return MPI_SUCCESS;
+    }
     *req = post_recv(buf, dt_size(dt) * (size_t)count, src, tag, ci->ctx, -1);
     (*req)->cid = c;
     progress();
@@ -1211,6 +1394,11 @@ int MPI_Irecv(void *buf, int count, MPI_Datatype dt, int src, int tag, MPI_Comm 
 
 static void finish_req(MPI_Request *req, MPI_Status *st) {
     Req *r = *req;
+    if (r->user_buf && r->kind == RQ_RECV) {   // non-contiguous receive: scatter the packed image into the user's layout
+        ACX_Mpi_layout L;
+        if (get_layout(r->user_dt, &L)) pack_unpack<false>(r->packed.data(), (char *)r->user_buf, r->user_count, L, (size_t)r->st._bytes);
+        r->user_buf = nullptr;
+    }
     if (st) {
         *st = r->st;
         if (st->MPI_SOURCE >= 0) st->MPI_SOURCE = from_world(comm_of(r->cid), st->MPI_SOURCE);   // report in the communicator's rank space
@@ -1322,6 +1510,7 @@ static int pinit(ReqKind k, void *buf, int partitions, MPI_Count count, MPI_Data
     if (!ci) return MPI_ERR_COMM;
     const int ctx = ci->ctx;
     if (partitions <= 0 || count < 0) return MPI_ERR_COUNT;
+    if (!dt_contig(dt)) return MPI_ERR_TYPE;   // partitioned transfers: contiguous datatypes only
     if (peer == MPI_ANY_SOURCE || (peer = to_world(ci, peer)) == -1000) return MPI_ERR_RANK;
     Req *r = new Req();
     r->cid = c;

@@ -199,3 +199,12 @@ def test_sub_communicators(built, np_):
     r = acxrun(built, np_, built / "build/tests/subcomm")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_derived_datatypes(built, np_):
+    """Strided faces of a 3-D block sent and received in place with subarray / vector datatypes: pack_kernel before the
+    send, unpack_kernel behind the wait (eager and rendezvous sizes, stream and host waits) — tests/c/datatypes.c."""
+    r = acxrun(built, np_, built / "build/tests/datatypes")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout

@@ -26,12 +26,25 @@ def test_minimpi_subcommunicators(built, np_):
 
 
 @pytest.mark.parametrize("np_", [1, 2, 3])
+def test_minimpi_derived_datatypes(built, np_):
+    """Vector / hvector / subarray / nested datatypes of the bundled MPI (tests/c/minimpi_types.c)."""
+    r = acxrun(built, np_, built / "build/tests/minimpi_types")
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+
+
+def test_pack_kernel_index_math_matches_mpi_pack(built):
+    """The __host__ __device__ layout arithmetic of the pack/unpack kernels, run on the CPU against MPI's own packing."""
+    r = acxrun(built, 1, built / "build/tests/layout_math")
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("np_", [1, 2, 3])
 def test_minimpi_thread_multiple(built, np_):
     r = acxrun(built, np_, built / "build/tests/minimpi_threads")
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("prog", ["ring", "ring_all", "procnull_comms", "wildcards", "subcomm"])
+@pytest.mark.parametrize("prog", ["ring", "ring_all", "procnull_comms", "wildcards", "subcomm", "datatypes"])
 @pytest.mark.parametrize("np_", [1, 2, 3])
 def test_ring_host_transport(built, prog, np_):
     r = acxrun(built, np_, built / f"build/tests/{prog}", env={"ACX_FORCE_HOST": "1"})

@@ -12,6 +12,9 @@ run() { timeout 120 ./bin/acxrun -np $NP --timeout 100 "$@" 2>&1 | tail -n 2; }
 echo "### 1. new conformance program (PROC_NULL, communicator contexts, wildcard rejection)"
 for np in 1 $NP; do timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/procnull_comms 2>&1 | tail -n 3; done
 
+for np in 1 2 $NP; do timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/datatypes 2>&1 | tail -n 3; done
+for np in 2 4; do timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/subcomm 2>&1 | tail -n 3; done
+
 echo "### 1b. experimental device-side wildcards (ACX_WILDCARDS=1)"
 for np in 1 2 $NP; do ACX_WILDCARDS=1 timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/wildcards 2>&1 | tail -n 3; done
 timeout 60 ./bin/acxrun -np 2 --timeout 50 build/tests/wildcards 2>&1 | tail -n 1   # default: rejected cleanly
