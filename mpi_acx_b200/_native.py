@@ -17,6 +17,9 @@ LIB_PATH = REPO / "lib" / "libacx.so"
 MPI_COMM_WORLD = 1
 MPI_THREAD_MULTIPLE = 3
 MPI_BYTE = (4 << 8) | 1
+MPI_ANY_SOURCE = -2
+MPI_ANY_TAG = -1
+MPI_PROC_NULL = -3
 QUEUE_STREAM = 0
 QUEUE_GRAPH = 1
 
@@ -64,6 +67,10 @@ def lib() -> ctypes.CDLL:
         _lib.MPI_Comm_size.argtypes = [ci, P(ci)]
         _lib.MPI_Barrier.argtypes = [ci]
         _lib.MPI_Initialized.argtypes = [P(ci)]
+        _lib.MPI_Type_contiguous.argtypes = [ci, ci, P(ci)]
+        _lib.MPI_Type_create_hvector.argtypes = [ci, ci, ctypes.c_longlong, ci, P(ci)]
+        _lib.MPI_Type_commit.argtypes = [P(ci)]
+        _lib.MPI_Type_free.argtypes = [P(ci)]
         _lib.MPIX_Isend_enqueue.argtypes = [vp, ci, ci, ci, ci, ci, P(vp), ci, vp]
         _lib.MPIX_Irecv_enqueue.argtypes = [vp, ci, ci, ci, ci, ci, P(vp), ci, vp]
         _lib.MPIX_Wait_enqueue.argtypes = [P(vp), P(MPIStatus), ci, vp]

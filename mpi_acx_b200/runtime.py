@@ -138,17 +138,73 @@ def _buf(t):
     return ctypes.c_void_p(t.data_ptr()), t.numel() * t.element_size()
 
 
+# Strided tensor views (a face of a 3-D block, a column of a matrix, ...) travel without a .contiguous() copy in user
+# code: the view's sizes/strides become an MPI derived datatype (nested hvectors around one contiguous run) and the
+# library's pack / unpack kernels gather and scatter it. The wire format is the view's elements in logical (row-major)
+# order, so a strided send matches a contiguous receive of the same shape and vice versa.
+_type_cache: dict = {}
+
+
+def strided_layout(shape: Sequence[int], strides: Sequence[int], itemsize: int):
+    """(run_bytes, [(count, stride_bytes), ...] inner -> outer) of a tensor view; raises if it cannot be expressed."""
+    dims = [(int(n), int(st) * itemsize) for n, st in zip(shape, strides) if int(n) != 1]
+    if any(st < 0 for _, st in dims):
+        raise AcxError("negative strides are not supported")
+    if any(st == 0 for _, st in dims):
+        raise AcxError("expanded (stride 0) views are not supported")
+    run = itemsize
+    while dims and dims[-1][1] == run:      # fold the innermost dimensions that continue the run
+        run *= dims[-1][0]
+        dims.pop()
+    folded: list = []
+    for n, st in reversed(dims):            # inner -> outer; merge adjacent dimensions that form one regular stride
+        if folded and st == folded[-1][0] * folded[-1][1]:
+            folded[-1] = (folded[-1][0] * n, folded[-1][1])
+        else:
+            folded.append((n, st))
+    if len(folded) > 3:
+        raise AcxError("view needs more than 3 strided dimensions; call .contiguous() first")
+    return run, folded
+
+
+def _typed_buf(t):
+    """(pointer, count, MPI datatype) for any dense or regularly strided tensor view."""
+    if t.is_contiguous():
+        p, nb = _buf(t)
+        return p, nb, N.MPI_BYTE
+    run, dims = strided_layout(t.shape, t.stride(), t.element_size())
+    key = (run, tuple(dims))
+    dt = _type_cache.get(key)
+    if dt is None:
+        L = N.lib()
+        cur = ctypes.c_int(0)
+        _ck(L.MPI_Type_contiguous(run, N.MPI_BYTE, ctypes.byref(cur)), "MPI_Type_contiguous")
+        for n, st in dims:
+            nxt = ctypes.c_int(0)
+            _ck(L.MPI_Type_create_hvector(n, 1, st, cur.value, ctypes.byref(nxt)), "MPI_Type_create_hvector")
+            cur = nxt
+        _ck(L.MPI_Type_commit(ctypes.byref(cur)), "MPI_Type_commit")
+        dt = _type_cache[key] = cur.value
+    return ctypes.c_void_p(t.data_ptr()), 1, dt
+
+
+PROC_NULL, ANY_SOURCE, ANY_TAG = N.MPI_PROC_NULL, N.MPI_ANY_SOURCE, N.MPI_ANY_TAG
+
+
 def isend(t, dest: int, tag: int = 0, stream=None) -> Request:
-    p, nb = _buf(t)
+    """Stream-ordered send of a tensor (dense, or a regularly strided view). `dest` may be PROC_NULL."""
+    p, n, dt = _typed_buf(t)
     h, cs = ctypes.c_void_p(), _stream_arg(stream)
-    _ck(N.lib().MPIX_Isend_enqueue(p, nb, N.MPI_BYTE, dest, tag, N.MPI_COMM_WORLD, ctypes.byref(h), N.QUEUE_STREAM, ctypes.byref(cs)), "MPIX_Isend_enqueue")
+    _ck(N.lib().MPIX_Isend_enqueue(p, n, dt, dest, tag, N.MPI_COMM_WORLD, ctypes.byref(h), N.QUEUE_STREAM, ctypes.byref(cs)), "MPIX_Isend_enqueue")
     return Request(h, t)
 
 
 def irecv(t, source: int, tag: int = 0, stream=None) -> Request:
-    p, nb = _buf(t)
+    """Stream-ordered receive into a tensor (dense, or a regularly strided view). `source` may be PROC_NULL
+    (or ANY_SOURCE / tag ANY_TAG where the transport supports wildcards)."""
+    p, n, dt = _typed_buf(t)
     h, cs = ctypes.c_void_p(), _stream_arg(stream)
-    _ck(N.lib().MPIX_Irecv_enqueue(p, nb, N.MPI_BYTE, source, tag, N.MPI_COMM_WORLD, ctypes.byref(h), N.QUEUE_STREAM, ctypes.byref(cs)), "MPIX_Irecv_enqueue")
+    _ck(N.lib().MPIX_Irecv_enqueue(p, n, dt, source, tag, N.MPI_COMM_WORLD, ctypes.byref(h), N.QUEUE_STREAM, ctypes.byref(cs)), "MPIX_Irecv_enqueue")
     return Request(h, t)
 
 

@@ -94,6 +94,27 @@ assert bool((pr == float((r - 1) %% n)).all())
 a.free(); b.free()
 st = acx.stats()
 assert st["sends_enqueued"] == 3
+# strided views travel without .contiguous(): the x-face of a 3-D block into the neighbour's ghost face, and into a dense tensor
+blk = (torch.arange(4 * 5 * 6, dtype=torch.float32) + 1000 * r).view(4, 5, 6).clone()
+ghost = torch.full((4, 5, 6), -1.0)
+dense = torch.zeros(4, 5)
+left, right = (r - 1) %% n, (r + 1) %% n
+q = [acx.irecv(ghost[:, :, 0], left, tag=9), acx.irecv(dense, left, tag=10), acx.isend(blk[:, :, 4], right, tag=9), acx.isend(blk[:, :, 4], right, tag=10)]
+acx.waitall_enqueue(q)
+want = (torch.arange(4 * 5 * 6, dtype=torch.float32) + 1000 * left).view(4, 5, 6)[:, :, 4]
+assert torch.equal(ghost[:, :, 0], want) and torch.equal(dense, want) and bool((ghost[:, :, 1:] == -1).all())
+# transposed (column-major) view -> dense
+m = (torch.arange(12, dtype=torch.int64) + 100 * r).view(3, 4)
+mt = torch.zeros(4, 3, dtype=torch.int64)
+q = [acx.irecv(mt, left, tag=11), acx.isend(m.t(), right, tag=11)]
+acx.waitall_enqueue(q)
+assert torch.equal(mt, (torch.arange(12, dtype=torch.int64) + 100 * left).view(3, 4).t())
+assert acx.strided_layout((4, 5, 1), (30, 6, 1), 4) == (4, [(20, 24)])   # y and z fold into one regular stride
+# MPI_PROC_NULL: completes at once, moves nothing
+untouched = torch.full((8,), 7.0)
+q = [acx.irecv(untouched, acx.PROC_NULL), acx.isend(untouched, acx.PROC_NULL)]
+acx.waitall_enqueue(q)
+assert bool((untouched == 7).all())
 acx.finalize()
 print("OK", r)
 """
