@@ -50,6 +50,7 @@ static std::vector<cudaStream_t> g_side;  // side streams, indexed by peer % siz
 static int g_wild = 0;                    // ACX_WILDCARDS: MPI_ANY_SOURCE / MPI_ANY_TAG receives on the device transport (experimental; matched at wait time)
 static AnyTable *g_any_tbl_d = nullptr;   // device copy of the peer window bases, built on first wildcard use
 static acx_anyres *g_anyres_d = nullptr;  // one resolution record per request slot
+static int g_pbatch = 0;                  // ACX_PBATCH: one kernel launch per MPIX_Startall / MPIX_Waitall group of partitioned requests instead of one per request
 static int g_branch = 0;                  // ACX_PEER_BRANCH: run EVERY operation with a peer on that peer's side stream (fork at enqueue, join at the wait)
 static int g_fuse_rndv = 1, g_fuse_min_ctas = 8, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
 static int g_pdl = 1;   // programmatic dependent launch between consecutive acx kernels on a stream (ACX_PDL)
@@ -516,6 +517,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
     acx_env_int("ACX_SIDE_STREAMS", nullptr, 1, &v); g_side_on = v != 0;
     acx_env_int("ACX_WILDCARDS", nullptr, 0, &v); g_wild = v != 0;   // experimental device-side wildcard matching (see recv_any_kernel)
+    acx_env_int("ACX_PBATCH", nullptr, 0, &v); g_pbatch = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_PEER_BRANCH", nullptr, 0, &v); g_branch = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_SENDER_PUSH", nullptr, 0, &v); g_apush = v != 0;   // opt-in: a spinning gate can deadlock against device-synchronizing host calls
     acx_env_int("ACX_FUSE_MAX_CTAS", nullptr, 32, &v); g_fuse_max_ctas = (int)v;
@@ -1705,14 +1707,33 @@ extern "C" int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses)
     // partitioned requests on the device transport: emit every completion kernel first, synchronize once
     if (g_acx && g_acx->device) {
         bool any = false;
+        PWaitBatch pb;
+        int nb = 0;
+        auto flush = [&]() -> int {
+            if (!nb) return 0;
+            pb.wd = make_wd();
+            void *args[] = {&pb};
+            ACX_CUDA_WD(cudaLaunchKernel((const void *)pwait_batch_kernel, dim3(nb), dim3(kWaitThreads), args, 0, g_acx->istream));
+            g_acx->st.kernels++;
+            nb = 0;
+            return 0;
+        };
         for (int i = 0; i < count; i++) {
             AcxRequest *r = reqs[i] ? as_request(reqs[i]) : nullptr;
             if (r && (r->kind == ACX_REQ_PSEND || r->kind == ACX_REQ_PRECV) && !r->host_transport && r->active) {
-                int rc = pwait_emit(r, g_acx->istream);
-                if (rc) return rc;
+                if (g_pbatch) {
+                    pb.ch[nb] = r->pchan_d; pb.e[nb] = r->epoch;
+                    r->active = false;
+                    int rc;
+                    if (++nb == kPBatch && (rc = flush())) return rc;
+                } else {
+                    int rc = pwait_emit(r, g_acx->istream);
+                    if (rc) return rc;
+                }
                 any = true;
             }
         }
+        { int rc = flush(); if (rc) return rc; }
         if (any) ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
     }
     for (int i = 0; i < count; i++) {
@@ -1887,14 +1908,38 @@ static int pstart_emit(AcxRequest *r, cudaStream_t stream) {
 extern "C" int MPIX_Startall(int count, MPIX_Request *reqs) {
     if (!g_acx || !g_acx->initialized) return MPI_ERR_OTHER;
     bool any_dev = false;
+    PStartBatch sb;
+    memset(&sb, 0, sizeof sb);
+    auto flush = [&]() -> int {
+        if (!sb.n) return 0;
+        void *args[] = {&sb};
+        ACX_CUDA_WD(cudaLaunchKernel((const void *)pstart_batch_kernel, dim3(1), dim3(32), args, 0, g_acx->istream));
+        g_acx->st.kernels++;
+        sb.n = 0;
+        return 0;
+    };
     for (int i = 0; i < count; i++) {
         AcxRequest *r = as_request(reqs[i]);
         if (!r || (r->kind != ACX_REQ_PSEND && r->kind != ACX_REQ_PRECV)) { ACX_ERR("MPIX_Start needs a partitioned request"); return MPI_ERR_REQUEST; }
         if (r->host_transport) { int rc = MPI_Start(&r->mpi_req); if (rc) return rc; r->active = true; continue; }
+        if (g_pbatch) {
+            int rc = presolve(r);
+            if (rc) return rc;
+            if (r->active) { ACX_ERR("MPIX_Start on an active partitioned request"); return MPI_ERR_REQUEST; }
+            r->epoch++;
+            r->active = true;
+            sb.epoch_local[sb.n] = r->pchan_h.epoch;
+            sb.cts_remote[sb.n] = r->kind == ACX_REQ_PRECV ? r->pchan_h.cts : nullptr;
+            sb.e[sb.n] = r->epoch;
+            if (++sb.n == kPBatch && (rc = flush())) return rc;
+            any_dev = true;
+            continue;
+        }
         int rc = pstart_emit(r, g_acx->istream);
         if (rc) return rc;
         any_dev = true;
     }
+    { int rc = flush(); if (rc) return rc; }
     // Kernels launched by the user right after Start (on any stream) must observe the new epoch.
     if (any_dev) ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
     return MPI_SUCCESS;

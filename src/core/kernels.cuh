@@ -738,10 +738,24 @@ __global__ void pstart_kernel(uint64_t *epoch_local, uint64_t *cts_remote, uint6
     st_release_sys(epoch_local, e);
     if (cts_remote) { __threadfence_system(); st_release_sys(cts_remote, e); }
 }
+// Batched Start (ACX_PBATCH=1): one launch starts up to kPBatch requests, one thread each.
+constexpr int kPBatch = 16;
+struct PStartBatch {
+    uint64_t *epoch_local[kPBatch];
+    uint64_t *cts_remote[kPBatch];
+    uint64_t e[kPBatch];
+    int n, pad;
+};
+__global__ void pstart_batch_kernel(PStartBatch b) {
+    const int i = (int)threadIdx.x;
+    if (i >= b.n) return;
+    st_release_sys(b.epoch_local[i], b.e[i]);
+    if (b.cts_remote[i]) { __threadfence_system(); st_release_sys(b.cts_remote[i], b.e[i]); }
+}
 
 // Completes one round: SEND waits until every partition was marked ready (sent[p]==e);
 // RECV waits for every arrival and copies out what device pollers have not claimed.
-__global__ void __launch_bounds__(kWaitThreads) pwait_kernel(const acx_pchan *ch, uint64_t e, Watchdog wd) {
+__device__ __forceinline__ void pwait_body(const acx_pchan *ch, uint64_t e, const Watchdog &wd) {
     __shared__ int s_copy;
     for (int p = 0; p < ch->partitions; p++) {
         if (ch->kind == ACX_PKIND_SEND) {
@@ -770,6 +784,15 @@ __global__ void __launch_bounds__(kWaitThreads) pwait_kernel(const acx_pchan *ch
         __syncthreads();
     }
 }
+
+__global__ void __launch_bounds__(kWaitThreads) pwait_kernel(const acx_pchan *ch, uint64_t e, Watchdog wd) { pwait_body(ch, e, wd); }
+// Batched completion (ACX_PBATCH=1): one CTA per request, one launch for a whole MPIX_Waitall.
+struct PWaitBatch {
+    const acx_pchan *ch[kPBatch];
+    uint64_t e[kPBatch];
+    Watchdog wd;
+};
+__global__ void __launch_bounds__(kWaitThreads) pwait_batch_kernel(PWaitBatch b) { pwait_body(b.ch[blockIdx.x], b.e[blockIdx.x], b.wd); }
 
 // Host-callable single-partition operations (MPIX_Pready_host / MPIX_Parrived_host).
 __global__ void pready_host_kernel(const acx_pchan *ch, int p) { pready_cta(p, ch); }

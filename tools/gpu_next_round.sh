@@ -37,6 +37,11 @@ done
 for br in 0 1; do echo "ring branch=$br: $(ACX_PEER_BRANCH=$br ACX_HEAP_BYTES=1g run bin/p2p_bench ring --bytes 268435456 | tail -n 1)"; done
 for br in 0 1; do echo "pingpong branch=$br: $(ACX_PEER_BRANCH=$br timeout 120 ./bin/acxrun -np 2 --timeout 100 bin/p2p_bench pingpong 2>&1 | tail -n 1 | cut -c1-400)"; done
 
+echo "### 3b. ACX_PBATCH=1 (batched partitioned Start/Wait): conformance + API-level halo step against the default and the reference"
+for np in 1 $NP; do ACX_PBATCH=1 timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/ring_partitioned 2>&1 | tail -n 1; done
+for pbv in 0 1; do echo "halo api pbatch=$pbv: $(ACX_PBATCH=$pbv run bin/halo_bench api --n 512 --steps 10 | tail -n 1)"; done
+echo "halo api reference: $(run $R/halo_bench api --n 512 --steps 10 | tail -n 1)"
+
 echo "### 4. ring with pre-posted receives (C harness) and bench.py at N=$NP (auto order = prepost from 3 GPUs up)"
 ACX_HEAP_BYTES=1g run bin/p2p_bench ring --bytes 268435456 --prepost | tee $O/ring_acx_prepost_n${NP}.json
 run $R/p2p_bench ring --bytes 268435456 --no-heap --prepost | tee $O/ring_ref_prepost_n${NP}.json
