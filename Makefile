@@ -14,7 +14,7 @@ BINS  := bin/acxrun
 BENCH := $(patsubst bench/%.cu,bin/%,$(wildcard bench/*.cu))
 CTESTS := $(patsubst tests/c/%.c,$(B)/tests/%,$(wildcard tests/c/*.c)) $(patsubst tests/c/%.cu,$(B)/tests/%,$(wildcard tests/c/*.cu))
 
-.PHONY: all clean lib tests bench examples tsan asan
+.PHONY: all clean lib tests bench examples tsan asan install
 all: lib $(BINS) tests bench
 bench: $(BENCH)
 bin/%: bench/%.cu $(LIB)
@@ -59,6 +59,16 @@ examples: $(LIB)
 	@mkdir -p $(B)/examples
 	$(NVCC) $(GENCODE) -O2 -Iinclude examples/stream_ring.c -o $(B)/examples/stream_ring -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
 	$(NVCC) $(GENCODE) -O2 -Iinclude examples/partitioned_producer.cu -o $(B)/examples/partitioned_producer -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
+
+# Install headers, the library and the launcher (PREFIX=/usr/local by default): a program written for the reference then
+# builds with  nvcc -I$(PREFIX)/include prog.cu -L$(PREFIX)/lib -lacx
+PREFIX ?= /usr/local
+install: lib bin/acxrun
+	install -d $(DESTDIR)$(PREFIX)/include $(DESTDIR)$(PREFIX)/lib $(DESTDIR)$(PREFIX)/bin
+	install -m 644 include/mpi-acx.h include/acx_device.cuh include/acx_kernels.h include/mpi.h $(DESTDIR)$(PREFIX)/include/
+	install -m 755 lib/libacx.so $(DESTDIR)$(PREFIX)/lib/
+	install -m 644 lib/libacxmpi.a $(DESTDIR)$(PREFIX)/lib/
+	install -m 755 bin/acxrun $(DESTDIR)$(PREFIX)/bin/
 
 clean:
 	rm -rf $(B) lib bin
