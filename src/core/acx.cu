@@ -50,6 +50,8 @@ static std::vector<cudaStream_t> g_side;  // side streams, indexed by peer % siz
 static int g_wild = 0;                    // ACX_WILDCARDS: MPI_ANY_SOURCE / MPI_ANY_TAG receives on the device transport (experimental; matched at wait time)
 static AnyTable *g_any_tbl_d = nullptr;   // device copy of the peer window bases, built on first wildcard use
 static acx_anyres *g_anyres_d = nullptr;  // one resolution record per request slot
+static int g_coop = 0;                    // ACX_COOP: cooperative moving with chunk stealing (both ends of a large rendezvous message copy it); must be set on every rank
+static long g_coop_min = 4 << 20;          // ACX_COOP_MIN_BYTES
 static int g_pbatch = 0;                  // ACX_PBATCH: one kernel launch per MPIX_Startall / MPIX_Waitall group of partitioned requests instead of one per request
 static int g_branch = 0;                  // ACX_PEER_BRANCH: run EVERY operation with a peer on that peer's side stream (fork at enqueue, join at the wait)
 static int g_fuse_rndv = 1, g_fuse_min_ctas = 8, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
@@ -95,6 +97,8 @@ static void report_watchdog() {
             case 0x5e08: what = "partitioned wait(recv): a device poller never finished its copy-out"; break;
             case 0x5e09: what = "fused rendezvous: CTA 0 never published the match decision"; break;
             case 0x5e0a: what = "sender-push gate: the matching receive was never posted"; break;
+            case 0x5e0b: what = "wildcard receive: no matching send arrived"; break;
+            case 0x5e0c: what = "cooperative-move gate: the peer never arrived"; break;
         }
         ACX_ERR("WATCHDOG (code 0x%llx, a=0x%llx b=0x%llx): %s", (unsigned long long)g_diag[0], (unsigned long long)g_diag[1],
                 (unsigned long long)g_diag[2], what);
@@ -517,6 +521,8 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
     acx_env_int("ACX_SIDE_STREAMS", nullptr, 1, &v); g_side_on = v != 0;
     acx_env_int("ACX_WILDCARDS", nullptr, 0, &v); g_wild = v != 0;   // experimental device-side wildcard matching (see recv_any_kernel)
+    acx_env_int("ACX_COOP", nullptr, 0, &v); g_coop = v != 0;   // opt-in until measured on hardware
+    acx_env_int("ACX_COOP_MIN_BYTES", nullptr, 4 << 20, &v); g_coop_min = std::max(65536L, v);
     acx_env_int("ACX_PBATCH", nullptr, 0, &v); g_pbatch = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_PEER_BRANCH", nullptr, 0, &v); g_branch = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_SENDER_PUSH", nullptr, 0, &v); g_apush = v != 0;   // opt-in: a spinning gate can deadlock against device-synchronizing host calls
@@ -1265,6 +1271,10 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         const bool fused = fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas;   // measured: pays off from ~512 KiB, costs ~1.5 us below
         const bool apush = !eager && !fused && g_apush && g_side_on && qtype == MPIX_QUEUE_CUDA_STREAM;
         sp.apush = apush ? 1 : 0;
+        // Cooperative moving: same decision on both ends (it depends on the message size only; a receive posted with a
+        // larger capacity than the message is handled by the agents' own n = min(bytes, cap))
+        r->coop = g_coop && !eager && !fused && !apush && !g_mover_tma && (long)bytes >= g_coop_min;
+        mp.coop = r->coop ? 1 : 0;
         if (!dropped && fused) { if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail; }
         else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
         if (!eager) {
@@ -1384,6 +1394,8 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         mp.op = rp.op; mp.local = dst_local; mp.ring = rp.ring; mp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;
         mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr; mp.vec256 = g_mover_256; mp.block_bytes = (uint32_t)g_mover_block;
         const int fgrid = (rndv_capable && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
+        r->coop = g_coop && rndv_capable && !(fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas) && !g_apush && !g_mover_tma && (long)bytes >= g_coop_min;
+        mp.coop = r->coop ? 1 : 0;
         if (fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas) {
             if ((rc = em.launch2(recv_rndv_fused, dim3(fgrid), dim3(kMoverThreads), rp, mp))) goto fail;
         } else {
@@ -1441,6 +1453,7 @@ static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_w
         }
         w->dst = r->dev_buf;
         w->bounce = r->bounce_off >= 0 ? g_acx->heap + r->bounce_off : nullptr;
+        w->coop = g_coop ? 1 : 0;   // the receiver's wait kernel owns the slot's chunk cursor reset
         if (r->typed) { w->dst = w->bounce; w->bounce = nullptr; }   // eager payloads are copied into the staging buffer too; unpack_kernel does the rest
         w->cap = r->bytes;
         if (status != MPI_STATUS_IGNORE && !host_wait) {
@@ -1540,6 +1553,34 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             if (r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max) continue;
             need.push_back({r, st});
         }
+    }
+    // Cooperative moving: each large rendezvous request gets an agent kernel in front of the waits, so this GPU copies its
+    // share of the message even when it arrived first (ACX_COOP).
+    for (const Item &it : need) {
+        AcxRequest *r = it.r;
+        if (!r->coop || r->wild) continue;
+        const acx_geom &G = g_acx->geom;
+        CoopParams cp;
+        memset(&cp, 0, sizeof cp);
+        cp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
+        cp.is_send = r->kind == ACX_REQ_SEND ? 1 : 0;
+        if (cp.is_send) {
+            cp.ring = acx_entries_of(g_acx->peer_ctrl[r->peer]) + acx_entry_index(G, g_acx->rank, r->chan, 0);
+            cp.sack = acx_sacks_of(g_acx->ctrl) + acx_entry_index(G, r->peer, r->chan, 0);
+        } else {
+            cp.ring = acx_entries_of(g_acx->ctrl) + acx_entry_index(G, r->peer, r->chan, 0);
+            cp.sack = acx_sacks_of(g_acx->peer_ctrl[r->peer]) + acx_entry_index(G, g_acx->rank, r->chan, 0);
+        }
+        cp.local = r->bounce_off >= 0 ? g_acx->heap + r->bounce_off : r->dev_buf;
+        cp.peer_heap = g_acx->peer_heap[r->peer];
+        cp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)r->peer * G.maxreg;
+        cp.bytes = r->bytes; cp.depth = G.depth; cp.vec256 = (uint32_t)g_mover_256; cp.wd = make_wd();
+        const bool par = em.parallel;
+        em.parallel = false;
+        rc = em.launch(coop_gate, dim3(1), dim3(32), cp);
+        if (!rc) rc = em.launch(coop_kernel, dim3(mover_grid_ldst(r->bytes)), dim3(kMoverThreads), cp);
+        em.parallel = par;
+        if (rc) return rc;
     }
     // Wildcard receives: resolve + match (+ pull) kernel, then a single-entry wait that reads the resolution.
     {

@@ -45,8 +45,8 @@ struct alignas(64) acx_entry {  // one slot of a (src -> me, channel) ring; live
     uint64_t consumed;   // #generations the receiver has finished with (receiver-local bookkeeping)
     uint64_t s_src_off;  // sender: heap offset of the source (rendezvous)
     uint64_t s_bytes;    // sender: message bytes
-    uint64_t r_dst_off;  // receiver: heap offset of the destination (rendezvous)
-    uint64_t r_cap;      // receiver: capacity in bytes
+    uint64_t coop_cursor; // cooperative moving (ACX_COOP): next unclaimed chunk of this generation's payload (atomic add by agents on either GPU)
+    uint64_t coop_done;   // cooperative moving: chunks fully copied; both are reset by the receiver's wait kernel before the slot is recycled
     uint32_t s_tag;
     uint32_t s_kind;     // ACX_KIND_*
 };
@@ -132,6 +132,15 @@ ACX_HDI long long acx_layout_unit_offset(const TypeLayout &L, uint64_t j) {
     return (long long)r * L.extent + L.disp + (long long)i2 * L.stride[2] + (long long)i1 * L.stride[1] + (long long)i0 * L.stride[0] + (long long)within;
 }
 
+// Cooperative moving (ACX_COOP=1): chunk size for an n-byte rendezvous payload. Both ends evaluate this, so it may only
+// depend on n. Small enough that two GPUs can share a message, large enough that the remote atomic per claim is noise.
+ACX_HDI uint64_t acx_coop_chunk(uint64_t n) {
+    const uint64_t unit = 64ull << 10;
+    if (n <= (8ull << 20)) return unit;
+    uint64_t c = (n / 128 + unit - 1) / unit * unit;
+    return c > (1ull << 20) ? (1ull << 20) : c;
+}
+
 // ---- host-side state -------------------------------------------------------------------
 #ifdef __cplusplus
 #include <atomic>
@@ -183,6 +192,7 @@ struct AcxRequest {
     bool in_graph;
     bool host_transport;      // no-GPU mode: backed by an MPI_Request
     bool null_op;             // peer was MPI_PROC_NULL: completes immediately, moves nothing, owns no slot
+    bool coop;                // ACX_COOP: large rendezvous operation whose mover claims chunks cooperatively; the wait launches a coop_kernel in front of the wait kernel
     bool typed;               // non-contiguous datatype: the wire image is staged in the heap (bounce_off), packed before the send / unpacked after the wait
     AcxLayout layout;
     bool wild;                // wildcard receive (MPI_ANY_SOURCE / MPI_ANY_TAG): matched by recv_any_kernel when the wait runs

@@ -247,7 +247,7 @@ struct MoverParams {
     acx_entry *ring;        // push: peer-mapped ring; pull: local ring
     acx_sack *sack;         // push: local sack; pull: peer-mapped sack at the sender
     uint32_t depth, push, peer, vec256;
-    uint32_t block_bytes, pad1;   // 0: one contiguous chunk per CTA; else CTAs sweep interleaved blocks of this size (DRAM-page friendly)
+    uint32_t block_bytes, coop;   // block_bytes 0: one contiguous chunk per CTA; else CTAs sweep interleaved blocks of this size (DRAM-page friendly). coop: claim chunks from the shared cursor (ACX_COOP)
     TraceCtx tr;
 };
 
@@ -276,12 +276,57 @@ __global__ void push_gate(GateParams p) {
     p.op->mover = 1;
 }
 
+// Cooperative moving (ACX_COOP=1): the payload is cut into acx_coop_chunk(n)-byte chunks behind an atomic cursor in the
+// RECEIVER's ring entry. Any CTA on either GPU may act as an agent: claim a chunk, copy it from its side (a sender pushes,
+// a receiver pulls), count it done; whoever completes the last chunk publishes done / sdone. The second arriver's mover
+// runs this loop, and so does the coop_kernel each side launches in front of its wait kernel, so a GPU that arrived
+// first — and would otherwise idle while its neighbour copies — takes its share.
+//   ent: the slot's entry at the receiver (local for a receiver, peer-mapped for a sender)
+__device__ __forceinline__ void coop_agent(acx_entry *ent, acx_sack *sk, char *dst, const char *src, uint64_t n, uint64_t g, uint32_t vec256) {
+    const uint64_t cb = acx_coop_chunk(n), C = (n + cb - 1) / cb;
+    __shared__ uint64_t s_claim;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            // The cursor carries the generation in its high half: a straggling agent of a finished generation (the
+            // receiver's wait kernel has already re-armed the slot) must not claim from the next one.
+            uint64_t cur = ld_acquire_sys(&ent->coop_cursor), got = ~0ull;
+            while ((uint32_t)(cur >> 32) == (uint32_t)g && (uint32_t)cur < C) {
+                const uint64_t seen = atom_cas_acqrel_sys(&ent->coop_cursor, cur, cur + 1);
+                if (seen == cur) { got = (uint32_t)cur; break; }
+                cur = seen;
+            }
+            s_claim = got;
+        }
+        __syncthreads();
+        const uint64_t i = s_claim;
+        __syncthreads();
+        if (i >= C) return;
+        const uint64_t lo = i * cb, len = n - lo < cb ? n - lo : cb;
+        if (vec256) copy_bytes_256(dst + lo, src + lo, len, threadIdx.x, blockDim.x);
+        else copy_bytes(dst + lo, src + lo, len, threadIdx.x, blockDim.x);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atom_add_acqrel_sys(&ent->coop_done, 1ull) == C - 1) {   // every chunk is in place (each agent released its copies)
+                st_release_sys(&ent->done, g + 1);    // receiver may consume
+                st_release_sys(&sk->sdone, g + 1);    // sender's buffer is reusable
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void mover_body(const MoverParams &p) {
     acx_op *op = p.op;
     if (!op->mover) return;
     const uint64_t n = op->n;
     char *peer = (char *)op->peer_ptr;
     if (blockIdx.x == 0 && threadIdx.x == 0) trace(p.tr, ACX_EV_MOVE_BEGIN, p.peer, op->ticket, n);
+    if (p.coop) {
+        const uint64_t k = op->ticket;
+        const uint32_t e = (uint32_t)(k % p.depth);
+        coop_agent(p.ring + e, p.sack + e, p.push ? peer : p.local, p.push ? p.local : peer, n, k / p.depth, p.vec256);
+        return;
+    }
     if (p.block_bytes) {
         // Interleaved blocks: at any instant the resident CTAs cover one contiguous window of the buffers, so the
         // DRAM pages they touch (source and destination) stay few — the access pattern of a plain elementwise copy.
@@ -461,7 +506,7 @@ __global__ void __launch_bounds__(kMoverThreads) recv_any_kernel(AnyParams p) {
     __syncthreads();
     MoverParams mp;
     mp.op = op; mp.local = p.dst; mp.ring = p.res->ring; mp.sack = p.res->sack;
-    mp.depth = (uint32_t)p.geom.depth; mp.push = 0; mp.peer = (uint32_t)p.res->src; mp.vec256 = p.vec256; mp.block_bytes = 0; mp.pad1 = 0; mp.tr = p.tr;
+    mp.depth = (uint32_t)p.geom.depth; mp.push = 0; mp.peer = (uint32_t)p.res->src; mp.vec256 = p.vec256; mp.block_bytes = 0; mp.coop = 0; mp.tr = p.tr;
     mover_body(mp);
     fused_exit(op);
 }
@@ -549,6 +594,77 @@ __global__ void __launch_bounds__(kTmaThreads) mover_tma(MoverParams p) {
     }
 }
 
+// Launched in front of the wait kernel for a large rendezvous request when ACX_COOP=1: coop_gate (one thread; waiting
+// here is legitimate, the user asked for a wait) returns once the peer has arrived or the transfer is complete, then
+// coop_kernel's CTAs join the agents of this message.
+struct CoopParams {
+    acx_op *op;
+    acx_entry *ring;      // the (src -> dst, chan) ring at the receiver: local for a receive, peer-mapped for a send
+    acx_sack *sack;       // acks at the sender: peer-mapped for a receive, local for a send
+    char *local;          // send: local source; receive: local landing address
+    char *peer_heap;
+    const uint64_t *xlat;
+    uint64_t bytes;       // send: message bytes; receive: capacity
+    uint32_t depth, is_send, vec256, pad;
+    Watchdog wd;
+};
+// One look at the slot (one thread): has the peer arrived, and if so what is there to move? Returns false while neither
+// the peer has arrived nor the transfer completed; *n == 0 on return true means "nothing for an agent to do".
+__device__ __forceinline__ bool coop_peek(const CoopParams &p, acx_entry *ent, acx_sack *sk, uint64_t g, uint64_t *n, uint64_t *peer) {
+    *n = 0; *peer = 0;
+    if (p.is_send) {
+        if (ld_acquire_sys(&sk->sdone) >= g + 1) return true;                     // already complete
+        if (ld_acquire_sys(&sk->r_gen) < g + 1) return false;                     // the receive is not posted yet
+        const uint64_t cap = ld_relaxed_sys(&sk->r_cap);                          // its destination is mirrored into my acks
+        *peer = (uint64_t)translate_peer(p.peer_heap, p.xlat, ld_relaxed_sys(&sk->r_dst_off));
+        *n = p.bytes < cap ? p.bytes : cap;
+        return true;
+    }
+    if (ld_acquire_sys(&ent->done) >= g + 1) return true;
+    if ((uint32_t)(ld_acquire_sys(&ent->state) >> 32) < (uint32_t)(g + 1)) return false;   // the send has not arrived yet
+    if (ent->s_kind == ACX_KIND_RNDV) {                                            // its header is in my entry
+        const uint64_t sb = ent->s_bytes;
+        *peer = (uint64_t)translate_peer(p.peer_heap, p.xlat, ent->s_src_off);
+        *n = sb < p.bytes ? sb : p.bytes;
+    }
+    return true;
+}
+// The waiting half, one thread: returns once the peer has arrived (or the transfer is complete), so the agent grid that
+// follows never spins and a late peer costs one resident warp, not half the GPU.
+__global__ void coop_gate(CoopParams p) {
+    pdl_prologue();
+    if (threadIdx.x != 0) return;
+    const uint64_t k = p.op->ticket;
+    const uint32_t e = (uint32_t)(k % p.depth);
+    uint64_t n, peer;
+    unsigned ns = 0;
+    const uint64_t t0 = p.wd.budget_ns ? globaltimer_ns() : 0;
+    while (!coop_peek(p, p.ring + e, p.sack + e, k / p.depth, &n, &peer)) {
+        if (ns) __nanosleep(ns);
+        ns = ns < 256 ? ns * 2 + 20 : 256;
+        if (p.wd.budget_ns && globaltimer_ns() - t0 > p.wd.budget_ns) { p.wd.diag[1] = k; p.wd.diag[2] = p.is_send; p.wd.diag[0] = 0x5e0c; __threadfence_system(); __trap(); }
+    }
+}
+__global__ void __launch_bounds__(kMoverThreads) coop_kernel(CoopParams p) {
+    pdl_prologue();
+    __shared__ uint64_t s_n, s_peer;
+    const uint64_t k = p.op->ticket;
+    const uint32_t e = (uint32_t)(k % p.depth);
+    const uint64_t g = k / p.depth;
+    acx_entry *ent = p.ring + e;
+    acx_sack *sk = p.sack + e;
+    if (threadIdx.x == 0) {
+        uint64_t n, peer;
+        if (!coop_peek(p, ent, sk, g, &n, &peer)) n = 0;   // cannot happen behind coop_gate; never spin here
+        s_n = n; s_peer = peer;
+    }
+    __syncthreads();
+    const uint64_t n = s_n;
+    if (!n) return;
+    char *peer = (char *)s_peer;
+    coop_agent(ent, sk, p.is_send ? peer : p.local, p.is_send ? p.local : peer, n, g, p.vec256);
+}
+
 // ---------------------------------------------------------------------------------------
 // Waits. One CTA per request, up to kWaitBatch requests per launch (Waitall = 1 launch).
 // ---------------------------------------------------------------------------------------
@@ -566,7 +682,7 @@ struct WaitOne {
     int32_t src, tag;
     uint32_t depth, eager_max;
     uint16_t is_recv, retire;
-    uint16_t bounce_kernel, pad16;  // bounce_kernel: a bounce_out_kernel follows (large private destination)
+    uint16_t bounce_kernel, coop;   // bounce_kernel: a bounce_out_kernel follows (large private destination); coop: reset the slot's chunk cursor when consuming (ACX_COOP)
     uint16_t off_source, off_tag, off_error, off_bytes;  // field offsets inside MPI_Status (0xffff = absent)
     const acx_anyres *any;  // wildcard receive: ring / sack / eager / src come from here (written by recv_any_kernel)
 };
@@ -644,6 +760,7 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
                 if (w.off_bytes != 0xffff) *(int64_t *)(w.ustatus + w.off_bytes) = (int64_t)n;
             }
             if (w.serial) { w.hstat->source = src; w.hstat->tag = stag; w.hstat->error = err; w.hstat->bytes = (int64_t)n; }
+            if (w.coop) { ent->coop_cursor = (g + 1) << 32; ent->coop_done = 0; __threadfence_system(); }   // re-arm the chunk cursor for generation g+1 before the slot is handed on
             // All reads of the slot are complete (data dependence + barrier): plain stores suffice.
             st_relaxed_sys(&ent->consumed, g + 1);
             st_relaxed_sys(&sack[e].efree, g + 1);  // remote: slot may be reused by generation g+1

@@ -37,6 +37,13 @@ done
 for br in 0 1; do echo "ring branch=$br: $(ACX_PEER_BRANCH=$br ACX_HEAP_BYTES=1g run bin/p2p_bench ring --bytes 268435456 | tail -n 1)"; done
 for br in 0 1; do echo "pingpong branch=$br: $(ACX_PEER_BRANCH=$br timeout 120 ./bin/acxrun -np 2 --timeout 100 bin/p2p_bench pingpong 2>&1 | tail -n 1 | cut -c1-400)"; done
 
+echo "### 3a. ACX_COOP=1 (cooperative moving with chunk stealing): conformance, then the ring in 'simple' order (no pre-posting) against the default"
+for t in large_msgs ring_all_device ring_all_graph ordering stress regcache; do ACX_COOP=1 run build/tests/$t 16777216 | tail -n 1; done
+for coop in 0 1; do echo "ring coop=$coop: $(ACX_COOP=$coop ACX_HEAP_BYTES=1g run bin/p2p_bench ring --bytes 268435456 | tail -n 1)"; done
+for coop in 0 1; do
+  ACX_COOP=$coop timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29704 bench.py --gpus $NP --order simple --no-extras 2>/dev/null | grep '^{' | tail -n 1 | cut -c1-260
+done
+
 echo "### 3b. ACX_PBATCH=1 (batched partitioned Start/Wait): conformance + API-level halo step against the default and the reference"
 for np in 1 $NP; do ACX_PBATCH=1 timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/ring_partitioned 2>&1 | tail -n 1; done
 for pbv in 0 1; do echo "halo api pbatch=$pbv: $(ACX_PBATCH=$pbv run bin/halo_bench api --n 512 --steps 10 | tail -n 1)"; done
