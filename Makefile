@@ -14,7 +14,7 @@ BINS  := bin/acxrun
 BENCH := $(patsubst bench/%.cu,bin/%,$(wildcard bench/*.cu))
 CTESTS := $(patsubst tests/c/%.c,$(B)/tests/%,$(wildcard tests/c/*.c)) $(patsubst tests/c/%.cu,$(B)/tests/%,$(wildcard tests/c/*.cu))
 
-.PHONY: all clean lib tests bench examples tsan asan install
+.PHONY: all clean lib tests bench examples tsan asan install extmpi-check extmpi-lib
 all: lib $(BINS) tests bench
 bench: $(BENCH)
 bin/%: bench/%.cu $(LIB)
@@ -42,6 +42,7 @@ $(B)/k_%.o: src/kernels/%.cu include/mpi-acx.h include/acx_device.cuh include/ac
 $(LIB): $(B)/acx.o $(B)/minimpi.o $(KOBJS) src/core/acx.map
 	@mkdir -p lib
 	$(NVCC) $(GENCODE) -shared -o $@ $(filter %.o,$^) -cudart static -ldl -lpthread -lrt -Xlinker --version-script=src/core/acx.map
+	ln -sf libacx.so lib/libmpi-acx.so   # the reference's library name: `-lmpi-acx` keeps working
 
 bin/acxrun: launcher/acxrun.cpp
 	@mkdir -p bin
@@ -60,6 +61,25 @@ examples: $(LIB)
 	$(NVCC) $(GENCODE) -O2 -Iinclude examples/stream_ring.c -o $(B)/examples/stream_ring -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
 	$(NVCC) $(GENCODE) -O2 -Iinclude examples/partitioned_producer.cu -o $(B)/examples/partitioned_producer -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
 
+# Portability check (compile only, no MPI needed): build the runtime and the fused kernels against a declarations-only
+# MPI whose handles are pointers to opaque structs (Open MPI style) instead of the bundled mini-MPI's integers. Proves
+# nothing outside the #ifdef ACX_MINI_MPI sections depends on the bundled library.
+extmpi-check:
+	@mkdir -p $(B)/extmpi
+	for f in src/core/acx.cu src/kernels/halo_stencil.cu src/kernels/pp_gemm.cu; do \
+	  $(NVCC) $(GENCODE) -std=c++17 -Itools/extmpi_stub -Iinclude -c $$f -o $(B)/extmpi/check.o || exit 1; done
+	@if nm -u $(B)/extmpi/check.o | grep -q ACX_Mpi; then echo "bundled-MPI extension used outside its guard"; exit 1; fi
+	@echo "extmpi-check: OK"
+
+# Build against an external MPI instead of the bundled one:  make extmpi-lib MPI_HOME=/opt/openmpi
+# (needs MPI-4 partitioned calls only for the host transport; produces lib/libacx_extmpi.so; untested here: the image has no MPI)
+extmpi-lib: $(KOBJS)
+	@test -n "$(MPI_HOME)" || (echo "set MPI_HOME"; exit 1)
+	@mkdir -p lib $(B)/extmpi
+	$(NVCC) $(GENCODE) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$(MPI_HOME)/include -Iinclude -c src/core/acx.cu -o $(B)/extmpi/acx.o
+	for f in halo_stencil pp_gemm; do $(NVCC) $(GENCODE) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I$(MPI_HOME)/include -Iinclude -c src/kernels/$$f.cu -o $(B)/extmpi/k_$$f.o || exit 1; done
+	$(NVCC) $(GENCODE) -shared -o lib/libacx_extmpi.so $(B)/extmpi/acx.o $(B)/extmpi/k_halo_stencil.o $(B)/extmpi/k_pp_gemm.o -cudart static -L$(MPI_HOME)/lib -lmpi -ldl -lpthread -lrt
+
 # Install headers, the library and the launcher (PREFIX=/usr/local by default): a program written for the reference then
 # builds with  nvcc -I$(PREFIX)/include prog.cu -L$(PREFIX)/lib -lacx
 PREFIX ?= /usr/local
@@ -67,6 +87,7 @@ install: lib bin/acxrun
 	install -d $(DESTDIR)$(PREFIX)/include $(DESTDIR)$(PREFIX)/lib $(DESTDIR)$(PREFIX)/bin
 	install -m 644 include/mpi-acx.h include/acx_device.cuh include/acx_kernels.h include/mpi.h $(DESTDIR)$(PREFIX)/include/
 	install -m 755 lib/libacx.so $(DESTDIR)$(PREFIX)/lib/
+	ln -sf libacx.so $(DESTDIR)$(PREFIX)/lib/libmpi-acx.so
 	install -m 644 lib/libacxmpi.a $(DESTDIR)$(PREFIX)/lib/
 	install -m 755 bin/acxrun $(DESTDIR)$(PREFIX)/bin/
 

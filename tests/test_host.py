@@ -202,3 +202,10 @@ def test_nccl_baseline_tool_control_flow(mode):
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert d["impl"] == "nccl-p2p" and d["bad_words"] == 0 and d["n_gpus"] == 2
+
+
+def test_library_compiles_against_pointer_handle_mpi(built):
+    """`make extmpi-check`: the runtime and the fused kernels build against an Open-MPI-shaped (pointer handles) MPI
+    header, i.e. nothing outside the ACX_MINI_MPI sections depends on the bundled mini-MPI."""
+    r = subprocess.run(["make", "-C", str(built), "extmpi-check"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "extmpi-check: OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
