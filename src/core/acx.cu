@@ -1271,10 +1271,9 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         const bool fused = fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas;   // measured: pays off from ~512 KiB, costs ~1.5 us below
         const bool apush = !eager && !fused && g_apush && g_side_on && qtype == MPIX_QUEUE_CUDA_STREAM;
         sp.apush = apush ? 1 : 0;
-        // Cooperative moving: same decision on both ends (it depends on the message size only; a receive posted with a
-        // larger capacity than the message is handled by the agents' own n = min(bytes, cap))
+        // Cooperative moving is a property of the MESSAGE, chosen here from its size and announced in the header
         r->coop = g_coop && !eager && !fused && !apush && !g_mover_tma && (long)bytes >= g_coop_min;
-        mp.coop = r->coop ? 1 : 0;
+        sp.coop = r->coop ? 1 : 0;   // travels in the message header: the receiver follows the sender's choice
         if (!dropped && fused) { if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail; }
         else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
         if (!eager) {
@@ -1394,8 +1393,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         mp.op = rp.op; mp.local = dst_local; mp.ring = rp.ring; mp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;
         mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr; mp.vec256 = g_mover_256; mp.block_bytes = (uint32_t)g_mover_block;
         const int fgrid = (rndv_capable && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
-        r->coop = g_coop && rndv_capable && !(fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas) && !g_apush && !g_mover_tma && (long)bytes >= g_coop_min;
-        mp.coop = r->coop ? 1 : 0;
+        r->coop = g_coop && rndv_capable && !g_apush && !g_mover_tma && (long)bytes >= g_coop_min;   // "may be": the wait's gate + agent kernels help only if the message says RNDV_COOP
         if (fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas) {
             if ((rc = em.launch2(recv_rndv_fused, dim3(fgrid), dim3(kMoverThreads), rp, mp))) goto fail;
         } else {

@@ -30,7 +30,7 @@
 #include "../../include/acx_device.cuh"
 
 // ---- shared host/device layout -----------------------------------------------------
-enum { ACX_KIND_EAGER = 1, ACX_KIND_RNDV = 2, ACX_KIND_RNDV_PUSH = 3 };   // RNDV: second arriver moves; RNDV_PUSH: the sender always pushes
+enum { ACX_KIND_EAGER = 1, ACX_KIND_RNDV = 2, ACX_KIND_RNDV_PUSH = 3, ACX_KIND_RNDV_COOP = 4 };   // RNDV: second arriver moves; RNDV_PUSH: the sender always pushes; RNDV_COOP: second arriver moves, both ends may help (chunk cursor)
 
 // Buffer locations travel as 64-bit "offsets": bit 63 clear = offset into the owner's symmetric heap;
 // bit 63 set = registered user allocation: bits [62:48] registration index, bits [47:0] offset inside it
@@ -72,7 +72,7 @@ struct alignas(64) acx_op {  // per request slot, local
     uint64_t recv_bytes; // receive side: actual message size
     uint64_t bounce_n;   // receive side: bytes the bounce-out kernel still has to copy (0 if eager/zero-copy)
     uint64_t fused_decided;  // single-launch rendezvous gate: 1 once CTA 0 has published the match of this launch
-    uint64_t pad2;
+    uint64_t coop;       // this message is moved cooperatively (kind RNDV_COOP): the mover claims chunks from the slot's cursor
 };
 
 struct acx_anyres {  // resolution of a wildcard receive (device memory, one per request slot): which ring the matched message sits in

@@ -121,7 +121,7 @@ struct SendParams {
     uint64_t bytes;
     uint64_t serial;
     uint32_t tag, depth, eager_max, peer;
-    uint32_t apush, pad0;   // apush: deterministic mode — this sender pushes the payload itself (gate + mover on its channel stream)
+    uint32_t apush, coop;   // apush: deterministic mode — this sender pushes the payload itself (gate + mover on its channel stream); coop: announce the message as RNDV_COOP (ACX_COOP)
     Watchdog wd;
     TraceCtx tr;
 };
@@ -134,9 +134,9 @@ __device__ __forceinline__ void send_rndv_match(const SendParams &p, uint64_t k)
     acx_entry *ent = p.ring + e;
 
     ent->s_src_off = p.src_off; ent->s_bytes = p.bytes;
-    *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)(p.apush ? ACX_KIND_RNDV_PUSH : ACX_KIND_RNDV) << 32);
+    *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)(p.apush ? ACX_KIND_RNDV_PUSH : p.coop ? ACX_KIND_RNDV_COOP : ACX_KIND_RNDV) << 32);
     uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull << 32);
-    p.op->ticket = k; p.op->eager = 0; p.op->cta_count = 0;
+    p.op->ticket = k; p.op->eager = 0; p.op->cta_count = 0; p.op->coop = p.coop;
     if (p.apush) {
         p.op->mover = 0;   // decided by push_gate on the channel stream once the receive is posted
     } else if ((uint32_t)old == (uint32_t)(g + 1)) {  // receive already posted: I move the data (push)
@@ -213,8 +213,9 @@ __device__ __forceinline__ void recv_match_at(const RecvParams &p, uint64_t k) {
         st_release_sys(&p.sack[e].r_gen, g + 1);   // a pushing sender's gate keys on this
     }
     uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull);   // release orders the mirror stores before it
-    p.op->ticket = k; p.op->cta_count = 0; p.op->mover = 0; p.op->bounce_n = 0;
-    if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && ent->s_kind == ACX_KIND_RNDV) {
+    p.op->ticket = k; p.op->cta_count = 0; p.op->mover = 0; p.op->bounce_n = 0; p.op->coop = 0;
+    if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && (ent->s_kind == ACX_KIND_RNDV || ent->s_kind == ACX_KIND_RNDV_COOP)) {
+        p.op->coop = ent->s_kind == ACX_KIND_RNDV_COOP;   // the sender decides how its message is moved
         // the send is already here and waiting: I move the data (pull)
         uint64_t sb = ent->s_bytes;
         p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, ent->s_src_off);
@@ -247,7 +248,7 @@ struct MoverParams {
     acx_entry *ring;        // push: peer-mapped ring; pull: local ring
     acx_sack *sack;         // push: local sack; pull: peer-mapped sack at the sender
     uint32_t depth, push, peer, vec256;
-    uint32_t block_bytes, coop;   // block_bytes 0: one contiguous chunk per CTA; else CTAs sweep interleaved blocks of this size (DRAM-page friendly). coop: claim chunks from the shared cursor (ACX_COOP)
+    uint32_t block_bytes, pad1;   // 0: one contiguous chunk per CTA; else CTAs sweep interleaved blocks of this size (DRAM-page friendly)
     TraceCtx tr;
 };
 
@@ -321,7 +322,7 @@ __device__ __forceinline__ void mover_body(const MoverParams &p) {
     const uint64_t n = op->n;
     char *peer = (char *)op->peer_ptr;
     if (blockIdx.x == 0 && threadIdx.x == 0) trace(p.tr, ACX_EV_MOVE_BEGIN, p.peer, op->ticket, n);
-    if (p.coop) {
+    if (op->coop) {
         const uint64_t k = op->ticket;
         const uint32_t e = (uint32_t)(k % p.depth);
         coop_agent(p.ring + e, p.sack + e, p.push ? peer : p.local, p.push ? p.local : peer, n, k / p.depth, p.vec256);
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(kMoverThreads) recv_any_kernel(AnyParams p) {
     __syncthreads();
     MoverParams mp;
     mp.op = op; mp.local = p.dst; mp.ring = p.res->ring; mp.sack = p.res->sack;
-    mp.depth = (uint32_t)p.geom.depth; mp.push = 0; mp.peer = (uint32_t)p.res->src; mp.vec256 = p.vec256; mp.block_bytes = 0; mp.coop = 0; mp.tr = p.tr;
+    mp.depth = (uint32_t)p.geom.depth; mp.push = 0; mp.peer = (uint32_t)p.res->src; mp.vec256 = p.vec256; mp.block_bytes = 0; mp.pad1 = 0; mp.tr = p.tr;
     mover_body(mp);
     fused_exit(op);
 }
@@ -622,7 +623,7 @@ __device__ __forceinline__ bool coop_peek(const CoopParams &p, acx_entry *ent, a
     }
     if (ld_acquire_sys(&ent->done) >= g + 1) return true;
     if ((uint32_t)(ld_acquire_sys(&ent->state) >> 32) < (uint32_t)(g + 1)) return false;   // the send has not arrived yet
-    if (ent->s_kind == ACX_KIND_RNDV) {                                            // its header is in my entry
+    if (ent->s_kind == ACX_KIND_RNDV_COOP) {                                       // its header is in my entry; only messages announced as cooperative have a cursor
         const uint64_t sb = ent->s_bytes;
         *peer = (uint64_t)translate_peer(p.peer_heap, p.xlat, ent->s_src_off);
         *n = sb < p.bytes ? sb : p.bytes;
