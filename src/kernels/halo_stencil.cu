@@ -447,6 +447,122 @@ __global__ void __launch_bounds__(LX * TY, MINB) halo_stencil_step_direct(HaloDe
     }
 }
 
+// Deeper-prefetch flavour of the direct kernel (ACX_HALO_VARIANT=7: PD=2, 8: PD=3; not the default — written after the
+// round's GPU budget was spent, to be measured next). ncu on the direct kernel shows ideal DRAM traffic but too few
+// DRAM-missing loads in flight per SM: only the own-row load of the next plane misses (the y+-1 rows and x edges hit in
+// L1/L2), one per thread. Here the own-row loads run PD planes ahead in a register ring (4 registers per stage), so
+// each SM keeps PD x 8 KiB of DRAM reads in flight instead of 8 KiB; everything else is the direct kernel unchanged.
+template <int PD>
+__global__ void __launch_bounds__(LX * TY, 1) halo_stencil_step_direct_pd(HaloDev P) {
+    static_assert(PD >= 2 && PD < TZ, "prefetch depth");
+    __shared__ __align__(16) __nv_bfloat16 xface[2][TZ * TY];
+    const int lx = threadIdx.x, ly = threadIdx.y, tid = ly * LX + lx;
+    const size_t plane = (size_t)P.nx * P.ny;
+    for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x) {
+        const int t = P.order[it];
+        const int tx = t % P.ntx, ty = (t / P.ntx) % P.nty, tz = t / (P.ntx * P.nty);
+        const bool fxm = tx == 0, fxp = tx == P.ntx - 1, fym = ty == 0, fyp = ty == P.nty - 1, fzm = tz == 0, fzp = tz == P.ntz - 1;
+        const int px_ = tz * P.nty + ty, py_ = tz * P.ntx + tx, pz_ = ty * P.ntx + tx;
+        if (tid == 0) {
+            if (fxm) acx::wait_arrived_epoch(P.recv[0], px_, P.wait_val);
+            if (fxp) acx::wait_arrived_epoch(P.recv[1], px_, P.wait_val);
+            if (fym) acx::wait_arrived_epoch(P.recv[2], py_, P.wait_val);
+            if (fyp) acx::wait_arrived_epoch(P.recv[3], py_, P.wait_val);
+            if (fzm) acx::wait_arrived_epoch(P.recv[4], pz_, P.wait_val);
+            if (fzp) acx::wait_arrived_epoch(P.recv[5], pz_, P.wait_val);
+        }
+        __syncthreads();
+        const int x0 = tx * TX + lx * 8, y = ty * TY + ly, z0 = tz * TZ;
+        const __nv_bfloat16 *c0p = P.u + (size_t)z0 * plane + (size_t)y * P.nx + x0;   // centre cell of plane z0
+        // --- operand sources, resolved once per tile: (pointer at plane z0, stride per plane in 16-B units or elements)
+        const uint4 *pc = reinterpret_cast<const uint4 *>(c0p);                 // own row
+        const size_t sc = plane / 8;
+        const uint4 *pym, *pyp; size_t sym, syp;                                // rows y-1 / y+1
+        if (ly == 0 && fym) { pym = (const uint4 *)acx::local_partition_ptr(P.recv[2], py_) + lx; sym = LX; }
+        else { pym = reinterpret_cast<const uint4 *>(c0p - P.nx); sym = sc; }
+        if (ly == TY - 1 && fyp) { pyp = (const uint4 *)acx::local_partition_ptr(P.recv[3], py_) + lx; syp = LX; }
+        else { pyp = reinterpret_cast<const uint4 *>(c0p + P.nx); syp = sc; }
+        const __nv_bfloat16 *pxe = c0p; size_t sxe = 0;                         // x-edge cell (lanes 0 and 31 only)
+        const bool xedge = lx == 0 || lx == LX - 1;
+        if (lx == 0) { if (fxm) { pxe = (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[0], px_) + ly; sxe = TY; } else { pxe = c0p - 1; sxe = plane; } }
+        if (lx == LX - 1) { if (fxp) { pxe = (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[1], px_) + ly; sxe = TY; } else { pxe = c0p + 8; sxe = plane; } }
+        uint4 *po = reinterpret_cast<uint4 *>(P.un + (size_t)z0 * plane + (size_t)y * P.nx + x0);
+        // remote landing buffers (packed): y faces advance one row of LX vectors per plane
+        uint4 *rym = (fym && ly == 0) ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[2], py_) + lx : nullptr;
+        uint4 *ryp = (fyp && ly == TY - 1) ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[3], py_) + lx : nullptr;
+        uint4 *rzm = fzm ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[4], pz_) + ly * LX + lx : nullptr;
+        uint4 *rzp = fzp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[5], pz_) + ly * LX + lx : nullptr;
+        __nv_bfloat16 *sxm = (fxm && lx == 0) ? &xface[0][ly] : nullptr, *sxp = (fxp && lx == LX - 1) ? &xface[1][ly] : nullptr;
+        // --- prologue: planes z0-1, z0, z0+1 and the first neighbours
+        float2 prev[4], cur[4];
+        unpack8x2(fzm ? ((const uint4 *)acx::local_partition_ptr(P.recv[4], pz_))[ly * LX + lx] : *(pc - sc), prev);
+        unpack8x2(*pc, cur);
+        // own-row ring: vq[i] holds plane z0 + 1 + i; plane z0 + TZ comes from the z+ landing buffer on a face tile
+        const uint4 *zp_land = fzp ? (const uint4 *)acx::local_partition_ptr(P.recv[5], pz_) + ly * LX + lx : nullptr;
+        uint4 vq[PD];
+#pragma unroll
+        for (int i = 0; i < PD; i++) vq[i] = *(pc + (size_t)(1 + i) * sc);       // PD < TZ: all inside the tile
+        uint4 vym = *pym, vyp = *pyp;
+        __nv_bfloat16 vxe = xedge ? *pxe : __float2bfloat16(0.f);
+        pym += sym; pyp += syp; pxe += sxe;
+#pragma unroll 2
+        for (int zl = 0; zl < TZ; zl++) {
+            // operands of THIS plane (own row loaded PD iterations ago, neighbours one iteration ago) ...
+            const uint4 un = vq[0], uym = vym, uyp = vyp;
+            const float edge = __bfloat162float(vxe);
+#pragma unroll
+            for (int i = 0; i + 1 < PD; i++) vq[i] = vq[i + 1];
+            // ... the loads of later planes go out before the math
+            const int q = zl + 1 + PD;                                           // own row, plane z0 + q
+            if (q < TZ) vq[PD - 1] = *(pc + (size_t)q * sc);
+            else if (q == TZ) vq[PD - 1] = zp_land ? *zp_land : *(pc + (size_t)q * sc);
+            if (zl + 1 < TZ) { vym = *pym; vyp = *pyp; if (xedge) vxe = *pxe; }
+            pym += sym; pyp += syp; pxe += sxe;
+            float2 ym[4], yp[4], nf[4], out[4];
+            unpack8x2(uym, ym); unpack8x2(uyp, yp); unpack8x2(un, nf);
+            float left = __shfl_up_sync(0xffffffffu, cur[3].y, 1), right = __shfl_down_sync(0xffffffffu, cur[0].x, 1);
+            if (lx == 0) left = edge;
+            if (lx == LX - 1) right = edge;
+            const float2 c0v = make_float2(P.c0, P.c0), c1v = make_float2(P.c1, P.c1);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // x-neighbour sums stay scalar (they straddle register pairs); everything else is FADD2/FMUL2/FFMA2
+                const float xs0 = (j == 0 ? left : cur[j - 1].y) + cur[j].y;
+                const float xs1 = cur[j].x + (j == 3 ? right : cur[j + 1].x);
+                const float2 t = __fadd2_rn(__fadd2_rn(make_float2(xs0, xs1), __fadd2_rn(ym[j], yp[j])), __fadd2_rn(prev[j], nf[j]));
+                out[j] = __ffma2_rn(c0v, cur[j], __fmul2_rn(c1v, t));
+            }
+            const uint4 vo = pack8x2(out);
+            *po = vo; po += sc;
+            if (rym) { *rym = vo; rym += LX; }
+            if (ryp) { *ryp = vo; ryp += LX; }
+            if (zl == 0 && rzm) *rzm = vo;
+            if (zl == TZ - 1 && rzp) *rzp = vo;
+            if (sxm) { *sxm = reinterpret_cast<const __nv_bfloat16 *>(&vo)[0]; sxm += TY; }
+            if (sxp) { *sxp = reinterpret_cast<const __nv_bfloat16 *>(&vo)[7]; sxp += TY; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { prev[j] = cur[j]; cur[j] = nf[j]; }
+        }
+        __syncthreads();
+        if (fxm && tid < TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[0], px_))[tid] = ((const uint4 *)xface[0])[tid];
+        if (fxp && tid >= 64 && tid < 64 + TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[1], px_))[tid - 64] = ((const uint4 *)xface[1])[tid - 64];
+        if (fxm | fxp | fym | fyp | fzm | fzp) {
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence_system();
+                if (fxm) acx::pready_signal_epoch(px_, P.send[0], P.signal_val);
+                if (fxp) acx::pready_signal_epoch(px_, P.send[1], P.signal_val);
+                if (fym) acx::pready_signal_epoch(py_, P.send[2], P.signal_val);
+                if (fyp) acx::pready_signal_epoch(py_, P.send[3], P.signal_val);
+                if (fzm) acx::pready_signal_epoch(pz_, P.send[4], P.signal_val);
+                if (fzp) acx::pready_signal_epoch(pz_, P.send[5], P.signal_val);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+
 // Initial exchange: faces of u^0 -> neighbours' parity-0 landing buffers, flag value 1.
 // One CTA per (face, partition).
 struct PackDev {
@@ -558,6 +674,8 @@ extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, f
     else if (h->variant == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_rows<3>, NW * 32, 0);
     else if (h->variant == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_rows<2>, NW * 32, 0);
     else if (h->variant == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_direct<1>, LX * TY, 0);
+    else if (h->variant == 7) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_direct_pd<2>, LX * TY, 0);
+    else if (h->variant == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_direct_pd<3>, LX * TY, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_direct<2>, LX * TY, 0);
     if (occ < 1) occ = 1;
     h->grid = std::min(h->ntiles, sms * occ);
@@ -598,6 +716,8 @@ extern "C" int acx_halo_step(acx_halo *h, int nsteps, cudaStream_t stream) {
         else if (h->variant == 3) halo_stencil_step_rows<3><<<h->grid, NW * 32, 0, stream>>>(P);
         else if (h->variant == 4) halo_stencil_step_rows<2><<<h->grid, NW * 32, 0, stream>>>(P);
         else if (h->variant == 5) halo_stencil_step_direct<1><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
+        else if (h->variant == 7) halo_stencil_step_direct_pd<2><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
+        else if (h->variant == 8) halo_stencil_step_direct_pd<3><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
         else halo_stencil_step_direct<2><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
         HCK(cudaGetLastError());
         h->cur ^= 1;

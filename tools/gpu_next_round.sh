@@ -49,6 +49,22 @@ for np in 1 $NP; do ACX_PBATCH=1 timeout 90 ./bin/acxrun -np $np --timeout 80 bu
 for pbv in 0 1; do echo "halo api pbatch=$pbv: $(ACX_PBATCH=$pbv run bin/halo_bench api --n 512 --steps 10 | tail -n 1)"; done
 echo "halo api reference: $(run $R/halo_bench api --n 512 --steps 10 | tail -n 1)"
 
+echo "### 3c. halo kernel: deeper own-row prefetch (variants 7 = PD2, 8 = PD3) against the default (5): numerics, then 512^3 step time"
+for v in 5 7 8; do
+  ACX_HALO_VARIANT=$v timeout 120 python - <<'PY' 2>&1 | tail -n 1
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+import mpi_acx_b200 as acx
+from mpi_acx_b200.ops import HaloStencil, stencil_reference
+acx.init(0)
+op = HaloStencil(256, 32, 64, (1, 1, 1)); torch.manual_seed(3)
+u0 = torch.randn(64, 32, 256, device="cuda").to(torch.bfloat16); op.field().copy_(u0); op.step(5); torch.cuda.synchronize()
+print("variant", os.environ["ACX_HALO_VARIANT"], "max abs err", (op.field().float() - stencil_reference(u0, steps=5).float()).abs().max().item())
+op.close(); acx.finalize()
+PY
+  echo "halo fused variant=$v: $(ACX_HALO_VARIANT=$v run bin/halo_bench fused --n 512 --steps 30 | tail -n 1)"
+done
+
 echo "### 4. ring with pre-posted receives (C harness) and bench.py at N=$NP (auto order = prepost from 3 GPUs up)"
 ACX_HEAP_BYTES=1g run bin/p2p_bench ring --bytes 268435456 --prepost | tee $O/ring_acx_prepost_n${NP}.json
 run $R/p2p_bench ring --bytes 268435456 --no-heap --prepost | tee $O/ring_ref_prepost_n${NP}.json
