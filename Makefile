@@ -14,7 +14,7 @@ BINS  := bin/acxrun
 BENCH := $(patsubst bench/%.cu,bin/%,$(wildcard bench/*.cu))
 CTESTS := $(patsubst tests/c/%.c,$(B)/tests/%,$(wildcard tests/c/*.c)) $(patsubst tests/c/%.cu,$(B)/tests/%,$(wildcard tests/c/*.cu))
 
-.PHONY: all clean lib tests bench examples tsan asan install extmpi-check extmpi-lib
+.PHONY: all clean lib tests bench examples tsan asan install extmpi-check extmpi-lib emu emu-tsan
 all: lib $(BINS) tests bench
 bench: $(BENCH)
 bin/%: bench/%.cu $(LIB)
@@ -90,6 +90,14 @@ install: lib bin/acxrun
 	ln -sf libacx.so $(DESTDIR)$(PREFIX)/lib/libmpi-acx.so
 	install -m 644 lib/libacxmpi.a $(DESTDIR)$(PREFIX)/lib/
 	install -m 755 bin/acxrun $(DESTDIR)$(PREFIX)/bin/
+
+# Host-side protocol emulation: the device kernels of src/core/kernels.cuh compiled as plain C++ and run on CPU threads
+# (one OS thread per CTA, one fiber per CUDA thread) for several ranks in one process. No GPU, no libacx.so.
+EMU_FLAGS := -std=c++17 -g -I/usr/local/cuda/include -Iinclude -Isrc/core
+emu:
+	@mkdir -p $(B)/tests
+	$(CXX) -O1 $(EMU_FLAGS) tests/emu/protocol_emu.cpp -o $(B)/tests/protocol_emu -lpthread
+	$(B)/tests/protocol_emu
 
 clean:
 	rm -rf $(B) lib bin

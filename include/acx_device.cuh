@@ -13,9 +13,12 @@
 
 #include <stdint.h>
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__)
 #define ACX_HD __host__ __device__
 #define ACX_D __device__ __forceinline__
+#elif defined(ACX_EMU)   // host-side protocol emulation (tests/emu): device code compiled as plain C++
+#define ACX_HD
+#define ACX_D inline
 #else
 #define ACX_HD
 #endif
@@ -41,10 +44,22 @@ struct acx_pchan {
     int32_t pad;
 };
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(ACX_EMU)
 namespace acx {
 
 // ---- system-scope flag primitives ---------------------------------------------------
+#ifdef ACX_EMU   // same names, C++ atomics: lets tests/emu run the protocol kernels on CPU threads
+ACX_D uint64_t ld_acquire_sys(const uint64_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+ACX_D uint64_t ld_relaxed_sys(const uint64_t *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+ACX_D void st_release_sys(uint64_t *p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+ACX_D void st_relaxed_sys(uint64_t *p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+ACX_D void red_release_add_sys(uint64_t *p, uint64_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
+ACX_D uint64_t atom_add_acqrel_sys(uint64_t *p, uint64_t v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+ACX_D uint64_t atom_cas_acqrel_sys(uint64_t *p, uint64_t cmp, uint64_t val) {
+    __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+    return cmp;   // the value found (== the expected one on success), like atom.cas
+}
+#else
 ACX_D uint64_t ld_acquire_sys(const uint64_t *p) {
     uint64_t v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -74,6 +89,7 @@ ACX_D uint64_t atom_cas_acqrel_sys(uint64_t *p, uint64_t cmp, uint64_t val) {
     asm volatile("atom.acq_rel.sys.global.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(cmp), "l"(val) : "memory");
     return old;
 }
+#endif  // ACX_EMU
 // Spin until *p >= v (acquire). Exponential nanosleep backoff keeps the LSU quiet.
 ACX_D void wait_geq_sys(const uint64_t *p, uint64_t v) {
     unsigned ns = 0;

@@ -478,20 +478,8 @@ static void make_geom(acx_geom &g, int n) {
     acx_env_int("ACX_NPFLAGS", nullptr, 1 << 16, &v); g.npflags = (uint32_t)v;
     acx_env_int("ACX_TRACE_RECORDS", nullptr, 1 << 14, &v);
     uint32_t nt = 1; while (nt < (uint32_t)v) nt <<= 1; g.ntrace = nt;
-    auto up = [](uint64_t x) { return (x + 255) & ~255ull; };
-    uint64_t o = 0;
-    uint64_t nslots = (uint64_t)n * g.nchan * g.depth;
-    g.off_entries = o;  o = up(o + nslots * sizeof(acx_entry));
-    g.off_sack = o;     o = up(o + nslots * sizeof(acx_sack));
-    g.off_send_seq = o; o = up(o + (uint64_t)n * g.nchan * 8);
-    g.off_recv_seq = o; o = up(o + (uint64_t)n * g.nchan * 8);
-    g.off_ops = o;      o = up(o + (uint64_t)g.nops * sizeof(acx_op));
-    g.off_pflags = o;   o = up(o + (uint64_t)g.npflags * 8);
-    g.off_trace = o;    o = up(o + (uint64_t)g.ntrace * sizeof(acx_trace_rec));
     acx_env_int("ACX_MAXREG", nullptr, 64, &v); g.maxreg = (uint32_t)std::min(std::max(1L, v), 64L);
-    g.off_xlat = o;     o = up(o + (uint64_t)n * g.maxreg * 8);
-    g.off_eager = o;    o = up(o + nslots * g.eager_max);
-    g.bytes = o;
+    acx_geom_layout(g);
 }
 
 // Reference: MPIX_Init, src/init.cpp:157-253 (flag table in mapped host memory + proxy thread). Here: device windows,

@@ -110,6 +110,24 @@ struct acx_geom {
 #endif
 ACX_HDI uint64_t acx_entry_index(const acx_geom &g, int src, int chan, int e) { return ((uint64_t)src * g.nchan + chan) * g.depth + e; }
 
+// Offsets of a control window from its configuration (nranks, nchan, depth, nops, eager_max, npflags, ntrace, maxreg
+// must be filled in). One definition for the runtime and for the host-side protocol emulation (tests/emu).
+inline void acx_geom_layout(acx_geom &g) {
+    auto up = [](uint64_t x) { return (x + 255) & ~255ull; };
+    const uint64_t n = (uint64_t)g.nranks, nslots = n * g.nchan * g.depth;
+    uint64_t o = 0;
+    g.off_entries = o;  o = up(o + nslots * sizeof(acx_entry));
+    g.off_sack = o;     o = up(o + nslots * sizeof(acx_sack));
+    g.off_send_seq = o; o = up(o + n * g.nchan * 8);
+    g.off_recv_seq = o; o = up(o + n * g.nchan * 8);
+    g.off_ops = o;      o = up(o + (uint64_t)g.nops * sizeof(acx_op));
+    g.off_pflags = o;   o = up(o + (uint64_t)g.npflags * 8);
+    g.off_trace = o;    o = up(o + (uint64_t)g.ntrace * sizeof(acx_trace_rec));
+    g.off_xlat = o;     o = up(o + n * g.maxreg * 8);
+    g.off_eager = o;    o = up(o + nslots * g.eager_max);
+    g.bytes = o;
+}
+
 // Strided datatype layout as the pack / unpack kernels consume it. Work is split in `vec`-byte units (the widest power of
 // two <= 16 dividing the run, every stride in use and both base addresses); unit j of the packed image belongs at
 // acx_layout_unit_offset(L, j) bytes from the user's buffer address.

@@ -26,6 +26,10 @@ struct TraceCtx {
 // Programmatic dependent launch: let the NEXT kernel in the stream get scheduled while this one still runs,
 // then wait for the PREVIOUS kernel's completion + memory flush before touching anything. Both instructions
 // are no-ops when the launch did not opt in (ACX_PDL=0, graph nodes, user kernels in between).
+#ifdef ACX_EMU   // host-side protocol emulation (tests/emu): kernels are called as functions in stream order
+__device__ __forceinline__ void pdl_prologue() {}
+__device__ __forceinline__ uint64_t globaltimer_ns() { return emu::now_ns(); }
+#else
 __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -36,6 +40,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#endif
 __device__ __forceinline__ void trace(const TraceCtx &t, uint32_t ev, uint32_t peer, uint64_t a, uint64_t b) {
     if (!t.ring) return;
     uint64_t i = atomicAdd((unsigned long long *)t.cursor, 1ull);
@@ -66,6 +71,10 @@ __device__ __forceinline__ void spin_geq(const uint64_t *p, uint64_t v, const Wa
 // 256-bit (LDG.256 / STG.256, new on sm_100) copy loop: half the LSU instructions per byte and
 // 1-KiB contiguous runs per warp instruction. Needs 32-B aligned pointers; tail via copy_bytes.
 struct alignas(32) v8u32 { uint32_t r[8]; };
+#ifdef ACX_EMU
+__device__ __forceinline__ v8u32 ld256(const char *p) { v8u32 v; memcpy(&v, p, 32); return v; }
+__device__ __forceinline__ void st256(char *p, const v8u32 &v) { memcpy(p, &v, 32); }
+#else
 __device__ __forceinline__ v8u32 ld256(const char *p) {
     v8u32 v;
     asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -76,6 +85,7 @@ __device__ __forceinline__ void st256(char *p, const v8u32 &v) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"l"(p), "r"(v.r[0]), "r"(v.r[1]), "r"(v.r[2]), "r"(v.r[3]), "r"(v.r[4]), "r"(v.r[5]), "r"(v.r[6]), "r"(v.r[7]) : "memory");
 }
+#endif
 __device__ __forceinline__ void copy_bytes_256(char *dst, const char *src, uint64_t n, unsigned tid, unsigned nthr) {
     if ((((uintptr_t)dst | (uintptr_t)src) & 31) != 0) { copy_bytes(dst, src, n, tid, nthr); return; }
     const uint64_t nv = n >> 5;
@@ -519,6 +529,7 @@ __global__ void __launch_bounds__(kMoverThreads) recv_any_kernel(AnyParams p) {
 // of 2048 LDG/STG pairs; peer addresses are served over NVLink by the TMA unit directly.
 // Falls back to the LDG/STG loop for pointers/sizes that are not 16-B aligned.
 // ---------------------------------------------------------------------------------------
+#ifndef ACX_EMU   // inline PTX throughout; the emulation exercises the LDG/STG mover
 constexpr int kTmaStages = 4;
 constexpr uint32_t kTmaChunk = 16384;   // 4 x 16 KiB per CTA: three CTAs fit per SM, so a pushing and a pulling mover can co-reside
 constexpr int kTmaThreads = 128;
@@ -594,6 +605,8 @@ __global__ void __launch_bounds__(kTmaThreads) mover_tma(MoverParams p) {
         }
     }
 }
+
+#endif  // !ACX_EMU
 
 // Launched in front of the wait kernel for a large rendezvous request when ACX_COOP=1: coop_gate (one thread; waiting
 // here is legitimate, the user asked for a wait) returns once the peer has arrived or the transfer is complete, then

@@ -209,3 +209,12 @@ def test_library_compiles_against_pointer_handle_mpi(built):
     header, i.e. nothing outside the ACX_MINI_MPI sections depends on the bundled mini-MPI."""
     r = subprocess.run(["make", "-C", str(built), "extmpi-check"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "extmpi-check: OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_device_protocol_on_cpu_threads(built):
+    """`make emu`: the protocol kernels of src/core/kernels.cuh (triggers, movers, waits, cooperative agents, wildcard
+    resolver, pack/unpack) compiled as plain C++ and run with real concurrency on CPU threads for 1-4 "ranks" with
+    randomized arrival orders (tests/emu). Checks matching, ring generations, credits, chunk claims and completion
+    accounting; memory-model fences are out of its reach (x86 is stronger than the GPU)."""
+    r = subprocess.run(["make", "-C", str(built), "emu"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "protocol_emu: PASS" in r.stdout, r.stdout[-2500:] + r.stderr[-2500:]
