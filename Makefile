@@ -14,7 +14,7 @@ BINS  := bin/acxrun
 BENCH := $(patsubst bench/%.cu,bin/%,$(wildcard bench/*.cu))
 CTESTS := $(patsubst tests/c/%.c,$(B)/tests/%,$(wildcard tests/c/*.c)) $(patsubst tests/c/%.cu,$(B)/tests/%,$(wildcard tests/c/*.cu))
 
-.PHONY: all clean lib tests bench examples tsan asan install extmpi-check extmpi-lib emu emu-tsan
+.PHONY: all clean lib tests bench examples tsan asan install extmpi-check extmpi-lib emu emu-lib emu-tests
 all: lib $(BINS) tests bench
 bench: $(BENCH)
 bin/%: bench/%.cu $(LIB)
@@ -91,13 +91,41 @@ install: lib bin/acxrun
 	install -m 644 lib/libacxmpi.a $(DESTDIR)$(PREFIX)/lib/
 	install -m 755 bin/acxrun $(DESTDIR)$(PREFIX)/bin/
 
-# Host-side protocol emulation: the device kernels of src/core/kernels.cuh compiled as plain C++ and run on CPU threads
-# (one OS thread per CTA, one fiber per CUDA thread) for several ranks in one process. No GPU, no libacx.so.
-EMU_FLAGS := -std=c++17 -g -I/usr/local/cuda/include -Iinclude -Isrc/core
+# ---- no-GPU emulation (tests/emu) ---------------------------------------------------------------------------------
+# `make emu`: the protocol kernels of src/core/kernels.cuh compiled as plain C++ and called directly, several ranks as
+# threads of one process (one OS thread per CTA, one fiber per CUDA thread). No GPU, no libacx.so.
+# `make emu-lib emu-tests`: build/emu/libacx_emu.so = the UNMODIFIED runtime (src/core/acx.cu as C++) + a software CUDA
+# runtime (tests/emu/cudart_emu.cpp: streams, events, capture, graphs, IPC memory) + the mini-MPI; the conformance
+# programs link against it and run under acxrun, one process per rank, on the *device* transport.
+CUDA_HOME ?= /usr/local/cuda
+EMU := $(B)/emu
+EMU_FLAGS := -std=c++17 -g -I$(CUDA_HOME)/include -Iinclude -Isrc/core -Itests/emu
+EMU_SAN ?=
 emu:
 	@mkdir -p $(B)/tests
 	$(CXX) -O1 $(EMU_FLAGS) tests/emu/protocol_emu.cpp -o $(B)/tests/protocol_emu -lpthread
 	$(B)/tests/protocol_emu
+
+EMU_CTESTS := $(patsubst tests/c/%.c,$(EMU)/tests/%,$(wildcard tests/c/*.c)) $(EMU)/tests/ring_partitioned
+emu-lib: $(EMU)/libacx_emu.so
+emu-tests: $(EMU_CTESTS)
+$(EMU)/acx.o: src/core/acx.cu src/core/internal.h src/core/kernels.cuh include/mpi-acx.h include/acx_device.cuh include/mpi.h tests/emu/cuda_emu.h
+	@mkdir -p $(EMU)
+	$(CXX) -O1 -fPIC $(EMU_FLAGS) $(EMU_SAN) -x c++ -include tests/emu/cuda_emu.h -c $< -o $@
+$(EMU)/cudart_emu.o: tests/emu/cudart_emu.cpp tests/emu/cuda_emu.h
+	@mkdir -p $(EMU)
+	$(CXX) -O1 -fPIC -Wall $(EMU_FLAGS) $(EMU_SAN) -c $< -o $@
+$(EMU)/minimpi.o: src/minimpi/minimpi.cpp include/mpi.h
+	@mkdir -p $(EMU)
+	$(CXX) $(CXXFLAGS) -g $(EMU_SAN) -c $< -o $@
+$(EMU)/libacx_emu.so: $(EMU)/acx.o $(EMU)/cudart_emu.o $(EMU)/minimpi.o
+	$(CXX) -shared $(EMU_SAN) -o $@ $^ -ldl -lpthread -lrt
+$(EMU)/tests/%: tests/c/%.c $(EMU)/libacx_emu.so tests/c/acx_test.h
+	@mkdir -p $(EMU)/tests
+	gcc -O1 -g $(EMU_SAN) -Iinclude -I$(CUDA_HOME)/include $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU)
+$(EMU)/tests/%: tests/c/%.cu $(EMU)/libacx_emu.so tests/c/acx_test.h tests/emu/cuda_emu.h
+	@mkdir -p $(EMU)/tests
+	$(CXX) -O1 $(EMU_FLAGS) $(EMU_SAN) -x c++ -include tests/emu/cuda_emu.h $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) -lpthread
 
 clean:
 	rm -rf $(B) lib bin

@@ -140,6 +140,18 @@ static __host__ __device__ __forceinline__ int MPIX_Parrived(void *request, int 
     return MPIX_Parrived_host((MPIX_Request *)request, partition, flag);
 #endif
 }
+#elif defined(ACX_EMU)
+/* Software device (tests/emu): kernels are plain functions run on fibers; one body serves host and "device" callers. */
+#include "acx_device.cuh"
+static inline int MPIX_Pready(int partition, void *request) {
+    return emu::cta ? acx::pready(partition, request) : MPIX_Pready_host(partition, (MPIX_Request *)request);
+}
+static inline int MPIX_Parrived(void *request, int partition, int *flag) {
+    if (!emu::cta) return MPIX_Parrived_host((MPIX_Request *)request, partition, flag);
+    const int rc = acx::parrived(request, partition, flag);
+    if (!*flag) emu::yield();   /* a polling loop must let the CTA's other fibers run */
+    return rc;
+}
 #endif /* __CUDACC__ */
 
 #endif

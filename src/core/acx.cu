@@ -132,6 +132,16 @@ static void release_request_resources(AcxRequest *r) {
     if (r->ev_done) { g_event_pool.push_back(r->ev_done); r->ev_done = nullptr; }
 }
 
+// A rendezvous-capable operation may have a mover (or gate + mover) on a side stream that the caller's stream never
+// joins. That kernel reads the operation's op record when it runs — possibly after the wait kernel has retired the
+// slot (an eager message into a rendezvous-sized receive completes without the mover) — so the slot and its bounce buffer
+// may only be handed to a new owner once the side branch has drained. Found by the software-device stress run
+// (tests/emu): a late mover read the NEXT owner's `mover` flag and published `done` early.
+static bool side_branch_finished(const AcxRequest *r) {
+    if (!r || !r->ev_done) return true;
+    return cudaEventQuery(r->ev_done) != cudaErrorNotReady;   // success, or a dead device (nothing to protect then)
+}
+
 void acx_slot_free(int slot) {
     // caller holds g_acx->mu
     AcxRequest *r = g_acx->slot_req[slot];
@@ -158,7 +168,7 @@ void acx_reclaim_retired() {
     size_t keep = 0;
     for (size_t i = 0; i < g_pending_retire.size(); i++) {
         const int s = g_pending_retire[i];
-        if (g_acx->slot_busy[s] == 3 && g_acx->hstat[s].retired) acx_slot_free(s);
+        if (g_acx->slot_busy[s] == 3 && g_acx->hstat[s].retired && side_branch_finished(g_acx->slot_req[s])) acx_slot_free(s);
         else if (g_acx->slot_busy[s] == 3) g_pending_retire[keep++] = s;
     }
     g_pending_retire.resize(keep);
@@ -168,7 +178,11 @@ int acx_slot_alloc(AcxRequest *r, bool graph) {
     std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
     if (g_acx->free_slots.empty() || g_pending_retire.size() >= 64) acx_reclaim_retired();
     if (g_acx->free_slots.empty()) {
-        // Waited-on stream ops retire asynchronously; give in-flight waits a moment.
+        // Waited-on stream ops retire asynchronously; give in-flight waits a moment. Slots whose wait has run but whose
+        // side-stream branch is still queued (a lagging side stream) are worth blocking for: that branch never spins.
+        for (int s2 : g_pending_retire)
+            if (g_acx->slot_busy[s2] == 3 && g_acx->hstat[s2].retired && !side_branch_finished(g_acx->slot_req[s2])) { cudaEventSynchronize(g_acx->slot_req[s2]->ev_done); break; }
+        acx_reclaim_retired();
         for (int i = 0; i < 2000 && g_acx->free_slots.empty(); i++) { usleep(100); acx_reclaim_retired(); }
         if (g_acx->free_slots.empty()) {
             ACX_ERR("out of request slots (%d); raise ACX_NFLAGS / MPIACX_NFLAGS", g_acx->geom.nops);
@@ -504,6 +518,9 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_NVTX", nullptr, 0, &v); g_nvtx = v != 0;
     if (getenv("MPIACX_DISABLE_MEMOPS")) ACX_LOG(1, "MPIACX_DISABLE_MEMOPS is accepted for compatibility; this library never uses stream memOps (kernels only)");
     { const char *m = getenv("ACX_MOVER"); g_mover_tma = m && !strcmp(m, "tma"); g_mover_256 = m && !strcmp(m, "ldst256"); }
+#ifdef ACX_EMU
+    g_mover_tma = 0;
+#endif
     acx_env_int("ACX_PDL", nullptr, 1, &v); g_pdl = v != 0;
     acx_env_int("ACX_MOVER_BLOCK", nullptr, 0, &v); g_mover_block = (int)std::max(0L, v) & ~511;
     acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
@@ -911,6 +928,7 @@ static int mover_grid_ldst(size_t bytes) {
 }
 
 static int launch_mover(Emitter &em, MoverParams &mp, size_t bytes) {
+#ifndef ACX_EMU   // the TMA mover is inline PTX; the software device runs the LDG/STG movers
     if (g_mover_tma) {
         static bool attr = false;
         if (!attr) {
@@ -919,6 +937,7 @@ static int launch_mover(Emitter &em, MoverParams &mp, size_t bytes) {
         }
         return em.launch(mover_tma, dim3(mover_grid(bytes)), dim3(kTmaThreads), mp, kTmaSmem);
     }
+#endif
     mp.vec256 = g_mover_256;
     mp.block_bytes = (uint32_t)g_mover_block;
     int grid = mover_grid_ldst(bytes);
@@ -1720,6 +1739,7 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
 #endif
         }
     }
+    if (r->ev_done) ACX_CUDA_WD(cudaEventSynchronize(r->ev_done));   // the side-stream mover still reads the op record (see side_branch_finished)
     {
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
         if (r->kind == ACX_REQ_RECV && !r->wild && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
@@ -2070,3 +2090,13 @@ extern "C" int MPIX_Parrived_host(MPIX_Request *request, int partition, int *fla
     *flag = *dflag;
     return MPI_SUCCESS;
 }
+
+#ifdef ACX_EMU
+// Software device (tests/emu): kernels are plain functions; tell its cudaLaunchKernel / cudaGraphAddKernelNode about
+// their argument lists. All of them are written for any blockDim (second argument), so the emulation may shrink blocks.
+ACX_EMU_KERNEL(copy_kernel, true) ACX_EMU_KERNEL(send_trigger, true) ACX_EMU_KERNEL(recv_trigger, true) ACX_EMU_KERNEL(push_gate, true)
+ACX_EMU_KERNEL(mover, true) ACX_EMU_KERNEL(send_rndv_fused, true) ACX_EMU_KERNEL(recv_rndv_fused, true) ACX_EMU_KERNEL(recv_any_kernel, true)
+ACX_EMU_KERNEL(coop_gate, true) ACX_EMU_KERNEL(coop_kernel, true) ACX_EMU_KERNEL(wait_kernel, true) ACX_EMU_KERNEL(bounce_out_kernel, true)
+ACX_EMU_KERNEL(pack_kernel, true) ACX_EMU_KERNEL(unpack_kernel, true) ACX_EMU_KERNEL(pstart_kernel, true) ACX_EMU_KERNEL(pstart_batch_kernel, true)
+ACX_EMU_KERNEL(pwait_kernel, true) ACX_EMU_KERNEL(pwait_batch_kernel, true) ACX_EMU_KERNEL(pready_host_kernel, true) ACX_EMU_KERNEL(parrived_host_kernel, true)
+#endif

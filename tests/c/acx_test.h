@@ -63,6 +63,12 @@ static int t_finish(const char *name) {
     MPI_Finalize();
     return t_errs != 0;
 }
+/* kern<<<grid, block>>>(args) on the default stream; under the software device (tests/emu) kernels are plain functions */
+#ifdef ACX_EMU
+#define T_LAUNCH(kern, grid, block, ...) T_CUDA(emu::launch_user(kern, grid, block, (cudaStream_t)0, __VA_ARGS__))
+#elif defined(__CUDACC__)
+#define T_LAUNCH(kern, grid, block, ...) kern<<<grid, block>>>(__VA_ARGS__)
+#endif
 #define T_RIGHT ((t_rank + 1) % t_size)
 #define T_LEFT ((t_rank + t_size - 1) % t_size)
 #endif

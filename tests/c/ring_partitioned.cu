@@ -40,8 +40,8 @@ static void run(int use_heap, int host_calls) {
             for (int p = NPART - 1; p >= 0; p--) T_OK(MPIX_Pready(p, &rq[0]));
             for (int p = 0; p < NPART; p++) { int f = 0; while (!f) T_OK(MPIX_Parrived(&rq[1], p, &f)); }
         } else {
-            mark_all_ready<<<1, NPART>>>(pq[0]);
-            poll_until_arrived<<<1, NPART>>>(pq[1]);
+            T_LAUNCH(mark_all_ready, 1, NPART, pq[0]);
+            T_LAUNCH(poll_until_arrived, 1, NPART, pq[1]);
             T_CUDA(cudaStreamSynchronize(0));
         }
         T_OK(MPIX_Waitall(2, rq, sts));

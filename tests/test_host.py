@@ -218,3 +218,16 @@ def test_device_protocol_on_cpu_threads(built):
     accounting; memory-model fences are out of its reach (x86 is stronger than the GPU)."""
     r = subprocess.run(["make", "-C", str(built), "emu"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "protocol_emu: PASS" in r.stdout, r.stdout[-2500:] + r.stderr[-2500:]
+
+
+def test_device_transport_on_software_cuda_device(built):
+    """`make emu-lib emu-tests` + tools/emu_matrix.sh: the unmodified runtime (src/core/acx.cu) linked against a software
+    CUDA runtime (tests/emu/cudart_emu.cpp: memfd-backed "device" memory with CUDA-IPC handles, stream worker threads,
+    events, stream capture, explicit graphs, user objects; kernels on fibers) runs every conformance program on the
+    DEVICE transport, one process per rank, plus the opt-in modes (cooperative moving, per-peer branches, sender push,
+    batched partitioned start/wait, device-side wildcards). This run found the slot-retirement race fixed in
+    acx_reclaim_retired (side_branch_finished)."""
+    r = subprocess.run(["make", "-C", str(built), "-j4", "emu-lib", "emu-tests"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
+    r = subprocess.run([str(built / "tools/emu_matrix.sh"), "quick"], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "0 failure(s)" in r.stdout, r.stdout[-4000:] + r.stderr[-1000:]

@@ -1,0 +1,50 @@
+#!/bin/bash
+# Run the conformance programs on the software CUDA device (make emu-lib emu-tests): one process per rank, device
+# transport, no GPU. Usage: tools/emu_matrix.sh [quick|full]   (exit code = number of failures)
+cd "$(dirname "$0")/.."
+mode=${1:-quick}
+export ACX_MPI_NO_CUDA=1          # mini-MPI: "device" memory is host-addressable here, plain memcpy is right
+T=build/emu/tests
+fails=0
+run() {  # run <label> <np> <prog> [env...]
+    local label=$1 np=$2 prog=$3; shift 3
+    local t0=$(date +%s%N)
+    out=$(env "$@" timeout 400 bin/acxrun -np $np --timeout 300 $T/$prog 2>&1)
+    rc=$?
+    local ms=$(( ($(date +%s%N) - t0) / 1000000 ))
+    if [ $rc -eq 0 ] && echo "$out" | grep -q "PASS"; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms
+    else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $rc "$(echo "$out" | tail -8)"; fails=$((fails+1)); fi
+}
+progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction ring_partitioned ordering large_msgs regcache procnull_comms subcomm datatypes"
+nps="1 2 3"
+[ "$mode" = full ] && nps="1 2 3 4"
+for p in $progs; do for np in $nps; do run default $np $p; done; done
+run default 2 stress; run default 3 stress
+run wildcards 3 wildcards ACX_WILDCARDS=1
+# opt-in modes written after the GPU budget was spent
+for p in ring ring_all ring_all_device large_msgs ordering stress; do
+    run coop 2 $p ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
+    run peer-branch 3 $p ACX_PEER_BRANCH=1
+    run sender-push 2 $p ACX_SENDER_PUSH=1
+done
+run coop 3 large_msgs ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
+run pbatch 2 ring_partitioned ACX_PBATCH=1
+run pbatch 3 ring_partitioned ACX_PBATCH=1
+if [ "$mode" = full ]; then
+    for p in ring_all large_msgs stress ordering; do
+        run no-fuse 2 $p ACX_FUSE_RNDV=0
+        run no-side-streams 2 $p ACX_SIDE_STREAMS=0
+        run ldst256 2 $p ACX_MOVER=ldst256
+        run mover-block 2 $p ACX_MOVER_BLOCK=4096
+        run depth8-chan2 2 $p ACX_DEPTH=8 ACX_NCHAN=2
+        run eager64 3 $p ACX_EAGER_MAX=64
+        run no-regcache 2 $p ACX_REGCACHE=0
+    done
+    run depth2-chan1 2 ring_all ACX_DEPTH=2 ACX_NCHAN=1
+    run depth2-chan1 3 stress ACX_DEPTH=2 ACX_NCHAN=1
+    run trace 2 ring ACX_TRACE=1 ACX_TRACE_DIR=/tmp
+    run wide-blocks 2 large_msgs ACX_EMU_MAX_BLOCK=64
+    run many-sms 2 large_msgs ACX_EMU_SMS=16
+fi
+echo "emu matrix ($mode): $fails failure(s)"
+exit $fails
