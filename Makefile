@@ -14,7 +14,7 @@ BINS  := bin/acxrun
 BENCH := $(patsubst bench/%.cu,bin/%,$(wildcard bench/*.cu))
 CTESTS := $(patsubst tests/c/%.c,$(B)/tests/%,$(wildcard tests/c/*.c)) $(patsubst tests/c/%.cu,$(B)/tests/%,$(wildcard tests/c/*.cu))
 
-.PHONY: all clean lib tests bench examples tsan asan install extmpi-check extmpi-lib emu emu-lib emu-tests
+.PHONY: all clean lib tests bench examples tsan asan install extmpi-check extmpi-lib emu emu-tsan emu-lib emu-tests emu-asan emu-tsan-matrix
 all: lib $(BINS) tests bench
 bench: $(BENCH)
 bin/%: bench/%.cu $(LIB)
@@ -98,6 +98,7 @@ install: lib bin/acxrun
 # runtime (tests/emu/cudart_emu.cpp: streams, events, capture, graphs, IPC memory) + the mini-MPI; the conformance
 # programs link against it and run under acxrun, one process per rank, on the *device* transport.
 CUDA_HOME ?= /usr/local/cuda
+SAN_CXX ?= $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 EMU := $(B)/emu
 EMU_FLAGS := -std=c++17 -g -I$(CUDA_HOME)/include -Iinclude -Isrc/core -Itests/emu
 EMU_SAN ?=
@@ -105,6 +106,13 @@ emu:
 	@mkdir -p $(B)/tests
 	$(CXX) -O1 $(EMU_FLAGS) tests/emu/protocol_emu.cpp -o $(B)/tests/protocol_emu -lpthread
 	$(B)/tests/protocol_emu
+
+# The same program under ThreadSanitizer (ranks and CTAs are threads of one process, so cross-rank accesses are visible to it):
+# checks the release/acquire pairing of the flag protocol against the C++ memory model.
+emu-tsan:
+	@mkdir -p $(B)/tests
+	$(SAN_CXX) -O1 -fsanitize=thread -Wno-tsan $(EMU_FLAGS) tests/emu/protocol_emu.cpp -o $(B)/tests/protocol_emu_tsan -lpthread
+	TSAN_OPTIONS="halt_on_error=1 history_size=4" $(B)/tests/protocol_emu_tsan
 
 EMU_CTESTS := $(patsubst tests/c/%.c,$(EMU)/tests/%,$(wildcard tests/c/*.c)) $(EMU)/tests/ring_partitioned
 emu-lib: $(EMU)/libacx_emu.so
@@ -127,10 +135,19 @@ $(EMU)/tests/%: tests/c/%.cu $(EMU)/libacx_emu.so tests/c/acx_test.h tests/emu/c
 	@mkdir -p $(EMU)/tests
 	$(CXX) -O1 $(EMU_FLAGS) $(EMU_SAN) -x c++ -include tests/emu/cuda_emu.h $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) -lpthread
 
+# ASan + UBSan (+ LeakSanitizer) build of the software-device stack and a run of the whole matrix on it
+emu-asan:
+	$(MAKE) EMU=$(B)/emu_asan EMU_SAN="-fsanitize=address,undefined -fno-omit-frame-pointer" CXX=$(SAN_CXX) emu-lib emu-tests
+	ASAN_OPTIONS=detect_leaks=1:detect_stack_use_after_return=0 UBSAN_OPTIONS=print_stacktrace=1 EMU_DIR=$(B)/emu_asan tools/emu_matrix.sh quick
+
+# ThreadSanitizer build of the software-device stack (host runtime, stream workers, CTAs of one process) + matrix
+emu-tsan-matrix:
+	$(MAKE) EMU=$(B)/emu_tsan EMU_SAN="-fsanitize=thread -Wno-tsan" CXX=$(SAN_CXX) emu-lib emu-tests
+	TSAN_OPTIONS="halt_on_error=0 history_size=4" EMU_DIR=$(B)/emu_tsan tools/emu_matrix.sh tsan
+
 clean:
 	rm -rf $(B) lib bin
 
-SAN_CXX ?= $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 # ThreadSanitizer build of the mini-MPI + its threaded test (host-side race detection; the reference has none)
 tsan:
 	@mkdir -p $(B)

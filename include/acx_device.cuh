@@ -52,7 +52,15 @@ namespace acx {
 ACX_D uint64_t ld_acquire_sys(const uint64_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 ACX_D uint64_t ld_relaxed_sys(const uint64_t *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 ACX_D void st_release_sys(uint64_t *p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#if defined(__SANITIZE_THREAD__)
+// ThreadSanitizer does not model stand-alone fences, and the device code publishes with "__threadfence_system(); relaxed
+// store" in places (legal on the GPU and in C++: fence-atomic synchronization). Under TSan a relaxed flag store is
+// therefore treated as a release — i.e. TSan assumes the fence in front of it exists and checks everything else
+// (reader-side acquires, plain accesses to shared records, slot reuse).
+ACX_D void st_relaxed_sys(uint64_t *p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#else
 ACX_D void st_relaxed_sys(uint64_t *p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+#endif
 ACX_D void red_release_add_sys(uint64_t *p, uint64_t v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
 ACX_D uint64_t atom_add_acqrel_sys(uint64_t *p, uint64_t v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
 ACX_D uint64_t atom_cas_acqrel_sys(uint64_t *p, uint64_t cmp, uint64_t val) {

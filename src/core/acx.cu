@@ -168,7 +168,7 @@ void acx_reclaim_retired() {
     size_t keep = 0;
     for (size_t i = 0; i < g_pending_retire.size(); i++) {
         const int s = g_pending_retire[i];
-        if (g_acx->slot_busy[s] == 3 && g_acx->hstat[s].retired && side_branch_finished(g_acx->slot_req[s])) acx_slot_free(s);
+        if (g_acx->slot_busy[s] == 3 && ACX_HOST_FLAG_GET(&g_acx->hstat[s].retired) && side_branch_finished(g_acx->slot_req[s])) acx_slot_free(s);
         else if (g_acx->slot_busy[s] == 3) g_pending_retire[keep++] = s;
     }
     g_pending_retire.resize(keep);
@@ -181,7 +181,7 @@ int acx_slot_alloc(AcxRequest *r, bool graph) {
         // Waited-on stream ops retire asynchronously; give in-flight waits a moment. Slots whose wait has run but whose
         // side-stream branch is still queued (a lagging side stream) are worth blocking for: that branch never spins.
         for (int s2 : g_pending_retire)
-            if (g_acx->slot_busy[s2] == 3 && g_acx->hstat[s2].retired && !side_branch_finished(g_acx->slot_req[s2])) { cudaEventSynchronize(g_acx->slot_req[s2]->ev_done); break; }
+            if (g_acx->slot_busy[s2] == 3 && ACX_HOST_FLAG_GET(&g_acx->hstat[s2].retired) && !side_branch_finished(g_acx->slot_req[s2])) { cudaEventSynchronize(g_acx->slot_req[s2]->ev_done); break; }
         acx_reclaim_retired();
         for (int i = 0; i < 2000 && g_acx->free_slots.empty(); i++) { usleep(100); acx_reclaim_retired(); }
         if (g_acx->free_slots.empty()) {
@@ -1695,9 +1695,9 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
     if (r->in_graph) { ACX_ERR("in-graph operations must be completed by a wait inside a graph"); return MPI_ERR_REQUEST; }
     if (r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max) {
         // eager send: complete once its trigger kernel has run; it says so in pinned host memory
-        volatile int32_t *flag = &g_acx->hstat[r->slot].retired;
+        const int32_t *flag = &g_acx->hstat[r->slot].retired;
         auto t0 = std::chrono::steady_clock::now();
-        while (!*flag) {
+        while (!ACX_HOST_FLAG_GET(flag)) {
             if (g_acx->watchdog_ms > 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(g_acx->watchdog_ms)) {
                 ACX_ERR("MPIX_Wait: send was never triggered on its stream (waited %ld ms)", g_acx->watchdog_ms);
                 return MPI_ERR_OTHER;

@@ -88,6 +88,17 @@ struct acx_host_status {  // pinned host memory, one per request slot; written b
     int64_t pad;
 };
 
+// `retired` (and the status fields next to it) live in pinned host memory: kernels store, the host polls. On hardware
+// that is a plain store into mapped memory and a volatile load; compiled for the software device (tests/emu) the same
+// accesses are atomics, so ThreadSanitizer sees them as the synchronization they are.
+#ifdef ACX_EMU
+#define ACX_HOST_FLAG_SET(p, v) __atomic_store_n((p), (v), __ATOMIC_RELEASE)
+#define ACX_HOST_FLAG_GET(p) __atomic_load_n((p), __ATOMIC_ACQUIRE)
+#else
+#define ACX_HOST_FLAG_SET(p, v) (*(p) = (v))
+#define ACX_HOST_FLAG_GET(p) (*(const volatile int32_t *)(p))
+#endif
+
 struct acx_trace_rec {  // device-side trace ring (ACX_TRACE=1)
     uint64_t t_ns;      // %globaltimer
     uint32_t ev, peer;

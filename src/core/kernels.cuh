@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
             *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)ACX_KIND_EAGER << 32);
             red_release_add_sys(&ent->state, 1ull << 32);
             // The source buffer is reusable as soon as this kernel retires: nothing to wait for later.
-            if (p.hstat) p.hstat->retired = 1;
+            if (p.hstat) ACX_HOST_FLAG_SET(&p.hstat->retired, 1);
             trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes);
         }
     } else if (tid == 0) {
@@ -774,14 +774,14 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
                 if (w.off_bytes != 0xffff) *(int64_t *)(w.ustatus + w.off_bytes) = (int64_t)n;
             }
             if (w.serial) { w.hstat->source = src; w.hstat->tag = stag; w.hstat->error = err; w.hstat->bytes = (int64_t)n; }
-            if (w.coop) { ent->coop_cursor = (g + 1) << 32; ent->coop_done = 0; __threadfence_system(); }   // re-arm the chunk cursor for generation g+1 before the slot is handed on
+            if (w.coop) { st_relaxed_sys(&ent->coop_cursor, (g + 1) << 32); st_relaxed_sys(&ent->coop_done, 0); __threadfence_system(); }   // atomic stores: a straggling agent of generation g may still be reading the cursor   // re-arm the chunk cursor for generation g+1 before the slot is handed on
             // All reads of the slot are complete (data dependence + barrier): plain stores suffice.
             st_relaxed_sys(&ent->consumed, g + 1);
             st_relaxed_sys(&sack[e].efree, g + 1);  // remote: slot may be reused by generation g+1
         }
     }
     if (tid == 0) {
-        if (w.retire) w.hstat->retired = 1;
+        if (w.retire) ACX_HOST_FLAG_SET(&w.hstat->retired, 1);
         trace(b.tr, ACX_EV_WAIT_END, w.src, op->ticket, s_n);
     }
 }
@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(kMoverThreads) bounce_out_kernel(BounceOutPara
     if (threadIdx.x == 0) {
         __threadfence();
         unsigned t = atomicAdd(&p.op->cta_count, 1u);
-        if (t == gridDim.x - 1) { p.op->cta_count = 0; p.hstat->retired = 1; }
+        if (t == gridDim.x - 1) { p.op->cta_count = 0; ACX_HOST_FLAG_SET(&p.hstat->retired, 1); }
     }
 }
 
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(256) unpack_kernel(UnpackParams p) {
     if (threadIdx.x == 0) {
         __threadfence();
         unsigned t = atomicAdd(&p.op->cta_count, 1u);
-        if (t == gridDim.x - 1) { p.op->cta_count = 0; p.hstat->retired = 1; }
+        if (t == gridDim.x - 1) { p.op->cta_count = 0; ACX_HOST_FLAG_SET(&p.hstat->retired, 1); }
     }
 }
 

@@ -3,7 +3,7 @@
  * Device transport: pack_kernel gathers the face into a heap staging buffer before the send; the message lands in a
  * staging buffer on the other side and unpack_kernel scatters it after the wait kernel.
  *  small block (8^3 ints):  faces are eager messages, host (static) arrays
- *  large block (64^3 floats): faces are rendezvous messages, symmetric-heap arrays; waits on the stream and on the host */
+ *  large block (64^3 floats): faces are rendezvous messages (63 x 63 x 4 B), symmetric-heap arrays; waits on the stream and on the host */
 #include "acx_test.h"
 
 static void put(void *dst, const void *src, size_t n) { if (t_gpu) T_CUDA(cudaMemcpy(dst, src, n, cudaMemcpyDefault)); else memcpy(dst, src, n); }
@@ -16,19 +16,20 @@ static void faces(int n, int use_heap, int host_wait, MPI_Datatype elem, int tag
     if (use_heap) T_OK(MPIX_Alloc_mem(cells * 4, MPI_INFO_NULL, &a));
     else { static int small[8 * 8 * 8]; a = small; }
     int sizes[3] = {n, n, n}, start[3], sub[3];
-    MPI_Datatype send_x, recv_x, send_y, recv_y, send_z, recv_z;
-    /* x faces: column pencils (run = 1 element): send interior x=n-2 to the right, receive into ghost x=0 from the left */
-    sub[0] = n; sub[1] = n; sub[2] = 1;
-    start[0] = 0; start[1] = 0; start[2] = n - 2; MPI_Type_create_subarray(3, sizes, sub, start, MPI_ORDER_C, elem, &send_x);
+    MPI_Datatype send_x, recv_x, face_y, row, face_z;
+    const int m = n - 1;   /* faces span coordinates 1..n-1 in their two free dimensions: the six buffers are pairwise disjoint
+                            * (concurrent operations on overlapping buffers are erroneous MPI, and TSan on the software device says so) */
+    /* x faces: column pencils (run = 1 element) as subarrays: send interior x=n-2 to the right, receive into ghost x=0 from the left */
+    sub[0] = m; sub[1] = m; sub[2] = 1;
+    start[0] = 1; start[1] = 1; start[2] = n - 2; MPI_Type_create_subarray(3, sizes, sub, start, MPI_ORDER_C, elem, &send_x);
     start[2] = 0; MPI_Type_create_subarray(3, sizes, sub, start, MPI_ORDER_C, elem, &recv_x);
-    /* y faces as vectors: n blocks (one per z) of n contiguous elements, stride one plane */
-    MPI_Type_vector(n, n, n * n, elem, &send_y);
-    MPI_Type_vector(n, n, n * n, elem, &recv_y);
-    /* z faces are contiguous planes: a contiguous derived type */
-    MPI_Type_contiguous(n * n, elem, &send_z);
-    MPI_Type_contiguous(n * n, elem, &recv_z);
-    MPI_Datatype *all[6] = {&send_x, &recv_x, &send_y, &recv_y, &send_z, &recv_z};
-    for (int i = 0; i < 6; i++) MPI_Type_commit(all[i]);
+    /* y faces as a vector: m blocks (one per z) of m contiguous elements, stride one plane; the buffer argument picks the face */
+    MPI_Type_vector(m, m, n * n, elem, &face_y);
+    /* z faces: a contiguous row type nested in an hvector (m rows, one block each, a row pitch apart) */
+    MPI_Type_contiguous(m, elem, &row);
+    MPI_Type_create_hvector(m, 1, (MPI_Aint)n * 4, row, &face_z);
+    MPI_Datatype *all[5] = {&send_x, &recv_x, &face_y, &row, &face_z};
+    for (int i = 0; i < 5; i++) MPI_Type_commit(all[i]);
 
     for (size_t i = 0; i < cells; i++) h[i] = (int)(1000000 * (t_rank + 1) + i);
     /* ghost layers start poisoned */
@@ -43,19 +44,18 @@ static void faces(int n, int use_heap, int host_wait, MPI_Datatype elem, int tag
     memset(st, 0xff, sizeof st);
     /* receives into ghosts x=0, y=0, z=0 from the left; sends of interior x=n-2, y=n-2, z=n-2 to the right */
     T_OK(MPIX_Irecv_enqueue(a, 1, recv_x, T_LEFT, tagbase + 0, MPI_COMM_WORLD, &rq[0], MPIX_QUEUE_CUDA_STREAM, &stream));
-    T_OK(MPIX_Irecv_enqueue(a, 1, recv_y, T_LEFT, tagbase + 1, MPI_COMM_WORLD, &rq[1], MPIX_QUEUE_CUDA_STREAM, &stream));
-    T_OK(MPIX_Irecv_enqueue(a, 1, recv_z, T_LEFT, tagbase + 2, MPI_COMM_WORLD, &rq[2], MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_OK(MPIX_Irecv_enqueue(a + IDX(n, 1, 0, 1), 1, face_y, T_LEFT, tagbase + 1, MPI_COMM_WORLD, &rq[1], MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_OK(MPIX_Irecv_enqueue(a + IDX(n, 0, 1, 1), 1, face_z, T_LEFT, tagbase + 2, MPI_COMM_WORLD, &rq[2], MPIX_QUEUE_CUDA_STREAM, &stream));
     T_OK(MPIX_Isend_enqueue(a, 1, send_x, T_RIGHT, tagbase + 0, MPI_COMM_WORLD, &rq[3], MPIX_QUEUE_CUDA_STREAM, &stream));
-    T_OK(MPIX_Isend_enqueue(a + IDX(n, 0, n - 2, 0), 1, send_y, T_RIGHT, tagbase + 1, MPI_COMM_WORLD, &rq[4], MPIX_QUEUE_CUDA_STREAM, &stream));
-    T_OK(MPIX_Isend_enqueue(a + IDX(n, n - 2, 0, 0), 1, send_z, T_RIGHT, tagbase + 2, MPI_COMM_WORLD, &rq[5], MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_OK(MPIX_Isend_enqueue(a + IDX(n, 1, n - 2, 1), 1, face_y, T_RIGHT, tagbase + 1, MPI_COMM_WORLD, &rq[4], MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_OK(MPIX_Isend_enqueue(a + IDX(n, n - 2, 1, 1), 1, face_z, T_RIGHT, tagbase + 2, MPI_COMM_WORLD, &rq[5], MPIX_QUEUE_CUDA_STREAM, &stream));
     if (host_wait) { for (int i = 0; i < 6; i++) T_OK(MPIX_Wait(&rq[i], &st[i])); }
     else {
         T_OK(MPIX_Waitall_enqueue(6, rq, st, MPIX_QUEUE_CUDA_STREAM, &stream));
         if (t_gpu) T_CUDA(cudaStreamSynchronize(stream));
     }
     put(h, a, cells * 4);
-    /* The three receives write overlapping ghost edges in posting order x, y, z; check each face where no later face overwrote it.
-     * Sender's data is ITS array before the exchange: interior cells carry 1000000*(left+1) + index; its own ghost cells carry -1/-2/-3. */
+    /* Sender's data is ITS array before the exchange: interior cells carry 1000000*(left+1) + index. */
     const int L = 1000000 * (T_LEFT + 1);
     int bad = 0;
     for (int y = 1; y < n; y++) for (int x = 1; x < n; x++) if (h[IDX(n, 0, y, x)] != L + (int)IDX(n, n - 2, y, x)) bad++;          /* z ghost <- left's z=n-2 plane */
@@ -63,12 +63,14 @@ static void faces(int n, int use_heap, int host_wait, MPI_Datatype elem, int tag
     for (int z = 1; z < n; z++) for (int y = 1; y < n; y++) if (h[IDX(n, z, y, 0)] != L + (int)IDX(n, z, y, n - 2)) bad++;          /* x ghost <- left's x=n-2 plane */
     /* interior untouched */
     for (int z = 1; z < n; z++) for (int y = 1; y < n; y++) for (int x = 1; x < n; x++) if (h[IDX(n, z, y, x)] != 1000000 * (t_rank + 1) + (int)IDX(n, z, y, x)) bad++;
+    /* ghost edges (two coordinates zero) belong to no face: still poisoned */
+    for (int k = 0; k < n; k++) { if (h[IDX(n, k, 0, 0)] >= 0) bad++; if (h[IDX(n, 0, k, 0)] >= 0) bad++; if (h[IDX(n, 0, 0, k)] >= 0) bad++; }
     T_CHECK(bad == 0, "n=%d heap=%d hostwait=%d: %d wrong cells", n, use_heap, host_wait, bad);
     int cnt = -1;
     MPI_Get_count(&st[0], recv_x, &cnt);
     T_CHECK(cnt == 1 && st[0].MPI_SOURCE == T_LEFT && st[0].MPI_TAG == tagbase && st[0].MPI_ERROR == MPI_SUCCESS, "status: count %d source %d tag %d err %d", cnt, st[0].MPI_SOURCE, st[0].MPI_TAG, st[0].MPI_ERROR);
     MPI_Barrier(MPI_COMM_WORLD);
-    for (int i = 0; i < 6; i++) MPI_Type_free(all[i]);
+    for (int i = 0; i < 5; i++) MPI_Type_free(all[i]);
     if (use_heap) MPIX_Free_mem(a);
     free(h);
 }

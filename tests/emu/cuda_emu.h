@@ -42,6 +42,20 @@
 #undef __forceinline__
 #define __forceinline__ inline
 
+// Sanitizer awareness: fibers switch stacks under the sanitizers' feet unless told.
+#if defined(__SANITIZE_ADDRESS__)
+#define EMU_ASAN 1
+extern "C" void __sanitizer_start_switch_fiber(void **fake_stack_save, const void *bottom, size_t size);
+extern "C" void __sanitizer_finish_switch_fiber(void *fake_stack_save, const void **bottom_old, size_t *size_old);
+#endif
+#if defined(__SANITIZE_THREAD__)
+#define EMU_TSAN 1
+extern "C" void *__tsan_get_current_fiber(void);
+extern "C" void *__tsan_create_fiber(unsigned flags);
+extern "C" void __tsan_destroy_fiber(void *fiber);
+extern "C" void __tsan_switch_to_fiber(void *fiber, unsigned flags);
+#endif
+
 namespace emu {
 struct Idx { unsigned x = 0, y = 0, z = 0; };
 struct Trap {};   // thrown through a fiber by __trap() and by yields once the device is dead
@@ -50,12 +64,15 @@ struct Fiber {
     Idx tid;
     int state = 0;   // 0 ready, 1 at barrier, 2 done
     char *stack = nullptr;
+    void *asan_fake = nullptr, *tsan = nullptr;
 };
 struct Cta {
     Idx bid, gdim, bdim;
     ucontext_t sched;
     Fiber *cur = nullptr;
     const std::function<void()> *body = nullptr;
+    void *asan_fake = nullptr, *tsan = nullptr;        // the scheduler's (= the OS thread's) own context
+    const void *asan_bottom = nullptr; size_t asan_size = 0;
 };
 inline thread_local Cta *cta = nullptr;
 inline std::atomic<int> g_trapped{0};   // sticky: the "device" is dead (reported as cudaErrorLaunchFailure by the software runtime)
@@ -63,14 +80,46 @@ constexpr size_t kFiberStack = 128u << 10;
 
 inline uint64_t now_ns() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec; }
 inline void check_trap() { if (g_trapped.load(std::memory_order_relaxed)) throw Trap(); }
-inline void yield() { Cta *c = cta; swapcontext(&c->cur->ctx, &c->sched); check_trap(); }
-inline void barrier() { Cta *c = cta; c->cur->state = 1; swapcontext(&c->cur->ctx, &c->sched); check_trap(); }
+// fiber -> scheduler. `dying`: the fiber never runs again (its fake stack may be released).
+inline void to_sched(Cta *c, bool dying) {
+    Fiber *f = c->cur;
+    (void)dying;
+#ifdef EMU_ASAN
+    __sanitizer_start_switch_fiber(dying ? nullptr : &f->asan_fake, c->asan_bottom, c->asan_size);
+#endif
+#ifdef EMU_TSAN
+    __tsan_switch_to_fiber(c->tsan, 0);
+#endif
+    swapcontext(&f->ctx, &c->sched);
+#ifdef EMU_ASAN
+    __sanitizer_finish_switch_fiber(f->asan_fake, &c->asan_bottom, &c->asan_size);   // resumed
+#endif
+}
+// scheduler -> fiber
+inline void to_fiber(Cta *c, Fiber *f) {
+    c->cur = f;
+#ifdef EMU_ASAN
+    __sanitizer_start_switch_fiber(&c->asan_fake, f->stack, kFiberStack);
+#endif
+#ifdef EMU_TSAN
+    __tsan_switch_to_fiber(f->tsan, 0);
+#endif
+    swapcontext(&c->sched, &f->ctx);
+#ifdef EMU_ASAN
+    __sanitizer_finish_switch_fiber(c->asan_fake, nullptr, nullptr);
+#endif
+}
+inline void yield() { Cta *c = cta; to_sched(c, false); check_trap(); }
+inline void barrier() { Cta *c = cta; c->cur->state = 1; to_sched(c, false); check_trap(); }
 inline void fiber_main() {
     Cta *c = cta;
+#ifdef EMU_ASAN
+    __sanitizer_finish_switch_fiber(nullptr, &c->asan_bottom, &c->asan_size);   // first entry
+#endif
     try { (*c->body)(); } catch (const Trap &) {}
     c = cta;
     c->cur->state = 2;
-    swapcontext(&c->cur->ctx, &c->sched);
+    to_sched(c, true);
 }
 
 // Fiber stacks are recycled per OS thread (mmap'ed, never zeroed by us).
@@ -102,12 +151,18 @@ inline void run_cta(unsigned bx, unsigned gx, unsigned threads, const std::funct
         f[i].ctx.uc_stack.ss_size = kFiberStack;
         f[i].ctx.uc_link = &c.sched;
         makecontext(&f[i].ctx, (void (*)())fiber_main, 0);
+#ifdef EMU_TSAN
+        f[i].tsan = __tsan_create_fiber(0);
+#endif
     }
+#ifdef EMU_TSAN
+    c.tsan = __tsan_get_current_fiber();
+#endif
     unsigned idle = 0, last_done = 0;
     for (;;) {
         unsigned done = 0, waiting = 0;
         for (unsigned i = 0; i < threads; i++) {
-            if (f[i].state == 0) { c.cur = &f[i]; swapcontext(&c.sched, &f[i].ctx); }
+            if (f[i].state == 0) to_fiber(&c, &f[i]);
             if (f[i].state == 2) done++; else if (f[i].state == 1) waiting++;
         }
         if (done == threads) break;
@@ -118,7 +173,12 @@ inline void run_cta(unsigned bx, unsigned gx, unsigned threads, const std::funct
         if (++idle < 64) sched_yield();
         else { timespec ts{0, idle < 1024 ? 2000 : 50000}; nanosleep(&ts, nullptr); }
     }
-    for (auto &x : f) stack_pool.put(x.stack);
+    for (auto &x : f) {
+        stack_pool.put(x.stack);
+#ifdef EMU_TSAN
+        __tsan_destroy_fiber(x.tsan);
+#endif
+    }
     cta = outer;
 }
 

@@ -534,9 +534,9 @@ cudaError_t cudaEventDestroy(cudaEvent_t ce) {
     if (!e) return fail(cudaErrorInvalidResourceHandle);
     // a pending record/wait task may still reference the event and cudaEventDestroy must not block: park it
     static std::mutex mu;
-    static std::vector<Event *> graveyard;
+    static std::vector<Event *> *graveyard = new std::vector<Event *>();   // never destroyed: stays reachable for leak checkers
     std::lock_guard<std::mutex> lk(mu);
-    graveyard.push_back(e);
+    graveyard->push_back(e);
     return cudaSuccess;
 }
 cudaError_t cudaEventRecord(cudaEvent_t ce, cudaStream_t cs) {

@@ -19,7 +19,7 @@ static int g_errs = 0;
 struct Rank {
     char *ctrl = nullptr, *heap = nullptr;
     std::vector<acx_host_status> hstat;
-    uint64_t serial = 1;
+    std::atomic<uint64_t> serial{1};   // two receive streams of one rank share it in run_wildcard_vs_specific
     uint64_t diag[4] = {0, 0, 0, 0};
 };
 static std::vector<Rank> R;
@@ -33,7 +33,7 @@ static void world_init(int n) {
     G.nranks = n; G.nchan = 2; G.depth = 2; G.nops = 64; G.eager_max = 64; G.npflags = 64; G.ntrace = 2; G.maxreg = 1;
     acx_geom_layout(G);
     st.geom = G; st.size = n;
-    R.assign(n, Rank());
+    R = std::vector<Rank>(n);
     for (auto &r : R) {
         r.ctrl = (char *)aligned_alloc(256, G.bytes); memset(r.ctrl, 0, G.bytes);
         r.heap = (char *)aligned_alloc(256, kHeap); memset(r.heap, 0, kHeap);

@@ -231,3 +231,17 @@ def test_device_transport_on_software_cuda_device(built):
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
     r = subprocess.run([str(built / "tools/emu_matrix.sh"), "quick"], capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and "0 failure(s)" in r.stdout, r.stdout[-4000:] + r.stderr[-1000:]
+
+
+def test_flag_protocol_under_thread_sanitizer(built):
+    """`make emu-tsan`: tests/emu/protocol_emu.cpp under ThreadSanitizer. Ranks, streams and CTAs are threads of one
+    process there, so TSan sees both ends of every message: it checks the release/acquire pairing of the flag protocol
+    (eager, rendezvous, cooperative chunk claims, wildcard resolver, pack/unpack) against the C++ memory model."""
+    r = subprocess.run(["make", "-C", str(built), "emu-tsan"], capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and "protocol_emu: PASS" in r.stdout and "ThreadSanitizer" not in r.stdout + r.stderr, r.stdout[-2500:] + r.stderr[-2500:]
+
+
+def test_device_transport_under_address_sanitizer(built):
+    """`make emu-asan`: runtime + software CUDA device + conformance programs built with ASan/UBSan/LSan, quick matrix."""
+    r = subprocess.run(["make", "-C", str(built), "emu-asan"], capture_output=True, text=True, timeout=2400)
+    assert r.returncode == 0 and "0 failure(s)" in r.stdout, r.stdout[-4000:] + r.stderr[-1500:]
