@@ -703,6 +703,7 @@ extern "C" int MPIX_Is_device_transport(void) { return g_acx && g_acx->device ? 
 
 extern "C" int MPIX_Get_stats(MPIX_Acx_stats *s) {
     if (!g_acx || !s) return MPI_ERR_ARG;
+    if (g_acx->device) { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); acx_reclaim_retired(); }   // slots of retired operations / destroyed graphs count as free
     s->sends_enqueued = g_acx->st.sends; s->recvs_enqueued = g_acx->st.recvs; s->waits_enqueued = g_acx->st.waits;
     s->bytes_sent = g_acx->st.bytes_sent; s->bytes_received = g_acx->st.bytes_recv;
     s->eager_msgs = g_acx->st.eager; s->rendezvous_msgs = g_acx->st.rndv; s->bounce_copies = g_acx->st.bounce;

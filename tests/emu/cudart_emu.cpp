@@ -476,7 +476,7 @@ cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
     char path[64];
     snprintf(path, sizeof path, "/proc/%d/fd/%d", x.pid, x.fd);
     int fd = open(path, O_RDWR);
-    if (fd < 0) { perror("emu: cudaIpcOpenMemHandle"); return fail(cudaErrorInvalidValue); }
+    if (fd < 0) return fail(cudaErrorInvalidValue);   // the exporter has freed the allocation (or is gone)
     void *m = mmap(nullptr, x.size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     close(fd);
     if (m == MAP_FAILED) return fail(cudaErrorMemoryAllocation);

@@ -246,3 +246,13 @@ def test_python_strided_views_match_torch_slicing(tmp_path):
     env = dict(os.environ, ACX_WATCHDOG_MS="30000")
     r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "STRIDED OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_graphs_with_rendezvous_messages_relaunched_past_ring_depth(built, np_):
+    """Captured and explicit graphs carrying 20 KB / 200 KB / 1 MiB messages (trigger + mover, fused rendezvous, bounce and
+    registered private buffers), one instantiation launched 40 times (> ACX_DEPTH): every launch must re-arm what it
+    consumed — tests/c/graph_large.c (validated on the software device in all opt-in modes)."""
+    r = acxrun(built, np_, built / "build/tests/graph_large")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout

@@ -16,7 +16,7 @@ run() {  # run <label> <np> <prog> [env...]
     if [ $rc -eq 0 ] && echo "$out" | grep -q "PASS"; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms
     else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $rc "$(echo "$out" | grep -v "ASan doesn\x27t fully support" | tail -${EMU_TAIL:-8})"; fails=$((fails+1)); fi
 }
-progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction ring_partitioned ordering large_msgs regcache procnull_comms subcomm datatypes"
+progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned ordering large_msgs regcache procnull_comms subcomm datatypes"
 nps="1 2 3"
 [ "$mode" = full ] && nps="1 2 3 4"
 for p in $progs; do for np in $nps; do run default $np $p; done; done
@@ -27,7 +27,7 @@ run wildcards 3 wildcards ACX_WILDCARDS=1
 # (cooperative moving) the completion chain runs through the other process and looks like a missing release here, so
 # cooperative moving is TSan-checked at np=1 (and, across ranks, by `make emu-tsan`, where ranks are threads).
 coop_np=2; [ "$mode" = tsan ] && coop_np=1
-for p in ring ring_all ring_all_device large_msgs ordering stress; do
+for p in ring ring_all ring_all_device graph_large large_msgs ordering stress; do
     run coop $coop_np $p ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
     run peer-branch 3 $p ACX_PEER_BRANCH=1
     run sender-push 2 $p ACX_SENDER_PUSH=1
@@ -36,7 +36,7 @@ done
 run pbatch 2 ring_partitioned ACX_PBATCH=1
 run pbatch 3 ring_partitioned ACX_PBATCH=1
 if [ "$mode" = full ]; then
-    for p in ring_all large_msgs stress ordering; do
+    for p in ring_all large_msgs stress ordering graph_large; do
         run no-fuse 2 $p ACX_FUSE_RNDV=0
         run no-side-streams 2 $p ACX_SIDE_STREAMS=0
         run ldst256 2 $p ACX_MOVER=ldst256
@@ -44,6 +44,7 @@ if [ "$mode" = full ]; then
         run depth8-chan2 2 $p ACX_DEPTH=8 ACX_NCHAN=2
         run eager64 3 $p ACX_EAGER_MAX=64
         run no-regcache 2 $p ACX_REGCACHE=0
+        run fuse-any-grid 2 $p ACX_FUSE_MIN_CTAS=1 ACX_EMU_SMS=16
     done
     run depth2-chan1 2 ring_all ACX_DEPTH=2 ACX_NCHAN=1
     run depth2-chan1 3 stress ACX_DEPTH=2 ACX_NCHAN=1
@@ -51,5 +52,9 @@ if [ "$mode" = full ]; then
     run wide-blocks 2 large_msgs ACX_EMU_MAX_BLOCK=64
     run many-sms 2 large_msgs ACX_EMU_SMS=16
 fi
+# failure detection: a dropped send must end in the device watchdog (trap -> sticky launch failure -> diagnostic), not in a hang
+out=$(ACX_FAULT_DROP_SEND=1 ACX_WATCHDOG_MS=1500 timeout 100 bin/acxrun -np 1 --timeout 60 $T/ring 2>&1); rc=$?
+if [ $rc -ne 0 ] && echo "$out" | grep -q "WATCHDOG (code 0x5e04" && echo "$out" | grep -q "FAULT INJECTION"; then printf "ok    %-24s np=1 %-28s\n" ring watchdog-on-dropped-send
+else printf "FAIL  ring np=1 watchdog-on-dropped-send rc=%d\n%s\n" $rc "$(echo "$out" | tail -5)"; fails=$((fails+1)); fi
 echo "emu matrix ($mode): $fails failure(s)"
 exit $fails
