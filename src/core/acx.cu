@@ -473,6 +473,71 @@ static void reg_finalize() {}
 #endif
 
 // =======================================================================================
+// stream memory operations (ACX_MEMOPS=1)
+// =======================================================================================
+// Reference: the memOps shim wrapWriteValue / wrapWaitValue / wrapBatchMemOp (src/sendrecv.cu:34-42) pokes and polls flags in
+// HOST memory for the CPU proxy. Point-to-point operations here cannot use it — a message's ring slot and generation come
+// from a ticket the trigger kernel takes on the device, so the host has no value to wait for — but the partitioned
+// protocol runs on epochs the HOST counts: MPIX_Start is "write epoch e to two words", completing a round is "wait until
+// sent[p] / arrived[p] >= e for every partition". Those are exactly cuStreamWriteValue64 / cuStreamWaitValue64(GEQ), on
+// flags in device HBM, and a whole MPIX_Startall / MPIX_Waitall group is ONE cuStreamBatchMemOp call: no kernel launch
+// and no SM held by a spinning CTA. Opt-in until measured on hardware (tools/gpu_next_round.sh). A memOp wait has
+// no watchdog, and receives that land in a private buffer still need the copy-out kernel.
+static int g_memops = 0;
+typedef int (*cuStreamBatchMemOpFn)(CUstream, unsigned int, CUstreamBatchMemOpParams *, unsigned int);
+static cuStreamBatchMemOpFn g_cuStreamBatchMemOp = nullptr;
+static const size_t kMemOpBatchMax = 256;   // per driver call
+
+static void memops_init() {
+    if (!g_memops) return;
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamBatchMemOp", &f, cudaEnableDefault, &q) != cudaSuccess || !f) {
+        cudaGetLastError();
+        ACX_LOG(1, "ACX_MEMOPS: cuStreamBatchMemOp is not available; using kernels");
+        g_memops = 0;
+        return;
+    }
+    g_cuStreamBatchMemOp = (cuStreamBatchMemOpFn)f;
+}
+struct MemOpBatch {
+    std::vector<CUstreamBatchMemOpParams> ops;
+    void write64(uint64_t *addr, uint64_t v) {
+        CUstreamBatchMemOpParams p;
+        memset(&p, 0, sizeof p);
+        p.writeValue.operation = CU_STREAM_MEM_OP_WRITE_VALUE_64;
+        p.writeValue.address = (CUdeviceptr)(uintptr_t)addr;
+        p.writeValue.value64 = v;
+        p.writeValue.flags = CU_STREAM_WRITE_VALUE_DEFAULT;   // default = memory barrier in front of the write (release)
+        ops.push_back(p);
+    }
+    void wait_geq64(const uint64_t *addr, uint64_t v) {
+        CUstreamBatchMemOpParams p;
+        memset(&p, 0, sizeof p);
+        p.waitValue.operation = CU_STREAM_MEM_OP_WAIT_VALUE_64;
+        p.waitValue.address = (CUdeviceptr)(uintptr_t)addr;
+        p.waitValue.value64 = v;
+        p.waitValue.flags = CU_STREAM_WAIT_VALUE_GEQ;
+        ops.push_back(p);
+    }
+    int flush(cudaStream_t stream) {   // operations of one call execute in array order
+        for (size_t i = 0; i < ops.size(); i += kMemOpBatchMax) {
+            const unsigned n = (unsigned)std::min(kMemOpBatchMax, ops.size() - i);
+            const int rc = g_cuStreamBatchMemOp((CUstream)stream, n, ops.data() + i, 0);
+            if (rc != 0) { ACX_ERR("cuStreamBatchMemOp failed (CUresult %d)", rc); return MPI_ERR_OTHER; }
+            g_acx->st.kernels++;   // counted with the launches: one enqueued device-side operation group
+        }
+        ops.clear();
+        return 0;
+    }
+};
+static bool stream_is_capturing(cudaStream_t s) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+    return cs == cudaStreamCaptureStatusActive;
+}
+
+// =======================================================================================
 // init / finalize
 // =======================================================================================
 struct Bootstrap {
@@ -516,7 +581,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_TRACE", nullptr, 0, &v); g_acx->trace = v != 0;
     acx_env_int("ACX_WATCHDOG_MS", nullptr, 0, &v); g_acx->watchdog_ms = v;
     acx_env_int("ACX_NVTX", nullptr, 0, &v); g_nvtx = v != 0;
-    if (getenv("MPIACX_DISABLE_MEMOPS")) ACX_LOG(1, "MPIACX_DISABLE_MEMOPS is accepted for compatibility; this library never uses stream memOps (kernels only)");
+    if (getenv("MPIACX_DISABLE_MEMOPS")) ACX_LOG(1, "MPIACX_DISABLE_MEMOPS: stream memOps stay off (they are opt-in here: ACX_MEMOPS=1, partitioned Start / Wait only)");
     { const char *m = getenv("ACX_MOVER"); g_mover_tma = m && !strcmp(m, "tma"); g_mover_256 = m && !strcmp(m, "ldst256"); }
 #ifdef ACX_EMU
     g_mover_tma = 0;
@@ -529,6 +594,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_COOP", nullptr, 0, &v); g_coop = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_COOP_MIN_BYTES", nullptr, 4 << 20, &v); g_coop_min = std::max(65536L, v);
     acx_env_int("ACX_PBATCH", nullptr, 0, &v); g_pbatch = v != 0;   // opt-in until measured on hardware
+    acx_env_int("ACX_MEMOPS", nullptr, 0, &v); g_memops = v != 0 && !getenv("MPIACX_DISABLE_MEMOPS");   // partitioned Start / Wait as stream memOps (opt-in until measured)
     acx_env_int("ACX_PEER_BRANCH", nullptr, 0, &v); g_branch = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_SENDER_PUSH", nullptr, 0, &v); g_apush = v != 0;   // opt-in: a spinning gate can deadlock against device-synchronizing host calls
     acx_env_int("ACX_FUSE_MAX_CTAS", nullptr, 32, &v); g_fuse_max_ctas = (int)v;
@@ -632,6 +698,7 @@ extern "C" int MPIX_Init(void) {
     g_acx->device = true;
     g_acx->initialized = true;
     reg_init();
+    memops_init();
 #ifdef ACX_MINI_MPI
     ACX_Mpi_set_abort_hook(report_watchdog);
 #endif
@@ -1678,6 +1745,7 @@ extern "C" int MPIX_Waitall_enqueue(int count, MPIX_Request *reqs, MPI_Status *s
 // ---- partitioned: forward declarations ----
 static int pwait_host(AcxRequest *r, MPI_Status *status);
 static int pwait_emit(AcxRequest *r, cudaStream_t stream);
+static bool pwait_memops(AcxRequest *r, MemOpBatch &mb);
 
 // Reference: MPIX_Wait / MPIX_Waitall, src/sendrecv.cu:582-651 (host spin on the flag; partitioned: spin per partition + MPI_Wait).
 extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
@@ -1755,6 +1823,7 @@ extern "C" int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses)
     // partitioned requests on the device transport: emit every completion kernel first, synchronize once
     if (g_acx && g_acx->device) {
         bool any = false;
+        MemOpBatch wait_ops;
         PWaitBatch pb;
         int nb = 0;
         auto flush = [&]() -> int {
@@ -1769,7 +1838,9 @@ extern "C" int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses)
         for (int i = 0; i < count; i++) {
             AcxRequest *r = reqs[i] ? as_request(reqs[i]) : nullptr;
             if (r && (r->kind == ACX_REQ_PSEND || r->kind == ACX_REQ_PRECV) && !r->host_transport && r->active) {
-                if (g_pbatch) {
+                if (pwait_memops(r, wait_ops)) {   // one cuStreamBatchMemOp for every request of the group that needs no copy-out
+                    r->active = false;
+                } else if (g_pbatch) {
                     pb.ch[nb] = r->pchan_d; pb.e[nb] = r->epoch;
                     r->active = false;
                     int rc;
@@ -1782,6 +1853,7 @@ extern "C" int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses)
             }
         }
         { int rc = flush(); if (rc) return rc; }
+        if (!wait_ops.ops.empty()) { int rc = wait_ops.flush(g_acx->istream); if (rc) return rc; }
         if (any) ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
     }
     for (int i = 0; i < count; i++) {
@@ -1946,6 +2018,12 @@ static int pstart_emit(AcxRequest *r, cudaStream_t stream) {
     uint64_t *epoch_local = r->pchan_h.epoch;
     uint64_t *cts_remote = r->kind == ACX_REQ_PRECV ? r->pchan_h.cts : nullptr;
     uint64_t e = r->epoch;
+    if (g_memops && !stream_is_capturing(stream)) {
+        MemOpBatch mb;
+        mb.write64(epoch_local, e);
+        if (cts_remote) mb.write64(cts_remote, e);   // peer-mapped: clear-to-send at the sender
+        return mb.flush(stream);
+    }
     void *args[] = {&epoch_local, &cts_remote, &e};
     ACX_CUDA_WD(cudaLaunchKernel((const void *)pstart_kernel, dim3(1), dim3(1), args, 0, stream));
     g_acx->st.kernels++;
@@ -1956,6 +2034,7 @@ static int pstart_emit(AcxRequest *r, cudaStream_t stream) {
 extern "C" int MPIX_Startall(int count, MPIX_Request *reqs) {
     if (!g_acx || !g_acx->initialized) return MPI_ERR_OTHER;
     bool any_dev = false;
+    MemOpBatch start_ops;
     PStartBatch sb;
     memset(&sb, 0, sizeof sb);
     auto flush = [&]() -> int {
@@ -1970,6 +2049,17 @@ extern "C" int MPIX_Startall(int count, MPIX_Request *reqs) {
         AcxRequest *r = as_request(reqs[i]);
         if (!r || (r->kind != ACX_REQ_PSEND && r->kind != ACX_REQ_PRECV)) { ACX_ERR("MPIX_Start needs a partitioned request"); return MPI_ERR_REQUEST; }
         if (r->host_transport) { int rc = MPI_Start(&r->mpi_req); if (rc) return rc; r->active = true; continue; }
+        if (g_memops) {   // the whole group becomes one cuStreamBatchMemOp (flushed below)
+            int rc = presolve(r);
+            if (rc) return rc;
+            if (r->active) { ACX_ERR("MPIX_Start on an active partitioned request"); return MPI_ERR_REQUEST; }
+            r->epoch++;
+            r->active = true;
+            start_ops.write64(r->pchan_h.epoch, r->epoch);
+            if (r->kind == ACX_REQ_PRECV) start_ops.write64(r->pchan_h.cts, r->epoch);
+            any_dev = true;
+            continue;
+        }
         if (g_pbatch) {
             int rc = presolve(r);
             if (rc) return rc;
@@ -1988,6 +2078,7 @@ extern "C" int MPIX_Startall(int count, MPIX_Request *reqs) {
         any_dev = true;
     }
     { int rc = flush(); if (rc) return rc; }
+    if (!start_ops.ops.empty()) { int rc = start_ops.flush(g_acx->istream); if (rc) return rc; }
     // Kernels launched by the user right after Start (on any stream) must observe the new epoch.
     if (any_dev) ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
     return MPI_SUCCESS;
@@ -2000,8 +2091,23 @@ extern "C" int MPIX_Start_enqueue(MPIX_Request *request, int qtype, void *queue)
     return pstart_emit(r, *(cudaStream_t *)queue);
 }
 
+// Completion of a round as memOp waits, when nothing has to be copied: a send waits for sent[p] >= e, a receive whose
+// landing zone IS the user's buffer for arrived[p] >= e. Returns false (nothing appended) when a kernel is needed.
+static bool pwait_memops(AcxRequest *r, MemOpBatch &mb) {
+    if (!g_memops || (size_t)r->partitions > kMemOpBatchMax) return false;
+    const acx_pchan &c = r->pchan_h;
+    if (r->kind == ACX_REQ_PSEND) { for (int p = 0; p < r->partitions; p++) mb.wait_geq64(c.local_flags + p, r->epoch); return true; }
+    if (c.land != c.user_buf) return false;   // private destination: pwait_kernel copies out what device pollers did not claim
+    for (int p = 0; p < r->partitions; p++) mb.wait_geq64(c.arrived + p, r->epoch);
+    return true;
+}
+
 static int pwait_emit(AcxRequest *r, cudaStream_t stream) {
     if (!r->active) return 0;
+    if (g_memops && !stream_is_capturing(stream)) {
+        MemOpBatch mb;
+        if (pwait_memops(r, mb)) { r->active = false; return mb.flush(stream); }
+    }
     const acx_pchan *ch = r->pchan_d;
     uint64_t e = r->epoch;
     Watchdog wd = make_wd();

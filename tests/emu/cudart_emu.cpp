@@ -15,6 +15,7 @@
 //   errors          a device __trap() is sticky: every later synchronizing call returns cudaErrorLaunchFailure
 #include "cuda_emu.h"
 
+#include <cuda.h>   // driver types of the stream memOps (CUstreamBatchMemOpParams)
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -306,6 +307,36 @@ int fake_cuPointerGetAttribute(void *data, int attr, unsigned long long ptr) {
     return 0;
 }
 
+// cuStreamBatchMemOp: value writes (release) and value waits (GEQ / EQ, acquire) executed in array order by the stream.
+void submit(Stream *s, const char *what, std::function<void()> t);
+int fake_cuStreamBatchMemOp(CUstream cs, unsigned int count, CUstreamBatchMemOpParams *ops, unsigned int) {
+    Stream *s = S((cudaStream_t)cs);
+    { std::lock_guard<std::mutex> lk(g_graph_mu); if (s->cap) return 900 /*CUDA_ERROR_STREAM_CAPTURE_UNSUPPORTED*/; }
+    auto v = std::make_shared<std::vector<CUstreamBatchMemOpParams>>(ops, ops + count);
+    for (const auto &o : *v)
+        if (o.operation != CU_STREAM_MEM_OP_WAIT_VALUE_64 && o.operation != CU_STREAM_MEM_OP_WRITE_VALUE_64 && o.operation != CU_STREAM_MEM_OP_WAIT_VALUE_32 &&
+            o.operation != CU_STREAM_MEM_OP_WRITE_VALUE_32) return 1 /*CUDA_ERROR_INVALID_VALUE*/;
+    submit(s, "batch-memop", [v] {
+        for (const auto &o : *v) {
+            if (o.operation == CU_STREAM_MEM_OP_WRITE_VALUE_64) __atomic_store_n((uint64_t *)o.writeValue.address, (uint64_t)o.writeValue.value64, __ATOMIC_RELEASE);
+            else if (o.operation == CU_STREAM_MEM_OP_WRITE_VALUE_32) __atomic_store_n((uint32_t *)o.writeValue.address, (uint32_t)o.writeValue.value, __ATOMIC_RELEASE);
+            else {
+                const bool w64 = o.operation == CU_STREAM_MEM_OP_WAIT_VALUE_64;
+                unsigned idle = 0;
+                for (;;) {
+                    if (emu::g_trapped.load()) return;
+                    bool ok;
+                    if (w64) { const uint64_t cur = __atomic_load_n((const uint64_t *)o.waitValue.address, __ATOMIC_ACQUIRE); ok = o.waitValue.flags == CU_STREAM_WAIT_VALUE_EQ ? cur == o.waitValue.value64 : (int64_t)(cur - o.waitValue.value64) >= 0; }
+                    else { const uint32_t cur = __atomic_load_n((const uint32_t *)o.waitValue.address, __ATOMIC_ACQUIRE); ok = o.waitValue.flags == CU_STREAM_WAIT_VALUE_EQ ? cur == o.waitValue.value : (int32_t)(cur - o.waitValue.value) >= 0; }
+                    if (ok) break;
+                    if (++idle < 64) sched_yield(); else { timespec ts{0, 5000}; nanosleep(&ts, nullptr); }
+                }
+            }
+        }
+    });
+    return 0;
+}
+
 }  // namespace
 
 namespace emu {
@@ -384,6 +415,7 @@ cudaError_t cudaGetDriverEntryPoint(const char *symbol, void **fn, unsigned long
     *fn = nullptr;
     if (!strcmp(symbol, "cuMemGetAddressRange")) *fn = (void *)fake_cuMemGetAddressRange;
     else if (!strcmp(symbol, "cuPointerGetAttribute")) *fn = (void *)fake_cuPointerGetAttribute;
+    else if (!strcmp(symbol, "cuStreamBatchMemOp")) *fn = (void *)fake_cuStreamBatchMemOp;
     if (st) *st = *fn ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
     return *fn ? cudaSuccess : fail(cudaErrorNotSupported);
 }

@@ -35,6 +35,9 @@ done
 [ "$mode" = tsan ] || run coop 3 large_msgs ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
 run pbatch 2 ring_partitioned ACX_PBATCH=1
 run pbatch 3 ring_partitioned ACX_PBATCH=1
+run memops 2 ring_partitioned ACX_MEMOPS=1
+run memops 3 ring_partitioned ACX_MEMOPS=1
+run memops 4 subcomm ACX_MEMOPS=1
 if [ "$mode" = full ]; then
     for p in ring_all large_msgs stress ordering graph_large; do
         run no-fuse 2 $p ACX_FUSE_RNDV=0

@@ -49,6 +49,15 @@ for np in 1 $NP; do ACX_PBATCH=1 timeout 90 ./bin/acxrun -np $np --timeout 80 bu
 for pbv in 0 1; do echo "halo api pbatch=$pbv: $(ACX_PBATCH=$pbv run bin/halo_bench api --n 512 --steps 10 | tail -n 1)"; done
 echo "halo api reference: $(run $R/halo_bench api --n 512 --steps 10 | tail -n 1)"
 
+echo "### 3b'. ACX_MEMOPS=1 (partitioned Start / Wait as one cuStreamBatchMemOp per group: value writes / GEQ waits on device flags)"
+# first question on hardware: does the driver accept a write-value to the peer-mapped (CUDA-IPC) clear-to-send word?
+for np in 1 $NP; do ACX_MEMOPS=1 timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/ring_partitioned 2>&1 | tail -n 2; done
+for np in 2 4; do ACX_MEMOPS=1 timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/subcomm 2>&1 | tail -n 1; done
+for mo in 0 1; do echo "halo api memops=$mo: $(ACX_MEMOPS=$mo run bin/halo_bench api --n 512 --steps 10 | tail -n 1)"; done
+
+echo "### 3b''. graphs with rendezvous-size messages relaunched past the ring depth (new conformance program)"
+for np in 1 $NP; do timeout 120 ./bin/acxrun -np $np --timeout 100 build/tests/graph_large 2>&1 | tail -n 2; done
+
 echo "### 3c. halo kernel: deeper own-row prefetch (variants 7 = PD2, 8 = PD3) against the default (5): numerics, then 512^3 step time"
 for v in 5 7 8; do
   ACX_HALO_VARIANT=$v timeout 120 python - <<'PY' 2>&1 | tail -n 1
