@@ -50,7 +50,7 @@ for pbv in 0 1; do echo "halo api pbatch=$pbv: $(ACX_PBATCH=$pbv run bin/halo_be
 echo "halo api reference: $(run $R/halo_bench api --n 512 --steps 10 | tail -n 1)"
 
 echo "### 3b'. ACX_MEMOPS=1 (partitioned Start / Wait as one cuStreamBatchMemOp per group: value writes / GEQ waits on device flags)"
-# first question on hardware: does the driver accept a write-value to the peer-mapped (CUDA-IPC) clear-to-send word?
+# (write-value to peer-mapped memory works on this box: profiles/hw_probe.md; the question is the cost of a batch)
 for np in 1 $NP; do ACX_MEMOPS=1 timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/ring_partitioned 2>&1 | tail -n 2; done
 for np in 2 4; do ACX_MEMOPS=1 timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/subcomm 2>&1 | tail -n 1; done
 for mo in 0 1; do echo "halo api memops=$mo: $(ACX_MEMOPS=$mo run bin/halo_bench api --n 512 --steps 10 | tail -n 1)"; done
