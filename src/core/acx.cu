@@ -41,6 +41,27 @@ static std::vector<int> g_pending_retire;                    // slots whose wait
 static std::vector<int> g_deferred_slots;                    // freed by graph user-object destructors
 static std::mutex g_deferred_mu;
 
+// Stream for the calling thread's host-blocking operations (MPIX_Wait, MPIX_Start(all), host Pready / Parrived, host waits
+// of partitioned rounds). One per application thread: these calls launch kernels that may SPIN (a wait for a message
+// that has not been sent yet), and on a shared stream one thread's spinning wait would hold back another thread's
+// unrelated Pready or Start — with three or more ranks that closes a cycle (tests/c/threads.c found it on the software
+// device). The thread that called MPIX_Init uses the library's first stream.
+static std::mutex g_host_streams_mu;
+static std::vector<cudaStream_t> g_host_streams;   // every stream handed out, destroyed at MPIX_Finalize
+static unsigned long long g_init_generation = 0;   // bumped by MPIX_Init: streams of an earlier init are never reused
+static cudaStream_t host_stream() {
+    thread_local cudaStream_t mine = nullptr;
+    thread_local unsigned long long mine_gen = 0;
+    if (mine && mine_gen == g_init_generation) return mine;
+    std::lock_guard<std::mutex> lk(g_host_streams_mu);
+    cudaStream_t s = nullptr;
+    if (g_host_streams.empty()) s = g_acx->istream;
+    else if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return g_acx->istream; }
+    g_host_streams.push_back(s);
+    mine = s; mine_gen = g_init_generation;
+    return s;
+}
+
 // NVTX ranges around the API calls (ACX_NVTX=1); header-only NVTX, a no-op without a tool attached.
 static int g_mover_tma = 0, g_mover_256 = 0, g_mover_block = 0;   // g_mover_block: interleaved block size in bytes (ACX_MOVER_BLOCK; 0 = one chunk per CTA)
 static int g_apush = 0;                   // deterministic large-message mode: the sender always pushes, gated on its per-channel stream (ACX_SENDER_PUSH)
@@ -402,6 +423,7 @@ static void reg_init() {
 // Map registrations our peers have published since the last call; ack them. Cheap when idle.
 static void reg_progress() {
     if (!g_reg_on) return;
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);   // application threads enqueue concurrently; new entries are rare
     bool wrote = false;
     std::vector<std::pair<int, uint32_t>> to_ack;
     for (int p = 0; p < g_acx->size; p++) {
@@ -416,8 +438,8 @@ static void reg_progress() {
                 else cudaGetLastError();
             }
             if (mapped) {
-                cudaMemcpyAsync(g_acx->ctrl + g_acx->geom.off_xlat + ((uint64_t)p * g_acx->geom.maxreg + i) * 8, &mapped, 8, cudaMemcpyHostToDevice, g_acx->istream);
-                cudaStreamSynchronize(g_acx->istream);   // `mapped` is a stack variable; entries are rare
+                cudaMemcpyAsync(g_acx->ctrl + g_acx->geom.off_xlat + ((uint64_t)p * g_acx->geom.maxreg + i) * 8, &mapped, 8, cudaMemcpyHostToDevice, host_stream());
+                cudaStreamSynchronize(host_stream());   // `mapped` is a stack variable; entries are rare
                 to_ack.push_back({p, i});
                 wrote = true;
             }
@@ -689,6 +711,8 @@ extern "C" int MPIX_Init(void) {
     cudaHostGetDevicePointer((void **)&g_acx->hstat_d, g_acx->hstat, 0);
     cudaHostGetDevicePointer((void **)&g_diag_d, g_diag, 0);
     cudaStreamCreateWithFlags(&g_acx->istream, cudaStreamNonBlocking);
+    { std::lock_guard<std::mutex> lk(g_host_streams_mu); g_host_streams.clear(); g_init_generation++; }
+    host_stream();   // the initializing thread takes the first one
     g_side.assign(8, nullptr);
     for (auto &ss : g_side) cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking);
     g_acx->slot_busy.assign(g_acx->geom.nops, 0);
@@ -744,6 +768,11 @@ extern "C" int MPIX_Finalize(void) {
         }
         MPI_Barrier(MPI_COMM_WORLD);
         for (auto &r : g_acx->host_regs) cudaHostUnregister((void *)r.lo);
+        {
+            std::lock_guard<std::mutex> lk(g_host_streams_mu);
+            for (cudaStream_t hs : g_host_streams) if (hs != g_acx->istream) cudaStreamDestroy(hs);
+            g_host_streams.clear();
+        }
         cudaStreamDestroy(g_acx->istream);
         for (auto ss : g_side) if (ss) cudaStreamDestroy(ss);
         g_side.clear();
@@ -1778,7 +1807,7 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
             AnyParams ap;
             fill_any(r, &ap);
             void *aargs[] = {&ap};
-            ACX_CUDA_WD(cudaLaunchKernel((const void *)recv_any_kernel, dim3(any_grid(r)), dim3(kMoverThreads), aargs, 0, g_acx->istream));
+            ACX_CUDA_WD(cudaLaunchKernel((const void *)recv_any_kernel, dim3(any_grid(r)), dim3(kMoverThreads), aargs, 0, host_stream()));
             g_acx->st.kernels++;
         }
         WaitBatch wb;
@@ -1787,16 +1816,16 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
         if (rc) return rc;
         wb.wd = make_wd(); wb.tr = make_tr();
         void *args[] = {&wb};
-        ACX_CUDA_WD(cudaLaunchKernel((const void *)wait_kernel, dim3(1), dim3(kWaitThreads), args, 0, g_acx->istream));
+        ACX_CUDA_WD(cudaLaunchKernel((const void *)wait_kernel, dim3(1), dim3(kWaitThreads), args, 0, host_stream()));
         g_acx->st.kernels++;
         if (r->kind == ACX_REQ_RECV && r->typed) {   // strided destination: scatter the staged image
             UnpackParams up;
             fill_unpack(r, false, &up);
             void *uargs[] = {&up};
-            ACX_CUDA_WD(cudaLaunchKernel((const void *)unpack_kernel, dim3(pack_grid(r->bytes, up.L.vec)), dim3(256), uargs, 0, g_acx->istream));
+            ACX_CUDA_WD(cudaLaunchKernel((const void *)unpack_kernel, dim3(pack_grid(r->bytes, up.L.vec)), dim3(256), uargs, 0, host_stream()));
             g_acx->st.kernels++;
         }
-        ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+        ACX_CUDA_WD(cudaStreamSynchronize(host_stream()));
     }
     if (status != MPI_STATUS_IGNORE) {
         if (r->kind == ACX_REQ_SEND) host_status_send(status, r);
@@ -1830,7 +1859,7 @@ extern "C" int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses)
             if (!nb) return 0;
             pb.wd = make_wd();
             void *args[] = {&pb};
-            ACX_CUDA_WD(cudaLaunchKernel((const void *)pwait_batch_kernel, dim3(nb), dim3(kWaitThreads), args, 0, g_acx->istream));
+            ACX_CUDA_WD(cudaLaunchKernel((const void *)pwait_batch_kernel, dim3(nb), dim3(kWaitThreads), args, 0, host_stream()));
             g_acx->st.kernels++;
             nb = 0;
             return 0;
@@ -1846,15 +1875,15 @@ extern "C" int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses)
                     int rc;
                     if (++nb == kPBatch && (rc = flush())) return rc;
                 } else {
-                    int rc = pwait_emit(r, g_acx->istream);
+                    int rc = pwait_emit(r, host_stream());
                     if (rc) return rc;
                 }
                 any = true;
             }
         }
         { int rc = flush(); if (rc) return rc; }
-        if (!wait_ops.ops.empty()) { int rc = wait_ops.flush(g_acx->istream); if (rc) return rc; }
-        if (any) ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+        if (!wait_ops.ops.empty()) { int rc = wait_ops.flush(host_stream()); if (rc) return rc; }
+        if (any) ACX_CUDA_WD(cudaStreamSynchronize(host_stream()));
     }
     for (int i = 0; i < count; i++) {
         int rc = MPIX_Wait(&reqs[i], statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[i]);
@@ -2040,7 +2069,7 @@ extern "C" int MPIX_Startall(int count, MPIX_Request *reqs) {
     auto flush = [&]() -> int {
         if (!sb.n) return 0;
         void *args[] = {&sb};
-        ACX_CUDA_WD(cudaLaunchKernel((const void *)pstart_batch_kernel, dim3(1), dim3(32), args, 0, g_acx->istream));
+        ACX_CUDA_WD(cudaLaunchKernel((const void *)pstart_batch_kernel, dim3(1), dim3(32), args, 0, host_stream()));
         g_acx->st.kernels++;
         sb.n = 0;
         return 0;
@@ -2073,14 +2102,14 @@ extern "C" int MPIX_Startall(int count, MPIX_Request *reqs) {
             any_dev = true;
             continue;
         }
-        int rc = pstart_emit(r, g_acx->istream);
+        int rc = pstart_emit(r, host_stream());
         if (rc) return rc;
         any_dev = true;
     }
     { int rc = flush(); if (rc) return rc; }
-    if (!start_ops.ops.empty()) { int rc = start_ops.flush(g_acx->istream); if (rc) return rc; }
+    if (!start_ops.ops.empty()) { int rc = start_ops.flush(host_stream()); if (rc) return rc; }
     // Kernels launched by the user right after Start (on any stream) must observe the new epoch.
-    if (any_dev) ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    if (any_dev) ACX_CUDA_WD(cudaStreamSynchronize(host_stream()));
     return MPI_SUCCESS;
 }
 extern "C" int MPIX_Start(MPIX_Request *request) { return MPIX_Startall(1, request); }
@@ -2130,9 +2159,9 @@ static int pwait_host(AcxRequest *r, MPI_Status *status) {
         r->active = false;
         return rc;
     }
-    int rc = pwait_emit(r, g_acx->istream);
+    int rc = pwait_emit(r, host_stream());
     if (rc) return rc;
-    ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    ACX_CUDA_WD(cudaStreamSynchronize(host_stream()));
     if (status != MPI_STATUS_IGNORE) {
         status->MPI_SOURCE = r->comm_peer; status->MPI_TAG = r->tag; status->MPI_ERROR = MPI_SUCCESS;
 #ifdef ACX_MINI_MPI
@@ -2174,8 +2203,8 @@ extern "C" int MPIX_Pready_host(int partition, MPIX_Request *request) {
     if (r->host_transport) return MPI_Pready(partition, r->mpi_req);
     const acx_pchan *ch = r->pchan_d;
     void *args[] = {&ch, &partition};
-    ACX_CUDA_WD(cudaLaunchKernel((const void *)pready_host_kernel, dim3(1), dim3(256), args, 0, g_acx->istream));
-    ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    ACX_CUDA_WD(cudaLaunchKernel((const void *)pready_host_kernel, dim3(1), dim3(256), args, 0, host_stream()));
+    ACX_CUDA_WD(cudaStreamSynchronize(host_stream()));
     return MPI_SUCCESS;
 }
 
@@ -2185,15 +2214,15 @@ extern "C" int MPIX_Parrived_host(MPIX_Request *request, int partition, int *fla
     if (partition < 0 || partition >= r->partitions) return MPI_ERR_ARG;
     if (r->host_transport) return MPI_Parrived(r->mpi_req, partition, flag);
     if (!r->active) { *flag = 1; return MPI_SUCCESS; }
-    static int *dflag = nullptr;
+    thread_local int *dflag = nullptr;   // one pinned word per calling thread (never freed: a few bytes per thread)
     if (!dflag) ACX_CUDA(cudaHostAlloc((void **)&dflag, sizeof(int), cudaHostAllocMapped));
     *dflag = 0;
     const acx_pchan *ch = r->pchan_d;
     int *dp = nullptr;
     cudaHostGetDevicePointer((void **)&dp, dflag, 0);
     void *args[] = {&ch, &partition, &dp};
-    ACX_CUDA_WD(cudaLaunchKernel((const void *)parrived_host_kernel, dim3(1), dim3(1), args, 0, g_acx->istream));
-    ACX_CUDA_WD(cudaStreamSynchronize(g_acx->istream));
+    ACX_CUDA_WD(cudaLaunchKernel((const void *)parrived_host_kernel, dim3(1), dim3(1), args, 0, host_stream()));
+    ACX_CUDA_WD(cudaStreamSynchronize(host_stream()));
     *flag = *dflag;
     return MPI_SUCCESS;
 }

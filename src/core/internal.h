@@ -283,7 +283,7 @@ struct AcxState {
     std::vector<AcxHostReg> host_regs;
     std::vector<AcxCommMap> comms;           // known communicators (context id + rank translation)
     MPI_Comm icomm;                          // private dup of COMM_WORLD for handshakes
-    uint64_t serial = 1;
+    std::atomic<uint64_t> serial{1};         // request serials (application threads enqueue concurrently)
     std::vector<std::vector<int>> recv_outstanding;  // [src][chan] posted-not-yet-waited recvs
     // config
     bool trace = false;

@@ -256,3 +256,13 @@ def test_graphs_with_rendezvous_messages_relaunched_past_ring_depth(built, np_):
     r = acxrun(built, np_, built / "build/tests/graph_large")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_application_threads_drive_the_library_concurrently(built, np_):
+    """Four p2p threads (own stream, own tag; stream and host waits; heap churn) + one partitioned thread per rank
+    (tests/c/threads.c). Host-blocking calls use per-thread internal streams, so one thread's spinning wait cannot hold
+    back another thread's Pready / Start (the deadlock this program found on the software device at 3 ranks)."""
+    r = acxrun(built, np_, built / "build/tests/threads")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout
