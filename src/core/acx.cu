@@ -1487,7 +1487,8 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         rp.ring = acx_entries_of(g_acx->ctrl) + ring_idx;
         rp.seq = (uint64_t *)(g_acx->ctrl + G.off_recv_seq) + ((uint64_t)source * G.nchan + r->chan);
         rp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
-        rp.sack = rndv_capable ? acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx : nullptr;
+        rp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;   // always: a small receive must overwrite the previous generation's mirror too
+        rp.rndv_capable = rndv_capable ? 1 : 0;
         rp.peer_heap = g_acx->peer_heap[source];
         rp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)source * G.maxreg;
         rp.dst_off = dst_off; rp.cap = bytes; rp.serial = r->serial; rp.depth = G.depth; rp.peer = source;

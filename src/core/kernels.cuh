@@ -154,6 +154,7 @@ __device__ __forceinline__ void send_rndv_match(const SendParams &p, uint64_t k)
         uint64_t cap = ld_relaxed_sys(&p.sack[e].r_cap), off = ld_relaxed_sys(&p.sack[e].r_dst_off);
         p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, off);
         p.op->n = p.bytes < cap ? p.bytes : cap;
+        if (p.op->n == 0) p.op->coop = 0;   // nothing to chunk (receive too small for a rendezvous message): the plain mover publishes completion
         p.op->mover = 1;
     } else {
         p.op->mover = 0;
@@ -208,6 +209,7 @@ struct RecvParams {
     uint64_t cap;
     uint64_t serial;
     uint32_t depth, peer;
+    uint32_t rndv_capable, pad0;   // 0: capacity <= eager_max — a rendezvous-size message can only be a truncation error: it is completed with no bytes moved
     Watchdog wd;
     TraceCtx tr;
 };
@@ -218,13 +220,21 @@ __device__ __forceinline__ void recv_match_at(const RecvParams &p, uint64_t k) {
     acx_entry *ent = p.ring + e;
     spin_geq(&ent->consumed, g, p.wd, 0x5e02);  // my own previous use of this slot is finished
     if (p.sack) {  // mirror the destination into the sender's memory: a late sender then needs no remote load
-        st_relaxed_sys(&p.sack[e].r_dst_off, p.dst_off);
-        st_relaxed_sys(&p.sack[e].r_cap, p.cap);
+        // A receive too small for any rendezvous message publishes capacity 0: a late rendezvous sender then "pushes" zero
+        // bytes and completes the (truncated) message, instead of acting on the mirror a previous generation left behind.
+        st_relaxed_sys(&p.sack[e].r_dst_off, p.rndv_capable ? p.dst_off : 0);
+        st_relaxed_sys(&p.sack[e].r_cap, p.rndv_capable ? p.cap : 0);
         st_release_sys(&p.sack[e].r_gen, g + 1);   // a pushing sender's gate keys on this
     }
     uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull);   // release orders the mirror stores before it
     p.op->ticket = k; p.op->cta_count = 0; p.op->mover = 0; p.op->bounce_n = 0; p.op->coop = 0;
-    if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && (ent->s_kind == ACX_KIND_RNDV || ent->s_kind == ACX_KIND_RNDV_COOP)) {
+    if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && (ent->s_kind == ACX_KIND_RNDV || ent->s_kind == ACX_KIND_RNDV_COOP) && !p.rndv_capable) {
+        // a rendezvous message is waiting for a receive that cannot hold it (no mover was launched for this receive):
+        // complete it here with nothing moved; the wait reports MPI_ERR_TRUNCATE and 0 bytes
+        __threadfence_system();
+        st_release_sys(&ent->done, g + 1);
+        if (p.sack) st_release_sys(&p.sack[e].sdone, g + 1);
+    } else if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && (ent->s_kind == ACX_KIND_RNDV || ent->s_kind == ACX_KIND_RNDV_COOP)) {
         p.op->coop = ent->s_kind == ACX_KIND_RNDV_COOP;   // the sender decides how its message is moved
         // the send is already here and waiting: I move the data (pull)
         uint64_t sb = ent->s_bytes;
@@ -284,6 +294,7 @@ __global__ void push_gate(GateParams p) {
     const uint64_t cap = ld_relaxed_sys(&p.sack[e].r_cap), off = ld_relaxed_sys(&p.sack[e].r_dst_off);
     p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, off);
     p.op->n = p.bytes < cap ? p.bytes : cap;
+    if (p.op->n == 0) p.op->coop = 0;
     p.op->mover = 1;
 }
 
@@ -499,7 +510,7 @@ __global__ void __launch_bounds__(kMoverThreads) recv_any_kernel(AnyParams p) {
             acx_sack *peer_sack = (acx_sack *)(p.tbl->peer_ctrl[src] + G.off_sack) + acx_entry_index(G, (int)p.me, chan, 0);
             RecvParams rp;
             rp.ring = entries + ring_idx;
-            rp.sack = p.rndv_capable ? peer_sack : nullptr;
+            rp.sack = peer_sack; rp.rndv_capable = p.rndv_capable;
             rp.seq = nullptr;
             rp.op = op;
             rp.peer_heap = p.tbl->peer_heap[src];
@@ -744,6 +755,7 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
             }
             uint64_t sb = ent->s_bytes;
             s_n = sb < w.cap ? sb : w.cap;
+            if (!eager && w.cap <= w.eager_max) s_n = 0;   // rendezvous message into an eager-size receive: truncated, nothing was moved
             s_eager = eager;
         }
     }

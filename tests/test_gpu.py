@@ -266,3 +266,13 @@ def test_application_threads_drive_the_library_concurrently(built, np_):
     r = acxrun(built, np_, built / "build/tests/threads")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_truncation_statuses_and_argument_validation(built, np_):
+    """Messages longer than the receive (eager, rendezvous, rendezvous into an eager-size receive: MPI_ERR_TRUNCATE, no
+    overrun), tag collisions on one channel reported as MPI_ERR_TAG, a 30-request Waitall_enqueue with statuses, invalid
+    arguments rejected without leaks, MPIX_Request_free completing un-waited requests — tests/c/status_errors.c."""
+    r = acxrun(built, np_, built / "build/tests/status_errors")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout
