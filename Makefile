@@ -114,7 +114,7 @@ emu-tsan:
 	$(SAN_CXX) -O1 -fsanitize=thread -Wno-tsan $(EMU_FLAGS) tests/emu/protocol_emu.cpp -o $(B)/tests/protocol_emu_tsan -lpthread
 	TSAN_OPTIONS="halt_on_error=1 history_size=4" $(B)/tests/protocol_emu_tsan
 
-EMU_CTESTS := $(patsubst tests/c/%.c,$(EMU)/tests/%,$(wildcard tests/c/*.c)) $(EMU)/tests/ring_partitioned
+EMU_CTESTS := $(patsubst tests/c/%.c,$(EMU)/tests/%,$(wildcard tests/c/*.c)) $(EMU)/tests/ring_partitioned $(EMU)/tests/partitioned_device
 emu-lib: $(EMU)/libacx_emu.so
 emu-tests: $(EMU_CTESTS)
 $(EMU)/acx.o: src/core/acx.cu src/core/internal.h src/core/kernels.cuh include/mpi-acx.h include/acx_device.cuh include/mpi.h tests/emu/cuda_emu.h

@@ -62,7 +62,7 @@ struct Trap {};   // thrown through a fiber by __trap() and by yields once the d
 struct Fiber {
     ucontext_t ctx;
     Idx tid;
-    int state = 0;   // 0 ready, 1 at barrier, 2 done
+    int state = 0;   // 0 ready, 1 at __syncthreads, 2 done, 3 at __syncwarp
     char *stack = nullptr;
     void *asan_fake = nullptr, *tsan = nullptr;
 };
@@ -111,6 +111,7 @@ inline void to_fiber(Cta *c, Fiber *f) {
 }
 inline void yield() { Cta *c = cta; to_sched(c, false); check_trap(); }
 inline void barrier() { Cta *c = cta; c->cur->state = 1; to_sched(c, false); check_trap(); }
+inline void warp_barrier() { Cta *c = cta; if (c->bdim.x <= 1) return; c->cur->state = 3; to_sched(c, false); check_trap(); }
 inline void fiber_main() {
     Cta *c = cta;
 #ifdef EMU_ASAN
@@ -167,6 +168,16 @@ inline void run_cta(unsigned bx, unsigned gx, unsigned threads, const std::funct
         }
         if (done == threads) break;
         if (waiting && waiting + done == threads) { for (auto &x : f) if (x.state == 1) x.state = 0; idle = 0; continue; }   // barrier released (exited threads do not take part)
+        {   // __syncwarp: a warp's lanes go on once every live lane of that warp has arrived
+            bool released = false;
+            for (unsigned w0 = 0; w0 < threads; w0 += 32) {
+                const unsigned w1 = w0 + 32 < threads ? w0 + 32 : threads;
+                unsigned at = 0, live = 0;
+                for (unsigned i = w0; i < w1; i++) { if (f[i].state == 3) at++; if (f[i].state != 2) live++; }
+                if (at && at == live) { for (unsigned i = w0; i < w1; i++) if (f[i].state == 3) f[i].state = 0; released = true; }
+            }
+            if (released) { idle = 0; continue; }
+        }
         // somebody is spinning on another CTA / rank / stream: give the CPU away — politely at first, then for real
         // (a box with fewer cores than emulated threads must not burn them all in sched_yield)
         if (done != last_done) { last_done = done; idle = 0; }
@@ -244,7 +255,7 @@ static const emu::Bid blockIdx{};
 static const emu::Bdim blockDim{};
 static const emu::Gdim gridDim{};
 inline void __syncthreads() { emu::barrier(); }
-inline void __syncwarp() {}
+inline void __syncwarp() { emu::warp_barrier(); }
 inline void __nanosleep(unsigned) { emu::yield(); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }

@@ -276,3 +276,14 @@ def test_truncation_statuses_and_argument_validation(built, np_):
     r = acxrun(built, np_, built / "build/tests/status_errors")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_device_partitioned_api(built, np_):
+    """include/acx_device.cuh beyond MPIX_Pready / MPIX_Parrived: zero-copy producer (remote_partition_ptr + pready_signal) with
+    a blocking consumer, cooperative pready_cta / pready_warp into heap and private receive buffers, stream-ordered rounds
+    (MPIX_Start_enqueue / MPIX_Pwait_enqueue), and a persistent kernel running 25 two-sided rounds on explicit epochs —
+    tests/c/partitioned_device.cu."""
+    r = acxrun(built, np_, built / "build/tests/partitioned_device")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout

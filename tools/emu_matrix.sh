@@ -16,7 +16,7 @@ run() {  # run <label> <np> <prog> [env...]
     if [ $rc -eq 0 ] && echo "$out" | grep -q "PASS"; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms
     else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $rc "$(echo "$out" | grep -v "ASan doesn\x27t fully support" | tail -${EMU_TAIL:-8})"; fails=$((fails+1)); fi
 }
-progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors"
+progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors"
 nps="1 2 3"
 [ "$mode" = full ] && nps="1 2 3 4"
 for p in $progs; do for np in $nps; do run default $np $p; done; done
@@ -38,6 +38,8 @@ run pbatch 3 ring_partitioned ACX_PBATCH=1
 run memops 2 ring_partitioned ACX_MEMOPS=1
 run memops 3 ring_partitioned ACX_MEMOPS=1
 run memops 4 subcomm ACX_MEMOPS=1
+run memops 2 partitioned_device ACX_MEMOPS=1
+run pbatch 3 partitioned_device ACX_PBATCH=1
 if [ "$mode" = full ]; then
     for p in ring_all large_msgs stress ordering graph_large status_errors; do
         run no-fuse 2 $p ACX_FUSE_RNDV=0
