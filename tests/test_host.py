@@ -245,3 +245,23 @@ def test_device_transport_under_address_sanitizer(built):
     """`make emu-asan`: runtime + software CUDA device + conformance programs built with ASan/UBSan/LSan, quick matrix."""
     r = subprocess.run(["make", "-C", str(built), "emu-asan"], capture_output=True, text=True, timeout=2400)
     assert r.returncode == 0 and "0 failure(s)" in r.stdout, r.stdout[-4000:] + r.stderr[-1500:]
+
+
+def test_device_trace_to_chrome_trace(built, tmp_path):
+    """ACX_TRACE=1 on the software device -> per-rank JSONL -> tools/trace_to_chrome.py: one Chrome/Perfetto trace with wait
+    and mover slices per rank and a flow arrow per message."""
+    import json
+    subprocess.run(["make", "-C", str(built), "-j4", "emu-lib", "emu-tests"], check=True, capture_output=True, timeout=900)
+    env = dict(os.environ, ACX_MPI_NO_CUDA="1", ACX_TRACE="1", ACX_TRACE_DIR=str(tmp_path))
+    r = subprocess.run([str(built / "bin/acxrun"), "-np", "2", "--timeout", "100", str(built / "build/emu/tests/large_msgs")], env=env, capture_output=True, text=True, timeout=200)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    out = tmp_path / "trace.json"
+    r = subprocess.run([sys.executable, str(built / "tools/trace_to_chrome.py"), str(tmp_path), "-o", str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    ev = json.loads(out.read_text())["traceEvents"]
+    kinds = {}
+    for e in ev:
+        kinds[e["ph"]] = kinds.get(e["ph"], 0) + 1
+    assert kinds.get("X", 0) > 50 and kinds.get("i", 0) > 50 and kinds.get("s", 0) == kinds.get("f", 0) > 20, kinds
+    assert {e["pid"] for e in ev} == {0, 1}
+    assert any(e["ph"] == "X" and e["name"].startswith("move") and e["args"]["bytes"] > 8192 for e in ev)
