@@ -1487,8 +1487,9 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         rp.ring = acx_entries_of(g_acx->ctrl) + ring_idx;
         rp.seq = (uint64_t *)(g_acx->ctrl + G.off_recv_seq) + ((uint64_t)source * G.nchan + r->chan);
         rp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
-        rp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;   // always: a small receive must overwrite the previous generation's mirror too
+        rp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;
         rp.rndv_capable = rndv_capable ? 1 : 0;
+        rp.publish = (rndv_capable || g_apush) ? 1 : 0;   // sender-push gates key on the mirror's generation: every receive must publish then
         rp.peer_heap = g_acx->peer_heap[source];
         rp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)source * G.maxreg;
         rp.dst_off = dst_off; rp.cap = bytes; rp.serial = r->serial; rp.depth = G.depth; rp.peer = source;

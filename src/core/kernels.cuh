@@ -150,8 +150,10 @@ __device__ __forceinline__ void send_rndv_match(const SendParams &p, uint64_t k)
     if (p.apush) {
         p.op->mover = 0;   // decided by push_gate on the channel stream once the receive is posted
     } else if ((uint32_t)old == (uint32_t)(g + 1)) {  // receive already posted: I move the data (push)
-        // the receiver mirrored its destination into MY sack before it bumped the state word
-        uint64_t cap = ld_relaxed_sys(&p.sack[e].r_cap), off = ld_relaxed_sys(&p.sack[e].r_dst_off);
+        // the receiver mirrored its destination into MY sack before it bumped the state word — if it can take a rendezvous
+        // message at all: a mirror of another generation means "too small", i.e. capacity 0 for this purpose
+        const bool fresh = ld_relaxed_sys(&p.sack[e].r_gen) == g + 1;
+        uint64_t cap = fresh ? ld_relaxed_sys(&p.sack[e].r_cap) : 0, off = fresh ? ld_relaxed_sys(&p.sack[e].r_dst_off) : 0;
         p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, off);
         p.op->n = p.bytes < cap ? p.bytes : cap;
         if (p.op->n == 0) p.op->coop = 0;   // nothing to chunk (receive too small for a rendezvous message): the plain mover publishes completion
@@ -209,7 +211,8 @@ struct RecvParams {
     uint64_t cap;
     uint64_t serial;
     uint32_t depth, peer;
-    uint32_t rndv_capable, pad0;   // 0: capacity <= eager_max — a rendezvous-size message can only be a truncation error: it is completed with no bytes moved
+    uint32_t rndv_capable;  // 0: capacity <= eager_max — a rendezvous-size message can only be a truncation error: it is completed with no bytes moved
+    uint32_t publish;       // mirror {destination, capacity} into the sender's sack (rendezvous-capable receives; every receive in sender-push mode)
     Watchdog wd;
     TraceCtx tr;
 };
@@ -219,9 +222,10 @@ __device__ __forceinline__ void recv_match_at(const RecvParams &p, uint64_t k) {
     uint64_t g = k / p.depth;
     acx_entry *ent = p.ring + e;
     spin_geq(&ent->consumed, g, p.wd, 0x5e02);  // my own previous use of this slot is finished
-    if (p.sack) {  // mirror the destination into the sender's memory: a late sender then needs no remote load
-        // A receive too small for any rendezvous message publishes capacity 0: a late rendezvous sender then "pushes" zero
-        // bytes and completes the (truncated) message, instead of acting on the mirror a previous generation left behind.
+    if (p.publish) {  // mirror the destination into the sender's memory: a late sender then needs no remote load
+        // Small receives (capacity <= eager_max) stay silent — three remote stores less on the latency path. A late
+        // rendezvous sender notices: the mirror's generation (r_gen) is not this slot generation's, so it moves nothing and
+        // completes the (truncated) message instead of acting on what an earlier generation left behind.
         st_relaxed_sys(&p.sack[e].r_dst_off, p.rndv_capable ? p.dst_off : 0);
         st_relaxed_sys(&p.sack[e].r_cap, p.rndv_capable ? p.cap : 0);
         st_release_sys(&p.sack[e].r_gen, g + 1);   // a pushing sender's gate keys on this
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(kMoverThreads) recv_any_kernel(AnyParams p) {
             acx_sack *peer_sack = (acx_sack *)(p.tbl->peer_ctrl[src] + G.off_sack) + acx_entry_index(G, (int)p.me, chan, 0);
             RecvParams rp;
             rp.ring = entries + ring_idx;
-            rp.sack = peer_sack; rp.rndv_capable = p.rndv_capable;
+            rp.sack = peer_sack; rp.rndv_capable = p.rndv_capable; rp.publish = p.rndv_capable;
             rp.seq = nullptr;
             rp.op = op;
             rp.peer_heap = p.tbl->peer_heap[src];

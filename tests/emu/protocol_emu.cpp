@@ -69,7 +69,7 @@ static void build_recv(int me, int src, int chan, uint64_t dst_off, uint64_t cap
     rp->ring = acx_entries_of(R[me].ctrl) + ring_idx;
     rp->seq = (uint64_t *)(R[me].ctrl + G.off_recv_seq) + ((uint64_t)src * G.nchan + chan);
     rp->op = op_of(me, slot);
-    rp->sack = acx_sacks_of(R[src].ctrl) + sack_idx; rp->rndv_capable = rndv ? 1 : 0;
+    rp->sack = acx_sacks_of(R[src].ctrl) + sack_idx; rp->rndv_capable = rndv ? 1 : 0; rp->publish = rp->rndv_capable;
     rp->peer_heap = R[src].heap;
     rp->xlat = (const uint64_t *)(R[me].ctrl + G.off_xlat) + (uint64_t)src * G.maxreg;
     rp->dst_off = rndv ? dst_off : ~0ull; rp->cap = cap; rp->serial = *serial = R[me].serial++; rp->depth = G.depth; rp->peer = src;
