@@ -131,6 +131,38 @@ static int run_ring(size_t bytes, int steps, int warmup, bool heap, bool e2e, bo
 // ------------------------------------------------------------------------------------------
 // Same ping-pong, but `unroll` iterations are captured once into a CUDA graph and the graph is relaunched: the host's
 // per-call launch cost (the limiter of the plain on-stream loop) is paid once, what remains is the device-side path.
+// One ping-pong iteration. `blocking` (acx-b200 only): MPIX_Send_enqueue / MPIX_Recv_enqueue — an eager receive is one fused
+// post+wait kernel, so an iteration is two launches per rank instead of three.
+static bool g_blocking = false;
+static int pingpong_iter(char *sbuf, char *rbuf, size_t b, cudaStream_t *st) {
+    const int peer = 1 - g_rank, t_out = g_rank == 0 ? 1 : 2, t_in = g_rank == 0 ? 2 : 1;
+#ifndef ACX_BENCH_REFERENCE
+    if (g_blocking) {
+        if (g_rank == 0) {
+            OK(MPIX_Send_enqueue(sbuf, (int)b, MPI_BYTE, peer, t_out, MPI_COMM_WORLD, MPIX_QUEUE_CUDA_STREAM, st));
+            OK(MPIX_Recv_enqueue(rbuf, (int)b, MPI_BYTE, peer, t_in, MPI_COMM_WORLD, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, st));
+        } else {
+            OK(MPIX_Recv_enqueue(rbuf, (int)b, MPI_BYTE, peer, t_in, MPI_COMM_WORLD, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, st));
+            OK(MPIX_Send_enqueue(sbuf, (int)b, MPI_BYTE, peer, t_out, MPI_COMM_WORLD, MPIX_QUEUE_CUDA_STREAM, st));
+        }
+        return 0;
+    }
+#endif
+    MPIX_Request q;
+    if (g_rank == 0) {
+        OK(MPIX_Isend_enqueue(sbuf, (int)b, MPI_BYTE, peer, t_out, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, st));
+        OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, st));
+        OK(MPIX_Irecv_enqueue(rbuf, (int)b, MPI_BYTE, peer, t_in, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, st));
+        OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, st));
+    } else {
+        OK(MPIX_Irecv_enqueue(rbuf, (int)b, MPI_BYTE, peer, t_in, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, st));
+        OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, st));
+        OK(MPIX_Isend_enqueue(sbuf, (int)b, MPI_BYTE, peer, t_out, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, st));
+        OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, st));
+    }
+    return 0;
+}
+
 static int run_pingpong_graph(size_t min_b, size_t max_b, bool heap, int launches) {
     if (g_size < 2) { if (g_rank == 0) printf("{\"bench\": \"pingpong_graph\", \"skipped\": \"needs >= 2 ranks\"}\n"); return 0; }
     const int unroll = 16;
@@ -140,25 +172,14 @@ static int run_pingpong_graph(size_t min_b, size_t max_b, bool heap, int launche
     CK(cudaMemset(sbuf, 1, max_b)); CK(cudaMemset(rbuf, 0, max_b));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    if (g_rank == 0) printf("{\"bench\": \"pingpong_graph\", \"impl\": \"%s\", \"heap\": %d, \"unroll\": %d, \"rows\": [", kImpl, (int)heap, unroll);
+    if (g_rank == 0) printf("{\"bench\": \"pingpong_graph\", \"impl\": \"%s\", \"heap\": %d, \"blocking_calls\": %d, \"unroll\": %d, \"rows\": [", kImpl, (int)heap, (int)g_blocking, unroll);
     bool first = true;
     for (size_t b = min_b; b <= max_b; b *= 4) {
         cudaGraph_t g; cudaGraphExec_t ge;
         if (g_rank < 2) {
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal));
             for (int i = 0; i < unroll; i++) {
-                MPIX_Request q;
-                if (g_rank == 0) {
-                    OK(MPIX_Isend_enqueue(sbuf, (int)b, MPI_BYTE, 1, 1, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
-                    OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
-                    OK(MPIX_Irecv_enqueue(rbuf, (int)b, MPI_BYTE, 1, 2, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
-                    OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
-                } else {
-                    OK(MPIX_Irecv_enqueue(rbuf, (int)b, MPI_BYTE, 0, 1, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
-                    OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
-                    OK(MPIX_Isend_enqueue(sbuf, (int)b, MPI_BYTE, 0, 2, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
-                    OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
-                }
+                pingpong_iter(sbuf, rbuf, b, &st);
             }
             CK(cudaStreamEndCapture(st, &g));
             CK(cudaGraphInstantiate(&ge, g, 0));
@@ -191,7 +212,7 @@ static int run_pingpong(size_t min_b, size_t max_b, bool heap, int max_iters) {
     CK(cudaMemset(sbuf, 1, max_b)); CK(cudaMemset(rbuf, 0, max_b));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    if (g_rank == 0) printf("{\"bench\": \"pingpong\", \"impl\": \"%s\", \"heap\": %d, \"rows\": [", kImpl, (int)heap);
+    if (g_rank == 0) printf("{\"bench\": \"pingpong\", \"impl\": \"%s\", \"heap\": %d, \"blocking_calls\": %d, \"rows\": [", kImpl, (int)heap, (int)g_blocking);
     bool first = true;
     for (size_t b = min_b; b <= max_b; b *= 2) {
         int iters = b <= (64u << 10) ? max_iters : b <= (16u << 20) ? max_iters / 4 : 6;
@@ -204,18 +225,7 @@ static int run_pingpong(size_t min_b, size_t max_b, bool heap, int max_iters) {
             if (phase == 1) CK(cudaEventRecord(e0, st));
             if (g_rank < 2) {
                 for (int i = 0; i < n; i++) {
-                    MPIX_Request q;
-                    if (g_rank == 0) {
-                        OK(MPIX_Isend_enqueue(sbuf, (int)b, MPI_BYTE, 1, 1, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
-                        OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
-                        OK(MPIX_Irecv_enqueue(rbuf, (int)b, MPI_BYTE, 1, 2, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
-                        OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
-                    } else {
-                        OK(MPIX_Irecv_enqueue(rbuf, (int)b, MPI_BYTE, 0, 1, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
-                        OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
-                        OK(MPIX_Isend_enqueue(sbuf, (int)b, MPI_BYTE, 0, 2, MPI_COMM_WORLD, &q, MPIX_QUEUE_CUDA_STREAM, &st));
-                        OK(MPIX_Wait_enqueue(&q, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
-                    }
+                    pingpong_iter(sbuf, rbuf, b, &st);
                 }
             }
             if (phase == 1) CK(cudaEventRecord(e1, st));
@@ -305,6 +315,7 @@ int main(int argc, char **argv) {
         else if (a == "--e2e") e2e = true;
         else if (a == "--no-verify") verify = false;
         else if (a == "--prepost") prepost = true;
+        else if (a == "--blocking") g_blocking = true;   // pingpong / pingpong_graph through MPIX_Send_enqueue / MPIX_Recv_enqueue (not in the reference build)
     }
     if (mode == "ring") rc = run_ring(bytes, steps, warmup, heap, e2e, verify, prepost);
     else if (mode == "pingpong") rc = run_pingpong(minb, maxb, heap, iters);

@@ -93,6 +93,12 @@ int MPIX_Peer_ptr_at(size_t offset, int peer, void **peer_ptr);
 int MPIX_Pready_host(int partition, MPIX_Request *request);
 int MPIX_Parrived_host(MPIX_Request *request, int partition, int *flag);
 
+/* Blocking-on-the-queue send and receive: work enqueued after the call runs once the operation is complete (= the Isend /
+ * Irecv + Wait pair, without a request handle). An eager-size MPIX_Recv_enqueue on a stream is ONE kernel (post + wait
+ * fused) and an eager MPIX_Send_enqueue is just its trigger, so a small-message exchange costs two launches instead of three. */
+int MPIX_Send_enqueue(const void *sendbuf, int nelems, MPI_Datatype dtype, int dst_rank, int tag, MPI_Comm comm, int queue_kind, void *queue_handle);
+int MPIX_Recv_enqueue(void *recvbuf, int nelems, MPI_Datatype dtype, int src_rank, int tag, MPI_Comm comm, MPI_Status *status, int queue_kind, void *queue_handle);
+
 /* Stream-ordered partitioned round control (the reference only has host Start/Wait):
  * enqueue the Start / the completion wait of a partitioned request on a stream. */
 int MPIX_Start_enqueue(MPIX_Request *request, int qtype, void *queue);

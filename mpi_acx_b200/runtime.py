@@ -208,6 +208,22 @@ def irecv(t, source: int, tag: int = 0, stream=None) -> Request:
     return Request(h, t)
 
 
+def send(t, dest: int, tag: int = 0, stream=None) -> None:
+    """Blocking-on-the-stream send (MPIX_Send_enqueue): later work on the stream runs once the tensor may be reused.
+    An eager-size message is a single trigger kernel."""
+    p, n, dt = _typed_buf(t)
+    cs = _stream_arg(stream)
+    _ck(N.lib().MPIX_Send_enqueue(p, n, dt, dest, tag, N.MPI_COMM_WORLD, N.QUEUE_STREAM, ctypes.byref(cs)), "MPIX_Send_enqueue")
+
+
+def recv(t, source: int, tag: int = 0, stream=None) -> None:
+    """Blocking-on-the-stream receive (MPIX_Recv_enqueue): later work on the stream sees the data. An eager-size dense
+    receive is ONE kernel (post + wait fused) instead of the two of irecv + wait_enqueue."""
+    p, n, dt = _typed_buf(t)
+    cs = _stream_arg(stream)
+    _ck(N.lib().MPIX_Recv_enqueue(p, n, dt, source, tag, N.MPI_COMM_WORLD, None, N.QUEUE_STREAM, ctypes.byref(cs)), "MPIX_Recv_enqueue")
+
+
 def waitall_enqueue(reqs: Iterable[Request], stream=None) -> None:
     reqs = list(reqs)
     arr = (ctypes.c_void_p * len(reqs))(*[r.h for r in reqs])

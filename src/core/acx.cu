@@ -1773,6 +1773,119 @@ extern "C" int MPIX_Waitall_enqueue(int count, MPIX_Request *reqs, MPI_Status *s
     return wait_enqueue_impl(count, reqs, statuses, qtype, queue);
 }
 
+// =======================================================================================
+// MPIX_Send_enqueue / MPIX_Recv_enqueue (extension): blocking on the queue, no request handle
+// =======================================================================================
+extern "C" int MPIX_Send_enqueue(const void *buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm, int qtype, void *queue) {
+    // An eager send is complete when its trigger retires, so the pair below launches exactly one kernel for it;
+    // a rendezvous send gets its trigger (+ mover) and a wait, as the two calls would.
+    MPIX_Request r = MPIX_REQUEST_NULL;
+    int rc = MPIX_Isend_enqueue(buf, count, datatype, dest, tag, comm, &r, qtype, queue);
+    if (rc) return rc;
+    if (qtype == MPIX_QUEUE_CUDA_GRAPH) {
+        // explicit-graph mode returns ONE graph per call: chain the wait's graph behind the send's as child nodes
+        cudaGraph_t gs = *(cudaGraph_t *)queue, gw = nullptr, g = nullptr;
+        rc = MPIX_Wait_enqueue(&r, MPI_STATUS_IGNORE, qtype, &gw);
+        if (rc) { cudaGraphDestroy(gs); return rc; }
+        cudaGraphNode_t a, b;
+        if (cudaGraphCreate(&g, 0) != cudaSuccess || cudaGraphAddChildGraphNode(&a, g, nullptr, 0, gs) != cudaSuccess || cudaGraphAddChildGraphNode(&b, g, &a, 1, gw) != cudaSuccess) {
+            ACX_ERR("MPIX_Send_enqueue: cannot compose the graph");
+            if (g) cudaGraphDestroy(g);
+            cudaGraphDestroy(gs); cudaGraphDestroy(gw);
+            return MPI_ERR_OTHER;
+        }
+        cudaGraphDestroy(gs); cudaGraphDestroy(gw);   // the child nodes hold clones (with the slots' user objects)
+        *(cudaGraph_t *)queue = g;
+        return MPI_SUCCESS;
+    }
+    return MPIX_Wait_enqueue(&r, MPI_STATUS_IGNORE, qtype, queue);
+}
+
+extern "C" int MPIX_Recv_enqueue(void *buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPI_Status *status, int qtype, void *queue) {
+    AcxRange _r("MPIX_Recv_enqueue");
+    // Fast path: device transport, stream queue (capturing or not), contiguous eager-size receive from a specific peer.
+    bool fast = g_acx && g_acx->initialized && g_acx->device && qtype == MPIX_QUEUE_CUDA_STREAM && queue && source >= 0 && tag >= 0 && !g_branch;
+    size_t bytes = 0; int ctx = 0, wsource = 0;
+    AcxLayout ty;
+    if (fast) {
+        MPIX_Request dummy = MPIX_REQUEST_NULL;
+        int rc = check_common("MPIX_Recv_enqueue", true, count, datatype, source, tag, comm, &dummy, queue, &bytes, &ctx, &wsource, &ty);
+        if (rc) return rc;
+        fast = !ty.noncontig && bytes <= g_acx->geom.eager_max;
+    }
+    if (!fast) {
+        MPIX_Request r = MPIX_REQUEST_NULL;
+        int rc = MPIX_Irecv_enqueue(buf, count, datatype, source, tag, comm, &r, qtype, queue);
+        if (rc) return rc;
+        if (qtype == MPIX_QUEUE_CUDA_GRAPH) {
+            cudaGraph_t gr = *(cudaGraph_t *)queue, gw = nullptr, g = nullptr;
+            rc = MPIX_Wait_enqueue(&r, status, qtype, &gw);
+            if (rc) { cudaGraphDestroy(gr); return rc; }
+            cudaGraphNode_t a, b;
+            if (cudaGraphCreate(&g, 0) != cudaSuccess || cudaGraphAddChildGraphNode(&a, g, nullptr, 0, gr) != cudaSuccess || cudaGraphAddChildGraphNode(&b, g, &a, 1, gw) != cudaSuccess) {
+                ACX_ERR("MPIX_Recv_enqueue: cannot compose the graph");
+                if (g) cudaGraphDestroy(g);
+                cudaGraphDestroy(gr); cudaGraphDestroy(gw);
+                return MPI_ERR_OTHER;
+            }
+            cudaGraphDestroy(gr); cudaGraphDestroy(gw);
+            *(cudaGraph_t *)queue = g;
+            return MPI_SUCCESS;
+        }
+        return MPIX_Wait_enqueue(&r, status, qtype, queue);
+    }
+    AcxRequest *r = new_request(ACX_REQ_RECV, wsource, tag, ctx, bytes, buf);
+    r->comm_peer = source;
+    source = wsource;
+    Emitter em;
+    int rc = em.begin(qtype, queue);
+    if (rc) { delete r; return rc; }
+    r->in_graph = em.in_graph();
+    r->chan = chan_of(tag, ctx);
+    if (!r->in_graph) {   // the depth check of MPIX_Irecv_enqueue: this receive occupies a ring slot until its kernel has run
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        if (g_acx->recv_outstanding[source][r->chan] >= g_acx->geom.depth) {
+            ACX_ERR("more than ACX_DEPTH=%d receives outstanding from rank %d on the channel of tag %d", g_acx->geom.depth, source, tag);
+            delete r;
+            return MPI_ERR_OTHER;
+        }
+    }
+    if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
+    if ((rc = acx_device_alias(buf, bytes, &r->dev_buf))) goto fail;
+    {
+        const acx_geom &G = g_acx->geom;
+        r->heap_off = acx_heap_offset_of(buf);
+        const uint64_t ring_idx = acx_entry_index(G, source, r->chan, 0), sack_idx = acx_entry_index(G, g_acx->rank, r->chan, 0);
+        RecvParams rp;
+        memset(&rp, 0, sizeof rp);
+        rp.ring = acx_entries_of(g_acx->ctrl) + ring_idx;
+        rp.seq = (uint64_t *)(g_acx->ctrl + G.off_recv_seq) + ((uint64_t)source * G.nchan + r->chan);
+        rp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
+        rp.sack = acx_sacks_of(g_acx->peer_ctrl[source]) + sack_idx;
+        rp.peer_heap = g_acx->peer_heap[source];
+        rp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)source * G.maxreg;
+        rp.dst_off = ~0ull; rp.cap = bytes; rp.serial = r->serial; rp.depth = G.depth; rp.peer = source;
+        rp.rndv_capable = 0; rp.publish = g_apush ? 1 : 0;
+        rp.wd = make_wd(); rp.tr = make_tr();
+        WaitBatch wb;
+        memset(&wb, 0, sizeof wb);
+        const bool retire = !em.in_graph();
+        if ((rc = fill_wait(r, status, retire, false, &wb.w[0]))) goto fail;
+        wb.wd = make_wd(); wb.tr = make_tr();
+        if ((rc = em.launch2(recv_wait_fused, dim3(1), dim3(kWaitThreads), rp, wb))) goto fail;
+    }
+    if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        if (!em.in_graph()) { g_acx->slot_busy[r->slot] = 3; g_pending_retire.push_back(r->slot); }   // reclaimed once the kernel marks it retired
+    }
+    g_acx->st.recvs++; g_acx->st.bytes_recv += bytes; g_acx->st.waits++;
+    return MPI_SUCCESS;
+fail:
+    { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); acx_slot_free(r->slot); }
+    return rc;
+}
+
 // ---- partitioned: forward declarations ----
 static int pwait_host(AcxRequest *r, MPI_Status *status);
 static int pwait_emit(AcxRequest *r, cudaStream_t stream);
@@ -2234,7 +2347,7 @@ extern "C" int MPIX_Parrived_host(MPIX_Request *request, int partition, int *fla
 // their argument lists. All of them are written for any blockDim (second argument), so the emulation may shrink blocks.
 ACX_EMU_KERNEL(copy_kernel, true) ACX_EMU_KERNEL(send_trigger, true) ACX_EMU_KERNEL(recv_trigger, true) ACX_EMU_KERNEL(push_gate, true)
 ACX_EMU_KERNEL(mover, true) ACX_EMU_KERNEL(send_rndv_fused, true) ACX_EMU_KERNEL(recv_rndv_fused, true) ACX_EMU_KERNEL(recv_any_kernel, true)
-ACX_EMU_KERNEL(coop_gate, true) ACX_EMU_KERNEL(coop_kernel, true) ACX_EMU_KERNEL(wait_kernel, true) ACX_EMU_KERNEL(bounce_out_kernel, true)
+ACX_EMU_KERNEL(coop_gate, true) ACX_EMU_KERNEL(coop_kernel, true) ACX_EMU_KERNEL(wait_kernel, true) ACX_EMU_KERNEL(recv_wait_fused, true) ACX_EMU_KERNEL(bounce_out_kernel, true)
 ACX_EMU_KERNEL(pack_kernel, true) ACX_EMU_KERNEL(unpack_kernel, true) ACX_EMU_KERNEL(pstart_kernel, true) ACX_EMU_KERNEL(pstart_batch_kernel, true)
 ACX_EMU_KERNEL(pwait_kernel, true) ACX_EMU_KERNEL(pwait_batch_kernel, true) ACX_EMU_KERNEL(pready_host_kernel, true) ACX_EMU_KERNEL(parrived_host_kernel, true)
 #endif

@@ -721,9 +721,7 @@ struct WaitBatch {
     TraceCtx tr;
 };
 
-__global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
-    pdl_prologue();
-    const WaitOne &w = b.w[blockIdx.x];
+__device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) {
     __shared__ uint64_t s_n;
     __shared__ int s_eager;
     const unsigned tid = threadIdx.x;
@@ -800,6 +798,19 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
         if (w.retire) ACX_HOST_FLAG_SET(&w.hstat->retired, 1);
         trace(b.tr, ACX_EV_WAIT_END, w.src, op->ticket, s_n);
     }
+}
+__global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
+    pdl_prologue();
+    wait_body(b, b.w[blockIdx.x]);
+}
+
+// MPIX_Recv_enqueue for eager-size receives: post + complete in ONE launch (trigger, then the wait's body). The small-
+// message exchange is bound by the host's launch rate (three launches per ping-pong iteration and rank); this makes it two.
+__global__ void __launch_bounds__(kWaitThreads) recv_wait_fused(RecvParams rp, WaitBatch b) {
+    pdl_prologue();
+    if (threadIdx.x == 0) recv_match(rp);
+    __syncthreads();
+    wait_body(b, b.w[0]);
 }
 
 // Copy-out of a bounced (private-destination) rendezvous receive at full width; the last CTA

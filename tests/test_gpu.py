@@ -287,3 +287,13 @@ def test_device_partitioned_api(built, np_):
     r = acxrun(built, np_, built / "build/tests/partitioned_device")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_blocking_send_recv_enqueue(built, np_):
+    """MPIX_Send_enqueue / MPIX_Recv_enqueue: eager receive as one fused post+wait kernel (2 launches per token-ring iteration,
+    asserted from the stats), larger payloads on the Isend/Irecv+Wait path, strided send, MPI_PROC_NULL, truncation, stream
+    capture relaunched 40 trips round the ring, explicit graphs — tests/c/sendrecv_enqueue.c."""
+    r = acxrun(built, np_, built / "build/tests/sendrecv_enqueue")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout

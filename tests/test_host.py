@@ -44,7 +44,7 @@ def test_minimpi_thread_multiple(built, np_):
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("prog", ["ring", "ring_all", "procnull_comms", "wildcards", "subcomm", "datatypes", "threads", "status_errors"])
+@pytest.mark.parametrize("prog", ["ring", "ring_all", "procnull_comms", "wildcards", "subcomm", "datatypes", "threads", "status_errors", "sendrecv_enqueue"])
 @pytest.mark.parametrize("np_", [1, 2, 3])
 def test_ring_host_transport(built, prog, np_):
     r = acxrun(built, np_, built / f"build/tests/{prog}", env={"ACX_FORCE_HOST": "1"})
@@ -115,6 +115,11 @@ untouched = torch.full((8,), 7.0)
 q = [acx.irecv(untouched, acx.PROC_NULL), acx.isend(untouched, acx.PROC_NULL)]
 acx.waitall_enqueue(q)
 assert bool((untouched == 7).all())
+# blocking-on-the-stream send / recv (MPIX_Send_enqueue / MPIX_Recv_enqueue)
+tok, got = torch.full((5,), float(r)), torch.zeros(5)
+acx.send(tok, right, tag=12)
+acx.recv(got, left, tag=12)
+assert bool((got == float(left)).all())
 acx.finalize()
 print("OK", r)
 """

@@ -16,7 +16,7 @@ run() {  # run <label> <np> <prog> [env...]
     if [ $rc -eq 0 ] && echo "$out" | grep -q "PASS"; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms
     else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $rc "$(echo "$out" | grep -v "ASan doesn\x27t fully support" | tail -${EMU_TAIL:-8})"; fails=$((fails+1)); fi
 }
-progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors"
+progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors sendrecv_enqueue"
 nps="1 2 3"
 [ "$mode" = full ] && nps="1 2 3 4"
 for p in $progs; do for np in $nps; do run default $np $p; done; done
@@ -27,7 +27,7 @@ run wildcards 3 wildcards ACX_WILDCARDS=1
 # (cooperative moving) the completion chain runs through the other process and looks like a missing release here, so
 # cooperative moving is TSan-checked at np=1 (and, across ranks, by `make emu-tsan`, where ranks are threads).
 coop_np=2; [ "$mode" = tsan ] && coop_np=1
-for p in ring ring_all ring_all_device graph_large large_msgs ordering stress status_errors; do
+for p in ring ring_all ring_all_device graph_large large_msgs ordering stress status_errors sendrecv_enqueue; do
     run coop $coop_np $p ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
     run peer-branch 3 $p ACX_PEER_BRANCH=1
     run sender-push 2 $p ACX_SENDER_PUSH=1

@@ -37,6 +37,11 @@ done
 for br in 0 1; do echo "ring branch=$br: $(ACX_PEER_BRANCH=$br ACX_HEAP_BYTES=1g run bin/p2p_bench ring --bytes 268435456 | tail -n 1)"; done
 for br in 0 1; do echo "pingpong branch=$br: $(ACX_PEER_BRANCH=$br timeout 120 ./bin/acxrun -np 2 --timeout 100 bin/p2p_bench pingpong 2>&1 | tail -n 1 | cut -c1-400)"; done
 
+echo "### 3'. MPIX_Send_enqueue / MPIX_Recv_enqueue (eager receive = one fused post+wait kernel: 2 launches per ping-pong iteration instead of 3)"
+for np in 1 $NP; do timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/sendrecv_enqueue 2>&1 | tail -n 2; done
+for bl in "" "--blocking"; do echo "pingpong $bl: $(timeout 120 ./bin/acxrun -np 2 --timeout 100 bin/p2p_bench pingpong --max 65536 $bl 2>&1 | tail -n 1 | cut -c1-500)"; done
+for bl in "" "--blocking"; do echo "pingpong_graph $bl: $(timeout 120 ./bin/acxrun -np 2 --timeout 100 bin/p2p_bench pingpong_graph --max 65536 $bl 2>&1 | tail -n 1 | cut -c1-500)"; done
+
 echo "### 3a. ACX_COOP=1 (cooperative moving with chunk stealing): conformance, then the ring in 'simple' order (no pre-posting) against the default"
 for t in large_msgs ring_all_device ring_all_graph ordering stress regcache; do ACX_COOP=1 run build/tests/$t 16777216 | tail -n 1; done
 for coop in 0 1; do echo "ring coop=$coop: $(ACX_COOP=$coop ACX_HEAP_BYTES=1g run bin/p2p_bench ring --bytes 268435456 | tail -n 1)"; done
