@@ -86,6 +86,7 @@ struct AcxRange {
 // Fault injection for tests (ACX_FAULT_DROP_SEND=n): the n-th send is never triggered, so the
 // matching receive can only end in the watchdog (failure-detection path).
 static long g_fault_drop_send = 0;
+static long g_fault_delay_us = 0;         // ACX_FAULT_DELAY_US=n: sleep a pseudo-random 0..n us on the host before every send / receive is enqueued (shakes arrival orders)
 static std::atomic<long> g_send_counter{0};
 
 static Watchdog make_wd() {
@@ -286,6 +287,23 @@ uint32_t acx_pflags_alloc(uint32_t n) {
 int acx_device_alias(const void *p, size_t bytes, char **out) {
     if (!p || bytes == 0) { *out = (char *)p; return 0; }
     if (acx_heap_offset_of(p) >= 0) { *out = (char *)p; return 0; }
+    {
+        // Host memory this library has already pinned (registrations are permanent): answered from the table, without the
+        // cudaPointerGetAttributes driver call — status words and small host buffers come through here on every operation.
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        const uintptr_t lo = (uintptr_t)p, hi = lo + bytes;
+        if (!g_acx->host_ptr_is_dev_ptr) {
+            for (auto &r : g_acx->host_regs) if (lo >= r.lo && hi <= r.hi) { *out = r.dptr + (lo - r.lo); return 0; }
+        } else {
+            uintptr_t cur = lo;
+            bool progress = true;
+            while (cur < hi && progress) {
+                progress = false;
+                for (auto &r : g_acx->host_regs) if (cur >= r.lo && cur < r.hi) { cur = r.hi; progress = true; break; }
+            }
+            if (cur >= hi) { *out = (char *)p; return 0; }
+        }
+    }
     cudaPointerAttributes a;
     cudaError_t e = cudaPointerGetAttributes(&a, p);
     if (e != cudaSuccess) { cudaGetLastError(); a.type = cudaMemoryTypeUnregistered; }
@@ -622,6 +640,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_FUSE_MAX_CTAS", nullptr, 32, &v); g_fuse_max_ctas = (int)v;
     acx_env_int("ACX_FUSE_MIN_CTAS", nullptr, 8, &v); g_fuse_min_ctas = (int)v;
     acx_env_int("ACX_FAULT_DROP_SEND", nullptr, 0, &v); g_fault_drop_send = v;
+    acx_env_int("ACX_FAULT_DELAY_US", nullptr, 0, &v); g_fault_delay_us = std::max(0L, v);
     acx_env_int("ACX_MOVER_MAX_CTAS", nullptr, 0, &v); g_acx->mover_max_ctas = (int)v;
     acx_env_int("ACX_MOVER_CTA_BYTES", nullptr, 64 << 10, &v); g_acx->mover_min_cta_bytes = (size_t)std::max(4096L, v);
     { int c0; if (acx_comm_ctx(MPI_COMM_WORLD, &c0)) return 1; }
@@ -1133,6 +1152,14 @@ static int launch_sender_push(Emitter &em, AcxRequest *r, SendParams &sp, MoverP
     return 0;
 }
 
+static void fault_delay() {
+    if (g_fault_delay_us <= 0) return;
+    static std::atomic<unsigned> seed{12345u};
+    unsigned x = seed.fetch_add(0x9e3779b9u) * 2654435761u + (unsigned)g_acx->rank * 40503u;
+    x ^= x >> 15;
+    usleep((useconds_t)(x % (unsigned)(g_fault_delay_us + 1)));
+}
+
 static inline int chan_of(int tag, int ctx) { return (int)(((unsigned)tag + 7u * (unsigned)ctx) % (unsigned)g_acx->geom.nchan); }
 
 static AcxRequest *new_request(AcxReqKind kind, int peer, int tag, int ctx, size_t bytes, const void *buf) {
@@ -1309,6 +1336,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         return MPI_SUCCESS;
     }
     if (dest == MPI_PROC_NULL) return make_null_op(r, qtype, queue, request);
+    fault_delay();
     dest = wdest;   // from here on: the world rank (windows, rings and side streams are indexed by it)
     Emitter em;
     BranchScope branch(em, r);
@@ -1423,6 +1451,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         return MPI_SUCCESS;
     }
     if (source == MPI_PROC_NULL) return make_null_op(r, qtype, queue, request);
+    fault_delay();
     source = wsource;   // world rank from here on
     Emitter em;
     BranchScope branch(em, r);

@@ -19,6 +19,9 @@ echo "### 1b. experimental device-side wildcards (ACX_WILDCARDS=1)"
 for np in 1 2 $NP; do ACX_WILDCARDS=1 timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/wildcards 2>&1 | tail -n 3; done
 timeout 60 ./bin/acxrun -np 2 --timeout 50 build/tests/wildcards 2>&1 | tail -n 1   # default: rejected cleanly
 
+echo "### 1c. arrival-order jitter (ACX_FAULT_DELAY_US=200): the second-arriver logic with both orders on hardware"
+for t in stress large_msgs ordering graph_large; do ACX_FAULT_DELAY_US=200 run build/tests/$t | tail -n 1; done
+
 echo "### 2. examples"
 make examples > /dev/null 2>&1
 for e in stream_ring partitioned_producer; do timeout 60 ./bin/acxrun -np $NP --timeout 50 build/examples/$e 2>&1 | tail -n $NP; done
