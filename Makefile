@@ -127,7 +127,7 @@ $(EMU)/minimpi.o: src/minimpi/minimpi.cpp include/mpi.h
 	@mkdir -p $(EMU)
 	$(CXX) $(CXXFLAGS) -g $(EMU_SAN) -c $< -o $@
 $(EMU)/libacx_emu.so: $(EMU)/acx.o $(EMU)/cudart_emu.o $(EMU)/minimpi.o
-	$(CXX) -shared $(EMU_SAN) -o $@ $^ -ldl -lpthread -lrt
+	$(CXX) -shared $(EMU_SAN) -Wl,-Bsymbolic-functions -o $@ $^ -ldl -lpthread -lrt   # own cuda* / MPI* definitions win even inside a process that also loaded the real libcudart (python + torch)
 $(EMU)/tests/%: tests/c/%.c $(EMU)/libacx_emu.so tests/c/acx_test.h
 	@mkdir -p $(EMU)/tests
 	gcc -O1 -g $(EMU_SAN) -Iinclude -I$(CUDA_HOME)/include $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU)

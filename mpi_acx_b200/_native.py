@@ -13,6 +13,10 @@ from pathlib import Path
 
 REPO = Path(__file__).resolve().parent.parent
 LIB_PATH = REPO / "lib" / "libacx.so"
+# CI without a GPU can point the binding at the software-device build (build/emu/libacx_emu.so, see tests/emu): the device
+# transport then runs on CPU tensors. Never set on a GPU box.
+if os.environ.get("ACX_LIB"):
+    LIB_PATH = Path(os.environ["ACX_LIB"]).resolve()
 
 MPI_COMM_WORLD = 1
 MPI_THREAD_MULTIPLE = 3

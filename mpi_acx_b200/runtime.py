@@ -68,6 +68,15 @@ def is_device_transport() -> bool:
     return bool(N.lib().MPIX_Is_device_transport())
 
 
+def synchronize() -> None:
+    """Wait for all enqueued work of this rank (torch.cuda.synchronize(); on the software device: its cudaDeviceSynchronize)."""
+    import torch
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    elif is_device_transport():
+        N.lib().cudaDeviceSynchronize()
+
+
 def barrier() -> None:
     N.lib().MPI_Barrier(N.MPI_COMM_WORLD)
 
@@ -109,7 +118,10 @@ def empty(shape: Sequence[int] | int, dtype=None):
     p = ctypes.c_void_p()
     _ck(N.lib().MPIX_Alloc_mem(nbytes, 0, ctypes.byref(p)), "MPIX_Alloc_mem")
     buf = _CudaBuffer(p.value, nbytes)
-    t = torch.as_tensor(buf, device="cuda")
+    if not torch.cuda.is_available():   # software device (ACX_LIB=...libacx_emu.so): "device" memory is host-addressable
+        t = torch.frombuffer((ctypes.c_ubyte * nbytes).from_address(p.value), dtype=torch.uint8)
+    else:
+        t = torch.as_tensor(buf, device="cuda")
     t = t[: numel * torch.empty((), dtype=dtype).element_size()].view(dtype).view(tuple(shape))
     t._acx_keepalive = buf  # tie heap block lifetime to the tensor
     return t

@@ -270,3 +270,14 @@ def test_device_trace_to_chrome_trace(built, tmp_path):
     assert kinds.get("X", 0) > 50 and kinds.get("i", 0) > 50 and kinds.get("s", 0) == kinds.get("f", 0) > 20, kinds
     assert {e["pid"] for e in ev} == {0, 1}
     assert any(e["ph"] == "X" and e["name"].startswith("move") and e["args"]["bytes"] > 8192 for e in ev)
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_python_binding_on_software_device(built, np_):
+    """mpi_acx_b200 loaded against build/emu/libacx_emu.so: the Python layer (strided views -> derived datatypes, heap tensors,
+    send / recv) drives the DEVICE transport on CPU tensors — tests/emu/python_on_software_device.py."""
+    subprocess.run(["make", "-C", str(built), "-j4", "emu-lib"], check=True, capture_output=True, timeout=900)
+    env = dict(os.environ, ACX_LIB=str(built / "build/emu/libacx_emu.so"), ACX_MPI_NO_CUDA="1", ACX_WATCHDOG_MS="30000")
+    cmd = [str(built / "bin/acxrun"), "-np", str(np_), "--timeout", "200", sys.executable, str(built / "tests/emu/python_on_software_device.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.count("PY-EMU OK") == np_, r.stdout[-2000:] + r.stderr[-2000:]
