@@ -33,5 +33,33 @@ for numel in (5, 3000, 200000):
         acx.recv(d, left, 3); acx.send(s, right, 3)
     acx.synchronize()
     assert torch.equal(d, torch.arange(numel, dtype=torch.float32) + left), numel
+# parallel/: pre-posted double-buffered ring (what bench.py runs from 3 GPUs up), all-pairs exchange, partitioned pipeline link
+from mpi_acx_b200.parallel import ring as pring
+from mpi_acx_b200.parallel.pipeline import PartitionedLink
+sbuf, rbufs = acx.empty(50000, torch.int32), [acx.empty(50000, torch.int32), acx.empty(50000, torch.int32)]
+seen = []
+def before(i): sbuf.fill_(1000 * r + i)
+def after(i, buf): acx.synchronize(); seen.append(int(buf[0]) == 1000 * left + i and int(buf[-1]) == 1000 * left + i)
+pring.ring_exchange_prepost(sbuf, rbufs, steps=6, tag=5, before_send=lambda i: (acx.synchronize(), before(i)), after_recv=after)
+acx.synchronize()
+assert seen == [True] * 6, seen
+chunks_s = [torch.full((3000,), 100 * r + k, dtype=torch.int32) for k in range(n)]
+chunks_r = [torch.zeros(3000, dtype=torch.int32) for _ in range(n)]
+pring.allpairs_exchange(chunks_s, chunks_r, tag=6)
+acx.synchronize()
+for k in range(n):
+    assert int(chunks_r[k][0]) == 100 * ((r - 1 - k) % n) + k, (k, int(chunks_r[k][0]))
+if n > 1:   # activations flow rank 0 -> 1 -> ... over persistent partitioned channels, host-driven rounds
+    act_in, act_out = acx.empty(4 * 256, torch.float32), acx.empty(4 * 256, torch.float32)
+    link = PartitionedLink(send_buf=act_out, recv_buf=act_in, partitions=4, tag=7)
+    for rnd in range(3):
+        act_out.fill_(float(10 * r + rnd)); act_in.zero_()
+        link.start()
+        if link.send is not None:
+            for p_ in range(4): link.send.pready(p_)
+        link.wait()
+        if r > 0:
+            assert bool((act_in == float(10 * (r - 1) + rnd)).all()), rnd
+    link.free()
 print("PY-EMU OK", r, acx.stats()["kernels_launched"])
 acx.finalize()

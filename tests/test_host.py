@@ -272,7 +272,7 @@ def test_device_trace_to_chrome_trace(built, tmp_path):
     assert any(e["ph"] == "X" and e["name"].startswith("move") and e["args"]["bytes"] > 8192 for e in ev)
 
 
-@pytest.mark.parametrize("np_", [1, 2])
+@pytest.mark.parametrize("np_", [1, 3])
 def test_python_binding_on_software_device(built, np_):
     """mpi_acx_b200 loaded against build/emu/libacx_emu.so: the Python layer (strided views -> derived datatypes, heap tensors,
     send / recv) drives the DEVICE transport on CPU tensors — tests/emu/python_on_software_device.py."""
