@@ -116,7 +116,7 @@ emu-tsan:
 
 EMU_CTESTS := $(patsubst tests/c/%.c,$(EMU)/tests/%,$(wildcard tests/c/*.c)) $(EMU)/tests/ring_partitioned $(EMU)/tests/partitioned_device
 emu-lib: $(EMU)/libacx_emu.so
-emu-tests: $(EMU_CTESTS)
+emu-tests: $(EMU_CTESTS) $(EMU)/p2p_bench
 $(EMU)/acx.o: src/core/acx.cu src/core/internal.h src/core/kernels.cuh include/mpi-acx.h include/acx_device.cuh include/mpi.h tests/emu/cuda_emu.h
 	@mkdir -p $(EMU)
 	$(CXX) -O1 -fPIC $(EMU_FLAGS) $(EMU_SAN) -x c++ -include tests/emu/cuda_emu.h -c $< -o $@
@@ -131,6 +131,8 @@ $(EMU)/libacx_emu.so: $(EMU)/acx.o $(EMU)/cudart_emu.o $(EMU)/minimpi.o
 $(EMU)/tests/%: tests/c/%.c $(EMU)/libacx_emu.so tests/c/acx_test.h
 	@mkdir -p $(EMU)/tests
 	gcc -O1 -g $(EMU_SAN) -Iinclude -I$(CUDA_HOME)/include $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU)
+$(EMU)/p2p_bench: bench/p2p_bench.cu $(EMU)/libacx_emu.so tests/emu/cuda_emu.h
+	$(CXX) -O1 $(EMU_FLAGS) $(EMU_SAN) -x c++ -include tests/emu/cuda_emu.h $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) -lpthread
 $(EMU)/tests/%: tests/c/%.cu $(EMU)/libacx_emu.so tests/c/acx_test.h tests/emu/cuda_emu.h
 	@mkdir -p $(EMU)/tests
 	$(CXX) -O1 $(EMU_FLAGS) $(EMU_SAN) -x c++ -include tests/emu/cuda_emu.h $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) -lpthread

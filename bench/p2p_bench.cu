@@ -19,6 +19,13 @@
 #define OK(x) do { int r_ = (x); if (r_) { fprintf(stderr, "[%d] %s:%d %s -> %d\n", g_rank, __FILE__, __LINE__, #x, r_); MPI_Abort(MPI_COMM_WORLD, 6); } } while (0)
 
 static int g_rank, g_size;
+// kernel<<<grid, block, 0, stream>>>(...); on the software CUDA device (tests/emu) kernels are plain functions and the
+// grid-stride helpers below run with a small geometry
+#ifdef ACX_EMU
+#define LAUNCH(kern, grid, block, stream, ...) CK(emu::launch_user(kern, (grid) > 4 ? 4 : (grid), (block) > 8 ? 8 : (block), stream, __VA_ARGS__))
+#else
+#define LAUNCH(kern, grid, block, stream, ...) kern<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#endif
 #ifdef ACX_BENCH_REFERENCE
 static const char *kImpl = "reference";
 #else
@@ -66,7 +73,7 @@ static int run_ring(size_t bytes, int steps, int warmup, bool heap, bool e2e, bo
     char *h_in = nullptr, *h_out = nullptr;
     const size_t d2h = 4096 < bytes ? 4096 : bytes;
     if (e2e) { CK(cudaMallocHost((void **)&h_in, bytes)); CK(cudaMallocHost((void **)&h_out, d2h)); memset(h_in, g_rank + 1, bytes); }
-    fill_kernel<<<592, 256, 0, st>>>((unsigned *)sbuf, bytes / 4, 77u * g_rank);
+    LAUNCH(fill_kernel, 592, 256, st, (unsigned *)sbuf, bytes / 4, 77u * g_rank);
     CK(cudaMemsetAsync(rbuf, 0, bytes, st));
     CK(cudaStreamSynchronize(st));
     int right = (g_rank + 1) % g_size, left = (g_rank + g_size - 1) % g_size;
@@ -101,7 +108,7 @@ static int run_ring(size_t bytes, int steps, int warmup, bool heap, bool e2e, bo
     if (verify && !e2e) {
         unsigned long long *dbad;
         CK(cudaMalloc(&dbad, 8)); CK(cudaMemset(dbad, 0, 8));
-        check_kernel<<<592, 256, 0, st>>>((const unsigned *)((prepost && ((warmup - 1) & 1)) ? rbuf2 : rbuf), bytes / 4, 77u * left, dbad);
+        LAUNCH(check_kernel, 592, 256, st, (const unsigned *)((prepost && ((warmup - 1) & 1)) ? rbuf2 : rbuf), bytes / 4, 77u * left, dbad);
         CK(cudaMemcpyAsync(&bad, dbad, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         cudaFree(dbad);

@@ -59,6 +59,32 @@ if [ "$mode" = full ]; then
     run wide-blocks 2 large_msgs ACX_EMU_MAX_BLOCK=64
     run many-sms 2 large_msgs ACX_EMU_SMS=16
 fi
+# the benchmark driver itself (bench/p2p_bench.cu built for the software device): every mode and option on small sizes;
+# timings mean nothing here, the payload check (bad_words) and the control flow do
+bench() {  # bench <np> <args...>
+    local np=$1; shift
+    out=$(ACX_HEAP_BYTES=64m timeout 400 bin/acxrun -np $np --timeout 300 ${EMU_DIR:-build/emu}/p2p_bench "$@" 2>&1); rc=$?
+    if echo "$out" | grep -qE "runtime error:|ERROR: AddressSanitizer|WARNING: ThreadSanitizer"; then rc=99; fi
+    if [ $rc -eq 0 ] && echo "$out" | tail -1 | grep -q '"bench"' && ! echo "$out" | grep -q '"bad_words": [1-9]'; then printf "ok    %-24s np=%d %s\n" p2p_bench $np "$*"
+    else printf "FAIL  p2p_bench np=%d %s rc=%d\n%s\n" $np "$*" $rc "$(echo "$out" | tail -5)"; fails=$((fails+1)); fi
+}
+if [ -x ${EMU_DIR:-build/emu}/p2p_bench ]; then
+    bench 2 ring --bytes 1048576 --steps 3 --warmup 3
+    bench 3 ring --bytes 300000 --steps 3 --warmup 3 --prepost
+    bench 2 pingpong --max 131072 --iters 6 --blocking
+    bench 3 allpairs --bytes 100000 --steps 3 --warmup 2
+    if [ "$mode" = full ]; then
+        bench 2 ring --bytes 262144 --steps 3 --warmup 3 --e2e
+        bench 3 ring --bytes 200000 --steps 3 --warmup 3 --no-heap
+        bench 2 pingpong --max 131072 --iters 6
+        bench 2 pingpong_graph --max 65536 --iters 4
+        bench 2 pingpong_graph --max 65536 --iters 4 --blocking
+        bench 4 allpairs --bytes 100000 --steps 3 --warmup 2
+        ACX_PEER_BRANCH=1 bench 4 allpairs --bytes 100000 --steps 3 --warmup 2
+        ACX_COOP=1 ACX_COOP_MIN_BYTES=65536 bench 3 ring --bytes 1048576 --steps 3 --warmup 3
+    fi
+fi
+
 # failure detection: a dropped send must end in the device watchdog (trap -> sticky launch failure -> diagnostic), not in a hang
 out=$(ACX_FAULT_DROP_SEND=1 ACX_WATCHDOG_MS=1500 timeout 100 bin/acxrun -np 1 --timeout 60 $T/ring 2>&1); rc=$?
 if [ $rc -ne 0 ] && echo "$out" | grep -q "WATCHDOG (code 0x5e04" && echo "$out" | grep -q "FAULT INJECTION"; then printf "ok    %-24s np=1 %-28s\n" ring watchdog-on-dropped-send
