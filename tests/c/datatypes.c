@@ -75,8 +75,56 @@ static void faces(int n, int use_heap, int host_wait, MPI_Datatype elem, int tag
     free(h);
 }
 
+/* Column blocks of a row-major matrix with element sizes 1, 2, 8 and 16 bytes: the pack / unpack kernels move the widest
+ * unit that divides the run, the strides and both addresses (1-, 2-, 4-, 8- and 16-byte units). `esize` bytes per element,
+ * `w` elements per row segment; strided send into a contiguous receive and back into a strided one. */
+static void columns(int esize, int w, int rows, int pitch_elems, int tag) {
+    const size_t pitch = (size_t)pitch_elems * esize, seg = (size_t)w * esize, total = pitch * rows;
+    unsigned char *h = (unsigned char *)malloc(total), *m, *packed, *back;
+    T_OK(MPIX_Alloc_mem(total, MPI_INFO_NULL, &m));
+    T_OK(MPIX_Alloc_mem(seg * rows, MPI_INFO_NULL, &packed));
+    T_OK(MPIX_Alloc_mem(total, MPI_INFO_NULL, &back));
+    MPI_Datatype elem, block;
+    MPI_Type_contiguous(esize, MPI_BYTE, &elem);
+    MPI_Type_vector(rows, w, pitch_elems, elem, &block);
+    MPI_Type_commit(&block);
+    for (size_t i = 0; i < total; i++) h[i] = (unsigned char)(i * 5 + t_rank * 3 + esize);
+    put(m, h, total);
+    memset(h, 0xee, total);
+    put(back, h, total);
+    const size_t off = (size_t)2 * esize;   /* the block starts at column 2 */
+    cudaStream_t stream = 0;
+    MPIX_Request rq[4];
+    T_OK(MPIX_Irecv_enqueue(packed, (int)(seg * rows), MPI_BYTE, T_LEFT, tag, MPI_COMM_WORLD, &rq[0], MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_OK(MPIX_Isend_enqueue(m + off, 1, block, T_RIGHT, tag, MPI_COMM_WORLD, &rq[1], MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_OK(MPIX_Waitall_enqueue(2, rq, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &stream));
+    /* and back: the dense image goes out again and is scattered into a strided block on the other side */
+    T_OK(MPIX_Irecv_enqueue(back + off, 1, block, T_RIGHT, tag + 1, MPI_COMM_WORLD, &rq[2], MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_OK(MPIX_Isend_enqueue(packed, (int)(seg * rows), MPI_BYTE, T_LEFT, tag + 1, MPI_COMM_WORLD, &rq[3], MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_OK(MPIX_Waitall_enqueue(2, rq + 2, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &stream));
+    if (t_gpu) T_CUDA(cudaStreamSynchronize(stream));
+    put(h, back, total);
+    /* my block travelled right and came back: inside the block my own data, outside untouched */
+    size_t bad = 0;
+    for (int r = 0; r < rows; r++) for (size_t b = 0; b < pitch; b++) {
+        const size_t i = (size_t)r * pitch + b;
+        const int inside = b >= off && b < off + seg;
+        const unsigned char want = inside ? (unsigned char)(i * 5 + t_rank * 3 + esize) : 0xee;
+        if (h[i] != want) bad++;
+    }
+    T_CHECK(bad == 0, "column block, %d-byte elements x %d: %zu wrong bytes", esize, w, bad);
+    MPI_Type_free(&block); MPI_Type_free(&elem);
+    T_OK(MPIX_Free_mem(m)); T_OK(MPIX_Free_mem(packed)); T_OK(MPIX_Free_mem(back));
+    free(h);
+}
+
 int main(int argc, char **argv) {
     t_init(&argc, &argv, 0);
+    columns(1, 3, 40, 11, 140);        /* 3-byte runs at odd offsets: byte units */
+    columns(2, 5, 40, 16, 142);        /* 10-byte runs: 2-byte units */
+    columns(8, 3, 30, 9, 144);         /* 24-byte runs: 8-byte units */
+    columns(16, 4, 300, 10, 146);      /* 64-byte runs: 16-byte units; 19 KB: rendezvous */
+    columns(4, 7, 20, 33, 148);        /* 28-byte runs: 4-byte units */
     faces(8, 0, 0, MPI_INT, 100);      /* eager faces (256 B), host arrays, stream waits */
     faces(8, 0, 1, MPI_INT, 110);      /* same, host waits */
     faces(64, 1, 0, MPI_FLOAT, 120);   /* rendezvous faces (16 KiB), heap arrays, stream waits (MPI_FLOAT: same size as int, payload is opaque) */

@@ -177,8 +177,36 @@ static void explicit_epoch_rounds(void) {
     T_CUDA(cudaFree(d_bad));
 }
 
+// ---- 5. peer pointers: a user kernel stores into a neighbour's symmetric-heap object directly (cf. nvshmem_ptr) ----------------
+__global__ void put_to_peer(int *peer_buf, int rank, int n) { for (int i = threadIdx.x; i < n; i += blockDim.x) peer_buf[i] = rank * 100000 + i; }
+static void peer_pointers(void) {
+    enum { N = 5000 };
+    static int h[N];
+    int *mine, *at_right = NULL, *again = NULL;
+    size_t off = 0;
+    T_OK(MPIX_Alloc_mem(N * sizeof(int), MPI_INFO_NULL, &mine));   /* same allocation sequence on every rank: same heap offset */
+    T_CUDA(cudaMemset(mine, 0, N * sizeof(int)));
+    MPI_Barrier(MPI_COMM_WORLD);
+    T_OK(MPIX_Peer_ptr(mine, T_RIGHT, (void **)&at_right));
+    T_OK(MPIX_Heap_offset(mine, &off));
+    T_OK(MPIX_Peer_ptr_at(off, T_RIGHT, (void **)&again));
+    T_CHECK(at_right == again && (t_size > 1 || at_right == mine), "peer pointer %p vs %p (mine %p)", (void *)at_right, (void *)again, (void *)mine);
+    int dummy;
+    T_CHECK(MPIX_Peer_ptr(&dummy, T_RIGHT, (void **)&again) == MPI_ERR_BUFFER, "a pointer outside the heap must be refused");
+    T_LAUNCH(put_to_peer, 1, 64, at_right, t_rank, (int)N);
+    T_CUDA(cudaStreamSynchronize(0));
+    MPI_Barrier(MPI_COMM_WORLD);   /* every rank's stores have been performed (kernel completion + barrier) */
+    T_CUDA(cudaMemcpy(h, mine, sizeof h, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for (int i = 0; i < N; i++) if (h[i] != T_LEFT * 100000 + i) bad++;
+    T_CHECK(bad == 0, "stores through MPIX_Peer_ptr: %d wrong values", bad);
+    MPI_Barrier(MPI_COMM_WORLD);
+    T_OK(MPIX_Free_mem(mine));
+}
+
 int main(int argc, char **argv) {
     t_init(&argc, &argv, 1);
+    peer_pointers();
     zero_copy_rounds();
     cooperative_rounds(0, 1);
     cooperative_rounds(1, 1);

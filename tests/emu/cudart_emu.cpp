@@ -373,7 +373,7 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
 cudaError_t cudaDeviceGetAttribute(int *v, enum cudaDeviceAttr a, int) {
     switch (a) {
         case cudaDevAttrMultiProcessorCount: *v = (int)env_long("ACX_EMU_SMS", 4); break;
-        case cudaDevAttrCanUseHostPointerForRegisteredMem: *v = 1; break;
+        case cudaDevAttrCanUseHostPointerForRegisteredMem: *v = env_long("ACX_EMU_NO_HOSTREG_UVA", 0) ? 0 : 1; break;   // 0: exercise the runtime's path for devices whose registered host memory has a separate device alias
         case cudaDevAttrPageableMemoryAccess: *v = 0; break;
         case cudaDevAttrComputeCapabilityMajor: *v = 10; break;
         case cudaDevAttrComputeCapabilityMinor: *v = 0; break;

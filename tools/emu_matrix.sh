@@ -55,6 +55,9 @@ if [ "$mode" = full ]; then
     run depth2-chan1 3 stress ACX_DEPTH=2 ACX_NCHAN=1
     for p in stress large_msgs graph_large ordering; do run delay-jitter 3 $p ACX_FAULT_DELAY_US=300; done
     run delay-jitter-coop 2 stress ACX_FAULT_DELAY_US=300 ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
+    for p in ring ring_all status_errors; do run no-hostreg-uva 2 $p ACX_EMU_NO_HOSTREG_UVA=1; done
+    run tiny-slots 2 stress ACX_NFLAGS=8
+    run tiny-slots 2 threads ACX_NFLAGS=8
     run trace 2 ring ACX_TRACE=1 ACX_TRACE_DIR=/tmp
     run wide-blocks 2 large_msgs ACX_EMU_MAX_BLOCK=64
     run many-sms 2 large_msgs ACX_EMU_SMS=16
