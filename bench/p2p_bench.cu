@@ -131,6 +131,7 @@ static int run_ring(size_t bytes, int steps, int warmup, bool heap, bool e2e, bo
                e2e ? bytes : (size_t)0, e2e ? d2h : (size_t)0);
     comm_free(sbuf, heap); comm_free(rbuf, heap);
     if (e2e) { cudaFreeHost(h_in); cudaFreeHost(h_out); }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaStreamDestroy(st);
     return badmax != 0;
 }
@@ -207,6 +208,7 @@ static int run_pingpong_graph(size_t min_b, size_t max_b, bool heap, int launche
     }
     if (g_rank == 0) printf("]}\n");
     comm_free(sbuf, heap); comm_free(rbuf, heap);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaStreamDestroy(st);
     return 0;
 }
@@ -249,6 +251,7 @@ static int run_pingpong(size_t min_b, size_t max_b, bool heap, int max_iters) {
     }
     if (g_rank == 0) printf("]}\n");
     comm_free(sbuf, heap); comm_free(rbuf, heap);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaStreamDestroy(st);
     return 0;
 }
@@ -292,6 +295,7 @@ static int run_allpairs(size_t bytes, int steps, int warmup, bool heap) {
     CK(cudaGraphExecDestroy(exec));
     CK(cudaGraphDestroy(graph));
     comm_free(sbuf, heap); comm_free(rbuf, heap);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaStreamDestroy(st);
     return 0;
 }

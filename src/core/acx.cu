@@ -1436,6 +1436,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
                                   void *queue) {
     AcxRange _r("MPIX_Irecv_enqueue");
     size_t bytes; int ctx, wsource;
+    bool counted = false;   // this receive has been added to recv_outstanding (undone on the error exits)
     AcxLayout ty;
     int rc = check_common("MPIX_Irecv_enqueue", true, count, datatype, source, tag, comm, request, queue, &bytes, &ctx, &wsource, &ty);
     if (rc) return rc;
@@ -1482,8 +1483,13 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
             return MPI_ERR_OTHER;
         }
         g_acx->recv_outstanding[source][r->chan]++;
+        counted = true;
     }
-    if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
+    if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) {
+        if (counted) { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); g_acx->recv_outstanding[source][r->chan]--; }
+        delete r;
+        return MPI_ERR_OTHER;
+    }
     if ((rc = acx_device_alias(buf, ty.noncontig ? (size_t)ty.span : bytes, &r->dev_buf))) goto fail;
     if ((rc = branch.begin())) goto fail;
     {
@@ -1548,7 +1554,11 @@ done:
     return MPI_SUCCESS;
 fail:
     if (qtype == MPIX_QUEUE_CUDA_GRAPH && em.graph) cudaGraphDestroy(em.graph);
-    { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); acx_slot_free(r->slot); }
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        if (counted) g_acx->recv_outstanding[r->peer][r->chan]--;   // the rejected receive does not occupy a ring slot
+        acx_slot_free(r->slot);
+    }
     return rc;
 }
 
