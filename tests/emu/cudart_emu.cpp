@@ -11,7 +11,7 @@
 //                   per CUDA thread; library kernels are blockDim-agnostic and run with small blocks (ACX_EMU_MAX_BLOCK)
 //   graphs          explicit construction, stream capture incl. cross-stream fork/join through events (with the
 //                   "unjoined work" check CUDA applies at cudaStreamEndCapture), child graphs, user objects with
-//                   reference counts, instantiate = clone, launch = nodes in topological (insertion) order
+//                   reference counts, instantiate = clone, launch = dataflow execution (independent branches run concurrently)
 //   errors          a device __trap() is sticky: every later synchronizing call returns cudaErrorLaunchFailure
 #include "cuda_emu.h"
 
@@ -139,18 +139,51 @@ Graph *clone_graph(const Graph *g) {
     for (auto &u : g->uobjs) { u.first->refs.fetch_add(u.second); c->uobjs.push_back(u); }
     return c;
 }
-void run_graph(const Graph *g) {
-    for (const Node *n : g->nodes) {
-        if (emu::g_trapped.load()) return;
-        switch (n->type) {
-            case kNodeKernel: n->kl.run(); break;
-            case kNodeChild: run_graph(n->child); break;
-            case kNodeMemcpy: memmove(n->dst, n->src, n->bytes); break;
-            case kNodeMemset: memset(n->dst, n->value, n->bytes); break;
-            case kNodeHost: n->fn(n->fn_arg); break;
-            case kNodeEmpty: break;
-        }
+void run_graph(const Graph *g);
+void run_node(const Node *n) {
+    if (emu::g_trapped.load()) return;
+    switch (n->type) {
+        case kNodeKernel: n->kl.run(); break;
+        case kNodeChild: run_graph(n->child); break;
+        case kNodeMemcpy: memmove(n->dst, n->src, n->bytes); break;
+        case kNodeMemset: memset(n->dst, n->value, n->bytes); break;
+        case kNodeHost: n->fn(n->fn_arg); break;
+        case kNodeEmpty: break;
     }
+}
+// Dataflow execution, like the hardware: a node starts as soon as its own dependencies have finished, so independent
+// branches of a graph (a captured side-stream mover next to the main chain, the send / receive children of an explicit
+// graph) really run concurrently — and ThreadSanitizer checks that every ordering the library relies on is an edge.
+// A linear chain (the common case) runs inline; ACX_EMU_GRAPH_SERIAL=1 forces insertion order for debugging.
+void run_graph(const Graph *g) {
+    const size_t n = g->nodes.size();
+    bool chain = true;
+    for (size_t i = 0; i < n && chain; i++) {
+        const Node *x = g->nodes[i];
+        if (i == 0 ? !x->deps.empty() : !(x->deps.size() == 1 && x->deps[0] == g->nodes[i - 1])) chain = false;
+    }
+    static const bool serial = env_long("ACX_EMU_GRAPH_SERIAL", 0) != 0;
+    if (chain || serial || n < 2) { for (const Node *x : g->nodes) run_node(x); return; }
+    std::unordered_map<const Node *, size_t> index;
+    for (size_t i = 0; i < n; i++) index[g->nodes[i]] = i;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> done(n, 0);
+    std::vector<std::thread> workers;
+    workers.reserve(n);
+    for (size_t i = 0; i < n; i++) {
+        workers.emplace_back([&, i] {
+            const Node *x = g->nodes[i];
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { for (const Node *d : x->deps) if (!done[index.at(d)]) return false; return true; });
+            }
+            run_node(x);
+            { std::lock_guard<std::mutex> lk(mu); done[i] = 1; }
+            cv.notify_all();
+        });
+    }
+    for (auto &w : workers) w.join();
 }
 std::mutex g_graph_mu;                 // graph construction is host-side and rare: one lock
 std::set<Graph *> g_graphs;            // live handles (validation)
