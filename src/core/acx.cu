@@ -1697,6 +1697,29 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             need.push_back({r, st});
         }
     }
+    // Wildcard receives: resolve + match (+ pull) kernel, then a single-entry wait that reads the resolution. They go FIRST:
+    // a wildcard receive is only posted by its resolver, and a cooperative gate of one of this rank's sends (below) spins until
+    // the peer's receive is posted — with every rank's resolver behind its own gates a ring of such exchanges never starts
+    // (found on the software device: wildcards.c with ACX_COOP=1).
+    {
+        std::vector<Item> plain;
+        for (const Item &it : need) {
+            if (!it.r->wild) { plain.push_back(it); continue; }
+            const bool par = em.parallel;
+            em.parallel = false;   // the wait node must follow the resolver node
+            AnyParams ap;
+            fill_any(it.r, &ap);
+            rc = em.launch(recv_any_kernel, dim3(any_grid(it.r)), dim3(kMoverThreads), ap);
+            WaitBatch wb;
+            memset(&wb, 0, sizeof wb);
+            if (!rc) rc = fill_wait(it.r, it.st, retire, false, &wb.w[0]);
+            wb.wd = make_wd(); wb.tr = make_tr();
+            if (!rc) rc = em.launch(wait_kernel, dim3(1), dim3(kWaitThreads), wb);
+            em.parallel = par;
+            if (rc) return rc;
+        }
+        need.swap(plain);
+    }
     // Cooperative moving: each large rendezvous request gets an agent kernel in front of the waits, so this GPU copies its
     // share of the message even when it arrived first (ACX_COOP).
     for (const Item &it : need) {
@@ -1724,26 +1747,6 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
         if (!rc) rc = em.launch(coop_kernel, dim3(mover_grid_ldst(r->bytes)), dim3(kMoverThreads), cp);
         em.parallel = par;
         if (rc) return rc;
-    }
-    // Wildcard receives: resolve + match (+ pull) kernel, then a single-entry wait that reads the resolution.
-    {
-        std::vector<Item> plain;
-        for (const Item &it : need) {
-            if (!it.r->wild) { plain.push_back(it); continue; }
-            const bool par = em.parallel;
-            em.parallel = false;   // the wait node must follow the resolver node
-            AnyParams ap;
-            fill_any(it.r, &ap);
-            rc = em.launch(recv_any_kernel, dim3(any_grid(it.r)), dim3(kMoverThreads), ap);
-            WaitBatch wb;
-            memset(&wb, 0, sizeof wb);
-            if (!rc) rc = fill_wait(it.r, it.st, retire, false, &wb.w[0]);
-            wb.wd = make_wd(); wb.tr = make_tr();
-            if (!rc) rc = em.launch(wait_kernel, dim3(1), dim3(kWaitThreads), wb);
-            em.parallel = par;
-            if (rc) return rc;
-        }
-        need.swap(plain);
     }
     for (size_t base = 0; base < need.size(); base += kWaitBatch) {
         WaitBatch wb;

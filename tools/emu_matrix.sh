@@ -22,6 +22,12 @@ nps="1 2 3"
 for p in $progs; do for np in $nps; do run default $np $p; done; done
 run default 2 stress; run default 3 stress
 run wildcards 3 wildcards ACX_WILDCARDS=1
+run wildcards 2 wildcards ACX_WILDCARDS=1
+run wildcards 4 wildcards ACX_WILDCARDS=1
+run wildcards-coop 3 wildcards ACX_WILDCARDS=1 ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
+run wildcards-jitter 3 wildcards ACX_WILDCARDS=1 ACX_FAULT_DELAY_US=200
+run wildcards-push 3 wildcards ACX_WILDCARDS=1 ACX_SENDER_PUSH=1
+run wildcards-branch 3 wildcards ACX_WILDCARDS=1 ACX_PEER_BRANCH=1
 # opt-in modes written after the GPU budget was spent
 # ThreadSanitizer builds (EMU_DIR=build/emu_tsan, mode tsan) see one process: when agents of BOTH ranks copy one message
 # (cooperative moving) the completion chain runs through the other process and looks like a missing release here, so
