@@ -1160,6 +1160,17 @@ static void fault_delay() {
     usleep((useconds_t)(x % (unsigned)(g_fault_delay_us + 1)));
 }
 
+// End-of-operation marker for stream-mode operations whose mover (or fused trigger+mover kernel) runs on the CALLER's
+// stream: an event behind the operation's last kernel. A host MPIX_Wait completes on a different (internal) stream as
+// soon as the data is in place — possibly while that kernel's tail still touches the op record (the fused kernels'
+// last CTA re-arms the gate; a first-arriver's mover has not even started) — so the slot may only be released once
+// this event has completed, exactly like the side branches' ev_done. Stream waits sit behind the kernel anyway.
+static void mark_operation_end(Emitter &em, AcxRequest *r) {
+    if (em.in_graph() || r->ev_done) return;
+    r->ev_done = event_get();
+    if (r->ev_done && cudaEventRecord(r->ev_done, em.stream) != cudaSuccess) { cudaGetLastError(); g_event_pool.push_back(r->ev_done); r->ev_done = nullptr; }
+}
+
 static inline int chan_of(int tag, int ctx) { return (int)(((unsigned)tag + 7u * (unsigned)ctx) % (unsigned)g_acx->geom.nchan); }
 
 static AcxRequest *new_request(AcxReqKind kind, int peer, int tag, int ctx, size_t bytes, const void *buf) {
@@ -1411,6 +1422,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         if (!eager) {
             if (apush) { if (!dropped && (rc = launch_sender_push(em, r, sp, mp, bytes))) goto fail; }
             else if (!fused && (rc = launch_mover_maybe_side(em, r, mp, bytes))) goto fail;
+            mark_operation_end(em, r);   // no-op when a side branch already carries the event
             g_acx->st.rndv++;
         } else {
             g_acx->st.eager++;
@@ -1541,6 +1553,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
             if ((rc = em.launch(recv_trigger, dim3(1), dim3(32), rp))) goto fail;
             if (rndv_capable && (rc = launch_mover_maybe_side(em, r, mp, bytes))) goto fail;
         }
+        if (rndv_capable) mark_operation_end(em, r);
     }
     if ((rc = branch.end())) goto fail;
 done:

@@ -33,10 +33,11 @@ run wildcards-branch 3 wildcards ACX_WILDCARDS=1 ACX_PEER_BRANCH=1
 # (cooperative moving) the completion chain runs through the other process and looks like a missing release here, so
 # cooperative moving is TSan-checked at np=1 (and, across ranks, by `make emu-tsan`, where ranks are threads).
 coop_np=2; [ "$mode" = tsan ] && coop_np=1
-for p in ring ring_all ring_all_device graph_large large_msgs ordering stress status_errors sendrecv_enqueue; do
+push_np=2; [ "$mode" = tsan ] && push_np=1   # same for sender-push with recycled heap buffers: the order between two pushes into one address runs through the receiver's process
+for p in ring ring_all ring_all_device graph_large large_msgs ordering stress status_errors sendrecv_enqueue threads; do
     run coop $coop_np $p ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
     run peer-branch 3 $p ACX_PEER_BRANCH=1
-    run sender-push 2 $p ACX_SENDER_PUSH=1
+    run sender-push $push_np $p ACX_SENDER_PUSH=1
 done
 [ "$mode" = tsan ] || run coop 3 large_msgs ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
 run pbatch 2 ring_partitioned ACX_PBATCH=1
@@ -47,12 +48,13 @@ run memops 4 subcomm ACX_MEMOPS=1
 run memops 2 partitioned_device ACX_MEMOPS=1
 run pbatch 3 partitioned_device ACX_PBATCH=1
 if [ "$mode" = full ]; then
-    for p in ring_all large_msgs stress ordering graph_large status_errors; do
+    run coop-no-side-streams 3 threads ACX_COOP=1 ACX_COOP_MIN_BYTES=65536 ACX_SIDE_STREAMS=0
+    for p in ring_all large_msgs stress ordering graph_large status_errors threads; do
         run no-fuse 2 $p ACX_FUSE_RNDV=0
         run no-side-streams 2 $p ACX_SIDE_STREAMS=0
         run ldst256 2 $p ACX_MOVER=ldst256
         run mover-block 2 $p ACX_MOVER_BLOCK=4096
-        run depth8-chan2 2 $p ACX_DEPTH=8 ACX_NCHAN=2
+        [ $p = threads ] || run depth8-chan2 2 $p ACX_DEPTH=8 ACX_NCHAN=2   # threads.c needs one channel per thread (tags that collide modulo ACX_NCHAN share a FIFO)
         run eager64 3 $p ACX_EAGER_MAX=64
         run no-regcache 2 $p ACX_REGCACHE=0
         run fuse-any-grid 2 $p ACX_FUSE_MIN_CTAS=1 ACX_EMU_SMS=16
