@@ -1353,6 +1353,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
     BranchScope branch(em, r);
     if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
     r->in_graph = em.in_graph();
+    r->stream = qtype == MPIX_QUEUE_CUDA_STREAM ? em.stream : nullptr;
     r->chan = chan_of(tag, ctx);
     if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
     if ((rc = acx_device_alias(buf, ty.noncontig ? (size_t)ty.span : bytes, &r->dev_buf))) goto fail;
@@ -1470,6 +1471,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
     BranchScope branch(em, r);
     if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
     r->in_graph = em.in_graph();
+    r->stream = qtype == MPIX_QUEUE_CUDA_STREAM ? em.stream : nullptr;
     if (source == MPI_ANY_SOURCE || tag == MPI_ANY_TAG) {
         // Wildcard: nothing is launched now; the wait resolves, matches and (for a rendezvous message) pulls.
         if (ty.noncontig) { ACX_ERR("wildcard receives with non-contiguous datatypes are not supported on the device transport"); if (qtype == MPIX_QUEUE_CUDA_GRAPH) cudaGraphDestroy(em.graph); delete r; return MPI_ERR_TYPE; }
@@ -1702,6 +1704,16 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             MPI_Status *st = statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[idx];
             idx++;
             if (r->kind == ACX_REQ_SEND && st != MPI_STATUS_IGNORE && !em.in_graph()) host_status_send(st, r);
+            if (!em.in_graph() && qtype == MPIX_QUEUE_CUDA_STREAM && r->stream != em.stream) {
+                // Waited on another stream than it was enqueued on (the reference allows it: its flags are global). Everything
+                // below assumes stream order between the operation's kernels and its wait (the wait kernel reads the ticket the
+                // trigger took; the wait of an eager send is elided altogether): create that order with an event.
+                cudaEvent_t xe = event_get();
+                cudaError_t xerr = xe ? cudaEventRecord(xe, r->stream) : cudaErrorMemoryAllocation;
+                if (xerr == cudaSuccess) xerr = cudaStreamWaitEvent(em.stream, xe, 0);
+                if (xe) { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); g_event_pool.push_back(xe); }   // the wait has captured the record: the event object may be reused
+                if (xerr != cudaSuccess) { ACX_ERR("cannot order the wait behind the stream the operation was enqueued on: %s", cudaGetErrorString(xerr)); return MPI_ERR_OTHER; }
+            }
             if (r->ev_done && (em.capturing || r->branched)) {   // join the forked branch: required when capturing, and for branched operations (eager sends rely on it)
                 cudaError_t je = cudaStreamWaitEvent(em.stream, r->ev_done, 0);
                 if (je != cudaSuccess) { ACX_ERR("cudaStreamWaitEvent(join): %s", cudaGetErrorString(je)); return MPI_ERR_OTHER; }

@@ -217,6 +217,7 @@ struct AcxRequest {
     char *dev_buf;            // device-accessible alias of user_buf
     int64_t bounce_off;       // heap offset of bounce buffer, -1 if none
     int64_t heap_off;         // heap offset of user_buf if it lives in the heap, else -1
+    cudaStream_t stream;      // stream-mode operations: where the operation was enqueued (a wait on another stream is ordered behind it with an event)
     cudaEvent_t ev_trig, ev_done;  // large transfers: mover runs on a per-peer side stream (fork after the trigger / join at the wait)
     bool in_graph;
     bool host_transport;      // no-GPU mode: backed by an MPI_Request

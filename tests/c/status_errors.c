@@ -8,6 +8,7 @@
  *   - invalid arguments come back as MPI error codes, the request stays MPIX_REQUEST_NULL and nothing leaks;
  *   - MPIX_Request_free on an un-waited basic request completes it (the reference ignores it, defect D11). */
 #include "acx_test.h"
+#include <time.h>
 
 static unsigned char pat(size_t i, int salt) { return (unsigned char)((i * 13u + (size_t)salt * 7u + 1) & 0xff); }
 
@@ -126,6 +127,44 @@ static void request_free_completes(void) {
     T_CHECK(bad == 0 && rq[0] == MPIX_REQUEST_NULL && rq[1] == MPIX_REQUEST_NULL, "Request_free on un-waited requests: %d wrong", bad);
 }
 
+/* Operations enqueued on one stream, waited on another (the reference allows it: its completion flags are global). The
+ * second stream is synchronized alone; the first one is deliberately kept busy behind a marker event so that a missing
+ * order would show. */
+static void stall_20ms(void *arg) { (void)arg; struct timespec ts = {0, 20 * 1000 * 1000}; nanosleep(&ts, NULL); }
+static void cross_stream_wait(void) {
+    if (!t_gpu) return;
+    cudaStream_t a, b;
+    T_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+    T_CUDA(cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking));
+    const size_t sizes[] = {64, 100000};
+    for (unsigned s = 0; s < 2; s++) {
+        const size_t n = sizes[s];
+        unsigned char *out, *in, *h = (unsigned char *)malloc(n), *h2 = NULL;
+        T_CUDA(cudaMallocHost((void **)&h2, n));
+        T_OK(MPIX_Alloc_mem(n, MPI_INFO_NULL, &out)); T_OK(MPIX_Alloc_mem(n, MPI_INFO_NULL, &in));
+        for (size_t i = 0; i < n; i++) h[i] = pat(i, t_rank + 60 + (int)s);
+        T_CUDA(cudaLaunchHostFunc(a, stall_20ms, NULL));                  /* stream a lags: stream b would run ahead of the triggers */
+        T_CUDA(cudaMemcpyAsync(out, h, n, cudaMemcpyHostToDevice, a));   /* on stream a: the send must see it */
+        T_CUDA(cudaMemsetAsync(in, 0, n, a));
+        MPIX_Request rq[2];
+        MPI_Status sts[2];
+        T_OK(MPIX_Irecv_enqueue(in, (int)n, MPI_BYTE, T_LEFT, 44, MPI_COMM_WORLD, &rq[0], MPIX_QUEUE_CUDA_STREAM, &a));
+        T_OK(MPIX_Isend_enqueue(out, (int)n, MPI_BYTE, T_RIGHT, 44, MPI_COMM_WORLD, &rq[1], MPIX_QUEUE_CUDA_STREAM, &a));
+        T_OK(MPIX_Waitall_enqueue(2, rq, sts, MPIX_QUEUE_CUDA_STREAM, &b));
+        T_CUDA(cudaMemcpyAsync(h2, in, n, cudaMemcpyDeviceToHost, b));
+        T_CUDA(cudaStreamSynchronize(b));
+        size_t bad = 0;
+        for (size_t i = 0; i < n; i++) if (h2[i] != pat(i, T_LEFT + 60 + (int)s)) bad++;
+        int cnt = -1;
+        MPI_Get_count(&sts[0], MPI_BYTE, &cnt);
+        T_CHECK(bad == 0 && cnt == (int)n, "wait on another stream, %zu B: %zu wrong bytes, count %d", n, bad, cnt);
+        T_CUDA(cudaStreamSynchronize(a));
+        T_OK(MPIX_Free_mem(out)); T_OK(MPIX_Free_mem(in));
+        cudaFreeHost(h2); free(h);
+    }
+    T_CUDA(cudaStreamDestroy(a)); T_CUDA(cudaStreamDestroy(b));
+}
+
 int main(int argc, char **argv) {
     t_init(&argc, &argv, 0);
     truncation(400, 160, 0, 30);          /* eager, stream wait */
@@ -135,6 +174,7 @@ int main(int argc, char **argv) {
     truncation(100000, 3000, 0, 34);      /* rendezvous-size message into an eager-size receive */
     truncation(100000, 3000, 1, 35);
     many_requests();
+    cross_stream_wait();
     if (t_gpu) tag_collision();
     bad_arguments();
     request_free_completes();
