@@ -59,6 +59,7 @@ $(B)/tests/%: tests/c/%.cu $(LIB)
 examples: $(LIB)
 	@mkdir -p $(B)/examples
 	$(NVCC) $(GENCODE) -O2 -Iinclude examples/stream_ring.c -o $(B)/examples/stream_ring -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
+	$(NVCC) $(GENCODE) -O2 -Iinclude examples/token_ring.c -o $(B)/examples/token_ring -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
 	$(NVCC) $(GENCODE) -O2 -Iinclude examples/partitioned_producer.cu -o $(B)/examples/partitioned_producer -Llib -lacx -Xlinker -rpath,'$$ORIGIN/../../lib' -cudart static
 
 # Portability check (compile only, no MPI needed): build the runtime and the fused kernels against a declarations-only

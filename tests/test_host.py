@@ -194,6 +194,10 @@ def test_examples_compile_and_python_example_runs(built):
     env = dict(os.environ, RANK="0", WORLD_SIZE="1", ACX_FORCE_HOST="1")
     r = subprocess.run([sys.executable, str(built / "examples/torch_ring.py")], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "received tensor filled with 1.0" in r.stdout, r.stdout + r.stderr
+    # the C examples that need no user kernel also run without a GPU (host transport)
+    for exe, expect in (("token_ring", "10 laps done"), ("stream_ring", "received bytes")):
+        r = acxrun(built, 3, built / f"build/examples/{exe}", env={"ACX_FORCE_HOST": "1"})
+        assert r.returncode == 0 and r.stdout.count(expect) == 3, r.stdout + r.stderr
 
 
 @pytest.mark.parametrize("mode", ["ring", "allpairs"])
