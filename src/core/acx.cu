@@ -161,7 +161,9 @@ static void release_request_resources(AcxRequest *r) {
 // (tests/emu): a late mover read the NEXT owner's `mover` flag and published `done` early.
 static bool side_branch_finished(const AcxRequest *r) {
     if (!r || !r->ev_done) return true;
-    return cudaEventQuery(r->ev_done) != cudaErrorNotReady;   // success, or a dead device (nothing to protect then)
+    if (cudaEventQuery(r->ev_done) != cudaErrorNotReady) return true;   // success, or a dead device (nothing to protect then)
+    cudaGetLastError();   // "not ready" is recorded as the thread's last error: clear it, or the caller's next cudaGetLastError() (torch checks every launch) reports it
+    return false;
 }
 
 void acx_slot_free(int slot) {

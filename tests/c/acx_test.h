@@ -57,6 +57,10 @@ static void t_init(int *argc, char ***argv, int need_gpu) {
 }
 
 static int t_finish(const char *name) {
+    if (t_gpu) {   /* the library must not leave a CUDA "last error" behind (cudaErrorNotReady from an event query, a failed probe, ...): applications check it after their own launches */
+        cudaError_t le = cudaGetLastError();
+        T_CHECK(le == cudaSuccess, "stale CUDA last-error after the test: %s", cudaGetErrorString(le));
+    }
     MPI_Allreduce(MPI_IN_PLACE, &t_errs, 1, MPI_INT, MPI_MAX, MPI_COMM_WORLD);
     if (MPIX_Finalize()) t_errs++;
     if (t_rank == 0) printf("%s: %s (np=%d, %s transport)\n", name, t_errs ? "FAIL" : "PASS", t_size, t_gpu ? "device" : "host");

@@ -588,7 +588,7 @@ cudaError_t cudaStreamSynchronize(cudaStream_t cs) {
 cudaError_t cudaStreamQuery(cudaStream_t cs) {
     Stream *s = S(cs);
     if (emu::g_trapped.load()) return fail(cudaErrorLaunchFailure);
-    return s->idle() ? cudaSuccess : cudaErrorNotReady;
+    return s->idle() ? cudaSuccess : fail(cudaErrorNotReady);
 }
 
 // ---- events -------------------------------------------------------------------------------------------------------
@@ -653,7 +653,7 @@ cudaError_t cudaEventQuery(cudaEvent_t ce) {
     Event *e = (Event *)ce;
     if (!e) return fail(cudaErrorInvalidResourceHandle);
     std::lock_guard<std::mutex> lk(e->mu);
-    return e->done >= e->recorded ? cudaSuccess : cudaErrorNotReady;
+    return e->done >= e->recorded ? cudaSuccess : fail(cudaErrorNotReady);   // like the real runtime: "not ready" becomes the thread's last error
 }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
     Event *x = (Event *)a, *y = (Event *)b;
