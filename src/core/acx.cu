@@ -89,6 +89,18 @@ static long g_fault_drop_send = 0;
 static long g_fault_delay_us = 0;         // ACX_FAULT_DELAY_US=n: sleep a pseudo-random 0..n us on the host before every send / receive is enqueued (shakes arrival orders)
 static std::atomic<long> g_send_counter{0};
 
+// The caller may be inside a stream capture begun in Global (or ThreadLocal) mode: CUDA then refuses "potentially unsafe"
+// calls from this thread — cudaHostRegister, cudaIpcOpenMemHandle, cudaMalloc, synchronous copies — and invalidates the
+// capture. Library-internal housekeeping of that kind (pinning a host buffer, mapping a peer's registered allocation,
+// first-use tables) is independent of what is being captured, so it runs with the thread's capture mode relaxed, as
+// cudaThreadExchangeStreamCaptureMode is meant to be used by libraries.
+struct CaptureRelax {
+    cudaStreamCaptureMode saved = cudaStreamCaptureModeRelaxed;
+    bool ok;
+    CaptureRelax() { ok = cudaThreadExchangeStreamCaptureMode(&saved) == cudaSuccess; if (!ok) cudaGetLastError(); }
+    ~CaptureRelax() { if (ok) cudaThreadExchangeStreamCaptureMode(&saved); }
+};
+
 static Watchdog make_wd() {
     Watchdog w;
     w.budget_ns = g_acx->watchdog_ms > 0 ? (uint64_t)g_acx->watchdog_ms * 1000000ull : 0;
@@ -306,6 +318,7 @@ int acx_device_alias(const void *p, size_t bytes, char **out) {
             if (cur >= hi) { *out = (char *)p; return 0; }
         }
     }
+    CaptureRelax relax;   // cudaHostRegister below may run inside a user's capture
     cudaPointerAttributes a;
     cudaError_t e = cudaPointerGetAttributes(&a, p);
     if (e != cudaSuccess) { cudaGetLastError(); a.type = cudaMemoryTypeUnregistered; }
@@ -444,6 +457,7 @@ static void reg_init() {
 static void reg_progress() {
     if (!g_reg_on) return;
     std::lock_guard<std::recursive_mutex> lk(g_acx->mu);   // application threads enqueue concurrently; new entries are rare
+    CaptureRelax relax;   // cudaIpcOpenMemHandle + a synchronous 8-byte copy: legal inside a user's capture only in relaxed mode
     bool wrote = false;
     std::vector<std::pair<int, uint32_t>> to_ack;
     for (int p = 0; p < g_acx->size; p++) {
@@ -473,6 +487,7 @@ static void reg_progress() {
 // has mapped; ~0 otherwise (caller bounces). Publishes the allocation on first sight.
 static uint64_t reg_encode(const void *p, size_t bytes, int peer) {
     if (!g_reg_on) return ~0ull;
+    CaptureRelax relax;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return ~0ull; }
     if (a.type != cudaMemoryTypeDevice || a.device != g_acx->dev) return ~0ull;
@@ -1295,6 +1310,7 @@ static void complete_null_op(AcxRequest *r, MPI_Status *st) {
 // Wildcard receives (experimental): device tables on first use, and the kernel that resolves + matches one at wait time.
 static int any_tables() {
     if (g_any_tbl_d) return 0;
+    CaptureRelax relax;
     if (g_acx->size > kAnyMaxRanks) { ACX_ERR("wildcard receives support up to %d ranks", kAnyMaxRanks); return MPI_ERR_OTHER; }
     AnyTable h;
     memset(&h, 0, sizeof h);
@@ -2170,6 +2186,7 @@ extern "C" int MPIX_Precv_init(void *buf, int partitions, MPI_Count count, MPI_D
 // the device descriptor.
 static int presolve(AcxRequest *r) {
     if (r->resolved) return 0;
+    CaptureRelax relax;   // cudaMalloc + cudaMemcpy of the device descriptor
     PHandshake *hs;
     { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); hs = g_hs[r]; }
     MPI_Wait(&hs->sreq, MPI_STATUS_IGNORE);

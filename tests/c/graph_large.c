@@ -64,6 +64,35 @@ static void run(int mode, int heap, size_t n, int tag) {
     free(h);
 }
 
+/* Token ring captured with PAGEABLE host buffers (static storage, like the stack variables of the reference's
+ * ring-all-graph test): the library pins them in place inside the capture. cudaHostRegister is a "potentially unsafe" call
+ * in a Global-mode capture; the library relaxes the thread's capture mode around its own housekeeping calls. */
+static void pageable_in_capture(void) {
+    static int pageable[2 * 1024];   /* two words a page apart */
+    int *send = &pageable[0], *recv = &pageable[1024];
+    *send = 700 + t_rank; *recv = -1;
+    cudaStream_t stream;
+    T_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    MPIX_Request rq[2];
+    T_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeGlobal));
+    T_OK(MPIX_Isend_enqueue(send, 1, MPI_INT, T_RIGHT, 39, MPI_COMM_WORLD, &rq[0], MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_OK(MPIX_Irecv_enqueue(recv, 1, MPI_INT, T_LEFT, 39, MPI_COMM_WORLD, &rq[1], MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_OK(MPIX_Waitall_enqueue(2, rq, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &stream));
+    T_CUDA(cudaStreamEndCapture(stream, &graph));
+    T_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    for (int hop = 0; hop < t_size; hop++) {
+        T_CUDA(cudaGraphLaunch(exec, stream));
+        T_CUDA(cudaMemcpyAsync(send, recv, sizeof(int), cudaMemcpyHostToHost, stream));
+    }
+    T_CUDA(cudaStreamSynchronize(stream));
+    T_CHECK(*recv == 700 + t_rank, "pageable buffers in a capture: token came back as %d", *recv);
+    T_CUDA(cudaGraphExecDestroy(exec));
+    T_CUDA(cudaGraphDestroy(graph));
+    T_CUDA(cudaStreamDestroy(stream));
+}
+
 int main(int argc, char **argv) {
     t_init(&argc, &argv, 1);
     const size_t sizes[] = {20000, 200000, 1u << 20};   /* above eager: trigger + mover; larger ones take the fused kernel on a full-size GPU */
@@ -71,6 +100,7 @@ int main(int argc, char **argv) {
     for (int mode = 0; mode < 2; mode++)
         for (int heap = 1; heap >= 0; heap--)
             for (unsigned s = 0; s < sizeof sizes / sizeof sizes[0]; s++) run(mode, heap, sizes[s], tag++);
+    pageable_in_capture();
     MPIX_Acx_stats s;
     MPIX_Get_stats(&s);
     T_CHECK(s.slots_in_use == 0, "%llu request slots still held after every graph was destroyed", s.slots_in_use);

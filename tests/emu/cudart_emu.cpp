@@ -197,6 +197,8 @@ struct Capture {
     Stream *origin;
     std::set<Stream *> members;
     unsigned long long id;
+    enum cudaStreamCaptureMode mode = cudaStreamCaptureModeGlobal;
+    bool invalid = false;   // an unsafe call was made while it was in progress: cudaStreamEndCapture reports it
 };
 struct Stream {
     static constexpr size_t kMaxQueued = 192;
@@ -254,6 +256,15 @@ struct Stream {
 };
 std::mutex g_streams_mu;
 std::set<Stream *> g_streams;
+// Capture-mode rules: while a capture begun in Global mode is in progress (ThreadLocal: by this thread), "potentially unsafe"
+// calls — allocation, registration, IPC mapping, synchronous copies, device synchronization — fail with
+// cudaErrorStreamCaptureUnsupported and invalidate the capture, unless the calling thread has switched itself to Relaxed
+// with cudaThreadExchangeStreamCaptureMode (what a library does around its own such calls).
+std::atomic<int> g_global_captures{0};
+thread_local int t_local_captures = 0;
+thread_local enum cudaStreamCaptureMode t_capture_mode = cudaStreamCaptureModeGlobal;
+struct Capture;
+void invalidate_all_captures();
 Stream *g_null = nullptr;
 
 Stream *new_stream(unsigned flags, bool is_null) {
@@ -273,6 +284,15 @@ Stream *S(cudaStream_t s) {
     if (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) return null_stream();
     return (Stream *)s;
 }
+bool unsafe_call_during_capture(const char *what) {
+    if (t_capture_mode == cudaStreamCaptureModeRelaxed) return false;
+    if (g_global_captures.load() == 0 && t_local_captures == 0) return false;
+    fprintf(stderr, "emu: %s during a stream capture (capture invalidated; a library wraps such calls in cudaThreadExchangeStreamCaptureMode(Relaxed))\n", what);
+    invalidate_all_captures();
+    return true;
+}
+#define EMU_UNSAFE(what) do { if (unsafe_call_during_capture(what)) return fail(cudaErrorStreamCaptureUnsupported); } while (0)
+
 // `s` will not run anything submitted from now on before `a`'s current tail has completed
 void order_after(Stream *s, Stream *a) {
     if (s == a) return;
@@ -311,6 +331,11 @@ struct Event {
 };
 unsigned long long g_capture_ids = 1;
 
+void invalidate_all_captures() {
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    std::lock_guard<std::mutex> l2(g_streams_mu);
+    for (Stream *st : g_streams) if (st->cap) st->cap->invalid = true;
+}
 bool reachable(Node *from, Node *target, std::set<Node *> &seen) {   // is `target` an ancestor-or-self of `from`?
     if (from == target) return true;
     if (!seen.insert(from).second) return false;
@@ -417,7 +442,9 @@ cudaError_t cudaDeviceGetAttribute(int *v, enum cudaDeviceAttr a, int) {
     return cudaSuccess;
 }
 cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
-cudaError_t cudaDeviceSynchronize(void) { sync_all(); return dead_or(cudaSuccess); }
+cudaError_t cudaDeviceSynchronize(void) {
+    EMU_UNSAFE("cudaDeviceSynchronize");
+    sync_all(); return dead_or(cudaSuccess); }
 cudaError_t cudaGetLastError(void) { cudaError_t e = t_last; t_last = cudaSuccess; return e; }
 cudaError_t cudaPeekAtLastError(void) { return t_last; }
 const char *cudaGetErrorString(cudaError_t e) {
@@ -456,6 +483,7 @@ cudaError_t cudaFuncSetAttribute(const void *, enum cudaFuncAttribute, int) { re
 
 // ---- memory -------------------------------------------------------------------------------------------------------
 cudaError_t cudaMalloc(void **p, size_t size) {
+    EMU_UNSAFE("cudaMalloc");
     if (!p) return fail(cudaErrorInvalidValue);
     if (size == 0) { *p = nullptr; return cudaSuccess; }
     const size_t map = (size + 4095) & ~(size_t)4095;
@@ -470,6 +498,7 @@ cudaError_t cudaMalloc(void **p, size_t size) {
 }
 cudaError_t cudaFree(void *p) {
     if (!p) return cudaSuccess;
+    EMU_UNSAFE("cudaFree");
     sync_all();   // cudaFree synchronizes the device: keeps the hazard the design documents (spinning gates vs. cudaFree) observable
     std::lock_guard<std::mutex> lk(g_mem_mu);
     auto it = g_allocs.find((uintptr_t)p);
@@ -481,6 +510,7 @@ cudaError_t cudaFree(void *p) {
 }
 cudaError_t cudaMallocManaged(void **p, size_t size, unsigned) { return cudaMalloc(p, size); }
 cudaError_t cudaHostAlloc(void **p, size_t size, unsigned) {
+    EMU_UNSAFE("cudaHostAlloc");
     void *m = nullptr;
     if (posix_memalign(&m, 4096, size ? size : 1)) return fail(cudaErrorMemoryAllocation);
     std::lock_guard<std::mutex> lk(g_mem_mu);
@@ -499,6 +529,7 @@ cudaError_t cudaFreeHost(void *p) {
     return cudaSuccess;
 }
 cudaError_t cudaHostRegister(void *p, size_t size, unsigned) {
+    EMU_UNSAFE("cudaHostRegister");
     std::lock_guard<std::mutex> lk(g_mem_mu);
     // like CUDA: a range overlapping an existing registration is rejected
     auto it = g_allocs.lower_bound((uintptr_t)p);
@@ -508,6 +539,7 @@ cudaError_t cudaHostRegister(void *p, size_t size, unsigned) {
     return cudaSuccess;
 }
 cudaError_t cudaHostUnregister(void *p) {
+    EMU_UNSAFE("cudaHostUnregister");
     std::lock_guard<std::mutex> lk(g_mem_mu);
     auto it = g_allocs.find((uintptr_t)p);
     if (it == g_allocs.end() || it->second.kind != kRegistered) return fail(cudaErrorHostMemoryNotRegistered);
@@ -534,6 +566,7 @@ cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
     return cudaSuccess;
 }
 cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+    EMU_UNSAFE("cudaIpcOpenMemHandle");
     IpcHandle x;
     memcpy(&x, &h, sizeof x);
     if (x.magic != kIpcMagic) return fail(cudaErrorInvalidValue);
@@ -691,6 +724,7 @@ cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, enum cudaMemcp
     return submit_or_capture(S(cs), nd, "memcpy", [dst, src, n] { memmove(dst, src, n); });
 }
 cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, enum cudaMemcpyKind k) {
+    EMU_UNSAFE("cudaMemcpy (synchronous)");
     cudaError_t e = cudaMemcpyAsync(dst, src, n, k, nullptr);
     return e != cudaSuccess ? e : cudaStreamSynchronize(nullptr);
 }
@@ -700,6 +734,7 @@ cudaError_t cudaMemsetAsync(void *dst, int v, size_t n, cudaStream_t cs) {
     return submit_or_capture(S(cs), nd, "memset", [dst, v, n] { memset(dst, v, n); });
 }
 cudaError_t cudaMemset(void *dst, int v, size_t n) {
+    EMU_UNSAFE("cudaMemset (synchronous)");
     cudaError_t e = cudaMemsetAsync(dst, v, n, nullptr);
     return e != cudaSuccess ? e : cudaStreamSynchronize(nullptr);
 }
@@ -710,13 +745,15 @@ cudaError_t cudaLaunchHostFunc(cudaStream_t cs, cudaHostFn_t fn, void *arg) {
 }
 
 // ---- stream capture -------------------------------------------------------------------------------------------------
-cudaError_t cudaStreamBeginCapture(cudaStream_t cs, enum cudaStreamCaptureMode) {
+cudaError_t cudaStreamBeginCapture(cudaStream_t cs, enum cudaStreamCaptureMode mode) {
     Stream *s = S(cs);
     if (s->is_null) return fail(cudaErrorStreamCaptureUnsupported);   // the legacy stream cannot be captured
     std::lock_guard<std::mutex> lk(g_graph_mu);
     if (s->cap) return fail(cudaErrorIllegalState);
     Capture *c = new Capture();
     c->graph = new Graph(); c->origin = s; c->members.insert(s); c->id = g_capture_ids++;
+    c->mode = mode;
+    if (mode == cudaStreamCaptureModeGlobal) g_global_captures++; else if (mode == cudaStreamCaptureModeThreadLocal) t_local_captures++;
     g_graphs.insert(c->graph);
     s->cap = c; s->cap_deps.clear();
     return cudaSuccess;
@@ -739,9 +776,18 @@ cudaError_t cudaStreamEndCapture(cudaStream_t cs, cudaGraph_t *out) {
     }
     for (Stream *m : c->members) { m->cap = nullptr; m->cap_deps.clear(); }
     Graph *g = c->graph;
+    if (c->mode == cudaStreamCaptureModeGlobal) g_global_captures--; else if (c->mode == cudaStreamCaptureModeThreadLocal) t_local_captures--;
+    const bool invalid = c->invalid;
     delete c;
+    if (invalid) { g_graphs.erase(g); delete g; if (out) *out = nullptr; return fail(cudaErrorStreamCaptureInvalidated); }
     if (unjoined) { g_graphs.erase(g); delete g; if (out) *out = nullptr; return fail(cudaErrorStreamCaptureUnjoined); }
     *out = (cudaGraph_t)g;
+    return cudaSuccess;
+}
+cudaError_t cudaThreadExchangeStreamCaptureMode(enum cudaStreamCaptureMode *mode) {
+    const enum cudaStreamCaptureMode old = t_capture_mode;
+    t_capture_mode = *mode;
+    *mode = old;
     return cudaSuccess;
 }
 cudaError_t cudaStreamIsCapturing(cudaStream_t cs, enum cudaStreamCaptureStatus *st) {
