@@ -718,7 +718,23 @@ cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t *cfg, const void *func,
     // launch attributes (programmatic stream serialization) only relax ordering on hardware; in-order execution is a legal schedule
     return cudaLaunchKernel(func, cfg->gridDim, cfg->blockDim, args, cfg->dynamicSmemBytes, cfg->stream);
 }
-cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, enum cudaMemcpyKind, cudaStream_t cs) {
+// With unified addressing the runtime knows what each pointer is: an explicit direction that contradicts it is an error.
+static bool is_device_memory(const void *p) {
+    std::lock_guard<std::mutex> lk(g_mem_mu);
+    const Alloc *a = find_alloc(p);
+    return a && (a->kind == kDevOwn || a->kind == kDevIpc);
+}
+static bool memcpy_kind_ok(void *dst, const void *src, enum cudaMemcpyKind k) {
+    switch (k) {
+        case cudaMemcpyHostToDevice: return !is_device_memory(src) && is_device_memory(dst);
+        case cudaMemcpyDeviceToHost: return is_device_memory(src) && !is_device_memory(dst);
+        case cudaMemcpyDeviceToDevice: return is_device_memory(src) && is_device_memory(dst);
+        case cudaMemcpyHostToHost: return !is_device_memory(src) && !is_device_memory(dst);
+        default: return true;
+    }
+}
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, enum cudaMemcpyKind k, cudaStream_t cs) {
+    if (n && !memcpy_kind_ok(dst, src, k)) { fprintf(stderr, "emu: cudaMemcpy direction %d contradicts the pointers (%p <- %p)\n", (int)k, dst, src); return fail(cudaErrorInvalidValue); }
     Node *nd = new Node();
     nd->type = kNodeMemcpy; nd->dst = dst; nd->src = src; nd->bytes = n;
     return submit_or_capture(S(cs), nd, "memcpy", [dst, src, n] { memmove(dst, src, n); });
