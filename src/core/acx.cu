@@ -56,7 +56,14 @@ static cudaStream_t host_stream() {
     std::lock_guard<std::mutex> lk(g_host_streams_mu);
     cudaStream_t s = nullptr;
     if (g_host_streams.empty()) s = g_acx->istream;
-    else if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return g_acx->istream; }
+    else {
+        // CUDA's current device is per thread (a fresh thread starts on device 0): the stream must live on the library's device
+        int cur = -1;
+        const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != g_acx->dev && cudaSetDevice(g_acx->dev) == cudaSuccess;
+        const cudaError_t ce = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        if (switched) cudaSetDevice(cur);
+        if (ce != cudaSuccess) { cudaGetLastError(); return g_acx->istream; }
+    }
     g_host_streams.push_back(s);
     mine = s; mine_gen = g_init_generation;
     return s;

@@ -10,6 +10,7 @@
 #define ITERS 60
 
 static int g_thread_errs[NTHREADS + 1];
+static int g_dev = -1;   /* the CUDA device of this rank: every application thread must make it current (CUDA's current device is per thread) */
 
 static unsigned char pat(size_t i, int salt) { return (unsigned char)((i * 37u + (size_t)salt * 11u) & 0xff); }
 
@@ -18,6 +19,7 @@ static void *p2p_thread(void *arg) {
     const int tag = 3 + id;                       /* distinct channels: tickets of different threads never interleave */
     const size_t sizes[3] = {48, 6000, 70000};    /* eager, eager (multi-thread copy), rendezvous */
     cudaStream_t st;
+    if (t_gpu) cudaSetDevice(g_dev);
     if (t_gpu) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); else st = 0;
     int errs = 0;
     for (int it = 0; it < ITERS && !errs; it++) {
@@ -54,6 +56,7 @@ static void *partitioned_thread(void *arg) {
     static int sendbuf[NP * PER], recvbuf[NP * PER];
     MPIX_Request rq[2];
     int errs = 0;
+    if (t_gpu) cudaSetDevice(g_dev);
     if (MPIX_Psend_init(sendbuf, NP, PER, MPI_INT, T_RIGHT, 90, MPI_COMM_WORLD, MPI_INFO_NULL, &rq[0])) errs++;
     if (MPIX_Precv_init(recvbuf, NP, PER, MPI_INT, T_LEFT, 90, MPI_COMM_WORLD, MPI_INFO_NULL, &rq[1])) errs++;
     for (int it = 0; it < 12 && !errs; it++) {
@@ -70,6 +73,7 @@ static void *partitioned_thread(void *arg) {
 
 int main(int argc, char **argv) {
     t_init(&argc, &argv, 0);
+    if (t_gpu) T_CUDA(cudaGetDevice(&g_dev));
     pthread_t th[NTHREADS + 1];
     for (long i = 0; i < NTHREADS; i++) pthread_create(&th[i], NULL, p2p_thread, (void *)i);
     pthread_create(&th[NTHREADS], NULL, partitioned_thread, NULL);
