@@ -34,6 +34,7 @@
 namespace {
 
 thread_local cudaError_t t_last = cudaSuccess;
+thread_local int t_dev = 0;   // CUDA's current device is per thread; a new thread starts on device 0
 cudaError_t fail(cudaError_t e) { t_last = e; return e; }
 cudaError_t dead_or(cudaError_t ok) { return emu::g_trapped.load() ? fail(cudaErrorLaunchFailure) : ok; }
 
@@ -43,7 +44,7 @@ long env_long(const char *n, long d) { const char *v = getenv(n); return v && *v
 // memory
 // ------------------------------------------------------------------------------------------------------------------
 enum { kDevOwn = 0, kDevIpc = 1, kPinned = 2, kRegistered = 3 };
-struct Alloc { char *base; size_t size; uint64_t id; int kind; int fd; };
+struct Alloc { char *base; size_t size; uint64_t id; int kind; int fd; int dev = 0; };
 std::mutex g_mem_mu;
 std::map<uintptr_t, Alloc> g_allocs;   // by base address
 uint64_t g_next_id = 1;
@@ -56,7 +57,7 @@ const Alloc *find_alloc(const void *p) {   // g_mem_mu held
     return ((uintptr_t)p < (uintptr_t)a.base + a.size) ? &a : nullptr;
 }
 
-struct IpcHandle { uint32_t magic; int32_t pid, fd; uint32_t pad; uint64_t size, id; };
+struct IpcHandle { uint32_t magic; int32_t pid, fd; uint32_t dev; uint64_t size, id; };
 static_assert(sizeof(IpcHandle) <= sizeof(cudaIpcMemHandle_t), "handle must fit");
 constexpr uint32_t kIpcMagic = 0xACE0E001u;
 
@@ -204,6 +205,7 @@ struct Stream {
     static constexpr size_t kMaxQueued = 192;
     unsigned flags = 0;
     bool is_null = false;
+    int dev = 0;            // the device that was current when the stream was created
     std::thread th;
     std::mutex mu;
     std::condition_variable cv, cv_done;
@@ -269,16 +271,20 @@ Stream *g_null = nullptr;
 
 Stream *new_stream(unsigned flags, bool is_null) {
     Stream *s = new Stream();
-    s->flags = flags; s->is_null = is_null;
+    s->flags = flags; s->is_null = is_null; s->dev = t_dev;
     s->th = std::thread([s] { s->worker(); });
     std::lock_guard<std::mutex> lk(g_streams_mu);
     g_streams.insert(s);
     return s;
 }
-Stream *null_stream() {
-    static std::once_flag once;
-    std::call_once(once, [] { g_null = new_stream(0, true); });
-    return g_null;
+Stream *null_stream() {   // one legacy default stream per device
+    static std::mutex mu;
+    static std::map<int, Stream *> per_dev;
+    std::lock_guard<std::mutex> lk(mu);
+    Stream *&s = per_dev[t_dev];
+    if (!s) s = new_stream(0, true);
+    g_null = s;
+    return s;
 }
 Stream *S(cudaStream_t s) {
     if (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) return null_stream();
@@ -318,6 +324,12 @@ Node *capture_node(Stream *s, Node *n) {
     s->cap->graph->nodes.push_back(n);
     s->cap_deps.assign(1, n);
     return n;
+}
+
+bool wrong_device(Stream *s, const char *what) {
+    if (s->dev == t_dev) return false;
+    fprintf(stderr, "emu: %s on a stream of device %d while device %d is current in this thread (missing cudaSetDevice?)\n", what, s->dev, t_dev);
+    return true;
 }
 
 struct Event {
@@ -369,6 +381,7 @@ int fake_cuPointerGetAttribute(void *data, int attr, unsigned long long ptr) {
 void submit(Stream *s, const char *what, std::function<void()> t);
 int fake_cuStreamBatchMemOp(CUstream cs, unsigned int count, CUstreamBatchMemOpParams *ops, unsigned int) {
     Stream *s = S((cudaStream_t)cs);
+    if (wrong_device(s, "cuStreamBatchMemOp")) return 400 /*CUDA_ERROR_INVALID_HANDLE*/;
     { std::lock_guard<std::mutex> lk(g_graph_mu); if (s->cap) return 900 /*CUDA_ERROR_STREAM_CAPTURE_UNSUPPORTED*/; }
     auto v = std::make_shared<std::vector<CUstreamBatchMemOpParams>>(ops, ops + count);
     for (const auto &o : *v)
@@ -418,8 +431,8 @@ void acx_emu_dump_streams(void) {
 
 // ---- device management --------------------------------------------------------------------------------------------
 cudaError_t cudaGetDeviceCount(int *n) { *n = (int)env_long("ACX_EMU_DEVICES", 1); return cudaSuccess; }
-cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
-cudaError_t cudaSetDevice(int d) { return d >= 0 && d < env_long("ACX_EMU_DEVICES", 1) ? cudaSuccess : fail(cudaErrorInvalidDevice); }
+cudaError_t cudaGetDevice(int *d) { *d = t_dev; return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= env_long("ACX_EMU_DEVICES", 1)) return fail(cudaErrorInvalidDevice); t_dev = d; return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     memset(p, 0, sizeof *p);
     snprintf(p->name, sizeof p->name, "acx-emu software device");
@@ -492,7 +505,7 @@ cudaError_t cudaMalloc(void **p, size_t size) {
     void *m = mmap(nullptr, map, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     if (m == MAP_FAILED) { close(fd); return fail(cudaErrorMemoryAllocation); }
     std::lock_guard<std::mutex> lk(g_mem_mu);
-    g_allocs[(uintptr_t)m] = Alloc{(char *)m, map, g_next_id++, kDevOwn, fd};
+    g_allocs[(uintptr_t)m] = Alloc{(char *)m, map, g_next_id++, kDevOwn, fd, t_dev};
     *p = m;
     return cudaSuccess;
 }
@@ -552,15 +565,15 @@ cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p) {
     std::lock_guard<std::mutex> lk(g_mem_mu);
     const Alloc *x = find_alloc(p);
     if (!x) { a->type = cudaMemoryTypeUnregistered; a->device = -1; return cudaSuccess; }
-    if (x->kind == kDevOwn || x->kind == kDevIpc) { a->type = cudaMemoryTypeDevice; a->device = 0; a->devicePointer = (void *)p; }
-    else { a->type = cudaMemoryTypeHost; a->device = 0; a->devicePointer = (void *)p; a->hostPointer = (void *)p; }
+    if (x->kind == kDevOwn || x->kind == kDevIpc) { a->type = cudaMemoryTypeDevice; a->device = x->dev; a->devicePointer = (void *)p; }
+    else { a->type = cudaMemoryTypeHost; a->device = t_dev; a->devicePointer = (void *)p; a->hostPointer = (void *)p; }
     return cudaSuccess;
 }
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
     std::lock_guard<std::mutex> lk(g_mem_mu);
     auto it = g_allocs.find((uintptr_t)p);
     if (it == g_allocs.end() || it->second.kind != kDevOwn) return fail(cudaErrorInvalidValue);   // base of an own allocation only
-    IpcHandle x{kIpcMagic, (int32_t)getpid(), it->second.fd, 0, it->second.size, it->second.id};
+    IpcHandle x{kIpcMagic, (int32_t)getpid(), it->second.fd, (uint32_t)it->second.dev, it->second.size, it->second.id};
     memset(h, 0, sizeof *h);
     memcpy(h, &x, sizeof x);
     return cudaSuccess;
@@ -579,7 +592,7 @@ cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
     close(fd);
     if (m == MAP_FAILED) return fail(cudaErrorMemoryAllocation);
     std::lock_guard<std::mutex> lk(g_mem_mu);
-    g_allocs[(uintptr_t)m] = Alloc{(char *)m, (size_t)x.size, g_next_id++, kDevIpc, -1};
+    g_allocs[(uintptr_t)m] = Alloc{(char *)m, (size_t)x.size, g_next_id++, kDevIpc, -1, (int)x.dev};
     *p = m;
     return cudaSuccess;
 }
@@ -640,7 +653,7 @@ cudaError_t cudaEventDestroy(cudaEvent_t ce) {
 cudaError_t cudaEventRecord(cudaEvent_t ce, cudaStream_t cs) {
     Event *e = (Event *)ce;
     Stream *s = S(cs);
-    if (!e) return fail(cudaErrorInvalidResourceHandle);
+    if (!e || wrong_device(s, "cudaEventRecord")) return fail(cudaErrorInvalidResourceHandle);
     {
         std::lock_guard<std::mutex> lk(g_graph_mu);
         if (s->cap) { e->cap = s->cap; e->cap_nodes = s->cap_deps; return cudaSuccess; }
@@ -697,6 +710,11 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
 
 // ---- work submission ------------------------------------------------------------------------------------------------
 static cudaError_t submit_or_capture(Stream *s, Node *n, const char *what, std::function<void()> t) {
+    if (s->dev != t_dev) {   // real CUDA: invalid resource handle — the calling thread has another device current than the stream's
+        fprintf(stderr, "emu: %s submitted to a stream of device %d while device %d is current in this thread (missing cudaSetDevice?)\n", what, s->dev, t_dev);
+        delete n;
+        return fail(cudaErrorInvalidResourceHandle);
+    }
     {
         std::lock_guard<std::mutex> lk(g_graph_mu);
         if (s->cap) { capture_node(s, n); return cudaSuccess; }
@@ -911,7 +929,7 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t ce, cudaStream_t cs) {
     Stream *s = S(cs);
     {
         std::lock_guard<std::mutex> lk(g_graph_mu);
-        if (!g_graphs.count(x) || !x->is_exec) return fail(cudaErrorInvalidResourceHandle);
+        if (!g_graphs.count(x) || !x->is_exec || wrong_device(s, "cudaGraphLaunch")) return fail(cudaErrorInvalidResourceHandle);
         if (s->cap) return fail(cudaErrorNotSupported);
     }
     if (emu::g_trapped.load()) return fail(cudaErrorLaunchFailure);
