@@ -14,7 +14,7 @@ BINS  := bin/acxrun
 BENCH := $(patsubst bench/%.cu,bin/%,$(wildcard bench/*.cu))
 CTESTS := $(patsubst tests/c/%.c,$(B)/tests/%,$(wildcard tests/c/*.c)) $(patsubst tests/c/%.cu,$(B)/tests/%,$(wildcard tests/c/*.cu))
 
-.PHONY: all clean lib tests bench examples tsan asan install extmpi-check extmpi-lib emu emu-tsan emu-lib emu-tests emu-asan emu-tsan-matrix
+.PHONY: all clean lib tests bench examples tsan asan install extmpi-check extmpi-lib emu emu-tsan emu-lib emu-tests emu-asan emu-tsan-matrix emu-reftests
 all: lib $(BINS) tests bench
 bench: $(BENCH)
 bin/%: bench/%.cu $(LIB)
@@ -132,6 +132,15 @@ $(EMU)/libacx_emu.so: $(EMU)/acx.o $(EMU)/cudart_emu.o $(EMU)/minimpi.o
 $(EMU)/tests/%: tests/c/%.c $(EMU)/libacx_emu.so tests/c/acx_test.h
 	@mkdir -p $(EMU)/tests
 	gcc -O1 -g $(EMU_SAN) -Iinclude -I$(CUDA_HOME)/include $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU)
+# Drop-in check: the REFERENCE's own test sources (read in place from $(REF), nothing is copied), unmodified, built against
+# include/ + the software device. The two graph tests use CUDA 11's five-argument cudaGraphInstantiate, which only the C++
+# runtime header still offers, so they are compiled as C++. ring-partitioned.cu needs nvcc (kernel launches).
+REF ?= /root/reference
+emu-reftests: $(EMU)/libacx_emu.so
+	@mkdir -p $(EMU)/reftests
+	for t in ring ring-all ring-all-device; do gcc -O1 -DDEBUG -Iinclude -I$(CUDA_HOME)/include $(REF)/test/src/$$t.c -o $(EMU)/reftests/$$t -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) || exit 1; done
+	for t in ring-all-graph ring-all-graph-construction; do $(CXX) -x c++ -O1 -DDEBUG -fpermissive -w -Iinclude -I$(CUDA_HOME)/include $(REF)/test/src/$$t.c -o $(EMU)/reftests/$$t -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) || exit 1; done
+
 $(EMU)/p2p_bench: bench/p2p_bench.cu $(EMU)/libacx_emu.so tests/emu/cuda_emu.h
 	$(CXX) -O1 $(EMU_FLAGS) $(EMU_SAN) -x c++ -include tests/emu/cuda_emu.h $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) -lpthread
 $(EMU)/tests/%: tests/c/%.cu $(EMU)/libacx_emu.so tests/c/acx_test.h tests/emu/cuda_emu.h
