@@ -134,12 +134,15 @@ $(EMU)/tests/%: tests/c/%.c $(EMU)/libacx_emu.so tests/c/acx_test.h
 	gcc -O1 -g $(EMU_SAN) -Iinclude -I$(CUDA_HOME)/include $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU)
 # Drop-in check: the REFERENCE's own test sources (read in place from $(REF), nothing is copied), unmodified, built against
 # include/ + the software device. The two graph tests use CUDA 11's five-argument cudaGraphInstantiate, which only the C++
-# runtime header still offers, so they are compiled as C++. ring-partitioned.cu needs nvcc (kernel launches).
+# runtime header still offers, so they are compiled as C++; ring-partitioned.cu is piped through sed, which spells its two
+# kernel<<<...>>>(...) launches as function calls (kernels are plain functions on the software device).
 REF ?= /root/reference
 emu-reftests: $(EMU)/libacx_emu.so
 	@mkdir -p $(EMU)/reftests
 	for t in ring ring-all ring-all-device; do gcc -O1 -DDEBUG -Iinclude -I$(CUDA_HOME)/include $(REF)/test/src/$$t.c -o $(EMU)/reftests/$$t -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) || exit 1; done
 	for t in ring-all-graph ring-all-graph-construction; do $(CXX) -x c++ -O1 -DDEBUG -fpermissive -w -Iinclude -I$(CUDA_HOME)/include $(REF)/test/src/$$t.c -o $(EMU)/reftests/$$t -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) || exit 1; done
+	sed -E 's/([A-Za-z_][A-Za-z_0-9]*)<<<([^,>]*),([^,>]*),([^,>]*),([^,>]*)>>>\((.*)\);/emu::launch_user(\1, \2, \3, (cudaStream_t)(\5), \6);/' $(REF)/test/src/ring-partitioned.cu | \
+	  $(CXX) -x c++ -O1 -DDEBUG -fpermissive -w $(EMU_FLAGS) -include tests/emu/cuda_emu.h - -o $(EMU)/reftests/ring-partitioned -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) -lpthread   # kernel<<<...>>>(...) spelled as a function call on the fly
 
 $(EMU)/p2p_bench: bench/p2p_bench.cu $(EMU)/libacx_emu.so tests/emu/cuda_emu.h
 	$(CXX) -O1 $(EMU_FLAGS) $(EMU_SAN) -x c++ -include tests/emu/cuda_emu.h $< -o $@ -L$(EMU) -lacx_emu -Wl,-rpath,$(CURDIR)/$(EMU) -lpthread

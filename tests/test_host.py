@@ -290,14 +290,15 @@ def test_python_binding_on_software_device(built, np_):
 def test_reference_test_sources_pass_unmodified_on_software_device(built):
     """Drop-in compatibility: the reference's OWN test programs (test/src/ring*.c, read in place, nothing copied) compile
     unmodified against include/mpi.h + include/mpi-acx.h and pass on the device transport of the software CUDA device, at
-    1, 2 and 4 ranks — including its stream capture with pageable stack buffers and its explicit-graph composition."""
+    1, 2 and 4 ranks — all six: stream capture with pageable stack buffers, explicit-graph composition, and the partitioned
+    test with its two user kernels (their <<<>>> launches are spelled as function calls by sed at build time)."""
     ref = "/root/reference/test/src"
     if not os.path.exists(ref + "/ring.c"):
         pytest.skip("reference sources are not available on this machine")
     r = subprocess.run(["make", "-C", str(built), "-j4", "emu-lib", "emu-reftests"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
     env = {"ACX_MPI_NO_CUDA": "1"}
-    for prog in ("ring", "ring-all", "ring-all-device", "ring-all-graph", "ring-all-graph-construction"):
+    for prog in ("ring", "ring-all", "ring-all-device", "ring-all-graph", "ring-all-graph-construction", "ring-partitioned"):
         for np_ in (1, 2, 4):
             r = acxrun(built, np_, built / f"build/emu/reftests/{prog}", env=env)
             assert r.returncode == 0 and "rror" not in r.stdout, f"{prog} np={np_}: " + r.stdout[-1500:] + r.stderr[-1500:]
