@@ -98,6 +98,19 @@ if [ -x ${EMU_DIR:-build/emu}/p2p_bench ]; then
     fi
 fi
 
+# the reference's own, unmodified test programs (make emu-reftests), default and opt-in modes; success = exit code 0
+if [ -x ${EMU_DIR:-build/emu}/reftests/ring ]; then
+    for rt in ring ring-all ring-all-device ring-all-graph ring-all-graph-construction ring-partitioned; do
+        for cfg in "" "ACX_PEER_BRANCH=1" "ACX_SENDER_PUSH=1" "ACX_PBATCH=1 ACX_MEMOPS=1" "ACX_FAULT_DELAY_US=200"; do
+            [ "$mode" = quick ] && [ -n "$cfg" ] && continue
+            out=$(env $cfg timeout 200 bin/acxrun -np 3 --timeout 100 ${EMU_DIR:-build/emu}/reftests/$rt 2>&1); rc=$?
+            if echo "$out" | grep -qE "runtime error:|ERROR: AddressSanitizer|WARNING: ThreadSanitizer"; then rc=99; fi
+            if [ $rc -eq 0 ]; then printf "ok    %-24s np=3 %s\n" "reference:$rt" "${cfg:-default}"
+            else printf "FAIL  reference:%s np=3 %s rc=%d\n%s\n" $rt "${cfg:-default}" $rc "$(echo "$out" | tail -5)"; fails=$((fails+1)); fi
+        done
+    done
+fi
+
 # failure detection: a dropped send must end in the device watchdog (trap -> sticky launch failure -> diagnostic), not in a hang
 out=$(ACX_FAULT_DROP_SEND=1 ACX_WATCHDOG_MS=1500 timeout 100 bin/acxrun -np 1 --timeout 60 $T/ring 2>&1); rc=$?
 if [ $rc -ne 0 ] && echo "$out" | grep -q "WATCHDOG (code 0x5e04" && echo "$out" | grep -q "FAULT INJECTION"; then printf "ok    %-24s np=1 %-28s\n" ring watchdog-on-dropped-send
