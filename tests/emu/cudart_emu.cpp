@@ -140,6 +140,7 @@ Graph *clone_graph(const Graph *g) {
     for (auto &u : g->uobjs) { u.first->refs.fetch_add(u.second); c->uobjs.push_back(u); }
     return c;
 }
+void jitter();
 void run_graph(const Graph *g);
 void run_node(const Node *n) {
     if (emu::g_trapped.load()) return;
@@ -179,6 +180,7 @@ void run_graph(const Graph *g) {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { for (const Node *d : x->deps) if (!done[index.at(d)]) return false; return true; });
             }
+            jitter();
             run_node(x);
             { std::lock_guard<std::mutex> lk(mu); done[i] = 1; }
             cv.notify_all();
@@ -201,6 +203,18 @@ struct Capture {
     enum cudaStreamCaptureMode mode = cudaStreamCaptureModeGlobal;
     bool invalid = false;   // an unsafe call was made while it was in progress: cudaStreamEndCapture reports it
 };
+// ACX_EMU_JITTER_US=n: every stream operation and graph node starts after a pseudo-random 0..n us — the hardware gives no
+// promise about when a runnable kernel starts, and late starters are what slot- and buffer-reuse races need.
+void jitter() {
+    static const long max_us = env_long("ACX_EMU_JITTER_US", 0);
+    if (max_us <= 0) return;
+    static std::atomic<unsigned> seed{(unsigned)getpid() * 2654435761u};
+    unsigned x = seed.fetch_add(0x9e3779b9u);
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13;
+    if (x & 3) return;   // three out of four start at once: bursts of order changes, not uniform slowness
+    timespec ts{0, (long)(x % (unsigned)max_us) * 1000};
+    nanosleep(&ts, nullptr);
+}
 struct Stream {
     static constexpr size_t kMaxQueued = 192;
     unsigned flags = 0;
@@ -228,6 +242,7 @@ struct Stream {
                 t = std::move(q.front().second);
                 q.pop_front();
             }
+            jitter();
             t();
             {
                 std::lock_guard<std::mutex> lk(mu);

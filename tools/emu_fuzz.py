@@ -11,7 +11,7 @@ random.seed(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 600
 opts = [("ACX_COOP=1", "ACX_COOP_MIN_BYTES=65536"), ("ACX_PEER_BRANCH=1",), ("ACX_SENDER_PUSH=1",), ("ACX_PBATCH=1",), ("ACX_MEMOPS=1",), ("ACX_FUSE_RNDV=0",),
         ("ACX_SIDE_STREAMS=0",), ("ACX_FUSE_MIN_CTAS=1", "ACX_EMU_SMS=16"), ("ACX_MOVER=ldst256",), ("ACX_MOVER_BLOCK=4096",), ("ACX_REGCACHE=0",),
-        ("ACX_FAULT_DELAY_US=200",), ("ACX_NFLAGS=16",), ("ACX_EMU_MAX_BLOCK=32",), ("ACX_EMU_NO_HOSTREG_UVA=1",), ("ACX_PDL=0",), ("ACX_EMU_SMS=2",), ("ACX_WILDCARDS=1",), ("ACX_EAGER_MAX=512",), ("ACX_MOVER_CTA_BYTES=4096",), ("ACX_MOVER_MAX_CTAS=3",)]
+        ("ACX_FAULT_DELAY_US=200",), ("ACX_NFLAGS=16",), ("ACX_EMU_MAX_BLOCK=32",), ("ACX_EMU_NO_HOSTREG_UVA=1",), ("ACX_PDL=0",), ("ACX_EMU_SMS=2",), ("ACX_EMU_JITTER_US=300",), ("ACX_EMU_JITTER_US=2000",), ("ACX_WILDCARDS=1",), ("ACX_EAGER_MAX=512",), ("ACX_MOVER_CTA_BYTES=4096",), ("ACX_MOVER_MAX_CTAS=3",)]
 progs_extra = ["wildcards"]
 progs = "ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors sendrecv_enqueue stress".split()
 t0 = time.time(); runs = fails = 0

@@ -66,6 +66,7 @@ if [ "$mode" = full ]; then
     for p in ring ring_all status_errors; do run no-hostreg-uva 2 $p ACX_EMU_NO_HOSTREG_UVA=1; done
     for p in ring_all threads graph_large partitioned_device regcache; do run two-devices 2 $p ACX_EMU_DEVICES=2; done
     run three-devices 3 threads ACX_EMU_DEVICES=3
+    for p in stress threads graph_large large_msgs partitioned_device sendrecv_enqueue; do run device-jitter 3 $p ACX_EMU_JITTER_US=500; done
     run tiny-slots 2 stress ACX_NFLAGS=8
     run tiny-slots 2 threads ACX_NFLAGS=8
     run trace 2 ring ACX_TRACE=1 ACX_TRACE_DIR=/tmp
