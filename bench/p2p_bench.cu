@@ -19,6 +19,7 @@
 #define OK(x) do { int r_ = (x); if (r_) { fprintf(stderr, "[%d] %s:%d %s -> %d\n", g_rank, __FILE__, __LINE__, #x, r_); MPI_Abort(MPI_COMM_WORLD, 6); } } while (0)
 
 static int g_rank, g_size;
+static bool g_sendrecv = false;   // ring --sendrecv (acx-b200 only)
 // kernel<<<grid, block, 0, stream>>>(...); on the software CUDA device (tests/emu) kernels are plain functions and the
 // grid-stride helpers below run with a small geometry
 #ifdef ACX_EMU
@@ -82,6 +83,13 @@ static int run_ring(size_t bytes, int steps, int warmup, bool heap, bool e2e, bo
     auto step = [&](int tag) {
         MPIX_Request rq[2];
         if (e2e) CK(cudaMemcpyAsync(sbuf, h_in, bytes, cudaMemcpyHostToDevice, st));
+#ifndef ACX_BENCH_REFERENCE
+        if (g_sendrecv) {   // --sendrecv: the step as one MPIX_Sendrecv_enqueue (one kernel for eager sizes)
+            OK(MPIX_Sendrecv_enqueue(sbuf, (int)bytes, MPI_BYTE, right, tag, rbuf, (int)bytes, MPI_BYTE, left, tag, MPI_COMM_WORLD, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
+            if (e2e) CK(cudaMemcpyAsync(h_out, rbuf, d2h, cudaMemcpyDeviceToHost, st));
+            return;
+        }
+#endif
         OK(MPIX_Irecv_enqueue(rbuf, (int)bytes, MPI_BYTE, left, tag, MPI_COMM_WORLD, &rq[1], MPIX_QUEUE_CUDA_STREAM, &st));
         OK(MPIX_Isend_enqueue(sbuf, (int)bytes, MPI_BYTE, right, tag, MPI_COMM_WORLD, &rq[0], MPIX_QUEUE_CUDA_STREAM, &st));
         OK(MPIX_Waitall_enqueue(2, rq, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
@@ -326,6 +334,7 @@ int main(int argc, char **argv) {
         else if (a == "--e2e") e2e = true;
         else if (a == "--no-verify") verify = false;
         else if (a == "--prepost") prepost = true;
+        else if (a == "--sendrecv") g_sendrecv = true;
         else if (a == "--blocking") g_blocking = true;   // pingpong / pingpong_graph through MPIX_Send_enqueue / MPIX_Recv_enqueue (not in the reference build)
     }
     if (mode == "ring") rc = run_ring(bytes, steps, warmup, heap, e2e, verify, prepost);

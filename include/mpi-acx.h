@@ -99,6 +99,12 @@ int MPIX_Parrived_host(MPIX_Request *request, int partition, int *flag);
 int MPIX_Send_enqueue(const void *sendbuf, int nelems, MPI_Datatype dtype, int dst_rank, int tag, MPI_Comm comm, int queue_kind, void *queue_handle);
 int MPIX_Recv_enqueue(void *recvbuf, int nelems, MPI_Datatype dtype, int src_rank, int tag, MPI_Comm comm, MPI_Status *status, int queue_kind, void *queue_handle);
 
+/* MPI_Sendrecv on the queue: later work runs once the receive has completed and the send buffer may be reused. With both
+ * halves contiguous and of eager size the whole exchange step is ONE kernel (post the receive, deposit the send, complete
+ * the receive); otherwise it is the Irecv + Isend + Waitall triple. */
+int MPIX_Sendrecv_enqueue(const void *sendbuf, int sendcount, MPI_Datatype sendtype, int dst_rank, int sendtag, void *recvbuf, int recvcount, MPI_Datatype recvtype,
+                          int src_rank, int recvtag, MPI_Comm comm, MPI_Status *status, int queue_kind, void *queue_handle);
+
 /* Stream-ordered partitioned round control (the reference only has host Start/Wait):
  * enqueue the Start / the completion wait of a partitioned request on a stream. */
 int MPIX_Start_enqueue(MPIX_Request *request, int qtype, void *queue);

@@ -80,6 +80,7 @@ def lib() -> ctypes.CDLL:
         _lib.MPIX_Wait_enqueue.argtypes = [P(vp), P(MPIStatus), ci, vp]
         _lib.MPIX_Send_enqueue.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp]
         _lib.MPIX_Recv_enqueue.argtypes = [vp, ci, ci, ci, ci, ci, P(MPIStatus), ci, vp]
+        _lib.MPIX_Sendrecv_enqueue.argtypes = [vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, P(MPIStatus), ci, vp]
         _lib.MPIX_Waitall_enqueue.argtypes = [ci, P(vp), P(MPIStatus), ci, vp]
         _lib.MPIX_Wait.argtypes = [P(vp), P(MPIStatus)]
         _lib.MPIX_Waitall.argtypes = [ci, P(vp), P(MPIStatus)]

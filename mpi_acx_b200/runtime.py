@@ -236,6 +236,15 @@ def recv(t, source: int, tag: int = 0, stream=None) -> None:
     _ck(N.lib().MPIX_Recv_enqueue(p, n, dt, source, tag, N.MPI_COMM_WORLD, None, N.QUEUE_STREAM, ctypes.byref(cs)), "MPIX_Recv_enqueue")
 
 
+def sendrecv(send_t, dest: int, recv_t, source: int, tag: int = 0, stream=None) -> None:
+    """MPI_Sendrecv on the stream (MPIX_Sendrecv_enqueue): one call per exchange step; with small dense tensors on both
+    sides, one kernel (receive posted, send deposited, receive completed)."""
+    sp, sn, sdt = _typed_buf(send_t)
+    rp, rn, rdt = _typed_buf(recv_t)
+    cs = _stream_arg(stream)
+    _ck(N.lib().MPIX_Sendrecv_enqueue(sp, sn, sdt, dest, tag, rp, rn, rdt, source, tag, N.MPI_COMM_WORLD, None, N.QUEUE_STREAM, ctypes.byref(cs)), "MPIX_Sendrecv_enqueue")
+
+
 def waitall_enqueue(reqs: Iterable[Request], stream=None) -> None:
     reqs = list(reqs)
     arr = (ctypes.c_void_p * len(reqs))(*[r.h for r in reqs])

@@ -1978,6 +1978,142 @@ fail:
     return rc;
 }
 
+// explicit-graph mode: one graph that runs `first[0..nfirst)` (independent of each other), then `last`; the inputs are consumed
+static int compose_graphs(cudaGraph_t *first, int nfirst, cudaGraph_t last, cudaGraph_t *out) {
+    cudaGraph_t g = nullptr;
+    cudaGraphNode_t nodes[4], tail;
+    cudaError_t e = cudaGraphCreate(&g, 0);
+    for (int i = 0; i < nfirst && e == cudaSuccess; i++) e = cudaGraphAddChildGraphNode(&nodes[i], g, nullptr, 0, first[i]);
+    if (e == cudaSuccess) e = cudaGraphAddChildGraphNode(&tail, g, nodes, (size_t)nfirst, last);
+    for (int i = 0; i < nfirst; i++) cudaGraphDestroy(first[i]);   // the child nodes hold clones (with the slots' user objects)
+    cudaGraphDestroy(last);
+    if (e != cudaSuccess) { ACX_ERR("cannot compose the operation's graph: %s", cudaGetErrorString(e)); if (g) cudaGraphDestroy(g); return MPI_ERR_OTHER; }
+    *out = g;
+    return MPI_SUCCESS;
+}
+
+extern "C" int MPIX_Sendrecv_enqueue(const void *sendbuf, int sendcount, MPI_Datatype sendtype, int dest, int sendtag, void *recvbuf, int recvcount, MPI_Datatype recvtype,
+                                     int source, int recvtag, MPI_Comm comm, MPI_Status *status, int qtype, void *queue) {
+    AcxRange _r("MPIX_Sendrecv_enqueue");
+    bool fast = g_acx && g_acx->initialized && g_acx->device && qtype == MPIX_QUEUE_CUDA_STREAM && queue && dest >= 0 && source >= 0 && sendtag >= 0 && recvtag >= 0 &&
+                !g_branch && !g_fault_drop_send;
+    size_t sbytes = 0, rbytes = 0; int sctx = 0, rctx = 0, wdest = 0, wsource = 0;
+    AcxLayout sty, rty;
+    if (fast) {
+        MPIX_Request dummy = MPIX_REQUEST_NULL;
+        int rc = check_common("MPIX_Sendrecv_enqueue", false, sendcount, sendtype, dest, sendtag, comm, &dummy, queue, &sbytes, &sctx, &wdest, &sty);
+        if (!rc) rc = check_common("MPIX_Sendrecv_enqueue", true, recvcount, recvtype, source, recvtag, comm, &dummy, queue, &rbytes, &rctx, &wsource, &rty);
+        if (rc) return rc;
+        fast = !sty.noncontig && !rty.noncontig && sbytes <= g_acx->geom.eager_max && rbytes <= g_acx->geom.eager_max;
+    }
+    if (!fast) {
+        MPIX_Request rq[2] = {MPIX_REQUEST_NULL, MPIX_REQUEST_NULL};
+        MPI_Status sts[2];
+        if (qtype == MPIX_QUEUE_CUDA_GRAPH) {
+            cudaGraph_t parts[2] = {nullptr, nullptr}, gw = nullptr;
+            int rc = MPIX_Irecv_enqueue(recvbuf, recvcount, recvtype, source, recvtag, comm, &rq[0], qtype, &parts[0]);
+            if (rc) return rc;
+            rc = MPIX_Isend_enqueue(sendbuf, sendcount, sendtype, dest, sendtag, comm, &rq[1], qtype, &parts[1]);
+            if (rc) { cudaGraphDestroy(parts[0]); return rc; }
+            rc = MPIX_Waitall_enqueue(2, rq, status == MPI_STATUS_IGNORE ? MPI_STATUSES_IGNORE : sts, qtype, &gw);
+            if (rc) { cudaGraphDestroy(parts[0]); cudaGraphDestroy(parts[1]); return rc; }
+            if (status != MPI_STATUS_IGNORE) ACX_LOG(1, "MPIX_Sendrecv_enqueue in explicit-graph mode fills no status (the graph outlives the call)");
+            return compose_graphs(parts, 2, gw, (cudaGraph_t *)queue);
+        }
+        int rc = MPIX_Irecv_enqueue(recvbuf, recvcount, recvtype, source, recvtag, comm, &rq[0], qtype, queue);
+        if (rc) return rc;
+        rc = MPIX_Isend_enqueue(sendbuf, sendcount, sendtype, dest, sendtag, comm, &rq[1], qtype, queue);
+        if (rc) return rc;
+        if (status == MPI_STATUS_IGNORE) return MPIX_Waitall_enqueue(2, rq, MPI_STATUSES_IGNORE, qtype, queue);
+        // the receive's status goes to the caller's word; the send's has no taker
+        rc = MPIX_Wait_enqueue(&rq[0], status, qtype, queue);
+        if (rc) return rc;
+        return MPIX_Wait_enqueue(&rq[1], MPI_STATUS_IGNORE, qtype, queue);
+    }
+    AcxRequest *r = new_request(ACX_REQ_RECV, wsource, recvtag, rctx, rbytes, recvbuf);
+    r->comm_peer = source;
+    Emitter em;
+    int rc = em.begin(qtype, queue);
+    if (rc) { delete r; return rc; }
+    r->in_graph = em.in_graph();
+    r->stream = em.stream;
+    r->chan = chan_of(recvtag, rctx);
+    if (!r->in_graph) {
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        if (g_acx->recv_outstanding[wsource][r->chan] >= g_acx->geom.depth) {
+            ACX_ERR("more than ACX_DEPTH=%d receives outstanding from rank %d on the channel of tag %d", g_acx->geom.depth, wsource, recvtag);
+            delete r;
+            return MPI_ERR_OTHER;
+        }
+    }
+    if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
+    char *send_alias = nullptr;
+    if ((rc = acx_device_alias(recvbuf, rbytes, &r->dev_buf)) || (rc = acx_device_alias(sendbuf, sbytes, &send_alias))) goto fail;
+    fault_delay();
+    {
+        const acx_geom &G = g_acx->geom;
+        r->heap_off = acx_heap_offset_of(recvbuf);
+        const int schan = chan_of(sendtag, sctx);
+        // receive half (as MPIX_Recv_enqueue)
+        const uint64_t rring = acx_entry_index(G, wsource, r->chan, 0), rsack = acx_entry_index(G, g_acx->rank, r->chan, 0);
+        RecvParams rp;
+        memset(&rp, 0, sizeof rp);
+        rp.ring = acx_entries_of(g_acx->ctrl) + rring;
+        rp.seq = (uint64_t *)(g_acx->ctrl + G.off_recv_seq) + ((uint64_t)wsource * G.nchan + r->chan);
+        rp.op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
+        rp.sack = acx_sacks_of(g_acx->peer_ctrl[wsource]) + rsack;
+        rp.peer_heap = g_acx->peer_heap[wsource];
+        rp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)wsource * G.maxreg;
+        rp.dst_off = ~0ull; rp.cap = rbytes; rp.serial = r->serial; rp.depth = G.depth; rp.peer = wsource;
+        rp.rndv_capable = 0; rp.publish = g_apush ? 1 : 0;
+        rp.wd = make_wd(); rp.tr = make_tr();
+        // send half: eager only, so it owns no op record and retires nothing (the kernel's end is its completion)
+        const uint64_t sring = acx_entry_index(G, g_acx->rank, schan, 0), ssack = acx_entry_index(G, wdest, schan, 0);
+        SendParams sp;
+        memset(&sp, 0, sizeof sp);
+        sp.ring = acx_entries_of(g_acx->peer_ctrl[wdest]) + sring;
+        sp.eager = g_acx->peer_ctrl[wdest] + G.off_eager + sring * G.eager_max;
+        sp.sack = acx_sacks_of(g_acx->ctrl) + ssack;
+        sp.seq = (uint64_t *)(g_acx->ctrl + G.off_send_seq) + ((uint64_t)wdest * G.nchan + schan);
+        sp.op = nullptr; sp.hstat = nullptr;
+        sp.src = send_alias; sp.peer_heap = g_acx->peer_heap[wdest];
+        sp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)wdest * G.maxreg;
+        sp.src_off = ~0ull; sp.bytes = sbytes; sp.serial = 0;
+        sp.tag = (uint32_t)sendtag; sp.depth = G.depth; sp.eager_max = G.eager_max; sp.peer = wdest;
+        sp.wd = make_wd(); sp.tr = make_tr();
+        WaitBatch wb;
+        memset(&wb, 0, sizeof wb);
+        const bool retire = !em.in_graph();
+        if ((rc = fill_wait(r, status, retire, false, &wb.w[0]))) goto fail;
+        wb.wd = make_wd(); wb.tr = make_tr();
+        void *args[] = {&sp, &rp, &wb};
+        cudaError_t le;
+        if (g_pdl && !em.capturing) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(1); cfg.blockDim = dim3(kWaitThreads); cfg.stream = em.stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            le = cudaLaunchKernelExC(&cfg, (const void *)sendrecv_fused, args);
+        } else le = cudaLaunchKernel((const void *)sendrecv_fused, dim3(1), dim3(kWaitThreads), args, 0, em.stream);
+        if (le != cudaSuccess) { report_watchdog(); ACX_ERR("kernel launch failed: %s", cudaGetErrorString(le)); rc = MPI_ERR_OTHER; goto fail; }
+        g_acx->st.kernels++;
+        if (em.capturing) g_acx->st.graph_nodes++;
+    }
+    if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        if (!em.in_graph()) { g_acx->slot_busy[r->slot] = 3; g_pending_retire.push_back(r->slot); }
+    }
+    g_acx->st.sends++; g_acx->st.bytes_sent += sbytes; g_acx->st.eager++;
+    g_acx->st.recvs++; g_acx->st.bytes_recv += rbytes; g_acx->st.waits += 2;
+    return MPI_SUCCESS;
+fail:
+    { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); acx_slot_free(r->slot); }
+    return rc;
+}
+
 // ---- partitioned: forward declarations ----
 static int pwait_host(AcxRequest *r, MPI_Status *status);
 static int pwait_emit(AcxRequest *r, cudaStream_t stream);
@@ -2440,7 +2576,7 @@ extern "C" int MPIX_Parrived_host(MPIX_Request *request, int partition, int *fla
 // their argument lists. All of them are written for any blockDim (second argument), so the emulation may shrink blocks.
 ACX_EMU_KERNEL(copy_kernel, true) ACX_EMU_KERNEL(send_trigger, true) ACX_EMU_KERNEL(recv_trigger, true) ACX_EMU_KERNEL(push_gate, true)
 ACX_EMU_KERNEL(mover, true) ACX_EMU_KERNEL(send_rndv_fused, true) ACX_EMU_KERNEL(recv_rndv_fused, true) ACX_EMU_KERNEL(recv_any_kernel, true)
-ACX_EMU_KERNEL(coop_gate, true) ACX_EMU_KERNEL(coop_kernel, true) ACX_EMU_KERNEL(wait_kernel, true) ACX_EMU_KERNEL(recv_wait_fused, true) ACX_EMU_KERNEL(bounce_out_kernel, true)
+ACX_EMU_KERNEL(coop_gate, true) ACX_EMU_KERNEL(coop_kernel, true) ACX_EMU_KERNEL(wait_kernel, true) ACX_EMU_KERNEL(recv_wait_fused, true) ACX_EMU_KERNEL(sendrecv_fused, true) ACX_EMU_KERNEL(bounce_out_kernel, true)
 ACX_EMU_KERNEL(pack_kernel, true) ACX_EMU_KERNEL(unpack_kernel, true) ACX_EMU_KERNEL(pstart_kernel, true) ACX_EMU_KERNEL(pstart_batch_kernel, true)
 ACX_EMU_KERNEL(pwait_kernel, true) ACX_EMU_KERNEL(pwait_batch_kernel, true) ACX_EMU_KERNEL(pready_host_kernel, true) ACX_EMU_KERNEL(parrived_host_kernel, true)
 #endif

@@ -165,8 +165,7 @@ __device__ __forceinline__ void send_rndv_match(const SendParams &p, uint64_t k)
     trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes | (1ull << 63));
 }
 
-__global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
-    pdl_prologue();
+__device__ __forceinline__ void send_body(const SendParams &p) {
     __shared__ uint64_t s_k;
     const unsigned tid = threadIdx.x;
     if (tid == 0) {
@@ -196,6 +195,10 @@ __global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
     } else if (tid == 0) {
         send_rndv_match(p, k);
     }
+}
+__global__ void __launch_bounds__(kTriggerThreads) send_trigger(SendParams p) {
+    pdl_prologue();
+    send_body(p);
 }
 // ---------------------------------------------------------------------------------------
 // RECV trigger: take a ticket, publish destination, add to the state word.
@@ -809,6 +812,16 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
 __global__ void __launch_bounds__(kWaitThreads) recv_wait_fused(RecvParams rp, WaitBatch b) {
     pdl_prologue();
     if (threadIdx.x == 0) recv_match(rp);
+    __syncthreads();
+    wait_body(b, b.w[0]);
+}
+// MPIX_Sendrecv_enqueue for eager sizes on both halves: the whole exchange step — post the receive, deposit the send,
+// complete the receive — in ONE launch (a ring or halo step with small messages costs three launches otherwise).
+__global__ void __launch_bounds__(kWaitThreads) sendrecv_fused(SendParams sp, RecvParams rp, WaitBatch b) {
+    pdl_prologue();
+    if (threadIdx.x == 0) recv_match(rp);
+    __syncthreads();
+    send_body(sp);          // eager: never waits for the peer beyond the slot credit
     __syncthreads();
     wait_body(b, b.w[0]);
 }

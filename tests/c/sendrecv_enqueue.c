@@ -136,9 +136,84 @@ static void in_graphs(void) {
     cudaFreeHost(send); cudaFreeHost(recv);
 }
 
+/* MPIX_Sendrecv_enqueue: a whole exchange step in one call — and, for small contiguous messages, one kernel. */
+static void sendrecv_steps(void) {
+    cudaStream_t st = 0;
+    int bad = 0;
+    static int out[2048], in[2048];   /* 8 KiB: the eager limit */
+    const int k0 = kernels_launched();
+    for (int it = 0; it < 70; it++) {   /* > ACX_DEPTH: ring slots wrap */
+        const int n = 1 + (it % 7) * 300;   /* 4 B .. 7.2 KB */
+        MPI_Status status;
+        for (int i = 0; i < n; i++) { out[i] = t_rank * 100000 + it * 1000 + i; in[i] = -1; }
+        T_OK(MPIX_Sendrecv_enqueue(out, n, MPI_INT, T_RIGHT, 12, in, 2048, MPI_INT, T_LEFT, 12, MPI_COMM_WORLD, &status, MPIX_QUEUE_CUDA_STREAM, &st));
+        if (t_gpu) T_CUDA(cudaStreamSynchronize(st));
+        int cnt = -1;
+        MPI_Get_count(&status, MPI_INT, &cnt);
+        if (cnt != n || status.MPI_SOURCE != T_LEFT || status.MPI_TAG != 12) bad++;
+        for (int i = 0; i < n; i++) if (in[i] != T_LEFT * 100000 + it * 1000 + i) { bad++; break; }
+    }
+    T_CHECK(bad == 0, "sendrecv steps: %d bad iterations", bad);
+    if (t_gpu && !getenv("ACX_PEER_BRANCH")) T_CHECK(kernels_launched() - k0 == 70, "an eager exchange step should be ONE launch, measured %d for 70", kernels_launched() - k0);
+    /* large halves (rendezvous): the general path underneath; both directions at once cannot deadlock (receive posted first) */
+    {
+        const size_t n = 150000;
+        unsigned char *o, *i_, *h = (unsigned char *)malloc(n);
+        T_OK(MPIX_Alloc_mem(n, MPI_INFO_NULL, &o)); T_OK(MPIX_Alloc_mem(n, MPI_INFO_NULL, &i_));
+        for (size_t i = 0; i < n; i++) h[i] = pat(i, t_rank + 9);
+        if (t_gpu) T_CUDA(cudaMemcpy(o, h, n, cudaMemcpyHostToDevice)); else memcpy(o, h, n);
+        T_OK(MPIX_Sendrecv_enqueue(o, (int)n, MPI_BYTE, T_RIGHT, 13, i_, (int)n, MPI_BYTE, T_LEFT, 13, MPI_COMM_WORLD, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
+        if (t_gpu) { T_CUDA(cudaStreamSynchronize(st)); T_CUDA(cudaMemcpy(h, i_, n, cudaMemcpyDeviceToHost)); } else memcpy(h, i_, n);
+        size_t wrong = 0;
+        for (size_t i = 0; i < n; i++) if (h[i] != pat(i, T_LEFT + 9)) wrong++;
+        T_CHECK(wrong == 0, "large sendrecv: %zu wrong bytes", wrong);
+        T_OK(MPIX_Free_mem(o)); T_OK(MPIX_Free_mem(i_)); free(h);
+    }
+    /* one half MPI_PROC_NULL (an open chain instead of a ring): rank 0 receives from nobody, the last rank sends to nobody */
+    {
+        int v = 1000 + t_rank, w = -1;
+        MPI_Status status;
+        const int to = t_rank + 1 < t_size ? t_rank + 1 : MPI_PROC_NULL, from = t_rank > 0 ? t_rank - 1 : MPI_PROC_NULL;
+        T_OK(MPIX_Sendrecv_enqueue(&v, 1, MPI_INT, to, 14, &w, 1, MPI_INT, from, 14, MPI_COMM_WORLD, &status, MPIX_QUEUE_CUDA_STREAM, &st));
+        if (t_gpu) T_CUDA(cudaStreamSynchronize(st));
+        T_CHECK(t_rank == 0 ? (w == -1 && status.MPI_SOURCE == MPI_PROC_NULL) : (w == 1000 + t_rank - 1 && status.MPI_SOURCE == t_rank - 1), "chain with MPI_PROC_NULL ends: got %d from %d", w, status.MPI_SOURCE);
+    }
+    if (!t_gpu) return;
+    /* in a captured graph, relaunched 40 trips round the ring; and as an explicit graph */
+    int *send, *recv;
+    T_CUDA(cudaMallocHost((void **)&send, sizeof(int)));
+    T_CUDA(cudaMallocHost((void **)&recv, sizeof(int)));
+    cudaStream_t stream;
+    T_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (int mode = 0; mode < 2; mode++) {
+        cudaGraph_t graph;
+        cudaGraphExec_t exec;
+        *send = 800 + t_rank + 50 * mode; *recv = -1;
+        if (mode == 0) {
+            T_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeGlobal));
+            T_OK(MPIX_Sendrecv_enqueue(send, 1, MPI_INT, T_RIGHT, 15, recv, 1, MPI_INT, T_LEFT, 15, MPI_COMM_WORLD, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &stream));
+            T_CUDA(cudaStreamEndCapture(stream, &graph));
+        } else {
+            T_OK(MPIX_Sendrecv_enqueue(send, 1, MPI_INT, T_RIGHT, 16, recv, 1, MPI_INT, T_LEFT, 16, MPI_COMM_WORLD, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_GRAPH, &graph));
+        }
+        T_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        for (int hop = 0; hop < 40 * t_size; hop++) {
+            T_CUDA(cudaGraphLaunch(exec, stream));
+            T_CUDA(cudaMemcpyAsync(send, recv, sizeof(int), cudaMemcpyHostToHost, stream));
+        }
+        T_CUDA(cudaStreamSynchronize(stream));
+        T_CHECK(*recv == 800 + t_rank + 50 * mode, "sendrecv in a graph (mode %d): token came back as %d", mode, *recv);
+        T_CUDA(cudaGraphExecDestroy(exec));
+        T_CUDA(cudaGraphDestroy(graph));
+    }
+    T_CUDA(cudaStreamDestroy(stream));
+    cudaFreeHost(send); cudaFreeHost(recv);
+}
+
 int main(int argc, char **argv) {
     t_init(&argc, &argv, 0);
     token_ring();
+    sendrecv_steps();
     payloads();
     odds_and_ends();
     if (t_gpu) in_graphs();

@@ -33,6 +33,18 @@ for numel in (5, 3000, 200000):
         acx.recv(d, left, 3); acx.send(s, right, 3)
     acx.synchronize()
     assert torch.equal(d, torch.arange(numel, dtype=torch.float32) + left), numel
+# one-call exchange step (one fused kernel for small dense tensors)
+a_, b_ = torch.full((100,), float(r)), torch.zeros(100)
+k0 = acx.stats()["kernels_launched"]
+acx.sendrecv(a_, right, b_, left, tag=8)
+acx.synchronize()
+assert bool((b_ == float(left)).all()) and acx.stats()["kernels_launched"] - k0 == 1
+# one-call exchange step (one fused kernel for small dense tensors)
+a_, b_ = torch.full((100,), float(r)), torch.zeros(100)
+k0 = acx.stats()["kernels_launched"]
+acx.sendrecv(a_, right, b_, left, tag=8)
+acx.synchronize()
+assert bool((b_ == float(left)).all()) and acx.stats()["kernels_launched"] - k0 == 1
 # parallel/: pre-posted double-buffered ring (what bench.py runs from 3 GPUs up), all-pairs exchange, partitioned pipeline link
 from mpi_acx_b200.parallel import ring as pring
 from mpi_acx_b200.parallel.pipeline import PartitionedLink

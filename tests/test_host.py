@@ -120,6 +120,9 @@ tok, got = torch.full((5,), float(r)), torch.zeros(5)
 acx.send(tok, right, tag=12)
 acx.recv(got, left, tag=12)
 assert bool((got == float(left)).all())
+got.zero_()
+acx.sendrecv(tok, right, got, left, tag=13)
+assert bool((got == float(left)).all())
 acx.finalize()
 print("OK", r)
 """

@@ -86,6 +86,7 @@ if [ -x ${EMU_DIR:-build/emu}/p2p_bench ]; then
     bench 2 ring --bytes 1048576 --steps 3 --warmup 3
     bench 3 ring --bytes 300000 --steps 3 --warmup 3 --prepost
     bench 2 pingpong --max 131072 --iters 6 --blocking
+    bench 3 ring --bytes 4096 --steps 5 --warmup 3 --sendrecv
     bench 3 allpairs --bytes 100000 --steps 3 --warmup 2
     if [ "$mode" = full ]; then
         bench 2 ring --bytes 262144 --steps 3 --warmup 3 --e2e

@@ -43,6 +43,7 @@ for br in 0 1; do echo "pingpong branch=$br: $(ACX_PEER_BRANCH=$br timeout 120 .
 echo "### 3'. MPIX_Send_enqueue / MPIX_Recv_enqueue (eager receive = one fused post+wait kernel: 2 launches per ping-pong iteration instead of 3)"
 for np in 1 $NP; do timeout 90 ./bin/acxrun -np $np --timeout 80 build/tests/sendrecv_enqueue 2>&1 | tail -n 2; done
 for bl in "" "--blocking"; do echo "pingpong $bl: $(timeout 120 ./bin/acxrun -np 2 --timeout 100 bin/p2p_bench pingpong --max 65536 $bl 2>&1 | tail -n 1 | cut -c1-500)"; done
+for sr in "" "--sendrecv"; do for b in 8 4096; do echo "ring $b B $sr: $(run bin/p2p_bench ring --bytes $b --steps 200 --warmup 20 $sr | tail -n 1 | cut -c1-200)"; done; done
 for bl in "" "--blocking"; do echo "pingpong_graph $bl: $(timeout 120 ./bin/acxrun -np 2 --timeout 100 bin/p2p_bench pingpong_graph --max 65536 $bl 2>&1 | tail -n 1 | cut -c1-500)"; done
 
 echo "### 3a. ACX_COOP=1 (cooperative moving with chunk stealing): conformance, then the ring in 'simple' order (no pre-posting) against the default"
