@@ -297,3 +297,13 @@ def test_blocking_send_recv_enqueue(built, np_):
     r = acxrun(built, np_, built / "build/tests/sendrecv_enqueue")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("prog", ["stress", "ordering", "large_msgs"])
+def test_second_arriver_logic_under_arrival_jitter(built, prog):
+    """ACX_FAULT_DELAY_US=200: a pseudo-random host delay before every send / receive is enqueued, so both arrival orders of
+    the rendezvous (sender second -> push, receiver second -> pull) occur in one run on hardware."""
+    args = ["16777216"] if prog == "large_msgs" else []
+    r = acxrun(built, 2, built / f"build/tests/{prog}", *args, env={"ACX_FAULT_DELAY_US": "200"}, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout
