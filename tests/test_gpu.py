@@ -307,3 +307,12 @@ def test_second_arriver_logic_under_arrival_jitter(built, prog):
     r = acxrun(built, 2, built / f"build/tests/{prog}", *args, env={"ACX_FAULT_DELAY_US": "200"}, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_reinitialization(built, np_):
+    """MPIX_Init / MPIX_Finalize twice in one process with eager, rendezvous (heap and private buffers), partitioned and
+    captured-graph traffic in both sessions — tests/c/reinit.c."""
+    r = acxrun(built, np_, built / "build/tests/reinit")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout
