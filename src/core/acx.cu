@@ -456,6 +456,11 @@ static void reg_init() {
     g_cuMemGetAddressRange = (cuMemGetAddressRangeFn)f1;
     g_cuPointerGetAttribute = (cuPointerGetAttributeFn)f2;
     g_reg_tables = (AcxRegTable *)scratch;   // zero-initialised by the job's rank 0 before anyone runs
+    {   // a re-initialization starts from an empty table (MPIX_Init ends with a barrier: nobody reads mine before that)
+        AcxRegTable *mine = g_reg_tables + g_acx->rank;
+        mine->count.store(0, std::memory_order_relaxed);
+        for (auto &row : mine->ack) for (auto &a : row) a.store(0, std::memory_order_relaxed);
+    }
     g_reg_seen.assign(g_acx->size, 0);
     g_reg_on = true;
 }
