@@ -264,6 +264,23 @@ def wait(req: Request) -> dict:
     return {"source": st.MPI_SOURCE, "tag": st.MPI_TAG, "error": st.MPI_ERROR, "bytes": st._bytes}
 
 
+def waitall(reqs: Iterable[Request]) -> list:
+    """Host-blocking MPIX_Waitall (include/mpi-acx.h; the reference's loop over MPIX_Wait, src/sendrecv.cu:642-651):
+    returns one status dict per request and nulls the handles."""
+    reqs = list(reqs)
+    arr = (ctypes.c_void_p * len(reqs))(*[r.h for r in reqs])
+    sts = (N.MPIStatus * len(reqs))()
+    _ck(N.lib().MPIX_Waitall(len(reqs), arr, sts), "MPIX_Waitall")
+    for r in reqs:
+        r.h = ctypes.c_void_p()
+    return [{"source": st.MPI_SOURCE, "tag": st.MPI_TAG, "error": st.MPI_ERROR, "bytes": st._bytes} for st in sts]
+
+
+def trace_dump(path: str) -> None:
+    """Write this rank's device trace ring (ACX_TRACE=1) as JSON lines; tools/trace_to_chrome.py merges the ranks."""
+    _ck(N.lib().MPIX_Trace_dump(str(path).encode()), "MPIX_Trace_dump")
+
+
 # ---- partitioned ----------------------------------------------------------------------------
 class PartitionedRequest:
     """Persistent partitioned channel endpoint; `.prequest` is the device handle (int) that

@@ -73,5 +73,12 @@ if n > 1:   # activations flow rank 0 -> 1 -> ... over persistent partitioned ch
         if r > 0:
             assert bool((act_in == float(10 * (r - 1) + rnd)).all()), rnd
     link.free()
+# host-blocking waitall with statuses: eager and rendezvous sizes, heap and private buffers
+for nel, mk in ((16, torch.zeros), (40000, torch.zeros), (40000, lambda k, dtype: acx.empty(k, dtype))):
+    sb, rb = mk(nel, dtype=torch.int32), mk(nel, dtype=torch.int32)
+    sb.fill_(7 + r); rb.zero_()
+    sts = acx.waitall([acx.irecv(rb, left, tag=8), acx.isend(sb, (r + 1) % n, tag=8)])
+    assert sts[0]["source"] == left and sts[0]["tag"] == 8 and sts[0]["bytes"] == 4 * nel and sts[0]["error"] == 0, sts
+    assert bool((rb == 7 + left).all())
 print("PY-EMU OK", r, acx.stats()["kernels_launched"])
 acx.finalize()

@@ -123,6 +123,14 @@ assert bool((got == float(left)).all())
 got.zero_()
 acx.sendrecv(tok, right, got, left, tag=13)
 assert bool((got == float(left)).all())
+# host-blocking waits with statuses (MPIX_Wait / MPIX_Waitall)
+a8, b8 = torch.full((8,), float(r)), torch.zeros(8)
+sts = acx.waitall([acx.irecv(b8, left, tag=14), acx.isend(a8, right, tag=14)])
+assert sts[0]["source"] == left and sts[0]["tag"] == 14 and sts[0]["bytes"] == 32 and sts[0]["error"] == 0, sts
+assert bool((b8 == float(left)).all())
+q = [acx.irecv(b8, left, tag=15), acx.isend(a8 + 1, right, tag=15)]
+st = acx.wait(q[0]); acx.wait(q[1])
+assert st["source"] == left and st["tag"] == 15 and bool((b8 == float(left) + 1).all())
 acx.finalize()
 print("OK", r)
 """
