@@ -4,6 +4,10 @@
 NVCC      ?= nvcc
 CXX       ?= g++
 GENCODE   ?= -gencode arch=compute_100a,code=sm_100a
+# the reference's spelling of the same knob (reference Makefile:3, README.md:75-81); anything but sm_100a will not compile (tcgen05 / TMA PTX)
+ifdef NVCC_GENCODE
+GENCODE := $(NVCC_GENCODE)
+endif
 NVCCFLAGS ?= $(GENCODE) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter -Iinclude
 CXXFLAGS  ?= -O2 -std=c++17 -fPIC -Wall -Wextra -Iinclude
 B := build
