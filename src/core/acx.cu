@@ -651,7 +651,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_WATCHDOG_MS", nullptr, 0, &v); g_acx->watchdog_ms = v;
     acx_env_int("ACX_NVTX", nullptr, 0, &v); g_nvtx = v != 0;
     if (getenv("MPIACX_DISABLE_MEMOPS")) ACX_LOG(1, "MPIACX_DISABLE_MEMOPS: stream memOps stay off (they are opt-in here: ACX_MEMOPS=1, partitioned Start / Wait only)");
-    { const char *m = getenv("ACX_MOVER"); g_mover_tma = m && !strcmp(m, "tma"); g_mover_256 = m && !strcmp(m, "ldst256"); }
+    { const char *m = getenv("ACX_MOVER"); g_mover_tma = m && !strcmp(m, "tma"); g_mover_256 = !m ? 0 : !strcmp(m, "ldst256") ? 1 : !strcmp(m, "ldstcs") ? 2 : 0; }   // copy-loop flavour, see copy_flavour()
 #ifdef ACX_EMU
     g_mover_tma = 0;
 #endif
@@ -1093,7 +1093,7 @@ static int launch_mover(Emitter &em, MoverParams &mp, size_t bytes) {
         grid = (int)std::max<size_t>(1, std::min<size_t>(g, (size_t)4 * g_acx->sm_count));
         if (!mp.block_bytes) mp.block_bytes = 128u << 10;
     }
-    return em.launch(mover, dim3(grid), dim3(kMoverThreads), mp);
+    return em.launch(g_coop ? mover : g_mover_256 == 1 ? mover_v256 : g_mover_256 == 2 ? mover_cs : mover_plain, dim3(grid), dim3(kMoverThreads), mp);
 }
 
 // Whole-operation branching (ACX_PEER_BRANCH=1): every kernel of an operation with peer p — bounce-in copy, trigger,
@@ -2580,7 +2580,7 @@ extern "C" int MPIX_Parrived_host(MPIX_Request *request, int partition, int *fla
 // Software device (tests/emu): kernels are plain functions; tell its cudaLaunchKernel / cudaGraphAddKernelNode about
 // their argument lists. All of them are written for any blockDim (second argument), so the emulation may shrink blocks.
 ACX_EMU_KERNEL(copy_kernel, true) ACX_EMU_KERNEL(send_trigger, true) ACX_EMU_KERNEL(recv_trigger, true) ACX_EMU_KERNEL(push_gate, true)
-ACX_EMU_KERNEL(mover, true) ACX_EMU_KERNEL(send_rndv_fused, true) ACX_EMU_KERNEL(recv_rndv_fused, true) ACX_EMU_KERNEL(recv_any_kernel, true)
+ACX_EMU_KERNEL(mover, true) ACX_EMU_KERNEL(mover_plain, true) ACX_EMU_KERNEL(mover_v256, true) ACX_EMU_KERNEL(mover_cs, true) ACX_EMU_KERNEL(send_rndv_fused, true) ACX_EMU_KERNEL(recv_rndv_fused, true) ACX_EMU_KERNEL(recv_any_kernel, true)
 ACX_EMU_KERNEL(coop_gate, true) ACX_EMU_KERNEL(coop_kernel, true) ACX_EMU_KERNEL(wait_kernel, true) ACX_EMU_KERNEL(recv_wait_fused, true) ACX_EMU_KERNEL(sendrecv_fused, true) ACX_EMU_KERNEL(bounce_out_kernel, true)
 ACX_EMU_KERNEL(pack_kernel, true) ACX_EMU_KERNEL(unpack_kernel, true) ACX_EMU_KERNEL(pstart_kernel, true) ACX_EMU_KERNEL(pstart_batch_kernel, true)
 ACX_EMU_KERNEL(pwait_kernel, true) ACX_EMU_KERNEL(pwait_batch_kernel, true) ACX_EMU_KERNEL(pready_host_kernel, true) ACX_EMU_KERNEL(parrived_host_kernel, true)

@@ -99,6 +99,36 @@ __device__ __forceinline__ void copy_bytes_256(char *dst, const char *src, uint6
     if (done < n) copy_bytes(dst + done, src + done, n - done, tid, nthr);
 }
 
+// Streaming flavour (ACX_MOVER=ldstcs): ld.global.cs / st.global.cs mark every line evict-first, for copies whose
+// working set is far beyond L2 (the 1-GPU self-transfer is HBM-bound: nothing it touches is read again).
+#ifdef ACX_EMU
+__device__ __forceinline__ int4 ld_cs(const int4 *p) { return *p; }
+__device__ __forceinline__ void st_cs(int4 *p, int4 v) { *p = v; }
+#else
+__device__ __forceinline__ int4 ld_cs(const int4 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_cs(int4 *p, int4 v) { __stcs(p, v); }
+#endif
+__device__ __forceinline__ void copy_bytes_cs(char *dst, const char *src, uint64_t n, unsigned tid, unsigned nthr) {
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) != 0) { copy_bytes(dst, src, n, tid, nthr); return; }
+    const uint64_t nv = n >> 4;
+    const int4 *s = (const int4 *)src;
+    int4 *d = (int4 *)dst;
+    uint64_t i = tid;
+    for (; i + 3ull * nthr < nv; i += 4ull * nthr) {
+        int4 a = ld_cs(s + i), b = ld_cs(s + i + nthr), c = ld_cs(s + i + 2ull * nthr), e = ld_cs(s + i + 3ull * nthr);
+        st_cs(d + i, a); st_cs(d + i + nthr, b); st_cs(d + i + 2ull * nthr, c); st_cs(d + i + 3ull * nthr, e);
+    }
+    for (; i < nv; i += nthr) st_cs(d + i, ld_cs(s + i));
+    const uint64_t done = nv << 4;
+    if (done < n) copy_bytes(dst + done, src + done, n - done, tid, nthr);
+}
+// Copy-loop flavour of the LDG/STG movers: 0 = 16-B vectors, 1 = 256-bit vectors, 2 = 16-B streaming.
+__device__ __forceinline__ void copy_flavour(uint32_t flavour, char *dst, const char *src, uint64_t n, unsigned tid, unsigned nthr) {
+    if (flavour == 1) copy_bytes_256(dst, src, n, tid, nthr);
+    else if (flavour == 2) copy_bytes_cs(dst, src, n, tid, nthr);
+    else copy_bytes(dst, src, n, tid, nthr);
+}
+
 // ---------------------------------------------------------------------------------------
 // Plain copy (bounce-in for private send buffers). Grid-stride, 16-B vectors.
 // ---------------------------------------------------------------------------------------
@@ -274,7 +304,7 @@ struct MoverParams {
     char *local;            // push: local source; pull: local destination
     acx_entry *ring;        // push: peer-mapped ring; pull: local ring
     acx_sack *sack;         // push: local sack; pull: peer-mapped sack at the sender
-    uint32_t depth, push, peer, vec256;
+    uint32_t depth, push, peer, vec256;   // vec256: copy-loop flavour (copy_flavour)
     uint32_t block_bytes, pad1;   // 0: one contiguous chunk per CTA; else CTAs sweep interleaved blocks of this size (DRAM-page friendly)
     TraceCtx tr;
 };
@@ -331,8 +361,7 @@ __device__ __forceinline__ void coop_agent(acx_entry *ent, acx_sack *sk, char *d
         __syncthreads();
         if (i >= C) return;
         const uint64_t lo = i * cb, len = n - lo < cb ? n - lo : cb;
-        if (vec256) copy_bytes_256(dst + lo, src + lo, len, threadIdx.x, blockDim.x);
-        else copy_bytes(dst + lo, src + lo, len, threadIdx.x, blockDim.x);
+        copy_flavour(vec256, dst + lo, src + lo, len, threadIdx.x, blockDim.x);
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();
@@ -344,13 +373,21 @@ __device__ __forceinline__ void coop_agent(acx_entry *ent, acx_sack *sk, char *d
     }
 }
 
-__device__ __forceinline__ void mover_body(const MoverParams &p) {
+// FL >= 0: one copy-loop flavour, no cooperative moving, compiled on its own — 64 registers, no spills, two 512-thread
+// CTAs per SM (what a bandwidth-sized grid needs: the copy is latency-bound, profiles/mover_ncu.md). FL < 0: the general
+// body (run-time flavour + the chunk-stealing agent), 108-112 registers = one CTA per SM — fine for the 8-32-CTA fused
+// kernels and the cooperative mode, and what the plain mover had silently become once the 256-bit loop was added.
+template <int FL>
+__device__ __forceinline__ void mover_body_t(const MoverParams &p) {
     acx_op *op = p.op;
     if (!op->mover) return;
     const uint64_t n = op->n;
     char *peer = (char *)op->peer_ptr;
+    const uint32_t flavour = FL < 0 ? p.vec256 : (uint32_t)FL;
     if (blockIdx.x == 0 && threadIdx.x == 0) trace(p.tr, ACX_EV_MOVE_BEGIN, p.peer, op->ticket, n);
-    if (op->coop) {
+    if (FL >= 0) {
+        if (op->coop) __trap();   // a peer announced a cooperative message while this rank runs without ACX_COOP: the environment must be the same on every rank
+    } else if (op->coop) {
         const uint64_t k = op->ticket;
         const uint32_t e = (uint32_t)(k % p.depth);
         coop_agent(p.ring + e, p.sack + e, p.push ? peer : p.local, p.push ? p.local : peer, n, k / p.depth, p.vec256);
@@ -364,8 +401,7 @@ __device__ __forceinline__ void mover_body(const MoverParams &p) {
             const uint64_t len = n - lo < bs ? n - lo : bs;
             char *d = p.push ? peer + lo : p.local + lo;
             const char *s = p.push ? p.local + lo : peer + lo;
-            if (p.vec256) copy_bytes_256(d, s, len, threadIdx.x, blockDim.x);
-            else copy_bytes(d, s, len, threadIdx.x, blockDim.x);
+            copy_flavour(flavour, d, s, len, threadIdx.x, blockDim.x);
         }
     }
     // Contiguous chunk per CTA: keeps each CTA's NVLink stream sequential.
@@ -375,8 +411,7 @@ __device__ __forceinline__ void mover_body(const MoverParams &p) {
         const uint64_t len = n - lo < per ? n - lo : per;
         char *d = p.push ? peer + lo : p.local + lo;
         const char *s = p.push ? p.local + lo : peer + lo;
-        if (p.vec256) copy_bytes_256(d, s, len, threadIdx.x, blockDim.x);
-        else copy_bytes(d, s, len, threadIdx.x, blockDim.x);
+        copy_flavour(flavour, d, s, len, threadIdx.x, blockDim.x);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -395,10 +430,16 @@ __device__ __forceinline__ void mover_body(const MoverParams &p) {
     }
 }
 
-__global__ void __launch_bounds__(kMoverThreads) mover(MoverParams p) {
+__device__ __forceinline__ void mover_body(const MoverParams &p) { mover_body_t<-1>(p); }
+
+__global__ void __launch_bounds__(kMoverThreads) mover(MoverParams p) {   // general: ACX_COOP=1
     pdl_prologue();
     mover_body(p);
 }
+// What launch_mover() picks unless ACX_COOP is set: one kernel per ACX_MOVER flavour (ldst = default, ldst256, ldstcs).
+__global__ void __launch_bounds__(kMoverThreads, 2) mover_plain(MoverParams p) { pdl_prologue(); mover_body_t<0>(p); }
+__global__ void __launch_bounds__(kMoverThreads) mover_v256(MoverParams p) { pdl_prologue(); mover_body_t<1>(p); }
+__global__ void __launch_bounds__(kMoverThreads, 2) mover_cs(MoverParams p) { pdl_prologue(); mover_body_t<2>(p); }
 
 // Single-launch rendezvous for small grids (all CTAs co-resident): CTA 0 runs the match and publishes the
 // decision; the others wait for it on a launch-indexed word (relaunch-safe in graphs), then everyone moves.

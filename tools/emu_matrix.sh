@@ -53,6 +53,7 @@ if [ "$mode" = full ]; then
         run no-fuse 2 $p ACX_FUSE_RNDV=0
         run no-side-streams 2 $p ACX_SIDE_STREAMS=0
         run ldst256 2 $p ACX_MOVER=ldst256
+        run ldstcs 2 $p ACX_MOVER=ldstcs
         run mover-block 2 $p ACX_MOVER_BLOCK=4096
         [ $p = threads ] || run depth8-chan2 2 $p ACX_DEPTH=8 ACX_NCHAN=2   # threads.c needs one channel per thread (tags that collide modulo ACX_NCHAN share a FIFO)
         run eager64 3 $p ACX_EAGER_MAX=64

@@ -106,7 +106,7 @@ echo "### 6b. self-transfer (N=1, the driver's 1-GPU headline; reference arm 0.1
 # ncu saw the mover alone at 97 us of the 129-us step (profiles/mover_ncu.md): the sweep decides the self-transfer default,
 # the trace (trigger / move-begin / move-end / wait timestamps from the device ring) shows what the other ~30 us are.
 if [ "$NP" = 2 ]; then
-  for mv in ldst ldst256 tma; do for blk in 0 65536 131072 262144; do for ctas in 0 296 592 1184; do
+  for mv in ldst ldstcs ldst256 tma; do for blk in 0 65536 131072 262144; do for ctas in 0 296 592 1184; do
     echo "mover=$mv block=$blk ctas=$ctas: $(ACX_MOVER=$mv ACX_MOVER_BLOCK=$blk ACX_MOVER_MAX_CTAS=$ctas ACX_HEAP_BYTES=1g timeout 60 ./bin/acxrun -np 1 --timeout 50 bin/p2p_bench ring --bytes 268435456 --steps 20 --warmup 5 2>&1 | tail -n 1 | cut -c100-170)"
   done; done; done | tee $O/self_copy_sweep.txt
   for pdl in 1 0; do echo "pdl=$pdl: $(ACX_PDL=$pdl ACX_HEAP_BYTES=1g timeout 60 ./bin/acxrun -np 1 --timeout 50 bin/p2p_bench ring --bytes 268435456 --steps 20 --warmup 5 2>&1 | tail -n 1 | cut -c100-170)"; done
