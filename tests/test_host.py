@@ -321,3 +321,28 @@ def test_random_option_combinations_on_software_device(built):
     subprocess.run(["make", "-C", str(built), "-j4", "emu-lib", "emu-tests"], check=True, capture_output=True, timeout=900)
     r = subprocess.run([sys.executable, str(built / "tools/emu_fuzz.py"), "5", "45"], cwd=str(built), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and ", 0 failures" in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+def test_hot_kernels_keep_their_register_budget(built):
+    """Occupancy guard (static, no GPU): the default large-message mover must stay at <= 64 registers without a stack
+    frame (two 512-thread CTAs per SM — it silently became 112 / one CTA per SM once when another copy loop joined its
+    kernel), the streaming flavour likewise, and the tcgen05 GEMM and the wait kernel must not spill."""
+    import re
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not installed")
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", str(built / "lib/libacx.so")], capture_output=True, text=True, timeout=120).stdout
+    usage = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        usage[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+
+    def find(part):
+        hits = [v for k, v in usage.items() if part in k]
+        assert len(hits) == 1, (part, [k for k in usage if part in k])
+        return hits[0]
+    for name in ("mover_plainE", "mover_csE"):
+        regs, stack = find(name)
+        assert regs <= 64 and stack == 0, (name, regs, stack)
+    assert find("gemm_fp8_kernel")[1] == 0
+    regs, stack = find("11wait_kernelE")
+    assert regs <= 64 and stack == 0, (regs, stack)
