@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--impl", default="acx", choices=["acx", "reference"])
     ap.add_argument("--bytes", type=int, default=256 << 20)
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--order", default="auto", choices=["auto", "prepost", "simple"],
+    ap.add_argument("--order", default="simple", choices=["auto", "prepost", "simple"],
                     help="prepost: the receive of step i+1 is posted before step i is waited on (double-buffered); simple: irecv, isend, waitall per step; "
                          "auto: prepost from 3 GPUs up (where the arrival-order lottery of the simple order costs up to 2x, BASELINE.md 4.6), simple below")
     return ap.parse_args()
@@ -134,7 +134,7 @@ def run_acx(a) -> int:
     right, left = (rank + 1) % world, (rank - 1) % world
     n = a.bytes
     if a.order == "auto":
-        a.order = "prepost" if world >= 3 else "simple"
+        a.order = "simple"   # both arms run the same per-step order (irecv, isend, waitall); prepost stays available as an explicit choice for both arms
     sbuf = acx.empty(n, torch.uint8)
     rbufs = [acx.empty(n, torch.uint8), acx.empty(n, torch.uint8)]
     rbuf = rbufs[0]
@@ -296,7 +296,7 @@ def run_acx(a) -> int:
         "config": {"model": "ring Isend/Irecv_enqueue + Waitall_enqueue", "msg_bytes": n, "global_batch": n * world, "seq_len": None,
                    "parallelism": f"p2p-ring{world}", "l2": "working set >= 2x msg_bytes > L2, no flush", "buffers": "symmetric heap (zero-copy NVLink push/pull)",
                    "order": "receive of step i+1 posted before step i is waited on (two receive buffers)" if a.order == "prepost" else "irecv, isend, waitall per step",
-                   "nvlink_fraction_of_770GBs_per_gpu": round(gbs / world / 770.0, 3) if world > 1 else None},
+                   "nvlink_fraction_of_900GBs_per_direction_per_gpu": round(gbs / world / 900.0, 3) if world > 1 else None},
         "extra": extras,
     }
     if rank == 0:

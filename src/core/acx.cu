@@ -38,7 +38,9 @@ int acx_env_int(const char *name, const char *alt, long dflt, long *out) {
 static uint64_t *g_diag = nullptr, *g_diag_d = nullptr;      // watchdog diagnostics (pinned)
 static uint64_t *g_trace_cursor = nullptr;                   // device
 static std::vector<int> g_pending_retire;                    // slots whose wait has been enqueued; freed once the device marks them retired
-static std::vector<int> g_deferred_slots;                    // freed by graph user-object destructors
+struct DeferredSlot { int slot; unsigned long long init_gen; };
+static std::vector<DeferredSlot> g_deferred_slots;           // freed by graph user-object destructors (CUDA may run those on an internal thread, after cudaGraphDestroy has returned)
+static std::atomic<int> g_graph_objs_live{0};                // user objects created and not yet destroyed
 static std::mutex g_deferred_mu;
 
 // Stream for the calling thread's host-blocking operations (MPIX_Wait, MPIX_Start(all), host Pready / Parrived, host waits
@@ -205,7 +207,8 @@ void acx_reclaim_retired() {
     // in pinned host memory; graph-owned slots come back through the deferred list.
     {
         std::lock_guard<std::mutex> lk(g_deferred_mu);
-        for (int s : g_deferred_slots) if (g_acx->slot_busy[s]) acx_slot_free(s);
+        for (const DeferredSlot &d : g_deferred_slots)   // a destructor that outlived its MPIX_Init/Finalize epoch names a slot of the OLD table: drop it
+            if (d.init_gen == g_init_generation && g_acx->slot_busy[d.slot] == 2) acx_slot_free(d.slot);
         g_deferred_slots.clear();
     }
     size_t keep = 0;
@@ -791,6 +794,9 @@ extern "C" int MPIX_Finalize(void) {
         {
             std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
             acx_reclaim_retired();
+            // The destructors of graph user objects may still be on their way (CUDA runs them on an internal thread some time
+            // after cudaGraphDestroy / cudaGraphExecDestroy return): give them a moment before calling a slot leaked.
+            for (int i = 0; i < 200 && g_graph_objs_live.load() > 0; i++) { usleep(1000); acx_reclaim_retired(); }
             int leaked = 0;
             for (int s = 0; s < g_acx->geom.nops; s++) if (g_acx->slot_busy[s] == 1 || g_acx->slot_busy[s] == 2) leaked++;
             if (leaked) printf("Warning: %d request slot(s) still in use at MPIX_Finalize (un-waited operations or live graphs)\n", leaked);
@@ -1033,23 +1039,26 @@ struct Emitter {
 // Resources that must live as long as a CUDA graph does (the reference attaches a
 // cudaUserObject whose destructor host-spins and frees, src/sendrecv.cu:106-127,174-184;
 // ours only queues the slots for reuse — destructors may not call CUDA).
-struct AcxGraphRes { std::vector<int> slots; };
+struct AcxGraphRes { std::vector<int> slots; unsigned long long init_gen; };
 static void CUDART_CB graph_res_destroy(void *p) {
     AcxGraphRes *g = (AcxGraphRes *)p;
     {
         std::lock_guard<std::mutex> lk(g_deferred_mu);
-        for (int s : g->slots) g_deferred_slots.push_back(s);
+        for (int s : g->slots) g_deferred_slots.push_back({s, g->init_gen});
     }
+    g_graph_objs_live.fetch_sub(1);
     delete g;
 }
 static int attach_to_graph(cudaGraph_t graph, int slot) {
     AcxGraphRes *res = new AcxGraphRes();
     res->slots.push_back(slot);
+    res->init_gen = g_init_generation;
     cudaUserObject_t obj;
     cudaError_t e = cudaUserObjectCreate(&obj, res, graph_res_destroy, 1, cudaUserObjectNoDestructorSync);
     if (e != cudaSuccess) { delete res; ACX_ERR("cudaUserObjectCreate: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+    g_graph_objs_live.fetch_add(1);
     e = cudaGraphRetainUserObject(graph, obj, 1, cudaGraphUserObjectMove);
-    if (e != cudaSuccess) { ACX_ERR("cudaGraphRetainUserObject: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+    if (e != cudaSuccess) { cudaUserObjectRelease(obj, 1); ACX_ERR("cudaGraphRetainUserObject: %s", cudaGetErrorString(e)); return MPI_ERR_OTHER; }
     return 0;
 }
 

@@ -100,8 +100,18 @@ cudaError_t make_launch(const void *func, dim3 grid, dim3 block, void **args, Ke
 // graphs
 // ------------------------------------------------------------------------------------------------------------------
 struct UserObj { void *ptr; cudaHostFn_t destroy; std::atomic<long> refs; };
+// The real runtime may run a user object's destructor on an internal thread some time AFTER the call that dropped the last
+// reference has returned (cudaUserObjectNoDestructorSync; observed on hardware in round 1: slots of a destroyed graph were
+// still held when cudaGraphDestroy returned). Modelled here: a detached thread, ACX_EMU_UOBJ_DELAY_MS (default 15) later.
+static std::atomic<int> g_uobj_async{0};
+struct UobjDrain { ~UobjDrain() { for (int i = 0; i < 3000 && g_uobj_async.load() > 0; i++) usleep(1000); } };
+static UobjDrain g_uobj_drain;
 void uobj_release(UserObj *o, long n) {
-    if (o->refs.fetch_sub(n) - n <= 0) { o->destroy(o->ptr); delete o; }
+    if (o->refs.fetch_sub(n) - n > 0) return;
+    static const long delay_ms = getenv("ACX_EMU_UOBJ_DELAY_MS") ? atol(getenv("ACX_EMU_UOBJ_DELAY_MS")) : 15;
+    if (delay_ms <= 0) { o->destroy(o->ptr); delete o; return; }
+    g_uobj_async.fetch_add(1);
+    std::thread([o] { usleep((useconds_t)delay_ms * 1000); o->destroy(o->ptr); delete o; g_uobj_async.fetch_sub(1); }).detach();
 }
 struct Graph;
 enum NodeType { kNodeKernel, kNodeEmpty, kNodeChild, kNodeMemcpy, kNodeMemset, kNodeHost };
