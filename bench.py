@@ -68,8 +68,12 @@ def run_reference(a) -> int:
         env["ACX_JOBID"] = f"ref_{port}_{phase}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}"
         cmd = [str(exe), "ring", "--bytes", str(a.bytes), "--steps", str(a.steps), "--warmup", str(max(3, a.warmup)), "--no-heap"] + extra
         from mpi_acx_b200.utils.clocks import ClockSampler
-        with ClockSampler(local) as cs:
-            p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1800)
+        # same placement policy as the acx arm (whose MPIX_Init binds itself): the rank runs on the socket its GPU hangs off,
+        # so cudaMallocHost staging memory is first-touched there — what mpiexec's default binding would give the reference
+        from mpi_acx_b200.utils.numa import gpu_numa_cpus
+        cpus = gpu_numa_cpus(local) if os.environ.get("ACX_NUMA_BIND", "1") != "0" else None
+        with ClockSampler(local, period_ms=50) as cs:
+            p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1800, preexec_fn=(lambda: os.sched_setaffinity(0, cpus)) if cpus else None)
         if p.returncode != 0:
             if rank == 0:
                 print(json.dumps({"impl": "reference", "unavailable": f"reference run failed rc={p.returncode}: {(p.stderr or p.stdout)[-300:]!r}"}))
@@ -144,7 +148,7 @@ def run_acx(a) -> int:
     h_in = torch.empty(n, dtype=torch.uint8)
     h_out = torch.empty(4096, dtype=torch.uint8)
     if not dry:
-        h_in, h_out = h_in.pin_memory(), h_out.pin_memory()
+        h_in, h_out = h_in.pin_memory(), h_out.pin_memory()   # after acx.init(): pages land on the GPU's NUMA node (MPIX_Init binds the rank)
     h_in.fill_(rank + 1)
     stream = torch.cuda.current_stream()
 
@@ -161,7 +165,18 @@ def run_acx(a) -> int:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # e2e: the step's input starts in pinned host memory. The library's host-staged exchange (parallel/staged.py) cuts the
+    # message into chunks and sends chunk i (stream-triggered isend, gated on that chunk's H2D copy) while chunk i+1 is
+    # still crossing PCIe; ACX_BENCH_E2E_CHUNKS=1 gives the plain copy-then-send sequence.
+    from mpi_acx_b200.parallel.staged import StagedExchange
+    e2e_chunks = int(os.environ.get("ACX_BENCH_E2E_CHUNKS", "8"))
+    plan = StagedExchange(sbuf, rbuf, right, left, chunks=e2e_chunks) if (e2e_chunks > 1 and not dry) else None
+
     def step(e2e: bool):
+        if e2e and plan is not None:
+            plan.step(h_in)
+            h_out.copy_(rbuf[:4096], non_blocking=True)
+            return
         if e2e:
             sbuf.copy_(h_in, non_blocking=True)
         rr = acx.irecv(rbuf, left, 0)
@@ -200,7 +215,7 @@ def run_acx(a) -> int:
 
     # One nvidia-smi sampler (rank 0's GPU), started well before the first timed region and kept running across
     # both: starting NVML clients on every rank at the instant the timed loop begins stalls kernel launches.
-    sampler = ClockSampler(local, period_ms=20) if rank == 0 and not dry else None
+    sampler = ClockSampler(local, period_ms=50) if rank == 0 and not dry else None
     if sampler:
         sampler.__enter__()
         import time
@@ -291,7 +306,8 @@ def run_acx(a) -> int:
         "metric": "ring_sendrecv_bandwidth", "value": round(gbs, 3), "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": W,
         "ms_per_step": round(ms, 6), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bytes", "data": "synthetic",
         "impl": "acx-b200", "verified": ok and ok_e2e, "clocks": clocks,
-        "e2e": {"value": round(gbs_e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 4096, "ms_per_step": round(ms_e2e, 6)},
+        "e2e": {"value": round(gbs_e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 4096, "ms_per_step": round(ms_e2e, 6),
+                "pipeline": (f"{len(plan.bounds)} chunks: H2D of chunk i+1 overlaps the stream-triggered send of chunk i (mpi_acx_b200.parallel.staged)" if plan is not None else "copy, then send")},
         "gpu_launches": int(launches),
         "config": {"model": "ring Isend/Irecv_enqueue + Waitall_enqueue", "msg_bytes": n, "global_batch": n * world, "seq_len": None,
                    "parallelism": f"p2p-ring{world}", "l2": "working set >= 2x msg_bytes > L2, no flush", "buffers": "symmetric heap (zero-copy NVLink push/pull)",

@@ -13,6 +13,9 @@
 #include <cstring>
 #include <thread>
 #include <unistd.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <ctype.h>
 #include <nvtx3/nvToolsExt.h>
 
 AcxState *g_acx = nullptr;
@@ -131,6 +134,7 @@ static void report_watchdog() {
         const char *what = "unknown";
         switch (g_diag[0]) {
             case 0x5e01: what = "send trigger: ring slot never freed (receiver not consuming; > ACX_DEPTH unconsumed sends on one channel?)"; break;
+            case 0x5e0d: what = "receive matched a message with another tag / communicator (a[63:32] wanted tag, a[31:0] got; b = contexts): more distinct (communicator, tag) pairs between two ranks than ACX_NCHAN-1, posted in another order than sent — raise ACX_NCHAN"; break;
             case 0x5e02: what = "recv trigger: own ring slot still in use (> ACX_DEPTH outstanding receives on one channel)"; break;
             case 0x5e03: what = "wait(send): rendezvous never completed (no matching receive)"; break;
             case 0x5e04: what = "wait(recv): message never arrived (no matching send)"; break;
@@ -622,7 +626,7 @@ struct Bootstrap {
 static void make_geom(acx_geom &g, int n) {
     long v;
     g.nranks = n;
-    acx_env_int("ACX_NCHAN", nullptr, 16, &v); g.nchan = (int)std::max(1L, v);
+    acx_env_int("ACX_NCHAN", nullptr, 32, &v); g.nchan = (int)std::max(1L, v);   // one channel per (communicator, tag) a pair of ranks uses (see chan_lookup); the last one is the overflow FIFO
     acx_env_int("ACX_DEPTH", nullptr, 32, &v); g.depth = (int)std::max(2L, v);
     acx_env_int("ACX_NFLAGS", "MPIACX_NFLAGS", 4096, &v); g.nops = (int)std::max(8L, v);
     acx_env_int("ACX_EAGER_MAX", nullptr, 8192, &v); g.eager_max = (uint32_t)((std::max(16L, v) + 15) & ~15L);
@@ -633,6 +637,60 @@ static void make_geom(acx_geom &g, int n) {
     acx_geom_layout(g);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// NUMA placement. On an HGX B200 node GPUs 0-3 hang off socket 0 and 4-7 off socket 1; a rank whose staging memory
+// or launching thread sits on the other socket pays the inter-socket link on every H2D copy and every launch
+// (round 1: 8-rank end-to-end step 9.1 ms against 5 ms of PCIe time). mpiexec-style launchers bind ranks; torchrun
+// does not, so MPIX_Init does it itself: the calling thread is restricted to the CPUs of the GPU's NUMA node and its
+// memory policy prefers that node (threads and pinned allocations made afterwards inherit both). ACX_NUMA_BIND=0
+// turns it off; a process whose affinity was already narrowed by its launcher is left alone.
+// ---------------------------------------------------------------------------------------
+static int acx_numa_bind(int dev) {
+#if defined(__linux__) && !defined(ACX_EMU)
+    long on = 1;
+    acx_env_int("ACX_NUMA_BIND", nullptr, 1, &on);
+    if (!on) return -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return -1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    char list[4096] = {0};
+    if (!fgets(list, sizeof list, f)) list[0] = 0;
+    fclose(f);
+    cpu_set_t want, have, both;
+    CPU_ZERO(&want);
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET(c, &want); }
+        else if (sscanf(tok, "%d", &a) == 1 && a < CPU_SETSIZE) CPU_SET(a, &want);
+    }
+    if (sched_getaffinity(0, sizeof have, &have) != 0) return -1;
+    CPU_AND(&both, &want, &have);
+    if (CPU_COUNT(&both) == 0) return -1;                        // the launcher confined us elsewhere: respect it
+    if (CPU_COUNT(&both) != CPU_COUNT(&have)) sched_setaffinity(0, sizeof both, &both);
+    // set_mempolicy(MPOL_PREFERRED, {node}): no libnuma in the image, so the raw system call
+    unsigned long mask[16] = {0};
+    if (node < (int)(sizeof mask * 8)) {
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof mask * 8);
+    }
+    return node;
+#else
+    (void)dev;
+    return -1;
+#endif
+}
+
+static void tagdir_init();   // channel directory (exact tag matching), defined with the front-ends
 // Reference: MPIX_Init, src/init.cpp:157-253 (flag table in mapped host memory + proxy thread). Here: device windows,
 // CUDA-IPC exchange, no thread.
 extern "C" int MPIX_Init(void) {
@@ -704,6 +762,7 @@ extern "C" int MPIX_Init(void) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, g_acx->dev) != cudaSuccess) { ACX_ERR("cudaGetDeviceProperties failed"); return 1; }
     g_acx->sm_count = prop.multiProcessorCount;
+    { const int node = acx_numa_bind(g_acx->dev); if (node >= 0) ACX_LOG(1, "bound to NUMA node %d (GPU %d's socket)", node, g_acx->dev); }
     cudaDeviceGetAttribute(&g_acx->pageable_access, cudaDevAttrPageableMemoryAccess, g_acx->dev);
     cudaDeviceGetAttribute(&g_acx->host_ptr_is_dev_ptr, cudaDevAttrCanUseHostPointerForRegisteredMem, g_acx->dev);
 
@@ -773,6 +832,7 @@ extern "C" int MPIX_Init(void) {
     g_acx->device = true;
     g_acx->initialized = true;
     reg_init();
+    tagdir_init();
     memops_init();
 #ifdef ACX_MINI_MPI
     ACX_Mpi_set_abort_hook(report_watchdog);
@@ -1209,7 +1269,58 @@ static void mark_operation_end(Emitter &em, AcxRequest *r) {
     if (r->ev_done && cudaEventRecord(r->ev_done, em.stream) != cudaSuccess) { cudaGetLastError(); g_event_pool.push_back(r->ev_done); r->ev_done = nullptr; }
 }
 
-static inline int chan_of(int tag, int ctx) { return (int)(((unsigned)tag + 7u * (unsigned)ctx) % (unsigned)g_acx->geom.nchan); }
+// ---------------------------------------------------------------------------------------
+// Channel directory: exact (source, tag, communicator) matching.
+// A message S -> R with (ctx, tag) travels on a per-pair channel (a FIFO ring, see internal.h). Round 1 hashed
+// (tag + 7 ctx) mod NCHAN, so two tags that collided shared one FIFO and a receive order different from the send order
+// swapped payloads (the reference hands tag and peer to MPI untouched, src/init.cpp:69-70,76-77, so any pattern matches).
+// Now every (ctx, tag) a pair uses gets its OWN channel, assigned on first use by whichever side gets there first: the
+// directory of the ordered pair lives in the job's shared-memory scratch (one 64-bit key per channel, claimed by
+// compare-and-swap), so sender and receiver agree without exchanging a message. The last channel is the overflow FIFO
+// for pairs that use more than NCHAN-1 distinct (ctx, tag) combinations: messages there carry ctx and tag in their
+// header and a receive that finds another message at the head of the FIFO is a fatal, diagnosed error (raise ACX_NCHAN),
+// never a silent mismatch. Without the shared scratch (an external MPI, > 64 ranks) everything hashes as before — with
+// the same fatal check.
+// ---------------------------------------------------------------------------------------
+static std::atomic<uint64_t> *g_tagdir = nullptr;   // [sender][receiver][nchan - 1] keys, 0 = free
+static inline uint64_t tagdir_key(int tag, int ctx) { return ((uint64_t)((uint32_t)ctx + 1u) << 32) | (uint32_t)tag; }
+static inline std::atomic<uint64_t> *tagdir_row(int sender, int receiver) {
+    return g_tagdir + ((size_t)sender * g_acx->size + receiver) * (size_t)(g_acx->geom.nchan - 1);
+}
+static inline int chan_hash(int tag, int ctx, int n) { return (int)(((unsigned)tag + 7u * (unsigned)ctx) % (unsigned)n); }
+// Channel of messages `sender` -> `receiver` (world ranks) with (ctx, tag); *exact = false when it is a shared FIFO.
+static int chan_lookup(int sender, int receiver, int tag, int ctx, bool *exact = nullptr) {
+    const int n = g_acx->geom.nchan;
+    if (exact) *exact = false;
+    if (!g_tagdir || n < 2) return chan_hash(tag, ctx, n);
+    const uint64_t key = tagdir_key(tag, ctx);
+    std::atomic<uint64_t> *row = tagdir_row(sender, receiver);
+    for (int i = 0; i < n - 1; i++) {
+        uint64_t cur = row[i].load(std::memory_order_acquire);
+        if (cur == 0 && row[i].compare_exchange_strong(cur, key, std::memory_order_acq_rel)) cur = key;
+        if (cur == key) { if (exact) *exact = true; return i; }
+    }
+    static bool warned = false;
+    if (!warned) { warned = true; ACX_LOG(0, "more than %d distinct (communicator, tag) pairs between ranks %d -> %d: the rest share the overflow channel (FIFO matching, checked); raise ACX_NCHAN", n - 1, sender, receiver); }
+    return n - 1;
+}
+static void tagdir_init() {
+    g_tagdir = nullptr;
+#ifdef ACX_MINI_MPI
+    long on = 1;
+    acx_env_int("ACX_TAGDIR", nullptr, 1, &on);
+    size_t sb = 0;
+    char *scratch = (char *)ACX_Mpi_shared_scratch(&sb);
+    const size_t off = (sizeof(AcxRegTable) * 64 + 4095) & ~(size_t)4095;   // behind the registration tables (always sized for 64 ranks)
+    const size_t need = (size_t)g_acx->size * g_acx->size * (size_t)(g_acx->geom.nchan - 1) * sizeof(std::atomic<uint64_t>);
+    if (!on || !scratch || g_acx->geom.nchan < 2 || off + need > sb) return;
+    g_tagdir = (std::atomic<uint64_t> *)(scratch + off);
+    // a re-initialization starts from an empty directory: every rank clears the rows it sends on; MPIX_Init ends with a
+    // barrier, and nobody enqueues before that
+    for (int r = 0; r < g_acx->size; r++)
+        for (int i = 0; i < g_acx->geom.nchan - 1; i++) tagdir_row(g_acx->rank, r)[i].store(0, std::memory_order_release);
+#endif
+}
 
 static AcxRequest *new_request(AcxReqKind kind, int peer, int tag, int ctx, size_t bytes, const void *buf) {
     AcxRequest *r = new AcxRequest();
@@ -1353,7 +1464,9 @@ static void fill_any(AcxRequest *r, AnyParams *ap) {
     ap->dst_off = r->bounce_off >= 0 ? (uint64_t)r->bounce_off : (r->heap_off >= 0 ? (uint64_t)r->heap_off : ~0ull);
     ap->cap = r->bytes; ap->serial = r->serial; ap->geom = G;
     if (r->peer == MPI_ANY_SOURCE) { ap->src_lo = 0; ap->src_hi = g_acx->size - 1; } else { ap->src_lo = ap->src_hi = r->peer; }
-    if (r->tag == MPI_ANY_TAG) { ap->chan_lo = 0; ap->chan_hi = G.nchan - 1; } else { ap->chan_lo = ap->chan_hi = chan_of(r->tag, r->comm_ctx); }
+    // channels are per (source, ctx, tag): a wildcard source or tag looks at the head of every channel and filters on the header
+    if (r->tag == MPI_ANY_TAG || r->peer == MPI_ANY_SOURCE) { ap->chan_lo = 0; ap->chan_hi = G.nchan - 1; } else { ap->chan_lo = ap->chan_hi = chan_lookup(r->peer, g_acx->rank, r->tag, r->comm_ctx); }
+    ap->want_ctx = (uint32_t)r->comm_ctx;
     ap->want_tag = r->tag; ap->me = (uint32_t)g_acx->rank; ap->vec256 = (uint32_t)g_mover_256;
     ap->wd = make_wd(); ap->tr = make_tr();
 }
@@ -1393,7 +1506,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
     if ((rc = em.begin(qtype, queue))) { delete r; return rc; }
     r->in_graph = em.in_graph();
     r->stream = qtype == MPIX_QUEUE_CUDA_STREAM ? em.stream : nullptr;
-    r->chan = chan_of(tag, ctx);
+    r->chan = chan_lookup(g_acx->rank, dest, tag, ctx);
     if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { delete r; return MPI_ERR_OTHER; }
     if ((rc = acx_device_alias(buf, ty.noncontig ? (size_t)ty.span : bytes, &r->dev_buf))) goto fail;
     if ((rc = branch.begin())) goto fail;
@@ -1442,7 +1555,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         sp.peer_heap = g_acx->peer_heap[dest];
         sp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)dest * G.maxreg;
         sp.src_off = src_off; sp.bytes = bytes; sp.serial = r->serial;
-        sp.tag = (uint32_t)tag; sp.depth = G.depth; sp.eager_max = G.eager_max; sp.peer = dest;
+        sp.tag = (uint32_t)tag; sp.ctx = (uint32_t)ctx; sp.depth = G.depth; sp.eager_max = G.eager_max; sp.peer = dest;
         sp.wd = make_wd(); sp.tr = make_tr();
         const bool dropped = g_fault_drop_send > 0 && ++g_send_counter == g_fault_drop_send;
         if (dropped) ACX_ERR("FAULT INJECTION: dropping send #%ld (tag %d -> rank %d)", g_fault_drop_send, tag, dest);
@@ -1526,7 +1639,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         if (qtype == MPIX_QUEUE_CUDA_GRAPH) { cudaGraphNode_t node; cudaGraphAddEmptyNode(&node, em.graph, nullptr, 0); }
         goto done;
     }
-    r->chan = chan_of(tag, ctx);
+    r->chan = chan_lookup(wsource, g_acx->rank, tag, ctx);
     if (!r->in_graph) {
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
         if (g_acx->recv_outstanding[source][r->chan] >= g_acx->geom.depth) {
@@ -1633,7 +1746,7 @@ static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_w
     w->depth = G.depth; w->eager_max = G.eager_max;
     w->serial = host_wait ? r->serial : 0;
     w->retire = retire ? 1 : 0;
-    w->src = r->comm_peer; w->tag = r->tag;   // status reports the peer in the caller's communicator
+    w->src = r->comm_peer; w->tag = r->tag; w->ctx = (uint32_t)r->comm_ctx;   // status reports the peer in the caller's communicator
     w->off_source = w->off_tag = w->off_error = w->off_bytes = 0xffff;
     if (r->kind == ACX_REQ_SEND) {
         w->is_recv = 0;
@@ -1947,7 +2060,7 @@ extern "C" int MPIX_Recv_enqueue(void *buf, int count, MPI_Datatype datatype, in
     int rc = em.begin(qtype, queue);
     if (rc) { delete r; return rc; }
     r->in_graph = em.in_graph();
-    r->chan = chan_of(tag, ctx);
+    r->chan = chan_lookup(source, g_acx->rank, tag, ctx);
     if (!r->in_graph) {   // the depth check of MPIX_Irecv_enqueue: this receive occupies a ring slot until its kernel has run
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
         if (g_acx->recv_outstanding[source][r->chan] >= g_acx->geom.depth) {
@@ -2051,7 +2164,7 @@ extern "C" int MPIX_Sendrecv_enqueue(const void *sendbuf, int sendcount, MPI_Dat
     if (rc) { delete r; return rc; }
     r->in_graph = em.in_graph();
     r->stream = em.stream;
-    r->chan = chan_of(recvtag, rctx);
+    r->chan = chan_lookup(wsource, g_acx->rank, recvtag, rctx);
     if (!r->in_graph) {
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
         if (g_acx->recv_outstanding[wsource][r->chan] >= g_acx->geom.depth) {
@@ -2067,7 +2180,7 @@ extern "C" int MPIX_Sendrecv_enqueue(const void *sendbuf, int sendcount, MPI_Dat
     {
         const acx_geom &G = g_acx->geom;
         r->heap_off = acx_heap_offset_of(recvbuf);
-        const int schan = chan_of(sendtag, sctx);
+        const int schan = chan_lookup(g_acx->rank, wdest, sendtag, sctx);
         // receive half (as MPIX_Recv_enqueue)
         const uint64_t rring = acx_entry_index(G, wsource, r->chan, 0), rsack = acx_entry_index(G, g_acx->rank, r->chan, 0);
         RecvParams rp;
@@ -2093,7 +2206,7 @@ extern "C" int MPIX_Sendrecv_enqueue(const void *sendbuf, int sendcount, MPI_Dat
         sp.src = send_alias; sp.peer_heap = g_acx->peer_heap[wdest];
         sp.xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)wdest * G.maxreg;
         sp.src_off = ~0ull; sp.bytes = sbytes; sp.serial = 0;
-        sp.tag = (uint32_t)sendtag; sp.depth = G.depth; sp.eager_max = G.eager_max; sp.peer = wdest;
+        sp.tag = (uint32_t)sendtag; sp.ctx = (uint32_t)sctx; sp.depth = G.depth; sp.eager_max = G.eager_max; sp.peer = wdest;
         sp.wd = make_wd(); sp.tr = make_tr();
         WaitBatch wb;
         memset(&wb, 0, sizeof wb);

@@ -48,8 +48,11 @@ struct alignas(64) acx_entry {  // one slot of a (src -> me, channel) ring; live
     uint64_t coop_cursor; // cooperative moving (ACX_COOP): next unclaimed chunk of this generation's payload (atomic add by agents on either GPU)
     uint64_t coop_done;   // cooperative moving: chunks fully copied; both are reset by the receiver's wait kernel before the slot is recycled
     uint32_t s_tag;
-    uint32_t s_kind;     // ACX_KIND_*
+    uint32_t s_kind;     // low 8 bits: ACX_KIND_*; upper 24 bits: the sender's communicator context (checked by the receive: see ACX_ENT_CTX)
 };
+#define ACX_ENT_KIND(x) ((uint32_t)(x) & 0xffu)
+#define ACX_ENT_CTX(x) ((uint32_t)(x) >> 8)
+#define ACX_ENT_HEADER(tag, kind, ctx) ((uint64_t)(uint32_t)(tag) | ((uint64_t)((uint32_t)(kind) | ((uint32_t)(ctx) << 8)) << 32))
 
 struct alignas(32) acx_sack {  // per slot, lives at the SENDER, written by the receiver / mover
     uint64_t sdone;      // #generations whose send completed (source buffer reusable)

@@ -161,6 +161,7 @@ struct SendParams {
     uint64_t bytes;
     uint64_t serial;
     uint32_t tag, depth, eager_max, peer;
+    uint32_t ctx, pad0;     // communicator context, travels in the slot header (exact (source, tag, comm) matching: a receive checks it)
     uint32_t apush, coop;   // apush: deterministic mode — this sender pushes the payload itself (gate + mover on its channel stream); coop: announce the message as RNDV_COOP (ACX_COOP)
     Watchdog wd;
     TraceCtx tr;
@@ -174,7 +175,7 @@ __device__ __forceinline__ void send_rndv_match(const SendParams &p, uint64_t k)
     acx_entry *ent = p.ring + e;
 
     ent->s_src_off = p.src_off; ent->s_bytes = p.bytes;
-    *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)(p.apush ? ACX_KIND_RNDV_PUSH : p.coop ? ACX_KIND_RNDV_COOP : ACX_KIND_RNDV) << 32);
+    *reinterpret_cast<uint64_t *>(&ent->s_tag) = ACX_ENT_HEADER(p.tag, p.apush ? ACX_KIND_RNDV_PUSH : p.coop ? ACX_KIND_RNDV_COOP : ACX_KIND_RNDV, p.ctx);
     uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull << 32);
     p.op->ticket = k; p.op->eager = 0; p.op->cta_count = 0; p.op->coop = p.coop;
     if (p.apush) {
@@ -216,7 +217,7 @@ __device__ __forceinline__ void send_body(const SendParams &p) {
         __syncthreads();
         if (tid == 0) {
             ent->s_bytes = p.bytes;
-            *reinterpret_cast<uint64_t *>(&ent->s_tag) = (uint64_t)p.tag | ((uint64_t)ACX_KIND_EAGER << 32);
+            *reinterpret_cast<uint64_t *>(&ent->s_tag) = ACX_ENT_HEADER(p.tag, ACX_KIND_EAGER, p.ctx);
             red_release_add_sys(&ent->state, 1ull << 32);
             // The source buffer is reusable as soon as this kernel retires: nothing to wait for later.
             if (p.hstat) ACX_HOST_FLAG_SET(&p.hstat->retired, 1);
@@ -265,14 +266,14 @@ __device__ __forceinline__ void recv_match_at(const RecvParams &p, uint64_t k) {
     }
     uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull);   // release orders the mirror stores before it
     p.op->ticket = k; p.op->cta_count = 0; p.op->mover = 0; p.op->bounce_n = 0; p.op->coop = 0;
-    if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && (ent->s_kind == ACX_KIND_RNDV || ent->s_kind == ACX_KIND_RNDV_COOP) && !p.rndv_capable) {
+    if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && (ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV || ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV_COOP) && !p.rndv_capable) {
         // a rendezvous message is waiting for a receive that cannot hold it (no mover was launched for this receive):
         // complete it here with nothing moved; the wait reports MPI_ERR_TRUNCATE and 0 bytes
         __threadfence_system();
         st_release_sys(&ent->done, g + 1);
         if (p.sack) st_release_sys(&p.sack[e].sdone, g + 1);
-    } else if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && (ent->s_kind == ACX_KIND_RNDV || ent->s_kind == ACX_KIND_RNDV_COOP)) {
-        p.op->coop = ent->s_kind == ACX_KIND_RNDV_COOP;   // the sender decides how its message is moved
+    } else if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && (ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV || ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV_COOP)) {
+        p.op->coop = ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV_COOP;   // the sender decides how its message is moved
         // the send is already here and waiting: I move the data (pull)
         uint64_t sb = ent->s_bytes;
         p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, ent->s_src_off);
@@ -512,6 +513,7 @@ struct AnyParams {
     acx_geom geom;
     int32_t src_lo, src_hi, chan_lo, chan_hi;   // inclusive candidate ranges
     int32_t want_tag;           // MPI_ANY_TAG = any
+    uint32_t want_ctx;          // the receive's communicator context: channels are per (ctx, tag), the header says which
     uint32_t me, vec256, rndv_capable;
     Watchdog wd;
     TraceCtx tr;
@@ -539,6 +541,7 @@ __global__ void __launch_bounds__(kMoverThreads) recv_any_kernel(AnyParams p) {
                         acx_entry *ent = entries + acx_entry_index(G, s, c, e);
                         if (ld_acquire_sys(&ent->consumed) < g) continue;                                   // my previous use of the slot is not finished
                         if ((uint32_t)(ld_acquire_sys(&ent->state) >> 32) < (uint32_t)(g + 1)) continue;    // the send with ticket kk is not here yet
+                        if (ACX_ENT_CTX(ent->s_kind) != p.want_ctx) continue;                               // a message of another communicator
                         if (p.want_tag != MPI_ANY_TAG && (int32_t)ent->s_tag != p.want_tag) continue;       // head of this channel carries another tag
                         if (atomicCAS((unsigned long long *)seq, (unsigned long long)kk, (unsigned long long)(kk + 1)) != kk) continue;   // a concurrent receive took it
                         src = s; chan = c; k = kk;
@@ -695,7 +698,7 @@ __device__ __forceinline__ bool coop_peek(const CoopParams &p, acx_entry *ent, a
     }
     if (ld_acquire_sys(&ent->done) >= g + 1) return true;
     if ((uint32_t)(ld_acquire_sys(&ent->state) >> 32) < (uint32_t)(g + 1)) return false;   // the send has not arrived yet
-    if (ent->s_kind == ACX_KIND_RNDV_COOP) {                                       // its header is in my entry; only messages announced as cooperative have a cursor
+    if (ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV_COOP) {                                       // its header is in my entry; only messages announced as cooperative have a cursor
         const uint64_t sb = ent->s_bytes;
         *peer = (uint64_t)translate_peer(p.peer_heap, p.xlat, ent->s_src_off);
         *n = sb < p.bytes ? sb : p.bytes;
@@ -754,6 +757,7 @@ struct WaitOne {
     uint64_t serial;        // != 0: first wait until op->armed == serial (host-side waits)
     int32_t src, tag;
     uint32_t depth, eager_max;
+    uint32_t ctx, pad0;     // the receive's communicator context (checked against the message header)
     uint16_t is_recv, retire;
     uint16_t bounce_kernel, coop;   // bounce_kernel: a bounce_out_kernel follows (large private destination); coop: reset the slot's chunk cursor when consuming (ACX_COOP)
     uint16_t off_source, off_tag, off_error, off_bytes;  // field offsets inside MPI_Status (0xffff = absent)
@@ -794,7 +798,7 @@ __device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) 
             int eager = 0;
             for (;;) {
                 if (ld_acquire_sys(&ent->done) >= g + 1) break;
-                if ((uint32_t)(ld_acquire_sys(&ent->state) >> 32) >= (uint32_t)(g + 1) && ent->s_kind == ACX_KIND_EAGER) { eager = 1; break; }
+                if ((uint32_t)(ld_acquire_sys(&ent->state) >> 32) >= (uint32_t)(g + 1) && ACX_ENT_KIND(ent->s_kind) == ACX_KIND_EAGER) { eager = 1; break; }
                 if (ns) __nanosleep(ns);
                 ns = ns < 256 ? ns * 2 + 20 : 256;
                 if (b.wd.budget_ns && globaltimer_ns() - t0 > b.wd.budget_ns) { b.wd.diag[1] = k; b.wd.diag[2] = ent->state; b.wd.diag[0] = 0x5e04; __threadfence_system(); __trap(); }
@@ -822,7 +826,16 @@ __device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) 
             acx_entry *ent = ring + e;
             const uint64_t sb = ent->s_bytes;
             const int32_t stag = (int32_t)ent->s_tag;
-            const int32_t err = (sb > w.cap) ? MPI_ERR_TRUNCATE : ((w.tag != MPI_ANY_TAG && stag != w.tag) ? MPI_ERR_TAG : MPI_SUCCESS);
+            // Channels are exact per (communicator, tag) (chan_lookup in acx.cu), so the header can only disagree on the shared
+            // overflow channel (or with the directory disabled) when receives were posted in another order than the sends.
+            // That is a mis-delivery, whether or not anybody looks at the status: diagnose it and stop.
+            const bool mismatch = (w.tag != MPI_ANY_TAG && stag != w.tag) || ACX_ENT_CTX(ent->s_kind) != w.ctx;
+            if (mismatch && b.wd.diag) {
+                b.wd.diag[1] = ((uint64_t)(uint32_t)w.tag << 32) | (uint32_t)stag; b.wd.diag[2] = ((uint64_t)w.ctx << 32) | ACX_ENT_CTX(ent->s_kind); b.wd.diag[0] = 0x5e0d;
+                __threadfence_system();
+                __trap();
+            }
+            const int32_t err = (sb > w.cap) ? MPI_ERR_TRUNCATE : (mismatch ? MPI_ERR_TAG : MPI_SUCCESS);
             op->recv_bytes = n;
             op->bounce_n = (w.bounce && w.bounce_kernel && !s_eager) ? n : 0;
             if (w.ustatus) {

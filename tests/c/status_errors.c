@@ -3,7 +3,7 @@
  *   - a message longer than the receive: only `capacity` bytes land (guard bytes behind the buffer stay intact), the
  *     status says MPI_ERR_TRUNCATE and counts the bytes delivered — eager and rendezvous sizes, stream and host waits;
  *   - device transport only: two tags that share a channel (tag mod ACX_NCHAN) are one FIFO, and a receive that meets
- *     the other tag's message is reported as MPI_ERR_TAG instead of silently delivering the wrong message;
+ *     (exact per-tag channels since round 2) is matched by tag, not by arrival order;
  *   - MPIX_Waitall_enqueue over more requests than one wait kernel takes (30 > 12), statuses for every one of them;
  *   - invalid arguments come back as MPI error codes, the request stays MPIX_REQUEST_NULL and nothing leaks;
  *   - MPIX_Request_free on an un-waited basic request completes it (the reference ignores it, defect D11). */
@@ -76,17 +76,21 @@ static void many_requests(void) {
 }
 
 static void tag_collision(void) {
-    /* tags 2 and 2 + nchan share a channel: the receive posted for tag 2 meets the message sent with the other tag */
+    /* tags 2 and 2 + nchan hashed onto one FIFO in round 1 and the receive for tag 2 met the other tag's message
+       (MPI_ERR_TAG). Channels are exact per (communicator, tag) now: posted in the "wrong" order, both still match. */
     const int nchan = getenv("ACX_NCHAN") ? atoi(getenv("ACX_NCHAN")) : 16;
-    int a = 1234 + t_rank, b = -1;
+    int a = 1234 + t_rank, a2 = 4321 + t_rank, b = -1, b2 = -1;
     cudaStream_t st = 0;
-    MPIX_Request rq[2];
-    MPI_Status sts[2];
-    T_OK(MPIX_Isend_enqueue(&a, 1, MPI_INT, T_RIGHT, 2 + nchan, MPI_COMM_WORLD, &rq[1], MPIX_QUEUE_CUDA_STREAM, &st));
-    T_OK(MPIX_Irecv_enqueue(&b, 1, MPI_INT, T_LEFT, 2, MPI_COMM_WORLD, &rq[0], MPIX_QUEUE_CUDA_STREAM, &st));
-    T_OK(MPIX_Waitall_enqueue(2, rq, sts, MPIX_QUEUE_CUDA_STREAM, &st));
+    MPIX_Request rq[4];
+    MPI_Status sts[4];
+    T_OK(MPIX_Isend_enqueue(&a, 1, MPI_INT, T_RIGHT, 2 + nchan, MPI_COMM_WORLD, &rq[2], MPIX_QUEUE_CUDA_STREAM, &st));
+    T_OK(MPIX_Isend_enqueue(&a2, 1, MPI_INT, T_RIGHT, 2, MPI_COMM_WORLD, &rq[3], MPIX_QUEUE_CUDA_STREAM, &st));
+    T_OK(MPIX_Irecv_enqueue(&b2, 1, MPI_INT, T_LEFT, 2, MPI_COMM_WORLD, &rq[0], MPIX_QUEUE_CUDA_STREAM, &st));
+    T_OK(MPIX_Irecv_enqueue(&b, 1, MPI_INT, T_LEFT, 2 + nchan, MPI_COMM_WORLD, &rq[1], MPIX_QUEUE_CUDA_STREAM, &st));
+    T_OK(MPIX_Waitall_enqueue(4, rq, sts, MPIX_QUEUE_CUDA_STREAM, &st));
     T_CUDA(cudaStreamSynchronize(st));
-    T_CHECK(sts[0].MPI_ERROR == MPI_ERR_TAG && sts[0].MPI_TAG == 2 + nchan, "tag collision: error %d tag %d (want MPI_ERR_TAG, the sender's tag)", sts[0].MPI_ERROR, sts[0].MPI_TAG);
+    T_CHECK(sts[0].MPI_ERROR == MPI_SUCCESS && sts[0].MPI_TAG == 2 && b2 == 4321 + T_LEFT, "tag 2: error %d tag %d value %d", sts[0].MPI_ERROR, sts[0].MPI_TAG, b2);
+    T_CHECK(sts[1].MPI_ERROR == MPI_SUCCESS && sts[1].MPI_TAG == 2 + nchan && b == 1234 + T_LEFT, "tag 2+nchan: error %d tag %d value %d", sts[1].MPI_ERROR, sts[1].MPI_TAG, b);
 }
 
 static void bad_arguments(void) {

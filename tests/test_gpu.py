@@ -316,3 +316,15 @@ def test_reinitialization(built, np_):
     r = acxrun(built, np_, built / "build/tests/reinit")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+@pytest.mark.parametrize("wild", [0, 1])
+def test_exact_tag_matching(built, np_, wild):
+    """24 tags to one peer (some colliding modulo 16 / 32) sent in the reverse of the receive order, eager and rendezvous
+    sizes mixed; the same tag on two communicators; 100 messages through one channel; with ACX_WILDCARDS=1 also
+    MPI_ANY_TAG / MPI_ANY_SOURCE next to specific receives — tests/c/tags.c (reference: tag and peer go to MPI untouched,
+    src/init.cpp:69-70,76-77)."""
+    r = acxrun(built, np_, built / "build/tests/tags", env={"ACX_WILDCARDS": str(wild)})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout

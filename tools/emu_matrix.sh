@@ -16,12 +16,16 @@ run() {  # run <label> <np> <prog> [env...]
     if [ $rc -eq 0 ] && echo "$out" | grep -q "PASS"; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms
     else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $rc "$(echo "$out" | grep -v "ASan doesn\x27t fully support" | tail -${EMU_TAIL:-8})"; fails=$((fails+1)); fi
 }
-progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors sendrecv_enqueue reinit"
+progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors sendrecv_enqueue reinit tags"
 nps="1 2 3"
 [ "$mode" = full ] && nps="1 2 3 4"
 for p in $progs; do for np in $nps; do run default $np $p; done; done
 run default 2 stress; run default 3 stress
 run wildcards 3 wildcards ACX_WILDCARDS=1
+run wildcards 3 tags ACX_WILDCARDS=1
+run wildcards 2 tags ACX_WILDCARDS=1
+run no-tagdir 2 ordering ACX_TAGDIR=0
+run nchan4-overflow 2 stress ACX_NCHAN=4
 run wildcards 2 wildcards ACX_WILDCARDS=1
 run wildcards 4 wildcards ACX_WILDCARDS=1
 run wildcards-coop 3 wildcards ACX_WILDCARDS=1 ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
