@@ -44,6 +44,49 @@ def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+
+# ------------------------------------------------------------------------------------------
+# Secondary numbers, same keys from BOTH arms: the shared C harnesses (bench/*.cu — one source, compiled once against
+# libacx and once with -DACX_BENCH_REFERENCE=1 against the unmodified reference) run as one process per rank under
+# the launcher's environment. Small-message ring steps, CUDA-graph all-pairs, API-level halo step, API-level
+# pipeline GEMM; the acx arm adds its fused kernels.
+def c_harness_extras(bindir: Path, world: int, local: int, rank: int, ref: bool, tag: str) -> dict:
+    import time
+    out: dict = {}
+    env = dict(os.environ)
+    env.setdefault("ACX_WATCHDOG_MS", "60000")
+    env["MPIACX_NFLAGS"] = "8192"
+    if not ref:
+        env["ACX_HEAP_BYTES"] = str(1 << 30)
+    noheap = ["--no-heap"] if ref else []
+    port = os.environ.get("MASTER_PORT", "0")
+    from mpi_acx_b200.utils.numa import gpu_numa_cpus
+    cpus = gpu_numa_cpus(local) if os.environ.get("ACX_NUMA_BIND", "1") != "0" else None
+    runs = []
+    for nb in (8, 4096, 1 << 20):
+        runs.append((f"ring_step_us_{nb}B", "p2p_bench", ["ring", "--bytes", str(nb), "--steps", "200", "--warmup", "20"] + noheap + ([] if ref else ["--sendrecv"]), lambda j: round(j["ms_per_step"] * 1e3, 3)))
+    if world >= 2:
+        for nb, name in ((1 << 20, "1MiB"), (16 << 20, "16MiB")):
+            runs.append((f"allpairs_graph_{name}_gbs_per_gpu", "p2p_bench", ["allpairs", "--bytes", str(nb)] + noheap, lambda j: round(j["gbs_per_gpu_out"], 2)))
+    runs.append(("halo_api_512cube_ms_per_step", "halo_bench", ["api", "--n", "512", "--steps", "10"], lambda j: round(j["ms_per_step"], 5)))
+    runs.append(("ppgemm_api_fp8_8192_ms_per_microbatch", "ppgemm_bench", ["api", "--steps", "10"], lambda j: round(j["ms_per_step"], 5)))
+    if not ref:
+        runs.append(("halo_fused_512cube_ms_per_step", "halo_bench", ["fused", "--n", "512", "--steps", "30"], lambda j: round(j["ms_per_step"], 5)))
+        runs.append(("ppgemm_fused_fp8_8192_ms_per_microbatch", "ppgemm_bench", ["fused", "--steps", "10"], lambda j: round(j["ms_per_step"], 5)))
+    for i, (key, exe, args, pick) in enumerate(runs):
+        env["ACX_JOBID"] = f"{tag}_{port}_{i}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}"
+        try:
+            p = subprocess.run([str(bindir / exe)] + args, env=env, capture_output=True, text=True, timeout=300,
+                               preexec_fn=(lambda: os.sched_setaffinity(0, cpus)) if cpus else None)
+            if rank == 0:
+                lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+                out[key] = pick(json.loads(lines[-1])) if p.returncode == 0 and lines else f"failed rc={p.returncode}: {(p.stderr or p.stdout)[-160:]!r}"
+        except Exception as ex:  # noqa: BLE001
+            if rank == 0:
+                out[key] = f"failed: {ex!r}"[:200]
+        time.sleep(0.2)
+    return out
+
 # ------------------------------------------------------------------------------------------
 def run_reference(a) -> int:
     rank, world, local = env_rank()
@@ -82,6 +125,7 @@ def run_reference(a) -> int:
             line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
             outs[phase] = json.loads(line)
             outs[phase + "_clocks"] = cs.summary
+    extras = {} if a.no_extras else c_harness_extras(REPO / "baseline" / "_ref" / "bin", world, local, rank, True, "refx")
     if rank == 0:
         d, e = outs["dev"], outs["e2e"]
         print(json.dumps({
@@ -92,7 +136,9 @@ def run_reference(a) -> int:
             "gpu_launches": None,
             "config": {"model": "ring Isend/Irecv_enqueue + Waitall_enqueue", "msg_bytes": a.bytes, "global_batch": a.bytes * world, "seq_len": None,
                        "parallelism": f"p2p-ring{world}", "l2": "working set 2x msg_bytes > L2, no flush",
+                       "order": "irecv, isend, waitall per step",
                        "note": "unmodified NVIDIA/mpi-acx (CPU proxy) over the bundled mini-MPI shim (shm + CUDA-IPC cudaMemcpyAsync); cudaMalloc buffers"},
+            "extra": extras,
         }))
     return 0
 
@@ -238,76 +284,45 @@ def run_acx(a) -> int:
     gbs = world * n / ms / 1e6
     gbs_e2e = world * n / ms_e2e / 1e6
 
+    e2e_desc = (f"{len(plan.bounds)} chunks: H2D of chunk i+1 overlaps the stream-triggered send of chunk i (mpi_acx_b200.parallel.staged)" if plan is not None else "copy, then send")
     extras = {}
     if not a.no_extras:
-        # small-message latency through the same API (ring of 8 B and 4 KiB messages, host buffers avoided)
+        # small-message ring step through the Python API: acx.sendrecv = MPIX_Sendrecv_enqueue, one call and (eager sizes)
+        # one kernel per exchange step — receive posted, send deposited, receive completed
         for nb in (8, 4096, 1 << 20):
             s2, r2 = acx.empty(nb, torch.uint8), acx.empty(nb, torch.uint8)
-            def small():
-                q = [acx.irecv(r2, left, 9), acx.isend(s2, right, 9)]
-                acx.waitall_enqueue(q)
             for _ in range(10):
-                small()
+                acx.sendrecv(s2, right, r2, left, 9)
             barrier()
             iters = 200
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for _ in range(iters):
-                small()
+                acx.sendrecv(s2, right, r2, left, 9)
             e1.record(stream)
             torch.cuda.synchronize()
-            extras[f"ring_step_us_{nb}B"] = round(max_over_ranks(e0.elapsed_time(e1)) / iters * 1e3, 3)
+            extras[f"ring_step_us_{nb}B_python"] = round(max_over_ranks(e0.elapsed_time(e1)) / iters * 1e3, 3)
             del s2, r2
         del sbuf, rbuf, got
         rbufs.clear()
         last_buf.clear()
+        plan = None
         sbuf = rbuf = None
-        # the two fused showcase kernels at this GPU count (BASELINE.json configs #3 and #4), best effort
-        try:
-            from mpi_acx_b200.models import Diffusion3D
-            m = Diffusion3D((512, 512, 512))
-            m.field.copy_(torch.randn(512, 512, 512, device="cuda").to(torch.bfloat16))
-            m.forward(3)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream); m.forward(20); e1.record(stream)
-            torch.cuda.synchronize()
-            hms = max_over_ranks(e0.elapsed_time(e1)) / 20
-            extras["halo_stencil_512cube_bf16_ms_per_step"] = round(hms, 5)
-            extras["halo_stencil_hbm_frac_of_measured_6571GBs"] = round(2 * 2 * 512 ** 3 / hms / 1e6 / 6570.9, 3)
-            extras["halo_decomp"] = list(m.decomp)
-            m.close()
-        except Exception as ex:  # noqa: BLE001
-            extras["halo_error"] = repr(ex)[:200]
-        try:
-            from mpi_acx_b200.models import PipelineLinearChain
-            pm = PipelineLinearChain(8192, 8192, 4)
-            pm.init_weights()
-            if rank == 0:
-                pm.op.input(0).copy_(torch.randn(8192, 8192, device="cuda").clamp_(-3, 3).to(torch.float8_e4m3fn))
-            barrier()
-            for _ in range(3):
-                pm.forward_microbatch()
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(10):
-                pm.forward_microbatch()
-            e1.record(stream)
-            torch.cuda.synchronize()
-            gms = max_over_ranks(e0.elapsed_time(e1)) / 10
-            extras["ppgemm_fp8_8192_ms_per_microbatch"] = round(gms, 5)
-            extras["ppgemm_fp8_tflops_total"] = round(world * 2 * 8192 ** 3 / gms / 1e9, 1)
-            barrier()
-            pm.close()
-        except Exception as ex:  # noqa: BLE001
-            extras["ppgemm_error"] = repr(ex)[:200]
+        barrier()
+        # the same C harnesses the reference arm runs (identical keys), plus the fused kernels
+        extras.update(c_harness_extras(REPO / "bin", world, local, rank, False, "acxx"))
+        hm = extras.get("halo_fused_512cube_ms_per_step")
+        if isinstance(hm, float):
+            extras["halo_fused_hbm_frac_of_measured_6571GBs"] = round(2 * 2 * 512 ** 3 / hm / 1e6 / 6570.9, 3)
+        gm = extras.get("ppgemm_fused_fp8_8192_ms_per_microbatch")
+        if isinstance(gm, float):
+            extras["ppgemm_fused_fp8_tflops_total"] = round(world * 2 * 8192 ** 3 / gm / 1e9, 1)
     out = {
         "metric": "ring_sendrecv_bandwidth", "value": round(gbs, 3), "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": W,
         "ms_per_step": round(ms, 6), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bytes", "data": "synthetic",
         "impl": "acx-b200", "verified": ok and ok_e2e, "clocks": clocks,
         "e2e": {"value": round(gbs_e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 4096, "ms_per_step": round(ms_e2e, 6),
-                "pipeline": (f"{len(plan.bounds)} chunks: H2D of chunk i+1 overlaps the stream-triggered send of chunk i (mpi_acx_b200.parallel.staged)" if plan is not None else "copy, then send")},
+                "pipeline": e2e_desc},
         "gpu_launches": int(launches),
         "config": {"model": "ring Isend/Irecv_enqueue + Waitall_enqueue", "msg_bytes": n, "global_batch": n * world, "seq_len": None,
                    "parallelism": f"p2p-ring{world}", "l2": "working set >= 2x msg_bytes > L2, no flush", "buffers": "symmetric heap (zero-copy NVLink push/pull)",

@@ -419,13 +419,16 @@ __device__ __forceinline__ void mover_body_t(const MoverParams &p) {
         __threadfence_system();   // one fence per CTA, cumulative over the CTA's stores (ordered by the barrier)
         unsigned t = atomicAdd(&op->cta_count, 1u);
         if (t == gridDim.x - 1) {
-            __threadfence();
+            // Every CTA fenced its own stores at system scope before it counted itself in; observing the full count (a
+            // gpu-scope atomic) makes them cumulative HERE, and the flags below must carry that to the other GPU: release
+            // at SYSTEM scope (a gpu-scope fence + relaxed.sys store is not a system-scope release in the PTX model).
             const uint64_t k = op->ticket;
             const uint32_t e = (uint32_t)(k % p.depth);
             const uint64_t g = k / p.depth;
             op->cta_count = 0;
-            st_relaxed_sys(&p.ring[e].done, g + 1);   // receiver may consume
-            st_relaxed_sys(&p.sack[e].sdone, g + 1);  // sender's buffer is reusable
+            __threadfence_system();
+            st_release_sys(&p.ring[e].done, g + 1);   // receiver may consume
+            st_release_sys(&p.sack[e].sdone, g + 1);  // sender's buffer is reusable
             trace(p.tr, ACX_EV_MOVE_END, p.peer, k, n);
         }
     }
@@ -656,13 +659,13 @@ __global__ void __launch_bounds__(kTmaThreads) mover_tma(MoverParams p) {
         __threadfence_system();
         unsigned t = atomicAdd(&op->cta_count, 1u);
         if (t == gridDim.x - 1) {
-            __threadfence();
             const uint64_t k = op->ticket;
             const uint32_t e = (uint32_t)(k % p.depth);
             const uint64_t g = k / p.depth;
             op->cta_count = 0;
-            st_relaxed_sys(&p.ring[e].done, g + 1);
-            st_relaxed_sys(&p.sack[e].sdone, g + 1);
+            __threadfence_system();
+            st_release_sys(&p.ring[e].done, g + 1);
+            st_release_sys(&p.sack[e].sdone, g + 1);
             trace(p.tr, ACX_EV_MOVE_END, p.peer, k, n);
         }
     }

@@ -585,10 +585,10 @@ void progress() {
     for (int p = 0; p < g.size; p++) if (!g_sendq[p].empty()) pump_sends(p);
     for (auto it = g_ipc_inflight.begin(); it != g_ipc_inflight.end();) {
         Req *r = *it;
-        if (g_cuda.EventQuery(r->ipc_event) == 0) {
-            g_cuda.EventDestroy(r->ipc_event); r->ipc_event = nullptr;
+        if (!r->ipc_event || g_cuda.EventQuery(r->ipc_event) == 0) {   // null: the copy finished on an earlier pass, only the FIN is still owed
+            if (r->ipc_event) { g_cuda.EventDestroy(r->ipc_event); r->ipc_event = nullptr; }
             CellHdr h{}; h.kind = CELL_FIN; h.cookie = r->ipc_cookie;
-            if (!ring_push(r->ipc_src, h, nullptr)) { ++it; continue; }  // retry FIN next round
+            if (!ring_push(r->ipc_src, h, nullptr)) { ++it; continue; }  // ring full: retry the FIN next round (the event is gone, see above)
             complete_recv(r, r->ipc_src, r->st.MPI_TAG, r->total);
             it = g_ipc_inflight.erase(it);
         } else {
