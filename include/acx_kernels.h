@@ -9,10 +9,17 @@ extern "C" {
 
 /* ---- halo exchange + 7-point stencil, bf16, periodic px*py*pz decomposition ------------ */
 typedef struct acx_halo acx_halo;
-/* Collective. Block nx*ny*nz per rank (multiples of 256/16/32). u_new = c0*u + c1*sum(6 nbrs). */
+/* Collective. Block nx*ny*nz per rank (nx 256 or 512, ny a multiple of 8, nz of 32). u_new = c0*u + c1*sum(6 nbrs).
+ * The two fields live in the symmetric heap WITH their ghost shell (neighbours store face cells into it in place), so
+ * the heap (ACX_HEAP_BYTES) must hold 2 x (nx+16)(ny+2)(nz+2) x 2 bytes. */
 int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, float c0, float c1, acx_halo **out);
-/* Device pointer (bf16, x fastest) of the current field; fill it before the first step. */
+/* Device pointer (bf16, x fastest) of interior cell (0,0,0) of the current field; the field is PITCHED: cell (x,y,z) sits
+ * at x + y*row_pitch + z*plane_pitch (acx_halo_field_pitch). Fill it before the first step — in place, or from / to a
+ * dense [nz][ny][nx] array with acx_halo_import_dense / acx_halo_export_dense. */
 void *acx_halo_field(acx_halo *h);
+void acx_halo_field_pitch(acx_halo *h, long long *row_pitch_cells, long long *plane_pitch_cells);
+int acx_halo_import_dense(acx_halo *h, const void *dense, cudaStream_t stream);
+int acx_halo_export_dense(acx_halo *h, void *dense, cudaStream_t stream);
 unsigned long long acx_halo_steps_done(acx_halo *h);
 int acx_halo_exchange_initial(acx_halo *h, cudaStream_t stream);
 /* Enqueue nsteps fused steps on `stream` (one kernel each; capturable in a CUDA graph). */

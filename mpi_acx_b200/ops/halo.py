@@ -8,15 +8,18 @@ from ..runtime import AcxError, _stream_arg
 
 
 class HaloStencil:
-    """Periodic px*py*pz decomposition, bf16 block nx*ny*nz per rank (multiples of 256/16/32).
-    One fused kernel per step: face tiles wait on the neighbour's arrival flags, compute, and store
-    their face cells straight into the neighbours' landing buffers over NVLink."""
+    """Periodic px*py*pz decomposition, bf16 block nx*ny*nz per rank (nx 256 or 512, ny % 8 == 0, nz % 32 == 0).
+    One fused kernel per step: TMA box loads feed a shared-memory plane ring, tiles acquire the neighbours' arrival flags,
+    compute, and store their face cells straight into the neighbours' ghost cells over NVLink (the fields live, with
+    their ghost shell, in the symmetric heap: ACX_HEAP_BYTES must hold both)."""
 
     def __init__(self, nx: int, ny: int, nz: int, decomp=(1, 1, 1), c0: float = 0.4, c1: float = 0.1):
         L = N.lib()
         L.acx_halo_create.argtypes = [ctypes.c_int] * 6 + [ctypes.c_float, ctypes.c_float, ctypes.POINTER(ctypes.c_void_p)]
         L.acx_halo_field.restype = ctypes.c_void_p
         L.acx_halo_field.argtypes = [ctypes.c_void_p]
+        L.acx_halo_field_pitch.restype = None
+        L.acx_halo_field_pitch.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]
         L.acx_halo_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.acx_halo_exchange_initial.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.acx_halo_destroy.argtypes = [ctypes.c_void_p]
@@ -29,13 +32,19 @@ class HaloStencil:
             raise AcxError("acx_halo_create failed")
 
     def field(self):
-        """Current field as a torch bf16 tensor [nz, ny, nx] (a view of device memory owned by the op)."""
+        """Current field as a torch bf16 tensor [nz, ny, nx]: a strided VIEW of the op's padded device array (rows and
+        planes are pitched: the ghost shell lives between them), so .copy_() / .float() / indexing work in place."""
         import torch
-        ptr = N.lib().acx_halo_field(self.h)
-        nbytes = self.shape[0] * self.shape[1] * self.shape[2] * 2
+        L = N.lib()
+        ptr = L.acx_halo_field(self.h)
+        rp, pp = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        L.acx_halo_field_pitch(self.h, ctypes.byref(rp), ctypes.byref(pp))
+        nz, ny, nx = self.shape
+        span = (nz - 1) * pp.value + (ny - 1) * rp.value + nx      # cells from the interior origin to the last interior cell
         holder = type("Buf", (), {})()
-        holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
-        return torch.as_tensor(holder, device="cuda").view(torch.bfloat16).view(self.shape)
+        holder.__cuda_array_interface__ = {"shape": (span * 2,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+        flat = torch.as_tensor(holder, device="cuda").view(torch.bfloat16)
+        return torch.as_strided(flat, (nz, ny, nx), (pp.value, rp.value, 1))
 
     def step(self, nsteps: int = 1, stream=None) -> None:
         cs = _stream_arg(stream)

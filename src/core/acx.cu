@@ -767,7 +767,7 @@ extern "C" int MPIX_Init(void) {
     cudaDeviceGetAttribute(&g_acx->host_ptr_is_dev_ptr, cudaDevAttrCanUseHostPointerForRegisteredMem, g_acx->dev);
 
     make_geom(g_acx->geom, g_acx->size);
-    acx_env_int("ACX_HEAP_BYTES", nullptr, 512L << 20, &v);
+    acx_env_int("ACX_HEAP_BYTES", nullptr, 1024L << 20, &v);   // 1 GiB of 180: the fused halo op keeps its two 512^3 fields (with ghost shell) here
     g_acx->heap_bytes = ((size_t)v + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
     cudaError_t e;
     if ((e = cudaMalloc((void **)&g_acx->ctrl, g_acx->geom.bytes)) != cudaSuccess || (e = cudaMalloc((void **)&g_acx->heap, g_acx->heap_bytes)) != cudaSuccess) {

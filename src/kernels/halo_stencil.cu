@@ -1,23 +1,32 @@
-// Fused halo-exchange + 3-D 7-point stencil for sm_100a (BASELINE.json config #3).
+// Fused halo-exchange + 3-D 7-point stencil for sm_100a (BASELINE.json config #3), round 2: TMA-fed.
 //
 // There is nothing like this in the reference (it never touches payload).
-// Each rank owns an nx*ny*nz bf16 block of a periodic px*py*pz decomposition. One kernel
-// per time step does everything:
-//   * tiles on a block face first wait (ld.acquire on LOCAL HBM flags) for the neighbour's
-//     face partition of the previous step, which the neighbour's kernel stored straight
-//     into this GPU's landing buffers over NVLink;
-//   * every tile z-marches through its 256x16x32 cells (16-B vector loads, fp32 math,
-//     y-neighbours through shared memory, x-neighbours through warp shuffles);
-//   * face cells are stored twice: into the local output array and — packed, 16-B vectors —
-//     into the neighbour's landing buffer (peer-mapped partitioned channel), followed by
-//     a release flag per partition (acx::pready_signal_epoch);
-//   * boundary tiles are scheduled first so the NVLink traffic overlaps the interior.
-// The 12+12 partitioned channels are ordinary MPIX_Psend_init/Precv_init requests on
-// symmetric-heap buffers; rounds advance on the device (explicit epochs), double-buffered.
+// Each rank owns an nx*ny*nz bf16 block of a periodic px*py*pz decomposition, stored WITH its ghost shell:
+//   row (y, z) = nx interior cells followed by 16 pad cells; pad[0] is the row's right ghost (x = nx) and pad[15] the
+//   NEXT row's left ghost (x = -1), so every interior row starts on a 32-B sector and "8 cells before the row" is a plain
+//   16-B vector; rows y = -1 and y = ny and planes z = -1 and z = nz are the y / z ghosts.
+// One kernel per time step does everything:
+//   * the field is read ONLY by TMA: cp.async.bulk.tensor.3d boxes of (whole padded row) x (TY + 2 rows) x (1 plane) —
+//     one contiguous 10.5 KB run of memory each — into a 6-stage shared-memory ring with full/empty mbarriers; the
+//     loads run 4 planes ahead of the math and straight through tile boundaries, so ~85 KB per SM are in flight at all
+//     times without a single register holding a prefetched operand (round 1: 113 registers, latency-bound at 34 % of HBM);
+//   * a tile is TY = 8 rows x all of x x TZ = 32 planes; thread (row, 8-cell vector) z-marches with the previous /
+//     current centre vectors in registers, reads the rows above / below and the next plane's centre from shared memory
+//     (3 LDS.128 per 8 cells), x-neighbours by warp shuffle (ghost / neighbouring-warp cells from shared memory);
+//   * ghost cells are written by the NEIGHBOURS: a tile's face cells are stored twice, into the local output field and —
+//     16-B vectors over NVLink — straight into the neighbour's ghost cells of ITS output field (peer-mapped symmetric
+//     heap), followed by one release flag per (face, tile) partition (acx::pready_signal_epoch on the partitioned
+//     channel); a tile's producer acquires the flags of the partitions its boxes cover (acx::wait_arrived_epoch, LOCAL
+//     HBM) and issues fence.proxy.async before its first TMA load;
+//   * tiles touching a y / z face are scheduled first so their NVLink stores overlap the interior sweep.
+// The 12 + 12 partitioned channels are ordinary MPIX_Psend_init / MPIX_Precv_init requests (flag-only use: the
+// producer stores the payload in place, the device API's zero-copy form); rounds advance on the device (explicit
+// epochs), the two fields alternate, and the stencil's own data dependence is the flow control (see acx_halo_step).
 // Host involvement per step: one kernel launch (capturable in a CUDA graph).
 #include <mpi.h>
 #include "../../include/mpi-acx.h"
 #include "../../include/acx_kernels.h"
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,25 +35,46 @@
 
 namespace {
 
-constexpr int TX = 256, TY = 16, TZ = 32;   // tile; 32 lanes x 8 cells along x, 16 rows, z-march of 32
-constexpr int LX = 32;
+constexpr int TY = 8, TZ = 32;      // tile: TY rows x all of x, z-march of TZ planes
+constexpr int STAGES = 6;           // shared-memory ring of planes
+constexpr int XPAD = 16;            // pad cells behind every row (see the layout comment above)
+constexpr int LAG = 2;              // a stage is refilled LAG planes after its last reader: the producer thread never waits for a sibling warp
 
 struct HaloDev {
-    const __nv_bfloat16 *u;
-    __nv_bfloat16 *un;
-    int nx, ny, nz, ntx, nty, ntz;
-    const acx_pchan *send[6];   // my face f -> neighbour in direction f (buffers of parity (s+1)&1)
-    const acx_pchan *recv[6];   // halo from direction f (parity s&1)
+    __nv_bfloat16 *un;              // interior origin (x = y = z = 0) of the local OUTPUT field
+    __nv_bfloat16 *nb[6];           // peer-mapped interior origins of the neighbours' output fields (face order X- X+ Y- Y+ Z- Z+)
+    int nx, ny, nz, nty, ntz, ntiles;
+    long long rp, pp;               // row / plane pitch in cells
+    const acx_pchan *send[6];       // flags: my face f -> neighbour in direction f
+    const acx_pchan *recv[6];       // flags: ghost cells behind face f have been written
     unsigned long long wait_val, signal_val;
     float c0, c1;
     const int *order;
-    int ntiles;
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "HW_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni HW_DONE;\n\t"
+        "bra.uni HW_LOOP;\n\t"
+        "HW_DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *tm, uint64_t *bar, void *dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 __device__ __forceinline__ void unpack8(const uint4 &v, float f[8]) {
-    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < 4; i++) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    for (int i = 0; i < 4; i++) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
 __device__ __forceinline__ uint4 pack8(const float f[8]) {
     uint4 v;
@@ -53,547 +83,165 @@ __device__ __forceinline__ uint4 pack8(const float f[8]) {
     for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
     return v;
 }
-__device__ __forceinline__ void unpack8x2(const uint4 &v, float2 f[4]) {
-    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; i++) f[i] = __bfloat1622float2(h[i]);
-}
-__device__ __forceinline__ uint4 pack8x2(const float2 f[4]) {
-    uint4 v;
-    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; i++) h[i] = __float22bfloat162_rn(f[i]);
-    return v;
-}
-__device__ __forceinline__ float bf(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
 
-// Face ids: 0 X-, 1 X+, 2 Y-, 3 Y+, 4 Z-, 5 Z+.
-// PD = software-pipeline depth of the z-march (planes in flight per thread); MINB = CTAs per SM the
-// register allocation is tuned for. Variants are selected at run time (ACX_HALO_VARIANT).
-template <int PD, int MINB>
-__global__ void __launch_bounds__(LX * TY, MINB) halo_stencil_step(HaloDev P) {
-    static_assert(TZ % PD == 0, "TZ must be a multiple of the prefetch depth");
-    __shared__ uint4 rows[2][TY][LX];                 // current plane, double-buffered (16 KiB)
-    __shared__ __align__(16) __nv_bfloat16 xface[2][TZ * TY];  // packed X-/X+ face of this tile (2 KiB)
-    const int lx = threadIdx.x, ly = threadIdx.y;
-    const int tid = ly * LX + lx;
-    const size_t plane = (size_t)P.nx * P.ny;
-    for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x) {
+// Face ids: 0 X-, 1 X+, 2 Y-, 3 Y+, 4 Z-, 5 Z+. Partition index of tile (ty, tc): x faces ty + nty * tc (every tile
+// touches both), y faces tc (tiles with ty == 0 / nty-1), z faces ty (tiles with tc == 0 / ntz-1).
+__global__ void __launch_bounds__(512, 2) halo_stencil_tma(const __grid_constant__ CUtensorMap tm, HaloDev P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int vpr = P.nx >> 3;                                   // 16-B vectors per row
+    const int ly = tid / vpr, vx = tid - ly * vpr;
+    const uint32_t row_bytes = (uint32_t)(P.nx + XPAD) * 2u;     // one padded row
+    const uint32_t stage_bytes = row_bytes * (TY + 2);           // what one box delivers
+    const uint32_t stage_stride = (stage_bytes + 127u) & ~127u;  // TMA destinations are 128-B aligned
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * stage_stride);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tile_done = empty + STAGES;                        // one per parity of the tile counter
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)nwarps); }
+        mbar_init(&tile_done[0], (uint32_t)nwarps); mbar_init(&tile_done[1], (uint32_t)nwarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- producer state (thread 0 only): a stream of planes that runs through tile boundaries ----
+    int p_it = blockIdx.x;      // tile iterator of the producer
+    int p_q = 0;                // next plane of that tile to load (0 .. TZ+1)
+    uint32_t p_cnt = 0;         // planes loaded so far (selects stage and phase)
+    auto produce = [&](uint32_t consumed) {   // `consumed` = planes every reader has certainly released (see LAG)
+        while (p_it < P.ntiles && p_cnt < consumed + (uint32_t)STAGES) {
+            const int t = P.order[p_it];
+            const int ty = t % P.nty, tc = t / P.nty;
+            if (p_q == 0) {
+                // the ghost cells this tile's boxes cover were written by the neighbours' previous step: acquire their flags
+                acx::wait_arrived_epoch(P.recv[0], t, P.wait_val);
+                acx::wait_arrived_epoch(P.recv[1], t, P.wait_val);
+                if (ty == 0) acx::wait_arrived_epoch(P.recv[2], tc, P.wait_val);
+                if (ty == P.nty - 1) acx::wait_arrived_epoch(P.recv[3], tc, P.wait_val);
+                if (tc == 0) acx::wait_arrived_epoch(P.recv[4], ty, P.wait_val);
+                if (tc == P.ntz - 1) acx::wait_arrived_epoch(P.recv[5], ty, P.wait_val);
+                asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes (remote stores, made visible by the acquire) before async-proxy reads
+            }
+            const uint32_t s = p_cnt % STAGES, use = p_cnt / STAGES;
+            mbar_wait(&empty[s], (use & 1u) ^ 1u);                 // every warp is done with the stage's previous plane
+            mbar_expect_tx(&full[s], stage_bytes);
+            // box origin in the padded tensor: u64 column 0 (= 16 B before the interior row), padded row ty*TY, padded plane tc*TZ + q
+            tma_load_3d(&tm, &full[s], smem + (size_t)s * stage_stride, 0, ty * TY, tc * TZ + p_q);
+            p_cnt++;
+            if (++p_q == TZ + 2) { p_q = 0; p_it += gridDim.x; }
+        }
+    };
+
+    uint32_t c_cnt = 0;         // planes consumed so far by this thread's warp
+    uint32_t tile_no = 0;
+    if (tid == 0) produce(0);
+    for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x, tile_no++) {
         const int t = P.order[it];
-        const int tx = t % P.ntx, ty = (t / P.ntx) % P.nty, tz = t / (P.ntx * P.nty);
-        const bool fxm = tx == 0, fxp = tx == P.ntx - 1, fym = ty == 0, fyp = ty == P.nty - 1, fzm = tz == 0, fzp = tz == P.ntz - 1;
-        const int px_ = tz * P.nty + ty, py_ = tz * P.ntx + tx, pz_ = ty * P.ntx + tx;   // partition index per face family
-        if (tid == 0) {
-            if (fxm) acx::wait_arrived_epoch(P.recv[0], px_, P.wait_val);
-            if (fxp) acx::wait_arrived_epoch(P.recv[1], px_, P.wait_val);
-            if (fym) acx::wait_arrived_epoch(P.recv[2], py_, P.wait_val);
-            if (fyp) acx::wait_arrived_epoch(P.recv[3], py_, P.wait_val);
-            if (fzm) acx::wait_arrived_epoch(P.recv[4], pz_, P.wait_val);
-            if (fzp) acx::wait_arrived_epoch(P.recv[5], pz_, P.wait_val);
-        }
-        __syncthreads();
-        const int x0 = tx * TX + lx * 8, y = ty * TY + ly, z0 = tz * TZ;
-        // landing buffers (local) and remote partitions for this tile
-        const __nv_bfloat16 *hxm = fxm ? (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[0], px_) : nullptr;
-        const __nv_bfloat16 *hxp = fxp ? (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[1], px_) : nullptr;
-        const uint4 *hym = fym ? (const uint4 *)acx::local_partition_ptr(P.recv[2], py_) : nullptr;
-        const uint4 *hyp = fyp ? (const uint4 *)acx::local_partition_ptr(P.recv[3], py_) : nullptr;
-        const uint4 *hzm = fzm ? (const uint4 *)acx::local_partition_ptr(P.recv[4], pz_) : nullptr;
-        const uint4 *hzp = fzp ? (const uint4 *)acx::local_partition_ptr(P.recv[5], pz_) : nullptr;
-        uint4 *rym = fym ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[2], py_) : nullptr;
-        uint4 *ryp = fyp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[3], py_) : nullptr;
-        uint4 *rzm = fzm ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[4], pz_) : nullptr;
-        uint4 *rzp = fzp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[5], pz_) : nullptr;
+        const int ty = t % P.nty, tc = t / P.nty;
+        const int y = ty * TY + ly, z0 = tc * TZ, x0 = vx * 8;
+        const bool fym = y == 0, fyp = y == P.ny - 1, fxm = vx == 0, fxp = vx == vpr - 1;
+        const uint32_t row_off = (uint32_t)(ly + 1) * row_bytes + 16u + (uint32_t)x0 * 2u;   // my vector inside a stage
+        auto stage_of = [&](uint32_t cnt) -> const unsigned char * { return smem + (size_t)(cnt % STAGES) * stage_stride; };
+        auto wait_full = [&](uint32_t cnt) { mbar_wait(&full[cnt % STAGES], (cnt / STAGES) & 1u); };
+        auto release = [&](uint32_t cnt) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[cnt % STAGES]); };
 
-        const __nv_bfloat16 *col = P.u + (size_t)y * P.nx + x0;   // + z*plane
-        auto load_plane = [&](int z) -> uint4 {
-            if (z < 0) return hzm[ly * LX + lx];
-            if (z >= P.nz) return hzp[ly * LX + lx];
-            return *reinterpret_cast<const uint4 *>(col + (size_t)z * plane);
-        };
-        // Edge operands come from global memory / landing buffers instead of shared memory; they are
-        // software-pipelined PD planes ahead exactly like the centre column, so no thread ever issues a
-        // load in the same iteration that consumes it.
-        const bool yedge = ly == 0 || ly == TY - 1, xedge = lx == 0 || lx == LX - 1;
-        const bool ylow = ly == 0, xlow = lx == 0;
-        auto load_yrow = [&](int zl) -> uint4 {   // row y-1 (ly==0) or y+1 (ly==TY-1) of plane z0+zl
-            const size_t zoff = (size_t)(z0 + zl) * plane;
-            if (ylow) return fym ? hym[zl * LX + lx] : *reinterpret_cast<const uint4 *>(col + zoff - P.nx);
-            return fyp ? hyp[zl * LX + lx] : *reinterpret_cast<const uint4 *>(col + zoff + P.nx);
-        };
-        auto load_xedge = [&](int zl) -> __nv_bfloat16 {   // cell x0-1 (lane 0) or x0+8 (lane 31) of plane z0+zl
-            const size_t zoff = (size_t)(z0 + zl) * plane;
-            if (xlow) return fxm ? hxm[zl * TY + ly] : col[zoff - 1];
-            return fxp ? hxp[zl * TY + ly] : col[zoff + 8];
-        };
-        uint4 q[PD], qy[PD];
-        __nv_bfloat16 qx[PD];
-#pragma unroll
-        for (int j = 0; j < PD; j++) {
-            q[j] = load_plane(z0 + 1 + j);
-            if (yedge) qy[j] = load_yrow(j);
-            if (xedge) qx[j] = load_xedge(j);
-        }
         float prev[8], cur[8];
-        uint4 vcur = load_plane(z0);
-        unpack8(load_plane(z0 - 1), prev);
-        unpack8(vcur, cur);
-#pragma unroll 1
-        for (int zb = 0; zb < TZ; zb += PD) {
-#pragma unroll
-            for (int j = 0; j < PD; j++) {
-                const int zl = zb + j, z = z0 + zl;
-                const uint4 vnext = q[j];
-                const uint4 vy = qy[j];
-                const __nv_bfloat16 vx = qx[j];
-                if (zl + 1 + PD <= TZ) q[j] = load_plane(z + 1 + PD);
-                if (zl + PD < TZ) {
-                    if (yedge) qy[j] = load_yrow(zl + PD);
-                    if (xedge) qx[j] = load_xedge(zl + PD);
-                }
-                rows[zl & 1][ly][lx] = vcur;
-                float left = __shfl_up_sync(0xffffffffu, cur[7], 1), right = __shfl_down_sync(0xffffffffu, cur[0], 1);
-                if (lx == 0) left = __bfloat162float(vx);
-                if (lx == LX - 1) right = __bfloat162float(vx);
-                __syncthreads();
-                float ym[8], yp[8], nxt[8];
-                unpack8(ly > 0 ? rows[zl & 1][ly - 1][lx] : vy, ym);
-                unpack8(ly < TY - 1 ? rows[zl & 1][ly + 1][lx] : vy, yp);
-                unpack8(vnext, nxt);
-                float out[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float xm = i == 0 ? left : cur[i - 1], xp = i == 7 ? right : cur[i + 1];
-                    out[i] = P.c0 * cur[i] + P.c1 * (((xm + xp) + (ym[i] + yp[i])) + (prev[i] + nxt[i]));
-                }
-                const uint4 vo = pack8(out);
-                *reinterpret_cast<uint4 *>(P.un + (size_t)z * plane + (size_t)y * P.nx + x0) = vo;
-                // face cells also go straight into the neighbours' landing buffers (NVLink stores)
-                if (fzm && zl == 0) rzm[ly * LX + lx] = vo;
-                if (fzp && zl == TZ - 1) rzp[ly * LX + lx] = vo;
-                if (fym && ly == 0) rym[zl * LX + lx] = vo;
-                if (fyp && ly == TY - 1) ryp[zl * LX + lx] = vo;
-                if (fxm && lx == 0) xface[0][zl * TY + ly] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[0];
-                if (fxp && lx == LX - 1) xface[1][zl * TY + ly] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[7];
-#pragma unroll
-                for (int i = 0; i < 8; i++) { prev[i] = cur[i]; cur[i] = nxt[i]; }
-                vcur = vnext;
-            }
-        }
-        __syncthreads();
-        if (fxm && tid < TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[0], px_))[tid] = ((const uint4 *)xface[0])[tid];
-        if (fxp && tid >= 64 && tid < 64 + TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[1], px_))[tid - 64] = ((const uint4 *)xface[1])[tid - 64];
-        if (fxm | fxp | fym | fyp | fzm | fzp) {
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence_system();   // one cumulative fence (the barrier ordered the other threads' stores before it)
-                if (fxm) acx::pready_signal_epoch(px_, P.send[0], P.signal_val);
-                if (fxp) acx::pready_signal_epoch(px_, P.send[1], P.signal_val);
-                if (fym) acx::pready_signal_epoch(py_, P.send[2], P.signal_val);
-                if (fyp) acx::pready_signal_epoch(py_, P.send[3], P.signal_val);
-                if (fzm) acx::pready_signal_epoch(pz_, P.send[4], P.signal_val);
-                if (fzp) acx::pready_signal_epoch(pz_, P.send[5], P.signal_val);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Barrier-free variant (default): 4 warps per CTA, each warp owns 4 rows x 256 columns of the tile
-// and z-marches on its own — y-neighbours of the strip's inner rows are already in registers, the two
-// rows above/below come from global memory (the adjacent warp loaded them a moment ago: L1/L2 hits)
-// or from the Y landing buffers, software-pipelined one plane ahead. No shared-memory exchange and no
-// __syncthreads inside the march; ~3x fewer instructions per cell than the shared-memory variants.
-// Same tile geometry (256x16x32), same partitions, same flags.
-// ---------------------------------------------------------------------------------------------
-constexpr int RW = 4;              // rows per warp
-constexpr int NW = TY / RW;        // warps per CTA
-
-template <int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB) halo_stencil_step_rows(HaloDev P) {
-    __shared__ __align__(16) __nv_bfloat16 xface[2][TZ * TY];
-    const int lx = threadIdx.x & 31, w = threadIdx.x >> 5, tid = threadIdx.x;
-    const size_t plane = (size_t)P.nx * P.ny;
-    for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x) {
-        const int t = P.order[it];
-        const int tx = t % P.ntx, ty = (t / P.ntx) % P.nty, tz = t / (P.ntx * P.nty);
-        const bool fxm = tx == 0, fxp = tx == P.ntx - 1, fym = ty == 0, fyp = ty == P.nty - 1, fzm = tz == 0, fzp = tz == P.ntz - 1;
-        const int px_ = tz * P.nty + ty, py_ = tz * P.ntx + tx, pz_ = ty * P.ntx + tx;
-        if (tid == 0) {
-            if (fxm) acx::wait_arrived_epoch(P.recv[0], px_, P.wait_val);
-            if (fxp) acx::wait_arrived_epoch(P.recv[1], px_, P.wait_val);
-            if (fym) acx::wait_arrived_epoch(P.recv[2], py_, P.wait_val);
-            if (fyp) acx::wait_arrived_epoch(P.recv[3], py_, P.wait_val);
-            if (fzm) acx::wait_arrived_epoch(P.recv[4], pz_, P.wait_val);
-            if (fzp) acx::wait_arrived_epoch(P.recv[5], pz_, P.wait_val);
-        }
-        __syncthreads();
-        const int x0 = tx * TX + lx * 8, yl0 = w * RW, y0 = ty * TY + yl0, z0 = tz * TZ;
-        const __nv_bfloat16 *hxm = fxm ? (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[0], px_) : nullptr;
-        const __nv_bfloat16 *hxp = fxp ? (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[1], px_) : nullptr;
-        const uint4 *hym = fym ? (const uint4 *)acx::local_partition_ptr(P.recv[2], py_) : nullptr;
-        const uint4 *hyp = fyp ? (const uint4 *)acx::local_partition_ptr(P.recv[3], py_) : nullptr;
-        const uint4 *hzm = fzm ? (const uint4 *)acx::local_partition_ptr(P.recv[4], pz_) : nullptr;
-        const uint4 *hzp = fzp ? (const uint4 *)acx::local_partition_ptr(P.recv[5], pz_) : nullptr;
-        uint4 *rym = fym ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[2], py_) : nullptr;
-        uint4 *ryp = fyp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[3], py_) : nullptr;
-        uint4 *rzm = fzm ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[4], pz_) : nullptr;
-        uint4 *rzp = fzp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[5], pz_) : nullptr;
-        const __nv_bfloat16 *col = P.u + (size_t)y0 * P.nx + x0;            // row r, plane z: col + z*plane + r*nx
-        __nv_bfloat16 *ocol = P.un + (size_t)y0 * P.nx + x0;
-        const bool top = w == 0, bot = w == NW - 1;
-        auto load_own = [&](int z, int r) -> uint4 {                          // own row r of plane z (z may be the z-halo)
-            if (z < 0) return hzm[(yl0 + r) * LX + lx];
-            if (z >= P.nz) return hzp[(yl0 + r) * LX + lx];
-            return *reinterpret_cast<const uint4 *>(col + (size_t)z * plane + (size_t)r * P.nx);
-        };
-        auto load_halo_lo = [&](int zl) -> uint4 {                            // row y0-1 of plane z0+zl
-            if (top && fym) return hym[zl * LX + lx];
-            return *reinterpret_cast<const uint4 *>(col + (size_t)(z0 + zl) * plane - P.nx);
-        };
-        auto load_halo_hi = [&](int zl) -> uint4 {                            // row y0+RW of plane z0+zl
-            if (bot && fyp) return hyp[zl * LX + lx];
-            return *reinterpret_cast<const uint4 *>(col + (size_t)(z0 + zl) * plane + (size_t)RW * P.nx);
-        };
-        auto load_xe = [&](int zl, int r) -> __nv_bfloat16 {                  // lane 0: cell x0-1; lane 31: cell x0+8
-            const size_t o = (size_t)(z0 + zl) * plane + (size_t)r * P.nx;
-            if (lx == 0) return fxm ? hxm[zl * TY + yl0 + r] : col[o - 1];
-            return fxp ? hxp[zl * TY + yl0 + r] : col[o + 8];
-        };
-        const bool xedge = lx == 0 || lx == LX - 1;
-        float prev[RW][8], cur[RW][8];
-        uint4 nxt[RW], hlo, hhi;
-        __nv_bfloat16 xe[RW];
-#pragma unroll
-        for (int r = 0; r < RW; r++) {
-            unpack8(load_own(z0 - 1, r), prev[r]);
-            unpack8(load_own(z0, r), cur[r]);
-            nxt[r] = load_own(z0 + 1, r);
-            xe[r] = xedge ? load_xe(0, r) : __float2bfloat16(0.f);
-        }
-        hlo = load_halo_lo(0); hhi = load_halo_hi(0);
+        wait_full(c_cnt);                                          // plane z0-1: only its centre row is needed
+        unpack8(*reinterpret_cast<const uint4 *>(stage_of(c_cnt) + row_off), prev);
+        release(c_cnt);
+        wait_full(c_cnt + 1);                                      // plane z0
+        unpack8(*reinterpret_cast<const uint4 *>(stage_of(c_cnt + 1) + row_off), cur);
+        __nv_bfloat16 *orow = P.un + (long long)z0 * P.pp + (long long)y * P.rp + x0;
+        const long long face_off = (long long)z0 * P.pp + (long long)y * P.rp;   // row origin relative to an interior origin
 #pragma unroll 1
         for (int zl = 0; zl < TZ; zl++) {
-            const int z = z0 + zl;
-            // consume this plane's prefetched operands ...
-            uint4 vn[RW];
-            float edge[RW];
+            const uint32_t cc = c_cnt + 1 + (uint32_t)zl;         // counter of the current plane; cc+1 = next plane
+            wait_full(cc + 1);
+            const unsigned char *sc = stage_of(cc), *sn = stage_of(cc + 1);
+            const uint4 vn = *reinterpret_cast<const uint4 *>(sn + row_off);
+            const uint4 vm = *reinterpret_cast<const uint4 *>(sc + row_off - row_bytes);
+            const uint4 vp = *reinterpret_cast<const uint4 *>(sc + row_off + row_bytes);
+            float left = __shfl_up_sync(0xffffffffu, cur[7], 1), right = __shfl_down_sync(0xffffffffu, cur[0], 1);
+            if (lane == 0) left = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sc + row_off - 2));      // x0-1: ghost (vx == 0) or the neighbouring warp's cell
+            if (lane == 31) right = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sc + row_off + 16));    // x0+8: ghost (last vector) or the neighbouring warp's cell
+            float ym[8], yp[8], nxt[8], out[8];
+            unpack8(vm, ym); unpack8(vp, yp); unpack8(vn, nxt);
 #pragma unroll
-            for (int r = 0; r < RW; r++) { vn[r] = nxt[r]; edge[r] = __bfloat162float(xe[r]); }
-            const uint4 vlo = hlo, vhi = hhi;
-            // ... and put the next plane's in flight before the math
-            if (zl + 1 < TZ) {
-#pragma unroll
-                for (int r = 0; r < RW; r++) { nxt[r] = load_own(z + 2, r); if (xedge) xe[r] = load_xe(zl + 1, r); }
-                hlo = load_halo_lo(zl + 1); hhi = load_halo_hi(zl + 1);
+            for (int i = 0; i < 8; i++) {
+                const float xm = i == 0 ? left : cur[i - 1], xp = i == 7 ? right : cur[i + 1];
+                out[i] = P.c0 * cur[i] + P.c1 * (((xm + xp) + (ym[i] + yp[i])) + (prev[i] + nxt[i]));
             }
-            float below[8];                       // old value of the row beneath the one being updated (y-1)
-            unpack8(vlo, below);
+            const uint4 vo = pack8(out);
+            const long long zoff = (long long)zl * P.pp;
+            *reinterpret_cast<uint4 *>(orow + zoff) = vo;
+            // face cells also go straight into the neighbours' ghost cells (NVLink stores; self for a periodic dimension of extent 1)
+            if (fxm) *reinterpret_cast<uint4 *>(P.nb[0] + face_off + zoff + P.nx) = vo;                       // their right ghost vector [nx, nx+8): cell 0 is the one they read
+            if (fxp) *reinterpret_cast<uint4 *>(P.nb[1] + face_off + zoff - 8) = vo;                          // their left ghost vector [-8, 0): cell 7 is x = -1
+            if (fym) *reinterpret_cast<uint4 *>(P.nb[2] + face_off + zoff + (long long)P.ny * P.rp + x0) = vo;   // their row y = ny
+            if (fyp) *reinterpret_cast<uint4 *>(P.nb[3] + face_off + zoff - (long long)P.ny * P.rp + x0) = vo;   // their row y = -1
+            if (z0 + zl == 0) *reinterpret_cast<uint4 *>(P.nb[4] + face_off + zoff + (long long)P.nz * P.pp + x0) = vo;          // their plane z = nz
+            if (z0 + zl == P.nz - 1) *reinterpret_cast<uint4 *>(P.nb[5] + face_off + zoff - (long long)P.nz * P.pp + x0) = vo;   // their plane z = -1
 #pragma unroll
-            for (int r = 0; r < RW; r++) {
-                float above[8], nf[8], out[8];
-                if (r < RW - 1) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) above[i] = cur[r + 1][i];
-                } else unpack8(vhi, above);
-                unpack8(vn[r], nf);
-                float left = __shfl_up_sync(0xffffffffu, cur[r][7], 1), right = __shfl_down_sync(0xffffffffu, cur[r][0], 1);
-                if (lx == 0) left = edge[r];
-                if (lx == LX - 1) right = edge[r];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const float xm = i == 0 ? left : cur[r][i - 1], xp = i == 7 ? right : cur[r][i + 1];
-                    out[i] = P.c0 * cur[r][i] + P.c1 * (((xm + xp) + (below[i] + above[i])) + (prev[r][i] + nf[i]));
-                }
-                const uint4 vo = pack8(out);
-                *reinterpret_cast<uint4 *>(ocol + (size_t)z * plane + (size_t)r * P.nx) = vo;
-                if (fzm && zl == 0) rzm[(yl0 + r) * LX + lx] = vo;
-                if (fzp && zl == TZ - 1) rzp[(yl0 + r) * LX + lx] = vo;
-                if (fym && top && r == 0) rym[zl * LX + lx] = vo;
-                if (fyp && bot && r == RW - 1) ryp[zl * LX + lx] = vo;
-                if (fxm && lx == 0) xface[0][zl * TY + yl0 + r] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[0];
-                if (fxp && lx == LX - 1) xface[1][zl * TY + yl0 + r] = reinterpret_cast<const __nv_bfloat16 *>(&vo)[7];
-#pragma unroll
-                for (int i = 0; i < 8; i++) { below[i] = cur[r][i]; prev[r][i] = cur[r][i]; cur[r][i] = nf[i]; }
-            }
+            for (int i = 0; i < 8; i++) { prev[i] = cur[i]; cur[i] = nxt[i]; }
+            release(cc);                                           // rows above / below of the current plane have been read
+            if (tid == 0) produce(cc >= (uint32_t)LAG ? cc - LAG + 1 : 0);   // planes 0 .. cc-LAG were released by everyone at least LAG iterations ago (or the wait inside is short)
         }
-        __syncthreads();
-        if (fxm && tid < TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[0], px_))[tid] = ((const uint4 *)xface[0])[tid];
-        if (fxp && tid >= 64 && tid < 64 + TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[1], px_))[tid - 64] = ((const uint4 *)xface[1])[tid - 64];
-        if (fxm | fxp | fym | fyp | fzm | fzp) {
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence_system();
-                if (fxm) acx::pready_signal_epoch(px_, P.send[0], P.signal_val);
-                if (fxp) acx::pready_signal_epoch(px_, P.send[1], P.signal_val);
-                if (fym) acx::pready_signal_epoch(py_, P.send[2], P.signal_val);
-                if (fyp) acx::pready_signal_epoch(py_, P.send[3], P.signal_val);
-                if (fzm) acx::pready_signal_epoch(pz_, P.send[4], P.signal_val);
-                if (fzp) acx::pready_signal_epoch(pz_, P.send[5], P.signal_val);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// "direct" variant (default): one row of 8 cells per thread, 512 threads per CTA, no shared-memory
-// exchange and no barrier inside the z-march. y-neighbours are read straight from global memory (the
-// warps above/below fetch the same rows as their centre: L1/L2 hits, DRAM traffic stays 1x), or from
-// the packed Y landing buffers on face tiles. Every operand source is resolved ONCE per tile into a
-// (pointer, plane-stride) pair, so the loop body is pointer bumps + 3 vector loads issued a full plane
-// ahead + fp32 math: ~2x fewer instructions than the other variants and <= 64 registers (2 CTAs/SM).
-// ---------------------------------------------------------------------------------------------
-template <int MINB>
-__global__ void __launch_bounds__(LX * TY, MINB) halo_stencil_step_direct(HaloDev P) {
-    __shared__ __align__(16) __nv_bfloat16 xface[2][TZ * TY];
-    const int lx = threadIdx.x, ly = threadIdx.y, tid = ly * LX + lx;
-    const size_t plane = (size_t)P.nx * P.ny;
-    for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x) {
-        const int t = P.order[it];
-        const int tx = t % P.ntx, ty = (t / P.ntx) % P.nty, tz = t / (P.ntx * P.nty);
-        const bool fxm = tx == 0, fxp = tx == P.ntx - 1, fym = ty == 0, fyp = ty == P.nty - 1, fzm = tz == 0, fzp = tz == P.ntz - 1;
-        const int px_ = tz * P.nty + ty, py_ = tz * P.ntx + tx, pz_ = ty * P.ntx + tx;
+        release(c_cnt + 1 + TZ);                                   // plane z0+TZ: centre only
+        c_cnt += TZ + 2;
+        // ---- publish the tile's faces: every warp's stores -> tile barrier -> one system-scope fence -> flags ----
+        __syncwarp();
+        if (lane == 0) { __threadfence(); mbar_arrive(&tile_done[tile_no & 1]); }
         if (tid == 0) {
-            if (fxm) acx::wait_arrived_epoch(P.recv[0], px_, P.wait_val);
-            if (fxp) acx::wait_arrived_epoch(P.recv[1], px_, P.wait_val);
-            if (fym) acx::wait_arrived_epoch(P.recv[2], py_, P.wait_val);
-            if (fyp) acx::wait_arrived_epoch(P.recv[3], py_, P.wait_val);
-            if (fzm) acx::wait_arrived_epoch(P.recv[4], pz_, P.wait_val);
-            if (fzp) acx::wait_arrived_epoch(P.recv[5], pz_, P.wait_val);
+            mbar_wait(&tile_done[tile_no & 1], (tile_no >> 1) & 1u);
+            __threadfence_system();
+            acx::pready_signal_epoch(t, P.send[0], P.signal_val);
+            acx::pready_signal_epoch(t, P.send[1], P.signal_val);
+            if (ty == 0) acx::pready_signal_epoch(tc, P.send[2], P.signal_val);
+            if (ty == P.nty - 1) acx::pready_signal_epoch(tc, P.send[3], P.signal_val);
+            if (tc == 0) acx::pready_signal_epoch(ty, P.send[4], P.signal_val);
+            if (tc == P.ntz - 1) acx::pready_signal_epoch(ty, P.send[5], P.signal_val);
         }
-        __syncthreads();
-        const int x0 = tx * TX + lx * 8, y = ty * TY + ly, z0 = tz * TZ;
-        const __nv_bfloat16 *c0p = P.u + (size_t)z0 * plane + (size_t)y * P.nx + x0;   // centre cell of plane z0
-        // --- operand sources, resolved once per tile: (pointer at plane z0, stride per plane in 16-B units or elements)
-        const uint4 *pc = reinterpret_cast<const uint4 *>(c0p);                 // own row
-        const size_t sc = plane / 8;
-        const uint4 *pym, *pyp; size_t sym, syp;                                // rows y-1 / y+1
-        if (ly == 0 && fym) { pym = (const uint4 *)acx::local_partition_ptr(P.recv[2], py_) + lx; sym = LX; }
-        else { pym = reinterpret_cast<const uint4 *>(c0p - P.nx); sym = sc; }
-        if (ly == TY - 1 && fyp) { pyp = (const uint4 *)acx::local_partition_ptr(P.recv[3], py_) + lx; syp = LX; }
-        else { pyp = reinterpret_cast<const uint4 *>(c0p + P.nx); syp = sc; }
-        const __nv_bfloat16 *pxe = c0p; size_t sxe = 0;                         // x-edge cell (lanes 0 and 31 only)
-        const bool xedge = lx == 0 || lx == LX - 1;
-        if (lx == 0) { if (fxm) { pxe = (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[0], px_) + ly; sxe = TY; } else { pxe = c0p - 1; sxe = plane; } }
-        if (lx == LX - 1) { if (fxp) { pxe = (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[1], px_) + ly; sxe = TY; } else { pxe = c0p + 8; sxe = plane; } }
-        uint4 *po = reinterpret_cast<uint4 *>(P.un + (size_t)z0 * plane + (size_t)y * P.nx + x0);
-        // remote landing buffers (packed): y faces advance one row of LX vectors per plane
-        uint4 *rym = (fym && ly == 0) ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[2], py_) + lx : nullptr;
-        uint4 *ryp = (fyp && ly == TY - 1) ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[3], py_) + lx : nullptr;
-        uint4 *rzm = fzm ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[4], pz_) + ly * LX + lx : nullptr;
-        uint4 *rzp = fzp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[5], pz_) + ly * LX + lx : nullptr;
-        __nv_bfloat16 *sxm = (fxm && lx == 0) ? &xface[0][ly] : nullptr, *sxp = (fxp && lx == LX - 1) ? &xface[1][ly] : nullptr;
-        // --- prologue: planes z0-1, z0, z0+1 and the first neighbours
-        float2 prev[4], cur[4];
-        unpack8x2(fzm ? ((const uint4 *)acx::local_partition_ptr(P.recv[4], pz_))[ly * LX + lx] : *(pc - sc), prev);
-        unpack8x2(*pc, cur);
-        uint4 vn = (TZ == 1 && fzp) ? ((const uint4 *)acx::local_partition_ptr(P.recv[5], pz_))[ly * LX + lx] : *(pc + sc);   // plane z0+1
-        uint4 vym = *pym, vyp = *pyp;
-        __nv_bfloat16 vxe = xedge ? *pxe : __float2bfloat16(0.f);
-        pc += 2 * sc; pym += sym; pyp += syp; pxe += sxe;
-#pragma unroll 2
-        for (int zl = 0; zl < TZ; zl++) {
-            // operands of THIS plane (loaded one iteration ago) ...
-            const uint4 un = vn, uym = vym, uyp = vyp;
-            const float edge = __bfloat162float(vxe);
-            // ... next plane's loads go out before the math
-            if (zl + 2 < TZ) vn = *pc;                                           // own row, plane z+2
-            else if (zl + 2 == TZ) vn = fzp ? ((const uint4 *)acx::local_partition_ptr(P.recv[5], pz_))[ly * LX + lx] : *pc;
-            if (zl + 1 < TZ) { vym = *pym; vyp = *pyp; if (xedge) vxe = *pxe; }
-            pc += sc; pym += sym; pyp += syp; pxe += sxe;
-            float2 ym[4], yp[4], nf[4], out[4];
-            unpack8x2(uym, ym); unpack8x2(uyp, yp); unpack8x2(un, nf);
-            float left = __shfl_up_sync(0xffffffffu, cur[3].y, 1), right = __shfl_down_sync(0xffffffffu, cur[0].x, 1);
-            if (lx == 0) left = edge;
-            if (lx == LX - 1) right = edge;
-            const float2 c0v = make_float2(P.c0, P.c0), c1v = make_float2(P.c1, P.c1);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                // x-neighbour sums stay scalar (they straddle register pairs); everything else is FADD2/FMUL2/FFMA2
-                const float xs0 = (j == 0 ? left : cur[j - 1].y) + cur[j].y;
-                const float xs1 = cur[j].x + (j == 3 ? right : cur[j + 1].x);
-                const float2 t = __fadd2_rn(__fadd2_rn(make_float2(xs0, xs1), __fadd2_rn(ym[j], yp[j])), __fadd2_rn(prev[j], nf[j]));
-                out[j] = __ffma2_rn(c0v, cur[j], __fmul2_rn(c1v, t));
-            }
-            const uint4 vo = pack8x2(out);
-            *po = vo; po += sc;
-            if (rym) { *rym = vo; rym += LX; }
-            if (ryp) { *ryp = vo; ryp += LX; }
-            if (zl == 0 && rzm) *rzm = vo;
-            if (zl == TZ - 1 && rzp) *rzp = vo;
-            if (sxm) { *sxm = reinterpret_cast<const __nv_bfloat16 *>(&vo)[0]; sxm += TY; }
-            if (sxp) { *sxp = reinterpret_cast<const __nv_bfloat16 *>(&vo)[7]; sxp += TY; }
-#pragma unroll
-            for (int j = 0; j < 4; j++) { prev[j] = cur[j]; cur[j] = nf[j]; }
-        }
-        __syncthreads();
-        if (fxm && tid < TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[0], px_))[tid] = ((const uint4 *)xface[0])[tid];
-        if (fxp && tid >= 64 && tid < 64 + TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[1], px_))[tid - 64] = ((const uint4 *)xface[1])[tid - 64];
-        if (fxm | fxp | fym | fyp | fzm | fzp) {
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence_system();
-                if (fxm) acx::pready_signal_epoch(px_, P.send[0], P.signal_val);
-                if (fxp) acx::pready_signal_epoch(px_, P.send[1], P.signal_val);
-                if (fym) acx::pready_signal_epoch(py_, P.send[2], P.signal_val);
-                if (fyp) acx::pready_signal_epoch(py_, P.send[3], P.signal_val);
-                if (fzm) acx::pready_signal_epoch(pz_, P.send[4], P.signal_val);
-                if (fzp) acx::pready_signal_epoch(pz_, P.send[5], P.signal_val);
-            }
-        }
-        __syncthreads();
     }
 }
 
-// Deeper-prefetch flavour of the direct kernel (ACX_HALO_VARIANT=7: PD=2, 8: PD=3; not the default — written after the
-// round's GPU budget was spent, to be measured next). ncu on the direct kernel shows ideal DRAM traffic but too few
-// DRAM-missing loads in flight per SM: only the own-row load of the next plane misses (the y+-1 rows and x edges hit in
-// L1/L2), one per thread. Here the own-row loads run PD planes ahead in a register ring (4 registers per stage), so
-// each SM keeps PD x 8 KiB of DRAM reads in flight instead of 8 KiB; everything else is the direct kernel unchanged.
-template <int PD>
-__global__ void __launch_bounds__(LX * TY, 1) halo_stencil_step_direct_pd(HaloDev P) {
-    static_assert(PD >= 2 && PD < TZ, "prefetch depth");
-    __shared__ __align__(16) __nv_bfloat16 xface[2][TZ * TY];
-    const int lx = threadIdx.x, ly = threadIdx.y, tid = ly * LX + lx;
-    const size_t plane = (size_t)P.nx * P.ny;
-    for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x) {
-        const int t = P.order[it];
-        const int tx = t % P.ntx, ty = (t / P.ntx) % P.nty, tz = t / (P.ntx * P.nty);
-        const bool fxm = tx == 0, fxp = tx == P.ntx - 1, fym = ty == 0, fyp = ty == P.nty - 1, fzm = tz == 0, fzp = tz == P.ntz - 1;
-        const int px_ = tz * P.nty + ty, py_ = tz * P.ntx + tx, pz_ = ty * P.ntx + tx;
-        if (tid == 0) {
-            if (fxm) acx::wait_arrived_epoch(P.recv[0], px_, P.wait_val);
-            if (fxp) acx::wait_arrived_epoch(P.recv[1], px_, P.wait_val);
-            if (fym) acx::wait_arrived_epoch(P.recv[2], py_, P.wait_val);
-            if (fyp) acx::wait_arrived_epoch(P.recv[3], py_, P.wait_val);
-            if (fzm) acx::wait_arrived_epoch(P.recv[4], pz_, P.wait_val);
-            if (fzp) acx::wait_arrived_epoch(P.recv[5], pz_, P.wait_val);
-        }
-        __syncthreads();
-        const int x0 = tx * TX + lx * 8, y = ty * TY + ly, z0 = tz * TZ;
-        const __nv_bfloat16 *c0p = P.u + (size_t)z0 * plane + (size_t)y * P.nx + x0;   // centre cell of plane z0
-        // --- operand sources, resolved once per tile: (pointer at plane z0, stride per plane in 16-B units or elements)
-        const uint4 *pc = reinterpret_cast<const uint4 *>(c0p);                 // own row
-        const size_t sc = plane / 8;
-        const uint4 *pym, *pyp; size_t sym, syp;                                // rows y-1 / y+1
-        if (ly == 0 && fym) { pym = (const uint4 *)acx::local_partition_ptr(P.recv[2], py_) + lx; sym = LX; }
-        else { pym = reinterpret_cast<const uint4 *>(c0p - P.nx); sym = sc; }
-        if (ly == TY - 1 && fyp) { pyp = (const uint4 *)acx::local_partition_ptr(P.recv[3], py_) + lx; syp = LX; }
-        else { pyp = reinterpret_cast<const uint4 *>(c0p + P.nx); syp = sc; }
-        const __nv_bfloat16 *pxe = c0p; size_t sxe = 0;                         // x-edge cell (lanes 0 and 31 only)
-        const bool xedge = lx == 0 || lx == LX - 1;
-        if (lx == 0) { if (fxm) { pxe = (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[0], px_) + ly; sxe = TY; } else { pxe = c0p - 1; sxe = plane; } }
-        if (lx == LX - 1) { if (fxp) { pxe = (const __nv_bfloat16 *)acx::local_partition_ptr(P.recv[1], px_) + ly; sxe = TY; } else { pxe = c0p + 8; sxe = plane; } }
-        uint4 *po = reinterpret_cast<uint4 *>(P.un + (size_t)z0 * plane + (size_t)y * P.nx + x0);
-        // remote landing buffers (packed): y faces advance one row of LX vectors per plane
-        uint4 *rym = (fym && ly == 0) ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[2], py_) + lx : nullptr;
-        uint4 *ryp = (fyp && ly == TY - 1) ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[3], py_) + lx : nullptr;
-        uint4 *rzm = fzm ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[4], pz_) + ly * LX + lx : nullptr;
-        uint4 *rzp = fzp ? (uint4 *)acx::remote_partition_ptr_nowait(P.send[5], pz_) + ly * LX + lx : nullptr;
-        __nv_bfloat16 *sxm = (fxm && lx == 0) ? &xface[0][ly] : nullptr, *sxp = (fxp && lx == LX - 1) ? &xface[1][ly] : nullptr;
-        // --- prologue: planes z0-1, z0, z0+1 and the first neighbours
-        float2 prev[4], cur[4];
-        unpack8x2(fzm ? ((const uint4 *)acx::local_partition_ptr(P.recv[4], pz_))[ly * LX + lx] : *(pc - sc), prev);
-        unpack8x2(*pc, cur);
-        // own-row ring: vq[i] holds plane z0 + 1 + i; plane z0 + TZ comes from the z+ landing buffer on a face tile
-        const uint4 *zp_land = fzp ? (const uint4 *)acx::local_partition_ptr(P.recv[5], pz_) + ly * LX + lx : nullptr;
-        uint4 vq[PD];
-#pragma unroll
-        for (int i = 0; i < PD; i++) vq[i] = *(pc + (size_t)(1 + i) * sc);       // PD < TZ: all inside the tile
-        uint4 vym = *pym, vyp = *pyp;
-        __nv_bfloat16 vxe = xedge ? *pxe : __float2bfloat16(0.f);
-        pym += sym; pyp += syp; pxe += sxe;
-#pragma unroll 2
-        for (int zl = 0; zl < TZ; zl++) {
-            // operands of THIS plane (own row loaded PD iterations ago, neighbours one iteration ago) ...
-            const uint4 un = vq[0], uym = vym, uyp = vyp;
-            const float edge = __bfloat162float(vxe);
-#pragma unroll
-            for (int i = 0; i + 1 < PD; i++) vq[i] = vq[i + 1];
-            // ... the loads of later planes go out before the math
-            const int q = zl + 1 + PD;                                           // own row, plane z0 + q
-            if (q < TZ) vq[PD - 1] = *(pc + (size_t)q * sc);
-            else if (q == TZ) vq[PD - 1] = zp_land ? *zp_land : *(pc + (size_t)q * sc);
-            if (zl + 1 < TZ) { vym = *pym; vyp = *pyp; if (xedge) vxe = *pxe; }
-            pym += sym; pyp += syp; pxe += sxe;
-            float2 ym[4], yp[4], nf[4], out[4];
-            unpack8x2(uym, ym); unpack8x2(uyp, yp); unpack8x2(un, nf);
-            float left = __shfl_up_sync(0xffffffffu, cur[3].y, 1), right = __shfl_down_sync(0xffffffffu, cur[0].x, 1);
-            if (lx == 0) left = edge;
-            if (lx == LX - 1) right = edge;
-            const float2 c0v = make_float2(P.c0, P.c0), c1v = make_float2(P.c1, P.c1);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                // x-neighbour sums stay scalar (they straddle register pairs); everything else is FADD2/FMUL2/FFMA2
-                const float xs0 = (j == 0 ? left : cur[j - 1].y) + cur[j].y;
-                const float xs1 = cur[j].x + (j == 3 ? right : cur[j + 1].x);
-                const float2 t = __fadd2_rn(__fadd2_rn(make_float2(xs0, xs1), __fadd2_rn(ym[j], yp[j])), __fadd2_rn(prev[j], nf[j]));
-                out[j] = __ffma2_rn(c0v, cur[j], __fmul2_rn(c1v, t));
-            }
-            const uint4 vo = pack8x2(out);
-            *po = vo; po += sc;
-            if (rym) { *rym = vo; rym += LX; }
-            if (ryp) { *ryp = vo; ryp += LX; }
-            if (zl == 0 && rzm) *rzm = vo;
-            if (zl == TZ - 1 && rzp) *rzp = vo;
-            if (sxm) { *sxm = reinterpret_cast<const __nv_bfloat16 *>(&vo)[0]; sxm += TY; }
-            if (sxp) { *sxp = reinterpret_cast<const __nv_bfloat16 *>(&vo)[7]; sxp += TY; }
-#pragma unroll
-            for (int j = 0; j < 4; j++) { prev[j] = cur[j]; cur[j] = nf[j]; }
-        }
-        __syncthreads();
-        if (fxm && tid < TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[0], px_))[tid] = ((const uint4 *)xface[0])[tid];
-        if (fxp && tid >= 64 && tid < 64 + TZ * TY / 8) ((uint4 *)acx::remote_partition_ptr_nowait(P.send[1], px_))[tid - 64] = ((const uint4 *)xface[1])[tid - 64];
-        if (fxm | fxp | fym | fyp | fzm | fzp) {
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence_system();
-                if (fxm) acx::pready_signal_epoch(px_, P.send[0], P.signal_val);
-                if (fxp) acx::pready_signal_epoch(px_, P.send[1], P.signal_val);
-                if (fym) acx::pready_signal_epoch(py_, P.send[2], P.signal_val);
-                if (fyp) acx::pready_signal_epoch(py_, P.send[3], P.signal_val);
-                if (fzm) acx::pready_signal_epoch(pz_, P.send[4], P.signal_val);
-                if (fzp) acx::pready_signal_epoch(pz_, P.send[5], P.signal_val);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-
-// Initial exchange: faces of u^0 -> neighbours' parity-0 landing buffers, flag value 1.
+// Initial exchange: faces of u^0 -> the neighbours' ghost cells of the SAME field, flag value 1 on the parity-0 channels.
 // One CTA per (face, partition).
 struct PackDev {
-    const __nv_bfloat16 *u;
-    int nx, ny, nz, ntx, nty, ntz;
+    const __nv_bfloat16 *u;         // interior origin of the local current field
+    __nv_bfloat16 *nb[6];           // neighbours' interior origins of THEIR current field
+    int nx, ny, nz, nty, ntz;
+    long long rp, pp;
     const acx_pchan *send[6];
     unsigned long long signal_val;
 };
 __global__ void halo_pack_faces(PackDev P) {
     const int f = blockIdx.y, p = blockIdx.x;
-    const int nparts = f < 2 ? P.nty * P.ntz : f < 4 ? P.ntx * P.ntz : P.ntx * P.nty;
+    const int nparts = f < 2 ? P.nty * P.ntz : f < 4 ? P.ntz : P.nty;
     if (p >= nparts) return;
-    __nv_bfloat16 *dst = (__nv_bfloat16 *)acx::remote_partition_ptr_nowait(P.send[f], p);
-    const size_t plane = (size_t)P.nx * P.ny;
-    if (f < 2) {
-        const int tz = p / P.nty, ty = p % P.nty, x = f == 0 ? 0 : P.nx - 1;
-        for (int i = threadIdx.x; i < TZ * TY; i += blockDim.x) {
-            const int zl = i / TY, yl = i % TY;
-            dst[i] = P.u[(size_t)(tz * TZ + zl) * plane + (size_t)(ty * TY + yl) * P.nx + x];
+    const int vpr = P.nx / 8;
+    if (f < 2) {            // x faces: partition = tile (ty, tc); one 16-B vector per (row, plane)
+        const int ty = p % P.nty, tc = p / P.nty;
+        for (int i = threadIdx.x; i < TY * TZ; i += blockDim.x) {
+            const int yl = i % TY, zl = i / TY;
+            const long long off = (long long)(tc * TZ + zl) * P.pp + (long long)(ty * TY + yl) * P.rp;
+            if (f == 0) *reinterpret_cast<uint4 *>(P.nb[0] + off + P.nx) = *reinterpret_cast<const uint4 *>(P.u + off);
+            else *reinterpret_cast<uint4 *>(P.nb[1] + off - 8) = *reinterpret_cast<const uint4 *>(P.u + off + P.nx - 8);
         }
-    } else if (f < 4) {
-        const int tz = p / P.ntx, tx = p % P.ntx, y = f == 2 ? 0 : P.ny - 1;
-        for (int i = threadIdx.x; i < TZ * TX; i += blockDim.x) {
-            const int zl = i / TX, xl = i % TX;
-            dst[i] = P.u[(size_t)(tz * TZ + zl) * plane + (size_t)y * P.nx + tx * TX + xl];
+    } else if (f < 4) {     // y faces: partition = z-chunk tc; row y = 0 (f == 2) or ny-1 of TZ planes
+        const int tc = p, y = f == 2 ? 0 : P.ny - 1;
+        for (int i = threadIdx.x; i < TZ * vpr; i += blockDim.x) {
+            const int zl = i / vpr, v = i % vpr;
+            const long long off = (long long)(tc * TZ + zl) * P.pp + (long long)y * P.rp + v * 8;
+            const long long shift = f == 2 ? (long long)P.ny * P.rp : -(long long)P.ny * P.rp;
+            *reinterpret_cast<uint4 *>(P.nb[f] + off + shift) = *reinterpret_cast<const uint4 *>(P.u + off);
         }
-    } else {
-        const int ty = p / P.ntx, tx = p % P.ntx, z = f == 4 ? 0 : P.nz - 1;
-        for (int i = threadIdx.x; i < TY * TX; i += blockDim.x) {
-            const int yl = i / TX, xl = i % TX;
-            dst[i] = P.u[(size_t)z * plane + (size_t)(ty * TY + yl) * P.nx + tx * TX + xl];
+    } else {                // z faces: partition = strip ty; plane z = 0 (f == 4) or nz-1, TY rows
+        const int ty = p, z = f == 4 ? 0 : P.nz - 1;
+        for (int i = threadIdx.x; i < TY * vpr; i += blockDim.x) {
+            const int yl = i / vpr, v = i % vpr;
+            const long long off = (long long)z * P.pp + (long long)(ty * TY + yl) * P.rp + v * 8;
+            const long long shift = f == 4 ? (long long)P.nz * P.pp : -(long long)P.nz * P.pp;
+            *reinterpret_cast<uint4 *>(P.nb[f] + off + shift) = *reinterpret_cast<const uint4 *>(P.u + off);
         }
     }
     __threadfence_system();
@@ -601,21 +249,52 @@ __global__ void halo_pack_faces(PackDev P) {
     if (threadIdx.x == 0) acx::pready_signal_epoch(p, P.send[f], P.signal_val);
 }
 
+// dense [nz][ny][nx] <-> the padded field (import / export for callers that keep a plain array)
+__global__ void halo_copy_dense(__nv_bfloat16 *padded, __nv_bfloat16 *dense, int nx, int ny, int nz, long long rp, long long pp, int to_padded) {
+    const long long nvec = (long long)nx / 8 * ny * nz;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % (nx / 8));
+        const long long r = i / (nx / 8);
+        const int y = (int)(r % ny), z = (int)(r / ny);
+        uint4 *a = reinterpret_cast<uint4 *>(padded + (long long)z * pp + (long long)y * rp + v * 8);
+        uint4 *b = reinterpret_cast<uint4 *>(dense + ((long long)z * ny + y) * nx + v * 8);
+        if (to_padded) *a = *b; else *b = *a;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
 }  // namespace
 
 struct acx_halo {
     int nx, ny, nz, px, py, pz, rank, size;
-    int ntx, nty, ntz, ntiles;
+    int nty, ntz, ntiles;
+    long long rp, pp;              // pitches in cells
+    size_t field_bytes;
     float c0, c1;
-    __nv_bfloat16 *u[2];
+    char *alloc[2];                // symmetric-heap allocations
+    __nv_bfloat16 *u[2];           // interior origins
+    __nv_bfloat16 *nbu[2][6];      // neighbours' interior origins (peer-mapped), per field and face
+    CUtensorMap tm[2];
     int cur;                       // u[cur] holds u^step
     unsigned long long step;       // number of completed steps
     bool exchanged;
-    void *land[2][6];              // recv landing buffers per parity/face (symmetric heap)
+    void *land[2][6];              // flag-only channels: tiny receive buffers the partitioned API wants (symmetric heap)
     MPIX_Request sreq[2][6], rreq[2][6];
     MPIX_Prequest spre[2][6], rpre[2][6];
     int *order_d;
-    int grid, variant;
+    int grid, threads;
+    size_t smem;
 };
 
 #define HCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "[acx halo] %s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return 1; } } while (0)
@@ -626,58 +305,79 @@ extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, f
     MPI_Comm_rank(MPI_COMM_WORLD, &rank);
     MPI_Comm_size(MPI_COMM_WORLD, &size);
     if (px * py * pz != size) { fprintf(stderr, "[acx halo] decomposition %dx%dx%d != %d ranks\n", px, py, pz, size); return 1; }
-    if (nx % TX || ny % TY || nz % TZ) { fprintf(stderr, "[acx halo] block %dx%dx%d must be a multiple of the %dx%dx%d tile\n", nx, ny, nz, TX, TY, TZ); return 1; }
+    if ((nx != 256 && nx != 512) || ny % TY || nz % TZ) { fprintf(stderr, "[acx halo] block %dx%dx%d: nx must be 256 or 512 (one thread per 8 cells, %d rows per CTA), ny a multiple of %d, nz of %d\n", nx, ny, nz, TY, TY, TZ); return 1; }
     acx_halo *h = new acx_halo();
     h->nx = nx; h->ny = ny; h->nz = nz; h->px = px; h->py = py; h->pz = pz; h->rank = rank; h->size = size; h->c0 = c0; h->c1 = c1;
-    h->ntx = nx / TX; h->nty = ny / TY; h->ntz = nz / TZ; h->ntiles = h->ntx * h->nty * h->ntz;
+    h->nty = ny / TY; h->ntz = nz / TZ; h->ntiles = h->nty * h->ntz;
+    h->rp = nx + XPAD; h->pp = h->rp * (ny + 2);
     h->cur = 0; h->step = 0; h->exchanged = false;
-    const size_t cells = (size_t)nx * ny * nz;
-    HCK(cudaMalloc((void **)&h->u[0], cells * 2));
-    HCK(cudaMalloc((void **)&h->u[1], cells * 2));
+    // padded field = (nz+2) planes of (ny+2) rows, plus one lead-in and one tail row (the tensor map starts 16 B early)
+    h->field_bytes = ((size_t)h->pp * (nz + 2) + 2 * (size_t)h->rp) * 2;
     const int cx = rank % px, cy = (rank / px) % py, cz = rank / (px * py);
     auto rk = [&](int x, int y, int z) { return (((z + pz) % pz) * py + ((y + py) % py)) * px + ((x + px) % px); };
     const int nbr[6] = {rk(cx - 1, cy, cz), rk(cx + 1, cy, cz), rk(cx, cy - 1, cz), rk(cx, cy + 1, cz), rk(cx, cy, cz - 1), rk(cx, cy, cz + 1)};
-    const int nparts[6] = {h->nty * h->ntz, h->nty * h->ntz, h->ntx * h->ntz, h->ntx * h->ntz, h->ntx * h->nty, h->ntx * h->nty};
-    const size_t pbytes[6] = {(size_t)TY * TZ * 2, (size_t)TY * TZ * 2, (size_t)TX * TZ * 2, (size_t)TX * TZ * 2, (size_t)TX * TY * 2, (size_t)TX * TY * 2};
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { fprintf(stderr, "[acx halo] cuTensorMapEncodeTiled is unavailable\n"); return 1; }
+    for (int b = 0; b < 2; b++) {
+        void *p = nullptr;
+        if (MPIX_Alloc_mem(h->field_bytes, MPI_INFO_NULL, &p)) {
+            fprintf(stderr, "[acx halo] the two padded fields need 2 x %.0f MiB of the symmetric heap (neighbours write ghost cells in place): raise ACX_HEAP_BYTES\n", h->field_bytes / 1048576.0);
+            return 1;
+        }
+        h->alloc[b] = (char *)p;
+        HCK(cudaMemset(p, 0, h->field_bytes));
+        // interior origin: skip the lead-in row, the z = -1 plane and the y = -1 row
+        h->u[b] = (__nv_bfloat16 *)(h->alloc[b]) + h->rp + h->pp + h->rp;
+        for (int f = 0; f < 6; f++) {
+            void *q = nullptr;
+            HOK(MPIX_Peer_ptr(h->u[b], nbr[f], &q));
+            h->nbu[b][f] = (__nv_bfloat16 *)q;
+        }
+        // 3-D tensor map over 8-byte elements (4 cells): {row, rows of a plane, planes}. Its origin sits 16 B before padded
+        // row 0 of padded plane 0, so a box that starts at column 0 begins with the row's left ghost vector.
+        char *base = h->alloc[b] + (size_t)h->rp * 2 - 16;
+        cuuint64_t dims[3] = {(cuuint64_t)(h->rp / 4), (cuuint64_t)(ny + 2), (cuuint64_t)(nz + 2)};
+        cuuint64_t strides[2] = {(cuuint64_t)h->rp * 2, (cuuint64_t)h->pp * 2};
+        cuuint32_t box[3] = {(cuuint32_t)(h->rp / 4), (cuuint32_t)(TY + 2), 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&h->tm[b], CU_TENSOR_MAP_DATA_TYPE_INT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { fprintf(stderr, "[acx halo] cuTensorMapEncodeTiled failed (%d)\n", (int)r); return 1; }
+    }
+    const int nparts[6] = {h->ntiles, h->ntiles, h->ntz, h->ntz, h->nty, h->nty};
     for (int par = 0; par < 2; par++)
         for (int f = 0; f < 6; f++) {
-            HOK(MPIX_Alloc_mem(nparts[f] * pbytes[f], MPI_INFO_NULL, &h->land[par][f]));
-            HCK(cudaMemset(h->land[par][f], 0, nparts[f] * pbytes[f]));
-            // My face f travels to nbr[f] and lands in ITS "halo from direction f^1" buffer: tag by the sender's face id.
+            // flag-only channels: the payload is stored in place by the producer (zero-copy form of the device API), the
+            // partitioned request carries the per-partition arrival flags; 16 bytes per partition keep the API honest
+            HOK(MPIX_Alloc_mem((size_t)nparts[f] * 16, MPI_INFO_NULL, &h->land[par][f]));
+            HCK(cudaMemset(h->land[par][f], 0, (size_t)nparts[f] * 16));
+            // My face f travels to nbr[f] and lands behind ITS face f^1: tag by the sender's face id.
             const int tag_send = 100 + par * 8 + f, tag_recv = 100 + par * 8 + (f ^ 1);
-            HOK(MPIX_Psend_init(nullptr, nparts[f], (MPI_Count)pbytes[f], MPI_BYTE, nbr[f], tag_send, MPI_COMM_WORLD, MPI_INFO_NULL, &h->sreq[par][f]));
-            HOK(MPIX_Precv_init(h->land[par][f], nparts[f], (MPI_Count)pbytes[f], MPI_BYTE, nbr[f], tag_recv, MPI_COMM_WORLD, MPI_INFO_NULL, &h->rreq[par][f]));
+            HOK(MPIX_Psend_init(nullptr, nparts[f], (MPI_Count)16, MPI_BYTE, nbr[f], tag_send, MPI_COMM_WORLD, MPI_INFO_NULL, &h->sreq[par][f]));
+            HOK(MPIX_Precv_init(h->land[par][f], nparts[f], (MPI_Count)16, MPI_BYTE, nbr[f], tag_recv, MPI_COMM_WORLD, MPI_INFO_NULL, &h->rreq[par][f]));
         }
     for (int par = 0; par < 2; par++)
         for (int f = 0; f < 6; f++) {
             HOK(MPIX_Prequest_create(h->sreq[par][f], &h->spre[par][f]));
             HOK(MPIX_Prequest_create(h->rreq[par][f], &h->rpre[par][f]));
         }
-    // boundary tiles first: their NVLink stores overlap the interior sweep
+    // tiles on a y / z face first: their NVLink stores overlap the interior sweep
     std::vector<int> order(h->ntiles);
     for (int i = 0; i < h->ntiles; i++) order[i] = i;
-    auto nfaces = [&](int t) {
-        int tx = t % h->ntx, ty = (t / h->ntx) % h->nty, tz = t / (h->ntx * h->nty);
-        return (tx == 0) + (tx == h->ntx - 1) + (ty == 0) + (ty == h->nty - 1) + (tz == 0) + (tz == h->ntz - 1);
-    };
+    auto nfaces = [&](int t) { int ty = t % h->nty, tc = t / h->nty; return (ty == 0) + (ty == h->nty - 1) + (tc == 0) + (tc == h->ntz - 1); };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nfaces(a) > nfaces(b); });
     HCK(cudaMalloc((void **)&h->order_d, sizeof(int) * h->ntiles));
     HCK(cudaMemcpy(h->order_d, order.data(), sizeof(int) * h->ntiles, cudaMemcpyHostToDevice));
+    h->threads = nx / 8 * TY;
+    h->smem = (size_t)STAGES * ((((size_t)(TY + 2) * (size_t)h->rp * 2) + 127) & ~(size_t)127) + (2 * STAGES + 2) * 8 + 16;
+    HCK(cudaFuncSetAttribute(halo_stencil_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const char *var = getenv("ACX_HALO_VARIANT");
-    h->variant = var ? atoi(var) : 5;
-    if (h->variant == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step<1, 2>, LX * TY, 0);
-    else if (h->variant == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step<2, 1>, LX * TY, 0);
-    else if (h->variant == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step<4, 1>, LX * TY, 0);
-    else if (h->variant == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_rows<3>, NW * 32, 0);
-    else if (h->variant == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_rows<2>, NW * 32, 0);
-    else if (h->variant == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_direct<1>, LX * TY, 0);
-    else if (h->variant == 7) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_direct_pd<2>, LX * TY, 0);
-    else if (h->variant == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_direct_pd<3>, LX * TY, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_step_direct<2>, LX * TY, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_tma, h->threads, h->smem);
     if (occ < 1) occ = 1;
+    const char *g = getenv("ACX_HALO_CTAS_PER_SM");
+    if (g && atoi(g) > 0) occ = std::min(occ, atoi(g));
     h->grid = std::min(h->ntiles, sms * occ);
     MPI_Barrier(MPI_COMM_WORLD);
     *out = h;
@@ -685,40 +385,48 @@ extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, f
 }
 
 extern "C" void *acx_halo_field(acx_halo *h) { return h->u[h->cur]; }
+extern "C" void acx_halo_field_pitch(acx_halo *h, long long *row_pitch_cells, long long *plane_pitch_cells) { *row_pitch_cells = h->rp; *plane_pitch_cells = h->pp; }
 extern "C" unsigned long long acx_halo_steps_done(acx_halo *h) { return h->step; }
+extern "C" int acx_halo_import_dense(acx_halo *h, const void *dense, cudaStream_t stream) {
+    halo_copy_dense<<<1184, 256, 0, stream>>>(h->u[h->cur], (__nv_bfloat16 *)dense, h->nx, h->ny, h->nz, h->rp, h->pp, 1);
+    HCK(cudaGetLastError());
+    return 0;
+}
+extern "C" int acx_halo_export_dense(acx_halo *h, void *dense, cudaStream_t stream) {
+    halo_copy_dense<<<1184, 256, 0, stream>>>(h->u[h->cur], (__nv_bfloat16 *)dense, h->nx, h->ny, h->nz, h->rp, h->pp, 0);
+    HCK(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int acx_halo_exchange_initial(acx_halo *h, cudaStream_t stream) {
     PackDev P;
-    P.u = h->u[h->cur]; P.nx = h->nx; P.ny = h->ny; P.nz = h->nz; P.ntx = h->ntx; P.nty = h->nty; P.ntz = h->ntz;
+    P.u = h->u[h->cur]; P.nx = h->nx; P.ny = h->ny; P.nz = h->nz; P.nty = h->nty; P.ntz = h->ntz; P.rp = h->rp; P.pp = h->pp;
     const int par = (int)(h->step & 1);
-    for (int f = 0; f < 6; f++) P.send[f] = (const acx_pchan *)h->spre[par][f];
+    for (int f = 0; f < 6; f++) { P.send[f] = (const acx_pchan *)h->spre[par][f]; P.nb[f] = h->nbu[h->cur][f]; }
     P.signal_val = h->step + 1;
-    int maxp = std::max(h->nty * h->ntz, std::max(h->ntx * h->ntz, h->ntx * h->nty));
-    halo_pack_faces<<<dim3(maxp, 6), 256, 0, stream>>>(P);
+    halo_pack_faces<<<dim3(h->ntiles, 6), 256, 0, stream>>>(P);
     HCK(cudaGetLastError());
     h->exchanged = true;
     return 0;
 }
 
+// Flow control without credits: step s reads U[s&1] (ghosts included) and writes U[(s+1)&1], mine and — for face cells —
+// the neighbours'. A neighbour's ghost cells of U[(s+1)&1] were last read by its step s-1, by exactly the tile whose
+// face flag (epoch s+1, parity s&1) this rank's mirror tile acquires before it computes anything in step s: when the
+// flag is visible that tile has finished, loads included. So nothing is overwritten while still being read.
 extern "C" int acx_halo_step(acx_halo *h, int nsteps, cudaStream_t stream) {
     if (!h->exchanged) HOK(acx_halo_exchange_initial(h, stream));
     for (int s = 0; s < nsteps; s++) {
         HaloDev P;
-        P.u = h->u[h->cur]; P.un = h->u[h->cur ^ 1];
-        P.nx = h->nx; P.ny = h->ny; P.nz = h->nz; P.ntx = h->ntx; P.nty = h->nty; P.ntz = h->ntz;
+        const int cur = h->cur, nxt = cur ^ 1;
+        P.un = h->u[nxt];
+        for (int f = 0; f < 6; f++) P.nb[f] = h->nbu[nxt][f];
+        P.nx = h->nx; P.ny = h->ny; P.nz = h->nz; P.nty = h->nty; P.ntz = h->ntz; P.ntiles = h->ntiles; P.rp = h->rp; P.pp = h->pp;
         const int rp = (int)(h->step & 1), sp = rp ^ 1;
         for (int f = 0; f < 6; f++) { P.recv[f] = (const acx_pchan *)h->rpre[rp][f]; P.send[f] = (const acx_pchan *)h->spre[sp][f]; }
         P.wait_val = h->step + 1; P.signal_val = h->step + 2;
-        P.c0 = h->c0; P.c1 = h->c1; P.order = h->order_d; P.ntiles = h->ntiles;
-        if (h->variant == 0) halo_stencil_step<1, 2><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
-        else if (h->variant == 1) halo_stencil_step<2, 1><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
-        else if (h->variant == 2) halo_stencil_step<4, 1><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
-        else if (h->variant == 3) halo_stencil_step_rows<3><<<h->grid, NW * 32, 0, stream>>>(P);
-        else if (h->variant == 4) halo_stencil_step_rows<2><<<h->grid, NW * 32, 0, stream>>>(P);
-        else if (h->variant == 5) halo_stencil_step_direct<1><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
-        else if (h->variant == 7) halo_stencil_step_direct_pd<2><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
-        else if (h->variant == 8) halo_stencil_step_direct_pd<3><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
-        else halo_stencil_step_direct<2><<<h->grid, dim3(LX, TY), 0, stream>>>(P);
+        P.c0 = h->c0; P.c1 = h->c1; P.order = h->order_d;
+        halo_stencil_tma<<<h->grid, h->threads, h->smem, stream>>>(h->tm[cur], P);
         HCK(cudaGetLastError());
         h->cur ^= 1;
         h->step++;
@@ -735,7 +443,8 @@ extern "C" int acx_halo_destroy(acx_halo *h) {
             MPIX_Request_free(&h->sreq[par][f]); MPIX_Request_free(&h->rreq[par][f]);
             MPIX_Free_mem(h->land[par][f]);
         }
-    cudaFree(h->u[0]); cudaFree(h->u[1]); cudaFree(h->order_d);
+    MPIX_Free_mem(h->alloc[0]); MPIX_Free_mem(h->alloc[1]);
+    cudaFree(h->order_d);
     delete h;
     return 0;
 }

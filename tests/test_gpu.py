@@ -154,6 +154,33 @@ op.close(); acx.finalize(); print("HALO OK")
     assert r.returncode == 0 and "HALO OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 
+def test_halo_stencil_many_tiles_per_cta_matches_torch_reference():
+    """512 x 384 x 256 block: 384 tiles over 296 resident CTAs, so CTAs run the TMA plane stream straight through tile
+    boundaries (the producer prefetches the next tile's planes while the current one is still being computed), every
+    face is 48 / 8 partitions wide, and 3 steps exercise both field parities — against the PyTorch fp32 reference."""
+    script = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import mpi_acx_b200 as acx
+from mpi_acx_b200.ops import HaloStencil, stencil_reference
+acx.init(0)
+op = HaloStencil(512, 384, 256, (1, 1, 1))
+torch.manual_seed(5)
+u0 = torch.randn(256, 384, 512, device="cuda").to(torch.bfloat16)
+op.field().copy_(u0)
+op.step(3)
+torch.cuda.synchronize()
+got = op.field().float()
+ref = stencil_reference(u0, steps=3).float()
+err = (got - ref).abs().max().item()
+print("max abs err", err)
+assert err <= 0.02, err
+op.close(); acx.finalize(); print("HALO OK")
+""" % str(REPO)
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300, env=dict(os.environ, ACX_WATCHDOG_MS="30000", ACX_HEAP_BYTES=str(1 << 30)))
+    assert r.returncode == 0 and "HALO OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
 def test_gemm_fp8_matches_torch_reference():
     """tcgen05 fp8 GEMM vs a plain PyTorch fp32 matmul of the dequantized operands."""
     script = r"""

@@ -346,3 +346,20 @@ def test_hot_kernels_keep_their_register_budget(built):
     assert find("gemm_fp8_kernel")[1] == 0
     regs, stack = find("11wait_kernelE")
     assert regs <= 64 and stack == 0, (regs, stack)
+    regs, stack = find("halo_stencil_tma")   # two 512-thread CTAs per SM: the TMA ring, not registers, holds the data in flight
+    assert regs <= 64 and stack == 0, (regs, stack)
+
+
+def test_halo_kernel_is_tma_fed(built):
+    """Static SASS evidence (no GPU): the fused halo/stencil kernel loads the field with TMA tensor boxes (UTMALDG.3D) and
+    synchronises on mbarriers (SYNCS), and contains no plain global loads of field data in its main loop."""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not installed")
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", "halo_stencil_tma", str(built / "lib/libacx.so")], capture_output=True, text=True, timeout=120).stdout
+    if "UTMALDG" not in out:   # older cuobjdump: -fun wants the mangled name; fall back to the whole listing
+        out = subprocess.run(["cuobjdump", "-sass", str(built / "lib/libacx.so")], capture_output=True, text=True, timeout=300).stdout
+        i = out.find("halo_stencil_tma")
+        j = out.find("Function :", i + 1)
+        out = out[i:j if j > 0 else None]
+    assert "UTMALDG.3D" in out and "SYNCS" in out
