@@ -85,6 +85,8 @@ static AnyTable *g_any_tbl_d = nullptr;   // device copy of the peer window base
 static acx_anyres *g_anyres_d = nullptr;  // one resolution record per request slot
 static int g_coop = 0;                    // ACX_COOP: cooperative moving with chunk stealing (both ends of a large rendezvous message copy it); must be set on every rank
 static long g_coop_min = 4 << 20;          // ACX_COOP_MIN_BYTES
+static long g_late_min = 4 << 20;          // ACX_LATE_PUSH_MIN: messages from this size up use the sender-moves protocol (RNDV_LATE); 0 = off
+static long g_late_fallback_us = 50;       // ACX_LATE_FALLBACK_US: grace period before a receive's wait pulls an unclaimed RNDV_LATE message itself
 static int g_pbatch = 0;                  // ACX_PBATCH: one kernel launch per MPIX_Startall / MPIX_Waitall group of partitioned requests instead of one per request
 static int g_branch = 0;                  // ACX_PEER_BRANCH: run EVERY operation with a peer on that peer's side stream (fork at enqueue, join at the wait)
 static int g_fuse_rndv = 1, g_fuse_min_ctas = 8, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
@@ -146,6 +148,7 @@ static void report_watchdog() {
             case 0x5e0a: what = "sender-push gate: the matching receive was never posted"; break;
             case 0x5e0b: what = "wildcard receive: no matching send arrived"; break;
             case 0x5e0c: what = "cooperative-move gate: the peer never arrived"; break;
+            case 0x5e0e: what = "wait kernel helper: the request's waiter CTA never decided (a = ticket, b = state word)"; break;
         }
         ACX_ERR("WATCHDOG (code 0x%llx, a=0x%llx b=0x%llx): %s", (unsigned long long)g_diag[0], (unsigned long long)g_diag[1],
                 (unsigned long long)g_diag[2], what);
@@ -373,7 +376,11 @@ int acx_device_alias(const void *p, size_t bytes, char **out) {
         e = cudaHostRegister((void *)cur, end - cur, cudaHostRegisterMapped | cudaHostRegisterPortable);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            if (g_acx->pageable_access) { *out = (char *)p; return 0; }  // HMM/ATS: the GPU can touch it as is
+            if (g_acx->pageable_access) {   // HMM/ATS: the GPU may be able to touch it as is
+                static bool warned = false;
+                if (!warned) { warned = true; ACX_LOG(0, "cudaHostRegister(%p, +%zu) failed (%s): relying on pageable-memory access for this buffer", (void *)cur, (size_t)(end - cur), cudaGetErrorString(e)); }
+                *out = (char *)p; return 0;
+            }
             ACX_ERR("cannot make host buffer %p (+%zu) device-accessible: %s", p, bytes, cudaGetErrorString(e));
             return MPI_ERR_BUFFER;
         }
@@ -723,6 +730,8 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_WILDCARDS", nullptr, 0, &v); g_wild = v != 0;   // experimental device-side wildcard matching (see recv_any_kernel)
     acx_env_int("ACX_COOP", nullptr, 0, &v); g_coop = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_COOP_MIN_BYTES", nullptr, 4 << 20, &v); g_coop_min = std::max(65536L, v);
+    acx_env_int("ACX_LATE_PUSH_MIN", nullptr, 4 << 20, &v); g_late_min = std::max(0L, v);   // must be the same on every rank (like every protocol knob)
+    acx_env_int("ACX_LATE_FALLBACK_US", nullptr, 50, &v); g_late_fallback_us = std::max(0L, v);
     acx_env_int("ACX_PBATCH", nullptr, 0, &v); g_pbatch = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_MEMOPS", nullptr, 0, &v); g_memops = v != 0 && !getenv("MPIACX_DISABLE_MEMOPS");   // partitioned Start / Wait as stream memOps (opt-in until measured)
     acx_env_int("ACX_PEER_BRANCH", nullptr, 0, &v); g_branch = v != 0;   // opt-in until measured on hardware
@@ -1570,6 +1579,12 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         // Cooperative moving is a property of the MESSAGE, chosen here from its size and announced in the header
         r->coop = g_coop && !eager && !fused && !apush && !g_mover_tma && (long)bytes >= g_coop_min;
         sp.coop = r->coop ? 1 : 0;   // travels in the message header: the receiver follows the sender's choice
+        // Large messages: the sender moves them — the mover behind this trigger if the receive is posted by then, the helper
+        // CTAs of this request's wait kernel otherwise. The receiver never pulls (except as a late fallback), so every GPU
+        // copies exactly its own sends whatever order ranks arrive in (a ring step stays one NVLink push per GPU).
+        r->late = g_late_min > 0 && !eager && !fused && !apush && !r->coop && (long)bytes >= g_late_min;
+        sp.late = r->late ? 1 : 0;
+        r->src_local = (char *)src_local;
         if (!dropped && fused) { if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail; }
         else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
         if (!eager) {
@@ -1746,11 +1761,20 @@ static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_w
     w->depth = G.depth; w->eager_max = G.eager_max;
     w->serial = host_wait ? r->serial : 0;
     w->retire = retire ? 1 : 0;
+    w->late_tag = (uint32_t)r->serial;
     w->src = r->comm_peer; w->tag = r->tag; w->ctx = (uint32_t)r->comm_ctx;   // status reports the peer in the caller's communicator
     w->off_source = w->off_tag = w->off_error = w->off_bytes = 0xffff;
     if (r->kind == ACX_REQ_SEND) {
         w->is_recv = 0;
         w->sack = acx_sacks_of(g_acx->ctrl) + acx_entry_index(G, r->peer, r->chan, 0);
+        if (r->late) {   // may have to push from the wait: see late_helper
+            w->late = 1;
+            w->ring = acx_entries_of(g_acx->peer_ctrl[r->peer]) + acx_entry_index(G, g_acx->rank, r->chan, 0);   // the slot at the receiver (claim, done)
+            w->late_local = r->src_local;
+            w->peer_heap = g_acx->peer_heap[r->peer];
+            w->xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)r->peer * G.maxreg;
+            w->late_bytes = r->bytes;
+        }
     } else {
         w->is_recv = 1;
         if (r->wild) {
@@ -1766,6 +1790,12 @@ static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_w
         w->coop = g_coop ? 1 : 0;   // the receiver's wait kernel owns the slot's chunk cursor reset
         if (r->typed) { w->dst = w->bounce; w->bounce = nullptr; }   // eager payloads are copied into the staging buffer too; unpack_kernel does the rest
         w->cap = r->bytes;
+        if (g_late_min > 0 && !r->wild && (long)r->bytes >= g_late_min) {   // may receive an RNDV_LATE message: fallback pull from the wait
+            w->late = 1;
+            w->late_local = r->bounce_off >= 0 ? g_acx->heap + r->bounce_off : r->dev_buf;
+            w->peer_heap = g_acx->peer_heap[r->peer];
+            w->xlat = (const uint64_t *)(g_acx->ctrl + G.off_xlat) + (uint64_t)r->peer * G.maxreg;
+        }
         if (status != MPI_STATUS_IGNORE && !host_wait) {
             char *ds = nullptr;
             int rc = acx_device_alias(status, sizeof(MPI_Status), &ds);
@@ -1796,6 +1826,27 @@ static void fill_unpack(AcxRequest *r, bool retire, UnpackParams *up) {
     up->user = r->dev_buf; up->packed = g_acx->heap + r->bounce_off; up->hstat = g_acx->hstat_d + r->slot;
     up->L = acx_device_layout(r->layout, r->dev_buf, up->packed);
     up->retire = retire ? 1 : 0;
+}
+
+// Grid of a wait kernel: one waiter CTA per request plus the helper CTAs of its RNDV_LATE requests (a late send's helpers
+// push the message if nobody has moved it yet, a receive's — fewer: it is a fallback — pull it). Sends share 2 x #SMs.
+static int plan_wait_grid(WaitBatch &wb, int n) {
+    wb.nreq = (uint32_t)n;
+    wb.fallback_ns = (uint64_t)g_late_fallback_us * 1000ull;
+    int nsend = 0;
+    for (int j = 0; j < n; j++) if (wb.w[j].late && !wb.w[j].is_recv) nsend++;
+    const size_t unit = 128u << 10;
+    int next = 0;
+    for (int j = 0; j < n; j++) {
+        WaitOne &w = wb.w[j];
+        if (!w.late) continue;
+        const size_t bytes = w.is_recv ? (size_t)w.cap : (size_t)w.late_bytes;
+        size_t want = std::max<size_t>(1, (bytes + unit - 1) / unit);
+        want = std::min<size_t>(want, w.is_recv ? 32 : (size_t)std::max(1, 2 * g_acx->sm_count / std::max(1, nsend)));
+        w.help_lo = (uint16_t)next; w.help_n = (uint16_t)want;
+        next += (int)want;
+    }
+    return n + next;
 }
 
 static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses, int qtype, void *queue) {
@@ -1891,7 +1942,7 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             memset(&wb, 0, sizeof wb);
             if (!rc) rc = fill_wait(it.r, it.st, retire, false, &wb.w[0]);
             wb.wd = make_wd(); wb.tr = make_tr();
-            if (!rc) rc = em.launch(wait_kernel, dim3(1), dim3(kWaitThreads), wb);
+            if (!rc) rc = em.launch(wait_kernel, dim3(plan_wait_grid(wb, 1)), dim3(kWaitThreads), wb);
             em.parallel = par;
             if (rc) return rc;
         }
@@ -1942,7 +1993,7 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             if (is_typed) typed.push_back(r);
         }
         wb.wd = make_wd(); wb.tr = make_tr();
-        if ((rc = em.launch(wait_kernel, dim3(n), dim3(kWaitThreads), wb))) return rc;
+        if ((rc = em.launch(wait_kernel, dim3(plan_wait_grid(wb, n)), dim3(kWaitThreads), wb))) return rc;
         for (AcxRequest *r : typed) {
             UnpackParams up;
             fill_unpack(r, retire, &up);
@@ -2286,7 +2337,8 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
         if (rc) return rc;
         wb.wd = make_wd(); wb.tr = make_tr();
         void *args[] = {&wb};
-        ACX_CUDA_WD(cudaLaunchKernel((const void *)wait_kernel, dim3(1), dim3(kWaitThreads), args, 0, host_stream()));
+        const int wgrid = plan_wait_grid(wb, 1);   // a late send may have to be pushed from here, a late receive pulled
+        ACX_CUDA_WD(cudaLaunchKernel((const void *)wait_kernel, dim3(wgrid), dim3(kWaitThreads), args, 0, host_stream()));
         g_acx->st.kernels++;
         if (r->kind == ACX_REQ_RECV && r->typed) {   // strided destination: scatter the staged image
             UnpackParams up;

@@ -30,7 +30,7 @@
 #include "../../include/acx_device.cuh"
 
 // ---- shared host/device layout -----------------------------------------------------
-enum { ACX_KIND_EAGER = 1, ACX_KIND_RNDV = 2, ACX_KIND_RNDV_PUSH = 3, ACX_KIND_RNDV_COOP = 4 };   // RNDV: second arriver moves; RNDV_PUSH: the sender always pushes; RNDV_COOP: second arriver moves, both ends may help (chunk cursor)
+enum { ACX_KIND_EAGER = 1, ACX_KIND_RNDV = 2, ACX_KIND_RNDV_PUSH = 3, ACX_KIND_RNDV_COOP = 4, ACX_KIND_RNDV_LATE = 5 };   // RNDV_LATE: large messages — the SENDER moves the data, at its trigger if the receive is posted by then, else from its wait kernel (see late_helper)   // RNDV: second arriver moves; RNDV_PUSH: the sender always pushes; RNDV_COOP: second arriver moves, both ends may help (chunk cursor)
 
 // Buffer locations travel as 64-bit "offsets": bit 63 clear = offset into the owner's symmetric heap;
 // bit 63 set = registered user allocation: bits [62:48] registration index, bits [47:0] offset inside it
@@ -47,6 +47,7 @@ struct alignas(64) acx_entry {  // one slot of a (src -> me, channel) ring; live
     uint64_t s_bytes;    // sender: message bytes
     uint64_t coop_cursor; // cooperative moving (ACX_COOP): next unclaimed chunk of this generation's payload (atomic add by agents on either GPU)
     uint64_t coop_done;   // cooperative moving: chunks fully copied; both are reset by the receiver's wait kernel before the slot is recycled
+    uint64_t claim;      // RNDV_LATE: who moves this generation's payload, ((generation + 1) << 2) | 1 sender / 2 receiver (fallback pull); CAS from either GPU
     uint32_t s_tag;
     uint32_t s_kind;     // low 8 bits: ACX_KIND_*; upper 24 bits: the sender's communicator context (checked by the receive: see ACX_ENT_CTX)
 };
@@ -76,6 +77,7 @@ struct alignas(64) acx_op {  // per request slot, local
     uint64_t bounce_n;   // receive side: bytes the bounce-out kernel still has to copy (0 if eager/zero-copy)
     uint64_t fused_decided;  // single-launch rendezvous gate: 1 once CTA 0 has published the match of this launch
     uint64_t coop;       // this message is moved cooperatively (kind RNDV_COOP): the mover claims chunks from the slot's cursor
+    uint64_t late_state; // RNDV_LATE at wait time: ((ticket + 1) << 2) | 1 nothing to move here / 2 move now (n, peer_ptr valid); written by the waiter CTA, polled by the helper CTAs
 };
 
 struct acx_anyres {  // resolution of a wildcard receive (device memory, one per request slot): which ring the matched message sits in
@@ -225,6 +227,8 @@ struct AcxRequest {
     bool in_graph;
     bool host_transport;      // no-GPU mode: backed by an MPI_Request
     bool null_op;             // peer was MPI_PROC_NULL: completes immediately, moves nothing, owns no slot
+    bool late;                // large message (>= ACX_LATE_PUSH_MIN): sender-moves protocol, the wait kernel carries helper CTAs
+    char *src_local;          // SEND: device address the message is read from (user buffer, bounce or packed image)
     bool coop;                // ACX_COOP: large rendezvous operation whose mover claims chunks cooperatively; the wait launches a coop_kernel in front of the wait kernel
     bool typed;               // non-contiguous datatype: the wire image is staged in the heap (bounce_off), packed before the send / unpacked after the wait
     AcxLayout layout;

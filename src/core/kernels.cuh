@@ -161,7 +161,7 @@ struct SendParams {
     uint64_t bytes;
     uint64_t serial;
     uint32_t tag, depth, eager_max, peer;
-    uint32_t ctx, pad0;     // communicator context, travels in the slot header (exact (source, tag, comm) matching: a receive checks it)
+    uint32_t ctx, late;     // ctx: communicator context, travels in the slot header (exact (source, tag, comm) matching: a receive checks it); late: announce RNDV_LATE (sender moves, now or at its wait)
     uint32_t apush, coop;   // apush: deterministic mode — this sender pushes the payload itself (gate + mover on its channel stream); coop: announce the message as RNDV_COOP (ACX_COOP)
     Watchdog wd;
     TraceCtx tr;
@@ -175,7 +175,7 @@ __device__ __forceinline__ void send_rndv_match(const SendParams &p, uint64_t k)
     acx_entry *ent = p.ring + e;
 
     ent->s_src_off = p.src_off; ent->s_bytes = p.bytes;
-    *reinterpret_cast<uint64_t *>(&ent->s_tag) = ACX_ENT_HEADER(p.tag, p.apush ? ACX_KIND_RNDV_PUSH : p.coop ? ACX_KIND_RNDV_COOP : ACX_KIND_RNDV, p.ctx);
+    *reinterpret_cast<uint64_t *>(&ent->s_tag) = ACX_ENT_HEADER(p.tag, p.apush ? ACX_KIND_RNDV_PUSH : p.coop ? ACX_KIND_RNDV_COOP : p.late ? ACX_KIND_RNDV_LATE : ACX_KIND_RNDV, p.ctx);
     uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull << 32);
     p.op->ticket = k; p.op->eager = 0; p.op->cta_count = 0; p.op->coop = p.coop;
     if (p.apush) {
@@ -188,6 +188,7 @@ __device__ __forceinline__ void send_rndv_match(const SendParams &p, uint64_t k)
         p.op->peer_ptr = (uint64_t)translate_peer(p.peer_heap, p.xlat, off);
         p.op->n = p.bytes < cap ? p.bytes : cap;
         if (p.op->n == 0) p.op->coop = 0;   // nothing to chunk (receive too small for a rendezvous message): the plain mover publishes completion
+        if (p.late) st_relaxed_sys(&ent->claim, ((g + 1) << 2) | 1ull);   // RNDV_LATE: the mover behind this trigger pushes now — the receiver's fallback pull must stay out
         p.op->mover = 1;
     } else {
         p.op->mover = 0;
@@ -266,7 +267,7 @@ __device__ __forceinline__ void recv_match_at(const RecvParams &p, uint64_t k) {
     }
     uint64_t old = atom_add_acqrel_sys(&ent->state, 1ull);   // release orders the mirror stores before it
     p.op->ticket = k; p.op->cta_count = 0; p.op->mover = 0; p.op->bounce_n = 0; p.op->coop = 0;
-    if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && (ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV || ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV_COOP) && !p.rndv_capable) {
+    if ((uint32_t)(old >> 32) == (uint32_t)(g + 1) && (ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV || ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV_COOP || ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV_LATE) && !p.rndv_capable) {
         // a rendezvous message is waiting for a receive that cannot hold it (no mover was launched for this receive):
         // complete it here with nothing moved; the wait reports MPI_ERR_TRUNCATE and 0 bytes
         __threadfence_system();
@@ -573,6 +574,27 @@ __global__ void __launch_bounds__(kMoverThreads) recv_any_kernel(AnyParams p) {
             rp.wd = p.wd; rp.tr = p.tr;
             p.res->ring = rp.ring; p.res->sack = peer_sack; p.res->eager = p.ctrl + G.off_eager + ring_idx * G.eager_max; p.res->src = src;
             recv_match_at(rp, k);
+            {   // A sender-moves (RNDV_LATE) message: this resolver runs at wait time, where moving data is legitimate, and the
+                // sender's own wait may be ordered behind something this receive gates — claim it and pull now unless the sender
+                // already has (no grace period: a wildcard receive only ever matches messages that have arrived).
+                acx_entry *ent = rp.ring + (uint32_t)(k % G.depth);
+                const uint64_t g = k / G.depth;
+                if (!op->mover && p.rndv_capable && ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV_LATE && ld_acquire_sys(&ent->done) < g + 1) {
+                    uint64_t cur = ld_relaxed_sys(&ent->claim);
+                    bool mine = false;
+                    while ((cur >> 2) != g + 1) {
+                        const uint64_t seen = atom_cas_acqrel_sys(&ent->claim, cur, ((g + 1) << 2) | 2ull);
+                        if (seen == cur) { mine = true; break; }
+                        cur = seen;
+                    }
+                    if (mine) {
+                        const uint64_t sb = ent->s_bytes;
+                        op->peer_ptr = (uint64_t)translate_peer(rp.peer_heap, rp.xlat, ent->s_src_off);
+                        op->n = sb < p.cap ? sb : p.cap;
+                        op->mover = 1;
+                    }
+                }
+            }
             __threadfence();
             st_release_sys(&op->fused_decided, 1);
         } else {
@@ -761,6 +783,14 @@ struct WaitOne {
     int32_t src, tag;
     uint32_t depth, eager_max;
     uint32_t ctx, pad0;     // the receive's communicator context (checked against the message header)
+    // RNDV_LATE (large messages; see late_helper): `late` marks a send that may have to push from this wait, or a receive
+    // that may have to fall back to pulling; helper CTAs help_lo .. help_lo+help_n-1 (counted behind the waiter CTAs) serve it
+    char *late_local;       // send: local source; recv: local landing address (heap buffer or bounce)
+    char *peer_heap;        // the peer's heap, peer-mapped
+    const uint64_t *xlat;   // translation row for registrations owned by the peer
+    uint64_t late_bytes;    // send: message bytes
+    uint16_t late, help_lo, help_n, pad1;
+    uint32_t late_tag, pad2;   // low bits of the request serial: together with the ticket it makes the op record's late_state word unique per (request, launch)
     uint16_t is_recv, retire;
     uint16_t bounce_kernel, coop;   // bounce_kernel: a bounce_out_kernel follows (large private destination); coop: reset the slot's chunk cursor when consuming (ACX_COOP)
     uint16_t off_source, off_tag, off_error, off_bytes;  // field offsets inside MPI_Status (0xffff = absent)
@@ -770,7 +800,13 @@ struct WaitBatch {
     WaitOne w[kWaitBatch];
     Watchdog wd;
     TraceCtx tr;
+    uint32_t nreq, pad;       // CTAs 0 .. nreq-1 are waiters (one per request); the rest are RNDV_LATE helpers
+    uint64_t fallback_ns;     // RNDV_LATE: how long a receive's wait watches an unclaimed message before it pulls it itself
 };
+
+// late_state = [request serial, 30 bits | ticket + 1, 32 bits | code, 2 bits]: an op record is reused by later requests (which may
+// draw the same ticket on another channel) and by graph relaunches (same request, next ticket) — a stale word must never match.
+__device__ __forceinline__ uint64_t late_tagv(const WaitOne &w, uint64_t k) { return ((uint64_t)(w.late_tag & 0x3fffffffu) << 34) | (((k + 1) & 0xffffffffull) << 2); }
 
 __device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) {
     __shared__ uint64_t s_n;
@@ -791,7 +827,50 @@ __device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) 
         const uint64_t g = k / w.depth;
         trace(b.tr, ACX_EV_WAIT_BEGIN, w.src, k, w.is_recv);
         if (!w.is_recv) {
-            spin_geq(&w.sack[e].sdone, g + 1, b.wd, 0x5e03);
+            if (w.late) {
+                // RNDV_LATE: if the receive was posted when the trigger ran, the mover launched behind it is pushing (or has
+                // pushed) — nothing to do here. Otherwise nobody has moved anything yet and the RECEIVER will not pull (its
+                // trigger leaves LATE messages alone, so that every GPU copies exactly its own sends, whatever the arrival
+                // order): as soon as the receive is posted (its mirror lands in my acks), claim the message and let this
+                // kernel's helper CTAs push it. Spinning here is what the user asked for; nothing spins at Isend time.
+                const uint64_t tagv = late_tagv(w, k);
+                if (op->mover) {
+                    st_release_sys(&op->late_state, tagv | 1ull);
+                    spin_geq(&w.sack[e].sdone, g + 1, b.wd, 0x5e03);
+                } else {
+                    unsigned ns = 0;
+                    const uint64_t t0 = b.wd.budget_ns ? globaltimer_ns() : 0;
+                    for (;;) {
+                        if (ld_acquire_sys(&w.sack[e].sdone) >= g + 1) { st_release_sys(&op->late_state, tagv | 1ull); break; }   // the receiver's fallback pull (or a truncation) completed it
+                        if (ld_acquire_sys(&w.sack[e].r_gen) == g + 1) {   // the receive is posted: its destination is mirrored into my acks
+                            acx_entry *rent = w.ring + e;                 // peer-mapped: the slot at the receiver
+                            uint64_t cur = ld_relaxed_sys(&rent->claim);
+                            bool mine = false;
+                            while ((cur >> 2) != g + 1) {
+                                const uint64_t seen = atom_cas_acqrel_sys(&rent->claim, cur, ((g + 1) << 2) | 1ull);
+                                if (seen == cur) { mine = true; break; }
+                                cur = seen;
+                            }
+                            if (mine) {
+                                const uint64_t cap = ld_relaxed_sys(&w.sack[e].r_cap), off = ld_relaxed_sys(&w.sack[e].r_dst_off);
+                                op->peer_ptr = (uint64_t)translate_peer(w.peer_heap, w.xlat, off);
+                                op->n = w.late_bytes < cap ? w.late_bytes : cap;
+                                op->cta_count = 0;
+                                st_release_sys(&op->late_state, tagv | 2ull);
+                            } else {
+                                st_release_sys(&op->late_state, tagv | 1ull);   // the receiver claimed it (fallback pull in progress)
+                            }
+                            spin_geq(&w.sack[e].sdone, g + 1, b.wd, 0x5e03);
+                            break;
+                        }
+                        if (ns) __nanosleep(ns);
+                        ns = ns < 256 ? ns * 2 + 20 : 256;
+                        if (b.wd.budget_ns && globaltimer_ns() - t0 > b.wd.budget_ns) { b.wd.diag[1] = k; b.wd.diag[2] = 1; b.wd.diag[0] = 0x5e03; __threadfence_system(); __trap(); }
+                    }
+                }
+            } else {
+                spin_geq(&w.sack[e].sdone, g + 1, b.wd, 0x5e03);
+            }
             s_n = 0; s_eager = 0;
         } else {
             acx_entry *ent = (w.any ? w.any->ring : w.ring) + e;
@@ -799,13 +878,41 @@ __device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) 
             unsigned ns = 0;
             uint64_t t0 = b.wd.budget_ns ? globaltimer_ns() : 0;
             int eager = 0;
+            uint64_t t_seen = 0;          // RNDV_LATE fallback: when the unclaimed message was first seen
+            bool late_decided = false;
             for (;;) {
                 if (ld_acquire_sys(&ent->done) >= g + 1) break;
-                if ((uint32_t)(ld_acquire_sys(&ent->state) >> 32) >= (uint32_t)(g + 1) && ACX_ENT_KIND(ent->s_kind) == ACX_KIND_EAGER) { eager = 1; break; }
+                const bool here = (uint32_t)(ld_acquire_sys(&ent->state) >> 32) >= (uint32_t)(g + 1);
+                if (here && ACX_ENT_KIND(ent->s_kind) == ACX_KIND_EAGER) { eager = 1; break; }
+                if (w.late && here && !late_decided && ACX_ENT_KIND(ent->s_kind) == ACX_KIND_RNDV_LATE) {
+                    // The sender moves LATE messages — from the mover behind its trigger, or from ITS wait kernel. If that wait is
+                    // not running (the sender waits for something else first: MPI lets it), nobody would ever move the message:
+                    // after a grace period this wait claims it and pulls it with its own helper CTAs (progress, at a price).
+                    const uint64_t now = globaltimer_ns();
+                    if (!t_seen) t_seen = now;
+                    else if (now - t_seen > b.fallback_ns) {
+                        uint64_t cur = ld_relaxed_sys(&ent->claim);
+                        bool mine = false;
+                        while ((cur >> 2) != g + 1) {
+                            const uint64_t seen = atom_cas_acqrel_sys(&ent->claim, cur, ((g + 1) << 2) | 2ull);
+                            if (seen == cur) { mine = true; break; }
+                            cur = seen;
+                        }
+                        if (mine) {
+                            const uint64_t sb = ent->s_bytes;
+                            op->peer_ptr = (uint64_t)translate_peer(w.peer_heap, w.xlat, ent->s_src_off);
+                            op->n = sb < w.cap ? sb : w.cap;
+                            op->cta_count = 0;
+                            st_release_sys(&op->late_state, late_tagv(w, k) | 2ull);
+                        }
+                        late_decided = true;   // mine: the helpers pull and publish `done`; theirs: the sender is on it
+                    }
+                }
                 if (ns) __nanosleep(ns);
                 ns = ns < 256 ? ns * 2 + 20 : 256;
                 if (b.wd.budget_ns && globaltimer_ns() - t0 > b.wd.budget_ns) { b.wd.diag[1] = k; b.wd.diag[2] = ent->state; b.wd.diag[0] = 0x5e04; __threadfence_system(); __trap(); }
             }
+            if (w.late && (ld_relaxed_sys(&op->late_state) >> 2) != (late_tagv(w, k) >> 2)) st_release_sys(&op->late_state, late_tagv(w, k) | 1ull);   // let the helper CTAs go: nothing to pull here
             uint64_t sb = ent->s_bytes;
             s_n = sb < w.cap ? sb : w.cap;
             if (!eager && w.cap <= w.eager_max) s_n = 0;   // rendezvous message into an eager-size receive: truncated, nothing was moved
@@ -859,9 +966,62 @@ __device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) 
         trace(b.tr, ACX_EV_WAIT_END, w.src, op->ticket, s_n);
     }
 }
+// RNDV_LATE helper CTAs of a wait kernel: they idle (on a LOCAL word) until the request's waiter CTA has decided, then
+// either leave or move the payload — a send's helpers push (STG over NVLink), a receive's fallback helpers pull. Static
+// slices, no helper waits for another, the last one out publishes completion to both ends (as the movers do).
+__device__ __forceinline__ void late_helper(const WaitBatch &b, unsigned h) {
+    int j = -1;
+#pragma unroll 1
+    for (int i = 0; i < (int)b.nreq && i < kWaitBatch; i++)
+        if (b.w[i].late && h >= b.w[i].help_lo && h < (unsigned)b.w[i].help_lo + b.w[i].help_n) { j = i; break; }
+    if (j < 0) return;
+    const WaitOne &w = b.w[j];
+    acx_op *op = w.op;
+    __shared__ uint64_t s_state, s_k;
+    if (threadIdx.x == 0) {
+        unsigned ns = 0;
+        const uint64_t t0 = b.wd.budget_ns ? globaltimer_ns() : 0;
+        if (w.serial) while (ld_acquire_sys(&op->armed) != w.serial) { __nanosleep(ns); ns = ns < 256 ? ns * 2 + 20 : 256; }   // host-side wait: the trigger may not have run yet
+        const uint64_t k = op->ticket;
+        uint64_t st;
+        ns = 0;
+        while (((st = ld_acquire_sys(&op->late_state)) >> 2) != (late_tagv(w, k) >> 2)) {
+            __nanosleep(ns); ns = ns < 512 ? ns * 2 + 40 : 512;
+            if (b.wd.budget_ns && globaltimer_ns() - t0 > b.wd.budget_ns) { b.wd.diag[1] = k; b.wd.diag[2] = st; b.wd.diag[0] = 0x5e0e; __threadfence_system(); __trap(); }
+        }
+        s_state = st; s_k = k;
+    }
+    __syncthreads();
+    if ((s_state & 3ull) != 2ull) return;
+    const uint64_t n = op->n, k = s_k;
+    char *peer = (char *)op->peer_ptr;
+    const unsigned rank = h - w.help_lo, nh = w.help_n;
+    if (rank == 0 && threadIdx.x == 0) trace(b.tr, ACX_EV_MOVE_BEGIN, (uint32_t)w.src, k, n);
+    const uint64_t per = ((n + nh - 1) / nh + 127) & ~127ull, lo = per * rank;
+    if (lo < n) {
+        const uint64_t len = n - lo < per ? n - lo : per;
+        if (w.is_recv) copy_bytes(w.late_local + lo, peer + lo, len, threadIdx.x, blockDim.x);
+        else copy_bytes(peer + lo, w.late_local + lo, len, threadIdx.x, blockDim.x);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(&op->cta_count, 1u) == nh - 1) {
+            const uint32_t e = (uint32_t)(k % w.depth);
+            const uint64_t g = k / w.depth;
+            op->cta_count = 0;
+            __threadfence_system();
+            // recv: w.ring is my ring, w.sack the sender's acks (peer-mapped); send: w.ring is the receiver's ring (peer-mapped), w.sack my acks
+            st_release_sys(&w.ring[e].done, g + 1);
+            st_release_sys(&w.sack[e].sdone, g + 1);
+            trace(b.tr, ACX_EV_MOVE_END, (uint32_t)w.src, k, n);
+        }
+    }
+}
 __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
     pdl_prologue();
-    wait_body(b, b.w[blockIdx.x]);
+    if (blockIdx.x < b.nreq) wait_body(b, b.w[blockIdx.x]);
+    else late_helper(b, blockIdx.x - b.nreq);
 }
 
 // MPIX_Recv_enqueue for eager-size receives: post + complete in ONE launch (trigger, then the wait's body). The small-

@@ -7,12 +7,13 @@
 //   16-B vector; rows y = -1 and y = ny and planes z = -1 and z = nz are the y / z ghosts.
 // One kernel per time step does everything:
 //   * the field is read ONLY by TMA: cp.async.bulk.tensor.3d boxes of (whole padded row) x (TY + 2 rows) x (1 plane) —
-//     one contiguous 10.5 KB run of memory each — into a 6-stage shared-memory ring with full/empty mbarriers; the
-//     loads run 4 planes ahead of the math and straight through tile boundaries, so ~85 KB per SM are in flight at all
+//     one contiguous 10.5 KB run of memory each — into an 8-stage shared-memory ring with full/empty mbarriers; the
+//     loads run 5 planes ahead of the math and straight through tile boundaries, so ~100 KB per SM are in flight at all
 //     times without a single register holding a prefetched operand (round 1: 113 registers, latency-bound at 34 % of HBM);
-//   * a tile is TY = 8 rows x all of x x TZ = 32 planes; thread (row, 8-cell vector) z-marches with the previous /
-//     current centre vectors in registers, reads the rows above / below and the next plane's centre from shared memory
-//     (3 LDS.128 per 8 cells), x-neighbours by warp shuffle (ghost / neighbouring-warp cells from shared memory);
+//   * a tile is TY = 8 rows x all of x x TZ = 32 planes; thread (row pair, 8-cell vector) z-marches with the previous /
+//     current centre vectors of its two rows in registers (each row is the other's y-neighbour), reads the row above /
+//     below the pair and the next plane's two centres from shared memory (4 LDS.128 per 16 cells), x-neighbours by warp
+//     shuffle (ghost / neighbouring-warp cells from shared memory), packed fp32 arithmetic (FADD2 / FFMA2);
 //   * ghost cells are written by the NEIGHBOURS: a tile's face cells are stored twice, into the local output field and —
 //     16-B vectors over NVLink — straight into the neighbour's ghost cells of ITS output field (peer-mapped symmetric
 //     heap), followed by one release flag per (face, tile) partition (acx::pready_signal_epoch on the partitioned
@@ -36,7 +37,7 @@
 namespace {
 
 constexpr int TY = 8, TZ = 32;      // tile: TY rows x all of x, z-march of TZ planes
-constexpr int STAGES = 6;           // shared-memory ring of planes
+constexpr int STAGES = 8;           // shared-memory ring of planes (8 x 10.6 KB per CTA, two CTAs per SM)
 constexpr int XPAD = 16;            // pad cells behind every row (see the layout comment above)
 constexpr int LAG = 2;              // a stage is refilled LAG planes after its last reader: the producer thread never waits for a sibling warp
 
@@ -71,26 +72,47 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap *tm, uint64_t *bar
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-__device__ __forceinline__ void unpack8(const uint4 &v, float f[8]) {
+// bf16x8 <-> four fp32 pairs. The stencil arithmetic runs on packed pairs (FADD2 / FMUL2 / FFMA2: two fp32 lanes per
+// instruction on sm_100): the kernel is issue-bound, not memory-bound, once TMA keeps the planes coming.
+__device__ __forceinline__ void unpack8(const uint4 &v, float2 f[4]) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < 4; i++) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    for (int i = 0; i < 4; i++) f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
 }
-__device__ __forceinline__ uint4 pack8(const float f[8]) {
+__device__ __forceinline__ uint4 pack8(const float2 f[4]) {
     uint4 v;
     __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
 #pragma unroll
-    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    for (int i = 0; i < 4; i++) h[i] = __float22bfloat162_rn(f[i]);
     return v;
+}
+// out = c0*cur + c1*(((xm + xp) + (ym + yp)) + (zm + zp)) for the 8 cells of one vector; left / right are the x-neighbours
+// of cells 0 and 7.
+__device__ __forceinline__ uint4 stencil8(const float2 cur[4], const float2 ym[4], const float2 yp[4], const float2 zm[4], const float2 zp[4], float left, float right,
+                                          float2 c0, float2 c1) {
+    float2 t[4], o[4];
+    t[0] = make_float2(left + cur[0].y, cur[0].x + cur[1].x);
+    t[1] = make_float2(cur[0].y + cur[1].y, cur[1].x + cur[2].x);
+    t[2] = make_float2(cur[1].y + cur[2].y, cur[2].x + cur[3].x);
+    t[3] = make_float2(cur[2].y + cur[3].y, cur[3].x + right);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 s = __fadd2_rn(__fadd2_rn(t[i], __fadd2_rn(ym[i], yp[i])), __fadd2_rn(zm[i], zp[i]));
+        o[i] = __ffma2_rn(c1, s, __fmul2_rn(c0, cur[i]));
+    }
+    return pack8(o);
 }
 
 // Face ids: 0 X-, 1 X+, 2 Y-, 3 Y+, 4 Z-, 5 Z+. Partition index of tile (ty, tc): x faces ty + nty * tc (every tile
 // touches both), y faces tc (tiles with ty == 0 / nty-1), z faces ty (tiles with tc == 0 / ntz-1).
-__global__ void __launch_bounds__(512, 2) halo_stencil_tma(const __grid_constant__ CUtensorMap tm, HaloDev P) {
+// Thread (rp, vx) owns rows 2*rp and 2*rp+1 of the tile's TY rows and the 8 cells vx*8 .. vx*8+7: two vectors per plane,
+// each the other's y-neighbour (registers), so a plane costs 4 LDS.128 per thread: the two next-plane centres, the row
+// above the pair and the row below it.
+__global__ void __launch_bounds__(256, 2) halo_stencil_tma(const __grid_constant__ CUtensorMap tm, HaloDev P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, nwarps = blockDim.x >> 5;
     const int vpr = P.nx >> 3;                                   // 16-B vectors per row
-    const int ly = tid / vpr, vx = tid - ly * vpr;
+    const int rp2 = tid / vpr, vx = tid - rp2 * vpr;             // row pair, vector
     const uint32_t row_bytes = (uint32_t)(P.nx + XPAD) * 2u;     // one padded row
     const uint32_t stage_bytes = row_bytes * (TY + 2);           // what one box delivers
     const uint32_t stage_stride = (stage_bytes + 127u) & ~127u;  // TMA destinations are 128-B aligned
@@ -107,99 +129,127 @@ __global__ void __launch_bounds__(512, 2) halo_stencil_tma(const __grid_constant
     // ---- producer state (thread 0 only): a stream of planes that runs through tile boundaries ----
     int p_it = blockIdx.x;      // tile iterator of the producer
     int p_q = 0;                // next plane of that tile to load (0 .. TZ+1)
-    uint32_t p_cnt = 0;         // planes loaded so far (selects stage and phase)
+    uint32_t p_cnt = 0;         // planes loaded so far
+    uint32_t p_stage = 0, p_par = 1;   // ring position of plane p_cnt; parity to wait for on its empty barrier (1 on the first pass: passes at once)
     auto produce = [&](uint32_t consumed) {   // `consumed` = planes every reader has certainly released (see LAG)
         while (p_it < P.ntiles && p_cnt < consumed + (uint32_t)STAGES) {
             const int t = P.order[p_it];
             const int ty = t % P.nty, tc = t / P.nty;
             if (p_q == 0) {
-                // the ghost cells this tile's boxes cover were written by the neighbours' previous step: acquire their flags
-                acx::wait_arrived_epoch(P.recv[0], t, P.wait_val);
-                acx::wait_arrived_epoch(P.recv[1], t, P.wait_val);
-                if (ty == 0) acx::wait_arrived_epoch(P.recv[2], tc, P.wait_val);
-                if (ty == P.nty - 1) acx::wait_arrived_epoch(P.recv[3], tc, P.wait_val);
-                if (tc == 0) acx::wait_arrived_epoch(P.recv[4], ty, P.wait_val);
-                if (tc == P.ntz - 1) acx::wait_arrived_epoch(P.recv[5], ty, P.wait_val);
+                // the ghost cells this tile's boxes cover were written by the neighbours' previous step: poll their flags (relaxed),
+                // then ONE acquire fence for all of them and the generic-to-async proxy fence in front of the TMA loads
+                auto poll = [&](const acx_pchan *ch, int part) { const uint64_t *f = ch->arrived + part; unsigned ns = 0; while (acx::ld_relaxed_sys(f) < P.wait_val) { __nanosleep(ns); ns = ns < 256 ? ns * 2 + 20 : 256; } };
+                poll(P.recv[0], t); poll(P.recv[1], t);
+                if (ty == 0) poll(P.recv[2], tc);
+                if (ty == P.nty - 1) poll(P.recv[3], tc);
+                if (tc == 0) poll(P.recv[4], ty);
+                if (tc == P.ntz - 1) poll(P.recv[5], ty);
+                asm volatile("fence.acq_rel.sys;" ::: "memory");
                 asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes (remote stores, made visible by the acquire) before async-proxy reads
             }
-            const uint32_t s = p_cnt % STAGES, use = p_cnt / STAGES;
-            mbar_wait(&empty[s], (use & 1u) ^ 1u);                 // every warp is done with the stage's previous plane
-            mbar_expect_tx(&full[s], stage_bytes);
+            mbar_wait(&empty[p_stage], p_par);                     // every warp is done with the stage's previous plane
+            mbar_expect_tx(&full[p_stage], stage_bytes);
             // box origin in the padded tensor: u64 column 0 (= 16 B before the interior row), padded row ty*TY, padded plane tc*TZ + q
-            tma_load_3d(&tm, &full[s], smem + (size_t)s * stage_stride, 0, ty * TY, tc * TZ + p_q);
+            tma_load_3d(&tm, &full[p_stage], smem + (size_t)p_stage * stage_stride, 0, ty * TY, tc * TZ + p_q);
             p_cnt++;
+            if (++p_stage == STAGES) { p_stage = 0; p_par ^= 1u; }
             if (++p_q == TZ + 2) { p_q = 0; p_it += gridDim.x; }
         }
     };
 
-    uint32_t c_cnt = 0;         // planes consumed so far by this thread's warp
+    // ---- consumer state: ring position / phase of the plane being consumed ----
+    uint32_t c_cnt = 0, c_stage = 0, c_par = 0;
+    auto advance = [&](uint32_t &st, uint32_t &par) { if (++st == STAGES) { st = 0; par ^= 1u; } };
+    auto release = [&](uint32_t st) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[st]); };
     uint32_t tile_no = 0;
+    const float2 c0v = make_float2(P.c0, P.c0), c1v = make_float2(P.c1, P.c1);
     if (tid == 0) produce(0);
     for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x, tile_no++) {
         const int t = P.order[it];
         const int ty = t % P.nty, tc = t / P.nty;
-        const int y = ty * TY + ly, z0 = tc * TZ, x0 = vx * 8;
-        const bool fym = y == 0, fyp = y == P.ny - 1, fxm = vx == 0, fxp = vx == vpr - 1;
-        const uint32_t row_off = (uint32_t)(ly + 1) * row_bytes + 16u + (uint32_t)x0 * 2u;   // my vector inside a stage
-        auto stage_of = [&](uint32_t cnt) -> const unsigned char * { return smem + (size_t)(cnt % STAGES) * stage_stride; };
-        auto wait_full = [&](uint32_t cnt) { mbar_wait(&full[cnt % STAGES], (cnt / STAGES) & 1u); };
-        auto release = [&](uint32_t cnt) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[cnt % STAGES]); };
+        const int ya = ty * TY + 2 * rp2, z0 = tc * TZ, x0 = vx * 8;
+        const uint32_t offA = (uint32_t)(2 * rp2 + 1) * row_bytes + 16u + (uint32_t)x0 * 2u;   // row A's vector inside a stage; row B is one row further
+        const uint32_t offB = offA + row_bytes;
 
-        float prev[8], cur[8];
-        wait_full(c_cnt);                                          // plane z0-1: only its centre row is needed
-        unpack8(*reinterpret_cast<const uint4 *>(stage_of(c_cnt) + row_off), prev);
-        release(c_cnt);
-        wait_full(c_cnt + 1);                                      // plane z0
-        unpack8(*reinterpret_cast<const uint4 *>(stage_of(c_cnt + 1) + row_off), cur);
-        __nv_bfloat16 *orow = P.un + (long long)z0 * P.pp + (long long)y * P.rp + x0;
-        const long long face_off = (long long)z0 * P.pp + (long long)y * P.rp;   // row origin relative to an interior origin
+        float2 prevA[4], curA[4], prevB[4], curB[4];
+        mbar_wait(&full[c_stage], c_par);                         // plane z0-1: only its centre rows are needed
+        {
+            const unsigned char *s = smem + (size_t)c_stage * stage_stride;
+            unpack8(*reinterpret_cast<const uint4 *>(s + offA), prevA);
+            unpack8(*reinterpret_cast<const uint4 *>(s + offB), prevB);
+        }
+        release(c_stage);
+        advance(c_stage, c_par); c_cnt++;
+        mbar_wait(&full[c_stage], c_par);                         // plane z0
+        {
+            const unsigned char *s = smem + (size_t)c_stage * stage_stride;
+            unpack8(*reinterpret_cast<const uint4 *>(s + offA), curA);
+            unpack8(*reinterpret_cast<const uint4 *>(s + offB), curB);
+        }
+        // which faces this thread's two rows / vector touch in this tile (most threads: none)
+        const uint32_t fmask = (vx == 0 ? 1u : 0u) | (vx == vpr - 1 ? 2u : 0u) | (ya == 0 ? 4u : 0u) | (ya + 1 == P.ny - 1 ? 8u : 0u) | (tc == 0 ? 16u : 0u) | (tc == P.ntz - 1 ? 32u : 0u);
+        long long off = (long long)z0 * P.pp + (long long)ya * P.rp;   // row A of the current plane, relative to an interior origin
+        uint32_t n_stage = c_stage, n_par = c_par;                 // ring position of the NEXT plane
+        advance(n_stage, n_par);
 #pragma unroll 1
         for (int zl = 0; zl < TZ; zl++) {
-            const uint32_t cc = c_cnt + 1 + (uint32_t)zl;         // counter of the current plane; cc+1 = next plane
-            wait_full(cc + 1);
-            const unsigned char *sc = stage_of(cc), *sn = stage_of(cc + 1);
-            const uint4 vn = *reinterpret_cast<const uint4 *>(sn + row_off);
-            const uint4 vm = *reinterpret_cast<const uint4 *>(sc + row_off - row_bytes);
-            const uint4 vp = *reinterpret_cast<const uint4 *>(sc + row_off + row_bytes);
-            float left = __shfl_up_sync(0xffffffffu, cur[7], 1), right = __shfl_down_sync(0xffffffffu, cur[0], 1);
-            if (lane == 0) left = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sc + row_off - 2));      // x0-1: ghost (vx == 0) or the neighbouring warp's cell
-            if (lane == 31) right = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sc + row_off + 16));    // x0+8: ghost (last vector) or the neighbouring warp's cell
-            float ym[8], yp[8], nxt[8], out[8];
-            unpack8(vm, ym); unpack8(vp, yp); unpack8(vn, nxt);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float xm = i == 0 ? left : cur[i - 1], xp = i == 7 ? right : cur[i + 1];
-                out[i] = P.c0 * cur[i] + P.c1 * (((xm + xp) + (ym[i] + yp[i])) + (prev[i] + nxt[i]));
+            mbar_wait(&full[n_stage], n_par);
+            const unsigned char *sc = smem + (size_t)c_stage * stage_stride, *sn = smem + (size_t)n_stage * stage_stride;
+            const uint4 vnA = *reinterpret_cast<const uint4 *>(sn + offA), vnB = *reinterpret_cast<const uint4 *>(sn + offB);
+            const uint4 vup = *reinterpret_cast<const uint4 *>(sc + offA - row_bytes), vdn = *reinterpret_cast<const uint4 *>(sc + offB + row_bytes);
+            float lA = __shfl_up_sync(0xffffffffu, curA[3].y, 1), rA = __shfl_down_sync(0xffffffffu, curA[0].x, 1);
+            float lB = __shfl_up_sync(0xffffffffu, curB[3].y, 1), rB = __shfl_down_sync(0xffffffffu, curB[0].x, 1);
+            if (lane == 0) {    // cell x0-1: the left ghost (vx == 0) or the neighbouring warp's last cell
+                lA = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sc + offA - 2));
+                lB = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sc + offB - 2));
             }
-            const uint4 vo = pack8(out);
-            const long long zoff = (long long)zl * P.pp;
-            *reinterpret_cast<uint4 *>(orow + zoff) = vo;
+            if (lane == 31) {   // cell x0+8: the right ghost (last vector) or the neighbouring warp's first cell
+                rA = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sc + offA + 16));
+                rB = __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(sc + offB + 16));
+            }
+            float2 nxtA[4], nxtB[4], edge[4];
+            unpack8(vnA, nxtA); unpack8(vup, edge);
+            const uint4 voA = stencil8(curA, edge, curB, prevA, nxtA, lA, rA, c0v, c1v);
+            unpack8(vnB, nxtB); unpack8(vdn, edge);
+            const uint4 voB = stencil8(curB, curA, edge, prevB, nxtB, lB, rB, c0v, c1v);
+            {
+                __nv_bfloat16 *o = P.un + off + x0;
+                *reinterpret_cast<uint4 *>(o) = voA;
+                *reinterpret_cast<uint4 *>(o + P.rp) = voB;
+            }
             // face cells also go straight into the neighbours' ghost cells (NVLink stores; self for a periodic dimension of extent 1)
-            if (fxm) *reinterpret_cast<uint4 *>(P.nb[0] + face_off + zoff + P.nx) = vo;                       // their right ghost vector [nx, nx+8): cell 0 is the one they read
-            if (fxp) *reinterpret_cast<uint4 *>(P.nb[1] + face_off + zoff - 8) = vo;                          // their left ghost vector [-8, 0): cell 7 is x = -1
-            if (fym) *reinterpret_cast<uint4 *>(P.nb[2] + face_off + zoff + (long long)P.ny * P.rp + x0) = vo;   // their row y = ny
-            if (fyp) *reinterpret_cast<uint4 *>(P.nb[3] + face_off + zoff - (long long)P.ny * P.rp + x0) = vo;   // their row y = -1
-            if (z0 + zl == 0) *reinterpret_cast<uint4 *>(P.nb[4] + face_off + zoff + (long long)P.nz * P.pp + x0) = vo;          // their plane z = nz
-            if (z0 + zl == P.nz - 1) *reinterpret_cast<uint4 *>(P.nb[5] + face_off + zoff - (long long)P.nz * P.pp + x0) = vo;   // their plane z = -1
+            if (fmask) {
+                if (fmask & 1u) { __nv_bfloat16 *g = P.nb[0] + off + P.nx; *reinterpret_cast<uint4 *>(g) = voA; *reinterpret_cast<uint4 *>(g + P.rp) = voB; }   // their right ghost vector [nx, nx+8): cell 0 is the one they read
+                if (fmask & 2u) { __nv_bfloat16 *g = P.nb[1] + off - 8; *reinterpret_cast<uint4 *>(g) = voA; *reinterpret_cast<uint4 *>(g + P.rp) = voB; }      // their left ghost vector [-8, 0): cell 7 is x = -1
+                if (fmask & 4u) *reinterpret_cast<uint4 *>(P.nb[2] + off + (long long)P.ny * P.rp + x0) = voA;                 // row A is y = 0 -> their row y = ny
+                if (fmask & 8u) *reinterpret_cast<uint4 *>(P.nb[3] + off + P.rp - (long long)P.ny * P.rp + x0) = voB;          // row B is y = ny-1 -> their row y = -1
+                if ((fmask & 16u) && zl == 0) { __nv_bfloat16 *g = P.nb[4] + off + (long long)P.nz * P.pp + x0; *reinterpret_cast<uint4 *>(g) = voA; *reinterpret_cast<uint4 *>(g + P.rp) = voB; }        // plane z = 0 -> their plane z = nz
+                if ((fmask & 32u) && zl == TZ - 1) { __nv_bfloat16 *g = P.nb[5] + off - (long long)P.nz * P.pp + x0; *reinterpret_cast<uint4 *>(g) = voA; *reinterpret_cast<uint4 *>(g + P.rp) = voB; }   // plane z = nz-1 -> their plane z = -1
+            }
 #pragma unroll
-            for (int i = 0; i < 8; i++) { prev[i] = cur[i]; cur[i] = nxt[i]; }
-            release(cc);                                           // rows above / below of the current plane have been read
-            if (tid == 0) produce(cc >= (uint32_t)LAG ? cc - LAG + 1 : 0);   // planes 0 .. cc-LAG were released by everyone at least LAG iterations ago (or the wait inside is short)
+            for (int i = 0; i < 4; i++) { prevA[i] = curA[i]; curA[i] = nxtA[i]; prevB[i] = curB[i]; curB[i] = nxtB[i]; }
+            off += P.pp;
+            release(c_stage);                                      // rows above / below of the current plane have been read
+            c_stage = n_stage; c_par = n_par; c_cnt++;
+            advance(n_stage, n_par);
+            if (tid == 0) produce(c_cnt > (uint32_t)LAG ? c_cnt - LAG : 0);   // planes below c_cnt-LAG were released by every warp at least LAG iterations ago (or the wait inside is short)
         }
-        release(c_cnt + 1 + TZ);                                   // plane z0+TZ: centre only
-        c_cnt += TZ + 2;
-        // ---- publish the tile's faces: every warp's stores -> tile barrier -> one system-scope fence -> flags ----
+        release(c_stage);                                          // plane z0+TZ: centres only
+        advance(c_stage, c_par); c_cnt++;
+        // ---- publish the tile's faces: every warp's stores -> tile barrier (release / acquire at CTA scope) -> ONE system-scope
+        // fence -> relaxed flag stores (fence + strong store = release). The last warp's lane 0 does it, not the producer thread:
+        // the plane stream keeps flowing while the flags go out.
         __syncwarp();
-        if (lane == 0) { __threadfence(); mbar_arrive(&tile_done[tile_no & 1]); }
-        if (tid == 0) {
+        if (lane == 0) mbar_arrive(&tile_done[tile_no & 1]);
+        if (tid == (int)blockDim.x - 32) {
             mbar_wait(&tile_done[tile_no & 1], (tile_no >> 1) & 1u);
             __threadfence_system();
-            acx::pready_signal_epoch(t, P.send[0], P.signal_val);
-            acx::pready_signal_epoch(t, P.send[1], P.signal_val);
-            if (ty == 0) acx::pready_signal_epoch(tc, P.send[2], P.signal_val);
-            if (ty == P.nty - 1) acx::pready_signal_epoch(tc, P.send[3], P.signal_val);
-            if (tc == 0) acx::pready_signal_epoch(ty, P.send[4], P.signal_val);
-            if (tc == P.ntz - 1) acx::pready_signal_epoch(ty, P.send[5], P.signal_val);
+            acx::st_relaxed_sys(P.send[0]->arrived + t, P.signal_val);
+            acx::st_relaxed_sys(P.send[1]->arrived + t, P.signal_val);
+            if (ty == 0) acx::st_relaxed_sys(P.send[2]->arrived + tc, P.signal_val);
+            if (ty == P.nty - 1) acx::st_relaxed_sys(P.send[3]->arrived + tc, P.signal_val);
+            if (tc == 0) acx::st_relaxed_sys(P.send[4]->arrived + ty, P.signal_val);
+            if (tc == P.ntz - 1) acx::st_relaxed_sys(P.send[5]->arrived + ty, P.signal_val);
         }
     }
 }
@@ -368,7 +418,7 @@ extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, f
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nfaces(a) > nfaces(b); });
     HCK(cudaMalloc((void **)&h->order_d, sizeof(int) * h->ntiles));
     HCK(cudaMemcpy(h->order_d, order.data(), sizeof(int) * h->ntiles, cudaMemcpyHostToDevice));
-    h->threads = nx / 8 * TY;
+    h->threads = nx / 8 * (TY / 2);   // two rows per thread
     h->smem = (size_t)STAGES * ((((size_t)(TY + 2) * (size_t)h->rp * 2) + 127) & ~(size_t)127) + (2 * STAGES + 2) * 8 + 16;
     HCK(cudaFuncSetAttribute(halo_stencil_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int dev = 0, sms = 148, occ = 1;
@@ -378,7 +428,10 @@ extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, f
     if (occ < 1) occ = 1;
     const char *g = getenv("ACX_HALO_CTAS_PER_SM");
     if (g && atoi(g) > 0) occ = std::min(occ, atoi(g));
-    h->grid = std::min(h->ntiles, sms * occ);
+    // equal-size tiles: a grid that does not divide them leaves most CTAs idle during the last wave (1024 tiles on 296 CTAs:
+    // four waves, the last one a quarter full). Use the fewest waves the resident CTAs allow and spread the tiles evenly.
+    const int slots = std::max(1, sms * occ), waves = (h->ntiles + slots - 1) / slots;
+    h->grid = std::min(h->ntiles, (h->ntiles + waves - 1) / waves);
     MPI_Barrier(MPI_COMM_WORLD);
     *out = h;
     return 0;

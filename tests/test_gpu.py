@@ -355,3 +355,13 @@ def test_exact_tag_matching(built, np_, wild):
     r = acxrun(built, np_, built / "build/tests/tags", env={"ACX_WILDCARDS": str(wild)})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_large_message_sender_moves_protocol(built, np_):
+    """8 MiB messages (>= ACX_LATE_PUSH_MIN): the sender moves them — at its trigger when the receive is posted, else from the
+    helper CTAs of its wait kernel; every rank sending first and waiting for its receive first needs the receiver-side
+    fallback pull; host waits; a relaunched graph — tests/c/late_push.c."""
+    r = acxrun(built, np_, built / "build/tests/late_push")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout

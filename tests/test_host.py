@@ -346,8 +346,8 @@ def test_hot_kernels_keep_their_register_budget(built):
     assert find("gemm_fp8_kernel")[1] == 0
     regs, stack = find("11wait_kernelE")
     assert regs <= 64 and stack == 0, (regs, stack)
-    regs, stack = find("halo_stencil_tma")   # two 512-thread CTAs per SM: the TMA ring, not registers, holds the data in flight
-    assert regs <= 64 and stack == 0, (regs, stack)
+    regs, stack = find("halo_stencil_tma")   # two 256-thread CTAs per SM, two rows per thread; the TMA ring, not registers, holds the data in flight
+    assert regs <= 128 and stack == 0, (regs, stack)
 
 
 def test_halo_kernel_is_tma_fed(built):

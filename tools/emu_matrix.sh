@@ -44,6 +44,19 @@ for p in ring ring_all ring_all_device graph_large large_msgs ordering stress st
     run sender-push $push_np $p ACX_SENDER_PUSH=1
 done
 [ "$mode" = tsan ] || run coop 3 large_msgs ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
+# large-message protocol (the sender moves, at its trigger or from its wait; receiver-side fallback pull) at emulation-sized messages
+LATE="ACX_LATE_PUSH_MIN=65536"
+lrun() { local label=$1 np=$2 prog=$3; shift 3; local t0=$(date +%s%N); out=$(env "$@" timeout 400 bin/acxrun -np $np --timeout 300 $T/$prog 262144 2>&1); rc=$?; local ms=$(( ($(date +%s%N) - t0) / 1000000 ));
+  if [ $rc -eq 0 ] && echo "$out" | grep -q "PASS"; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms; else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $rc "$(echo "$out" | tail -8)"; fails=$((fails+1)); fi; }
+for np in 1 2 3; do lrun late $np late_push $LATE; done
+lrun late-no-fallback-grace 2 late_push $LATE ACX_LATE_FALLBACK_US=0
+lrun late-jitter 3 late_push $LATE ACX_FAULT_DELAY_US=300
+lrun late-no-side-streams 2 late_push $LATE ACX_SIDE_STREAMS=0
+for p in large_msgs ring_all_device ring_all_graph graph_large ordering stress status_errors threads regcache; do
+    run late 2 $p $LATE
+    run late-jitter 3 $p $LATE ACX_FAULT_DELAY_US=200
+done
+run late-wildcards 3 wildcards ACX_WILDCARDS=1 $LATE
 run pbatch 2 ring_partitioned ACX_PBATCH=1
 run pbatch 3 ring_partitioned ACX_PBATCH=1
 run memops 2 ring_partitioned ACX_MEMOPS=1
