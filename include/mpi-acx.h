@@ -85,6 +85,10 @@ int MPIX_Free_mem(void *base);
  * this GPU dereferences to load/store the peer's instance directly over NVLink (cf. nvshmem_ptr).
  * `local` must come from MPIX_Alloc_mem at the same allocation sequence point on both ranks. */
 int MPIX_Peer_ptr(const void *local, int peer, void **peer_ptr);
+/* Pageable host buffers are pinned in place on first use and the registration is cached (and re-validated against the page
+ * frames behind it where /proc/self/pagemap shows them). Call this before freeing a host buffer the library has seen if you
+ * want its pages unpinned right away; it is never required for correctness where the validation works. */
+int MPIX_Buffer_forget(const void *buf, size_t bytes);
 /* Asymmetric allocations: exchange MPIX_Heap_offset() values, then map the peer's offset. */
 int MPIX_Heap_offset(const void *local, size_t *offset);
 int MPIX_Peer_ptr_at(size_t offset, int peer, void **peer_ptr);

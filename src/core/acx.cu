@@ -14,6 +14,7 @@
 #include <thread>
 #include <unistd.h>
 #include <sched.h>
+#include <fcntl.h>
 #include <sys/syscall.h>
 #include <ctype.h>
 #include <nvtx3/nvToolsExt.h>
@@ -87,7 +88,7 @@ static int g_coop = 0;                    // ACX_COOP: cooperative moving with c
 static long g_coop_min = 4 << 20;          // ACX_COOP_MIN_BYTES
 static long g_late_min = 4 << 20;          // ACX_LATE_PUSH_MIN: messages from this size up use the sender-moves protocol (RNDV_LATE); 0 = off
 static long g_late_fallback_us = 50;       // ACX_LATE_FALLBACK_US: grace period before a receive's wait pulls an unclaimed RNDV_LATE message itself
-static int g_pbatch = 0;                  // ACX_PBATCH: one kernel launch per MPIX_Startall / MPIX_Waitall group of partitioned requests instead of one per request
+static int g_pbatch = 1;                  // ACX_PBATCH (default on since round 2): one kernel launch per MPIX_Startall / MPIX_Waitall group of partitioned requests instead of one per request
 static int g_branch = 0;                  // ACX_PEER_BRANCH: run EVERY operation with a peer on that peer's side stream (fork at enqueue, join at the wait)
 static int g_fuse_rndv = 1, g_fuse_min_ctas = 8, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
 static int g_pdl = 1;   // programmatic dependent launch between consecutive acx kernels on a stream (ACX_PDL)
@@ -315,6 +316,56 @@ uint32_t acx_pflags_alloc(uint32_t n) {
     return r;
 }
 
+// Registrations of pageable host memory are cached (page granular) — and the application may free a buffer and get the same
+// addresses back from a later mmap: the cached registration then still maps the OLD, driver-pinned physical pages while the
+// CPU sees new ones (sends would transmit stale data, receives land in orphaned pages; the reference hands host buffers to
+// MPI and has no such cache). Pinned pages cannot migrate, so a registration is still good exactly when the first page's
+// physical frame is the one recorded when it was pinned: /proc/self/pagemap tells (frames are hidden from unprivileged
+// processes — then the check is skipped and cached host buffers must outlive the library, or be dropped explicitly with
+// MPIX_Buffer_forget).
+static uint64_t acx_pfn_of(uintptr_t va) {
+#if defined(__linux__) && !defined(ACX_EMU)
+    static int fd = -2;
+    if (fd == -2) fd = open("/proc/self/pagemap", O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return 0;
+    uint64_t v = 0;
+    if (pread(fd, &v, 8, (off_t)(va / 4096) * 8) != 8) return 0;
+    if (!(v >> 63)) return 0;                       // not present
+    return v & ((1ull << 55) - 1);                  // 0 when the kernel hides frame numbers
+#else
+    (void)va;
+    return 0;
+#endif
+}
+// Drop cached registrations that no longer describe the memory behind their addresses. Caller holds g_acx->mu.
+static void acx_host_regs_validate(uintptr_t lo, uintptr_t hi) {
+    for (size_t i = 0; i < g_acx->host_regs.size();) {
+        AcxHostReg &r = g_acx->host_regs[i];
+        if (r.pfn && r.hi > lo && r.lo < hi) {
+            const uint64_t now = acx_pfn_of(r.lo);
+            if (now != r.pfn) {
+                ACX_LOG(1, "host registration [%#lx, %#lx) went stale (the buffer was unmapped and its addresses reused): re-pinning", (unsigned long)r.lo, (unsigned long)r.hi);
+                cudaHostUnregister((void *)r.lo);
+                cudaGetLastError();
+                g_acx->host_regs.erase(g_acx->host_regs.begin() + (long)i);
+                continue;
+            }
+        }
+        i++;
+    }
+}
+extern "C" int MPIX_Buffer_forget(const void *buf, size_t bytes) {
+    if (!g_acx || !g_acx->initialized || !g_acx->device) return MPI_SUCCESS;
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    const uintptr_t lo = (uintptr_t)buf & ~(uintptr_t)4095, hi = ((uintptr_t)buf + bytes + 4095) & ~(uintptr_t)4095;
+    for (size_t i = 0; i < g_acx->host_regs.size();) {
+        AcxHostReg &r = g_acx->host_regs[i];
+        if (r.lo >= lo && r.hi <= hi) { cudaHostUnregister((void *)r.lo); cudaGetLastError(); g_acx->host_regs.erase(g_acx->host_regs.begin() + (long)i); }
+        else i++;
+    }
+    return MPI_SUCCESS;
+}
+
 int acx_device_alias(const void *p, size_t bytes, char **out) {
     if (!p || bytes == 0) { *out = (char *)p; return 0; }
     if (acx_heap_offset_of(p) >= 0) { *out = (char *)p; return 0; }
@@ -323,6 +374,7 @@ int acx_device_alias(const void *p, size_t bytes, char **out) {
         // cudaPointerGetAttributes driver call — status words and small host buffers come through here on every operation.
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
         const uintptr_t lo = (uintptr_t)p, hi = lo + bytes;
+        if (!g_acx->host_regs.empty()) acx_host_regs_validate(lo, hi);
         if (!g_acx->host_ptr_is_dev_ptr) {
             for (auto &r : g_acx->host_regs) if (lo >= r.lo && hi <= r.hi) { *out = r.dptr + (lo - r.lo); return 0; }
         } else {
@@ -340,7 +392,19 @@ int acx_device_alias(const void *p, size_t bytes, char **out) {
     cudaError_t e = cudaPointerGetAttributes(&a, p);
     if (e != cudaSuccess) { cudaGetLastError(); a.type = cudaMemoryTypeUnregistered; }
     if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) { *out = (char *)p; return 0; }
-    if (a.type == cudaMemoryTypeHost) { *out = (char *)a.devicePointer; return 0; }
+    if (a.type == cudaMemoryTypeHost) {
+        // Pinned host memory. If the page `p` starts in is one of OUR page-granular registrations, the buffer may still run
+        // into pages nobody has pinned yet (the table lookup above found the range only partly covered): fall through and
+        // register the rest. Trusting the attribute here sent kernels into unpinned pages — served by HMM page faults on this
+        // platform, racing with the cudaHostRegister of that very page for the next buffer: an intermittent "illegal memory
+        // access" on hardware (tests/c/status_errors.c, 1-KiB rows of a static array as message buffers).
+        bool ours = false;
+        {
+            std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+            for (auto &r : g_acx->host_regs) if ((uintptr_t)p >= r.lo && (uintptr_t)p < r.hi) { ours = true; break; }
+        }
+        if (!ours) { *out = (char *)a.devicePointer; return 0; }   // the application's own pinned allocation (cudaMallocHost / cudaHostRegister): pinned as a whole
+    }
     // pageable host memory: pin + map the covering pages. Registrations are never undone while the
     // library is up (device aliases are baked into persistent requests and graphs), so a new range that
     // partially overlaps earlier ones only registers the pages that are still uncovered.
@@ -360,7 +424,7 @@ int acx_device_alias(const void *p, size_t bytes, char **out) {
         }
         char *d = nullptr;
         cudaHostGetDevicePointer((void **)&d, (void *)lo, 0);
-        g_acx->host_regs.push_back({lo, hi, d});
+        g_acx->host_regs.push_back({lo, hi, d, acx_pfn_of(lo)});
         *out = d + ((uintptr_t)p - lo);
         return 0;
     }
@@ -384,7 +448,7 @@ int acx_device_alias(const void *p, size_t bytes, char **out) {
             ACX_ERR("cannot make host buffer %p (+%zu) device-accessible: %s", p, bytes, cudaGetErrorString(e));
             return MPI_ERR_BUFFER;
         }
-        g_acx->host_regs.push_back({cur, end, (char *)cur});
+        g_acx->host_regs.push_back({cur, end, (char *)cur, acx_pfn_of(cur)});
         cur = end;
     }
     *out = (char *)p;
@@ -732,7 +796,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_COOP_MIN_BYTES", nullptr, 4 << 20, &v); g_coop_min = std::max(65536L, v);
     acx_env_int("ACX_LATE_PUSH_MIN", nullptr, 4 << 20, &v); g_late_min = std::max(0L, v);   // must be the same on every rank (like every protocol knob)
     acx_env_int("ACX_LATE_FALLBACK_US", nullptr, 50, &v); g_late_fallback_us = std::max(0L, v);
-    acx_env_int("ACX_PBATCH", nullptr, 0, &v); g_pbatch = v != 0;   // opt-in until measured on hardware
+    acx_env_int("ACX_PBATCH", nullptr, 1, &v); g_pbatch = v != 0;   // one launch per MPIX_Startall / MPIX_Waitall group: measured 0.641 vs 0.776 ms per API-level halo step on 2x B200 (reference arm 0.700), profiles/raw/r2_call1/halo_api.txt
     acx_env_int("ACX_MEMOPS", nullptr, 0, &v); g_memops = v != 0 && !getenv("MPIACX_DISABLE_MEMOPS");   // partitioned Start / Wait as stream memOps (opt-in until measured)
     acx_env_int("ACX_PEER_BRANCH", nullptr, 0, &v); g_branch = v != 0;   // opt-in until measured on hardware
     acx_env_int("ACX_SENDER_PUSH", nullptr, 0, &v); g_apush = v != 0;   // opt-in: a spinning gate can deadlock against device-synchronizing host calls

@@ -254,7 +254,7 @@ struct AcxRequest {
     acx_pchan pchan_h;
 };
 
-struct AcxHostReg { uintptr_t lo, hi; char *dptr; };
+struct AcxHostReg { uintptr_t lo, hi; char *dptr; uint64_t pfn; };   // pfn: physical frame of the first page when it was pinned (0 = unknown): a different frame later means the application unmapped and re-mapped the range
 
 // A communicator the library has seen: its matching context and the translation between its ranks and COMM_WORLD's
 // (all windows, rings and side streams are indexed by world rank; the API speaks communicator ranks).

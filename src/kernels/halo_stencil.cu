@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256, 2) halo_stencil_tma(const __grid_constant
         long long off = (long long)z0 * P.pp + (long long)ya * P.rp;   // row A of the current plane, relative to an interior origin
         uint32_t n_stage = c_stage, n_par = c_par;                 // ring position of the NEXT plane
         advance(n_stage, n_par);
-#pragma unroll 1
+#pragma unroll 3   // the prev / cur / next register roles rotate with period 3: unrolled, the rotation is renaming instead of 32 moves per plane
         for (int zl = 0; zl < TZ; zl++) {
             mbar_wait(&full[n_stage], n_par);
             const unsigned char *sc = smem + (size_t)c_stage * stage_stride, *sn = smem + (size_t)n_stage * stage_stride;

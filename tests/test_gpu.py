@@ -365,3 +365,13 @@ def test_large_message_sender_moves_protocol(built, np_):
     r = acxrun(built, np_, built / "build/tests/late_push")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_host_buffers_reused_addresses_and_partially_pinned_rows(built, np_):
+    """A pageable host buffer is unmapped and its addresses come back from the next mmap: the cached registration must be
+    re-validated (page frames), not trusted; and 1-KiB rows of a static array, pinned page by page, all in flight —
+    tests/c/host_reuse.c (the intermittent illegal access of status_errors on hardware)."""
+    r = acxrun(built, np_, built / "build/tests/host_reuse")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout

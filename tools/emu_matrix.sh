@@ -16,7 +16,7 @@ run() {  # run <label> <np> <prog> [env...]
     if [ $rc -eq 0 ] && echo "$out" | grep -q "PASS"; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms
     else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $rc "$(echo "$out" | grep -v "ASan doesn\x27t fully support" | tail -${EMU_TAIL:-8})"; fails=$((fails+1)); fi
 }
-progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors sendrecv_enqueue reinit tags"
+progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors sendrecv_enqueue reinit tags host_reuse"
 nps="1 2 3"
 [ "$mode" = full ] && nps="1 2 3 4"
 for p in $progs; do for np in $nps; do run default $np $p; done; done
