@@ -87,6 +87,7 @@ static acx_anyres *g_anyres_d = nullptr;  // one resolution record per request s
 static int g_coop = 0;                    // ACX_COOP: cooperative moving with chunk stealing (both ends of a large rendezvous message copy it); must be set on every rank
 static long g_coop_min = 4 << 20;          // ACX_COOP_MIN_BYTES
 static long g_late_min = 4 << 20;          // ACX_LATE_PUSH_MIN: messages from this size up use the sender-moves protocol (RNDV_LATE); 0 = off
+static long g_late_helpers = 0;            // ACX_LATE_HELPERS: helper CTAs all late sends of one wait kernel share (0 = one per SM)
 static long g_late_fallback_us = 50;       // ACX_LATE_FALLBACK_US: grace period before a receive's wait pulls an unclaimed RNDV_LATE message itself
 static int g_pbatch = 1;                  // ACX_PBATCH (default on since round 2): one kernel launch per MPIX_Startall / MPIX_Waitall group of partitioned requests instead of one per request
 static int g_branch = 0;                  // ACX_PEER_BRANCH: run EVERY operation with a peer on that peer's side stream (fork at enqueue, join at the wait)
@@ -169,6 +170,24 @@ static void report_watchdog() {
 // =======================================================================================
 // allocators
 // =======================================================================================
+// Small host-to-device copies of library data go through a pinned scratch page: the library pins USER host buffers page by
+// page, so a local variable or a heap object of ours may share a page with one, and CUDA rejects (invalid argument) a
+// cudaMemcpy whose host range is only partly pinned — first seen on hardware with the wildcard tables.
+static int acx_h2d(void *dst, const void *src, size_t n, cudaStream_t stream) {
+    static char *scratch = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!scratch && cudaMallocHost((void **)&scratch, 4096) != cudaSuccess) { cudaGetLastError(); scratch = nullptr; }
+    for (size_t off = 0; off < n; off += 4096) {
+        const size_t len = std::min<size_t>(4096, n - off);
+        const void *from = (const char *)src + off;
+        if (scratch) { memcpy(scratch, from, len); from = scratch; }
+        cudaError_t e = cudaMemcpyAsync((char *)dst + off, from, len, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { ACX_ERR("host-to-device copy of %zu bytes failed: %s", n, cudaGetErrorString(e)); return MPI_ERR_OTHER; }
+    }
+    return 0;
+}
 static std::vector<cudaEvent_t> g_event_pool;
 static cudaEvent_t event_get() {
     std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
@@ -562,8 +581,7 @@ static void reg_progress() {
                 else cudaGetLastError();
             }
             if (mapped) {
-                cudaMemcpyAsync(g_acx->ctrl + g_acx->geom.off_xlat + ((uint64_t)p * g_acx->geom.maxreg + i) * 8, &mapped, 8, cudaMemcpyHostToDevice, host_stream());
-                cudaStreamSynchronize(host_stream());   // `mapped` is a stack variable; entries are rare
+                acx_h2d(g_acx->ctrl + g_acx->geom.off_xlat + ((uint64_t)p * g_acx->geom.maxreg + i) * 8, &mapped, 8, host_stream());   // entries are rare
                 to_ack.push_back({p, i});
                 wrote = true;
             }
@@ -796,6 +814,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_COOP_MIN_BYTES", nullptr, 4 << 20, &v); g_coop_min = std::max(65536L, v);
     acx_env_int("ACX_LATE_PUSH_MIN", nullptr, 4 << 20, &v); g_late_min = std::max(0L, v);   // must be the same on every rank (like every protocol knob)
     acx_env_int("ACX_LATE_FALLBACK_US", nullptr, 50, &v); g_late_fallback_us = std::max(0L, v);
+    acx_env_int("ACX_LATE_HELPERS", nullptr, 0, &v); g_late_helpers = std::max(0L, v);
     acx_env_int("ACX_PBATCH", nullptr, 1, &v); g_pbatch = v != 0;   // one launch per MPIX_Startall / MPIX_Waitall group: measured 0.641 vs 0.776 ms per API-level halo step on 2x B200 (reference arm 0.700), profiles/raw/r2_call1/halo_api.txt
     acx_env_int("ACX_MEMOPS", nullptr, 0, &v); g_memops = v != 0 && !getenv("MPIACX_DISABLE_MEMOPS");   // partitioned Start / Wait as stream memOps (opt-in until measured)
     acx_env_int("ACX_PEER_BRANCH", nullptr, 0, &v); g_branch = v != 0;   // opt-in until measured on hardware
@@ -1521,7 +1540,7 @@ static int any_tables() {
     memset(&h, 0, sizeof h);
     for (int i = 0; i < g_acx->size; i++) { h.peer_ctrl[i] = g_acx->peer_ctrl[i]; h.peer_heap[i] = g_acx->peer_heap[i]; }
     ACX_CUDA(cudaMalloc((void **)&g_any_tbl_d, sizeof h));
-    ACX_CUDA(cudaMemcpy(g_any_tbl_d, &h, sizeof h, cudaMemcpyHostToDevice));
+    if (acx_h2d(g_any_tbl_d, &h, sizeof h, host_stream())) return MPI_ERR_OTHER;
     ACX_CUDA(cudaMalloc((void **)&g_anyres_d, sizeof(acx_anyres) * (size_t)g_acx->geom.nops));
     ACX_CUDA(cudaMemset(g_anyres_d, 0, sizeof(acx_anyres) * (size_t)g_acx->geom.nops));
     return 0;
@@ -1893,7 +1912,7 @@ static void fill_unpack(AcxRequest *r, bool retire, UnpackParams *up) {
 }
 
 // Grid of a wait kernel: one waiter CTA per request plus the helper CTAs of its RNDV_LATE requests (a late send's helpers
-// push the message if nobody has moved it yet, a receive's — fewer: it is a fallback — pull it). Sends share 2 x #SMs.
+// push the message if nobody has moved it yet, a receive's — fewer: it is a fallback — pull it). Sends share one CTA per SM.
 static int plan_wait_grid(WaitBatch &wb, int n) {
     wb.nreq = (uint32_t)n;
     wb.fallback_ns = (uint64_t)g_late_fallback_us * 1000ull;
@@ -1906,7 +1925,7 @@ static int plan_wait_grid(WaitBatch &wb, int n) {
         if (!w.late) continue;
         const size_t bytes = w.is_recv ? (size_t)w.cap : (size_t)w.late_bytes;
         size_t want = std::max<size_t>(1, (bytes + unit - 1) / unit);
-        want = std::min<size_t>(want, w.is_recv ? 32 : (size_t)std::max(1, 2 * g_acx->sm_count / std::max(1, nsend)));
+        want = std::min<size_t>(want, w.is_recv ? 16 : (size_t)std::max(1, (int)(g_late_helpers > 0 ? g_late_helpers : g_acx->sm_count) / std::max(1, nsend)));   // 148 x 256 threads push as fast as the 74 x 512 mover (tools/bwprobe); a receive's helpers are a fallback
         w.help_lo = (uint16_t)next; w.help_n = (uint16_t)want;
         next += (int)want;
     }
@@ -2601,7 +2620,7 @@ static int presolve(AcxRequest *r) {
         c.cts = peerpf + hs->theirs.pf_cts;  // remote: written at Start
     }
     ACX_CUDA(cudaMalloc((void **)&r->pchan_d, sizeof(acx_pchan)));
-    ACX_CUDA(cudaMemcpy(r->pchan_d, &c, sizeof c, cudaMemcpyHostToDevice));
+    if (acx_h2d(r->pchan_d, &c, sizeof c, host_stream())) return MPI_ERR_OTHER;
     { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); g_hs.erase(r); }
     delete hs;
     r->resolved = true;

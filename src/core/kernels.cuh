@@ -28,12 +28,15 @@ struct TraceCtx {
 // are no-ops when the launch did not opt in (ACX_PDL=0, graph nodes, user kernels in between).
 #ifdef ACX_EMU   // host-side protocol emulation (tests/emu): kernels are called as functions in stream order
 __device__ __forceinline__ void pdl_prologue() {}
+__device__ __forceinline__ void pdl_wait_only() {}
 __device__ __forceinline__ uint64_t globaltimer_ns() { return emu::now_ns(); }
 #else
 __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+
+__device__ __forceinline__ void pdl_wait_only() { asm volatile("griddepcontrol.wait;" ::: "memory"); }   // dependents start when this grid has finished
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
@@ -1019,7 +1022,11 @@ __device__ __forceinline__ void late_helper(const WaitBatch &b, unsigned h) {
     }
 }
 __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
-    pdl_prologue();
+    // With helper CTAs on board this kernel must NOT release its programmatic dependents early: the next step's kernels —
+    // among them the next wait kernel with its few hundred helper CTAs — would become resident at once and sit in
+    // griddepcontrol.wait holding registers and thread slots while the mover this kernel waits for starves (measured on
+    // B200: the 256-MiB self-ring slowed down in proportion to the helper count and hung at 296; fine with ACX_PDL=0).
+    if (gridDim.x > b.nreq) pdl_wait_only(); else pdl_prologue();
     if (blockIdx.x < b.nreq) wait_body(b, b.w[blockIdx.x]);
     else late_helper(b, blockIdx.x - b.nreq);
 }
