@@ -196,6 +196,11 @@ def run_acx(a) -> int:
     if not dry:
         h_in, h_out = h_in.pin_memory(), h_out.pin_memory()   # after acx.init(): pages land on the GPU's NUMA node (MPIX_Init binds the rank)
     h_in.fill_(rank + 1)
+    # a stream of our own, not the legacy default stream torch starts on: stream 0 synchronizes implicitly with every blocking
+    # stream of the process and takes no programmatic dependent launches — the C harness (and any real application) enqueues
+    # communication on an ordinary stream
+    if not dry:
+        torch.cuda.set_stream(torch.cuda.Stream())
     stream = torch.cuda.current_stream()
 
     def barrier():

@@ -150,6 +150,7 @@ static void report_watchdog() {
             case 0x5e0a: what = "sender-push gate: the matching receive was never posted"; break;
             case 0x5e0b: what = "wildcard receive: no matching send arrived"; break;
             case 0x5e0c: what = "cooperative-move gate: the peer never arrived"; break;
+            case 0x5e0f: what = "host-predicted ticket (b) differs from the one the trigger drew (a): a memOp wait was built on the wrong slot"; break;
             case 0x5e0e: what = "wait kernel helper: the request's waiter CTA never decided (a = ticket, b = state word)"; break;
         }
         ACX_ERR("WATCHDOG (code 0x%llx, a=0x%llx b=0x%llx): %s", (unsigned long long)g_diag[0], (unsigned long long)g_diag[1],
@@ -434,6 +435,20 @@ int acx_device_alias(const void *p, size_t bytes, char **out) {
         // no unified addressing for registered memory: one registration must cover the buffer
         for (auto &r : g_acx->host_regs)
             if (lo >= r.lo && hi <= r.hi) { *out = r.dptr + ((uintptr_t)p - r.lo); return 0; }
+        // partly covered by earlier registrations: replace them by one registration of the union (their aliases die with
+        // them — acceptable on the rare platform without unified addressing of registered memory; nothing of theirs can be
+        // in flight for THIS buffer, and other buffers on those pages are re-aliased on their next use)
+        for (size_t i = 0; i < g_acx->host_regs.size();) {
+            AcxHostReg &r = g_acx->host_regs[i];
+            if (r.hi > lo && r.lo < hi) {
+                lo = std::min(lo, r.lo); hi = std::max(hi, r.hi);
+                cudaHostUnregister((void *)r.lo); cudaGetLastError();
+                g_acx->host_regs.erase(g_acx->host_regs.begin() + (long)i);
+                i = 0;   // the union grew: re-scan
+                continue;
+            }
+            i++;
+        }
         e = cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterMapped | cudaHostRegisterPortable);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -921,6 +936,8 @@ extern "C" int MPIX_Init(void) {
     g_acx->slot_req.assign(g_acx->geom.nops, nullptr);
     for (int s = g_acx->geom.nops - 1; s >= 0; s--) g_acx->free_slots.push_back(s);
     g_acx->recv_outstanding.assign(g_acx->size, std::vector<int>(g_acx->geom.nchan, 0));
+    g_acx->send_count.assign(g_acx->size, std::vector<AcxState::ChanCount>(g_acx->geom.nchan));
+    g_acx->recv_count.assign(g_acx->size, std::vector<AcxState::ChanCount>(g_acx->geom.nchan));
     g_acx->device = true;
     g_acx->initialized = true;
     reg_init();
@@ -1414,12 +1431,28 @@ static void tagdir_init() {
 #endif
 }
 
+// Predict the ticket the trigger kernel of a stream-mode operation will draw (see AcxState::ChanCount). ~0 = unknown.
+static uint64_t host_ticket(bool is_send, int peer, int chan, cudaStream_t stream, bool in_graph) {
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    AcxState::ChanCount &c = (is_send ? g_acx->send_count : g_acx->recv_count)[(size_t)peer][(size_t)chan];
+    if (in_graph) c.dev = true;                                   // a graph's launches are invisible to the host
+    else if (c.next > 0 && c.stream != stream) c.dev = true;      // two streams: the execution order of their triggers is anybody's guess
+    if (c.dev) return ~0ull;
+    c.stream = stream;
+    return c.next++;
+}
+static void host_tickets_forget_recv(int source) {   // a wildcard receive claims tickets on whichever channel matches
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    for (int s = 0; s < g_acx->size; s++) if (source < 0 || s == source) for (auto &c : g_acx->recv_count[(size_t)s]) c.dev = true;
+}
+
 static AcxRequest *new_request(AcxReqKind kind, int peer, int tag, int ctx, size_t bytes, const void *buf) {
     AcxRequest *r = new AcxRequest();
     memset((void *)r, 0, sizeof *r);
     r->magic = ACX_REQ_MAGIC; r->kind = kind; r->peer = peer; r->comm_peer = peer; r->tag = tag; r->comm_ctx = ctx; r->bytes = bytes;
     r->user_buf = (void *)buf; r->bounce_off = -1; r->heap_off = -1; r->slot = -1; r->land_off = -1;
     r->serial = g_acx->serial++;
+    r->hticket = ~0ull;
     r->mpi_req = MPI_REQUEST_NULL;
     return r;
 }
@@ -1668,6 +1701,7 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         r->late = g_late_min > 0 && !eager && !fused && !apush && !r->coop && (long)bytes >= g_late_min;
         sp.late = r->late ? 1 : 0;
         r->src_local = (char *)src_local;
+        if (!dropped) r->hticket = host_ticket(true, dest, r->chan, r->stream, r->in_graph);
         if (!dropped && fused) { if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail; }
         else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
         if (!eager) {
@@ -1726,6 +1760,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         // Wildcard: nothing is launched now; the wait resolves, matches and (for a rendezvous message) pulls.
         if (ty.noncontig) { ACX_ERR("wildcard receives with non-contiguous datatypes are not supported on the device transport"); if (qtype == MPIX_QUEUE_CUDA_GRAPH) cudaGraphDestroy(em.graph); delete r; return MPI_ERR_TYPE; }
         r->wild = true; r->chan = -1;
+        host_tickets_forget_recv(source == MPI_ANY_SOURCE ? -1 : wsource);   // it will claim a ticket on whichever channel matches: the host can no longer predict those
         if ((rc = any_tables())) { if (qtype == MPIX_QUEUE_CUDA_GRAPH) cudaGraphDestroy(em.graph); delete r; return rc; }
         if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) { if (qtype == MPIX_QUEUE_CUDA_GRAPH) cudaGraphDestroy(em.graph); delete r; return MPI_ERR_OTHER; }
         if ((rc = acx_device_alias(buf, bytes, &r->dev_buf))) goto fail;
@@ -1799,6 +1834,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr; mp.vec256 = g_mover_256; mp.block_bytes = (uint32_t)g_mover_block;
         const int fgrid = (rndv_capable && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
         r->coop = g_coop && rndv_capable && !g_apush && !g_mover_tma && (long)bytes >= g_coop_min;   // "may be": the wait's gate + agent kernels help only if the message says RNDV_COOP
+        r->hticket = host_ticket(false, source, r->chan, r->stream, r->in_graph);
         if (fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas) {
             if ((rc = em.launch2(recv_rndv_fused, dim3(fgrid), dim3(kMoverThreads), rp, mp))) goto fail;
         } else {
@@ -1845,6 +1881,7 @@ static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_w
     w->serial = host_wait ? r->serial : 0;
     w->retire = retire ? 1 : 0;
     w->late_tag = (uint32_t)r->serial;
+    w->hticket = r->hticket;
     w->src = r->comm_peer; w->tag = r->tag; w->ctx = (uint32_t)r->comm_ctx;   // status reports the peer in the caller's communicator
     w->off_source = w->off_tag = w->off_error = w->off_bytes = 0xffff;
     if (r->kind == ACX_REQ_SEND) {
@@ -2076,6 +2113,24 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             if (is_typed) typed.push_back(r);
         }
         wb.wd = make_wd(); wb.tr = make_tr();
+        if (g_memops && g_cuStreamBatchMemOp && qtype == MPIX_QUEUE_CUDA_STREAM && !em.capturing) {
+            // Stream memOps on the on-stream path (the reference's cuStreamWaitValue32, src/sendrecv.cu:373-385, polls a host flag
+            // over PCIe; here the words live in local HBM): where the host could predict an operation's ticket, the stream
+            // waits for its completion word in the memOp unit — no SM spins — and the completion kernel behind it (copy-out of
+            // eager payloads, status, slot bookkeeping) finds everything in place. Large sends (which may have to push from
+            // their wait) and operations on device-counted channels keep the spinning wait.
+            MemOpBatch mb;
+            const acx_geom &G = g_acx->geom;
+            for (int j = 0; j < n; j++) {
+                AcxRequest *r = need[base + j].r;
+                if (r->hticket == ~0ull || r->wild) continue;
+                const uint32_t e = (uint32_t)(r->hticket % (uint64_t)G.depth);
+                const uint64_t g = r->hticket / (uint64_t)G.depth;
+                if (r->kind == ACX_REQ_RECV) mb.wait_geq64(&(acx_entries_of(g_acx->ctrl) + acx_entry_index(G, r->peer, r->chan, 0))[e].done, g + 1);
+                else if (!r->late) mb.wait_geq64(&(acx_sacks_of(g_acx->ctrl) + acx_entry_index(G, r->peer, r->chan, 0))[e].sdone, g + 1);
+            }
+            if (!mb.ops.empty() && (rc = mb.flush(em.stream))) return rc;
+        }
         if ((rc = em.launch(wait_kernel, dim3(plan_wait_grid(wb, n)), dim3(kWaitThreads), wb))) return rc;
         for (AcxRequest *r : typed) {
             UnpackParams up;
@@ -2225,6 +2280,8 @@ extern "C" int MPIX_Recv_enqueue(void *buf, int count, MPI_Datatype datatype, in
         const bool retire = !em.in_graph();
         if ((rc = fill_wait(r, status, retire, false, &wb.w[0]))) goto fail;
         wb.wd = make_wd(); wb.tr = make_tr();
+        r->hticket = host_ticket(false, source, r->chan, em.stream, r->in_graph);
+        wb.w[0].hticket = r->hticket;
         if ((rc = em.launch2(recv_wait_fused, dim3(1), dim3(kWaitThreads), rp, wb))) goto fail;
     }
     if (em.capturing && (rc = attach_to_graph(em.graph, r->slot))) goto fail;
@@ -2347,6 +2404,9 @@ extern "C" int MPIX_Sendrecv_enqueue(const void *sendbuf, int sendcount, MPI_Dat
         const bool retire = !em.in_graph();
         if ((rc = fill_wait(r, status, retire, false, &wb.w[0]))) goto fail;
         wb.wd = make_wd(); wb.tr = make_tr();
+        r->hticket = host_ticket(false, wsource, r->chan, em.stream, r->in_graph);   // both halves draw a ticket in this kernel
+        wb.w[0].hticket = r->hticket;
+        (void)host_ticket(true, wdest, schan, em.stream, r->in_graph);
         void *args[] = {&sp, &rp, &wb};
         cudaError_t le;
         if (g_pdl && !em.capturing) {

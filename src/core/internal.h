@@ -227,6 +227,7 @@ struct AcxRequest {
     bool in_graph;
     bool host_transport;      // no-GPU mode: backed by an MPI_Request
     bool null_op;             // peer was MPI_PROC_NULL: completes immediately, moves nothing, owns no slot
+    uint64_t hticket;         // ticket this operation's trigger will draw, predicted on the host (~0 = unknown: graphs, several streams or wildcards on its channel); lets a stream wait be a memOp
     bool late;                // large message (>= ACX_LATE_PUSH_MIN): sender-moves protocol, the wait kernel carries helper CTAs
     char *src_local;          // SEND: device address the message is read from (user buffer, bounce or packed image)
     bool coop;                // ACX_COOP: large rendezvous operation whose mover claims chunks cooperatively; the wait launches a coop_kernel in front of the wait kernel
@@ -293,6 +294,11 @@ struct AcxState {
     MPI_Comm icomm;                          // private dup of COMM_WORLD for handshakes
     std::atomic<uint64_t> serial{1};         // request serials (application threads enqueue concurrently)
     std::vector<std::vector<int>> recv_outstanding;  // [src][chan] posted-not-yet-waited recvs
+    // Host-side ticket prediction per (peer, channel, direction): exact while every operation on the channel is enqueued in
+    // stream mode on ONE stream (tickets are drawn by the trigger kernels in execution order); a graph, a second stream or a
+    // wildcard receive makes the channel device-counted for good.
+    struct ChanCount { uint64_t next = 0; cudaStream_t stream = nullptr; bool dev = false; };
+    std::vector<std::vector<ChanCount>> send_count, recv_count;   // [peer][chan]
     // config
     bool trace = false;
     int verbose = 0;

@@ -223,6 +223,7 @@ __device__ __forceinline__ void send_body(const SendParams &p) {
             ent->s_bytes = p.bytes;
             *reinterpret_cast<uint64_t *>(&ent->s_tag) = ACX_ENT_HEADER(p.tag, ACX_KIND_EAGER, p.ctx);
             red_release_add_sys(&ent->state, 1ull << 32);
+            st_release_sys(&ent->done, k / p.depth + 1);   // one completion word for every kind of message: what a stream memOp (or a wait kernel) watches
             // The source buffer is reusable as soon as this kernel retires: nothing to wait for later.
             if (p.hstat) ACX_HOST_FLAG_SET(&p.hstat->retired, 1);
             trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes);
@@ -793,6 +794,7 @@ struct WaitOne {
     const uint64_t *xlat;   // translation row for registrations owned by the peer
     uint64_t late_bytes;    // send: message bytes
     uint16_t late, help_lo, help_n, pad1;
+    uint64_t hticket;          // host-predicted ticket (~0: none): checked against the ticket the trigger drew
     uint32_t late_tag, pad2;   // low bits of the request serial: together with the ticket it makes the op record's late_state word unique per (request, launch)
     uint16_t is_recv, retire;
     uint16_t bounce_kernel, coop;   // bounce_kernel: a bounce_out_kernel follows (large private destination); coop: reset the slot's chunk cursor when consuming (ACX_COOP)
@@ -826,6 +828,11 @@ __device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) 
             }
         }
         const uint64_t k = op->ticket;
+        if (w.hticket != ~0ull && k != w.hticket) {   // the host predicted this ticket and built memOp waits on it: a wrong prediction must never pass silently
+            b.wd.diag[1] = k; b.wd.diag[2] = w.hticket; b.wd.diag[0] = 0x5e0f;
+            __threadfence_system();
+            __trap();
+        }
         const uint32_t e = (uint32_t)(k % w.depth);
         const uint64_t g = k / w.depth;
         trace(b.tr, ACX_EV_WAIT_BEGIN, w.src, k, w.is_recv);
@@ -915,6 +922,7 @@ __device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) 
                 ns = ns < 256 ? ns * 2 + 20 : 256;
                 if (b.wd.budget_ns && globaltimer_ns() - t0 > b.wd.budget_ns) { b.wd.diag[1] = k; b.wd.diag[2] = ent->state; b.wd.diag[0] = 0x5e04; __threadfence_system(); __trap(); }
             }
+            if (!eager && (uint32_t)(ld_acquire_sys(&ent->state) >> 32) >= (uint32_t)(g + 1) && ACX_ENT_KIND(ent->s_kind) == ACX_KIND_EAGER) eager = 1;   // left the loop through `done`: eager deposits set it too
             if (w.late && (ld_relaxed_sys(&op->late_state) >> 2) != (late_tagv(w, k) >> 2)) st_release_sys(&op->late_state, late_tagv(w, k) | 1ull);   // let the helper CTAs go: nothing to pull here
             uint64_t sb = ent->s_bytes;
             s_n = sb < w.cap ? sb : w.cap;

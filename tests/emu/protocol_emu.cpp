@@ -79,6 +79,7 @@ static void build_recv(int me, int src, int chan, uint64_t dst_off, uint64_t cap
 }
 static void build_wait(int me, bool is_recv, int peer, int chan, uint64_t dst_off, uint64_t cap, int tag, int slot, bool coop, const acx_anyres *any, WaitOne *w) {
     memset(w, 0, sizeof *w);
+    w->hticket = ~0ull;   // no host-side ticket prediction here
     w->op = op_of(me, slot); w->hstat = &R[me].hstat[slot];
     w->depth = G.depth; w->eager_max = G.eager_max; w->retire = 1; w->src = peer; w->tag = tag;
     w->off_source = w->off_tag = w->off_error = w->off_bytes = 0xffff;
@@ -91,7 +92,7 @@ static void build_wait(int me, bool is_recv, int peer, int chan, uint64_t dst_of
         w->eager = R[me].ctrl + G.off_eager + ring_idx * G.eager_max;
         w->sack = acx_sacks_of(R[peer].ctrl) + acx_entry_index(G, me, chan, 0);
     }
-    w->dst = R[me].heap + dst_off; w->cap = cap; w->coop = coop ? 1 : 0;
+    w->dst = R[me].heap + dst_off; w->cap = cap; w->coop = coop ? 1 : 0; w->hticket = ~0ull;
 }
 static void build_coop(int me, bool is_send, int peer, int chan, uint64_t off, uint64_t bytes, int slot, CoopParams *cp) {
     memset(cp, 0, sizeof *cp);
@@ -148,6 +149,7 @@ static void ring_rank(int me, int n, size_t bytes, int iters, bool coop, int mov
         int nw = 1;
         if (rndv) { build_wait(me, false, right, chan, 0, 0, tag, s_slot, coop, nullptr, &wb.w[1]); nw = 2; }
         wb.wd = wd_of(me); wb.tr = no_trace();
+        wb.nreq = (uint32_t)nw;
         emu::launch(nw, kBlk, [=] { wait_kernel(wb); });
         const size_t bad = mismatches(R[me].heap + r_off, bytes, 1000u * left + it);
         CHECK(bad == 0, "ring n=%d bytes=%zu coop=%d iter %d rank %d: %zu wrong bytes", n, bytes, (int)coop, it, me, bad);
@@ -202,6 +204,7 @@ static Msg recv_one(int me, int src, int tag, uint64_t dst_off, uint64_t cap, bo
     R[me].hstat[slot] = acx_host_status();
     // read the status the way a host wait would: ask the kernel to fill hstat (serial != 0 makes it wait for `armed` first)
     wb.w[0].serial = op_of(me, slot)->armed;
+    wb.nreq = 1;
     emu::launch(1, kBlk, [=] { wait_kernel(wb); });
     Msg m;
     memcpy(&m, R[me].heap + dst_off, sizeof m);
@@ -238,7 +241,8 @@ static void sender_rank(int me, int count, int jitter_us, unsigned seed, bool on
             memset(&wb, 0, sizeof wb);
             build_wait(me, false, 0, tag % G.nchan, 0, 0, tag, slot, false, nullptr, &wb.w[0]);
             wb.wd = wd_of(me); wb.tr = no_trace();
-            emu::launch(1, kBlk, [=] { wait_kernel(wb); });   // the source buffer is reused by the next message
+            wb.nreq = 1;
+    emu::launch(1, kBlk, [=] { wait_kernel(wb); });   // the source buffer is reused by the next message
         } else {
             // eager: the trigger has copied the payload out; nothing to wait for
         }
@@ -331,6 +335,7 @@ static void typed_rank(int me, int n, int nx, int ny, int nz, int iters, unsigne
         int nw = 1;
         if (rndv) { build_wait(me, false, right, chan, 0, 0, tag, s_slot, false, nullptr, &wb.w[1]); nw = 2; }
         wb.wd = wd_of(me); wb.tr = no_trace();
+        wb.nreq = (uint32_t)nw;
         emu::launch(nw, kBlk, [=] { wait_kernel(wb); });
         UnpackParams up;
         memset(&up, 0, sizeof up);

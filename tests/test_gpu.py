@@ -375,3 +375,13 @@ def test_host_buffers_reused_addresses_and_partially_pinned_rows(built, np_):
     r = acxrun(built, np_, built / "build/tests/host_reuse")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("prog", ["ring", "ring_all", "ordering", "stress", "tags", "late_push"])
+def test_stream_memops_on_the_p2p_path(built, prog):
+    """ACX_MEMOPS=1: the waits of operations whose ticket the host can predict become cuStreamWaitValue64 (GEQ) on the
+    completion words in local HBM, batched per MPIX_Waitall_enqueue; the completion kernel behind them never spins. A wrong
+    prediction traps (0x5e0f). Reference: src/sendrecv.cu:373-385, 479-513 (WaitValue32 on host flags)."""
+    r = acxrun(built, 2, built / f"build/tests/{prog}", env={"ACX_MEMOPS": "1"})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout

@@ -57,6 +57,10 @@ for p in large_msgs ring_all_device ring_all_graph graph_large ordering stress s
     run late-jitter 3 $p $LATE ACX_FAULT_DELAY_US=200
 done
 run late-wildcards 3 wildcards ACX_WILDCARDS=1 $LATE
+# stream memOps on the on-stream p2p path: waits of host-predictable operations are cuStreamWaitValue64 on local completion words
+for p in ring ring_all ring_all_device ordering stress status_errors tags threads large_msgs sendrecv_enqueue late_push; do run memops-p2p 2 $p ACX_MEMOPS=1; done
+run memops-p2p 3 stress ACX_MEMOPS=1 ACX_FAULT_DELAY_US=200
+run memops-p2p-late 2 large_msgs ACX_MEMOPS=1 ACX_LATE_PUSH_MIN=65536
 run pbatch 2 ring_partitioned ACX_PBATCH=1
 run pbatch 3 ring_partitioned ACX_PBATCH=1
 run memops 2 ring_partitioned ACX_MEMOPS=1
