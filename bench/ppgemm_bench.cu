@@ -110,7 +110,7 @@ __global__ void poll_all(PQ p) { if ((int)threadIdx.x < p.n) { int f = 0; while 
 #ifdef ACX_BENCH_REFERENCE
 __global__ void ready_all(PQ p) { if ((int)threadIdx.x < p.n) MPIX_Pready(threadIdx.x, p.q); }
 #else
-__global__ void __launch_bounds__(512) ready_all(PQ p) { acx::pready_cta(blockIdx.x, p.q); }
+__global__ void __launch_bounds__(512) ready_all(PQ p) { acx::pready_grid((int)(blockIdx.x / 32), p.q, blockIdx.x % 32, 32); }   // 16-MiB panels: a grid per partition, not one CTA
 #endif
 
 static int run_api(int M, int D, int P, int steps, int warmup, bool check) {
@@ -154,7 +154,7 @@ static int run_api(int M, int D, int P, int steps, int warmup, bool check) {
 #ifdef ACX_BENCH_REFERENCE
             ready_all<<<1, 32, 0, st>>>(p);
 #else
-            ready_all<<<P, 512, 0, st>>>(p);
+            ready_all<<<P * 32, 512, 0, st>>>(p);
             CK(cudaGetLastError());
 #endif
         }

@@ -42,6 +42,7 @@ struct acx_pchan {
     int32_t peer;
     int32_t tag;
     int32_t pad;
+    uint64_t *work;          // SEND: work[partitions], local CTA counters of the grid-cooperative Pready (pready_grid); null on RECV
 };
 
 #if defined(__CUDACC__) || defined(ACX_EMU)
@@ -196,6 +197,35 @@ ACX_D int pready_warp(int p, const void *preq) {
 ACX_D int pready_cta(int p, const void *preq) {
     unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
     return pready_group(p, preq, tid, blockDim.x * blockDim.y * blockDim.z, [] { __syncthreads(); });
+}
+
+// Grid-cooperative Pready for LARGE partitions: `ncta` CTAs (this one is number `cta`, 0 <= cta < ncta) copy disjoint slices
+// of partition p at NVLink bandwidth — one CTA moves ~20 GB/s, a 16-MiB activation panel wants tens of them — and the last
+// one to finish publishes the flag (monotonic per-partition counter in local HBM: epoch-safe, nothing to reset).
+// Launch e.g. ready<<<partitions * 32, 512>>> with p = blockIdx.x / 32, cta = blockIdx.x % 32, ncta = 32.
+ACX_D int pready_grid(int p, const void *preq, unsigned cta, unsigned ncta) {
+    const acx_pchan *ch = pchan(preq);
+    const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z), nthr = blockDim.x * blockDim.y * blockDim.z;
+    const uint64_t e = ld_relaxed_sys(ch->epoch);
+    if (tid == 0) wait_geq_sys(ch->cts, e);
+    __syncthreads();
+    const uint64_t per = ((ch->part_bytes + ncta - 1) / ncta + 127) & ~127ull, lo = per * cta;
+    if (lo < ch->part_bytes) {
+        const uint64_t len = ch->part_bytes - lo < per ? ch->part_bytes - lo : per, off = (uint64_t)p * ch->part_bytes + lo;
+        copy_bytes(ch->land + off, ch->user_buf + off, len, tid, nthr);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        // work[p] counts CTA arrivals over all rounds; every round contributes exactly ncta of them (one grid shape per request)
+        const uint64_t seen = atom_add_acqrel_sys(ch->work + p, 1ull) + 1;
+        if (seen % ncta == 0) {
+            __threadfence_system();
+            st_release_sys(ch->arrived + p, e);
+            st_release_sys(ch->local_flags + p, e);
+        }
+    }
+    return 0;
 }
 
 // MPI-conformant single-thread Pready (what MPIX_Pready maps to on the device):

@@ -90,7 +90,7 @@ static long g_late_min = 4 << 20;          // ACX_LATE_PUSH_MIN: messages from t
 static long g_late_helpers = 0;            // ACX_LATE_HELPERS: helper CTAs all late sends of one wait kernel share (0 = one per SM)
 static long g_late_fallback_us = 50;       // ACX_LATE_FALLBACK_US: grace period before a receive's wait pulls an unclaimed RNDV_LATE message itself
 static int g_pbatch = 1;                  // ACX_PBATCH (default on since round 2): one kernel launch per MPIX_Startall / MPIX_Waitall group of partitioned requests instead of one per request
-static int g_branch = 0;                  // ACX_PEER_BRANCH: run EVERY operation with a peer on that peer's side stream (fork at enqueue, join at the wait)
+static int g_branch = 2;                  // ACX_PEER_BRANCH: run every operation with a peer on that peer's side stream (fork at enqueue, join at the wait): 0 never, 1 always, 2 (default) while the stream is capturing — there the forks are graph edges and cost nothing at run time
 static int g_fuse_rndv = 1, g_fuse_min_ctas = 8, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
 static int g_pdl = 1;   // programmatic dependent launch between consecutive acx kernels on a stream (ACX_PDL)
 static bool g_nvtx = false;
@@ -832,7 +832,7 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_LATE_HELPERS", nullptr, 0, &v); g_late_helpers = std::max(0L, v);
     acx_env_int("ACX_PBATCH", nullptr, 1, &v); g_pbatch = v != 0;   // one launch per MPIX_Startall / MPIX_Waitall group: measured 0.641 vs 0.776 ms per API-level halo step on 2x B200 (reference arm 0.700), profiles/raw/r2_call1/halo_api.txt
     acx_env_int("ACX_MEMOPS", nullptr, 0, &v); g_memops = v != 0 && !getenv("MPIACX_DISABLE_MEMOPS");   // partitioned Start / Wait as stream memOps (opt-in until measured)
-    acx_env_int("ACX_PEER_BRANCH", nullptr, 0, &v); g_branch = v != 0;   // opt-in until measured on hardware
+    acx_env_int("ACX_PEER_BRANCH", nullptr, 2, &v); g_branch = (int)std::max(0L, std::min(2L, v));   // 8x B200 all-pairs under CUDA graphs, 1 MiB per pair: 79.6 GB/s per GPU with branches vs 22.3 without (reference 45.8); 16 MiB: 288.6 vs 290.4 (profiles/raw/r2_call9)
     acx_env_int("ACX_SENDER_PUSH", nullptr, 0, &v); g_apush = v != 0;   // opt-in: a spinning gate can deadlock against device-synchronizing host calls
     acx_env_int("ACX_FUSE_MAX_CTAS", nullptr, 32, &v); g_fuse_max_ctas = (int)v;
     acx_env_int("ACX_FUSE_MIN_CTAS", nullptr, 8, &v); g_fuse_min_ctas = (int)v;
@@ -936,6 +936,7 @@ extern "C" int MPIX_Init(void) {
     g_acx->slot_req.assign(g_acx->geom.nops, nullptr);
     for (int s = g_acx->geom.nops - 1; s >= 0; s--) g_acx->free_slots.push_back(s);
     g_acx->recv_outstanding.assign(g_acx->size, std::vector<int>(g_acx->geom.nchan, 0));
+    g_acx->recv_deferred.assign(g_acx->size, std::vector<std::vector<AcxRequest *>>(g_acx->geom.nchan));
     g_acx->send_count.assign(g_acx->size, std::vector<AcxState::ChanCount>(g_acx->geom.nchan));
     g_acx->recv_count.assign(g_acx->size, std::vector<AcxState::ChanCount>(g_acx->geom.nchan));
     g_acx->device = true;
@@ -1287,7 +1288,7 @@ struct BranchScope {
     bool on = false;
     BranchScope(Emitter &e, AcxRequest *req) : em(e), r(req) {}
     int begin() {
-        if (!g_branch || g_apush || em.qtype != MPIX_QUEUE_CUDA_STREAM || g_side.empty()) return 0;
+        if (!(g_branch == 1 || (g_branch == 2 && em.capturing)) || g_apush || em.qtype != MPIX_QUEUE_CUDA_STREAM || g_side.empty()) return 0;
         r->ev_trig = event_get(); r->ev_done = event_get();
         if (!r->ev_trig || !r->ev_done) return 0;   // out of events: stay on the caller's stream (still correct)
         cudaStream_t side = g_side[(size_t)r->peer % g_side.size()];
@@ -1601,6 +1602,53 @@ static int any_grid(const AcxRequest *r) {
     return (int)std::max<size_t>(1, std::min<size_t>(g, 32));   // all CTAs must be co-resident: they wait for CTA 0's match
 }
 
+static bool recv_channel_backlogged(int src, int chan) {   // full ring or deferred receives ahead: a fused receive must not jump the queue
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    return g_acx->recv_outstanding[(size_t)src][(size_t)chan] >= g_acx->geom.depth || !g_acx->recv_deferred[(size_t)src][(size_t)chan].empty();
+}
+// The kernels of a posted receive: trigger (+ mover, or the single-launch rendezvous kernel). Called from MPIX_Irecv_enqueue,
+// or later — for a receive that found its channel's ring full — from the wait that makes room.
+struct DeferredRecv { RecvParams rp; MoverParams mp; int fgrid; bool rndv_capable; size_t bytes; };
+static int launch_recv(Emitter &em, AcxRequest *r, RecvParams &rp, MoverParams &mp, int fgrid, bool rndv_capable, size_t bytes) {
+    int rc;
+    r->hticket = host_ticket(false, r->peer, r->chan, em.stream, r->in_graph);
+    if (fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas) {
+        if ((rc = em.launch2(recv_rndv_fused, dim3(fgrid), dim3(kMoverThreads), rp, mp))) return rc;
+    } else {
+        if ((rc = em.launch(recv_trigger, dim3(1), dim3(32), rp))) return rc;
+        if (rndv_capable && (rc = launch_mover_maybe_side(em, r, mp, bytes))) return rc;
+    }
+    if (rndv_capable) mark_operation_end(em, r);
+    return 0;
+}
+// Launch the deferred receives of `upto`'s channel, oldest first, as far as the ring has room — at least up to and including
+// `upto` (null: as many as fit). Called with the emitter of a wait that is about to complete receives of that channel.
+static int launch_deferred_recvs(Emitter &em, int src, int chan, AcxRequest *upto) {
+    for (;;) {
+        AcxRequest *d = nullptr;
+        {
+            std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+            auto &q = g_acx->recv_deferred[(size_t)src][(size_t)chan];
+            if (q.empty()) return 0;
+            if (g_acx->recv_outstanding[(size_t)src][(size_t)chan] >= g_acx->geom.depth) {
+                bool needed = false;
+                if (upto) for (AcxRequest *x : q) if (x == upto) needed = true;
+                if (!needed) return 0;
+                return -2;   // the ring is full and `upto` is still queued: the caller completes what it has (making room) or reports the error
+            }
+            d = q.front();
+            q.erase(q.begin());
+            g_acx->recv_outstanding[(size_t)src][(size_t)chan]++;
+        }
+        DeferredRecv *dr = (DeferredRecv *)d->deferred;
+        d->deferred = nullptr;
+        d->stream = em.stream;
+        const int rc = launch_recv(em, d, dr->rp, dr->mp, dr->fgrid, dr->rndv_capable, dr->bytes);
+        delete dr;
+        if (rc) return rc;
+    }
+}
+
 // =======================================================================================
 // MPIX_Isend_enqueue / MPIX_Irecv_enqueue
 // =======================================================================================
@@ -1734,6 +1782,7 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
     AcxRange _r("MPIX_Irecv_enqueue");
     size_t bytes; int ctx, wsource;
     bool counted = false;   // this receive has been added to recv_outstanding (undone on the error exits)
+    bool defer = false;     // the channel's ring is full: keep the receive, launch its trigger from a later wait
     AcxLayout ty;
     int rc = check_common("MPIX_Irecv_enqueue", true, count, datatype, source, tag, comm, request, queue, &bytes, &ctx, &wsource, &ty);
     if (rc) return rc;
@@ -1774,15 +1823,13 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
     }
     r->chan = chan_lookup(wsource, g_acx->rank, tag, ctx);
     if (!r->in_graph) {
+        // A channel's ring holds ACX_DEPTH receives between trigger and wait. The reference allows MPIACX_NFLAGS operations in
+        // flight (include/mpi-acx-internal.h:141, src/triggered.cpp:35-62); here a receive beyond the ring's depth — or behind an
+        // earlier deferred one: tickets are drawn in posting order — keeps its slot and buffers but its trigger is launched
+        // later, from the wait that makes room (launch_deferred_recvs). Round 1 rejected it.
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
-        if (g_acx->recv_outstanding[source][r->chan] >= g_acx->geom.depth) {
-            ACX_ERR("more than ACX_DEPTH=%d receives outstanding (posted, not yet waited) from rank %d on the channel of tag %d; wait on earlier ones or raise ACX_DEPTH",
-                    g_acx->geom.depth, source, tag);
-            delete r;
-            return MPI_ERR_OTHER;
-        }
-        g_acx->recv_outstanding[source][r->chan]++;
-        counted = true;
+        defer = g_acx->recv_outstanding[source][r->chan] >= g_acx->geom.depth || !g_acx->recv_deferred[source][r->chan].empty();
+        if (!defer) { g_acx->recv_outstanding[source][r->chan]++; counted = true; }
     }
     if ((r->slot = acx_slot_alloc(r, r->in_graph)) < 0) {
         if (counted) { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); g_acx->recv_outstanding[source][r->chan]--; }
@@ -1834,14 +1881,12 @@ extern "C" int MPIX_Irecv_enqueue(void *buf, int count, MPI_Datatype datatype, i
         mp.depth = G.depth; mp.push = 0; mp.peer = source; mp.tr = rp.tr; mp.vec256 = g_mover_256; mp.block_bytes = (uint32_t)g_mover_block;
         const int fgrid = (rndv_capable && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
         r->coop = g_coop && rndv_capable && !g_apush && !g_mover_tma && (long)bytes >= g_coop_min;   // "may be": the wait's gate + agent kernels help only if the message says RNDV_COOP
-        r->hticket = host_ticket(false, source, r->chan, r->stream, r->in_graph);
-        if (fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas) {
-            if ((rc = em.launch2(recv_rndv_fused, dim3(fgrid), dim3(kMoverThreads), rp, mp))) goto fail;
-        } else {
-            if ((rc = em.launch(recv_trigger, dim3(1), dim3(32), rp))) goto fail;
-            if (rndv_capable && (rc = launch_mover_maybe_side(em, r, mp, bytes))) goto fail;
-        }
-        if (rndv_capable) mark_operation_end(em, r);
+        if (defer) {
+            DeferredRecv *d = new DeferredRecv{rp, mp, fgrid, rndv_capable, bytes};
+            r->deferred = d;
+            std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+            g_acx->recv_deferred[source][r->chan].push_back(r);
+        } else if ((rc = launch_recv(em, r, rp, mp, fgrid, rndv_capable, bytes))) goto fail;
     }
     if ((rc = branch.end())) goto fail;
 done:
@@ -2096,10 +2141,27 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
         em.parallel = par;
         if (rc) return rc;
     }
-    for (size_t base = 0; base < need.size(); base += kWaitBatch) {
+    for (size_t base = 0, step = 0; base < need.size(); base += step) {
         WaitBatch wb;
         memset(&wb, 0, sizeof wb);
         int n = (int)std::min((size_t)kWaitBatch, need.size() - base);
+        // receives that were posted while their channel's ring was full: their triggers go out now, in posting order (the waits
+        // of earlier batches have made room)
+        for (int j = 0; j < n; j++) {
+            AcxRequest *r = need[base + j].r;
+            if (r->kind == ACX_REQ_RECV && r->deferred) {
+                const bool par = em.parallel;
+                em.parallel = false;
+                rc = launch_deferred_recvs(em, r->peer, r->chan, r);
+                em.parallel = par;
+                if (rc == -2 && j > 0) { n = j; break; }   // no room yet: complete the requests in front of it first (this batch ends here)
+                if (rc == -2) {
+                    ACX_ERR("receive from rank %d (tag %d) was posted behind %d others that are still un-waited on its channel: wait on earlier receives first (or raise ACX_DEPTH)", r->peer, r->tag, g_acx->geom.depth);
+                    return MPI_ERR_OTHER;
+                }
+                if (rc) return rc;
+            }
+        }
         std::vector<AcxRequest *> bounced, typed;
         for (int j = 0; j < n; j++) {
             AcxRequest *r = need[base + j].r;
@@ -2132,6 +2194,17 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             if (!mb.ops.empty() && (rc = mb.flush(em.stream))) return rc;
         }
         if ((rc = em.launch(wait_kernel, dim3(plan_wait_grid(wb, n)), dim3(kWaitThreads), wb))) return rc;
+        if (retire) {   // these receives no longer occupy ring slots once this kernel has run: later triggers on the stream may reuse them
+            std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+            for (int j = 0; j < n; j++) {
+                AcxRequest *r = need[base + j].r;
+                if (r->kind == ACX_REQ_RECV && !r->wild && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
+            }
+        }
+        if (retire) for (int j = 0; j < n; j++) {   // post deferred receives of the channels just served as early as there is room
+            AcxRequest *r = need[base + j].r;
+            if (r->kind == ACX_REQ_RECV && !r->wild && (rc = launch_deferred_recvs(em, r->peer, r->chan, nullptr))) return rc;
+        }
         for (AcxRequest *r : typed) {
             UnpackParams up;
             fill_unpack(r, retire, &up);
@@ -2152,6 +2225,7 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             em.parallel = par;
             if (rc) return rc;
         }
+        step = (size_t)n;
     }
     if (qtype == MPIX_QUEUE_CUDA_GRAPH && !em.last) {
         cudaGraphNode_t node;
@@ -2161,7 +2235,6 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
         for (AcxRequest *r : rs) {
             if (retire) { g_acx->slot_busy[r->slot] = 3; g_pending_retire.push_back(r->slot); }  // reclaimed once the device marks it retired
-            if (retire && r->kind == ACX_REQ_RECV && !r->wild && g_acx->recv_outstanding[r->peer][r->chan] > 0) g_acx->recv_outstanding[r->peer][r->chan]--;
         }
     }
     for (int i = 0; i < count; i++) reqs[i] = MPIX_REQUEST_NULL;  // handle is consumed at enqueue time (reference: src/sendrecv.cu:430-432)
@@ -2212,14 +2285,14 @@ extern "C" int MPIX_Send_enqueue(const void *buf, int count, MPI_Datatype dataty
 extern "C" int MPIX_Recv_enqueue(void *buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPI_Status *status, int qtype, void *queue) {
     AcxRange _r("MPIX_Recv_enqueue");
     // Fast path: device transport, stream queue (capturing or not), contiguous eager-size receive from a specific peer.
-    bool fast = g_acx && g_acx->initialized && g_acx->device && qtype == MPIX_QUEUE_CUDA_STREAM && queue && source >= 0 && tag >= 0 && !g_branch;
+    bool fast = g_acx && g_acx->initialized && g_acx->device && qtype == MPIX_QUEUE_CUDA_STREAM && queue && source >= 0 && tag >= 0 && g_branch != 1;
     size_t bytes = 0; int ctx = 0, wsource = 0;
     AcxLayout ty;
     if (fast) {
         MPIX_Request dummy = MPIX_REQUEST_NULL;
         int rc = check_common("MPIX_Recv_enqueue", true, count, datatype, source, tag, comm, &dummy, queue, &bytes, &ctx, &wsource, &ty);
         if (rc) return rc;
-        fast = !ty.noncontig && bytes <= g_acx->geom.eager_max;
+        fast = !ty.noncontig && bytes <= g_acx->geom.eager_max && !recv_channel_backlogged(wsource, chan_lookup(wsource, g_acx->rank, tag, ctx));
     }
     if (!fast) {
         MPIX_Request r = MPIX_REQUEST_NULL;
@@ -2314,7 +2387,7 @@ extern "C" int MPIX_Sendrecv_enqueue(const void *sendbuf, int sendcount, MPI_Dat
                                      int source, int recvtag, MPI_Comm comm, MPI_Status *status, int qtype, void *queue) {
     AcxRange _r("MPIX_Sendrecv_enqueue");
     bool fast = g_acx && g_acx->initialized && g_acx->device && qtype == MPIX_QUEUE_CUDA_STREAM && queue && dest >= 0 && source >= 0 && sendtag >= 0 && recvtag >= 0 &&
-                !g_branch && !g_fault_drop_send;
+                g_branch != 1 && !g_fault_drop_send;
     size_t sbytes = 0, rbytes = 0; int sctx = 0, rctx = 0, wdest = 0, wsource = 0;
     AcxLayout sty, rty;
     if (fast) {
@@ -2322,7 +2395,8 @@ extern "C" int MPIX_Sendrecv_enqueue(const void *sendbuf, int sendcount, MPI_Dat
         int rc = check_common("MPIX_Sendrecv_enqueue", false, sendcount, sendtype, dest, sendtag, comm, &dummy, queue, &sbytes, &sctx, &wdest, &sty);
         if (!rc) rc = check_common("MPIX_Sendrecv_enqueue", true, recvcount, recvtype, source, recvtag, comm, &dummy, queue, &rbytes, &rctx, &wsource, &rty);
         if (rc) return rc;
-        fast = !sty.noncontig && !rty.noncontig && sbytes <= g_acx->geom.eager_max && rbytes <= g_acx->geom.eager_max;
+        fast = !sty.noncontig && !rty.noncontig && sbytes <= g_acx->geom.eager_max && rbytes <= g_acx->geom.eager_max &&
+               !recv_channel_backlogged(wsource, chan_lookup(wsource, g_acx->rank, recvtag, rctx));
     }
     if (!fast) {
         MPIX_Request rq[2] = {MPIX_REQUEST_NULL, MPIX_REQUEST_NULL};
@@ -2474,6 +2548,14 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
             ACX_CUDA_WD(cudaLaunchKernel((const void *)recv_any_kernel, dim3(any_grid(r)), dim3(kMoverThreads), aargs, 0, host_stream()));
             g_acx->st.kernels++;
         }
+        if (r->kind == ACX_REQ_RECV && r->deferred) {   // posted while its channel's ring was full: its trigger goes out now (internal stream)
+            Emitter hem;
+            cudaStream_t hs = host_stream();
+            int drc = hem.begin(MPIX_QUEUE_CUDA_STREAM, &hs);
+            if (!drc) drc = launch_deferred_recvs(hem, r->peer, r->chan, r);
+            if (drc == -2) { ACX_ERR("receive from rank %d (tag %d) was posted behind %d others that are still un-waited on its channel: wait on earlier receives first (or raise ACX_DEPTH)", r->peer, r->tag, g_acx->geom.depth); drc = MPI_ERR_OTHER; }
+            if (drc) return drc;
+        }
         WaitBatch wb;
         memset(&wb, 0, sizeof wb);
         int rc = fill_wait(r, MPI_STATUS_IGNORE, false, true, &wb.w[0]);
@@ -2609,9 +2691,9 @@ static int pinit_common(AcxReqKind kind, const void *buf, int partitions, MPI_Co
     memset(hs, 0, sizeof *hs);
     hs->mine.partitions = partitions; hs->mine.part_bytes = part_bytes; hs->mine.land_off = -1;
     if (kind == ACX_REQ_PSEND) {
-        uint32_t base = acx_pflags_alloc(partitions + 2);
+        uint32_t base = acx_pflags_alloc(2 * partitions + 2);   // sent[p], cts, epoch, work[p] (CTA counters of the grid-cooperative Pready)
         if (base == UINT32_MAX) { delete r; delete hs; return MPI_ERR_OTHER; }
-        r->pf_local = base; r->pf_cts = base + partitions; r->pf_epoch = base + partitions + 1;
+        r->pf_local = base; r->pf_cts = base + partitions; r->pf_epoch = base + partitions + 1; r->pf_work = base + partitions + 2;
         hs->mine.pf_cts = r->pf_cts;
     } else {
         uint32_t base = acx_pflags_alloc(2 * partitions + 1);
@@ -2672,6 +2754,7 @@ static int presolve(AcxRequest *r) {
         c.arrived = peerpf + hs->theirs.pf_arrived;
         c.local_flags = mypf + r->pf_local;
         c.cts = mypf + r->pf_cts;
+        c.work = mypf + r->pf_work;
     } else {
         c.kind = ACX_PKIND_RECV;
         c.land = r->land_is_user ? r->dev_buf : g_acx->heap + r->land_off;

@@ -227,6 +227,7 @@ struct AcxRequest {
     bool in_graph;
     bool host_transport;      // no-GPU mode: backed by an MPI_Request
     bool null_op;             // peer was MPI_PROC_NULL: completes immediately, moves nothing, owns no slot
+    void *deferred;           // RECV posted while its channel's ring was full (> ACX_DEPTH receives outstanding): the trigger is launched later, in posting order, from a wait (DeferredRecv in acx.cu)
     uint64_t hticket;         // ticket this operation's trigger will draw, predicted on the host (~0 = unknown: graphs, several streams or wildcards on its channel); lets a stream wait be a memOp
     bool late;                // large message (>= ACX_LATE_PUSH_MIN): sender-moves protocol, the wait kernel carries helper CTAs
     char *src_local;          // SEND: device address the message is read from (user buffer, bounce or packed image)
@@ -251,6 +252,7 @@ struct AcxRequest {
     uint32_t pf_local;        // SEND: sent[] ; RECV: copied[]
     uint32_t pf_cts;          // SEND: cts word index (mine); RECV: the sender's cts index
     uint32_t pf_epoch;        // my epoch word
+    uint32_t pf_work;         // SEND: work[partitions], CTA counters of acx::pready_grid
     acx_pchan *pchan_d;       // device descriptor (lives in my pflags-adjacent area via cudaMalloc)
     acx_pchan pchan_h;
 };
@@ -297,6 +299,7 @@ struct AcxState {
     // Host-side ticket prediction per (peer, channel, direction): exact while every operation on the channel is enqueued in
     // stream mode on ONE stream (tickets are drawn by the trigger kernels in execution order); a graph, a second stream or a
     // wildcard receive makes the channel device-counted for good.
+    std::vector<std::vector<std::vector<AcxRequest *>>> recv_deferred;   // [src][chan]: receives whose trigger has not been launched yet, in posting order
     struct ChanCount { uint64_t next = 0; cudaStream_t stream = nullptr; bool dev = false; };
     std::vector<std::vector<ChanCount>> send_count, recv_count;   // [peer][chan]
     // config

@@ -22,6 +22,7 @@
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 
 namespace acxg {
 namespace {   // internal linkage: every module that includes this header owns a private copy of the kernel and its
@@ -325,10 +326,37 @@ inline int make_tmap_kmajor(CUtensorMap *tm, const void *base, uint64_t rows, ui
     return r == CUDA_SUCCESS ? 0 : 2;
 }
 
+// Tensor maps are pure functions of (base, rows, K, box rows): encode once per operand and keep them — a pipeline stage
+// launches the same two or three operands for every microbatch (round 1 re-encoded both maps on every launch).
+inline bool cached_tmap_copy(CUtensorMap *out, const void *base, uint64_t rows, uint64_t K, uint32_t box_rows);
+inline const CUtensorMap *cached_tmap(const void *base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+    struct Key { const void *base; uint64_t rows, K; uint32_t box; };
+    struct Slot { Key k; CUtensorMap tm; };
+    static Slot cache[16];
+    static int used = 0, next = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    for (int i = 0; i < used; i++)
+        if (cache[i].k.base == base && cache[i].k.rows == rows && cache[i].k.K == K && cache[i].k.box == box_rows) return &cache[i].tm;
+    Slot &s = cache[used < 16 ? used++ : (next++ % 16)];
+    if (make_tmap_kmajor(&s.tm, base, rows, K, box_rows)) { s.k.base = nullptr; return nullptr; }
+    s.k = Key{base, rows, K, box_rows};
+    return &s.tm;
+}
+
+inline bool cached_tmap_copy(CUtensorMap *out, const void *base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+    static std::mutex mu2;
+    std::lock_guard<std::mutex> lk(mu2);   // the copy happens under this lock: a concurrent launch may evict the slot
+    const CUtensorMap *t = cached_tmap(base, rows, K, box_rows);
+    if (!t) return false;
+    *out = *t;
+    return true;
+}
+
 inline int launch_gemm_fp8(const uint8_t *X, const uint8_t *W, uint8_t *out, int M, int N, int K, float scale, const Gating &g, int num_sms, cudaStream_t stream) {
     if (M % BM || N % BN || K % BK) return 3;
     Params P;
-    if (make_tmap_kmajor(&P.tmA, X, M, K, BM) || make_tmap_kmajor(&P.tmB, W, N, K, BN)) return 4;
+    if (!cached_tmap_copy(&P.tmA, X, (uint64_t)M, (uint64_t)K, BM) || !cached_tmap_copy(&P.tmB, W, (uint64_t)N, (uint64_t)K, BN)) return 4;
     P.out = out; P.M = M; P.N = N; P.K = K; P.scale = scale; P.g = g;
     static bool attr_set = false;
     if (!attr_set) {

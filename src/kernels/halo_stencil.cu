@@ -39,7 +39,6 @@ namespace {
 constexpr int TY = 8, TZ = 32;      // tile: TY rows x all of x, z-march of TZ planes
 constexpr int STAGES = 8;           // shared-memory ring of planes (8 x 10.6 KB per CTA, two CTAs per SM)
 constexpr int XPAD = 16;            // pad cells behind every row (see the layout comment above)
-constexpr int LAG = 2;              // a stage is refilled LAG planes after its last reader: the producer thread never waits for a sibling warp
 
 struct HaloDev {
     __nv_bfloat16 *un;              // interior origin (x = y = z = 0) of the local OUTPUT field
@@ -108,11 +107,13 @@ __device__ __forceinline__ uint4 stencil8(const float2 cur[4], const float2 ym[4
 // Thread (rp, vx) owns rows 2*rp and 2*rp+1 of the tile's TY rows and the 8 cells vx*8 .. vx*8+7: two vectors per plane,
 // each the other's y-neighbour (registers), so a plane costs 4 LDS.128 per thread: the two next-plane centres, the row
 // above the pair and the row below it.
-__global__ void __launch_bounds__(256, 2) halo_stencil_tma(const __grid_constant__ CUtensorMap tm, HaloDev P) {
+__global__ void __maxnreg__(112) halo_stencil_tma(const __grid_constant__ CUtensorMap tm, HaloDev P) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ncw = (int)(blockDim.x >> 5) - 1;                  // compute warps; the last warp is the producer
+    const bool producer = (tid >> 5) == ncw;
     const int vpr = P.nx >> 3;                                   // 16-B vectors per row
-    const int rp2 = tid / vpr, vx = tid - rp2 * vpr;             // row pair, vector
+    const int rp2 = tid / vpr, vx = tid - rp2 * vpr;             // row pair, vector (compute threads)
     const uint32_t row_bytes = (uint32_t)(P.nx + XPAD) * 2u;     // one padded row
     const uint32_t stage_bytes = row_bytes * (TY + 2);           // what one box delivers
     const uint32_t stage_stride = (stage_bytes + 127u) & ~127u;  // TMA destinations are 128-B aligned
@@ -120,50 +121,70 @@ __global__ void __launch_bounds__(256, 2) halo_stencil_tma(const __grid_constant
     uint64_t *empty = full + STAGES;
     uint64_t *tile_done = empty + STAGES;                        // one per parity of the tile counter
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)nwarps); }
-        mbar_init(&tile_done[0], (uint32_t)nwarps); mbar_init(&tile_done[1], (uint32_t)nwarps);
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)ncw); }
+        mbar_init(&tile_done[0], (uint32_t)ncw); mbar_init(&tile_done[1], (uint32_t)ncw);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // ---- producer state (thread 0 only): a stream of planes that runs through tile boundaries ----
-    int p_it = blockIdx.x;      // tile iterator of the producer
-    int p_q = 0;                // next plane of that tile to load (0 .. TZ+1)
-    uint32_t p_cnt = 0;         // planes loaded so far
-    uint32_t p_stage = 0, p_par = 1;   // ring position of plane p_cnt; parity to wait for on its empty barrier (1 on the first pass: passes at once)
-    auto produce = [&](uint32_t consumed) {   // `consumed` = planes every reader has certainly released (see LAG)
-        while (p_it < P.ntiles && p_cnt < consumed + (uint32_t)STAGES) {
-            const int t = P.order[p_it];
+    if (producer) {
+        // ---- producer warp (one lane): an uninterrupted stream of plane loads, straight through tile boundaries, as far ahead
+        // of the math as the ring allows; between loads it publishes the face flags of tiles the compute warps have finished ----
+        if (lane != 0) return;
+        uint32_t p_stage = 0, p_par = 1;       // ring position of the next load; parity to wait for on its empty barrier (1 on the first pass: passes at once)
+        uint32_t sig_no = 0;                   // tiles whose flags have been published
+        int sig_it = blockIdx.x;
+        auto try_signal = [&](bool block) {
+            // tile number sig_no is complete when every compute warp has arrived on its tile barrier
+            const uint32_t par = (sig_no >> 1) & 1u;
+            uint32_t ok;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&tile_done[sig_no & 1])), "r"(par) : "memory");
+            if (!ok) { if (!block) return false; mbar_wait(&tile_done[sig_no & 1], par); }
+            const int t = P.order[sig_it];
             const int ty = t % P.nty, tc = t / P.nty;
-            if (p_q == 0) {
-                // the ghost cells this tile's boxes cover were written by the neighbours' previous step: poll their flags (relaxed),
-                // then ONE acquire fence for all of them and the generic-to-async proxy fence in front of the TMA loads
-                auto poll = [&](const acx_pchan *ch, int part) { const uint64_t *f = ch->arrived + part; unsigned ns = 0; while (acx::ld_relaxed_sys(f) < P.wait_val) { __nanosleep(ns); ns = ns < 256 ? ns * 2 + 20 : 256; } };
-                poll(P.recv[0], t); poll(P.recv[1], t);
-                if (ty == 0) poll(P.recv[2], tc);
-                if (ty == P.nty - 1) poll(P.recv[3], tc);
-                if (tc == 0) poll(P.recv[4], ty);
-                if (tc == P.ntz - 1) poll(P.recv[5], ty);
-                asm volatile("fence.acq_rel.sys;" ::: "memory");
-                asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes (remote stores, made visible by the acquire) before async-proxy reads
+            __threadfence_system();            // ONE system-scope fence, then relaxed flag stores (fence + strong store = release)
+            acx::st_relaxed_sys(P.send[0]->arrived + t, P.signal_val);
+            acx::st_relaxed_sys(P.send[1]->arrived + t, P.signal_val);
+            if (ty == 0) acx::st_relaxed_sys(P.send[2]->arrived + tc, P.signal_val);
+            if (ty == P.nty - 1) acx::st_relaxed_sys(P.send[3]->arrived + tc, P.signal_val);
+            if (tc == 0) acx::st_relaxed_sys(P.send[4]->arrived + ty, P.signal_val);
+            if (tc == P.ntz - 1) acx::st_relaxed_sys(P.send[5]->arrived + ty, P.signal_val);
+            sig_no++; sig_it += gridDim.x;
+            return true;
+        };
+        uint32_t loaded_tiles = 0;
+        for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x, loaded_tiles++) {
+            const int t = P.order[it];
+            const int ty = t % P.nty, tc = t / P.nty;
+            // the ghost cells this tile's boxes cover were written by the neighbours' previous step: poll their flags (relaxed),
+            // then ONE acquire fence for all of them and the generic-to-async proxy fence in front of the TMA loads
+            auto poll = [&](const acx_pchan *ch, int part) { const uint64_t *f = ch->arrived + part; unsigned ns = 0; while (acx::ld_relaxed_sys(f) < P.wait_val) { __nanosleep(ns); ns = ns < 256 ? ns * 2 + 20 : 256; } };
+            poll(P.recv[0], t); poll(P.recv[1], t);
+            if (ty == 0) poll(P.recv[2], tc);
+            if (ty == P.nty - 1) poll(P.recv[3], tc);
+            if (tc == 0) poll(P.recv[4], ty);
+            if (tc == P.ntz - 1) poll(P.recv[5], ty);
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes (remote stores, made visible by the acquire) before async-proxy reads
+            for (int q = 0; q < TZ + 2; q++) {
+                mbar_wait(&empty[p_stage], p_par);                 // every compute warp is done with the stage's previous plane
+                mbar_expect_tx(&full[p_stage], stage_bytes);
+                // box origin in the padded tensor: u64 column 0 (= 16 B before the interior row), padded row ty*TY, padded plane tc*TZ + q
+                tma_load_3d(&tm, &full[p_stage], smem + (size_t)p_stage * stage_stride, 0, ty * TY, tc * TZ + q);
+                if (++p_stage == STAGES) { p_stage = 0; p_par ^= 1u; }
+                if ((q & 7) == 7 && sig_no < loaded_tiles) try_signal(false);
             }
-            mbar_wait(&empty[p_stage], p_par);                     // every warp is done with the stage's previous plane
-            mbar_expect_tx(&full[p_stage], stage_bytes);
-            // box origin in the padded tensor: u64 column 0 (= 16 B before the interior row), padded row ty*TY, padded plane tc*TZ + q
-            tma_load_3d(&tm, &full[p_stage], smem + (size_t)p_stage * stage_stride, 0, ty * TY, tc * TZ + p_q);
-            p_cnt++;
-            if (++p_stage == STAGES) { p_stage = 0; p_par ^= 1u; }
-            if (++p_q == TZ + 2) { p_q = 0; p_it += gridDim.x; }
         }
-    };
+        while (sig_no < loaded_tiles) try_signal(true);
+        return;
+    }
 
-    // ---- consumer state: ring position / phase of the plane being consumed ----
-    uint32_t c_cnt = 0, c_stage = 0, c_par = 0;
+    // ---- compute warps ----
+    uint32_t c_stage = 0, c_par = 0;           // ring position / phase of the plane being consumed
     auto advance = [&](uint32_t &st, uint32_t &par) { if (++st == STAGES) { st = 0; par ^= 1u; } };
     auto release = [&](uint32_t st) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[st]); };
     uint32_t tile_no = 0;
     const float2 c0v = make_float2(P.c0, P.c0), c1v = make_float2(P.c1, P.c1);
-    if (tid == 0) produce(0);
     for (int it = blockIdx.x; it < P.ntiles; it += gridDim.x, tile_no++) {
         const int t = P.order[it];
         const int ty = t % P.nty, tc = t / P.nty;
@@ -179,7 +200,7 @@ __global__ void __launch_bounds__(256, 2) halo_stencil_tma(const __grid_constant
             unpack8(*reinterpret_cast<const uint4 *>(s + offB), prevB);
         }
         release(c_stage);
-        advance(c_stage, c_par); c_cnt++;
+        advance(c_stage, c_par);
         mbar_wait(&full[c_stage], c_par);                         // plane z0
         {
             const unsigned char *s = smem + (size_t)c_stage * stage_stride;
@@ -230,27 +251,15 @@ __global__ void __launch_bounds__(256, 2) halo_stencil_tma(const __grid_constant
             for (int i = 0; i < 4; i++) { prevA[i] = curA[i]; curA[i] = nxtA[i]; prevB[i] = curB[i]; curB[i] = nxtB[i]; }
             off += P.pp;
             release(c_stage);                                      // rows above / below of the current plane have been read
-            c_stage = n_stage; c_par = n_par; c_cnt++;
+            c_stage = n_stage; c_par = n_par;
             advance(n_stage, n_par);
-            if (tid == 0) produce(c_cnt > (uint32_t)LAG ? c_cnt - LAG : 0);   // planes below c_cnt-LAG were released by every warp at least LAG iterations ago (or the wait inside is short)
         }
         release(c_stage);                                          // plane z0+TZ: centres only
-        advance(c_stage, c_par); c_cnt++;
-        // ---- publish the tile's faces: every warp's stores -> tile barrier (release / acquire at CTA scope) -> ONE system-scope
-        // fence -> relaxed flag stores (fence + strong store = release). The last warp's lane 0 does it, not the producer thread:
-        // the plane stream keeps flowing while the flags go out.
+        advance(c_stage, c_par);
+        // the tile's stores are done: tell the producer warp, which publishes the face flags (release / acquire at CTA scope
+        // through the barrier, one system-scope fence on its side)
         __syncwarp();
         if (lane == 0) mbar_arrive(&tile_done[tile_no & 1]);
-        if (tid == (int)blockDim.x - 32) {
-            mbar_wait(&tile_done[tile_no & 1], (tile_no >> 1) & 1u);
-            __threadfence_system();
-            acx::st_relaxed_sys(P.send[0]->arrived + t, P.signal_val);
-            acx::st_relaxed_sys(P.send[1]->arrived + t, P.signal_val);
-            if (ty == 0) acx::st_relaxed_sys(P.send[2]->arrived + tc, P.signal_val);
-            if (ty == P.nty - 1) acx::st_relaxed_sys(P.send[3]->arrived + tc, P.signal_val);
-            if (tc == 0) acx::st_relaxed_sys(P.send[4]->arrived + ty, P.signal_val);
-            if (tc == P.ntz - 1) acx::st_relaxed_sys(P.send[5]->arrived + ty, P.signal_val);
-        }
     }
 }
 
@@ -418,7 +427,7 @@ extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, f
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nfaces(a) > nfaces(b); });
     HCK(cudaMalloc((void **)&h->order_d, sizeof(int) * h->ntiles));
     HCK(cudaMemcpy(h->order_d, order.data(), sizeof(int) * h->ntiles, cudaMemcpyHostToDevice));
-    h->threads = nx / 8 * (TY / 2);   // two rows per thread
+    h->threads = nx / 8 * (TY / 2) + 32;   // two rows per thread, plus the producer warp
     h->smem = (size_t)STAGES * ((((size_t)(TY + 2) * (size_t)h->rp * 2) + 127) & ~(size_t)127) + (2 * STAGES + 2) * 8 + 16;
     HCK(cudaFuncSetAttribute(halo_stencil_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int dev = 0, sms = 148, occ = 1;

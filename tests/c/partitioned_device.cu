@@ -26,6 +26,7 @@ __global__ void consume_blocking(MPIX_Prequest recv, int left, int round, int *b
 
 // ---- 2. cooperative copies from a send buffer ---------------------------------------------------------------------------
 __global__ void ready_by_cta(MPIX_Prequest send) { acx::pready_cta(blockIdx.x, send); }                      // one CTA per partition
+__global__ void ready_by_grid(MPIX_Prequest send) { acx::pready_grid((int)(blockIdx.x / 3), send, blockIdx.x % 3, 3); }   // three CTAs per partition, the last one to finish signals
 __global__ void ready_by_warp(MPIX_Prequest send) { acx::pready_warp((int)(threadIdx.x >> 5), send); }       // one warp per partition
 __global__ void poll_all(MPIX_Prequest recv) {                                                              // thread p polls partition p
     int f = 0;
@@ -79,13 +80,14 @@ static void cooperative_rounds(int use_warp, int heap) {
         T_CUDA(cudaMemcpy(send, h_send, sizeof h_send, cudaMemcpyHostToDevice));
         T_CUDA(cudaMemset(recv, 0xff, sizeof h_recv));
         T_OK(MPIX_Startall(2, rq));
-        if (use_warp) T_LAUNCH(ready_by_warp, 1, 32 * PARTS, pq[0]); else T_LAUNCH(ready_by_cta, PARTS, 64, pq[0]);
+        if (use_warp == 2) T_LAUNCH(ready_by_grid, PARTS * 3, 64, pq[0]);   /* three CTAs share each partition */
+        else if (use_warp) T_LAUNCH(ready_by_warp, 1, 32 * PARTS, pq[0]); else T_LAUNCH(ready_by_cta, PARTS, 64, pq[0]);
         T_LAUNCH(poll_all, 1, PARTS, pq[1]);
         T_CUDA(cudaStreamSynchronize(0));
         T_OK(MPIX_Waitall(2, rq, MPI_STATUSES_IGNORE));
         T_CUDA(cudaMemcpy(h_recv, recv, sizeof h_recv, cudaMemcpyDeviceToHost));
         int bad = count_bad(h_recv, round + 10 * use_warp);
-        T_CHECK(bad == 0, "cooperative pready (%s, %s buffers) round %d: %d wrong values", use_warp ? "warp" : "cta", heap ? "heap" : "private", round, bad);
+        T_CHECK(bad == 0, "cooperative pready (%s, %s buffers) round %d: %d wrong values", use_warp == 2 ? "grid" : use_warp ? "warp" : "cta", heap ? "heap" : "private", round, bad);
     }
     T_OK(MPIX_Request_free(&rq[0])); T_OK(MPIX_Request_free(&rq[1]));
     if (heap) { T_OK(MPIX_Free_mem(send)); T_OK(MPIX_Free_mem(recv)); } else { T_CUDA(cudaFree(send)); T_CUDA(cudaFree(recv)); }
@@ -212,6 +214,8 @@ int main(int argc, char **argv) {
     cooperative_rounds(1, 1);
     cooperative_rounds(0, 0);
     cooperative_rounds(1, 0);
+    cooperative_rounds(2, 1);
+    cooperative_rounds(2, 0);
     stream_ordered_rounds();
     explicit_epoch_rounds();
     return t_finish("partitioned_device");

@@ -225,13 +225,13 @@ inline void register_kernel_fn(void (*k)(A...), const char *name, bool scalable)
 struct KernelRegistrar { template <typename... A> KernelRegistrar(void (*k)(A...), const char *name, bool scalable) { register_kernel_fn(k, name, scalable); } };
 // kern<<<grid, block, 0, stream>>>(args...) for user kernels of test programs
 template <typename... A, typename... B>
-inline cudaError_t launch_user(void (*k)(A...), unsigned grid, unsigned block, cudaStream_t stream, B... args) {
+inline cudaError_t launch_user(void (*k)(A...), dim3 grid, dim3 block, cudaStream_t stream, B... args) {   // dim3 converts from unsigned
     register_kernel_fn(k, "user kernel", false);   // idempotent
     std::tuple<std::remove_reference_t<A>...> vals(args...);
     void *ptrs[sizeof...(A) ? sizeof...(A) : 1];
     size_t i = 0;
     std::apply([&](auto &...v) { ((ptrs[i++] = (void *)&v), ...); }, vals);
-    return cudaLaunchKernel((const void *)k, dim3(grid), dim3(block), ptrs, 0, stream);
+    return cudaLaunchKernel((const void *)k, grid, block, ptrs, 0, stream);
 }
 }  // namespace emu
 #define ACX_EMU_KERNEL(k, scalable) static const emu::KernelRegistrar emu_registrar_##k(k, #k, scalable);

@@ -44,7 +44,7 @@ def test_minimpi_thread_multiple(built, np_):
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("prog", ["ring", "ring_all", "procnull_comms", "wildcards", "subcomm", "datatypes", "threads", "status_errors", "sendrecv_enqueue", "reinit", "tags", "host_reuse"])
+@pytest.mark.parametrize("prog", ["ring", "ring_all", "procnull_comms", "wildcards", "subcomm", "datatypes", "threads", "status_errors", "sendrecv_enqueue", "reinit", "tags", "host_reuse", "many_outstanding"])
 @pytest.mark.parametrize("np_", [1, 2, 3])
 def test_ring_host_transport(built, prog, np_):
     r = acxrun(built, np_, built / f"build/tests/{prog}", env={"ACX_FORCE_HOST": "1"})

@@ -16,7 +16,7 @@ run() {  # run <label> <np> <prog> [env...]
     if [ $rc -eq 0 ] && echo "$out" | grep -q "PASS"; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms
     else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $rc "$(echo "$out" | grep -v "ASan doesn\x27t fully support" | tail -${EMU_TAIL:-8})"; fails=$((fails+1)); fi
 }
-progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors sendrecv_enqueue reinit tags host_reuse"
+progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors sendrecv_enqueue reinit tags host_reuse many_outstanding"
 nps="1 2 3"
 [ "$mode" = full ] && nps="1 2 3 4"
 for p in $progs; do for np in $nps; do run default $np $p; done; done
@@ -61,6 +61,7 @@ run late-wildcards 3 wildcards ACX_WILDCARDS=1 $LATE
 for p in ring ring_all ring_all_device ordering stress status_errors tags threads large_msgs sendrecv_enqueue late_push; do run memops-p2p 2 $p ACX_MEMOPS=1; done
 run memops-p2p 3 stress ACX_MEMOPS=1 ACX_FAULT_DELAY_US=200
 run memops-p2p-late 2 large_msgs ACX_MEMOPS=1 ACX_LATE_PUSH_MIN=65536
+run memops-p2p 2 many_outstanding ACX_MEMOPS=1
 run pbatch 2 ring_partitioned ACX_PBATCH=1
 run pbatch 3 ring_partitioned ACX_PBATCH=1
 run memops 2 ring_partitioned ACX_MEMOPS=1
