@@ -122,6 +122,7 @@ typedef struct MPIX_Acx_stats {
     unsigned long long kernels_launched, graph_nodes_added;
     unsigned long long slots_in_use, slots_high_water;
     unsigned long long heap_bytes_in_use, heap_bytes_high_water;
+    unsigned long long copy_engine_msgs;   /* rendezvous messages moved by cudaMemcpyAsync (ACX_CE_MIN) */
 } MPIX_Acx_stats;
 int MPIX_Get_stats(MPIX_Acx_stats *stats);
 /* 1 when the GPU transport is active, 0 when running on the host (no-GPU) transport. */

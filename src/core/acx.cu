@@ -88,6 +88,9 @@ static int g_coop = 0;                    // ACX_COOP: cooperative moving with c
 static long g_coop_min = 4 << 20;          // ACX_COOP_MIN_BYTES
 static long g_late_min = 4 << 20;          // ACX_LATE_PUSH_MIN: messages from this size up use the sender-moves protocol (RNDV_LATE); 0 = off
 static long g_late_helpers = 0;            // ACX_LATE_HELPERS: helper CTAs all late sends of one wait kernel share (0 = one per SM)
+static long g_ce_min = 4 << 20;            // ACX_CE_MIN: stream-mode messages from this size up travel by copy engine when the sender's host can see the matching receive's enqueue-time record (0 = off)
+static long g_ce_spin_us = 40;             // ACX_CE_SPIN_US: how long MPIX_Isend_enqueue looks for that record before it takes the kernel path
+static long g_ce_spin_busy_us = 300;       // ACX_CE_SPIN_BUSY_US: ... when the caller's stream still has work queued (the host is ahead of its GPU: waiting for the neighbour's host costs nothing)
 static long g_late_fallback_us = 50;       // ACX_LATE_FALLBACK_US: grace period before a receive's wait pulls an unclaimed RNDV_LATE message itself
 static int g_pbatch = 1;                  // ACX_PBATCH (default on since round 2): one kernel launch per MPIX_Startall / MPIX_Waitall group of partitioned requests instead of one per request
 static int g_branch = 2;                  // ACX_PEER_BRANCH: run every operation with a peer on that peer's side stream (fork at enqueue, join at the wait): 0 never, 1 always, 2 (default) while the stream is capturing — there the forks are graph edges and cost nothing at run time
@@ -151,6 +154,9 @@ static void report_watchdog() {
             case 0x5e0b: what = "wildcard receive: no matching send arrived"; break;
             case 0x5e0c: what = "cooperative-move gate: the peer never arrived"; break;
             case 0x5e0f: what = "host-predicted ticket (b) differs from the one the trigger drew (a): a memOp wait was built on the wrong slot"; break;
+            case 0x5e10: what = "copy-engine send: host-predicted ticket (b) differs from the one the trigger drew (a)"; break;
+            case 0x5e11: what = "copy-engine send: the matching receive (enqueued by its host) was never posted on the device"; break;
+            case 0x5e12: what = "copy-engine send: the receive's device-side destination (a) is not the one its host published (b), or it is too small"; break;
             case 0x5e0e: what = "wait kernel helper: the request's waiter CTA never decided (a = ticket, b = state word)"; break;
         }
         ACX_ERR("WATCHDOG (code 0x%llx, a=0x%llx b=0x%llx): %s", (unsigned long long)g_diag[0], (unsigned long long)g_diag[1],
@@ -550,6 +556,7 @@ static AcxRegTable *g_reg_tables = nullptr;
 static std::unordered_map<uint64_t, int> g_reg_mine;     // buffer id -> entry index (-1: not registrable)
 static std::vector<uint32_t> g_reg_seen;
 static std::vector<void *> g_reg_opened;
+static std::vector<uint64_t> g_xlat_host;   // host copy of the device translation table: [owner rank][entry] -> address mapped here (copy-engine sends resolve destinations on the host)
 typedef int (*cuMemGetAddressRangeFn)(unsigned long long *, size_t *, unsigned long long);
 typedef int (*cuPointerGetAttributeFn)(void *, int, unsigned long long);
 static cuMemGetAddressRangeFn g_cuMemGetAddressRange = nullptr;
@@ -574,6 +581,7 @@ static void reg_init() {
         for (auto &row : mine->ack) for (auto &a : row) a.store(0, std::memory_order_relaxed);
     }
     g_reg_seen.assign(g_acx->size, 0);
+    g_xlat_host.assign((size_t)g_acx->size * g_acx->geom.maxreg, 0);
     g_reg_on = true;
 }
 
@@ -597,6 +605,7 @@ static void reg_progress() {
             }
             if (mapped) {
                 acx_h2d(g_acx->ctrl + g_acx->geom.off_xlat + ((uint64_t)p * g_acx->geom.maxreg + i) * 8, &mapped, 8, host_stream());   // entries are rare
+                g_xlat_host[(size_t)p * g_acx->geom.maxreg + i] = mapped;
                 to_ack.push_back({p, i});
                 wrote = true;
             }
@@ -794,6 +803,7 @@ static int acx_numa_bind(int dev) {
 #endif
 }
 
+static void ce_init();       // enqueue-time receive records (copy-engine rendezvous), defined with the front-ends
 static void tagdir_init();   // channel directory (exact tag matching), defined with the front-ends
 // Reference: MPIX_Init, src/init.cpp:157-253 (flag table in mapped host memory + proxy thread). Here: device windows,
 // CUDA-IPC exchange, no thread.
@@ -831,6 +841,9 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_LATE_FALLBACK_US", nullptr, 50, &v); g_late_fallback_us = std::max(0L, v);
     acx_env_int("ACX_LATE_HELPERS", nullptr, 0, &v); g_late_helpers = std::max(0L, v);
     acx_env_int("ACX_PBATCH", nullptr, 1, &v); g_pbatch = v != 0;   // one launch per MPIX_Startall / MPIX_Waitall group: measured 0.641 vs 0.776 ms per API-level halo step on 2x B200 (reference arm 0.700), profiles/raw/r2_call1/halo_api.txt
+    acx_env_int("ACX_CE_MIN", nullptr, 4 << 20, &v); g_ce_min = std::max(0L, v);
+    acx_env_int("ACX_CE_SPIN_US", nullptr, 40, &v); g_ce_spin_us = std::max(0L, v);
+    acx_env_int("ACX_CE_SPIN_BUSY_US", nullptr, 300, &v); g_ce_spin_busy_us = std::max(0L, v);
     acx_env_int("ACX_MEMOPS", nullptr, 0, &v); g_memops = v != 0 && !getenv("MPIACX_DISABLE_MEMOPS");   // partitioned Start / Wait as stream memOps (opt-in until measured)
     acx_env_int("ACX_PEER_BRANCH", nullptr, 2, &v); g_branch = (int)std::max(0L, std::min(2L, v));   // 8x B200 all-pairs under CUDA graphs, 1 MiB per pair: 79.6 GB/s per GPU with branches vs 22.3 without (reference 45.8); 16 MiB: 288.6 vs 290.4 (profiles/raw/r2_call9)
     acx_env_int("ACX_SENDER_PUSH", nullptr, 0, &v); g_apush = v != 0;   // opt-in: a spinning gate can deadlock against device-synchronizing host calls
@@ -943,6 +956,7 @@ extern "C" int MPIX_Init(void) {
     g_acx->initialized = true;
     reg_init();
     tagdir_init();
+    ce_init();
     memops_init();
 #ifdef ACX_MINI_MPI
     ACX_Mpi_set_abort_hook(report_watchdog);
@@ -1030,6 +1044,7 @@ extern "C" int MPIX_Get_stats(MPIX_Acx_stats *s) {
     s->kernels_launched = g_acx->st.kernels; s->graph_nodes_added = g_acx->st.graph_nodes;
     s->slots_in_use = g_acx->slots_in_use; s->slots_high_water = g_acx->st.slots_hw;
     s->heap_bytes_in_use = g_acx->heap_in_use; s->heap_bytes_high_water = g_acx->st.heap_hw;
+    s->copy_engine_msgs = g_acx->st.ce;
     return MPI_SUCCESS;
 }
 
@@ -1106,6 +1121,7 @@ struct Emitter {
     cudaGraph_t graph = nullptr;          // GRAPH mode: graph under construction; capture: the capture graph
     cudaGraphNode_t last = nullptr;
     bool parallel = false;                // GRAPH mode: do not chain nodes (independent waits)
+    bool no_pdl = false;                  // plain launches (kernels that sit next to a copy-engine copy in their stream)
 
     int begin(int qt, void *queue) {
         qtype = qt;
@@ -1134,7 +1150,7 @@ struct Emitter {
         void *args[] = {&params};
         if (qtype == MPIX_QUEUE_CUDA_STREAM) {
             cudaError_t e;
-            if (g_pdl && !capturing) {
+            if (g_pdl && !capturing && !no_pdl) {
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
                 cudaLaunchAttribute at[1];
@@ -1164,7 +1180,7 @@ struct Emitter {
         void *args[] = {&p1, &p2};
         if (qtype == MPIX_QUEUE_CUDA_STREAM) {
             cudaError_t e;
-            if (g_pdl && !capturing) {
+            if (g_pdl && !capturing && !no_pdl) {
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = grid; cfg.blockDim = block; cfg.stream = stream;
                 cudaLaunchAttribute at[1];
@@ -1360,6 +1376,42 @@ static int launch_sender_push(Emitter &em, AcxRequest *r, SendParams &sp, MoverP
     return 0;
 }
 
+// Copy-engine variant of the above (see the record ring at ce_lookup): gate kernel, cudaMemcpyAsync, completion kernel on the
+// sender's (peer, channel) stream, forked from the caller's stream behind the trigger. `dst` is the receive's buffer as mapped
+// here, read from the receiver's enqueue-time record; the gate checks it against what the receive's trigger publishes.
+static int launch_sender_ce(Emitter &em, AcxRequest *r, SendParams &sp, char *dst, uint64_t dst_off, const char *src, size_t bytes) {
+    cudaStream_t cs;
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+        auto key = std::make_pair(r->peer, r->chan);
+        auto it = g_chan_streams.find(key);
+        if (it == g_chan_streams.end()) {
+            cudaStream_t ns = nullptr;
+            ACX_CUDA(cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking));
+            it = g_chan_streams.emplace(key, ns).first;
+        }
+        cs = it->second;
+    }
+    r->ev_trig = event_get(); r->ev_done = event_get();
+    if (!r->ev_trig || !r->ev_done) return MPI_ERR_OTHER;
+    ACX_CUDA(cudaEventRecord(r->ev_trig, em.stream));
+    ACX_CUDA(cudaStreamWaitEvent(cs, r->ev_trig, 0));
+    Emitter es = em;
+    es.stream = cs;
+    es.no_pdl = true;   // the gate follows an event wait, the completion kernel a copy: full stream dependencies, nothing programmatic
+    CeParams cp;
+    memset(&cp, 0, sizeof cp);
+    cp.op = sp.op; cp.ring = sp.ring; cp.sack = sp.sack; cp.ticket = r->hticket; cp.dst_off = dst_off; cp.bytes = bytes;
+    cp.depth = sp.depth; cp.peer = sp.peer; cp.wd = sp.wd; cp.tr = sp.tr;
+    int rc = es.launch(ce_gate, dim3(1), dim3(32), cp);
+    if (rc) return rc;
+    ACX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, cs));
+    if ((rc = es.launch(ce_complete, dim3(1), dim3(32), cp))) return rc;
+    ACX_CUDA(cudaEventRecord(r->ev_done, cs));
+    g_acx->st.ce++;
+    return 0;
+}
+
 static void fault_delay() {
     if (g_fault_delay_us <= 0) return;
     static std::atomic<unsigned> seed{12345u};
@@ -1445,6 +1497,101 @@ static uint64_t host_ticket(bool is_send, int peer, int chan, cudaStream_t strea
 static void host_tickets_forget_recv(int source) {   // a wildcard receive claims tickets on whichever channel matches
     std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
     for (int s = 0; s < g_acx->size; s++) if (source < 0 || s == source) for (auto &c : g_acx->recv_count[(size_t)s]) c.dev = true;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Copy-engine rendezvous: enqueue-time records of posted receives, in the job's shared-memory scratch.
+// The device protocol learns a receive's destination when its trigger kernel EXECUTES — too late for a cudaMemcpyAsync, whose
+// addresses are fixed when it is enqueued. But where both hosts count tickets (host_ticket: stream-mode operations on one
+// stream per channel) the k-th send of a channel matches the k-th receive, and the receiver's host knows the destination
+// when it ENQUEUES the receive: it leaves {ticket, destination code, capacity} in a small ring per (sender, receiver,
+// channel). A sender that finds the record of its ticket there hands the payload to the copy engines (launch_sender_ce);
+// one that does not (receive not enqueued yet, device-counted channel, graph) takes the kernel path. Which path a message
+// takes is the sender's call alone; the receiver's device side is the same either way (RNDV_PUSH: it publishes its mirror
+// and waits for `done`).
+// ---------------------------------------------------------------------------------------
+struct AcxCeRec { std::atomic<uint64_t> seq; uint64_t dst_off, cap, pad; };   // seq = ticket + 1, stored last (release)
+constexpr int kCeDepth = 16;
+static AcxCeRec *g_ce_recs = nullptr;
+static std::unique_ptr<std::atomic<int>[]> g_ce_miss;   // [dest][chan]: consecutive sends that found no record (stop waiting for one after a few)
+static inline AcxCeRec *ce_row(int sender, int receiver, int chan) {
+    return g_ce_recs + (((size_t)sender * g_acx->size + receiver) * (size_t)g_acx->geom.nchan + chan) * kCeDepth;
+}
+static void ce_init() {
+    g_ce_recs = nullptr;
+#ifdef ACX_MINI_MPI
+    if (g_ce_min <= 0) return;
+    size_t sb = 0;
+    char *scratch = (char *)ACX_Mpi_shared_scratch(&sb);
+    size_t off = (sizeof(AcxRegTable) * 64 + 4095) & ~(size_t)4095;
+    off += (size_t)g_acx->size * g_acx->size * (size_t)std::max(0, (int)g_acx->geom.nchan - 1) * sizeof(std::atomic<uint64_t>);   // the channel directory
+    off = (off + 4095) & ~(size_t)4095;
+    const size_t need = (size_t)g_acx->size * g_acx->size * (size_t)g_acx->geom.nchan * kCeDepth * sizeof(AcxCeRec);
+    if (!scratch || off + need > sb) return;
+    g_ce_recs = (AcxCeRec *)(scratch + off);
+    // a re-initialization starts from empty rings: every rank clears the rows it receives on (MPIX_Init ends with a barrier)
+    for (int s = 0; s < g_acx->size; s++)
+        for (int c = 0; c < (int)g_acx->geom.nchan; c++)
+            for (int i = 0; i < kCeDepth; i++) ce_row(s, g_acx->rank, c)[i].seq.store(0, std::memory_order_release);
+    g_ce_miss.reset(new std::atomic<int>[(size_t)g_acx->size * g_acx->geom.nchan]);
+    for (size_t i = 0; i < (size_t)g_acx->size * g_acx->geom.nchan; i++) g_ce_miss[i].store(0, std::memory_order_relaxed);
+#endif
+}
+// Receiver, at enqueue time: receive number `ticket` of (source -> me, chan) will land at `dst_off` (heap offset or registration code).
+static void ce_publish(int source, int chan, uint64_t ticket, uint64_t dst_off, uint64_t cap) {
+    if (!g_ce_recs || ticket == ~0ull || dst_off == ~0ull) return;
+    AcxCeRec *rec = ce_row(source, g_acx->rank, chan) + ticket % kCeDepth;
+    rec->seq.store(0, std::memory_order_relaxed);
+    std::atomic_thread_fence(std::memory_order_release);
+    rec->dst_off = dst_off; rec->cap = cap;
+    rec->seq.store(ticket + 1, std::memory_order_release);
+}
+// Sender, at enqueue time: the address (mapped here) send number `ticket` of (me -> dest, chan) must be copied to, or null.
+static char *ce_lookup(int dest, int chan, uint64_t ticket, size_t bytes, cudaStream_t stream, uint64_t *dst_off) {
+    if (!g_ce_recs || ticket == ~0ull) return nullptr;
+    AcxCeRec *rec = ce_row(g_acx->rank, dest, chan) + ticket % kCeDepth;
+    std::atomic<int> &miss = g_ce_miss[(size_t)dest * g_acx->geom.nchan + chan];
+    uint64_t off = 0, cap = 0;
+    bool found = false, extended = false;
+    long limit = g_ce_spin_us;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const uint64_t s1 = rec->seq.load(std::memory_order_acquire);
+        if (s1 == ticket + 1) {
+            off = rec->dst_off; cap = rec->cap;
+            std::atomic_thread_fence(std::memory_order_acquire);
+            if (rec->seq.load(std::memory_order_relaxed) == s1) { found = true; break; }   // not overwritten by a later receive meanwhile
+            break;
+        }
+        if (s1 > ticket + 1) break;   // a later receive has taken the record: the one for this ticket is gone
+        if (miss.load(std::memory_order_relaxed) >= 8 || g_ce_spin_us <= 0) break;   // this peer does not post its receives ahead of my sends: do not hold the caller up
+        const long waited = (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        if (waited >= limit) {
+            // Hosts enqueue far ahead of their GPUs and drift apart; a host whose stream still has work queued loses nothing by
+            // letting its neighbour's host catch up (which keeps the ranks' enqueue fronts together, and the copy engines in use).
+            if (!extended && g_ce_spin_busy_us > limit && cudaStreamQuery(stream) == cudaErrorNotReady) { cudaGetLastError(); extended = true; limit = g_ce_spin_busy_us; continue; }
+            cudaGetLastError();
+            break;
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (!found) { if (miss.load(std::memory_order_relaxed) < 1 << 20) miss.fetch_add(1, std::memory_order_relaxed); return nullptr; }
+    miss.store(0, std::memory_order_relaxed);
+    if (cap < bytes) return nullptr;   // truncation: the kernel path reports it
+    *dst_off = off;
+    if (off & ACX_OFF_REG_BIT) {
+#ifdef ACX_MINI_MPI
+        const size_t idx = (size_t)dest * g_acx->geom.maxreg + ACX_OFF_REG_IDX(off);
+        if (idx >= g_xlat_host.size() || !g_xlat_host[idx]) return nullptr;
+        return (char *)(g_xlat_host[idx] + ACX_OFF_REG_OFF(off));
+#else
+        return nullptr;
+#endif
+    }
+    return g_acx->peer_heap[dest] + off;
 }
 
 static AcxRequest *new_request(AcxReqKind kind, int peer, int tag, int ctx, size_t bytes, const void *buf) {
@@ -1612,6 +1759,7 @@ struct DeferredRecv { RecvParams rp; MoverParams mp; int fgrid; bool rndv_capabl
 static int launch_recv(Emitter &em, AcxRequest *r, RecvParams &rp, MoverParams &mp, int fgrid, bool rndv_capable, size_t bytes) {
     int rc;
     r->hticket = host_ticket(false, r->peer, r->chan, em.stream, r->in_graph);
+    if (rndv_capable && rp.publish && !r->in_graph) ce_publish(r->peer, r->chan, r->hticket, rp.dst_off, rp.cap);   // a sender whose host sees this may use the copy engines
     if (fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas) {
         if ((rc = em.launch2(recv_rndv_fused, dim3(fgrid), dim3(kMoverThreads), rp, mp))) return rc;
     } else {
@@ -1746,14 +1894,22 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         // Large messages: the sender moves them — the mover behind this trigger if the receive is posted by then, the helper
         // CTAs of this request's wait kernel otherwise. The receiver never pulls (except as a late fallback), so every GPU
         // copies exactly its own sends whatever order ranks arrive in (a ring step stays one NVLink push per GPU).
-        r->late = g_late_min > 0 && !eager && !fused && !apush && !r->coop && (long)bytes >= g_late_min;
-        sp.late = r->late ? 1 : 0;
         r->src_local = (char *)src_local;
         if (!dropped) r->hticket = host_ticket(true, dest, r->chan, r->stream, r->in_graph);
+        // Copy-engine rendezvous: if the receiver's host has already enqueued the matching receive (its record is in shared
+        // memory), the destination is known now and the copy engines move the payload; decided per message, by the sender.
+        char *ce_dst = nullptr;
+        uint64_t ce_off = 0;
+        if (g_ce_min > 0 && !eager && !fused && !apush && !r->coop && !dropped && (long)bytes >= g_ce_min && g_side_on && qtype == MPIX_QUEUE_CUDA_STREAM && !em.capturing && !r->branched)
+            ce_dst = ce_lookup(dest, r->chan, r->hticket, bytes, em.stream, &ce_off);
+        if (ce_dst) sp.apush = 1;   // announced as RNDV_PUSH: the receiver leaves the message alone
+        r->late = g_late_min > 0 && !eager && !fused && !apush && !ce_dst && !r->coop && (long)bytes >= g_late_min;
+        sp.late = r->late ? 1 : 0;
         if (!dropped && fused) { if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail; }
         else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
         if (!eager) {
-            if (apush) { if (!dropped && (rc = launch_sender_push(em, r, sp, mp, bytes))) goto fail; }
+            if (ce_dst) { if ((rc = launch_sender_ce(em, r, sp, ce_dst, ce_off, src_local, bytes))) goto fail; }
+            else if (apush) { if (!dropped && (rc = launch_sender_push(em, r, sp, mp, bytes))) goto fail; }
             else if (!fused && (rc = launch_mover_maybe_side(em, r, mp, bytes))) goto fail;
             mark_operation_end(em, r);   // no-op when a side branch already carries the event
             g_acx->st.rndv++;
@@ -2183,7 +2339,13 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             // their wait) and operations on device-counted channels keep the spinning wait.
             MemOpBatch mb;
             const acx_geom &G = g_acx->geom;
-            for (int j = 0; j < n; j++) {
+            // A batch with a large-message request keeps the spinning wait for ALL its requests: its wait kernel may have to move
+            // data itself (a late send's helper CTAs push, a large receive's pull as a fallback), and a memOp in front of that
+            // kernel waiting for another request of the batch would wait for exactly the data the kernel has not moved yet
+            // (tests/c/ce_path.c part 3 with ACX_MEMOPS=1: every rank's send posted first — a deadlock on the software device).
+            bool movers_in_wait = false;
+            for (int j = 0; j < n; j++) if (wb.w[j].late) movers_in_wait = true;
+            for (int j = 0; j < n && !movers_in_wait; j++) {
                 AcxRequest *r = need[base + j].r;
                 if (r->hticket == ~0ull || r->wild) continue;
                 const uint32_t e = (uint32_t)(r->hticket % (uint64_t)G.depth);
@@ -2979,7 +3141,7 @@ extern "C" int MPIX_Parrived_host(MPIX_Request *request, int partition, int *fla
 #ifdef ACX_EMU
 // Software device (tests/emu): kernels are plain functions; tell its cudaLaunchKernel / cudaGraphAddKernelNode about
 // their argument lists. All of them are written for any blockDim (second argument), so the emulation may shrink blocks.
-ACX_EMU_KERNEL(copy_kernel, true) ACX_EMU_KERNEL(send_trigger, true) ACX_EMU_KERNEL(recv_trigger, true) ACX_EMU_KERNEL(push_gate, true)
+ACX_EMU_KERNEL(copy_kernel, true) ACX_EMU_KERNEL(send_trigger, true) ACX_EMU_KERNEL(recv_trigger, true) ACX_EMU_KERNEL(push_gate, true) ACX_EMU_KERNEL(ce_gate, true) ACX_EMU_KERNEL(ce_complete, true)
 ACX_EMU_KERNEL(mover, true) ACX_EMU_KERNEL(mover_plain, true) ACX_EMU_KERNEL(mover_v256, true) ACX_EMU_KERNEL(mover_cs, true) ACX_EMU_KERNEL(send_rndv_fused, true) ACX_EMU_KERNEL(recv_rndv_fused, true) ACX_EMU_KERNEL(recv_any_kernel, true)
 ACX_EMU_KERNEL(coop_gate, true) ACX_EMU_KERNEL(coop_kernel, true) ACX_EMU_KERNEL(wait_kernel, true) ACX_EMU_KERNEL(recv_wait_fused, true) ACX_EMU_KERNEL(sendrecv_fused, true) ACX_EMU_KERNEL(bounce_out_kernel, true)
 ACX_EMU_KERNEL(pack_kernel, true) ACX_EMU_KERNEL(unpack_kernel, true) ACX_EMU_KERNEL(pstart_kernel, true) ACX_EMU_KERNEL(pstart_batch_kernel, true)

@@ -311,7 +311,7 @@ struct AcxState {
     // stats
     struct {
         std::atomic<unsigned long long> sends{0}, recvs{0}, waits{0}, bytes_sent{0}, bytes_recv{0}, eager{0}, rndv{0}, bounce{0},
-            kernels{0}, graph_nodes{0}, slots_hw{0}, heap_hw{0};
+            kernels{0}, graph_nodes{0}, slots_hw{0}, heap_hw{0}, ce{0};
     } st;
     size_t heap_in_use = 0;
     int slots_in_use = 0;

@@ -70,6 +70,11 @@ __device__ __forceinline__ void spin_geq(const uint64_t *p, uint64_t v, const Wa
         }
     }
 }
+__device__ __forceinline__ void wd_fail(const Watchdog &wd, uint64_t code, uint64_t a, uint64_t b) {   // diagnosed fatal error
+    if (wd.diag) { wd.diag[1] = a; wd.diag[2] = b; wd.diag[0] = code; }
+    __threadfence_system();
+    __trap();
+}
 
 // 256-bit (LDG.256 / STG.256, new on sm_100) copy loop: half the LSU instructions per byte and
 // 1-KiB contiguous runs per warp instruction. Needs 32-B aligned pointers; tail via copy_bytes.
@@ -339,6 +344,48 @@ __global__ void push_gate(GateParams p) {
     p.op->n = p.bytes < cap ? p.bytes : cap;
     if (p.op->n == 0) p.op->coop = 0;
     p.op->mover = 1;
+}
+
+// Copy-engine rendezvous (ACX_CE_MIN; host side: launch_sender_ce in acx.cu). The sender's host found the receiver's
+// enqueue-time record of the matching receive (destination, capacity — both ranks count tickets on the host), so the
+// destination address is known when the operation is enqueued and the payload can travel by cudaMemcpyAsync — the copy
+// engines reach ~760 GB/s per direction where SM-issued stores stop at ~690 (tools/bwprobe.cu) and no SM is occupied.
+// On the sender's (peer, channel) stream: ce_gate — wait until the receive has really been posted on the device (its
+// mirror in MY sack carries this generation), check the host's prediction — then the copy, then ce_complete, which
+// publishes completion to both sides exactly as the last CTA of a mover does. The message travels as RNDV_PUSH: the
+// receiver never moves it.
+struct CeParams {
+    acx_op *op;
+    acx_entry *ring;         // peer-mapped: the receiver's ring for (me -> dst, chan)
+    acx_sack *sack;          // local
+    uint64_t ticket;         // host-predicted ticket of this send
+    uint64_t dst_off, bytes; // host-read destination code and message size
+    uint32_t depth, peer;
+    Watchdog wd;
+    TraceCtx tr;
+};
+__global__ void ce_gate(CeParams p) {
+    pdl_prologue();
+    if (threadIdx.x != 0) return;
+    const uint64_t k = p.op->ticket;
+    if (k != p.ticket) { wd_fail(p.wd, 0x5e10, k, p.ticket); }   // the host mis-predicted the ticket: the copy behind this kernel would land in the wrong receive's buffer
+    const uint32_t e = (uint32_t)(k % p.depth);
+    const uint64_t g = k / p.depth;
+    spin_geq(&p.sack[e].r_gen, g + 1, p.wd, 0x5e11);
+    const uint64_t cap = ld_relaxed_sys(&p.sack[e].r_cap), off = ld_relaxed_sys(&p.sack[e].r_dst_off);
+    if (off != p.dst_off || cap < p.bytes) { wd_fail(p.wd, 0x5e12, off, p.dst_off); }
+    trace(p.tr, ACX_EV_MOVE_BEGIN, p.peer, k, p.bytes);
+}
+__global__ void ce_complete(CeParams p) {
+    pdl_prologue();
+    if (threadIdx.x != 0) return;
+    const uint64_t k = p.ticket;
+    const uint32_t e = (uint32_t)(k % p.depth);
+    const uint64_t g = k / p.depth;
+    __threadfence_system();
+    st_release_sys(&p.ring[e].done, g + 1);   // receiver may consume (the copy before this kernel in stream order has landed)
+    st_release_sys(&p.sack[e].sdone, g + 1);  // sender's buffer is reusable
+    trace(p.tr, ACX_EV_MOVE_END, p.peer, k, p.bytes);
 }
 
 // Cooperative moving (ACX_COOP=1): the payload is cut into acx_coop_chunk(n)-byte chunks behind an atomic cursor in the

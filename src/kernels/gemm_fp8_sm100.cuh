@@ -23,6 +23,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <mutex>
+#include <stdlib.h>
+
+#ifndef ACX_GEMM_PAIR_DEFAULT
+#define ACX_GEMM_PAIR_DEFAULT 0   // flipped to 1 once the CTA-pair kernel has passed tests/c/gemm_fp8_test.cu on hardware
+#endif
 
 namespace acxg {
 namespace {   // internal linkage: every module that includes this header owns a private copy of the kernel and its
@@ -301,6 +306,209 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_fp8_kernel(const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on the two SMs of a TPC owns one 256x256 output tile.
+// CTA r of the pair loads rows [128 r, 128 r + 128) of the tile's X panel and rows [128 r, +128) of its W panel — half of
+// each operand — and ONE thread of the leader CTA (rank 0) issues tcgen05.mma.cta_group::2 M256 N256 K32, which reads both
+// CTAs' shared memory and accumulates rows 128 r .. +127 into CTA r's tensor memory. Per SM and MMA the shared-memory read
+// traffic drops from 4 KiB (A) + 8 KiB (B) to 4 + 4 KiB and the TMA fill traffic from 48 to 32 KiB per k-block, which is
+// what the single-CTA kernel is bound by (tensor pipe 87 % active, profiles/gemm_fp8_ncu.md); the smaller stages also buy a
+// 6-deep ring. Synchronisation across the pair:
+//   full[s]   lives in the LEADER: its producer arms it with the bytes of BOTH CTAs' loads; the peer's TMA loads are
+//             cp.async.bulk.tensor ... .cta_group::2 pointing at the leader's barrier (mapa);
+//   empty[s]  in each CTA: the leader's tcgen05.commit is multicast to both, so each producer sees its stage freed;
+//   tfull[a]  in each CTA, same multicast commit: both epilogues start on their own half of the accumulator;
+//   tempty[a] in the leader, 8 arrivals: the four epilogue warps of both CTAs (remote mbarrier.arrive for the peer's).
+// The epilogue and the partition gating are per CTA and identical to the single-CTA kernel's (each CTA owns 128 rows).
+constexpr int STAGES2 = 6;
+constexpr int A_STAGE2 = BM * BK, B_STAGE2 = (BN / 2) * BK;          // 16 KiB + 16 KiB per CTA
+constexpr int STAGE_BYTES2 = A_STAGE2 + B_STAGE2;
+constexpr int SMEM_BYTES2 = STAGES2 * STAGE_BYTES2 + OUT_TILE + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {   // address of the same shared-memory location in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier that may live in the PEER CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *tm, uint32_t bar_cluster_addr, void *dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {   // arrives on the barrier at this offset in BOTH CTAs when the MMAs issued so far retire
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t umma_idesc_e4m3_pair() {   // D=f32, A=B=e4m3, K-major, N=256, M=256 (both CTAs)
+    uint32_t d = 0;
+    d |= 1u << 4;
+    d |= (uint32_t)(BN >> 3) << 17;
+    d |= (uint32_t)((2 * BM) >> 4) << 24;
+    return d;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_fp8_pair_kernel(const __grid_constant__ Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem, *sB = smem + STAGES2 * A_STAGE2, *sOut = smem + STAGES2 * STAGE_BYTES2;
+    uint64_t *bars = (uint64_t *)(sOut + OUT_TILE);
+    uint64_t *full = bars, *empty = bars + STAGES2, *tfull = bars + 2 * STAGES2, *tempty = bars + 2 * STAGES2 + 2;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES2 + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_n = P.N / BN, tiles_m2 = P.M / (2 * BM), ntiles = tiles_m2 * tiles_n, kblocks = P.K / BK;
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+    if (warp == 0 && elect_one()) { tma_prefetch_desc(&P.tmA); tma_prefetch_desc(&P.tmB); }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < STAGES2; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {   // one warp of EACH CTA of the pair issues the pair-wide allocation
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the peer's barriers are initialised and its tensor memory allocated before anything is signalled across
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs: own half of each operand; completion lands on the leader's full barrier) =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = cluster_id; t < ntiles; t += nclusters) {
+                const int tm = 2 * (t / tiles_n) + (int)rank, tn = t % tiles_n;
+                if (P.g.in_arrived) {
+                    spin_geq_sys(P.g.in_arrived + (tm * BM) / P.g.rows_per_panel, P.g.in_epoch);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                for (int kb = 0; kb < kblocks; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES2);
+                    const uint32_t fb = mapa_shared(smem_u32(&full[stage]), 0);
+                    tma_load_2d_pair(&P.tmA, fb, sA + stage * A_STAGE2, kb * BK, tm * BM);
+                    tma_load_2d_pair(&P.tmB, fb, sB + stage * B_STAGE2, kb * BK, tn * BN + (int)rank * (BN / 2));
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (leader) {
+            const uint32_t idesc = umma_idesc_e4m3_pair();
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int t = cluster_id; t < ntiles; t += nclusters) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);          // both CTAs' epilogues drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
+                for (int kb = 0; kb < kblocks; kb++) {
+                    mbar_wait(&full[stage], phase);               // both CTAs' loads landed
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * A_STAGE2));
+                        const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * B_STAGE2));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++)
+                            tc_mma_f8_pair(tmem_d, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), idesc, (kb | k) != 0);
+                        tc_commit_pair(&empty[stage]);
+                        if (kb == kblocks - 1) tc_commit_pair(&tfull[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): warps 4..7 own TMEM lanes 32*(warp-4) .. +31 == rows of this CTA's half of the tile =====
+        const int ew = warp - 4, row = ew * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        bool credit_ok = P.g.credit == nullptr;
+        for (int t = cluster_id; t < ntiles; t += nclusters) {
+            const int tm = 2 * (t / tiles_n) + (int)rank, tn = t % tiles_n;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t v[32];
+                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                tc_wait_ld();
+                uint32_t packed[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float f0 = __uint_as_float(v[4 * i]) * P.scale, f1 = __uint_as_float(v[4 * i + 1]) * P.scale;
+                    const float f2 = __uint_as_float(v[4 * i + 2]) * P.scale, f3 = __uint_as_float(v[4 * i + 3]) * P.scale;
+                    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f0, f1), __NV_SATFINITE, __NV_E4M3);
+                    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f2, f3), __NV_SATFINITE, __NV_E4M3);
+                    packed[i] = lo | (hi << 16);
+                }
+                const int ch0 = 2 * c, ch1 = 2 * c + 1;
+                *reinterpret_cast<uint4 *>(sOut + row * BN + ((ch0 ^ (row & 15)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                *reinterpret_cast<uint4 *>(sOut + row * BN + ((ch1 ^ (row & 15)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // the leader's MMA warp may overwrite this accumulator (in both CTAs) once all 8 warps are here
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (!credit_ok) {
+                if (threadIdx.x == 128) spin_geq_sys(P.g.credit, P.g.credit_need);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                credit_ok = true;
+            }
+            uint8_t *gout = P.out + (size_t)(tm * BM) * P.N + (size_t)tn * BN;
+            const int et = threadIdx.x - 128;
+#pragma unroll 4
+            for (int i = 0; i < (BM * BN / 16) / 128; i++) {
+                const int idx = i * 128 + et, r = idx >> 4, ch = idx & 15;
+                const uint4 val = *reinterpret_cast<const uint4 *>(sOut + r * BN + ((ch ^ (r & 15)) << 4));
+                *reinterpret_cast<uint4 *>(gout + (size_t)r * P.N + (ch << 4)) = val;
+            }
+            if (P.g.panel_count) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 128) {
+                    __threadfence_system();
+                    const int panel = (tm * BM) / P.g.rows_per_panel;
+                    const unsigned long long old = atomicAdd(P.g.panel_count + panel, 1ull);
+                    if (old + 1 == P.g.panel_target && P.g.out_arrived) {
+                        __threadfence_system();
+                        st_release_sys_u64(P.g.out_arrived + panel, P.g.out_epoch);
+                    }
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    // ===== teardown: neither CTA may leave (or free tensor memory) while the other can still signal its barriers or read its smem =====
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (threadIdx.x == 0 && P.g.done_count) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(P.g.done_count, 1ull);
+        if (old + 1 == P.g.done_target && P.g.credit_out) st_release_sys_u64(P.g.credit_out, P.g.credit_out_val);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -353,19 +561,37 @@ inline bool cached_tmap_copy(CUtensorMap *out, const void *base, uint64_t rows, 
     return true;
 }
 
+// CTA-pair kernel (cta_group::2) when the shape allows it (M a multiple of 256); ACX_GEMM_PAIR=0 keeps the single-CTA kernel.
+inline bool gemm_use_pair(int M) {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("ACX_GEMM_PAIR"); on = e ? atoi(e) != 0 : ACX_GEMM_PAIR_DEFAULT; }
+    return on && M % (2 * BM) == 0;
+}
+// Number of CTAs launch_gemm_fp8 starts for this shape (pipeline stages count finished CTAs).
+inline int gemm_grid(int M, int N, int num_sms) {
+    if (gemm_use_pair(M)) {
+        const int ntiles = (M / (2 * BM)) * (N / BN);
+        return 2 * (ntiles < num_sms / 2 ? ntiles : num_sms / 2);
+    }
+    const int ntiles = (M / BM) * (N / BN);
+    return ntiles < num_sms ? ntiles : num_sms;
+}
+
 inline int launch_gemm_fp8(const uint8_t *X, const uint8_t *W, uint8_t *out, int M, int N, int K, float scale, const Gating &g, int num_sms, cudaStream_t stream) {
     if (M % BM || N % BN || K % BK) return 3;
+    const bool pair = gemm_use_pair(M);
     Params P;
-    if (!cached_tmap_copy(&P.tmA, X, (uint64_t)M, (uint64_t)K, BM) || !cached_tmap_copy(&P.tmB, W, (uint64_t)N, (uint64_t)K, BN)) return 4;
+    if (!cached_tmap_copy(&P.tmA, X, (uint64_t)M, (uint64_t)K, BM) || !cached_tmap_copy(&P.tmB, W, (uint64_t)N, (uint64_t)K, pair ? BN / 2 : BN)) return 4;
     P.out = out; P.M = M; P.N = N; P.K = K; P.scale = scale; P.g = g;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_fp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return 5;
+        if (cudaFuncSetAttribute(gemm_fp8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES2) != cudaSuccess) return 5;
         attr_set = true;
     }
-    const int ntiles = (M / BM) * (N / BN);
-    const int grid = ntiles < num_sms ? ntiles : num_sms;
-    gemm_fp8_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(P);
+    const int grid = gemm_grid(M, N, num_sms);
+    if (pair) gemm_fp8_pair_kernel<<<grid, THREADS, SMEM_BYTES2, stream>>>(P);
+    else gemm_fp8_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : 6;
 }
 

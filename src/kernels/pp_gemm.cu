@@ -49,8 +49,7 @@ extern "C" int acx_ppgemm_create(int M, int D, int partitions, float scale, acx_
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, dev);
-    const int ntiles = (M / acxg::BM) * (D / acxg::BN);
-    h->grid = ntiles < h->sms ? ntiles : h->sms;
+    h->grid = acxg::gemm_grid(M, D, h->sms);
     const size_t act = (size_t)M * D;
     PCK(cudaMalloc((void **)&h->W, (size_t)D * D));
     for (int b = 0; b < 2; b++) { POK(MPIX_Alloc_mem(act, MPI_INFO_NULL, &h->xin[b])); PCK(cudaMemset(h->xin[b], 0, act)); }

@@ -155,7 +155,7 @@ void die(const char *fmt, ...) {
 // ---------------------------------------------------------------------------------
 constexpr uint32_t kMagic = 0xAC0B2001u;
 constexpr size_t kBlobBytes = 8192;         // per-rank exchange blob
-constexpr size_t kScratchBytes = 1u << 20;  // libacx control area (directories, registries)
+constexpr size_t kScratchBytes = 8u << 20;  // libacx control area (directories, registries)
 
 enum CellKind : uint32_t { CELL_HDR = 1, CELL_DATA = 2, CELL_RTS_IPC = 3, CELL_FIN = 4 };
 

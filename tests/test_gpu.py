@@ -349,6 +349,19 @@ def test_large_message_sender_moves_protocol(built, np_):
 
 
 @pytest.mark.parametrize("np_", [1, 2])
+@pytest.mark.parametrize("ce_min", [4 << 20, 0])
+def test_copy_engine_rendezvous(built, np_, ce_min):
+    """8 MiB messages with the copy-engine rendezvous on (ACX_CE_MIN, default) and off: where the sender's host sees the
+    receiver's enqueue-time record of the matching receive the payload travels by cudaMemcpyAsync behind a gate kernel, else by
+    the kernel movers; the receive posted first / the send first, free-running ring steps, sizes mixed on one channel, private
+    destinations, truncation, a second stream on the channel — tests/c/ce_path.c (the reference's transfers are its MPI's
+    copy-engine copies, src/init.cpp:64-80)."""
+    r = acxrun(built, np_, built / "build/tests/ce_path", env={"ACX_CE_MIN": str(ce_min)})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.parametrize("np_", [1, 2])
 def test_host_buffers_reused_addresses_and_partially_pinned_rows(built, np_):
     """A pageable host buffer is unmapped and its addresses come back from the next mmap: the cached registration must be
     re-validated (page frames), not trusted; and 1-KiB rows of a static array, pinned page by page, all in flight —

@@ -57,6 +57,19 @@ for p in large_msgs ring_all_device ring_all_graph graph_large ordering stress s
     run late-jitter 3 $p $LATE ACX_FAULT_DELAY_US=200
 done
 run late-wildcards 3 wildcards ACX_WILDCARDS=1 $LATE
+# copy-engine rendezvous (ACX_CE_MIN) at emulation-sized messages: the sender's host reads the receiver's enqueue-time record
+CE="ACX_CE_MIN=16384 ACX_LATE_PUSH_MIN=65536"
+for np in 1 2 3; do lrun ce $np ce_path $CE; done
+[ "$mode" = full ] && lrun ce 4 ce_path $CE
+lrun ce-off 2 ce_path ACX_CE_MIN=0 ACX_LATE_PUSH_MIN=65536
+lrun ce-jitter 3 ce_path $CE ACX_FAULT_DELAY_US=300
+lrun ce-no-spin 2 ce_path $CE ACX_CE_SPIN_US=0
+lrun ce-memops 2 ce_path $CE ACX_MEMOPS=1
+lrun ce-late 2 late_push $CE
+for p in large_msgs ring_all_device stress status_errors threads regcache many_outstanding ordering tags datatypes reinit; do
+    run ce 2 $p $CE
+    run ce-jitter 3 $p $CE ACX_FAULT_DELAY_US=200
+done
 # stream memOps on the on-stream p2p path: waits of host-predictable operations are cuStreamWaitValue64 on local completion words
 for p in ring ring_all ring_all_device ordering stress status_errors tags threads large_msgs sendrecv_enqueue late_push; do run memops-p2p 2 $p ACX_MEMOPS=1; done
 run memops-p2p 3 stress ACX_MEMOPS=1 ACX_FAULT_DELAY_US=200
