@@ -88,7 +88,9 @@ static int g_coop = 0;                    // ACX_COOP: cooperative moving with c
 static long g_coop_min = 4 << 20;          // ACX_COOP_MIN_BYTES
 static long g_late_min = 4 << 20;          // ACX_LATE_PUSH_MIN: messages from this size up use the sender-moves protocol (RNDV_LATE); 0 = off
 static long g_late_helpers = 0;            // ACX_LATE_HELPERS: helper CTAs all late sends of one wait kernel share (0 = one per SM)
-static long g_ce_min = 4 << 20;            // ACX_CE_MIN: stream-mode messages from this size up travel by copy engine when the sender's host can see the matching receive's enqueue-time record (0 = off)
+static long g_ce_min = 64 << 20;           // ACX_CE_MIN: stream-mode messages from this size up travel by copy engine when the sender's host can see the matching receive's enqueue-time record (0 = off); measured break-even with the SM mover on a 2-GPU ring: 64 MiB (profiles/raw/r2_call11/sweep.txt)
+static long g_wait_early_helpers = 32;     // ACX_WAIT_EARLY_HELPERS: a wait kernel with at most this many helper CTAs still releases its programmatic dependents early
+static long g_ce_spingate = 0;             // ACX_CE_SPINGATE: the gate kernel waits for the send's trigger itself (acquire spin on the op record) instead of behind a cross-stream event
 static long g_ce_spin_us = 40;             // ACX_CE_SPIN_US: how long MPIX_Isend_enqueue looks for that record before it takes the kernel path
 static long g_ce_spin_busy_us = 300;       // ACX_CE_SPIN_BUSY_US: ... when the caller's stream still has work queued (the host is ahead of its GPU: waiting for the neighbour's host costs nothing)
 static long g_late_fallback_us = 50;       // ACX_LATE_FALLBACK_US: grace period before a receive's wait pulls an unclaimed RNDV_LATE message itself
@@ -157,6 +159,7 @@ static void report_watchdog() {
             case 0x5e10: what = "copy-engine send: host-predicted ticket (b) differs from the one the trigger drew (a)"; break;
             case 0x5e11: what = "copy-engine send: the matching receive (enqueued by its host) was never posted on the device"; break;
             case 0x5e12: what = "copy-engine send: the receive's device-side destination (a) is not the one its host published (b), or it is too small"; break;
+            case 0x5e13: what = "copy-engine send: the send's trigger never ran (gate kernel without an event, ACX_CE_SPINGATE)"; break;
             case 0x5e0e: what = "wait kernel helper: the request's waiter CTA never decided (a = ticket, b = state word)"; break;
         }
         ACX_ERR("WATCHDOG (code 0x%llx, a=0x%llx b=0x%llx): %s", (unsigned long long)g_diag[0], (unsigned long long)g_diag[1],
@@ -841,7 +844,9 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_LATE_FALLBACK_US", nullptr, 50, &v); g_late_fallback_us = std::max(0L, v);
     acx_env_int("ACX_LATE_HELPERS", nullptr, 0, &v); g_late_helpers = std::max(0L, v);
     acx_env_int("ACX_PBATCH", nullptr, 1, &v); g_pbatch = v != 0;   // one launch per MPIX_Startall / MPIX_Waitall group: measured 0.641 vs 0.776 ms per API-level halo step on 2x B200 (reference arm 0.700), profiles/raw/r2_call1/halo_api.txt
-    acx_env_int("ACX_CE_MIN", nullptr, 4 << 20, &v); g_ce_min = std::max(0L, v);
+    acx_env_int("ACX_CE_MIN", nullptr, 64 << 20, &v); g_ce_min = std::max(0L, v);
+    acx_env_int("ACX_WAIT_EARLY_HELPERS", nullptr, 32, &v); g_wait_early_helpers = std::max(0L, v);
+    acx_env_int("ACX_CE_SPINGATE", nullptr, 0, &v); g_ce_spingate = v != 0;
     acx_env_int("ACX_CE_SPIN_US", nullptr, 40, &v); g_ce_spin_us = std::max(0L, v);
     acx_env_int("ACX_CE_SPIN_BUSY_US", nullptr, 300, &v); g_ce_spin_busy_us = std::max(0L, v);
     acx_env_int("ACX_MEMOPS", nullptr, 0, &v); g_memops = v != 0 && !getenv("MPIACX_DISABLE_MEMOPS");   // partitioned Start / Wait as stream memOps (opt-in until measured)
@@ -1392,10 +1397,15 @@ static int launch_sender_ce(Emitter &em, AcxRequest *r, SendParams &sp, char *ds
         }
         cs = it->second;
     }
-    r->ev_trig = event_get(); r->ev_done = event_get();
-    if (!r->ev_trig || !r->ev_done) return MPI_ERR_OTHER;
-    ACX_CUDA(cudaEventRecord(r->ev_trig, em.stream));
-    ACX_CUDA(cudaStreamWaitEvent(cs, r->ev_trig, 0));
+    r->ev_done = event_get();
+    if (!r->ev_done) return MPI_ERR_OTHER;
+    const bool spingate = g_ce_spingate != 0;
+    if (!spingate) {
+        r->ev_trig = event_get();
+        if (!r->ev_trig) return MPI_ERR_OTHER;
+        ACX_CUDA(cudaEventRecord(r->ev_trig, em.stream));
+        ACX_CUDA(cudaStreamWaitEvent(cs, r->ev_trig, 0));
+    }
     Emitter es = em;
     es.stream = cs;
     es.no_pdl = true;   // the gate follows an event wait, the completion kernel a copy: full stream dependencies, nothing programmatic
@@ -1403,6 +1413,7 @@ static int launch_sender_ce(Emitter &em, AcxRequest *r, SendParams &sp, char *ds
     memset(&cp, 0, sizeof cp);
     cp.op = sp.op; cp.ring = sp.ring; cp.sack = sp.sack; cp.ticket = r->hticket; cp.dst_off = dst_off; cp.bytes = bytes;
     cp.depth = sp.depth; cp.peer = sp.peer; cp.wd = sp.wd; cp.tr = sp.tr;
+    cp.serial = spingate ? sp.serial : 0;
     int rc = es.launch(ce_gate, dim3(1), dim3(32), cp);
     if (rc) return rc;
     ACX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, cs));
@@ -2154,6 +2165,7 @@ static void fill_unpack(AcxRequest *r, bool retire, UnpackParams *up) {
 static int plan_wait_grid(WaitBatch &wb, int n) {
     wb.nreq = (uint32_t)n;
     wb.fallback_ns = (uint64_t)g_late_fallback_us * 1000ull;
+    wb.early_release_max = (uint32_t)g_wait_early_helpers;
     int nsend = 0;
     for (int j = 0; j < n; j++) if (wb.w[j].late && !wb.w[j].is_recv) nsend++;
     const size_t unit = 128u << 10;

@@ -360,6 +360,7 @@ struct CeParams {
     acx_sack *sack;          // local
     uint64_t ticket;         // host-predicted ticket of this send
     uint64_t dst_off, bytes; // host-read destination code and message size
+    uint64_t serial;         // != 0: no event orders this kernel behind the send's trigger — wait until the trigger has armed the op record for this request
     uint32_t depth, peer;
     Watchdog wd;
     TraceCtx tr;
@@ -367,6 +368,15 @@ struct CeParams {
 __global__ void ce_gate(CeParams p) {
     pdl_prologue();
     if (threadIdx.x != 0) return;
+    if (p.serial) {   // ACX_CE_SPINGATE: the cross-stream event hop (record + wait, several microseconds on the step's critical path) is replaced by this acquire spin
+        unsigned ns = 0;
+        const uint64_t t0 = p.wd.budget_ns ? globaltimer_ns() : 0;
+        while (ld_acquire_sys(&p.op->armed) != p.serial) {
+            if (ns) __nanosleep(ns);
+            ns = ns < 256 ? ns * 2 + 20 : 256;
+            if (p.wd.budget_ns && globaltimer_ns() - t0 > p.wd.budget_ns) wd_fail(p.wd, 0x5e13, (uint64_t)&p.op->armed, p.serial);
+        }
+    }
     const uint64_t k = p.op->ticket;
     if (k != p.ticket) { wd_fail(p.wd, 0x5e10, k, p.ticket); }   // the host mis-predicted the ticket: the copy behind this kernel would land in the wrong receive's buffer
     const uint32_t e = (uint32_t)(k % p.depth);
@@ -854,6 +864,7 @@ struct WaitBatch {
     TraceCtx tr;
     uint32_t nreq, pad;       // CTAs 0 .. nreq-1 are waiters (one per request); the rest are RNDV_LATE helpers
     uint64_t fallback_ns;     // RNDV_LATE: how long a receive's wait watches an unclaimed message before it pulls it itself
+    uint32_t early_release_max, pad_er;   // helper CTAs up to which the kernel still releases its programmatic dependents early
 };
 
 // late_state = [request serial, 30 bits | ticket + 1, 32 bits | code, 2 bits]: an op record is reused by later requests (which may
@@ -1081,7 +1092,10 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
     // among them the next wait kernel with its few hundred helper CTAs — would become resident at once and sit in
     // griddepcontrol.wait holding registers and thread slots while the mover this kernel waits for starves (measured on
     // B200: the 256-MiB self-ring slowed down in proportion to the helper count and hung at 296; fine with ACX_PDL=0).
-    if (gridDim.x > b.nreq) pdl_wait_only(); else pdl_prologue();
+    // A receive's fallback helpers are few (<= 16 per request): with only those on board the early release is harmless, and
+    // the next step's trigger is resident when this kernel ends instead of a full launch later (device trace of the 256-MiB
+    // ring step: 10 us between wait_end and the next recv_trigger, profiles/ring_step_trace.md).
+    if (gridDim.x > b.nreq + b.early_release_max) pdl_wait_only(); else pdl_prologue();
     if (blockIdx.x < b.nreq) wait_body(b, b.w[blockIdx.x]);
     else late_helper(b, blockIdx.x - b.nreq);
 }

@@ -9,7 +9,7 @@
  *   5. a receive larger than the message, a cudaMalloc'd (registered or bounced) destination, a status;
  *   6. a message larger than the receive (truncation): the record says so, the kernel path reports MPI_ERR_TRUNCATE;
  *   7. a second stream on the channel: the host stops predicting tickets, later messages take the kernel path and arrive.
- * usage: ce_path [bytes]   (default 8 MiB; the emulation matrix passes a small size with ACX_CE_MIN lowered) */
+ * usage: ce_path [bytes]   (default 8 MiB — below the default ACX_CE_MIN of 64 MiB, so the GPU suite sets ACX_CE_MIN; the emulation matrix passes a small size) */
 #include "acx_test.h"
 #include <unistd.h>
 
@@ -36,7 +36,7 @@ int main(int argc, char **argv) {
     verbose = getenv("CE_PATH_VERBOSE") != NULL;
     N = argc > 1 ? (size_t)atoll(argv[1]) : (8u << 20);
     const char *cm = getenv("ACX_CE_MIN");
-    const long ce_min = cm ? atol(cm) : (4 << 20);
+    const long ce_min = cm ? atol(cm) : (64 << 20);
     const int expect_ce = ce_min > 0 && (long)N >= ce_min && !getenv("ACX_SENDER_PUSH") && !getenv("ACX_COOP") && !getenv("ACX_PEER_BRANCH") &&
                           !(getenv("ACX_SIDE_STREAMS") && atoi(getenv("ACX_SIDE_STREAMS")) == 0);
     hbuf = (unsigned char *)malloc(2 * N);

@@ -351,12 +351,20 @@ def test_large_message_sender_moves_protocol(built, np_):
 @pytest.mark.parametrize("np_", [1, 2])
 @pytest.mark.parametrize("ce_min", [4 << 20, 0])
 def test_copy_engine_rendezvous(built, np_, ce_min):
-    """8 MiB messages with the copy-engine rendezvous on (ACX_CE_MIN, default) and off: where the sender's host sees the
+    """8 MiB messages with the copy-engine rendezvous on (ACX_CE_MIN lowered from its 64 MiB default) and off: where the sender's host sees the
     receiver's enqueue-time record of the matching receive the payload travels by cudaMemcpyAsync behind a gate kernel, else by
     the kernel movers; the receive posted first / the send first, free-running ring steps, sizes mixed on one channel, private
     destinations, truncation, a second stream on the channel — tests/c/ce_path.c (the reference's transfers are its MPI's
     copy-engine copies, src/init.cpp:64-80)."""
     r = acxrun(built, np_, built / "build/tests/ce_path", env={"ACX_CE_MIN": str(ce_min)})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+def test_copy_engine_rendezvous_default_threshold(built):
+    """64 MiB messages with the environment untouched: the default configuration takes the copy-engine path (the test program
+    asserts MPIX_Acx_stats::copy_engine_msgs moved) — tests/c/ce_path.c."""
+    r = acxrun(built, 2, built / "build/tests/ce_path", "67108864", env={"ACX_HEAP_BYTES": str(1 << 30)})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
 
