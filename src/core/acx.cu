@@ -89,8 +89,8 @@ static long g_coop_min = 4 << 20;          // ACX_COOP_MIN_BYTES
 static long g_late_min = 4 << 20;          // ACX_LATE_PUSH_MIN: messages from this size up use the sender-moves protocol (RNDV_LATE); 0 = off
 static long g_late_helpers = 0;            // ACX_LATE_HELPERS: helper CTAs all late sends of one wait kernel share (0 = one per SM)
 static long g_ce_min = 64 << 20;           // ACX_CE_MIN: stream-mode messages from this size up travel by copy engine when the sender's host can see the matching receive's enqueue-time record (0 = off); measured break-even with the SM mover on a 2-GPU ring: 64 MiB (profiles/raw/r2_call11/sweep.txt)
-static long g_wait_early_helpers = 32;     // ACX_WAIT_EARLY_HELPERS: a wait kernel with at most this many helper CTAs still releases its programmatic dependents early
-static long g_ce_spingate = 0;             // ACX_CE_SPINGATE: the gate kernel waits for the send's trigger itself (acquire spin on the op record) instead of behind a cross-stream event
+static long g_wait_early_helpers = 0;      // ACX_WAIT_EARLY_HELPERS: a wait kernel with at most this many helper CTAs still releases its programmatic dependents early (measured: no gain on the ring step, profiles/raw/r2_call13/ring.txt — off)
+static long g_ce_spingate = 1;             // ACX_CE_SPINGATE: the gate kernel waits for the send's trigger itself (acquire spin on the op record) instead of behind a cross-stream event
 static long g_ce_spin_us = 40;             // ACX_CE_SPIN_US: how long MPIX_Isend_enqueue looks for that record before it takes the kernel path
 static long g_ce_spin_busy_us = 300;       // ACX_CE_SPIN_BUSY_US: ... when the caller's stream still has work queued (the host is ahead of its GPU: waiting for the neighbour's host costs nothing)
 static long g_late_fallback_us = 50;       // ACX_LATE_FALLBACK_US: grace period before a receive's wait pulls an unclaimed RNDV_LATE message itself
@@ -680,14 +680,15 @@ typedef int (*cuStreamBatchMemOpFn)(CUstream, unsigned int, CUstreamBatchMemOpPa
 static cuStreamBatchMemOpFn g_cuStreamBatchMemOp = nullptr;
 static const size_t kMemOpBatchMax = 256;   // per driver call
 
+static long g_ce_memop = 1;                // ACX_CE_MEMOP: copy-engine sends publish completion with cuStreamWriteValue64 instead of a kernel (1), and also wait for the receive's mirror with cuStreamWaitValue64 instead of the gate kernel (2)
 static void memops_init() {
-    if (!g_memops) return;
+    if (!g_memops && !g_ce_memop) return;
     void *f = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuStreamBatchMemOp", &f, cudaEnableDefault, &q) != cudaSuccess || !f) {
         cudaGetLastError();
         ACX_LOG(1, "ACX_MEMOPS: cuStreamBatchMemOp is not available; using kernels");
-        g_memops = 0;
+        g_memops = 0; g_ce_memop = 0;
         return;
     }
     g_cuStreamBatchMemOp = (cuStreamBatchMemOpFn)f;
@@ -845,8 +846,9 @@ extern "C" int MPIX_Init(void) {
     acx_env_int("ACX_LATE_HELPERS", nullptr, 0, &v); g_late_helpers = std::max(0L, v);
     acx_env_int("ACX_PBATCH", nullptr, 1, &v); g_pbatch = v != 0;   // one launch per MPIX_Startall / MPIX_Waitall group: measured 0.641 vs 0.776 ms per API-level halo step on 2x B200 (reference arm 0.700), profiles/raw/r2_call1/halo_api.txt
     acx_env_int("ACX_CE_MIN", nullptr, 64 << 20, &v); g_ce_min = std::max(0L, v);
-    acx_env_int("ACX_WAIT_EARLY_HELPERS", nullptr, 32, &v); g_wait_early_helpers = std::max(0L, v);
-    acx_env_int("ACX_CE_SPINGATE", nullptr, 0, &v); g_ce_spingate = v != 0;
+    acx_env_int("ACX_WAIT_EARLY_HELPERS", nullptr, 0, &v); g_wait_early_helpers = std::max(0L, v);
+    acx_env_int("ACX_CE_MEMOP", nullptr, 1, &v); g_ce_memop = getenv("MPIACX_DISABLE_MEMOPS") ? 0 : std::max(0L, v);
+    acx_env_int("ACX_CE_SPINGATE", nullptr, 1, &v); g_ce_spingate = v != 0;
     acx_env_int("ACX_CE_SPIN_US", nullptr, 40, &v); g_ce_spin_us = std::max(0L, v);
     acx_env_int("ACX_CE_SPIN_BUSY_US", nullptr, 300, &v); g_ce_spin_busy_us = std::max(0L, v);
     acx_env_int("ACX_MEMOPS", nullptr, 0, &v); g_memops = v != 0 && !getenv("MPIACX_DISABLE_MEMOPS");   // partitioned Start / Wait as stream memOps (opt-in until measured)
@@ -1414,10 +1416,23 @@ static int launch_sender_ce(Emitter &em, AcxRequest *r, SendParams &sp, char *ds
     cp.op = sp.op; cp.ring = sp.ring; cp.sack = sp.sack; cp.ticket = r->hticket; cp.dst_off = dst_off; cp.bytes = bytes;
     cp.depth = sp.depth; cp.peer = sp.peer; cp.wd = sp.wd; cp.tr = sp.tr;
     cp.serial = spingate ? sp.serial : 0;
-    int rc = es.launch(ce_gate, dim3(1), dim3(32), cp);
-    if (rc) return rc;
+    // ACX_CE_MEMOP: the words on both sides of the copy are known on the host (ticket -> slot and generation), so the stream can
+    // wait for the mirror and publish completion in its memOp unit, next to the copy engine's own queue, instead of in kernels.
+    const uint32_t ce_e = (uint32_t)(r->hticket % (uint64_t)sp.depth);
+    const uint64_t ce_g = r->hticket / (uint64_t)sp.depth;
+    int rc = 0;
+    if (g_ce_memop >= 2 && g_cuStreamBatchMemOp && !spingate) {
+        MemOpBatch mb;
+        mb.wait_geq64(&sp.sack[ce_e].r_gen, ce_g + 1);   // the drawn ticket is checked against the prediction by the wait kernel (0x5e0f)
+        if ((rc = mb.flush(cs))) return rc;
+    } else if ((rc = es.launch(ce_gate, dim3(1), dim3(32), cp))) return rc;
     ACX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, cs));
-    if ((rc = es.launch(ce_complete, dim3(1), dim3(32), cp))) return rc;
+    if (g_ce_memop >= 1 && g_cuStreamBatchMemOp) {
+        MemOpBatch mb;
+        mb.write64(&sp.ring[ce_e].done, ce_g + 1);    // receiver may consume (peer-mapped word)
+        mb.write64(&sp.sack[ce_e].sdone, ce_g + 1);   // sender's buffer is reusable
+        if ((rc = mb.flush(cs))) return rc;
+    } else if ((rc = es.launch(ce_complete, dim3(1), dim3(32), cp))) return rc;
     ACX_CUDA(cudaEventRecord(r->ev_done, cs));
     g_acx->st.ce++;
     return 0;

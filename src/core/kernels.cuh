@@ -1092,9 +1092,8 @@ __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {
     // among them the next wait kernel with its few hundred helper CTAs — would become resident at once and sit in
     // griddepcontrol.wait holding registers and thread slots while the mover this kernel waits for starves (measured on
     // B200: the 256-MiB self-ring slowed down in proportion to the helper count and hung at 296; fine with ACX_PDL=0).
-    // A receive's fallback helpers are few (<= 16 per request): with only those on board the early release is harmless, and
-    // the next step's trigger is resident when this kernel ends instead of a full launch later (device trace of the 256-MiB
-    // ring step: 10 us between wait_end and the next recv_trigger, profiles/ring_step_trace.md).
+    // ACX_WAIT_EARLY_HELPERS lets a kernel with only a few (receive-fallback) helpers release early all the same; measured on
+    // the 256-MiB ring step it buys nothing (0.3897 vs 0.3899-0.3903 ms), so the limit is 0 by default.
     if (gridDim.x > b.nreq + b.early_release_max) pdl_wait_only(); else pdl_prologue();
     if (blockIdx.x < b.nreq) wait_body(b, b.w[blockIdx.x]);
     else late_helper(b, blockIdx.x - b.nreq);
