@@ -162,8 +162,11 @@ op.close(); acx.finalize(); print("HALO OK")
     assert r.returncode == 0 and "HALO OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 
-def test_gemm_fp8_matches_torch_reference():
-    """tcgen05 fp8 GEMM vs a plain PyTorch fp32 matmul of the dequantized operands."""
+@pytest.mark.parametrize("pair", [1, 0])
+def test_gemm_fp8_matches_torch_reference(pair):
+    """tcgen05 fp8 GEMM vs a plain PyTorch fp32 matmul of the dequantized operands: the CTA-pair kernel (cta_group::2, shapes
+    with M a multiple of 256) and the single-CTA kernel; 4096x4096x2048 is 256 cluster tiles on 74 clusters (512 tiles on 148
+    CTAs for the single-CTA kernel): the persistent loop, the ring's phase flips and the double-buffered accumulator are covered."""
     script = r"""
 import sys, torch
 sys.path.insert(0, %r)
@@ -171,7 +174,7 @@ import mpi_acx_b200 as acx
 from mpi_acx_b200.ops import gemm_fp8
 acx.init(0)
 torch.manual_seed(5)
-for (M, N, K) in [(128, 256, 128), (256, 512, 1024), (1024, 1024, 4096)]:
+for (M, N, K) in [(128, 256, 128), (256, 512, 1024), (1024, 1024, 4096), (4096, 4096, 2048)]:
     x = torch.randn(M, K, device="cuda").clamp_(-3, 3).to(torch.float8_e4m3fn)
     w = torch.randn(N, K, device="cuda").clamp_(-3, 3).to(torch.float8_e4m3fn)
     scale = 1.0 / K ** 0.5
@@ -186,8 +189,27 @@ for (M, N, K) in [(128, 256, 128), (256, 512, 1024), (1024, 1024, 4096)]:
     assert bad == 0, (M, N, K, bad)
 acx.finalize(); print("GEMM OK")
 """ % str(REPO)
-    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300, env=dict(os.environ, ACX_GEMM_PAIR=str(pair)))
     assert r.returncode == 0 and "GEMM OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.parametrize("pair", [1, 0])
+def test_gemm_fp8_8192_cube_against_double_precision_samples(built, pair):
+    """The benchmarked shape itself: 8192^3, 4096 sampled outputs against a double-precision dot product of the dequantised
+    operands (tests/c/gemm_fp8_test.cu), both kernels."""
+    r = subprocess.run([str(built / "build/tests/gemm_fp8_test"), "8192", "8192", "8192", "3"], capture_output=True, text=True, timeout=200,
+                       env=dict(os.environ, ACX_GEMM_PAIR=str(pair)))
+    assert r.returncode == 0 and "gemm_fp8_test: PASS" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_pipeline_gemm_fused_stages_verify(built, np_):
+    """The GEMM as a pipeline stage (partition-gated TMA producer, epilogue storing into the next stage's input buffer and
+    releasing its partition flags): every stage's last microbatch is checked against a double-precision reference
+    (bench/ppgemm_bench.cu `verify_wrong`); np=2 shares the GPU when only one is present."""
+    r = acxrun(built, np_, built / "bin/ppgemm_bench", "fused", "--m", "2048", "--d", "2048", "--steps", "6", env={"ACX_HEAP_BYTES": str(1 << 30)})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"verify_wrong": 0' in r.stdout, r.stdout[-1000:]
 
 
 @pytest.mark.parametrize("np_", [1, 2])
