@@ -24,7 +24,11 @@
 #include <stdint.h>
 #include <mutex>
 #include <stdlib.h>
+#include <string.h>
 
+#ifndef ACX_GEMM_TMA_STORE_DEFAULT
+#define ACX_GEMM_TMA_STORE_DEFAULT 0
+#endif
 #ifndef ACX_GEMM_PAIR_DEFAULT
 #define ACX_GEMM_PAIR_DEFAULT 1   // the CTA-pair kernel: 3.28 PFLOP/s at 8192^3 against 2.82 for the single-CTA kernel (profiles/gemm_pair_ncu.md)
 #endif
@@ -62,6 +66,8 @@ struct Gating {            // all pointers may be null (= feature off)
 
 struct Params {
     CUtensorMap tmA, tmB;   // X [M][K] and W [N][K], both K-major, box {128 B, BM|BN rows}, SWIZZLE_128B
+    CUtensorMap tmC;        // Y [M][N], box {128 B, 128 rows}, SWIZZLE_128B — used when tma_store is set
+    int tma_store;          // the epilogue hands the staged tile to TMA (two cp.async.bulk.tensor stores per tile) instead of storing it with 128 threads
     uint8_t *out;           // Y [M][N] e4m3 (local or peer-mapped)
     int M, N, K;
     float scale;
@@ -93,6 +99,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *tm, uint64_t *bar
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // the staged tile has been read: the buffer may be overwritten
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }             // the stores have been performed
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_fp8_kernel(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = P.N / BN, tiles_m = P.M / BM, ntiles = tiles_m * tiles_n, kblocks = P.K / BK;
 
-    if (warp == 0 && elect_one()) { tma_prefetch_desc(&P.tmA); tma_prefetch_desc(&P.tmB); }
+    if (warp == 0 && elect_one()) { tma_prefetch_desc(&P.tmA); tma_prefetch_desc(&P.tmB); if (P.tma_store) tma_prefetch_desc(&P.tmC); }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
@@ -239,7 +251,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_fp8_kernel(const __grid_const
             const int tm = t / tiles_n, tn = t % tiles_n;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            // all four warps must be done reading sOut of the previous tile before it is overwritten
+            // all four warps (or the TMA store of the previous tile) must be done reading sOut before it is overwritten
+            if (P.tma_store && threadIdx.x == 128) bulk_wait_read0();
             asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
             for (int c = 0; c < BN / 32; c++) {
@@ -257,32 +270,48 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_fp8_kernel(const __grid_const
                 }
                 // row-major staging, 16-B chunks XOR-swizzled by row so both this write and the read below are conflict-free
                 const int ch0 = 2 * c, ch1 = 2 * c + 1;
-                *reinterpret_cast<uint4 *>(sOut + row * BN + ((ch0 ^ (row & 15)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                *reinterpret_cast<uint4 *>(sOut + row * BN + ((ch1 ^ (row & 15)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                if (P.tma_store) {   // two 128-row x 128-B boxes in the TMA SWIZZLE_128B layout (16-B chunk index XOR row mod 8)
+                    *reinterpret_cast<uint4 *>(sOut + (ch0 >> 3) * (BM * 128) + row * 128 + (((ch0 & 7) ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    *reinterpret_cast<uint4 *>(sOut + (ch1 >> 3) * (BM * 128) + row * 128 + (((ch1 & 7) ^ (row & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                } else {
+                    *reinterpret_cast<uint4 *>(sOut + row * BN + ((ch0 ^ (row & 15)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    *reinterpret_cast<uint4 *>(sOut + row * BN + ((ch1 ^ (row & 15)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                }
             }
             // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (P.tma_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's staging writes before the async proxy's reads
             asm volatile("bar.sync 1, 128;" ::: "memory");      // staging tile complete
             if (!credit_ok) {                                    // next stage still reading the buffer we are about to overwrite?
                 if (threadIdx.x == 128) spin_geq_sys(P.g.credit, P.g.credit_need);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 credit_ok = true;
             }
-            // coalesced write-out: each warp instruction stores two full 256-B rows
-            uint8_t *gout = P.out + (size_t)(tm * BM) * P.N + (size_t)tn * BN;
-            const int et = threadIdx.x - 128;
+            // write-out: TMA (two bulk tensor stores per tile), or coalesced — each warp instruction stores two full 256-B rows
+            if (P.tma_store) {
+                // (the writers' fence.proxy.async sits in front of the "staging tile complete" barrier above)
+                if (threadIdx.x == 128) {
+                    tma_store_2d(&P.tmC, sOut, tn * BN, tm * BM);
+                    tma_store_2d(&P.tmC, sOut + BM * 128, tn * BN + 128, tm * BM);
+                    bulk_commit();
+                    if (P.g.panel_count) bulk_wait0();   // the tile must have landed (at the next stage) before it is counted
+                }
+            } else {
+                uint8_t *gout = P.out + (size_t)(tm * BM) * P.N + (size_t)tn * BN;
+                const int et = threadIdx.x - 128;
 #pragma unroll 4
-            for (int i = 0; i < (BM * BN / 16) / 128; i++) {
-                const int idx = i * 128 + et, r = idx >> 4, ch = idx & 15;
-                const uint4 val = *reinterpret_cast<const uint4 *>(sOut + r * BN + ((ch ^ (r & 15)) << 4));
-                *reinterpret_cast<uint4 *>(gout + (size_t)r * P.N + (ch << 4)) = val;
+                for (int i = 0; i < (BM * BN / 16) / 128; i++) {
+                    const int idx = i * 128 + et, r = idx >> 4, ch = idx & 15;
+                    const uint4 val = *reinterpret_cast<const uint4 *>(sOut + r * BN + ((ch ^ (r & 15)) << 4));
+                    *reinterpret_cast<uint4 *>(gout + (size_t)r * P.N + (ch << 4)) = val;
+                }
             }
             if (P.g.panel_count) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // all stores of this tile issued
+                asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (threadIdx.x == 128) {
-                    __threadfence_system();                      // cumulative over the 128 threads' (remote) stores
+                    __threadfence_system();
                     const int panel = (tm * BM) / P.g.rows_per_panel;
                     const unsigned long long old = atomicAdd(P.g.panel_count + panel, 1ull);
                     if (old + 1 == P.g.panel_target && P.g.out_arrived) {
@@ -293,6 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_fp8_kernel(const __grid_const
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (P.tma_store && threadIdx.x == 128) bulk_wait0();   // shared memory must outlive the last tile's stores
     }
     // ===== teardown =====
     tc_fence_before();
@@ -374,7 +404,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_fp8
     const int tiles_n = P.N / BN, tiles_m2 = P.M / (2 * BM), ntiles = tiles_m2 * tiles_n, kblocks = P.K / BK;
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
-    if (warp == 0 && elect_one()) { tma_prefetch_desc(&P.tmA); tma_prefetch_desc(&P.tmB); }
+    if (warp == 0 && elect_one()) { tma_prefetch_desc(&P.tmA); tma_prefetch_desc(&P.tmB); if (P.tma_store) tma_prefetch_desc(&P.tmC); }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < STAGES2; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
@@ -446,6 +476,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_fp8
             const int tm = 2 * (t / tiles_n) + (int)rank, tn = t % tiles_n;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            if (P.tma_store && threadIdx.x == 128) bulk_wait_read0();
             asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
             for (int c = 0; c < BN / 32; c++) {
@@ -462,25 +493,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_fp8
                     packed[i] = lo | (hi << 16);
                 }
                 const int ch0 = 2 * c, ch1 = 2 * c + 1;
-                *reinterpret_cast<uint4 *>(sOut + row * BN + ((ch0 ^ (row & 15)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                *reinterpret_cast<uint4 *>(sOut + row * BN + ((ch1 ^ (row & 15)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                if (P.tma_store) {   // two 128-row x 128-B boxes in the TMA SWIZZLE_128B layout (16-B chunk index XOR row mod 8)
+                    *reinterpret_cast<uint4 *>(sOut + (ch0 >> 3) * (BM * 128) + row * 128 + (((ch0 & 7) ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    *reinterpret_cast<uint4 *>(sOut + (ch1 >> 3) * (BM * 128) + row * 128 + (((ch1 & 7) ^ (row & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                } else {
+                    *reinterpret_cast<uint4 *>(sOut + row * BN + ((ch0 ^ (row & 15)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    *reinterpret_cast<uint4 *>(sOut + row * BN + ((ch1 ^ (row & 15)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));   // the leader's MMA warp may overwrite this accumulator (in both CTAs) once all 8 warps are here
+            if (P.tma_store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (!credit_ok) {
                 if (threadIdx.x == 128) spin_geq_sys(P.g.credit, P.g.credit_need);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 credit_ok = true;
             }
-            uint8_t *gout = P.out + (size_t)(tm * BM) * P.N + (size_t)tn * BN;
-            const int et = threadIdx.x - 128;
+            if (P.tma_store) {
+                // (the writers' fence.proxy.async sits in front of the "staging tile complete" barrier above)
+                if (threadIdx.x == 128) {
+                    tma_store_2d(&P.tmC, sOut, tn * BN, tm * BM);
+                    tma_store_2d(&P.tmC, sOut + BM * 128, tn * BN + 128, tm * BM);
+                    bulk_commit();
+                    if (P.g.panel_count) bulk_wait0();   // the tile must have landed (at the next stage) before it is counted
+                }
+            } else {
+                uint8_t *gout = P.out + (size_t)(tm * BM) * P.N + (size_t)tn * BN;
+                const int et = threadIdx.x - 128;
 #pragma unroll 4
-            for (int i = 0; i < (BM * BN / 16) / 128; i++) {
-                const int idx = i * 128 + et, r = idx >> 4, ch = idx & 15;
-                const uint4 val = *reinterpret_cast<const uint4 *>(sOut + r * BN + ((ch ^ (r & 15)) << 4));
-                *reinterpret_cast<uint4 *>(gout + (size_t)r * P.N + (ch << 4)) = val;
+                for (int i = 0; i < (BM * BN / 16) / 128; i++) {
+                    const int idx = i * 128 + et, r = idx >> 4, ch = idx & 15;
+                    const uint4 val = *reinterpret_cast<const uint4 *>(sOut + r * BN + ((ch ^ (r & 15)) << 4));
+                    *reinterpret_cast<uint4 *>(gout + (size_t)r * P.N + (ch << 4)) = val;
+                }
             }
             if (P.g.panel_count) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -496,6 +543,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) gemm_fp8
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (P.tma_store && threadIdx.x == 128) bulk_wait0();
     }
     // ===== teardown: neither CTA may leave (or free tensor memory) while the other can still signal its barriers or read its smem =====
     tc_fence_before();
@@ -583,6 +631,12 @@ inline int launch_gemm_fp8(const uint8_t *X, const uint8_t *W, uint8_t *out, int
     Params P;
     if (!cached_tmap_copy(&P.tmA, X, (uint64_t)M, (uint64_t)K, BM) || !cached_tmap_copy(&P.tmB, W, (uint64_t)N, (uint64_t)K, pair ? BN / 2 : BN)) return 4;
     P.out = out; P.M = M; P.N = N; P.K = K; P.scale = scale; P.g = g;
+    // ACX_GEMM_TMA_STORE: 1 = TMA-store epilogue for local outputs, 2 = also when the output is the next pipeline stage's input buffer (peer memory)
+    static int tma_store_mode = -1;
+    if (tma_store_mode < 0) { const char *e = getenv("ACX_GEMM_TMA_STORE"); tma_store_mode = e ? atoi(e) : ACX_GEMM_TMA_STORE_DEFAULT; }
+    P.tma_store = (tma_store_mode >= 2 || (tma_store_mode == 1 && !g.out_arrived)) ? 1 : 0;
+    memset(&P.tmC, 0, sizeof P.tmC);
+    if (P.tma_store && !cached_tmap_copy(&P.tmC, out, (uint64_t)M, (uint64_t)N, BM)) return 4;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_fp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return 5;

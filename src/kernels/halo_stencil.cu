@@ -34,9 +34,15 @@
 #include <vector>
 #include <algorithm>
 
+#ifndef ACX_HALO_TILE16_DEFAULT
+#define ACX_HALO_TILE16_DEFAULT 0
+#endif
+
 namespace {
 
-constexpr int TY = 8, TZ = 32;      // tile: TY rows x all of x, z-march of TZ planes
+// tile: TY rows x all of x, z-march of TZ planes. Two geometries are compiled: 8 x 32 (8 compute warps + the producer warp: nine
+// warps are allocated as twelve, so 108 registers leave room for ONE CTA per SM) and 16 x 16 (16 compute warps + the producer warp
+// in one CTA per SM at 96 registers: twice the warps to hide the math's latency behind, ACX_HALO_TILE=16).
 constexpr int STAGES = 8;           // shared-memory ring of planes (8 x 10.6 KB per CTA, two CTAs per SM)
 constexpr int XPAD = 16;            // pad cells behind every row (see the layout comment above)
 
@@ -50,6 +56,7 @@ struct HaloDev {
     unsigned long long wait_val, signal_val;
     float c0, c1;
     const int *order;
+    const unsigned char *in_box0;   // != null (ACX_HALO_BULK=1): address of box (0, 0, 0) of the INPUT field — a box is one contiguous run of memory, so it can travel as a 1-D bulk copy instead of a 3-D tensor box
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,6 +72,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra.uni HW_LOOP;\n\t"
         "HW_DONE:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(const void *src, uint64_t *bar, void *dst, uint32_t bytes) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap *tm, uint64_t *bar, void *dst, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -107,7 +118,8 @@ __device__ __forceinline__ uint4 stencil8(const float2 cur[4], const float2 ym[4
 // Thread (rp, vx) owns rows 2*rp and 2*rp+1 of the tile's TY rows and the 8 cells vx*8 .. vx*8+7: two vectors per plane,
 // each the other's y-neighbour (registers), so a plane costs 4 LDS.128 per thread: the two next-plane centres, the row
 // above the pair and the row below it.
-__global__ void __maxnreg__(112) halo_stencil_tma(const __grid_constant__ CUtensorMap tm, HaloDev P) {
+template <int TY, int TZ>
+__device__ __forceinline__ void halo_stencil_body(const CUtensorMap &tm, const HaloDev &P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int ncw = (int)(blockDim.x >> 5) - 1;                  // compute warps; the last warp is the producer
@@ -170,7 +182,8 @@ __global__ void __maxnreg__(112) halo_stencil_tma(const __grid_constant__ CUtens
                 mbar_wait(&empty[p_stage], p_par);                 // every compute warp is done with the stage's previous plane
                 mbar_expect_tx(&full[p_stage], stage_bytes);
                 // box origin in the padded tensor: u64 column 0 (= 16 B before the interior row), padded row ty*TY, padded plane tc*TZ + q
-                tma_load_3d(&tm, &full[p_stage], smem + (size_t)p_stage * stage_stride, 0, ty * TY, tc * TZ + q);
+                if (P.in_box0) bulk_load_1d(P.in_box0 + ((long long)(tc * TZ + q) * P.pp + (long long)(ty * TY) * P.rp) * 2, &full[p_stage], smem + (size_t)p_stage * stage_stride, stage_bytes);
+                else tma_load_3d(&tm, &full[p_stage], smem + (size_t)p_stage * stage_stride, 0, ty * TY, tc * TZ + q);
                 if (++p_stage == STAGES) { p_stage = 0; p_par ^= 1u; }
                 if ((q & 7) == 7 && sig_no < loaded_tiles) try_signal(false);
             }
@@ -263,17 +276,21 @@ __global__ void __maxnreg__(112) halo_stencil_tma(const __grid_constant__ CUtens
     }
 }
 
+__global__ void __maxnreg__(112) halo_stencil_tma(const __grid_constant__ CUtensorMap tm, HaloDev P) { halo_stencil_body<8, 32>(tm, P); }
+__global__ void __maxnreg__(96) halo_stencil_tma16(const __grid_constant__ CUtensorMap tm, HaloDev P) { halo_stencil_body<16, 16>(tm, P); }
+
 // Initial exchange: faces of u^0 -> the neighbours' ghost cells of the SAME field, flag value 1 on the parity-0 channels.
 // One CTA per (face, partition).
 struct PackDev {
     const __nv_bfloat16 *u;         // interior origin of the local current field
     __nv_bfloat16 *nb[6];           // neighbours' interior origins of THEIR current field
-    int nx, ny, nz, nty, ntz;
+    int nx, ny, nz, nty, ntz, TY, TZ;
     long long rp, pp;
     const acx_pchan *send[6];
     unsigned long long signal_val;
 };
 __global__ void halo_pack_faces(PackDev P) {
+    const int TY = P.TY, TZ = P.TZ;
     const int f = blockIdx.y, p = blockIdx.x;
     const int nparts = f < 2 ? P.nty * P.ntz : f < 4 ? P.ntz : P.nty;
     if (p >= nparts) return;
@@ -337,7 +354,7 @@ EncodeTiledFn encode_fn() {
 
 struct acx_halo {
     int nx, ny, nz, px, py, pz, rank, size;
-    int nty, ntz, ntiles;
+    int nty, ntz, ntiles, ty, tz;  // ty x tz: tile geometry (rows, planes)
     long long rp, pp;              // pitches in cells
     size_t field_bytes;
     float c0, c1;
@@ -352,7 +369,7 @@ struct acx_halo {
     MPIX_Request sreq[2][6], rreq[2][6];
     MPIX_Prequest spre[2][6], rpre[2][6];
     int *order_d;
-    int grid, threads;
+    int grid, threads, bulk;
     size_t smem;
 };
 
@@ -364,8 +381,12 @@ extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, f
     MPI_Comm_rank(MPI_COMM_WORLD, &rank);
     MPI_Comm_size(MPI_COMM_WORLD, &size);
     if (px * py * pz != size) { fprintf(stderr, "[acx halo] decomposition %dx%dx%d != %d ranks\n", px, py, pz, size); return 1; }
+    const char *tile_env = getenv("ACX_HALO_TILE");
+    const int tile16 = tile_env ? atoi(tile_env) == 16 : ACX_HALO_TILE16_DEFAULT;
+    const int TY = tile16 ? 16 : 8, TZ = tile16 ? 16 : 32;
     if ((nx != 256 && nx != 512) || ny % TY || nz % TZ) { fprintf(stderr, "[acx halo] block %dx%dx%d: nx must be 256 or 512 (one thread per 8 cells, %d rows per CTA), ny a multiple of %d, nz of %d\n", nx, ny, nz, TY, TY, TZ); return 1; }
     acx_halo *h = new acx_halo();
+    h->ty = TY; h->tz = TZ;
     h->nx = nx; h->ny = ny; h->nz = nz; h->px = px; h->py = py; h->pz = pz; h->rank = rank; h->size = size; h->c0 = c0; h->c1 = c1;
     h->nty = ny / TY; h->ntz = nz / TZ; h->ntiles = h->nty * h->ntz;
     h->rp = nx + XPAD; h->pp = h->rp * (ny + 2);
@@ -397,7 +418,7 @@ extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, f
         char *base = h->alloc[b] + (size_t)h->rp * 2 - 16;
         cuuint64_t dims[3] = {(cuuint64_t)(h->rp / 4), (cuuint64_t)(ny + 2), (cuuint64_t)(nz + 2)};
         cuuint64_t strides[2] = {(cuuint64_t)h->rp * 2, (cuuint64_t)h->pp * 2};
-        cuuint32_t box[3] = {(cuuint32_t)(h->rp / 4), (cuuint32_t)(TY + 2), 1};
+        cuuint32_t box[3] = {(cuuint32_t)(h->rp / 4), (cuuint32_t)(h->ty + 2), 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&h->tm[b], CU_TENSOR_MAP_DATA_TYPE_INT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -427,14 +448,15 @@ extern "C" int acx_halo_create(int nx, int ny, int nz, int px, int py, int pz, f
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nfaces(a) > nfaces(b); });
     HCK(cudaMalloc((void **)&h->order_d, sizeof(int) * h->ntiles));
     HCK(cudaMemcpy(h->order_d, order.data(), sizeof(int) * h->ntiles, cudaMemcpyHostToDevice));
-    h->threads = nx / 8 * (TY / 2) + 32;   // two rows per thread, plus the producer warp
-    h->smem = (size_t)STAGES * ((((size_t)(TY + 2) * (size_t)h->rp * 2) + 127) & ~(size_t)127) + (2 * STAGES + 2) * 8 + 16;
-    HCK(cudaFuncSetAttribute(halo_stencil_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    h->threads = nx / 8 * (h->ty / 2) + 32;   // two rows per thread, plus the producer warp
+    h->smem = (size_t)STAGES * ((((size_t)(h->ty + 2) * (size_t)h->rp * 2) + 127) & ~(size_t)127) + (2 * STAGES + 2) * 8 + 16;
+    HCK(cudaFuncSetAttribute(h->ty == 16 ? halo_stencil_tma16 : halo_stencil_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, halo_stencil_tma, h->threads, h->smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->ty == 16 ? halo_stencil_tma16 : halo_stencil_tma, h->threads, h->smem);
     if (occ < 1) occ = 1;
+    h->bulk = getenv("ACX_HALO_BULK") && atoi(getenv("ACX_HALO_BULK")) != 0;
     const char *g = getenv("ACX_HALO_CTAS_PER_SM");
     if (g && atoi(g) > 0) occ = std::min(occ, atoi(g));
     // equal-size tiles: a grid that does not divide them leaves most CTAs idle during the last wave (1024 tiles on 296 CTAs:
@@ -462,7 +484,7 @@ extern "C" int acx_halo_export_dense(acx_halo *h, void *dense, cudaStream_t stre
 
 extern "C" int acx_halo_exchange_initial(acx_halo *h, cudaStream_t stream) {
     PackDev P;
-    P.u = h->u[h->cur]; P.nx = h->nx; P.ny = h->ny; P.nz = h->nz; P.nty = h->nty; P.ntz = h->ntz; P.rp = h->rp; P.pp = h->pp;
+    P.u = h->u[h->cur]; P.nx = h->nx; P.ny = h->ny; P.nz = h->nz; P.nty = h->nty; P.ntz = h->ntz; P.TY = h->ty; P.TZ = h->tz; P.rp = h->rp; P.pp = h->pp;
     const int par = (int)(h->step & 1);
     for (int f = 0; f < 6; f++) { P.send[f] = (const acx_pchan *)h->spre[par][f]; P.nb[f] = h->nbu[h->cur][f]; }
     P.signal_val = h->step + 1;
@@ -488,7 +510,9 @@ extern "C" int acx_halo_step(acx_halo *h, int nsteps, cudaStream_t stream) {
         for (int f = 0; f < 6; f++) { P.recv[f] = (const acx_pchan *)h->rpre[rp][f]; P.send[f] = (const acx_pchan *)h->spre[sp][f]; }
         P.wait_val = h->step + 1; P.signal_val = h->step + 2;
         P.c0 = h->c0; P.c1 = h->c1; P.order = h->order_d;
-        halo_stencil_tma<<<h->grid, h->threads, h->smem, stream>>>(h->tm[cur], P);
+        P.in_box0 = h->bulk ? (const unsigned char *)h->alloc[cur] + (size_t)h->rp * 2 - 16 : nullptr;
+        if (h->ty == 16) halo_stencil_tma16<<<h->grid, h->threads, h->smem, stream>>>(h->tm[cur], P);
+        else halo_stencil_tma<<<h->grid, h->threads, h->smem, stream>>>(h->tm[cur], P);
         HCK(cudaGetLastError());
         h->cur ^= 1;
         h->step++;

@@ -110,8 +110,10 @@ def test_more_receives_outstanding_than_the_ring_is_deep(built, np_):
     assert "PASS" in r.stdout and "device transport" in r.stdout
 
 
-def test_halo_stencil_matches_torch_reference():
-    """Fused halo+stencil kernel on one GPU (periodic self-exchange) vs the plain PyTorch fp32 reference."""
+@pytest.mark.parametrize("tile", [8, 16])
+def test_halo_stencil_matches_torch_reference(tile):
+    """Fused halo+stencil kernel on one GPU (periodic self-exchange) vs the plain PyTorch fp32 reference; both tile
+    geometries (ACX_HALO_TILE: 8 rows x 32 planes, 16 x 16)."""
     script = r"""
 import sys, torch
 sys.path.insert(0, %r)
@@ -131,11 +133,12 @@ print("max abs err", err)
 assert err <= 0.02, err
 op.close(); acx.finalize(); print("HALO OK")
 """ % str(REPO)
-    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300, env=dict(os.environ, ACX_WATCHDOG_MS="30000"))
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300, env=dict(os.environ, ACX_WATCHDOG_MS="30000", ACX_HALO_TILE=str(tile)))
     assert r.returncode == 0 and "HALO OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 
-def test_halo_stencil_many_tiles_per_cta_matches_torch_reference():
+@pytest.mark.parametrize("tile", [8, 16])
+def test_halo_stencil_many_tiles_per_cta_matches_torch_reference(tile):
     """512 x 384 x 256 block: 384 tiles over 296 resident CTAs, so CTAs run the TMA plane stream straight through tile
     boundaries (the producer prefetches the next tile's planes while the current one is still being computed), every
     face is 48 / 8 partitions wide, and 3 steps exercise both field parities — against the PyTorch fp32 reference."""
@@ -158,7 +161,7 @@ print("max abs err", err)
 assert err <= 0.02, err
 op.close(); acx.finalize(); print("HALO OK")
 """ % str(REPO)
-    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300, env=dict(os.environ, ACX_WATCHDOG_MS="30000", ACX_HEAP_BYTES=str(1 << 30)))
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300, env=dict(os.environ, ACX_WATCHDOG_MS="30000", ACX_HEAP_BYTES=str(1 << 30), ACX_HALO_TILE=str(tile)))
     assert r.returncode == 0 and "HALO OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 

@@ -346,8 +346,11 @@ def test_hot_kernels_keep_their_register_budget(built):
     assert find("gemm_fp8_kernel")[1] == 0
     regs, stack = find("11wait_kernelE")
     assert regs <= 64 and stack == 0, (regs, stack)
-    regs, stack = find("halo_stencil_tma")   # two 256-thread CTAs per SM, two rows per thread; the TMA ring, not registers, holds the data in flight
+    regs, stack = find("halo_stencil_tmaE")   # 8 x 32 tiles: 288 threads, two rows per thread; the TMA ring, not registers, holds the data in flight
     assert regs <= 128 and stack == 0, (regs, stack)
+    regs, stack = find("halo_stencil_tma16E")   # 16 x 16 tiles: 17 warps are allocated as 20, so 96 registers is the most one CTA of 544 threads can have
+    assert regs <= 96, (regs, stack)
+    assert find("gemm_fp8_pair_kernel")[1] == 0
 
 
 def test_halo_kernel_is_tma_fed(built):

@@ -90,7 +90,11 @@ if [ "$mode" = full ]; then
         run ldst256 2 $p ACX_MOVER=ldst256
         run ldstcs 2 $p ACX_MOVER=ldstcs
         run mover-block 2 $p ACX_MOVER_BLOCK=4096
-        [ $p = threads ] || run depth8-chan2 2 $p ACX_DEPTH=8 ACX_NCHAN=2   # threads.c needs one channel per thread (tags that collide modulo ACX_NCHAN share a FIFO)
+        # a small ring and a single exact channel + the overflow FIFO. Not for threads.c (one channel per thread), nor for programs
+        # that keep more than 8 sends un-consumed on one channel: a send's trigger waits for slot credit on its stream (DESIGN.md
+        # "sends in flight per channel are bounded by the ring depth"), so status_errors.c (30 requests up front) needs the
+        # default depth and large_msgs.c its tags on separate channels
+        case $p in threads|status_errors) ;; large_msgs) run depth8-chan4 2 $p ACX_DEPTH=8 ACX_NCHAN=4 ;; *) run depth8-chan2 2 $p ACX_DEPTH=8 ACX_NCHAN=2 ;; esac
         run eager64 3 $p ACX_EAGER_MAX=64
         run no-regcache 2 $p ACX_REGCACHE=0
         run fuse-any-grid 2 $p ACX_FUSE_MIN_CTAS=1 ACX_EMU_SMS=16
