@@ -27,7 +27,7 @@
 #include <string.h>
 
 #ifndef ACX_GEMM_TMA_STORE_DEFAULT
-#define ACX_GEMM_TMA_STORE_DEFAULT 0
+#define ACX_GEMM_TMA_STORE_DEFAULT 1   // local outputs go out by TMA; 2 = the next stage's buffer too
 #endif
 #ifndef ACX_GEMM_PAIR_DEFAULT
 #define ACX_GEMM_PAIR_DEFAULT 1   // the CTA-pair kernel: 3.28 PFLOP/s at 8192^3 against 2.82 for the single-CTA kernel (profiles/gemm_pair_ncu.md)
