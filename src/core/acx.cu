@@ -160,6 +160,7 @@ static void report_watchdog() {
             case 0x5e11: what = "copy-engine send: the matching receive (enqueued by its host) was never posted on the device"; break;
             case 0x5e12: what = "copy-engine send: the receive's device-side destination (a) is not the one its host published (b), or it is too small"; break;
             case 0x5e13: what = "copy-engine send: the send's trigger never ran (gate kernel without an event, ACX_CE_SPINGATE)"; break;
+            case 0x5e14: what = "wait kernel: helper CTAs never checked out (a = helpers, b = checked out)"; break;
             case 0x5e0e: what = "wait kernel helper: the request's waiter CTA never decided (a = ticket, b = state word)"; break;
         }
         ACX_ERR("WATCHDOG (code 0x%llx, a=0x%llx b=0x%llx): %s", (unsigned long long)g_diag[0], (unsigned long long)g_diag[1],

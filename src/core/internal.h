@@ -78,6 +78,7 @@ struct alignas(64) acx_op {  // per request slot, local
     uint64_t fused_decided;  // single-launch rendezvous gate: 1 once CTA 0 has published the match of this launch
     uint64_t coop;       // this message is moved cooperatively (kind RNDV_COOP): the mover claims chunks from the slot's cursor
     uint64_t late_state; // RNDV_LATE at wait time: ((ticket + 1) << 2) | 1 nothing to move here / 2 move now (n, peer_ptr valid); written by the waiter CTA, polled by the helper CTAs
+    uint64_t helpers_out; // helper CTAs of the current wait kernel that are done with this record; the waiter CTA retires the slot only when all of them are (and resets the count)
 };
 
 struct acx_anyres {  // resolution of a wildcard receive (device memory, one per request slot): which ring the matched message sits in

@@ -1031,9 +1031,29 @@ __device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) 
         }
     }
     if (tid == 0) {
+        if (w.late && w.help_n) {
+            // The helper CTAs of this request read the op record (ticket, decision word, source / destination) — and a helper may
+            // be scheduled late. Once this CTA says "retired" the host hands the slot to the next request, whose trigger (with
+            // several application threads: on another stream) rewrites the record: a helper that only starts then never sees its
+            // decision and spins for good (ThreadSanitizer on the software device: tests/c/threads.c with large messages). So the
+            // slot is not retired before every helper has checked out.
+            unsigned ns = 0;
+            const uint64_t t0 = b.wd.budget_ns ? globaltimer_ns() : 0;
+            while (ld_acquire_sys(&op->helpers_out) < (uint64_t)w.help_n) {
+                if (ns) __nanosleep(ns);
+                ns = ns < 256 ? ns * 2 + 20 : 256;
+                if (b.wd.budget_ns && globaltimer_ns() - t0 > b.wd.budget_ns) wd_fail(b.wd, 0x5e14, (uint64_t)w.help_n, ld_relaxed_sys(&op->helpers_out));
+            }
+            st_relaxed_sys(&op->helpers_out, 0);   // the next wait kernel on this record (next owner, or a relaunch of this graph) counts from zero
+        }
         if (w.retire) ACX_HOST_FLAG_SET(&w.hstat->retired, 1);
         trace(b.tr, ACX_EV_WAIT_END, w.src, op->ticket, s_n);
     }
+}
+// A helper CTA's last access to the op record (thread 0, after the CTA's other threads are done with it).
+__device__ __forceinline__ void helper_checkout(acx_op *op) {
+    __threadfence();
+    atomicAdd((unsigned long long *)&op->helpers_out, 1ull);
 }
 // RNDV_LATE helper CTAs of a wait kernel: they idle (on a LOCAL word) until the request's waiter CTA has decided, then
 // either leave or move the payload — a send's helpers push (STG over NVLink), a receive's fallback helpers pull. Static
@@ -1061,7 +1081,7 @@ __device__ __forceinline__ void late_helper(const WaitBatch &b, unsigned h) {
         s_state = st; s_k = k;
     }
     __syncthreads();
-    if ((s_state & 3ull) != 2ull) return;
+    if ((s_state & 3ull) != 2ull) { if (threadIdx.x == 0) helper_checkout(op); return; }
     const uint64_t n = op->n, k = s_k;
     char *peer = (char *)op->peer_ptr;
     const unsigned rank = h - w.help_lo, nh = w.help_n;
@@ -1085,6 +1105,7 @@ __device__ __forceinline__ void late_helper(const WaitBatch &b, unsigned h) {
             st_release_sys(&w.sack[e].sdone, g + 1);
             trace(b.tr, ACX_EV_MOVE_END, (uint32_t)w.src, k, n);
         }
+        helper_checkout(op);   // after the barrier above: every thread of this CTA has read what it needed from the record
     }
 }
 __global__ void __launch_bounds__(kWaitThreads) wait_kernel(WaitBatch b) {

@@ -225,8 +225,24 @@ void jitter() {
     timespec ts{0, (long)(x % (unsigned)max_us) * 1000};
     nanosleep(&ts, nullptr);
 }
+// ACX_EMU_HW_QUEUES=n: the hardware's work queues. A GPU takes work from a few queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by
+// default) onto which the driver maps all streams of a process, and a queue is strictly in order: an entry is handed to the
+// device only when the entries in front of it have been, and an entry whose own stream predecessor has not finished yet (a
+// kernel behind a spinning kernel of the same stream, an event or memOp wait that is not satisfied) holds up everything queued
+// behind it — operations of OTHER streams included. That false dependency turns "two threads, two streams, each waiting for a
+// message" into a deadlock across ranks when the streams share a queue (tests/c/threads.c on hardware).
+// Streams are assigned round-robin in creation order; 0 (default) = every stream has its own queue.
+struct HwQueue { std::mutex mu; std::condition_variable cv; uint64_t tail = 0, started = 0; };
+std::vector<HwQueue *> &hw_queues() {
+    static std::vector<HwQueue *> qs = [] { std::vector<HwQueue *> v; const long n = env_long("ACX_EMU_HW_QUEUES", 0); for (long i = 0; i < n; i++) v.push_back(new HwQueue()); return v; }();
+    return qs;
+}
+bool holds_hw_queue(const char *what) { return !strcmp(what, "event-wait") || !strcmp(what, "batch-memop"); }   // semaphore acquires: the queue stalls AT them until they are satisfied
+
 struct Stream {
     static constexpr size_t kMaxQueued = 192;
+    HwQueue *hwq = nullptr;
+    std::deque<uint64_t> hw_seq;   // queue position of each pending operation (parallel to q)
     unsigned flags = 0;
     bool is_null = false;
     int dev = 0;            // the device that was current when the stream was created
@@ -252,8 +268,18 @@ struct Stream {
                 t = std::move(q.front().second);
                 q.pop_front();
             }
+            uint64_t hw_pos = 0;
+            bool hw_hold = false;
+            if (hwq) {
+                { std::lock_guard<std::mutex> lk(mu); hw_pos = hw_seq.front(); hw_seq.pop_front(); }
+                hw_hold = holds_hw_queue(running);
+                std::unique_lock<std::mutex> lk(hwq->mu);
+                hwq->cv.wait(lk, [&] { return hwq->started + 1 == hw_pos; });   // everything in front of it in the queue has been handed to the device
+                if (!hw_hold) { hwq->started = hw_pos; hwq->cv.notify_all(); }
+            }
             jitter();
             t();
+            if (hwq && hw_hold) { std::lock_guard<std::mutex> lk(hwq->mu); hwq->started = hw_pos; hwq->cv.notify_all(); }
             {
                 std::lock_guard<std::mutex> lk(mu);
                 completed++;
@@ -268,6 +294,7 @@ struct Stream {
             // like the hardware's launch queue, a stream takes a bounded number of pending operations; the host blocks beyond
             std::unique_lock<std::mutex> lk(mu);
             cv_done.wait(lk, [&] { return q.size() < kMaxQueued; });
+            if (hwq) { std::lock_guard<std::mutex> hl(hwq->mu); hw_seq.push_back(++hwq->tail); }   // position in the hardware queue = host enqueue order
             q.emplace_back(what, std::move(t));
             n = ++submitted;
         }
@@ -297,6 +324,7 @@ Stream *g_null = nullptr;
 Stream *new_stream(unsigned flags, bool is_null) {
     Stream *s = new Stream();
     s->flags = flags; s->is_null = is_null; s->dev = t_dev;
+    { static std::atomic<unsigned> created{0}; auto &qs = hw_queues(); if (!qs.empty()) s->hwq = qs[created.fetch_add(1) % qs.size()]; }
     s->th = std::thread([s] { s->worker(); });
     std::lock_guard<std::mutex> lk(g_streams_mu);
     g_streams.insert(s);
