@@ -53,6 +53,9 @@ lrun late-no-fallback-grace 2 late_push $LATE ACX_LATE_FALLBACK_US=0
 lrun late-jitter 3 late_push $LATE ACX_FAULT_DELAY_US=300
 lrun late-no-side-streams 2 late_push $LATE ACX_SIDE_STREAMS=0
 for p in large_msgs ring_all_device ring_all_graph graph_large ordering stress status_errors threads regcache; do
+    # (ThreadSanitizer, threads.c: two pushes of different application threads into one recycled peer address are ordered through
+    # the receiving process, which a one-process sanitizer cannot see — checked at np=1 there, as for sender-push above)
+    if [ "$mode" = tsan ] && [ $p = threads ]; then run late 1 $p $LATE; run late-jitter 1 $p $LATE ACX_FAULT_DELAY_US=200; continue; fi
     run late 2 $p $LATE
     run late-jitter 3 $p $LATE ACX_FAULT_DELAY_US=200
 done
