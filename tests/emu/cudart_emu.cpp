@@ -233,9 +233,9 @@ void jitter() {
 // message" into a deadlock across ranks when the streams share a queue (tests/c/threads.c on hardware).
 // Streams are assigned round-robin in creation order; 0 (default) = every stream has its own queue.
 struct HwQueue { std::mutex mu; std::condition_variable cv; uint64_t tail = 0, started = 0; };
-std::vector<HwQueue *> &hw_queues() {
-    static std::vector<HwQueue *> qs = [] { std::vector<HwQueue *> v; const long n = env_long("ACX_EMU_HW_QUEUES", 0); for (long i = 0; i < n; i++) v.push_back(new HwQueue()); return v; }();
-    return qs;
+std::vector<HwQueue *> &hw_queues() {   // never destroyed: stream workers may outlive static destructors, and the queues stay reachable for LeakSanitizer
+    static std::vector<HwQueue *> *qs = [] { auto *v = new std::vector<HwQueue *>(); const long n = env_long("ACX_EMU_HW_QUEUES", 0); for (long i = 0; i < n; i++) v->push_back(new HwQueue()); return v; }();
+    return *qs;
 }
 bool holds_hw_queue(const char *what) { return !strcmp(what, "event-wait") || !strcmp(what, "batch-memop"); }   // semaphore acquires: the queue stalls AT them until they are satisfied
 
