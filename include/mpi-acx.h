@@ -123,6 +123,7 @@ typedef struct MPIX_Acx_stats {
     unsigned long long slots_in_use, slots_high_water;
     unsigned long long heap_bytes_in_use, heap_bytes_high_water;
     unsigned long long copy_engine_msgs;   /* rendezvous messages moved by cudaMemcpyAsync (ACX_CE_MIN) */
+    unsigned long long overflow_sends;     /* sends whose trigger waited for its ring slot on a pool stream (more than ACX_DEPTH un-waited sends on one channel) */
 } MPIX_Acx_stats;
 int MPIX_Get_stats(MPIX_Acx_stats *stats);
 /* 1 when the GPU transport is active, 0 when running on the host (no-GPU) transport. */

@@ -36,7 +36,7 @@ class AcxStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_ulonglong) for n in (
         "sends_enqueued", "recvs_enqueued", "waits_enqueued", "bytes_sent", "bytes_received", "eager_msgs",
         "rendezvous_msgs", "bounce_copies", "kernels_launched", "graph_nodes_added", "slots_in_use",
-        "slots_high_water", "heap_bytes_in_use", "heap_bytes_high_water", "copy_engine_msgs")]
+        "slots_high_water", "heap_bytes_in_use", "heap_bytes_high_water", "copy_engine_msgs", "overflow_sends")]
 
 
 def build_native(force: bool = False) -> None:

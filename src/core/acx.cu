@@ -79,6 +79,8 @@ static cudaStream_t host_stream() {
 static int g_mover_tma = 0, g_mover_256 = 0, g_mover_block = 0;   // g_mover_block: interleaved block size in bytes (ACX_MOVER_BLOCK; 0 = one chunk per CTA)
 static int g_apush = 0;                   // deterministic large-message mode: the sender always pushes, gated on its per-channel stream (ACX_SENDER_PUSH)
 static std::map<std::pair<int, int>, cudaStream_t> g_chan_streams;   // (peer, channel) -> stream for sender-push movers
+struct OverflowStream { cudaStream_t s; AcxRequest *owner; };
+static std::vector<OverflowStream> g_ovf_pool;   // pool streams of overflow sends (send_overflow_begin); guarded by g_acx->mu
 static int g_side_on = 1;                 // run large movers on per-peer side streams so transfers to different peers overlap (ACX_SIDE_STREAMS)
 static std::vector<cudaStream_t> g_side;  // side streams, indexed by peer % size
 static int g_wild = 0;                    // ACX_WILDCARDS: MPI_ANY_SOURCE / MPI_ANY_TAG receives on the device transport (experimental; matched at wait time)
@@ -97,6 +99,8 @@ static long g_late_fallback_us = 50;       // ACX_LATE_FALLBACK_US: grace period
 static int g_pbatch = 1;                  // ACX_PBATCH (default on since round 2): one kernel launch per MPIX_Startall / MPIX_Waitall group of partitioned requests instead of one per request
 static int g_branch = 2;                  // ACX_PEER_BRANCH: run every operation with a peer on that peer's side stream (fork at enqueue, join at the wait): 0 never, 1 always, 2 (default) while the stream is capturing — there the forks are graph edges and cost nothing at run time
 static int g_fuse_rndv = 1, g_fuse_min_ctas = 8, g_fuse_max_ctas = 32;   // single-launch rendezvous for grids up to this many CTAs (ACX_FUSE_RNDV, ACX_FUSE_MAX_CTAS)
+static long g_send_overflow_max = 128;   // ACX_SEND_OVERFLOW_MAX: overflow sends that may be waiting for ring slots at one time, over all channels (each has a pool stream to itself while it waits)
+static int g_send_overflow = 1;   // ACX_SEND_OVERFLOW: the triggers of stream-mode sends beyond a ring's worth of un-waited sends on one channel run on pool streams instead of holding up the caller's (send_overflow_begin)
 static int g_pdl = 1;   // programmatic dependent launch between consecutive acx kernels on a stream (ACX_PDL)
 static bool g_nvtx = false;
 struct AcxRange {
@@ -161,6 +165,8 @@ static void report_watchdog() {
             case 0x5e12: what = "copy-engine send: the receive's device-side destination (a) is not the one its host published (b), or it is too small"; break;
             case 0x5e13: what = "copy-engine send: the send's trigger never ran (gate kernel without an event, ACX_CE_SPINGATE)"; break;
             case 0x5e14: what = "wait kernel: helper CTAs never checked out (a = helpers, b = checked out)"; break;
+            case 0x5e15: what = "overflow send: the channel's ticket counter never reached the ticket the host counted for it (b)"; break;
+            case 0x5e16: what = "overflow send: the ticket the host counted (a) was drawn by another send (counter at b)"; break;
             case 0x5e0e: what = "wait kernel helper: the request's waiter CTA never decided (a = ticket, b = state word)"; break;
         }
         ACX_ERR("WATCHDOG (code 0x%llx, a=0x%llx b=0x%llx): %s", (unsigned long long)g_diag[0], (unsigned long long)g_diag[1],
@@ -207,7 +213,10 @@ static cudaEvent_t event_get() {
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return e;
 }
+static void send_flow_release(AcxRequest *r);   // sends in flight per channel (send_overflow_begin)
+static void send_flow_forget(AcxRequest *r);
 static void release_request_resources(AcxRequest *r) {
+    send_flow_forget(r);
     if (r->bounce_off >= 0) { acx_heap_free(r->bounce_off); r->bounce_off = -1; }
     if (r->ev_trig) { g_event_pool.push_back(r->ev_trig); r->ev_trig = nullptr; }
     if (r->ev_done) { g_event_pool.push_back(r->ev_done); r->ev_done = nullptr; }
@@ -229,6 +238,7 @@ void acx_slot_free(int slot) {
     // caller holds g_acx->mu
     AcxRequest *r = g_acx->slot_req[slot];
     if (r) {
+        send_flow_release(r);   // a send released without a wait (error exits)
         release_request_resources(r);
         r->magic = 0;
         delete r;
@@ -836,6 +846,8 @@ extern "C" int MPIX_Init(void) {
     g_mover_tma = 0;
 #endif
     acx_env_int("ACX_PDL", nullptr, 1, &v); g_pdl = v != 0;
+    acx_env_int("ACX_SEND_OVERFLOW", nullptr, 1, &v); g_send_overflow = v != 0;
+    acx_env_int("ACX_SEND_OVERFLOW_MAX", nullptr, 128, &v); g_send_overflow_max = v < 0 ? 0 : v;
     acx_env_int("ACX_MOVER_BLOCK", nullptr, 0, &v); g_mover_block = (int)std::max(0L, v) & ~511;
     acx_env_int("ACX_FUSE_RNDV", nullptr, 1, &v); g_fuse_rndv = v != 0;
     acx_env_int("ACX_SIDE_STREAMS", nullptr, 1, &v); g_side_on = v != 0;
@@ -959,6 +971,7 @@ extern "C" int MPIX_Init(void) {
     g_acx->recv_outstanding.assign(g_acx->size, std::vector<int>(g_acx->geom.nchan, 0));
     g_acx->recv_deferred.assign(g_acx->size, std::vector<std::vector<AcxRequest *>>(g_acx->geom.nchan));
     g_acx->send_count.assign(g_acx->size, std::vector<AcxState::ChanCount>(g_acx->geom.nchan));
+    g_acx->send_flow.assign(g_acx->size, std::vector<AcxState::SendFlow>(g_acx->geom.nchan));
     g_acx->recv_count.assign(g_acx->size, std::vector<AcxState::ChanCount>(g_acx->geom.nchan));
     g_acx->device = true;
     g_acx->initialized = true;
@@ -1024,6 +1037,8 @@ extern "C" int MPIX_Finalize(void) {
         g_side.clear();
         for (auto &kv : g_chan_streams) cudaStreamDestroy(kv.second);
         g_chan_streams.clear();
+        for (OverflowStream &o : g_ovf_pool) cudaStreamDestroy(o.s);
+        g_ovf_pool.clear();
         for (auto e : g_event_pool) cudaEventDestroy(e);
         g_event_pool.clear();
         cudaFreeHost(g_acx->hstat);
@@ -1053,6 +1068,7 @@ extern "C" int MPIX_Get_stats(MPIX_Acx_stats *s) {
     s->slots_in_use = g_acx->slots_in_use; s->slots_high_water = g_acx->st.slots_hw;
     s->heap_bytes_in_use = g_acx->heap_in_use; s->heap_bytes_high_water = g_acx->st.heap_hw;
     s->copy_engine_msgs = g_acx->st.ce;
+    s->overflow_sends = g_acx->st.send_overflow;
     return MPI_SUCCESS;
 }
 
@@ -1333,6 +1349,95 @@ struct BranchScope {
         return 0;
     }
 };
+
+// Sends in flight beyond a channel's ring depth (ACX_SEND_OVERFLOW, default on).
+// The trigger of a send draws a ticket and waits ON ITS STREAM until the ring slot of that ticket is free again, i.e. until the
+// receiver has consumed the message `depth` tickets earlier. A program that enqueues more than `depth` sends on one channel
+// before the operations the peer needs for progress (a burst of 100 MPIX_Isend_enqueue, then the receives, then one
+// MPIX_Waitall_enqueue — legal MPI, and fine with the reference, whose triggers only set a flag for the proxy thread) used to
+// stop its own stream there for good. Now the host counts, per channel, the stream-mode sends that have been enqueued and not
+// yet waited on; a send that finds `depth` of them ahead of it — or earlier overflow sends still pending — becomes an
+// OVERFLOW send: its trigger runs on a pool stream, forked from the caller's stream by an event (it still reads the buffer in
+// stream order), waits for slot credit there and holds up nobody.
+//  * Nothing is ever enqueued BEHIND a waiting trigger. CUDA feeds all streams of a process through a few in-order hardware
+//    queues: an operation that waits for its stream predecessor holds up whatever other streams queued
+//    behind it — and the predecessor here would be a trigger spinning for credit that only later work of this process (the
+//    waits of its receives) can produce. A first version that chained a channel's overflow triggers on one stream and recorded
+//    an event behind each deadlocked on the software device with one or two hardware queues. So every pending overflow trigger
+//    has a pool stream to itself and is the last thing on it: a rendezvous message gets trigger and mover in one kernel
+//    (send_rndv_fused, one or two CTAs) and there is no event behind it — it reports to the host through its slot's pinned
+//    status record (trig_serial) and to its wait kernel through op->armed.
+//  * Ticket order without stream order: the trigger gets the ticket the HOST counted for it (host_ticket) and takes it when the
+//    channel's counter reaches that value. Channels whose tickets the host cannot count (graphs, several streams) keep the old
+//    behaviour.
+//  * A wait call completes its overflow sends LAST, behind the wait kernels of everything else it was given: the receives
+//    completed there are what returns credit to the peer's overflow sends, and the peer is usually in the mirror image of the
+//    same call.
+// A steady-state exchange (send, receive, wait per step) never has more than a few un-waited sends per channel and never gets
+// here: the cost on the hot path is one counter under the library mutex.
+// What remains bounded: an overflow send completes only once the receiver has WAITED on the receive `depth` messages
+// earlier (slot credit is returned by the receiver's wait, not by its trigger), and ACX_SEND_OVERFLOW_MAX of them can be
+// pending at a time — see DESIGN.md section 8.
+static bool overflow_trigger_pending(const AcxRequest *r) {   // has this overflow send's trigger drawn its ticket yet?
+    return ACX_HOST_FLAG_GET(&g_acx->hstat[r->slot].trig_serial) != (int32_t)(uint32_t)r->serial;
+}
+static bool send_channel_backlogged_locked(int dest, int chan) {   // caller holds g_acx->mu
+    AcxState::SendFlow &f = g_acx->send_flow[(size_t)dest][(size_t)chan];
+    if (f.last) {
+        if (overflow_trigger_pending(f.last)) return true;   // earlier overflow sends have not drawn their tickets yet (they draw in order)
+        f.last = nullptr;
+    }
+    return f.unwaited >= g_acx->geom.depth;
+}
+static bool send_channel_backlogged(int dest, int chan) {   // a fused send (MPIX_Sendrecv_enqueue) must not jump the queue
+    if (!g_send_overflow) return false;
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    return send_channel_backlogged_locked(dest, chan);
+}
+static void send_flow_forget(AcxRequest *r) {   // caller holds g_acx->mu; the request is going away
+    if (!r->overflow || r->slot < 0 || !g_acx || (size_t)r->peer >= g_acx->send_flow.size()) return;
+    AcxState::SendFlow &f = g_acx->send_flow[(size_t)r->peer][(size_t)r->chan];
+    if (f.last == r) f.last = nullptr;
+    for (OverflowStream &o : g_ovf_pool) if (o.owner == r) o.owner = nullptr;
+}
+static void send_flow_release(AcxRequest *r) {   // caller holds g_acx->mu; the request's wait has been enqueued (or it is being released)
+    if (!r || !r->send_counted) return;
+    r->send_counted = false;
+    AcxState::SendFlow &f = g_acx->send_flow[(size_t)r->peer][(size_t)r->chan];
+    if (f.unwaited > 0) f.unwaited--;
+}
+// Count a stream-mode send against its channel and decide whether it is an overflow send (needs the host's ticket).
+// 0: ordinary send; 1: overflow send, *stream is the pool stream for its trigger; < 0: refused.
+static int send_overflow_begin(AcxRequest *r, cudaStream_t *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
+    AcxState::SendFlow &f = g_acx->send_flow[(size_t)r->peer][(size_t)r->chan];
+    const bool overflow = r->hticket != ~0ull && send_channel_backlogged_locked(r->peer, r->chan);
+    if (!overflow) { f.unwaited++; r->send_counted = true; return 0; }
+    OverflowStream *slot = nullptr;
+    for (OverflowStream &o : g_ovf_pool) {
+        if (o.owner && !overflow_trigger_pending(o.owner)) o.owner = nullptr;   // that trigger is past its waits: whatever follows it on the stream will run
+        if (!o.owner) { slot = &o; break; }
+    }
+    if (!slot) {
+        if ((long)g_ovf_pool.size() >= g_send_overflow_max) {
+            ACX_ERR("%ld sends are waiting for ring slots on overflow streams (ACX_SEND_OVERFLOW_MAX) and %d sends to rank %d (tag %d) are not yet waited on: wait on earlier sends first", g_send_overflow_max, f.unwaited, r->peer, r->tag);
+            return -1;
+        }
+        cudaStream_t ns = nullptr;
+        if (cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ACX_ERR("cannot create an overflow stream"); return -1; }
+        g_ovf_pool.push_back({ns, nullptr});
+        slot = &g_ovf_pool.back();
+    }
+    slot->owner = r;
+    *stream = slot->s;
+    f.unwaited++;
+    r->send_counted = true;
+    r->overflow = true;
+    f.last = r;
+    ACX_HOST_FLAG_SET(&g_acx->hstat[r->slot].trig_serial, 0);
+    g_acx->st.send_overflow++;
+    return 1;
+}
 
 // Unfused movers of stream-mode operations run on a per-peer side stream, forked after the trigger kernel: the
 // user's stream is not held up by the transfer, and transfers to/from different peers overlap (all-pairs,
@@ -1911,30 +2016,59 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
         memset(&mp, 0, sizeof mp);
         mp.op = sp.op; mp.local = (char *)src_local; mp.ring = sp.ring; mp.sack = sp.sack; mp.depth = G.depth; mp.push = 1; mp.peer = dest; mp.tr = sp.tr;
         mp.vec256 = g_mover_256; mp.block_bytes = (uint32_t)g_mover_block;
-        const int fgrid = (!eager && g_fuse_rndv && !g_mover_tma) ? mover_grid_ldst(bytes) : 0;
+        r->src_local = (char *)src_local;
+        if (!dropped) r->hticket = host_ticket(true, dest, r->chan, r->stream, r->in_graph);
+        // More un-waited sends on this channel than its ring holds: the trigger goes to a pool stream (see send_overflow_begin)
+        cudaStream_t ovf_stream = nullptr;
+        if (g_send_overflow && !dropped && !branch.on && qtype == MPIX_QUEUE_CUDA_STREAM && !em.capturing && !g_apush) {
+            const int ov = send_overflow_begin(r, &ovf_stream);
+            if (ov < 0) { rc = MPI_ERR_OTHER; goto fail; }
+        }
+        const int fgrid = (!eager && g_fuse_rndv && !g_mover_tma && !r->overflow) ? mover_grid_ldst(bytes) : 0;
         const bool fused = fgrid >= g_fuse_min_ctas && fgrid <= g_fuse_max_ctas;   // measured: pays off from ~512 KiB, costs ~1.5 us below
         const bool apush = !eager && !fused && g_apush && g_side_on && qtype == MPIX_QUEUE_CUDA_STREAM;
         sp.apush = apush ? 1 : 0;
         // Cooperative moving is a property of the MESSAGE, chosen here from its size and announced in the header
-        r->coop = g_coop && !eager && !fused && !apush && !g_mover_tma && (long)bytes >= g_coop_min;
+        r->coop = g_coop && !eager && !fused && !apush && !g_mover_tma && !r->overflow && (long)bytes >= g_coop_min;
         sp.coop = r->coop ? 1 : 0;   // travels in the message header: the receiver follows the sender's choice
         // Large messages: the sender moves them — the mover behind this trigger if the receive is posted by then, the helper
         // CTAs of this request's wait kernel otherwise. The receiver never pulls (except as a late fallback), so every GPU
         // copies exactly its own sends whatever order ranks arrive in (a ring step stays one NVLink push per GPU).
-        r->src_local = (char *)src_local;
-        if (!dropped) r->hticket = host_ticket(true, dest, r->chan, r->stream, r->in_graph);
         // Copy-engine rendezvous: if the receiver's host has already enqueued the matching receive (its record is in shared
         // memory), the destination is known now and the copy engines move the payload; decided per message, by the sender.
         char *ce_dst = nullptr;
         uint64_t ce_off = 0;
-        if (g_ce_min > 0 && !eager && !fused && !apush && !r->coop && !dropped && (long)bytes >= g_ce_min && g_side_on && qtype == MPIX_QUEUE_CUDA_STREAM && !em.capturing && !r->branched)
+        if (g_ce_min > 0 && !eager && !fused && !apush && !r->coop && !dropped && !r->overflow && (long)bytes >= g_ce_min && g_side_on && qtype == MPIX_QUEUE_CUDA_STREAM && !em.capturing && !r->branched)
             ce_dst = ce_lookup(dest, r->chan, r->hticket, bytes, em.stream, &ce_off);
         if (ce_dst) sp.apush = 1;   // announced as RNDV_PUSH: the receiver leaves the message alone
-        r->late = g_late_min > 0 && !eager && !fused && !apush && !ce_dst && !r->coop && (long)bytes >= g_late_min;
+        r->late = g_late_min > 0 && !eager && !fused && !apush && !ce_dst && !r->coop && !r->overflow && (long)bytes >= g_late_min;
         sp.late = r->late ? 1 : 0;
+        if (r->overflow) {
+            // the trigger alone, on a pool stream, behind an event that marks this point of the caller's stream (what the caller's
+            // stream has done to the buffer so far — and the pack / bounce copy above — comes first); nothing follows it there
+            cudaEvent_t fork = event_get();
+            if (!fork) { rc = MPI_ERR_OTHER; goto fail; }
+            cudaError_t fe = cudaEventRecord(fork, em.stream);
+            if (fe == cudaSuccess) fe = cudaStreamWaitEvent(ovf_stream, fork, 0);
+            { std::lock_guard<std::recursive_mutex> lk(g_acx->mu); g_event_pool.push_back(fork); }   // the wait has captured the record: the event object may be reused
+            if (fe != cudaSuccess) { ACX_ERR("cannot fork the overflow stream: %s", cudaGetErrorString(fe)); rc = MPI_ERR_OTHER; goto fail; }
+            sp.hticket1 = r->hticket + 1;
+            sp.hdone = &(g_acx->hstat_d + r->slot)->trig_serial; sp.hserial = (uint32_t)r->serial;
+            sp.hstat = nullptr;      // its wait kernel retires the slot (an eager trigger that did would hand the op record on while that kernel is still to run)
+            Emitter eo = em;
+            eo.stream = ovf_stream;
+            eo.no_pdl = true;        // behind an event wait: a full dependency, nothing programmatic
+            // rendezvous: trigger and mover in ONE kernel (nothing may follow a waiting trigger on its stream), with a grid of at
+            // most two CTAs — up to ACX_SEND_OVERFLOW_MAX of these sit resident while they wait for credit
+            if (eager) rc = eo.launch(send_trigger, dim3(1), dim3(bytes > 512 ? kTriggerThreads : 32), sp);
+            else rc = eo.launch2(send_rndv_fused, dim3(bytes > (1u << 20) ? 2 : 1), dim3(kMoverThreads), sp, mp);
+            if (rc) goto fail;
+            if (eager) g_acx->st.eager++; else g_acx->st.rndv++;
+        } else
         if (!dropped && fused) { if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail; }
         else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
-        if (!eager) {
+        if (r->overflow) {
+        } else if (!eager) {
             if (ce_dst) { if ((rc = launch_sender_ce(em, r, sp, ce_dst, ce_off, src_local, bytes))) goto fail; }
             else if (apush) { if (!dropped && (rc = launch_sender_push(em, r, sp, mp, bytes))) goto fail; }
             else if (!fused && (rc = launch_mover_maybe_side(em, r, mp, bytes))) goto fail;
@@ -2106,7 +2240,8 @@ static int fill_wait(AcxRequest *r, MPI_Status *status, bool retire, bool host_w
     w->op = (acx_op *)(g_acx->ctrl + G.off_ops) + r->slot;
     w->hstat = g_acx->hstat_d + r->slot;
     w->depth = G.depth; w->eager_max = G.eager_max;
-    w->serial = host_wait ? r->serial : 0;
+    w->serial = (host_wait || r->overflow) ? r->serial : 0;   // an overflow send's trigger runs on a pool stream: no stream order between it and this wait
+    w->trigger_only = (r->overflow && r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max) ? 1 : 0;
     w->retire = retire ? 1 : 0;
     w->late_tag = (uint32_t)r->serial;
     w->hticket = r->hticket;
@@ -2270,7 +2405,7 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
                 cudaError_t je = cudaStreamWaitEvent(em.stream, r->ev_done, 0);
                 if (je != cudaSuccess) { ACX_ERR("cudaStreamWaitEvent(join): %s", cudaGetErrorString(je)); return MPI_ERR_OTHER; }
             }
-            if (r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max) continue;
+            if (r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max && !r->overflow) continue;   // (an overflow send's trigger is on a pool stream: its wait is a kernel)
             need.push_back({r, st});
         }
     }
@@ -2325,10 +2460,16 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
         em.parallel = par;
         if (rc) return rc;
     }
+    // Overflow sends go last (see send_overflow_begin): their wait kernels hold this stream until the receiver has consumed
+    // earlier messages of the channel, and the receiver may be waiting for exactly the receives this call completes.
+    std::stable_partition(need.begin(), need.end(), [](const Item &it) { return !it.r->overflow; });
+    size_t first_ovf = need.size();
+    for (size_t i = 0; i < need.size(); i++) if (need[i].r->overflow) { first_ovf = i; break; }
     for (size_t base = 0, step = 0; base < need.size(); base += step) {
         WaitBatch wb;
         memset(&wb, 0, sizeof wb);
         int n = (int)std::min((size_t)kWaitBatch, need.size() - base);
+        if (base < first_ovf) n = (int)std::min((size_t)n, first_ovf - base);   // no batch mixes the two kinds
         // receives that were posted while their channel's ring was full: their triggers go out now, in posting order (the waits
         // of earlier batches have made room)
         for (int j = 0; j < n; j++) {
@@ -2375,7 +2516,7 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
             for (int j = 0; j < n; j++) if (wb.w[j].late) movers_in_wait = true;
             for (int j = 0; j < n && !movers_in_wait; j++) {
                 AcxRequest *r = need[base + j].r;
-                if (r->hticket == ~0ull || r->wild) continue;
+                if (r->hticket == ~0ull || r->wild || r->overflow) continue;
                 const uint32_t e = (uint32_t)(r->hticket % (uint64_t)G.depth);
                 const uint64_t g = r->hticket / (uint64_t)G.depth;
                 if (r->kind == ACX_REQ_RECV) mb.wait_geq64(&(acx_entries_of(g_acx->ctrl) + acx_entry_index(G, r->peer, r->chan, 0))[e].done, g + 1);
@@ -2424,6 +2565,7 @@ static int wait_enqueue_impl(int count, MPIX_Request *reqs, MPI_Status *statuses
     {
         std::lock_guard<std::recursive_mutex> lk(g_acx->mu);
         for (AcxRequest *r : rs) {
+            send_flow_release(r);   // waited on: no longer counts against its channel's sends in flight
             if (retire) { g_acx->slot_busy[r->slot] = 3; g_pending_retire.push_back(r->slot); }  // reclaimed once the device marks it retired
         }
     }
@@ -2586,7 +2728,8 @@ extern "C" int MPIX_Sendrecv_enqueue(const void *sendbuf, int sendcount, MPI_Dat
         if (!rc) rc = check_common("MPIX_Sendrecv_enqueue", true, recvcount, recvtype, source, recvtag, comm, &dummy, queue, &rbytes, &rctx, &wsource, &rty);
         if (rc) return rc;
         fast = !sty.noncontig && !rty.noncontig && sbytes <= g_acx->geom.eager_max && rbytes <= g_acx->geom.eager_max &&
-               !recv_channel_backlogged(wsource, chan_lookup(wsource, g_acx->rank, recvtag, rctx));
+               !recv_channel_backlogged(wsource, chan_lookup(wsource, g_acx->rank, recvtag, rctx)) &&
+               !send_channel_backlogged(wdest, chan_lookup(g_acx->rank, wdest, sendtag, sctx));
     }
     if (!fast) {
         MPIX_Request rq[2] = {MPIX_REQUEST_NULL, MPIX_REQUEST_NULL};
@@ -2719,7 +2862,7 @@ extern "C" int MPIX_Wait(MPIX_Request *req, MPI_Status *status) {
     }
     if (r->null_op) { complete_null_op(r, status); *req = MPIX_REQUEST_NULL; return MPI_SUCCESS; }
     if (r->in_graph) { ACX_ERR("in-graph operations must be completed by a wait inside a graph"); return MPI_ERR_REQUEST; }
-    if (r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max) {
+    if (r->kind == ACX_REQ_SEND && r->bytes <= g_acx->geom.eager_max && !r->overflow) {   // (an overflow send's slot may only be released once a wait kernel has seen the trigger's LAST store, op->armed)
         // eager send: complete once its trigger kernel has run; it says so in pinned host memory
         const int32_t *flag = &g_acx->hstat[r->slot].retired;
         auto t0 = std::chrono::steady_clock::now();
@@ -2822,9 +2965,15 @@ extern "C" int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses)
         if (!wait_ops.ops.empty()) { int rc = wait_ops.flush(host_stream()); if (rc) return rc; }
         if (any) ACX_CUDA_WD(cudaStreamSynchronize(host_stream()));
     }
-    for (int i = 0; i < count; i++) {
-        int rc = MPIX_Wait(&reqs[i], statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[i]);
-        if (rc) return rc;
+    // Overflow sends last, as in the stream waits (SendOverflow): they complete only once the peer has consumed earlier
+    // messages of their channel, and the peer's host may be sitting in the mirror image of this very call.
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = 0; i < count; i++) {
+            AcxRequest *r = reqs[i] ? as_request(reqs[i]) : nullptr;
+            if (pass == 0 && r && r->overflow) continue;
+            int rc = MPIX_Wait(&reqs[i], statuses == MPI_STATUSES_IGNORE ? MPI_STATUS_IGNORE : &statuses[i]);
+            if (rc) return rc;
+        }
     }
     return MPI_SUCCESS;
 }

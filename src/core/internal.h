@@ -91,7 +91,8 @@ struct acx_anyres {  // resolution of a wildcard receive (device memory, one per
 struct acx_host_status {  // pinned host memory, one per request slot; written by wait kernels
     int32_t source, tag, error, retired;
     int64_t bytes;
-    int64_t pad;
+    int32_t trig_serial;      // overflow sends: low 32 bits of the request serial, stored by the trigger once it has drawn its ticket and deposited / announced the message
+    int32_t pad;
 };
 
 // `retired` (and the status fields next to it) live in pinned host memory: kernels store, the host polls. On hardware
@@ -237,6 +238,8 @@ struct AcxRequest {
     AcxLayout layout;
     bool wild;                // wildcard receive (MPI_ANY_SOURCE / MPI_ANY_TAG): matched by recv_any_kernel when the wait runs
     bool branched;            // ACX_PEER_BRANCH: all of this operation's kernels ran on the peer's side stream (the wait joins ev_done)
+    bool overflow;            // SEND enqueued while its channel already had a ring's worth of un-waited sends (or earlier overflow sends still pending): its trigger runs on a pool stream with the host's ticket, its wait is a kernel that watches op->armed and comes AFTER the waits of everything else in the same call
+    bool send_counted;        // SEND that is counted in AcxState::send_flow[peer][chan].unwaited (until its wait is enqueued / it is released)
     MPI_Request mpi_req;
     MPI_Status *user_status;
     AcxGraphRes *gres;
@@ -303,6 +306,10 @@ struct AcxState {
     std::vector<std::vector<std::vector<AcxRequest *>>> recv_deferred;   // [src][chan]: receives whose trigger has not been launched yet, in posting order
     struct ChanCount { uint64_t next = 0; cudaStream_t stream = nullptr; bool dev = false; };
     std::vector<std::vector<ChanCount>> send_count, recv_count;   // [peer][chan]
+    // Sends in flight beyond a channel's ring depth (ACX_SEND_OVERFLOW, acx.cu: SendOverflow): stream-mode sends enqueued and not
+    // yet waited on, per channel; the overflow stream that carries the sends which could otherwise hold up the caller's stream.
+    struct SendFlow { int unwaited = 0; AcxRequest *last = nullptr; };   // last: the newest overflow send of the channel while its trigger may still be pending (acx_host_status::trig_serial tells); cleared when that request is released
+    std::vector<std::vector<SendFlow>> send_flow;   // [peer][chan]
     // config
     bool trace = false;
     int verbose = 0;
@@ -312,7 +319,7 @@ struct AcxState {
     // stats
     struct {
         std::atomic<unsigned long long> sends{0}, recvs{0}, waits{0}, bytes_sent{0}, bytes_recv{0}, eager{0}, rndv{0}, bounce{0},
-            kernels{0}, graph_nodes{0}, slots_hw{0}, heap_hw{0}, ce{0};
+            kernels{0}, graph_nodes{0}, slots_hw{0}, heap_hw{0}, ce{0}, send_overflow{0};
     } st;
     size_t heap_in_use = 0;
     int slots_in_use = 0;

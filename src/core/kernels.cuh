@@ -170,6 +170,14 @@ struct SendParams {
     uint64_t serial;
     uint32_t tag, depth, eager_max, peer;
     uint32_t ctx, late;     // ctx: communicator context, travels in the slot header (exact (source, tag, comm) matching: a receive checks it); late: announce RNDV_LATE (sender moves, now or at its wait)
+    // Overflow sends (acx.cu: SendOverflow) run on a pool stream of their own, several of one channel at a time: the ticket is the
+    // one the HOST counted (hticket1 - 1; 0 = draw from the counter), taken when the channel's counter reaches it, so tickets
+    // keep the enqueue order without any stream order between the triggers; the trigger reports to the host (hdone) and to the
+    // wait kernel (op->armed, for eager messages too). Nothing follows it on its stream: a rendezvous message gets the
+    // single-launch kernel (send_rndv_fused) with a small grid.
+    uint64_t hticket1;
+    int32_t *hdone;         // pinned host word of the slot (acx_host_status::trig_serial): set to hserial once the ticket is drawn and the message deposited / announced
+    uint32_t hserial, pad_ov;
     uint32_t apush, coop;   // apush: deterministic mode — this sender pushes the payload itself (gate + mover on its channel stream); coop: announce the message as RNDV_COOP (ACX_COOP)
     Watchdog wd;
     TraceCtx tr;
@@ -201,15 +209,27 @@ __device__ __forceinline__ void send_rndv_match(const SendParams &p, uint64_t k)
     } else {
         p.op->mover = 0;
     }
+    if (p.hdone) ACX_HOST_FLAG_SET(p.hdone, (int32_t)p.hserial);
     st_release_sys(&p.op->armed, p.serial);
     trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes | (1ull << 63));
+}
+
+// A send's ticket on its channel (one thread): drawn from the channel's counter — or, for an overflow send, the one the host
+// counted for it, taken when the counter gets there (the overflow triggers of a channel run on different streams).
+__device__ __forceinline__ uint64_t send_take_ticket(const SendParams &p) {
+    if (!p.hticket1) return atomicAdd((unsigned long long *)p.seq, 1ull);
+    const uint64_t k = p.hticket1 - 1;
+    spin_geq(p.seq, k, p.wd, 0x5e15);
+    if (ld_relaxed_sys(p.seq) != k) wd_fail(p.wd, 0x5e16, k, ld_relaxed_sys(p.seq));   // somebody drew the ticket the host had counted for this send
+    st_release_sys(p.seq, k + 1);
+    return k;
 }
 
 __device__ __forceinline__ void send_body(const SendParams &p) {
     __shared__ uint64_t s_k;
     const unsigned tid = threadIdx.x;
     if (tid == 0) {
-        uint64_t k = atomicAdd((unsigned long long *)p.seq, 1ull);
+        const uint64_t k = send_take_ticket(p);
         uint32_t e = (uint32_t)(k % p.depth);
         uint64_t g = k / p.depth;
         spin_geq(&p.sack[e].efree, g, p.wd, 0x5e01);  // slot's previous generation consumed
@@ -231,6 +251,11 @@ __device__ __forceinline__ void send_body(const SendParams &p) {
             st_release_sys(&ent->done, k / p.depth + 1);   // one completion word for every kind of message: what a stream memOp (or a wait kernel) watches
             // The source buffer is reusable as soon as this kernel retires: nothing to wait for later.
             if (p.hstat) ACX_HOST_FLAG_SET(&p.hstat->retired, 1);
+            if (p.hdone) {   // overflow send: its wait is a kernel on another stream, which watches the op record
+                ACX_HOST_FLAG_SET(p.hdone, (int32_t)p.hserial);
+                p.op->ticket = k;
+                st_release_sys(&p.op->armed, p.serial);
+            }
             trace(p.tr, ACX_EV_SEND_TRIGGER, p.peer, k, p.bytes);
         }
     } else if (tid == 0) {
@@ -524,7 +549,7 @@ __global__ void __launch_bounds__(kMoverThreads) send_rndv_fused(SendParams sp, 
     acx_op *op = sp.op;
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) {
-            const uint64_t k = atomicAdd((unsigned long long *)sp.seq, 1ull);
+            const uint64_t k = send_take_ticket(sp);
             spin_geq(&sp.sack[k % sp.depth].efree, k / sp.depth, sp.wd, 0x5e01);
             send_rndv_match(sp, k);
             __threadfence();
@@ -850,7 +875,7 @@ struct WaitOne {
     char *peer_heap;        // the peer's heap, peer-mapped
     const uint64_t *xlat;   // translation row for registrations owned by the peer
     uint64_t late_bytes;    // send: message bytes
-    uint16_t late, help_lo, help_n, pad1;
+    uint16_t late, help_lo, help_n, trigger_only;   // trigger_only: eager overflow send — complete once its trigger (on a pool stream) has run, i.e. op->armed == serial
     uint64_t hticket;          // host-predicted ticket (~0: none): checked against the ticket the trigger drew
     uint32_t late_tag, pad2;   // low bits of the request serial: together with the ticket it makes the op record's late_state word unique per (request, launch)
     uint16_t is_recv, retire;
@@ -894,7 +919,9 @@ __device__ __forceinline__ void wait_body(const WaitBatch &b, const WaitOne &w) 
         const uint32_t e = (uint32_t)(k % w.depth);
         const uint64_t g = k / w.depth;
         trace(b.tr, ACX_EV_WAIT_BEGIN, w.src, k, w.is_recv);
-        if (!w.is_recv) {
+        if (!w.is_recv && w.trigger_only) {
+            s_n = 0; s_eager = 0;   // the trigger has run (armed): the payload is in the receiver's slot, the buffer is reusable
+        } else if (!w.is_recv) {
             if (w.late) {
                 // RNDV_LATE: if the receive was posted when the trigger ran, the mover launched behind it is pushing (or has
                 // pushed) — nothing to do here. Otherwise nobody has moved anything yet and the RECEIVER will not pull (its

@@ -7,7 +7,12 @@
  *      waits for slot credit like a standard-mode MPI_Send waits for buffer space;
  *   2. the same with host MPIX_Waitall;
  *   3. waiting FIRST on a receive that sits behind 32 un-waited ones is an error (nothing can make room), not a deadlock;
- *      waiting in order afterwards works. */
+ *      waiting in order afterwards works;
+ *   4. the mirror image for SENDS: 80 sends enqueued up front on one channel, then the 80 receives, then ONE wait call for all
+ *      160 requests (sends listed first) — on the stream, and on the host. A send's trigger waits for slot credit, which the
+ *      receiver returns from the wait of the message 32 tickets earlier: the triggers of the sends beyond the ring wait on pool
+ *      streams (MPIX_Acx_stats::overflow_sends) instead of stopping the caller's stream in front of the receives, and a wait
+ *      call completes its overflow sends last. Then a second round on the same channel, waiting receives and sends in two calls. */
 #include "acx_test.h"
 
 #define K 100
@@ -53,6 +58,40 @@ static void out_of_order_wait(cudaStream_t st) {
     T_CHECK(bad == 0, "in-order waits after the refused one: %d wrong", bad);
 }
 
+static unsigned long long overflow_count(void) { MPIX_Acx_stats s; MPIX_Get_stats(&s); return s.overflow_sends; }
+
+static void send_burst(int host_wait, int two_calls, cudaStream_t st) {
+    enum { KB = 80 };   /* 48 overflow sends */
+    static int *sbuf[KB], *rbuf[KB];
+    MPIX_Request rq[2 * KB];   /* sends first, then receives */
+    const int salt = 7 * host_wait + 3 * two_calls;
+    for (int k = 0; k < KB; k++) {
+        if (!sbuf[k]) { sbuf[k] = (int *)malloc(sizeof(int) * 5000); rbuf[k] = (int *)malloc(sizeof(int) * 5000); }
+        for (int i = 0; i < len_of(k); i++) { sbuf[k][i] = t_rank * 1000000 + k * 100 + (i % 83) + salt; rbuf[k][i] = -1; }
+    }
+    const unsigned long long before = overflow_count();
+    for (int k = 0; k < KB; k++) T_OK(MPIX_Isend_enqueue(sbuf[k], len_of(k), MPI_INT, T_RIGHT, 8, MPI_COMM_WORLD, &rq[k], MPIX_QUEUE_CUDA_STREAM, &st));
+    for (int k = 0; k < KB; k++) T_OK(MPIX_Irecv_enqueue(rbuf[k], 5000, MPI_INT, T_LEFT, 8, MPI_COMM_WORLD, &rq[KB + k], MPIX_QUEUE_CUDA_STREAM, &st));
+    const int depth = getenv("ACX_DEPTH") ? atoi(getenv("ACX_DEPTH")) : 32;
+    if (t_gpu) T_CHECK(overflow_count() - before == (unsigned long long)(KB - depth), "%llu sends took the overflow stream, expected %d (%d un-waited sends on one channel, ring depth %d)", overflow_count() - before, KB - depth, KB, depth);
+    if (two_calls) {   /* receives, then sends: the order a program has to use when it splits the wait */
+        if (host_wait) { T_OK(MPIX_Waitall(KB, rq + KB, MPI_STATUSES_IGNORE)); T_OK(MPIX_Waitall(KB, rq, MPI_STATUSES_IGNORE)); }
+        else { T_OK(MPIX_Waitall_enqueue(KB, rq + KB, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st)); T_OK(MPIX_Waitall_enqueue(KB, rq, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st)); }
+    } else if (host_wait) T_OK(MPIX_Waitall(2 * KB, rq, MPI_STATUSES_IGNORE));
+    else T_OK(MPIX_Waitall_enqueue(2 * KB, rq, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
+    if (!host_wait && t_gpu) T_CUDA(cudaStreamSynchronize(st));
+    int bad = 0;
+    for (int k = 0; k < KB; k++) for (int i = 0; i < len_of(k); i++) if (rbuf[k][i] != T_LEFT * 1000000 + k * 100 + (i % 83) + salt) { bad++; break; }
+    T_CHECK(bad == 0, "%d of %d messages wrong with %d sends in flight on one channel (%s wait, %s)", bad, KB, KB, host_wait ? "host" : "stream", two_calls ? "two calls" : "one call");
+    /* the channel is back to normal: a plain exchange behind the burst stays on the caller's stream */
+    const unsigned long long mid = overflow_count();
+    int a = 4242 + t_rank, b = -1;
+    T_OK(MPIX_Sendrecv_enqueue(&a, 1, MPI_INT, T_RIGHT, 8, &b, 1, MPI_INT, T_LEFT, 8, MPI_COMM_WORLD, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
+    if (t_gpu) T_CUDA(cudaStreamSynchronize(st));
+    T_CHECK(b == 4242 + T_LEFT, "exchange behind the burst delivered %d, expected %d", b, 4242 + T_LEFT);
+    if (t_gpu && !host_wait) T_CHECK(overflow_count() == mid, "a single send on a drained channel took the overflow stream");
+}
+
 int main(int argc, char **argv) {
     t_init(&argc, &argv, 0);
     cudaStream_t st = 0;
@@ -60,6 +99,12 @@ int main(int argc, char **argv) {
     round_trip(0, st);
     round_trip(1, st);
     out_of_order_wait(st);
+    if (!getenv("ACX_TEST_NO_SEND_BURST")) {   /* (the GPU suite runs part 4 as a test of its own) */
+        send_burst(0, 0, st);
+        send_burst(1, 0, st);
+        send_burst(0, 1, st);
+        send_burst(1, 1, st);
+    }
     if (t_gpu) T_CUDA(cudaStreamDestroy(st));
     return t_finish("many_outstanding");
 }

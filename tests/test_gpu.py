@@ -105,7 +105,7 @@ def test_more_receives_outstanding_than_the_ring_is_deep(built, np_):
     host flavour): receives beyond the ring's depth are launched from the waits that make room, in posting order; waiting
     first on one that sits behind 32 un-waited receives is refused, not a deadlock — tests/c/many_outstanding.c
     (reference capacity: MPIACX_NFLAGS, include/mpi-acx-internal.h:141)."""
-    r = acxrun(built, np_, built / "build/tests/many_outstanding")
+    r = acxrun(built, np_, built / "build/tests/many_outstanding", env={"ACX_TEST_NO_SEND_BURST": "1"})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
 
@@ -420,5 +420,19 @@ def test_stream_memops_on_the_p2p_path(built, prog):
     completion words in local HBM, batched per MPIX_Waitall_enqueue; the completion kernel behind them never spins. A wrong
     prediction traps (0x5e0f). Reference: src/sendrecv.cu:373-385, 479-513 (WaitValue32 on host flags)."""
     r = acxrun(built, 2, built / f"build/tests/{prog}", env={"ACX_MEMOPS": "1"})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASS" in r.stdout and "device transport" in r.stdout
+
+
+@pytest.mark.xfail(strict=False, reason="overflow sends were written after the round's GPU budget was spent: verified on the software device only (1-8 hardware queues, jitter, ASan/TSan); first hardware run")
+@pytest.mark.parametrize("np_", [1, 2])
+def test_more_sends_in_flight_than_the_ring_is_deep(built, np_):
+    """80 sends enqueued up front on one channel (ACX_DEPTH = 32), then the 80 receives, ONE wait call over all 160 requests
+    (stream and host flavour), then split waits: the triggers of the sends beyond the ring wait for their slot on pool streams
+    with host-counted tickets instead of stopping the caller's stream in front of the receives (DESIGN.md section 3c,
+    MPIX_Acx_stats::overflow_sends) — tests/c/many_outstanding.c part 4. The reference's triggers only set a flag for its
+    proxy thread (src/sendrecv.cu:157-162), so this pattern runs there. Last in the file and with a watchdog: a failure
+    here cannot hide or hang the other tests."""
+    r = acxrun(built, np_, built / "build/tests/many_outstanding", env={"ACX_WATCHDOG_MS": "30000"})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout

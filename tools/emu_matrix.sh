@@ -82,6 +82,13 @@ done
 for p in ring_all ring_all_graph graph_large large_msgs stress status_errors ordering sendrecv_enqueue ring_partitioned partitioned_device; do run hwq2 2 $p ACX_EMU_HW_QUEUES=2; done
 lrun hwq1-ce 2 ce_path $CE ACX_EMU_HW_QUEUES=1
 lrun hwq1-late 3 late_push $LATE ACX_EMU_HW_QUEUES=1
+# overflow sends (more un-waited sends on a channel than its ring holds): nothing may sit behind a trigger
+# that waits for slot credit — one hardware queue must be enough; a ring of 8 makes 72 of the 80 sends overflow sends
+for np in 1 2 3; do run hwq1-overflow $np many_outstanding ACX_EMU_HW_QUEUES=1; done
+run hwq2-overflow 2 many_outstanding ACX_EMU_HW_QUEUES=2
+run depth8-overflow 2 many_outstanding ACX_DEPTH=8
+run depth8-overflow 2 status_errors ACX_DEPTH=8
+run overflow-jitter 3 many_outstanding ACX_FAULT_DELAY_US=200
 run hwq2-threads-1rank 1 threads ACX_EMU_HW_QUEUES=2
 run hwq32-threads 2 threads ACX_EMU_HW_QUEUES=32
 out=$(env ACX_EMU_HW_QUEUES=2 timeout 40 bin/acxrun -np 2 --timeout 20 $T/threads 2>&1); rc=$?
@@ -106,10 +113,8 @@ if [ "$mode" = full ]; then
         run ldst256 2 $p ACX_MOVER=ldst256
         run ldstcs 2 $p ACX_MOVER=ldstcs
         run mover-block 2 $p ACX_MOVER_BLOCK=4096
-        # a small ring and a single exact channel + the overflow FIFO. Not for threads.c (one channel per thread), nor for programs
-        # that keep more than 8 sends un-consumed on one channel: a send's trigger waits for slot credit on its stream (DESIGN.md
-        # "sends in flight per channel are bounded by the ring depth"), so status_errors.c (30 requests up front) needs the
-        # default depth and large_msgs.c its tags on separate channels
+        # a small ring and a single exact channel + the overflow FIFO. Not for threads.c (one channel per thread) nor
+        # status_errors.c (more distinct tags than channels); large_msgs.c needs its tags on separate channels
         case $p in threads|status_errors) ;; large_msgs) run depth8-chan4 2 $p ACX_DEPTH=8 ACX_NCHAN=4 ;; *) run depth8-chan2 2 $p ACX_DEPTH=8 ACX_NCHAN=2 ;; esac
         run eager64 3 $p ACX_EAGER_MAX=64
         run no-regcache 2 $p ACX_REGCACHE=0
