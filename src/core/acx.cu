@@ -1423,10 +1423,17 @@ static int send_overflow_begin(AcxRequest *r, cudaStream_t *stream) {
             ACX_ERR("%ld sends are waiting for ring slots on overflow streams (ACX_SEND_OVERFLOW_MAX) and %d sends to rank %d (tag %d) are not yet waited on: wait on earlier sends first", g_send_overflow_max, f.unwaited, r->peer, r->tag);
             return -1;
         }
-        cudaStream_t ns = nullptr;
-        if (cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ACX_ERR("cannot create an overflow stream"); return -1; }
-        g_ovf_pool.push_back({ns, nullptr});
-        slot = &g_ovf_pool.back();
+        // grow the pool in blocks (the first overflow send of the process creates 16 streams, then the pool doubles): few calls
+        // into the driver's stream allocator while triggers are already waiting on the device
+        const size_t first_new = g_ovf_pool.size();
+        const size_t grow = std::min<size_t>((size_t)g_send_overflow_max - first_new, std::max<size_t>(16, first_new));
+        for (size_t i = 0; i < grow; i++) {
+            cudaStream_t ns = nullptr;
+            if (cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); break; }
+            g_ovf_pool.push_back({ns, nullptr});
+        }
+        if (g_ovf_pool.size() == first_new) { ACX_ERR("cannot create an overflow stream"); return -1; }
+        slot = &g_ovf_pool[first_new];
     }
     slot->owner = r;
     *stream = slot->s;
