@@ -2071,10 +2071,11 @@ extern "C" int MPIX_Isend_enqueue(const void *buf, int count, MPI_Datatype datat
             else rc = eo.launch2(send_rndv_fused, dim3(bytes > (1u << 20) ? 2 : 1), dim3(kMoverThreads), sp, mp);
             if (rc) goto fail;
             if (eager) g_acx->st.eager++; else g_acx->st.rndv++;
-        } else
-        if (!dropped && fused) { if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail; }
-        else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
+        } else if (!dropped && fused) {
+            if ((rc = em.launch2(send_rndv_fused, dim3(fgrid), dim3(kMoverThreads), sp, mp))) goto fail;
+        } else if (!dropped && (rc = em.launch(send_trigger, dim3(1), dim3(eager && bytes > 512 ? kTriggerThreads : 32), sp))) goto fail;
         if (r->overflow) {
+            // complete as launched: no mover, no copy engine, no end-of-operation event
         } else if (!eager) {
             if (ce_dst) { if ((rc = launch_sender_ce(em, r, sp, ce_dst, ce_off, src_local, bytes))) goto fail; }
             else if (apush) { if (!dropped && (rc = launch_sender_push(em, r, sp, mp, bytes))) goto fail; }

@@ -15,7 +15,9 @@ opts = [("ACX_COOP=1", "ACX_COOP_MIN_BYTES=65536"), ("ACX_PEER_BRANCH=1",), ("AC
         # round 2: sender-moves protocol and copy-engine rendezvous at emulation-sized messages, their variants, exact-tag directory off, hardware work queues
         ("ACX_LATE_PUSH_MIN=65536",), ("ACX_LATE_PUSH_MIN=65536", "ACX_LATE_FALLBACK_US=0"), ("ACX_CE_MIN=16384", "ACX_LATE_PUSH_MIN=65536"), ("ACX_CE_MIN=16384", "ACX_CE_SPINGATE=0"),
         ("ACX_CE_MIN=16384", "ACX_CE_MEMOP=0"), ("ACX_CE_MIN=16384", "ACX_CE_MEMOP=2", "ACX_CE_SPINGATE=0"), ("ACX_CE_MIN=16384", "ACX_CE_SPIN_US=0"), ("ACX_TAGDIR=0",),
-        ("ACX_EMU_HW_QUEUES=1",), ("ACX_EMU_HW_QUEUES=2",), ("ACX_EMU_HW_QUEUES=3",)]
+        ("ACX_EMU_HW_QUEUES=1",), ("ACX_EMU_HW_QUEUES=2",), ("ACX_EMU_HW_QUEUES=3",),
+        # overflow sends: a ring of 8 turns the bursts of many_outstanding / status_errors / stress into overflow sends; off = the old behaviour
+        ("ACX_DEPTH=8",), ("ACX_DEPTH=8", "ACX_EMU_HW_QUEUES=1"), ("ACX_SEND_OVERFLOW=0",)]
 progs_extra = ["wildcards", "tags", "many_outstanding", "host_reuse", "reinit", "late_push", "ce_path"]
 sized = {"late_push": "262144", "ce_path": "262144"}   # programs that take their message size as an argument
 progs = "ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors sendrecv_enqueue stress".split()
@@ -36,6 +38,8 @@ while time.time() - t0 < budget:
     if "ACX_EMU_HW_QUEUES" in env and prog == "threads" and np_ > 1: continue   # several application threads per rank need a hardware queue per stream
     if prog == "ce_path" and ("ACX_CE_MIN" not in env or any(k in env for k in ("ACX_COOP", "ACX_SENDER_PUSH", "ACX_PEER_BRANCH", "ACX_SIDE_STREAMS", "ACX_WILDCARDS", "ACX_MOVER_MAX_CTAS", "ACX_NFLAGS"))): continue   # asserts that the copy engines were used
     if "ACX_TAGDIR" in env and prog in ("tags", "threads"): continue   # need one channel per tag
+    if "ACX_NFLAGS" in env and prog == "many_outstanding": continue     # 200 requests at a time
+    if env.get("ACX_SEND_OVERFLOW") == "0" and "ACX_DEPTH" in env: continue   # bursts longer than the ring need the overflow path
     r = subprocess.run(["bin/acxrun", "-np", str(np_), "--timeout", "240", os.environ.get("EMU_DIR", "build/emu") + f"/tests/{prog}"] + ([sized[prog]] if prog in sized else []), env=env, capture_output=True, text=True, timeout=400)
     runs += 1
     if r.returncode != 0 or "PASS" not in r.stdout or "ThreadSanitizer" in r.stderr or "AddressSanitizer" in r.stderr or "runtime error:" in r.stderr:
