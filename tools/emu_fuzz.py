@@ -38,7 +38,9 @@ while time.time() - t0 < budget:
     if "ACX_EMU_HW_QUEUES" in env and prog == "threads" and np_ > 1: continue   # several application threads per rank need a hardware queue per stream
     if prog == "ce_path" and ("ACX_CE_MIN" not in env or any(k in env for k in ("ACX_COOP", "ACX_SENDER_PUSH", "ACX_PEER_BRANCH", "ACX_SIDE_STREAMS", "ACX_WILDCARDS", "ACX_MOVER_MAX_CTAS", "ACX_NFLAGS"))): continue   # asserts that the copy engines were used
     if "ACX_TAGDIR" in env and prog in ("tags", "threads"): continue   # need one channel per tag
-    if "ACX_NFLAGS" in env and prog == "many_outstanding": continue     # 200 requests at a time
+    if "ACX_NFLAGS" in env and prog in ("many_outstanding", "tags", "host_reuse"): continue     # more than 16 requests at a time
+    if "ACX_DEPTH" in env and ("ACX_SENDER_PUSH" in env or "ACX_PEER_BRANCH" in env): continue      # no overflow path in these modes: bursts longer than the ring stop their stream
+    if "ACX_EMU_HW_QUEUES" in env and "ACX_SENDER_PUSH" in env: continue   # the push gate waits on a channel stream with its mover queued behind it: needs a hardware queue of its own (opt-in mode)
     if env.get("ACX_SEND_OVERFLOW") == "0" and "ACX_DEPTH" in env: continue   # bursts longer than the ring need the overflow path
     r = subprocess.run(["bin/acxrun", "-np", str(np_), "--timeout", "240", os.environ.get("EMU_DIR", "build/emu") + f"/tests/{prog}"] + ([sized[prog]] if prog in sized else []), env=env, capture_output=True, text=True, timeout=400)
     runs += 1
