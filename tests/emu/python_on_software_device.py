@@ -80,5 +80,15 @@ for nel, mk in ((16, torch.zeros), (40000, torch.zeros), (40000, lambda k, dtype
     sts = acx.waitall([acx.irecv(rb, left, tag=8), acx.isend(sb, (r + 1) % n, tag=8)])
     assert sts[0]["source"] == left and sts[0]["tag"] == 8 and sts[0]["bytes"] == 4 * nel and sts[0]["error"] == 0, sts
     assert bool((rb == 7 + left).all())
+# a burst of sends before the receives they need (more than a ring holds): the triggers beyond the ring wait on pool streams and
+# one waitall completes everything
+ov0 = acx.stats()["overflow_sends"]
+outs = [torch.full((6 + k % 5,), 100 * r + k, dtype=torch.int64) for k in range(45)]
+ins = [torch.zeros(6 + k % 5, dtype=torch.int64) for k in range(45)]
+q = [acx.isend(t, right, tag=12) for t in outs] + [acx.irecv(t, left, tag=12) for t in ins]
+acx.waitall_enqueue(q)
+acx.synchronize()
+assert all(bool((ins[k] == 100 * left + k).all()) for k in range(45))
+assert acx.stats()["overflow_sends"] - ov0 == 45 - 32, acx.stats()["overflow_sends"] - ov0
 print("PY-EMU OK", r, acx.stats()["kernels_launched"])
 acx.finalize()

@@ -148,6 +148,23 @@ def test_python_binding_two_processes(built, tmp_path):
     assert all("OK" in o for o in outs)
 
 
+def test_python_stats_mirror_matches_the_c_struct(built, tmp_path):
+    """mpi_acx_b200._native.AcxStats is a hand-written ctypes mirror of MPIX_Acx_stats (include/mpi-acx.h): same size, same
+    field names in the same order — MPIX_Get_stats writes through the pointer it is given."""
+    import ctypes, re
+    from mpi_acx_b200 import _native as N
+    hdr = (built / "include/mpi-acx.h").read_text()
+    body = hdr[hdr.index("typedef struct MPIX_Acx_stats"):hdr.index("} MPIX_Acx_stats;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n.strip() for decl in re.findall(r"unsigned long long ([^;]+);", body) for n in decl.split(",")]
+    assert names == [n for n, _ in N.AcxStats._fields_]
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <mpi.h>\n#include <mpi-acx.h>\nint main(void) { printf("%zu\\n", sizeof(MPIX_Acx_stats)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", str(built / "include"), "-I", "/usr/local/cuda/include", str(src), "-o", str(exe)], check=True)
+    assert int(subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout) == ctypes.sizeof(N.AcxStats)
+
+
 def test_api_surface_matches_reference_header(built):
     """Every entry point of the reference's include/mpi-acx.h exists in ours with the same arity."""
     import re
