@@ -1014,9 +1014,9 @@ extern "C" int MPIX_Finalize(void) {
         if (g_acx->verbose >= 1) {
             MPIX_Acx_stats s;
             MPIX_Get_stats(&s);
-            fprintf(stderr, "[acx %d] stats: sends %llu recvs %llu waits %llu | bytes tx %llu rx(cap) %llu | eager %llu rndv %llu bounce %llu | kernels %llu graph-nodes %llu | slots hw %llu heap hw %llu\n",
+            fprintf(stderr, "[acx %d] stats: sends %llu recvs %llu waits %llu | bytes tx %llu rx(cap) %llu | eager %llu rndv %llu bounce %llu | kernels %llu graph-nodes %llu | slots hw %llu heap hw %llu | copy-engine %llu overflow-sends %llu\n",
                     g_acx->rank, s.sends_enqueued, s.recvs_enqueued, s.waits_enqueued, s.bytes_sent, s.bytes_received, s.eager_msgs, s.rendezvous_msgs, s.bounce_copies,
-                    s.kernels_launched, s.graph_nodes_added, s.slots_high_water, s.heap_bytes_high_water);
+                    s.kernels_launched, s.graph_nodes_added, s.slots_high_water, s.heap_bytes_high_water, s.copy_engine_msgs, s.overflow_sends);
         }
         reg_finalize();
         g_pending_retire.clear();

@@ -105,7 +105,9 @@ def test_more_receives_outstanding_than_the_ring_is_deep(built, np_):
     host flavour): receives beyond the ring's depth are launched from the waits that make room, in posting order; waiting
     first on one that sits behind 32 un-waited receives is refused, not a deadlock — tests/c/many_outstanding.c
     (reference capacity: MPIACX_NFLAGS, include/mpi-acx-internal.h:141)."""
-    r = acxrun(built, np_, built / "build/tests/many_outstanding", env={"ACX_TEST_NO_SEND_BURST": "1"})
+    # parts 1-3 as they ran on hardware in this round: without the overflow path for sends (part 3 keeps 40 sends un-waited on one
+    # channel, whose last 8 would take it); that path has a test of its own at the end of this file
+    r = acxrun(built, np_, built / "build/tests/many_outstanding", env={"ACX_TEST_NO_SEND_BURST": "1", "ACX_SEND_OVERFLOW": "0"})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PASS" in r.stdout and "device transport" in r.stdout
 
