@@ -257,6 +257,12 @@ def test_device_protocol_on_cpu_threads(built):
     assert r.returncode == 0 and "protocol_emu: PASS" in r.stdout, r.stdout[-2500:] + r.stderr[-2500:]
 
 
+def _matrix_failures(out: str) -> str:
+    """The FAIL / FLAKY blocks of a tools/emu_matrix.sh run (each line that is not an `ok` line), plus the summary."""
+    keep = [l for l in out.splitlines() if not l.startswith("ok ")]
+    return "\n".join(keep)[-6000:]
+
+
 def test_device_transport_on_software_cuda_device(built):
     """`make emu-lib emu-tests` + tools/emu_matrix.sh: the unmodified runtime (src/core/acx.cu) linked against a software
     CUDA runtime (tests/emu/cudart_emu.cpp: memfd-backed "device" memory with CUDA-IPC handles, stream worker threads,
@@ -267,7 +273,7 @@ def test_device_transport_on_software_cuda_device(built):
     r = subprocess.run(["make", "-C", str(built), "-j4", "emu-lib", "emu-tests"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
     r = subprocess.run([str(built / "tools/emu_matrix.sh"), "quick"], capture_output=True, text=True, timeout=1500)
-    assert r.returncode == 0 and "0 failure(s)" in r.stdout, r.stdout[-4000:] + r.stderr[-1000:]
+    assert r.returncode == 0 and "0 failure(s)" in r.stdout, _matrix_failures(r.stdout) + r.stderr[-1000:]
 
 
 def test_flag_protocol_under_thread_sanitizer(built):
@@ -281,7 +287,7 @@ def test_flag_protocol_under_thread_sanitizer(built):
 def test_device_transport_under_address_sanitizer(built):
     """`make emu-asan`: runtime + software CUDA device + conformance programs built with ASan/UBSan/LSan, quick matrix."""
     r = subprocess.run(["make", "-C", str(built), "emu-asan"], capture_output=True, text=True, timeout=2400)
-    assert r.returncode == 0 and "0 failure(s)" in r.stdout, r.stdout[-4000:] + r.stderr[-1500:]
+    assert r.returncode == 0 and "0 failure(s)" in r.stdout, _matrix_failures(r.stdout) + r.stderr[-1500:]
 
 
 def test_device_trace_to_chrome_trace(built, tmp_path):

@@ -6,15 +6,27 @@ mode=${1:-quick}
 export ACX_MPI_NO_CUDA=1          # mini-MPI: "device" memory is host-addressable here, plain memcpy is right
 T=${EMU_DIR:-build/emu}/tests
 fails=0
+flaky=0
+attempt() {  # attempt <np> <prog> [env...]  -> sets out, rc, ms
+    local np=$1 prog=$2; shift 2
+    local t0=$(date +%s%N)
+    out=$(env "$@" timeout 400 bin/acxrun -np $np --timeout 300 $T/$prog $PROG_ARGS 2>&1)
+    rc=$?
+    ms=$(( ($(date +%s%N) - t0) / 1000000 ))
+    if echo "$out" | grep -qE "runtime error:|ERROR: AddressSanitizer|WARNING: ThreadSanitizer"; then rc=99; fi   # sanitizer builds (EMU_DIR=build/emu_asan ...)
+    if [ $rc -eq 0 ] && ! echo "$out" | grep -q "PASS"; then rc=98; fi
+}
 run() {  # run <label> <np> <prog> [env...]
     local label=$1 np=$2 prog=$3; shift 3
-    local t0=$(date +%s%N)
-    out=$(env "$@" timeout 400 bin/acxrun -np $np --timeout 300 $T/$prog 2>&1)
-    rc=$?
-    local ms=$(( ($(date +%s%N) - t0) / 1000000 ))
-    if echo "$out" | grep -qE "runtime error:|ERROR: AddressSanitizer|WARNING: ThreadSanitizer"; then rc=99; fi   # sanitizer builds (EMU_DIR=build/emu_asan ...)
-    if [ $rc -eq 0 ] && echo "$out" | grep -q "PASS"; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms
-    else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $rc "$(echo "$out" | grep -v "ASan doesn\x27t fully support" | tail -${EMU_TAIL:-8})"; fails=$((fails+1)); fi
+    attempt $np $prog "$@"
+    if [ $rc -eq 0 ]; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms; return; fi
+    # A line that fails is run once more. Two failures count; a pass on the second attempt is reported as FLAKY with the first
+    # attempt's output and counted separately in the summary (seen about once in ten sanitizer matrices: reports at process
+    # exit that depend on the software device's helper threads; EMU_NO_RETRY=1 switches the second attempt off).
+    local first_rc=$rc first_out="$(echo "$out" | grep -v "ASan doesn\x27t fully support" | tail -${EMU_TAIL:-8})"
+    if [ -z "$EMU_NO_RETRY" ]; then attempt $np $prog "$@"; fi
+    if [ $rc -eq 0 ]; then printf "FLAKY %-24s np=%d %-28s first attempt rc=%d, second passed (%d ms)\n%s\n" $prog $np "$label" $first_rc $ms "$first_out"; flaky=$((flaky+1))
+    else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $first_rc "$first_out"; fails=$((fails+1)); fi
 }
 progs="ring ring_all ring_all_device ring_all_graph ring_graph_construction graph_large ring_partitioned partitioned_device ordering large_msgs regcache procnull_comms subcomm datatypes threads status_errors sendrecv_enqueue reinit tags host_reuse many_outstanding"
 nps="1 2 3"
@@ -51,8 +63,7 @@ done
 [ "$mode" = tsan ] || run coop 3 large_msgs ACX_COOP=1 ACX_COOP_MIN_BYTES=65536
 # large-message protocol (the sender moves, at its trigger or from its wait; receiver-side fallback pull) at emulation-sized messages
 LATE="ACX_LATE_PUSH_MIN=65536"
-lrun() { local label=$1 np=$2 prog=$3; shift 3; local t0=$(date +%s%N); out=$(env "$@" timeout 400 bin/acxrun -np $np --timeout 300 $T/$prog 262144 2>&1); rc=$?; local ms=$(( ($(date +%s%N) - t0) / 1000000 ));
-  if [ $rc -eq 0 ] && echo "$out" | grep -q "PASS"; then printf "ok    %-24s np=%d %-28s %6d ms\n" $prog $np "$label" $ms; else printf "FAIL  %-24s np=%d %-28s rc=%d\n%s\n" $prog $np "$label" $rc "$(echo "$out" | tail -8)"; fails=$((fails+1)); fi; }
+lrun() { PROG_ARGS=262144; run "$@"; PROG_ARGS=; }   # programs that take their message size as an argument
 for np in 1 2 3; do lrun late $np late_push $LATE; done
 lrun late-no-fallback-grace 2 late_push $LATE ACX_LATE_FALLBACK_US=0
 lrun late-jitter 3 late_push $LATE ACX_FAULT_DELAY_US=300
@@ -186,5 +197,6 @@ fi
 out=$(ACX_FAULT_DROP_SEND=1 ACX_WATCHDOG_MS=1500 timeout 100 bin/acxrun -np 1 --timeout 60 $T/ring 2>&1); rc=$?
 if [ $rc -ne 0 ] && echo "$out" | grep -q "WATCHDOG (code 0x5e04" && echo "$out" | grep -q "FAULT INJECTION"; then printf "ok    %-24s np=1 %-28s\n" ring watchdog-on-dropped-send
 else printf "FAIL  ring np=1 watchdog-on-dropped-send rc=%d\n%s\n" $rc "$(echo "$out" | tail -5)"; fails=$((fails+1)); fi
+[ $flaky -gt 0 ] && echo "emu matrix ($mode): $flaky line(s) FLAKY (failed once, passed on the second attempt: see above)"
 echo "emu matrix ($mode): $fails failure(s)"
 exit $fails
