@@ -2973,7 +2973,7 @@ extern "C" int MPIX_Waitall(int count, MPIX_Request *reqs, MPI_Status *statuses)
         if (!wait_ops.ops.empty()) { int rc = wait_ops.flush(host_stream()); if (rc) return rc; }
         if (any) ACX_CUDA_WD(cudaStreamSynchronize(host_stream()));
     }
-    // Overflow sends last, as in the stream waits (SendOverflow): they complete only once the peer has consumed earlier
+    // Overflow sends last, as in the stream waits (send_overflow_begin): they complete only once the peer has consumed earlier
     // messages of their channel, and the peer's host may be sitting in the mirror image of this very call.
     for (int pass = 0; pass < 2; pass++) {
         for (int i = 0; i < count; i++) {

@@ -306,8 +306,8 @@ struct AcxState {
     std::vector<std::vector<std::vector<AcxRequest *>>> recv_deferred;   // [src][chan]: receives whose trigger has not been launched yet, in posting order
     struct ChanCount { uint64_t next = 0; cudaStream_t stream = nullptr; bool dev = false; };
     std::vector<std::vector<ChanCount>> send_count, recv_count;   // [peer][chan]
-    // Sends in flight beyond a channel's ring depth (ACX_SEND_OVERFLOW, acx.cu: SendOverflow): stream-mode sends enqueued and not
-    // yet waited on, per channel; the overflow stream that carries the sends which could otherwise hold up the caller's stream.
+    // Sends in flight beyond a channel's ring depth (ACX_SEND_OVERFLOW, acx.cu: send_overflow_begin): stream-mode sends enqueued and not
+    // yet waited on, per channel, and the newest overflow send whose trigger may still be waiting on its pool stream.
     struct SendFlow { int unwaited = 0; AcxRequest *last = nullptr; };   // last: the newest overflow send of the channel while its trigger may still be pending (acx_host_status::trig_serial tells); cleared when that request is released
     std::vector<std::vector<SendFlow>> send_flow;   // [peer][chan]
     // config

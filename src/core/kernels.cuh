@@ -170,7 +170,7 @@ struct SendParams {
     uint64_t serial;
     uint32_t tag, depth, eager_max, peer;
     uint32_t ctx, late;     // ctx: communicator context, travels in the slot header (exact (source, tag, comm) matching: a receive checks it); late: announce RNDV_LATE (sender moves, now or at its wait)
-    // Overflow sends (acx.cu: SendOverflow) run on a pool stream of their own, several of one channel at a time: the ticket is the
+    // Overflow sends (acx.cu: send_overflow_begin) run on a pool stream of their own, several of one channel at a time: the ticket is the
     // one the HOST counted (hticket1 - 1; 0 = draw from the counter), taken when the channel's counter reaches it, so tickets
     // keep the enqueue order without any stream order between the triggers; the trigger reports to the host (hdone) and to the
     // wait kernel (op->armed, for eager messages too). Nothing follows it on its stream: a rendezvous message gets the

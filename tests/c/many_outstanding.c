@@ -73,7 +73,7 @@ static void send_burst(int host_wait, int two_calls, cudaStream_t st) {
     for (int k = 0; k < KB; k++) T_OK(MPIX_Isend_enqueue(sbuf[k], len_of(k), MPI_INT, T_RIGHT, 8, MPI_COMM_WORLD, &rq[k], MPIX_QUEUE_CUDA_STREAM, &st));
     for (int k = 0; k < KB; k++) T_OK(MPIX_Irecv_enqueue(rbuf[k], 5000, MPI_INT, T_LEFT, 8, MPI_COMM_WORLD, &rq[KB + k], MPIX_QUEUE_CUDA_STREAM, &st));
     const int depth = getenv("ACX_DEPTH") ? atoi(getenv("ACX_DEPTH")) : 32;
-    if (t_gpu) T_CHECK(overflow_count() - before == (unsigned long long)(KB - depth), "%llu sends took the overflow stream, expected %d (%d un-waited sends on one channel, ring depth %d)", overflow_count() - before, KB - depth, KB, depth);
+    if (t_gpu) T_CHECK(overflow_count() - before == (unsigned long long)(KB - depth), "%llu sends took the overflow path, expected %d (%d un-waited sends on one channel, ring depth %d)", overflow_count() - before, KB - depth, KB, depth);
     if (two_calls) {   /* receives, then sends: the order a program has to use when it splits the wait */
         if (host_wait) { T_OK(MPIX_Waitall(KB, rq + KB, MPI_STATUSES_IGNORE)); T_OK(MPIX_Waitall(KB, rq, MPI_STATUSES_IGNORE)); }
         else { T_OK(MPIX_Waitall_enqueue(KB, rq + KB, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st)); T_OK(MPIX_Waitall_enqueue(KB, rq, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st)); }
@@ -89,7 +89,7 @@ static void send_burst(int host_wait, int two_calls, cudaStream_t st) {
     T_OK(MPIX_Sendrecv_enqueue(&a, 1, MPI_INT, T_RIGHT, 8, &b, 1, MPI_INT, T_LEFT, 8, MPI_COMM_WORLD, MPI_STATUS_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
     if (t_gpu) T_CUDA(cudaStreamSynchronize(st));
     T_CHECK(b == 4242 + T_LEFT, "exchange behind the burst delivered %d, expected %d", b, 4242 + T_LEFT);
-    if (t_gpu && !host_wait) T_CHECK(overflow_count() == mid, "a single send on a drained channel took the overflow stream");
+    if (t_gpu && !host_wait) T_CHECK(overflow_count() == mid, "a single send on a drained channel took the overflow path");
 }
 
 int main(int argc, char **argv) {
