@@ -92,6 +92,28 @@ static void send_burst(int host_wait, int two_calls, cudaStream_t st) {
     if (t_gpu && !host_wait) T_CHECK(overflow_count() == mid, "a single send on a drained channel took the overflow path");
 }
 
+/* The same with rendezvous messages above 1 MiB: an overflow send of that size is ONE two-CTA kernel (trigger + mover) on its
+ * pool stream; CTA 1 waits for CTA 0's match while that waits for slot credit. 36 messages of 1.25 MiB, one wait call. */
+static void big_burst(cudaStream_t st) {
+    enum { KG = 36, N = 327680 };
+    static int *sbuf[KG], *rbuf[KG];
+    MPIX_Request rq[2 * KG];
+    for (int k = 0; k < KG; k++) {
+        if (!sbuf[k]) { sbuf[k] = (int *)malloc(sizeof(int) * N); rbuf[k] = (int *)malloc(sizeof(int) * N); }
+        for (int i = 0; i < N; i++) { sbuf[k][i] = t_rank * 7919 + k * 131 + i; rbuf[k][i] = -1; }
+    }
+    const unsigned long long before = overflow_count();
+    for (int k = 0; k < KG; k++) T_OK(MPIX_Isend_enqueue(sbuf[k], N, MPI_INT, T_RIGHT, 9, MPI_COMM_WORLD, &rq[k], MPIX_QUEUE_CUDA_STREAM, &st));
+    for (int k = 0; k < KG; k++) T_OK(MPIX_Irecv_enqueue(rbuf[k], N, MPI_INT, T_LEFT, 9, MPI_COMM_WORLD, &rq[KG + k], MPIX_QUEUE_CUDA_STREAM, &st));
+    const int depth = getenv("ACX_DEPTH") ? atoi(getenv("ACX_DEPTH")) : 32;
+    if (t_gpu && depth < KG) T_CHECK(overflow_count() - before == (unsigned long long)(KG - depth), "%llu large sends took the overflow path, expected %d", overflow_count() - before, KG - depth);
+    T_OK(MPIX_Waitall_enqueue(2 * KG, rq, MPI_STATUSES_IGNORE, MPIX_QUEUE_CUDA_STREAM, &st));
+    if (t_gpu) T_CUDA(cudaStreamSynchronize(st));
+    int bad = 0;
+    for (int k = 0; k < KG; k++) for (int i = 0; i < N; i += 997) if (rbuf[k][i] != T_LEFT * 7919 + k * 131 + i) { bad++; break; }
+    T_CHECK(bad == 0, "%d of %d large messages wrong with %d sends in flight on one channel", bad, KG, KG);
+}
+
 int main(int argc, char **argv) {
     t_init(&argc, &argv, 0);
     cudaStream_t st = 0;
@@ -109,6 +131,7 @@ int main(int argc, char **argv) {
         send_burst(1, 0, st);
         send_burst(0, 1, st);
         send_burst(1, 1, st);
+        big_burst(st);
     }
     if (t_gpu) T_CUDA(cudaStreamDestroy(st));
     return t_finish("many_outstanding");
